@@ -1,0 +1,25 @@
+"""boxtree_b200 -- B200-native (sm_100a) tree build + FMM traversal generation.
+
+Drop-in for the ``TreeBuilder.__call__`` -> ``Tree`` ->
+``FMMTraversalBuilder.__call__`` -> ``FMMTraversalInfo`` path of
+`inducer/boxtree <https://github.com/inducer/boxtree>`__ (same names, argument
+meaning and error behaviour as ``boxtree/__init__.py:26-52``), implemented as
+hand-written CUDA kernels behind a C ABI (``include/boxtree_b200.h``).
+
+Particle orderings and CSR storage follow the reference's conventions
+(``boxtree/__init__.py:114-166``): ``user_source_ids`` maps tree order to user
+order for sources, ``sorted_target_ids`` maps user order to tree order for
+targets; ``*_starts``/``*_lists`` pairs are CSR with ``starts`` of length
+``nrows + 1``.
+"""
+from .array_context import TorchArrayContext, make_obj_array
+from .tree import Tree, TreeOfBoxes, box_flags_enum
+from .tree_build import MaxLevelsExceeded, TreeBuilder
+from .traversal import BuiltList, FMMTraversalBuilder, FMMTraversalInfo
+
+__all__ = [
+    "TorchArrayContext", "make_obj_array",
+    "Tree", "TreeOfBoxes", "box_flags_enum",
+    "TreeBuilder", "MaxLevelsExceeded",
+    "FMMTraversalBuilder", "FMMTraversalInfo", "BuiltList",
+]

@@ -1,0 +1,161 @@
+"""ctypes binding of ``libboxtree_b200.so`` (see ``include/boxtree_b200.h``).
+
+The product path has no CPU fallback: importing this module without the built
+library, or calling into it without a CUDA device, raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libboxtree_b200.so")
+
+BT_F32, BT_F64 = 0, 1
+
+# control block slots (include/boxtree_b200.h)
+CTL_NBOXES = 0
+CTL_NSPLIT = 1
+CTL_OVERSIZE = 2
+CTL_OVERFLOW = 3
+CTL_NSPLIT_REGULAR = 4
+CTL_COMMITTED = 5
+CTL_NBOXES_FINAL = 6
+CTL_NBIG = 7
+CTL_NHUGE = 8
+CTL_LR_FOUND = 16
+CTL_SIZE = 64
+
+vp = C.c_void_p
+
+
+class bt_particles(C.Structure):
+    _fields_ = [("sources", vp * 3), ("targets", vp * 3), ("source_radii", vp),
+                ("target_radii", vp), ("nsources", C.c_int64), ("ntargets", C.c_int64)]
+
+
+class bt_pool(C.Structure):
+    _fields_ = [("start", vp), ("count", vp), ("level", vp), ("parent", vp), ("child0", vp),
+                ("has_children", vp), ("force_split", vp), ("nonchild", vp), ("center", vp * 3),
+                ("capacity", C.c_int32)]
+
+
+class bt_box_out(C.Structure):
+    _fields_ = [("box_start", vp), ("box_count", vp), ("box_nonchild", vp), ("box_levels", vp),
+                ("box_parent_ids", vp), ("box_child_ids", vp), ("box_centers", vp),
+                ("has_children", vp), ("real_children", vp)]
+
+
+class bt_tree_view(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("nboxes", C.c_int32), ("aligned_nboxes", C.c_int32),
+                ("nlevels", C.c_int32), ("root_extent", C.c_double), ("box_centers", vp),
+                ("box_levels", vp), ("box_child_ids", vp), ("box_flags", vp),
+                ("box_parent_ids", vp), ("well_sep_is_n_away", C.c_int32)]
+
+
+class bt_list_args(C.Structure):
+    _fields_ = [("row_boxes", vp), ("coll_starts", vp), ("coll_lists", vp),
+                ("stick_out_factor", C.c_double), ("with_extent", C.c_int32)]
+
+
+class bt_list3_args(C.Structure):
+    _fields_ = [("target_boxes", vp), ("coll_starts", vp), ("coll_lists", vp),
+                ("stick_out_factor", C.c_double), ("targets_have_extent", C.c_int32),
+                ("sources_have_extent", C.c_int32), ("crit", C.c_int32),
+                ("box_target_bounding_box_min", vp), ("box_target_bounding_box_max", vp),
+                ("box_source_counts_cumul", vp), ("min_nsources_cumul", C.c_int32)]
+
+
+# every exported symbol of include/boxtree_b200.h with its argument types
+_i, _i64, _d = C.c_int, C.c_int64, C.c_double
+_P = C.POINTER
+SIGNATURES = {
+    "bt_max_key_level": [_i],
+    "bt_bounding_box": [_i, _i, _P(bt_particles), vp, vp],
+    "bt_make_keys": [_i, _i, _P(bt_particles), _P(_d), _P(_d), _i, _d, vp, vp],
+    "bt_sort_particles": [_i64, _i, _i, vp, vp, vp, vp, _P(_i), vp],
+    "bt_weight_prefix": [_i64, vp, vp, vp, vp],
+    "bt_pool_init": [_i, _i, _P(bt_pool), _i64, _i, vp, _P(_d), vp, vp],
+    "bt_level_step": [_i, _i, _P(bt_pool), vp, vp, vp, vp, vp, _i, _i, _i, _i, _i, _i, _i, _i,
+                      _d, _i, vp],
+    "bt_level_restrict": [_i, _i, _P(bt_pool), vp, _i, _i, _d, vp],
+    "bt_finalize_numbering": [_i, _i, _P(bt_pool), _i, _i, _i, vp, vp, vp, vp, vp],
+    "bt_gather_boxes": [_i, _i, _P(bt_pool), _i, vp, vp, _i, _i, _P(bt_box_out), vp],
+    "bt_leaf_fixup": [_i, vp, vp, vp, vp, vp, vp, _i, vp, vp],
+    "bt_sort_u32_segment": [_i64, vp, vp],
+    "bt_split_sources_targets": [_i64, _i64, vp, vp, vp, vp, vp, vp],
+    "bt_reverse_index": [_i64, vp, vp, vp],
+    "bt_permute": [_i, _i, _P(bt_particles), vp, _i64, _P(vp), vp, vp],
+    "bt_box_info": [_i, _i, _i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    "bt_box_extents": [_i, _i, _i, _i, _i, vp, vp, vp, vp, _P(vp), vp, vp, vp, vp],
+    "bt_trav_box_list": [_i, _i, vp, vp, vp, vp, vp],
+    "bt_trav_level_starts": [_i, vp, vp, _i, vp, vp],
+    "bt_trav_build_list": [_i, _i, _i, _P(bt_tree_view), _P(bt_list_args), _i, vp, vp, vp, vp,
+                           vp, vp],
+    "bt_trav_list3": [_i, _i, _P(bt_tree_view), _P(bt_list3_args), _i, vp, vp, vp, vp, vp],
+    "bt_trav_list3_compress": [_i, _i, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    "bt_trav_merge_lists": [_i, _i, vp, _i, _P(vp), _P(vp), vp, vp, vp, vp],
+    "bt_gather_i32": [_i64, vp, vp, vp, vp],
+}
+
+_lib = None
+
+
+class BoxtreeB200Error(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library; fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BoxtreeB200Error(
+                f"{LIB_PATH} is missing: build it with `python -m boxtree_b200.build` "
+                "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+        _lib = lib
+    return _lib
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        raise BoxtreeB200Error(f"{what} failed with status {code}"
+                               + (" (CUDA error)" if code < 10000 else ""))
+
+
+def dtype_code(np_dtype) -> int:
+    np_dtype = np.dtype(np_dtype)
+    if np_dtype == np.float32:
+        return BT_F32
+    if np_dtype == np.float64:
+        return BT_F64
+    raise TypeError(f"unsupported coordinate dtype: {np_dtype}")
+
+
+def dptr(t):
+    """Device pointer of a torch tensor (or NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "device-resident contiguous tensor required"
+    return t.data_ptr()
+
+
+def darray(values):
+    arr = (C.c_double * 3)()
+    for k, v in enumerate(values):
+        arr[k] = float(v)
+    return arr
+
+
+def ptr_array(tensors):
+    arr = (vp * max(len(tensors), 1))()
+    for k, t in enumerate(tensors):
+        arr[k] = dptr(t)
+    return arr

@@ -1,0 +1,62 @@
+// Shared helpers for the boxtree_b200 CUDA kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define BT_OK 0
+#define BT_ERR_BAD_ARG 10001
+#define BT_ERR_UNSUPPORTED 10002
+
+#define BT_CHECK(call)                                   \
+    do {                                                 \
+        cudaError_t bt_e_ = (call);                      \
+        if (bt_e_ != cudaSuccess) return (int)bt_e_;     \
+    } while (0)
+#define BT_LAUNCH_CHECK() BT_CHECK(cudaGetLastError())
+#define BT_TRY(expr)                                     \
+    do {                                                 \
+        int bt_r_ = (expr);                              \
+        if (bt_r_ != 0) return bt_r_;                    \
+    } while (0)
+
+namespace bt {
+
+constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
+
+// Grid for a grid-stride loop over n items: enough blocks to cover n, capped at
+// a multiple of the SM count so the tail wave stays balanced.
+static inline int grid_for(int64_t n, int block, int blocks_per_sm = 8)
+{
+    int64_t need = (n + block - 1) / block;
+    int64_t cap = (int64_t)kNumSMs * blocks_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+template <typename T> struct CoordTraits;
+template <> struct CoordTraits<float> {
+    __host__ __device__ static float maxval() { return 3.402823466e+38f; }
+    __host__ __device__ static float eps() { return 1.1920928955078125e-07f; }
+};
+template <> struct CoordTraits<double> {
+    __host__ __device__ static double maxval() { return 1.7976931348623157e+308; }
+    __host__ __device__ static double eps() { return 2.220446049250313e-16; }
+};
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+
+// streaming (read-once) loads / stores that bypass L1 allocation
+__device__ __forceinline__ unsigned long long ld_stream_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ unsigned ld_stream_u32(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+}  // namespace bt

@@ -1,0 +1,455 @@
+"""``FMMTraversalBuilder`` / ``FMMTraversalInfo``: drop-in for ``boxtree.traversal``.
+
+Same constructor, call signature, error behaviour and output record as the
+reference (``boxtree/traversal.py:1353-1705`` FMMTraversalInfo, ``:1721-2345``
+builder); lists are built by sm_100a kernels (``csrc/traversal.cu``) that
+follow the reference's count -> scan -> write protocol with rows in the append
+order of the reference's tree walks, so every CSR array is identical.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, replace
+from typing import Any
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import bt_list3_args, bt_list_args, bt_tree_view, check, dptr
+from .array_context import TorchArrayContext, make_obj_array
+from .tree import Tree, TreeOfBoxes
+
+CRIT_CODE = {"static_linf": 0, "precise_linf": 1, "static_l2": 2}
+_INT32_MAX = 2**31 - 1
+
+
+@dataclass(frozen=True)
+class BuiltList:
+    """Mirror of ``pyopencl.algorithm.BuiltList`` as used by the reference
+    (``boxtree/array_context.py:222-238``, ``traversal.py:1523-1538``)."""
+    count: int | None
+    starts: Any
+    lists: Any
+    num_nonempty_lists: int | None = None
+    nonempty_indices: Any = None
+    compressed_indices: Any = None
+
+
+@dataclass(frozen=True)
+class FMMTraversalInfo:
+    """Interaction lists for an FMM (``boxtree/traversal.py:1353-1705``)."""
+    tree: Any
+    well_sep_is_n_away: int
+
+    source_boxes: Any
+    target_boxes: Any
+    level_start_source_box_nrs: Any
+    level_start_target_box_nrs: Any
+    source_parent_boxes: Any
+    level_start_source_parent_box_nrs: Any
+    target_or_target_parent_boxes: Any
+    level_start_target_or_target_parent_box_nrs: Any
+
+    same_level_non_well_sep_boxes_starts: Any
+    same_level_non_well_sep_boxes_lists: Any
+
+    neighbor_source_boxes_starts: Any
+    neighbor_source_boxes_lists: Any
+
+    from_sep_siblings_starts: Any
+    from_sep_siblings_lists: Any
+
+    from_sep_smaller_by_level: Any
+    target_boxes_sep_smaller_by_source_level: Any
+    from_sep_close_smaller_starts: Any
+    from_sep_close_smaller_lists: Any
+
+    from_sep_bigger_starts: Any
+    from_sep_bigger_lists: Any
+    from_sep_close_bigger_starts: Any
+    from_sep_close_bigger_lists: Any
+
+    @property
+    def nboxes(self):
+        return self.tree.nboxes
+
+    @property
+    def nlevels(self):
+        return self.tree.nlevels
+
+    @property
+    def ntarget_boxes(self):
+        return int(self.target_boxes.shape[0])
+
+    @property
+    def ntarget_or_target_parent_boxes(self):
+        return int(self.target_or_target_parent_boxes.shape[0])
+
+    def merge_close_lists(self, actx: TorchArrayContext, debug: bool = False):
+        """``traversal.py:1650-1693``: fold both "close" lists into list 1."""
+        starts, lists = _merge_lists(
+            actx, _cabi.load(), None, self.ntarget_boxes,
+            [self.neighbor_source_boxes_starts, self.from_sep_close_smaller_starts,
+             self.from_sep_close_bigger_starts],
+            [self.neighbor_source_boxes_lists, self.from_sep_close_smaller_lists,
+             self.from_sep_close_bigger_lists])
+        return replace(self, neighbor_source_boxes_starts=starts,
+                       neighbor_source_boxes_lists=lists,
+                       from_sep_close_smaller_starts=None, from_sep_close_smaller_lists=None,
+                       from_sep_close_bigger_starts=None, from_sep_close_bigger_lists=None)
+
+    def get_box_list(self, what, index):
+        starts = getattr(self, f"{what}_starts")
+        lists = getattr(self, f"{what}_lists")
+        start, stop = (int(x) for x in starts[index:index + 2])
+        return lists[start:stop]
+
+
+def _read_i64(actx, dev: torch.Tensor) -> np.ndarray:
+    host = torch.empty(dev.shape, dtype=dev.dtype, pin_memory=True)
+    host.copy_(dev, non_blocking=True)
+    actx.stream.synchronize()
+    return host.numpy().copy()
+
+
+def _check_int32(total: int, what: str) -> None:
+    if total > _INT32_MAX:
+        raise OverflowError(
+            f"{what} has {total} entries, which exceeds the int32 CSR index range "
+            "(the reference's ListOfListsBuilder uses int32 starts as well)")
+
+
+def _merge_lists(actx, lib, output_to_input_box, noutput, starts, lists):
+    """_ListMerger, ``traversal.py:1298-1344``."""
+    sh = actx.stream_handle
+    with torch.cuda.stream(actx.stream):
+        nl = len(starts)
+        sp = _cabi.ptr_array(starts)
+        lp = _cabi.ptr_array(lists)
+        new_starts = actx.empty(noutput + 1, np.int32)
+        totals = actx.zeros(2, np.int64)
+        check(lib.bt_trav_merge_lists(0, noutput, dptr(output_to_input_box), nl, sp, lp,
+                                      dptr(new_starts), None, dptr(totals), sh),
+              "bt_trav_merge_lists")
+        total = int(_read_i64(actx, totals)[0])
+        _check_int32(total, "merged list")
+        new_lists = actx.empty(total, np.int32)
+        check(lib.bt_trav_merge_lists(1, noutput, dptr(output_to_input_box), nl, sp, lp,
+                                      dptr(new_starts), dptr(new_lists), dptr(totals), sh),
+              "bt_trav_merge_lists")
+    return new_starts, new_lists
+
+
+class FMMTraversalBuilder:
+    """Mirrors ``boxtree.traversal.FMMTraversalBuilder`` (``traversal.py:1721``)."""
+
+    def __init__(self, array_context: TorchArrayContext, *, well_sep_is_n_away: int = 1,
+                 from_sep_smaller_crit: str | None = None) -> None:
+        assert isinstance(array_context, TorchArrayContext)
+        self._setup_actx = array_context
+        self.well_sep_is_n_away = well_sep_is_n_away
+        self.from_sep_smaller_crit = from_sep_smaller_crit
+        self._lib = _cabi.load()
+
+    def _resolve_crit(self, extent_norm, sources_have_extent, targets_have_extent) -> str:
+        # traversal.py:1776-1805
+        crit = self.from_sep_smaller_crit
+        if crit is None:
+            crit = "precise_linf"
+        if extent_norm == "linf":
+            pass
+        elif extent_norm == "l2":
+            if crit == "static_linf":
+                raise ValueError("the static l^inf from-sep-smaller criterion "
+                                 "cannot be used with the l^2 extent norm")
+        elif extent_norm is None:
+            assert not (sources_have_extent or targets_have_extent)
+        else:
+            raise ValueError(f"unexpected value of 'extent_norm': {extent_norm}")
+        if crit not in CRIT_CODE:
+            raise ValueError(f"unexpected value of 'from_sep_smaller_crit': {crit}")
+        return crit
+
+    def __call__(self, actx: TorchArrayContext, tree: Tree | TreeOfBoxes, wait_for=None,
+                 debug: bool = False, _from_sep_smaller_min_nsources_cumul: int | None = None,
+                 source_boxes_mask=None, source_parent_boxes_mask=None):
+        """See ``boxtree/traversal.py:1969-1990``.
+
+        :returns: ``(trav, event)``; *event* is a :class:`torch.cuda.Event`.
+        """
+        assert isinstance(actx, TorchArrayContext)
+        lib = self._lib
+
+        min_nsrc = _from_sep_smaller_min_nsources_cumul
+        if min_nsrc is None:
+            min_nsrc = 0
+
+        if not tree._is_pruned:
+            raise ValueError("tree must be pruned for traversal generation")
+        if tree.sources_have_extent:
+            raise NotImplementedError(
+                "trees with source extent are not supported for traversal generation")
+
+        crit = self._resolve_crit(tree.extent_norm, tree.sources_have_extent,
+                                  tree.targets_have_extent)
+
+        # a TreeOfBoxes (host numpy) is moved to the device first (traversal.py:1971, 2010)
+        if isinstance(tree.box_flags, np.ndarray):
+            dev_tree = actx.from_numpy(tree)
+        else:
+            dev_tree = tree
+
+        nlevels = int(tree.nlevels)
+        nboxes = int(tree.nboxes)
+        dimensions = int(tree.dimensions)
+        sources_are_targets = getattr(tree, "sources_are_targets", True)
+        coord_dtype = np.dtype(tree.coord_dtype)
+        dcode = _cabi.dtype_code(coord_dtype)
+        stream = actx.stream
+        sh = actx.stream_handle
+        with_extent = bool(tree.sources_have_extent or tree.targets_have_extent)
+
+        def dev(a, dt=None):
+            if isinstance(a, np.ndarray):
+                a = actx.from_numpy(np.ascontiguousarray(a if dt is None else a.astype(dt)))
+            return a.contiguous()
+
+        with torch.cuda.stream(stream), torch.cuda.device(actx.device):
+            box_flags = dev(dev_tree.box_flags)
+            box_levels = dev(dev_tree.box_levels)
+            box_parent_ids = dev(dev_tree.box_parent_ids)
+            box_centers = dev(dev_tree.box_centers)
+            box_child_ids = dev(dev_tree.box_child_ids)
+            if dev_tree.level_start_box_nrs is None:
+                raise ValueError("tree.level_start_box_nrs is required")
+            level_start_box_nrs = dev(dev_tree.level_start_box_nrs, np.int32)
+            if level_start_box_nrs.dtype != torch.int32:
+                level_start_box_nrs = level_start_box_nrs.to(torch.int32)
+
+            tv = bt_tree_view()
+            tv.dim = dimensions
+            tv.nboxes = nboxes
+            tv.aligned_nboxes = int(box_child_ids.shape[-1])
+            tv.nlevels = nlevels
+            tv.root_extent = float(tree.root_extent)
+            tv.box_centers = dptr(box_centers)
+            tv.box_levels = dptr(box_levels)
+            tv.box_child_ids = dptr(box_child_ids)
+            tv.box_flags = dptr(box_flags)
+            tv.box_parent_ids = dptr(box_parent_ids)
+            tv.well_sep_is_n_away = int(self.well_sep_is_n_away)
+            if int(box_centers.shape[-1]) != tv.aligned_nboxes:
+                raise ValueError("box_centers and box_child_ids must share their padded length")
+
+            # {{{ b1/b2: box lists and their level starts (traversal.py:2054-2124)
+
+            sbm = None if source_boxes_mask is None else dev(source_boxes_mask, np.int8)
+            spbm = None if source_parent_boxes_mask is None else \
+                dev(source_parent_boxes_mask, np.int8)
+            nwhich = 3 if sources_are_targets else 4
+            raw = [actx.empty(max(nboxes, 1), np.int32) for _ in range(nwhich)]
+            counts_dev = actx.zeros(4, np.int32)
+            masks = [spbm, sbm, None, None]
+            for which in range(nwhich):
+                check(lib.bt_trav_box_list(which, nboxes, dptr(box_flags), dptr(masks[which]),
+                                           dptr(raw[which]), dptr(counts_dev[which:which + 1]),
+                                           sh), "bt_trav_box_list")
+            counts = counts_dev.cpu().numpy()
+            source_parent_boxes = raw[0][:int(counts[0])]
+            source_boxes = raw[1][:int(counts[1])]
+            target_or_target_parent_boxes = raw[2][:int(counts[2])]
+            target_boxes = source_boxes if sources_are_targets else raw[3][:int(counts[3])]
+            ntb = int(target_boxes.shape[0])
+            ntp = int(target_or_target_parent_boxes.shape[0])
+
+            def level_starts(box_list):
+                out = actx.empty(nlevels + 1, np.int32)
+                check(lib.bt_trav_level_starts(nlevels, dptr(level_start_box_nrs),
+                                               dptr(box_list), int(box_list.shape[0]),
+                                               dptr(out), sh), "bt_trav_level_starts")
+                return out
+
+            lss = level_starts(source_boxes)
+            lssp = level_starts(source_parent_boxes)
+            lst = lss if sources_are_targets else level_starts(target_boxes)
+            lstp = level_starts(target_or_target_parent_boxes)
+
+            # }}}
+
+            totals = actx.zeros(8, np.int64)
+
+            def list_args(row_boxes, coll=None):
+                a = bt_list_args()
+                a.row_boxes = dptr(row_boxes)
+                a.coll_starts = dptr(coll[0]) if coll else None
+                a.coll_lists = dptr(coll[1]) if coll else None
+                a.stick_out_factor = float(tree.stick_out_factor)
+                a.with_extent = int(with_extent)
+                return a
+
+            # {{{ b3: same-level non-well-separated boxes (traversal.py:2135-2141)
+
+            coll_starts = actx.empty(nboxes + 1, np.int32)
+            a_coll = list_args(None)
+            check(lib.bt_trav_build_list(dcode, 0, 0, C.byref(tv), C.byref(a_coll), nboxes,
+                                         dptr(coll_starts), None, None, None, dptr(totals), sh),
+                  "colleagues count")
+            total = int(_read_i64(actx, totals)[0])
+            _check_int32(total, "same_level_non_well_sep_boxes")
+            coll_lists = actx.empty(total, np.int32)
+            check(lib.bt_trav_build_list(dcode, 0, 1, C.byref(tv), C.byref(a_coll), nboxes,
+                                         dptr(coll_starts), dptr(coll_lists), None, None,
+                                         dptr(totals), sh), "colleagues fill")
+            coll = (coll_starts, coll_lists)
+
+            # }}}
+
+            # {{{ count phases of lists 1-4, then ONE readback
+
+            l1_starts = actx.empty(ntb + 1, np.int32)
+            a1 = list_args(target_boxes)
+            check(lib.bt_trav_build_list(dcode, 1, 0, C.byref(tv), C.byref(a1), ntb,
+                                         dptr(l1_starts), None, None, None, dptr(totals[0:]), sh),
+                  "list 1 count")
+
+            l2_starts = actx.empty(ntp + 1, np.int32)
+            a2 = list_args(target_or_target_parent_boxes, coll)
+            check(lib.bt_trav_build_list(dcode, 2, 0, C.byref(tv), C.byref(a2), ntp,
+                                         dptr(l2_starts), None, None, None, dptr(totals[1:]), sh),
+                  "list 2 count")
+
+            l4_starts = actx.empty(ntp + 1, np.int32)
+            l4c_starts_raw = actx.empty(ntp + 1, np.int32) if with_extent else None
+            a4 = list_args(target_or_target_parent_boxes, coll)
+            check(lib.bt_trav_build_list(dcode, 4, 0, C.byref(tv), C.byref(a4), ntp,
+                                         dptr(l4_starts), None, dptr(l4c_starts_raw), None,
+                                         dptr(totals[2:]), sh), "list 4 count")
+
+            a3 = bt_list3_args()
+            a3.target_boxes = dptr(target_boxes)
+            a3.coll_starts = dptr(coll_starts)
+            a3.coll_lists = dptr(coll_lists)
+            a3.stick_out_factor = float(tree.stick_out_factor)
+            a3.targets_have_extent = int(tree.targets_have_extent)
+            a3.sources_have_extent = int(tree.sources_have_extent)
+            a3.crit = CRIT_CODE[crit]
+            keep_alive = []
+            if tree.targets_have_extent:
+                bbmin = dev(dev_tree.box_target_bounding_box_min)
+                bbmax = dev(dev_tree.box_target_bounding_box_max)
+                bsc = dev(dev_tree.box_source_counts_cumul)
+                keep_alive += [bbmin, bbmax, bsc]
+                a3.box_target_bounding_box_min = dptr(bbmin)
+                a3.box_target_bounding_box_max = dptr(bbmax)
+                a3.box_source_counts_cumul = dptr(bsc)
+            a3.min_nsources_cumul = int(min_nsrc)
+            rowlen = ntb + 1
+            G = actx.empty((nlevels + 1) * rowlen + 1, np.int32)
+            Cc = actx.empty((nlevels + 1) * rowlen + 1, np.int32)
+            summary = actx.zeros(2 * (nlevels + 2), np.int64)
+            check(lib.bt_trav_list3(dcode, 0, C.byref(tv), C.byref(a3), ntb, dptr(G), dptr(Cc),
+                                    None, dptr(summary), sh), "list 3 count")
+
+            both = _read_i64(actx, torch.cat([totals, summary]))
+            tot = both[:8]
+            summ = both[8:]
+            g0 = summ[:nlevels + 2]              # G[l][0], l = 0..nlevels, then grand total
+            c0 = summ[nlevels + 2:]
+            _check_int32(int(tot[0]), "neighbor_source_boxes")
+            _check_int32(int(tot[1]), "from_sep_siblings")
+            _check_int32(int(tot[2]), "from_sep_bigger")
+            _check_int32(int(g0[nlevels + 1]), "from_sep_smaller")
+
+            # }}}
+
+            # {{{ fill phases
+
+            l1_lists = actx.empty(int(tot[0]), np.int32)
+            check(lib.bt_trav_build_list(dcode, 1, 1, C.byref(tv), C.byref(a1), ntb,
+                                         dptr(l1_starts), dptr(l1_lists), None, None, None, sh),
+                  "list 1 fill")
+            l2_lists = actx.empty(int(tot[1]), np.int32)
+            check(lib.bt_trav_build_list(dcode, 2, 1, C.byref(tv), C.byref(a2), ntp,
+                                         dptr(l2_starts), dptr(l2_lists), None, None, None, sh),
+                  "list 2 fill")
+            l4_lists = actx.empty(int(tot[2]), np.int32)
+            l4c_lists_raw = actx.empty(int(tot[3]), np.int32) if with_extent else None
+            check(lib.bt_trav_build_list(dcode, 4, 1, C.byref(tv), C.byref(a4), ntp,
+                                         dptr(l4_starts), dptr(l4_lists), dptr(l4c_starts_raw),
+                                         dptr(l4c_lists_raw), None, sh), "list 4 fill")
+
+            l3_all = actx.empty(int(g0[nlevels + 1]), np.int32)
+            check(lib.bt_trav_list3(dcode, 1, C.byref(tv), C.byref(a3), ntb, dptr(G), dptr(Cc),
+                                    dptr(l3_all), dptr(summary), sh), "list 3 fill")
+            nne_total = int(c0[nlevels])         # non-empty rows over all source levels
+            cstarts = actx.empty(nne_total + nlevels, np.int32)
+            nonempty_all = actx.empty(max(nne_total, 1), np.int32)
+            tb_nonempty_all = actx.empty(max(nne_total, 1), np.int32)
+            comp_idx = actx.empty((nlevels, rowlen), np.int32)
+            close3_starts = actx.empty(rowlen, np.int32) if with_extent else None
+            check(lib.bt_trav_list3_compress(nlevels, ntb, dptr(G), dptr(Cc), dptr(target_boxes),
+                                             dptr(cstarts), dptr(nonempty_all),
+                                             dptr(tb_nonempty_all), dptr(comp_idx),
+                                             dptr(close3_starts), sh), "list 3 compress")
+
+            from_sep_smaller_by_level = []
+            target_boxes_sep_smaller_by_source_level = []
+            for lev in range(nlevels):
+                nne = int(c0[lev + 1] - c0[lev])
+                noff = int(c0[lev])
+                soff = noff + lev
+                cnt = int(g0[lev + 1] - g0[lev])
+                from_sep_smaller_by_level.append(BuiltList(
+                    count=cnt,
+                    starts=cstarts[soff:soff + nne + 1],
+                    lists=l3_all[int(g0[lev]):int(g0[lev + 1])],
+                    num_nonempty_lists=nne,
+                    nonempty_indices=nonempty_all[noff:noff + nne],
+                    compressed_indices=comp_idx[lev]))
+                target_boxes_sep_smaller_by_source_level.append(tb_nonempty_all[noff:noff + nne])
+            if with_extent:
+                close3_lists = l3_all[int(g0[nlevels]):int(g0[nlevels + 1])]
+            else:
+                close3_starts = close3_lists = None
+
+            # list 4 close: re-index from target_or_target_parent_boxes to target_boxes
+            # (traversal.py:2255-2287, 1293-1304)
+            if with_extent:
+                rev = actx.zeros(max(nboxes, 1), np.int32)
+                check(lib.bt_reverse_index(ntp, dptr(target_or_target_parent_boxes), dptr(rev),
+                                           sh), "bt_reverse_index")
+                out_to_in = actx.empty(max(ntb, 1), np.int32)
+                check(lib.bt_gather_i32(ntb, dptr(rev), dptr(target_boxes), dptr(out_to_in), sh),
+                      "bt_gather_i32")
+                close4_starts, close4_lists = _merge_lists(
+                    actx, lib, out_to_in, ntb, [l4c_starts_raw], [l4c_lists_raw])
+            else:
+                close4_starts = close4_lists = None
+
+            # }}}
+
+            evt = torch.cuda.Event()
+            evt.record(stream)
+
+        info = FMMTraversalInfo(
+            tree=tree, well_sep_is_n_away=self.well_sep_is_n_away,
+            source_boxes=source_boxes, target_boxes=target_boxes,
+            level_start_source_box_nrs=lss, level_start_target_box_nrs=lst,
+            source_parent_boxes=source_parent_boxes,
+            level_start_source_parent_box_nrs=lssp,
+            target_or_target_parent_boxes=target_or_target_parent_boxes,
+            level_start_target_or_target_parent_box_nrs=lstp,
+            same_level_non_well_sep_boxes_starts=coll_starts,
+            same_level_non_well_sep_boxes_lists=coll_lists,
+            neighbor_source_boxes_starts=l1_starts, neighbor_source_boxes_lists=l1_lists,
+            from_sep_siblings_starts=l2_starts, from_sep_siblings_lists=l2_lists,
+            from_sep_smaller_by_level=make_obj_array(from_sep_smaller_by_level),
+            target_boxes_sep_smaller_by_source_level=make_obj_array(
+                target_boxes_sep_smaller_by_source_level),
+            from_sep_close_smaller_starts=close3_starts,
+            from_sep_close_smaller_lists=close3_lists,
+            from_sep_bigger_starts=l4_starts, from_sep_bigger_lists=l4_lists,
+            from_sep_close_bigger_starts=close4_starts,
+            from_sep_close_bigger_lists=close4_lists)
+        return actx.freeze(info), evt

@@ -1,0 +1,627 @@
+"""``TreeBuilder``: drop-in for ``boxtree.tree_build.TreeBuilder`` on B200.
+
+Same call signature, argument meaning, error behaviour and outputs as the
+reference (``boxtree/tree_build.py:93-1878``); the work is done by hand-written
+sm_100a kernels in ``libboxtree_b200.so`` (``include/boxtree_b200.h``) on
+torch-owned device buffers.  There is no CPU fallback.
+
+Algorithm: Morton keys for all levels at once -> one stable
+one-sweep radix sort -> per-level split loop on box data only (child ranges by
+binary search in the sorted keys) -> pruning / level-major renumbering ->
+source/target split, permutation, flags, particle extents.  The host keeps the
+reference's loop control (``tree_build.py:698-1276``) with one small readback
+per level.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import (CTL_LR_FOUND, CTL_NBOXES, CTL_NBOXES_FINAL, CTL_NHUGE, CTL_NSPLIT_REGULAR,
+                    CTL_OVERFLOW, CTL_OVERSIZE, CTL_SIZE, bt_box_out, bt_particles, bt_pool, check,
+                    dptr)
+from .array_context import TorchArrayContext, make_obj_array, numpy_dtype_of
+from .tree import Tree, box_flags_enum
+
+
+class MaxLevelsExceeded(RuntimeError):  # noqa: N818  (reference name, tree_build.py:79)
+    pass
+
+
+EXTENT_NORM_CODE = {None: 0, "linf": 1, "l2": 2}
+_LEAF_SMEM_CAP = 4096
+
+
+class _Pool:
+    """Creation-order box pool (device), grown by doubling."""
+
+    def __init__(self, actx, dim, coord_torch_dtype, capacity):
+        self.actx, self.dim, self.cdt = actx, dim, coord_torch_dtype
+        self.capacity = 0
+        self.arrays: dict[str, torch.Tensor] = {}
+        self.center: list[torch.Tensor] = []
+        self._alloc(capacity)
+
+    def _alloc(self, capacity):
+        dev = self.actx.device
+        old = self.arrays
+        oldc = self.center
+        n_old = self.capacity
+        spec = {"start": torch.int32, "count": torch.int32, "level": torch.uint8,
+                "parent": torch.int32, "child0": torch.int32, "has_children": torch.uint8,
+                "force_split": torch.uint8, "nonchild": torch.int32}
+        self.arrays = {}
+        for name, dt in spec.items():
+            a = torch.zeros(capacity, dtype=dt, device=dev)
+            if n_old:
+                a[:n_old].copy_(old[name])
+            self.arrays[name] = a
+        self.center = []
+        for ax in range(self.dim):
+            a = torch.zeros(capacity, dtype=self.cdt, device=dev)
+            if n_old:
+                a[:n_old].copy_(oldc[ax])
+            self.center.append(a)
+        self.split_list = torch.empty(capacity, dtype=torch.int32, device=dev)
+        self.flag = torch.empty(capacity, dtype=torch.uint8, device=dev)
+        self.capacity = capacity
+
+    def ensure(self, capacity):
+        if capacity > self.capacity:
+            new = self.capacity
+            while new < capacity:
+                new *= 2
+            self._alloc(new)
+
+    def struct(self) -> bt_pool:
+        p = bt_pool()
+        for name in ("start", "count", "level", "parent", "child0", "has_children",
+                     "force_split", "nonchild"):
+            setattr(p, name, dptr(self.arrays[name]))
+        for ax in range(self.dim):
+            p.center[ax] = dptr(self.center[ax])
+        p.capacity = self.capacity
+        return p
+
+
+class TreeBuilder:
+    """Builds a :class:`boxtree_b200.Tree`; mirrors ``boxtree.TreeBuilder``."""
+
+    morton_nr_dtype = np.dtype(np.int8)
+    box_level_dtype = np.dtype(np.uint8)
+    ROOT_EXTENT_STRETCH_FACTOR = 1e-4
+
+    def __init__(self, array_context: TorchArrayContext) -> None:
+        assert isinstance(array_context, TorchArrayContext)
+        self._setup_actx = array_context
+        self._lib = _cabi.load()
+        self.last_stats: dict[str, Any] = {}
+
+    # {{{ helpers
+
+    @staticmethod
+    def _as_device_1d(actx, a, name):
+        if isinstance(a, np.ndarray):
+            a = actx.from_numpy(a)
+        if not isinstance(a, torch.Tensor):
+            raise TypeError(f"'{name}' must be a torch tensor or numpy array")
+        if not a.is_cuda:
+            a = a.to(actx.device)
+        return a.contiguous()
+
+    # }}}
+
+    def __call__(self, actx: TorchArrayContext, particles, kind="adaptive",
+                 max_particles_in_box=None, allocator=None, debug=False, targets=None,
+                 source_radii=None, target_radii=None, stick_out_factor=None,
+                 refine_weights=None, max_leaf_refine_weight=None, wait_for=None,
+                 extent_norm=None, bbox=None, **kwargs):
+        """See ``boxtree/tree_build.py:145-214`` for the argument documentation.
+
+        :returns: ``(tree, event)``; *event* is a :class:`torch.cuda.Event`
+            recorded on the array context's stream.
+        """
+        assert isinstance(actx, TorchArrayContext)
+        lib = self._lib
+
+        if allocator is not None:
+            from warnings import warn
+            warn("Passing in 'allocator' is deprecated. The allocator of the "
+                 "array context 'actx' is used throughout.", DeprecationWarning, stacklevel=2)
+
+        # {{{ input processing (tree_build.py:225-295)
+
+        if kind not in ["adaptive", "adaptive-level-restricted", "non-adaptive"]:
+            raise ValueError(f"unknown tree kind: '{kind}'")
+
+        dimensions = len(particles)
+        if dimensions not in (1, 2, 3):
+            raise ValueError("only 1, 2 and 3 dimensions are supported")
+
+        sources_are_targets = targets is None
+        sources_have_extent = source_radii is not None
+        targets_have_extent = target_radii is not None
+
+        if extent_norm is None:
+            extent_norm = "linf"
+        if extent_norm not in ["linf", "l2"]:
+            raise ValueError(f"unexpected value of 'extent_norm': {extent_norm}")
+        srcntgts_extent_norm = extent_norm
+        srcntgts_have_extent = sources_have_extent or targets_have_extent
+        if not srcntgts_have_extent:
+            srcntgts_extent_norm = None
+        if srcntgts_extent_norm and targets is None:
+            raise ValueError("must specify targets when specifying any kind of radii")
+
+        particle_id_dtype = np.dtype(np.int32)
+        box_id_dtype = np.dtype(np.int32)
+
+        particles = [self._as_device_1d(actx, p, "particles") for p in particles]
+        coord_dtypes = {p.dtype for p in particles}
+        if len(coord_dtypes) != 1:
+            raise ValueError("all coordinate arrays must have the same dtype")
+        coord_tdtype = particles[0].dtype
+        coord_dtype = numpy_dtype_of(particles[0])
+        if coord_dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+            raise TypeError(f"unsupported coordinate dtype: {coord_dtype}")
+        dcode = _cabi.dtype_code(coord_dtype)
+
+        nsources = int(particles[0].shape[0])
+        if any(int(p.shape[0]) != nsources for p in particles):
+            raise ValueError("coordinate arrays must have the same length")
+        if targets is None:
+            ntargets = 0
+            nsrcntgts = nsources
+        else:
+            targets = [self._as_device_1d(actx, t, "targets") for t in targets]
+            if len(targets) != dimensions:
+                raise ValueError("sources and targets must have the same dimension")
+            ntargets = int(targets[0].shape[0])
+            if any(int(t.shape[0]) != ntargets for t in targets):
+                raise ValueError("coordinate arrays must have the same length")
+            nsrcntgts = nsources + ntargets
+
+        if source_radii is not None:
+            source_radii = self._as_device_1d(actx, source_radii, "source_radii")
+            if tuple(source_radii.shape) != (nsources,):
+                raise ValueError("'source_radii' has an invalid shape: "
+                                 f"{tuple(source_radii.shape)} (expected ({nsources},))")
+            if source_radii.dtype != coord_tdtype:
+                raise TypeError("dtypes of coordinate array 'particles' and 'source_radii' "
+                                f"must agree: got {coord_tdtype} and {source_radii.dtype}")
+        if target_radii is not None:
+            target_radii = self._as_device_1d(actx, target_radii, "target_radii")
+            if tuple(target_radii.shape) != (ntargets,):
+                raise ValueError("'target_radii' has an invalid shape: "
+                                 f"{tuple(target_radii.shape)} (expected ({ntargets},))")
+            if target_radii.dtype != coord_tdtype:
+                raise TypeError("dtypes of coordinate array 'particles' and 'target_radii' "
+                                f"must agree: got {coord_tdtype} and {target_radii.dtype}")
+
+        if sources_have_extent or targets_have_extent:
+            if stick_out_factor is None:
+                raise ValueError("if sources or targets have extent, "
+                                 "'stick_out_factor' must be explicitly specified")
+        else:
+            stick_out_factor = 0
+
+        if targets is not None and targets[0].dtype != coord_tdtype:
+            raise TypeError("sources and targets coordinates must have same dtype: "
+                            f"got {coord_tdtype} and {targets[0].dtype}")
+
+        if nsrcntgts >= 2**30:
+            raise NotImplementedError("more than 2**30 particles per device are not supported")
+
+        # }}}
+
+        # {{{ refine weights (tree_build.py:405-452)
+
+        specified_max = max_particles_in_box is not None
+        specified_weights = refine_weights is not None and max_leaf_refine_weight is not None
+        if specified_max and specified_weights:
+            raise ValueError("may only specify one of 'max_particles_in_box' and "
+                             "'refine_weights'/'max_leaf_refine_weight")
+        elif not specified_max and not specified_weights:
+            raise ValueError("must specify either 'max_particles_in_box' or "
+                             "'refine_weights'/'max_leaf_refine_weight'")
+        elif specified_max:
+            refine_weights = None          # every particle weighs 1
+            max_leaf_refine_weight = max_particles_in_box
+        else:
+            refine_weights = self._as_device_1d(actx, refine_weights, "refine_weights")
+            if refine_weights.dtype != torch.int32:
+                raise TypeError("'refine_weights' must have dtype 'int32' "
+                                f"(got {refine_weights.dtype})")
+
+        if max_leaf_refine_weight <= 0:
+            raise ValueError(
+                f"'max_leaf_refine_weight' must be positive: {max_leaf_refine_weight}")
+
+        if refine_weights is not None and nsrcntgts:
+            if max_leaf_refine_weight < int(refine_weights.max()):
+                raise ValueError(
+                    "entries of 'refine_weights' cannot exceed 'max_leaf_refine_weight'")
+            if int(refine_weights.min()) < 0:
+                raise ValueError("all entries of 'refine_weights' must be nonnegative")
+            total_refine_weight = int(refine_weights.sum(dtype=torch.int64))
+        else:
+            total_refine_weight = nsrcntgts
+        max_leaf_refine_weight = int(max_leaf_refine_weight)
+
+        # }}}
+
+        stream = actx.stream
+        sh = actx.stream_handle
+        level_restrict = kind == "adaptive-level-restricted"
+        adaptive = kind != "non-adaptive"
+        have_ext = int(srcntgts_have_extent)
+        nb = 2**dimensions
+
+        with torch.cuda.stream(stream), torch.cuda.device(actx.device):
+            # {{{ particle view (virtual concatenation, tree_build.py:328-388)
+
+            P = bt_particles()
+            for ax in range(dimensions):
+                P.sources[ax] = dptr(particles[ax])
+                P.targets[ax] = dptr(targets[ax]) if targets is not None else None
+            P.source_radii = dptr(source_radii)
+            P.target_radii = dptr(target_radii)
+            P.nsources = nsources
+            P.ntargets = ntargets
+
+            # }}}
+
+            # {{{ bounding box (tree_build.py:458-508)
+
+            if nsrcntgts == 0:
+                raise ValueError("cannot build a tree without particles")
+
+            bbox_dev = actx.empty(2 * dimensions, coord_dtype)
+            check(lib.bt_bounding_box(dcode, dimensions, C.byref(P), dptr(bbox_dev), sh),
+                  "bt_bounding_box")
+            bbox_auto = bbox_dev.cpu().numpy()
+            auto_min = bbox_auto[0::2].copy()
+            auto_max = bbox_auto[1::2].copy()
+
+            if bbox is None:
+                root_extent = max(auto_max[i] - auto_min[i] for i in range(dimensions)) \
+                    * (1 + TreeBuilder.ROOT_EXTENT_STRETCH_FACTOR)
+                bbox_min = auto_min.copy()
+                bbox_max = bbox_min + root_extent
+            else:
+                if not isinstance(bbox, np.ndarray):
+                    raise NotImplementedError(f"unsupported bounding box type: {type(bbox)}")
+                assert len(bbox) == dimensions
+                bbox_min = np.empty(dimensions, coord_dtype)
+                bbox_max = np.empty(dimensions, coord_dtype)
+                for i in range(dimensions):
+                    bbox_min[i] = bbox[i][0]
+                    bbox_max[i] = bbox[i][1]
+                    assert bbox_min[i] < bbox_max[i]
+                    assert bbox_min[i] <= auto_min[i]
+                    assert bbox_max[i] >= auto_max[i]
+                bbox_exts = bbox_max - bbox_min
+                for ext in bbox_exts:
+                    assert abs(ext - bbox_exts[0]) < 1e-15
+                root_extent = bbox_exts[0]
+            root_extent = coord_dtype.type(root_extent)
+            root_center = [bbox_min[d] + (bbox_max[d] - bbox_min[d]) / 2 for d in range(dimensions)]
+
+            # }}}
+
+            # {{{ keys + sort
+
+            key_bufs = [actx.empty(nsrcntgts, np.int64), actx.empty(nsrcntgts, np.int64)]
+            id_bufs = [actx.empty(nsrcntgts, np.int32), actx.empty(nsrcntgts, np.int32)]
+            check(lib.bt_make_keys(dcode, dimensions, C.byref(P), _cabi.darray(bbox_min),
+                                   _cabi.darray(bbox_max), EXTENT_NORM_CODE[srcntgts_extent_norm],
+                                   float(stick_out_factor), dptr(key_bufs[0]), sh), "bt_make_keys")
+            in_alt = C.c_int(0)
+            check(lib.bt_sort_particles(nsrcntgts, dimensions, have_ext, dptr(key_bufs[0]),
+                                        dptr(key_bufs[1]), dptr(id_bufs[0]), dptr(id_bufs[1]),
+                                        C.byref(in_alt), sh), "bt_sort_particles")
+            keys = key_bufs[in_alt.value]
+            ids = id_bufs[in_alt.value]
+            del key_bufs, id_bufs
+
+            wprefix = None
+            if refine_weights is not None:
+                wprefix = actx.empty(nsrcntgts + 1, np.int64)
+                check(lib.bt_weight_prefix(nsrcntgts, dptr(ids), dptr(refine_weights),
+                                           dptr(wprefix), sh), "bt_weight_prefix")
+
+            # }}}
+
+            # {{{ level loop (tree_build.py:653-1276)
+
+            nboxes_guess = kwargs.get("nboxes_guess")
+            if nboxes_guess is None:
+                nboxes_guess = int(nb * ((max_leaf_refine_weight + total_refine_weight - 1)
+                                         // max_leaf_refine_weight)) + 1
+            assert nboxes_guess > 0
+            pool = _Pool(actx, dimensions, coord_tdtype, max(int(nboxes_guess), 2))
+            ctl = actx.zeros(CTL_SIZE, np.int32)
+            ctl_host = torch.empty(CTL_SIZE, dtype=torch.int32, pin_memory=True)
+            check(lib.bt_pool_init(dcode, dimensions, C.byref(pool.struct()), nsrcntgts, have_ext,
+                                   dptr(keys), _cabi.darray(root_center), dptr(ctl), sh),
+                  "bt_pool_init")
+
+            nlevels_max = 2 * (np.finfo(coord_dtype).nmant + 1)
+            max_key_level = lib.bt_max_key_level(dimensions)
+            level = 1 if total_refine_weight > max_leaf_refine_weight else 0
+            nboxes = 1
+            level_block_start = 0            # first pool id of the boxes on level-1
+            final_level_restrict_iteration = False
+            nreallocs = 0
+            niterations = 0
+
+            def read_ctl():
+                ctl_host.copy_(ctl, non_blocking=True)
+                stream.synchronize()
+                return ctl_host.numpy()
+
+            while level:
+                niterations += 1
+                if level + 1 >= nlevels_max or level > max_key_level:
+                    raise MaxLevelsExceeded(
+                        "Level count exceeded number of significant "
+                        "bits in coordinate dtype. That means that a large number "
+                        "of particles was indistinguishable up to floating point "
+                        "precision (because they ended up in the same box).")
+
+                lo = 0 if level_restrict else level_block_start
+                ncand = nboxes - lo
+                if adaptive and not level_restrict:
+                    bound = min(ncand, total_refine_weight // (max_leaf_refine_weight + 1) + 1)
+                else:
+                    bound = min(ncand, nboxes - level_block_start
+                                + (1024 if level_restrict else 0))
+                pool.ensure(nboxes + nb * bound)
+
+                skip_if_no_regular = int(bool(srcntgts_have_extent)
+                                         and not final_level_restrict_iteration)
+
+                def run_step(run_decide):
+                    check(lib.bt_level_step(
+                        dcode, dimensions, C.byref(pool.struct()), dptr(keys), dptr(wprefix),
+                        dptr(ctl), dptr(pool.split_list), dptr(pool.flag), lo, nboxes, level,
+                        max_leaf_refine_weight, int(adaptive), int(level_restrict), have_ext,
+                        skip_if_no_regular, float(root_extent), run_decide, sh), "bt_level_step")
+                    if level_restrict and not final_level_restrict_iteration:
+                        check(lib.bt_level_restrict(dcode, dimensions, C.byref(pool.struct()),
+                                                    dptr(ctl), level, pool.capacity,
+                                                    float(root_extent), sh), "bt_level_restrict")
+
+                run_step(1)
+                h = read_ctl()
+                while h[CTL_OVERFLOW]:
+                    nreallocs += 1
+                    pool.ensure(nboxes + nb * int(h[_cabi.CTL_NSPLIT]))
+                    run_step(0)
+                    h = read_ctl()
+
+                nsplit_regular = int(h[CTL_NSPLIT_REGULAR])
+                have_oversize_split_box = int(h[CTL_OVERSIZE])
+
+                if nsplit_regular == 0:
+                    # no new boxes on the new level (tree_build.py:1016-1025)
+                    if srcntgts_have_extent and not final_level_restrict_iteration:
+                        level -= 1
+                        break
+                    assert final_level_restrict_iteration
+
+                level_block_start = nboxes
+                nboxes = int(h[CTL_NBOXES])
+
+                if final_level_restrict_iteration:
+                    level -= 1
+                    break
+
+                if level_restrict:
+                    did_upper_level_split = bool(level - 2 >= 1 and h[CTL_LR_FOUND + level - 2])
+                    if have_oversize_split_box == 0 and did_upper_level_split:
+                        final_level_restrict_iteration = True
+                        level += 1
+                        continue
+
+                if not have_oversize_split_box:
+                    break
+                level += 1
+
+            nlevels = level + 1
+
+            # }}}
+
+            # {{{ prune / renumber (tree_build.py:1330-1456)
+
+            prune_empty_leaves = not kwargs.get("skip_prune")
+            map_old2new = actx.empty(nboxes, np.int32)
+            src_of_new = actx.empty(nboxes, np.int32)
+            level_start_dev = actx.zeros(nlevels + 2, np.int32)
+            check(lib.bt_finalize_numbering(dcode, dimensions, C.byref(pool.struct()), nboxes,
+                                            int(level_restrict), int(not prune_empty_leaves),
+                                            dptr(ctl), dptr(map_old2new), dptr(src_of_new),
+                                            dptr(level_start_dev), sh), "bt_finalize_numbering")
+            h = read_ctl()
+            nfinal = int(h[CTL_NBOXES_FINAL])
+            level_start_box_nrs = level_start_dev.cpu().numpy()[:nlevels + 1].copy()
+            level_start_box_nrs[nlevels] = nfinal
+
+            aligned_nboxes = ((nfinal + 31) // 32) * 32
+            box_srcntgt_starts = actx.empty(nfinal, np.int32)
+            box_srcntgt_counts_cumul = actx.empty(nfinal, np.int32)
+            box_srcntgt_counts_nonchild = actx.empty(nfinal, np.int32)
+            box_levels = actx.empty(nfinal, np.uint8)
+            box_parent_ids = actx.empty(nfinal, np.int32)
+            box_child_ids = actx.zeros((nb, aligned_nboxes), np.int32)
+            box_centers = actx.zeros((dimensions, aligned_nboxes), coord_dtype)
+            box_has_children = actx.empty(nfinal, np.uint8)
+            box_real_children = actx.empty(nfinal, np.uint8)
+            out = bt_box_out()
+            out.box_start = dptr(box_srcntgt_starts)
+            out.box_count = dptr(box_srcntgt_counts_cumul)
+            out.box_nonchild = dptr(box_srcntgt_counts_nonchild)
+            out.box_levels = dptr(box_levels)
+            out.box_parent_ids = dptr(box_parent_ids)
+            out.box_child_ids = dptr(box_child_ids)
+            out.box_centers = dptr(box_centers)
+            out.has_children = dptr(box_has_children)
+            out.real_children = dptr(box_real_children)
+            check(lib.bt_gather_boxes(dcode, dimensions, C.byref(pool.struct()), have_ext,
+                                      dptr(src_of_new), dptr(map_old2new), nfinal, aligned_nboxes,
+                                      C.byref(out), sh), "bt_gather_boxes")
+
+            # }}}
+
+            # {{{ particle order inside never-partitioned boxes
+
+            big_list = actx.empty(max(nfinal, 1), np.int32)
+            huge_list = actx.empty(max(nfinal, 1), np.int32)
+            check(lib.bt_leaf_fixup(nfinal, dptr(box_srcntgt_starts),
+                                    dptr(box_srcntgt_counts_cumul), dptr(box_real_children),
+                                    dptr(ids), dptr(ctl), dptr(big_list), nfinal, dptr(huge_list),
+                                    sh), "bt_leaf_fixup")
+            leaves_bounded = (refine_weights is None and not srcntgts_have_extent and adaptive
+                              and max_leaf_refine_weight <= _LEAF_SMEM_CAP)
+            if not leaves_bounded:
+                h = read_ctl()
+                nhuge = int(h[CTL_NHUGE])
+                if nhuge:
+                    hl = huge_list[:nhuge].cpu().numpy()
+                    st = box_srcntgt_starts.cpu().numpy()
+                    cn = box_srcntgt_counts_cumul.cpu().numpy()
+                    for b in hl:
+                        seg = ids[int(st[b]):int(st[b]) + int(cn[b])]
+                        check(lib.bt_sort_u32_segment(int(cn[b]), dptr(seg), sh),
+                              "bt_sort_u32_segment")
+            del big_list, huge_list
+
+            # }}}
+
+            # {{{ sources / targets (tree_build.py:1464-1620)
+
+            if sources_are_targets:
+                user_source_ids = ids
+                sorted_target_ids = actx.empty(nsrcntgts, np.int32)
+                check(lib.bt_reverse_index(nsrcntgts, dptr(ids), dptr(sorted_target_ids), sh),
+                      "bt_reverse_index")
+                source_numbers = None
+                srcntgt_target_ids = None
+            else:
+                source_numbers = actx.empty(nsrcntgts + 1, np.int32)
+                user_source_ids = actx.empty(nsources, np.int32)
+                srcntgt_target_ids = actx.empty(ntargets, np.int32)
+                sorted_target_ids = actx.empty(ntargets, np.int32)
+                check(lib.bt_split_sources_targets(
+                    nsrcntgts, nsources, dptr(ids), dptr(source_numbers), dptr(user_source_ids),
+                    dptr(srcntgt_target_ids), dptr(sorted_target_ids), sh),
+                    "bt_split_sources_targets")
+
+            def permute(from_ids, n, want_radii):
+                outs = [actx.empty(n, coord_dtype) for _ in range(dimensions)]
+                radii = actx.empty(n, coord_dtype) if want_radii else None
+                check(lib.bt_permute(dcode, dimensions, C.byref(P), dptr(from_ids), n,
+                                     _cabi.ptr_array(outs), dptr(radii), sh), "bt_permute")
+                return make_obj_array(outs), radii
+
+            if sources_are_targets:
+                sources, _ = permute(user_source_ids, nsrcntgts, False)
+                tgts = sources
+                out_source_radii = out_target_radii = None
+            else:
+                sources, out_source_radii = permute(user_source_ids, nsources,
+                                                    srcntgts_have_extent)
+                tgts, out_target_radii = permute(srcntgt_target_ids, ntargets,
+                                                 srcntgts_have_extent)
+
+            # }}}
+
+            # {{{ per-box particle ranges and flags (tree_build.py:1666-1723)
+
+            box_flags = actx.empty(nfinal, box_flags_enum.dtype)
+            if sources_are_targets:
+                box_source_starts = box_target_starts = box_srcntgt_starts
+                box_source_counts_cumul = box_target_counts_cumul = box_srcntgt_counts_cumul
+                box_source_counts_nonchild = box_target_counts_nonchild = \
+                    actx.empty(nfinal, np.int32)
+            else:
+                box_source_starts = actx.empty(nfinal, np.int32)
+                box_source_counts_cumul = actx.empty(nfinal, np.int32)
+                box_source_counts_nonchild = actx.empty(nfinal, np.int32)
+                box_target_starts = actx.empty(nfinal, np.int32)
+                box_target_counts_cumul = actx.empty(nfinal, np.int32)
+                box_target_counts_nonchild = actx.empty(nfinal, np.int32)
+            check(lib.bt_box_info(
+                nfinal, int(sources_are_targets), have_ext, dptr(box_srcntgt_starts),
+                dptr(box_srcntgt_counts_cumul), dptr(box_srcntgt_counts_nonchild),
+                dptr(box_has_children), dptr(source_numbers),
+                dptr(box_source_starts), dptr(box_source_counts_nonchild),
+                dptr(box_source_counts_cumul), dptr(box_target_starts),
+                dptr(box_target_counts_nonchild), dptr(box_target_counts_cumul),
+                dptr(box_flags), sh), "bt_box_info")
+
+            # }}}
+
+            # {{{ box particle extents (tree_build.py:1730-1802)
+
+            bb_src_min = actx.zeros((dimensions, aligned_nboxes), coord_dtype)
+            bb_src_max = actx.zeros((dimensions, aligned_nboxes), coord_dtype)
+            if sources_are_targets:
+                bb_tgt_min, bb_tgt_max = bb_src_min, bb_src_max
+            else:
+                bb_tgt_min = actx.zeros((dimensions, aligned_nboxes), coord_dtype)
+                bb_tgt_max = actx.zeros((dimensions, aligned_nboxes), coord_dtype)
+
+            rounds = [(sources, out_source_radii if sources_have_extent else None,
+                       box_source_starts, box_source_counts_nonchild, bb_src_min, bb_src_max)]
+            if not sources_are_targets:
+                rounds.append((tgts, out_target_radii if targets_have_extent else None,
+                               box_target_starts, box_target_counts_nonchild, bb_tgt_min,
+                               bb_tgt_max))
+            for lev in range(nlevels - 1, -1, -1):
+                start, stop = int(level_start_box_nrs[lev]), int(level_start_box_nrs[lev + 1])
+                for parts, radii, pstarts, pcounts, bmin, bmax in rounds:
+                    check(lib.bt_box_extents(
+                        dcode, dimensions, start, stop, aligned_nboxes, dptr(box_child_ids),
+                        dptr(box_centers), dptr(pstarts), dptr(pcounts),
+                        _cabi.ptr_array(list(parts)), dptr(radii), dptr(bmin), dptr(bmax), sh),
+                        "bt_box_extents")
+
+            # }}}
+
+            level_start_dev_out = actx.from_numpy(level_start_box_nrs.astype(np.int32))
+            evt = torch.cuda.Event()
+            evt.record(stream)
+
+        self.last_stats = {"level_iterations": niterations, "nboxes_pre_prune": nboxes,
+                           "reallocs": nreallocs}
+
+        tree = Tree(
+            sources_are_targets=sources_are_targets,
+            sources_have_extent=sources_have_extent,
+            targets_have_extent=targets_have_extent,
+            particle_id_dtype=particle_id_dtype, box_id_dtype=box_id_dtype,
+            coord_dtype=coord_dtype, box_level_dtype=self.box_level_dtype,
+            bounding_box=(bbox_min, bbox_max), root_extent=root_extent,
+            stick_out_factor=stick_out_factor, extent_norm=srcntgts_extent_norm,
+            level_start_box_nrs=level_start_dev_out,
+            sources=sources, targets=tgts,
+            source_radii=out_source_radii if sources_have_extent else None,
+            target_radii=out_target_radii if targets_have_extent else None,
+            box_source_starts=box_source_starts,
+            box_source_counts_nonchild=box_source_counts_nonchild,
+            box_source_counts_cumul=box_source_counts_cumul,
+            box_target_starts=box_target_starts,
+            box_target_counts_nonchild=box_target_counts_nonchild,
+            box_target_counts_cumul=box_target_counts_cumul,
+            box_parent_ids=box_parent_ids, box_child_ids=box_child_ids,
+            box_centers=box_centers, box_levels=box_levels, box_flags=box_flags,
+            user_source_ids=user_source_ids, sorted_target_ids=sorted_target_ids,
+            box_source_bounding_box_min=bb_src_min, box_source_bounding_box_max=bb_src_max,
+            box_target_bounding_box_min=bb_tgt_min, box_target_bounding_box_max=bb_tgt_max,
+            _is_pruned=prune_empty_leaves)
+        return actx.freeze(tree), evt

@@ -1,0 +1,263 @@
+/*
+ * boxtree_b200.h -- C ABI of libboxtree_b200.so (sm_100a kernels for the
+ * TreeBuilder -> Tree -> FMMTraversalBuilder -> FMMTraversalInfo path).
+ *
+ * The natural FFI seam of the reference is its two records of compiled device
+ * kernels: boxtree/tree_build_kernels.py:130-150 (`_KernelInfo`, 13 tree-build
+ * kernels + bounding box + gappy copy) and boxtree/traversal.py:1710-1718
+ * (`_KernelInfo`, 7 list builders).  Each entry point below names the reference
+ * kernel(s) it replaces (paths relative to the reference checkout).
+ *
+ * Conventions: every pointer is a DEVICE pointer unless stated otherwise; sizes
+ * are element counts; `stream` is a cudaStream_t passed as void*; every call
+ * only ENQUEUES work on `stream` and returns 0 on success, a cudaError_t value
+ * (< 10000) or a BT_ERR_* code otherwise.  No torch types cross this boundary.
+ * dtype: BT_F32 / BT_F64 coordinate type; dim: 1, 2 or 3.
+ */
+#ifndef BOXTREE_B200_H
+#define BOXTREE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BT_F32 0
+#define BT_F64 1
+
+/* box flag bits -- boxtree/tree.py:133-142 */
+#define BT_BOX_IS_SOURCE_BOX 1
+#define BT_BOX_IS_TARGET_BOX 2
+#define BT_BOX_HAS_SOURCE_CHILD_BOXES 4
+#define BT_BOX_HAS_TARGET_CHILD_BOXES 8
+
+/* slots of the int32 device control block `ctl` (BT_CTL_SIZE entries) */
+#define BT_CTL_NBOXES 0          /* boxes in the pool */
+#define BT_CTL_NSPLIT 1          /* boxes split in this level iteration */
+#define BT_CTL_OVERSIZE 2        /* have_oversize_split_box (tree_build.py:641) */
+#define BT_CTL_OVERFLOW 3        /* pool capacity too small; grow and call again */
+#define BT_CTL_NSPLIT_REGULAR 4  /* splits of boxes on the level above the new one */
+#define BT_CTL_COMMITTED 5
+#define BT_CTL_NBOXES_FINAL 6
+#define BT_CTL_NBIG 7
+#define BT_CTL_NHUGE 8
+#define BT_CTL_LR_FOUND 16       /* [16 + level]: have_upper_level_split_box per level */
+#define BT_CTL_LR_SLOTS 48
+#define BT_CTL_SIZE 64
+
+typedef struct {
+    const void *sources[3];     /* per-axis coordinate arrays, [nsources] */
+    const void *targets[3];     /* per-axis, [ntargets]; NULL when sources are targets */
+    const void *source_radii;   /* [nsources] or NULL */
+    const void *target_radii;   /* [ntargets] or NULL */
+    int64_t nsources;
+    int64_t ntargets;           /* 0 when sources are targets */
+} bt_particles;
+
+/* creation-order box pool used while the level loop runs */
+typedef struct {
+    int32_t *start;             /* first particle (sorted order); 0 for empty boxes */
+    int32_t *count;             /* cumulative particle count */
+    uint8_t *level;
+    int32_t *parent;
+    int32_t *child0;            /* id of Morton child 0 (children are contiguous); 0 = none */
+    uint8_t *has_children;
+    uint8_t *force_split;
+    int32_t *nonchild;          /* particles that stop in this box (extents) */
+    void *center[3];
+    int32_t capacity;
+} bt_pool;
+
+typedef struct {
+    int32_t *box_start;         /* box_srcntgt_starts */
+    int32_t *box_count;         /* box_srcntgt_counts_cumul */
+    int32_t *box_nonchild;      /* box_srcntgt_counts_nonchild (extents) */
+    uint8_t *box_levels;
+    int32_t *box_parent_ids;
+    int32_t *box_child_ids;     /* [2^dim, aligned_nboxes] */
+    void *box_centers;          /* [dim, aligned_nboxes] */
+    uint8_t *has_children;
+    uint8_t *real_children;
+} bt_box_out;
+
+/* deepest level the 64-bit sort key resolves for `dim` (MaxLevelsExceeded above) */
+int bt_max_key_level(int dim);
+
+/* bounding_box.py:54-122 (BBOX_REDUCTION_TPL).  out_minmax: [2*dim] coords,
+ * laid out min_x, max_x, min_y, max_y, ... like make_bounding_box_dtype (:35-52) */
+int bt_bounding_box(int dtype, int dim, const bt_particles *p, void *out_minmax, void *stream);
+
+/* Digit computation of morton_scan (tree_build_kernels.py:308-470) for all levels
+ * at once.  bbox_min/bbox_max are HOST arrays [dim].  extent_norm: 0 none, 1 linf, 2 l2. */
+int bt_make_keys(int dtype, int dim, const bt_particles *p, const double *bbox_min,
+                 const double *bbox_max, int extent_norm, double stick_out_factor, uint64_t *keys,
+                 void *stream);
+
+/* Stable radix sort of (key, particle id); replaces the per-level partition
+ * morton_scan + renumber_particles (tree_build_kernels.py:247-508, 717-819).
+ * ids are generated (identity) by the first pass.  *result_in_alt (HOST) tells
+ * which buffer pair holds the result. */
+int bt_sort_particles(int64_t n, int dim, int have_extent, uint64_t *keys, uint64_t *keys_alt,
+                      uint32_t *ids, uint32_t *ids_alt, int *result_in_alt, void *stream);
+
+/* refine weights in sorted order -> exclusive int64 prefix, wprefix[n] = total
+ * (the pwt fields of the morton_scan struct, tree_build_kernels.py:462-466) */
+int bt_weight_prefix(int64_t n, const uint32_t *sorted_ids, const int32_t *weights,
+                     int64_t *wprefix, void *stream);
+
+/* root box and control block (tree_build.py:586-618, 656-668).  root_center: HOST [dim] */
+int bt_pool_init(int dtype, int dim, const bt_pool *pool, int64_t n, int have_extent,
+                 const uint64_t *keys, const double *root_center, int32_t *ctl, void *stream);
+
+/* One iteration of the level loop (tree_build.py:698-1121) on per-box data:
+ * split_box_id_scan (tree_build_kernels.py:514-640) + box_splitter (:646-711).
+ * Boxes [lo, nboxes) of the pool are examined.  run_decide = 0 repeats only the
+ * child creation after the caller enlarged the pool (BT_CTL_OVERFLOW). */
+int bt_level_step(int dtype, int dim, const bt_pool *pool, const uint64_t *keys,
+                  const int64_t *wprefix, int32_t *ctl, int32_t *split_list, uint8_t *flag, int lo,
+                  int nboxes, int level, int maxw, int adaptive, int level_restrict,
+                  int have_extent, int skip_if_no_regular, double root_extent, int run_decide,
+                  void *stream);
+
+/* level_restrict kernel + upper-level sweep (tree_build_kernels.py:825-915,
+ * tree_build.py:1145-1200); the sweep's early exit is a device-side flag chain. */
+int bt_level_restrict(int dtype, int dim, const bt_pool *pool, int32_t *ctl, int built_level,
+                      int nboxes_upper, double root_extent, void *stream);
+
+/* prune / renumber: find_prune_indices_scan, find_level_box_counts_scan
+ * (tree_build_kernels.py:1697-1742) and the gappy copies of tree_build.py:1389-1431 */
+int bt_finalize_numbering(int dtype, int dim, const bt_pool *pool, int nboxes, int level_restrict,
+                          int skip_prune, int32_t *ctl, int32_t *map_old2new, int32_t *src_of_new,
+                          int32_t *level_start, void *stream);
+int bt_gather_boxes(int dtype, int dim, const bt_pool *pool, int have_extent,
+                    const int32_t *src_of_new, const int32_t *map_old2new, int nfinal, int aligned,
+                    const bt_box_out *out, void *stream);
+
+/* restores ascending-user-id order inside never-partitioned boxes (the order the
+ * reference's stable partition leaves, tree_build_kernels.py:766-798) */
+int bt_leaf_fixup(int nboxes, const int32_t *box_start, const int32_t *box_count,
+                  const uint8_t *real_children, uint32_t *ids, int32_t *ctl, int32_t *big_list,
+                  int big_cap, int32_t *huge_list, void *stream);
+int bt_sort_u32_segment(int64_t n, uint32_t *ids, void *stream);
+
+/* source_counter + find_source_and_target_indices, particle part
+ * (tree_build_kernels.py:1770-1782, 1151-1161); source_numbers is [n+1] */
+int bt_split_sources_targets(int64_t n, int64_t nsources, const uint32_t *sorted_ids,
+                             int32_t *source_numbers, int32_t *user_source_ids,
+                             int32_t *srcntgt_target_ids, int32_t *sorted_target_ids, void *stream);
+/* tools.py:81-109 (reverse_index_array) */
+int bt_reverse_index(int64_t n, const uint32_t *ids, int32_t *out, void *stream);
+
+/* srcntgt_permuter + cl_array.take (tree_build_kernels.py:1170-1186, tree_build.py:1609-1616).
+ * outs: HOST array of dim device pointers */
+int bt_permute(int dtype, int dim, const bt_particles *p, const int32_t *from_ids, int64_t n,
+               void *const *outs, void *out_radii, void *stream);
+
+/* find_source_and_target_indices box part + box_info (tree_build_kernels.py:1062-1147, 1192-1305) */
+int bt_box_info(int nboxes, int sources_are_targets, int have_extent, const int32_t *box_start,
+                const int32_t *box_count, const int32_t *box_nonchild, const uint8_t *has_children,
+                const int32_t *source_numbers, int32_t *src_starts, int32_t *src_nonchild,
+                int32_t *src_cumul, int32_t *tgt_starts, int32_t *tgt_nonchild, int32_t *tgt_cumul,
+                uint8_t *box_flags, void *stream);
+
+/* find_box_extents for boxes [start, stop) of one level (tree_build_kernels.py:1311-1399).
+ * particles: HOST array of dim device pointers (tree-ordered coordinates) */
+int bt_box_extents(int dtype, int dim, int start, int stop, int aligned,
+                   const int32_t *box_child_ids, const void *box_centers, const int32_t *pstarts,
+                   const int32_t *pcounts, void *const *particles, const void *radii, void *bb_min,
+                   void *bb_max, void *stream);
+
+/* ---------------------------------------------------------------- traversal */
+
+typedef struct {
+    int32_t dim;
+    int32_t nboxes;
+    int32_t aligned_nboxes;
+    int32_t nlevels;
+    double root_extent;
+    const void *box_centers;            /* [dim, aligned] */
+    const uint8_t *box_levels;
+    const int32_t *box_child_ids;       /* [2^dim, aligned] */
+    const uint8_t *box_flags;
+    const int32_t *box_parent_ids;
+    int32_t well_sep_is_n_away;
+} bt_tree_view;
+
+/* sources_parents_and_targets (traversal.py:326-355): which = 0 source_parent_boxes,
+ * 1 source_boxes, 2 target_or_target_parent_boxes, 3 target_boxes.  Writes the
+ * compacted ascending box list and its length (*count_dev, device int32). */
+int bt_trav_box_list(int which, int nboxes, const uint8_t *box_flags, const int8_t *mask,
+                     int32_t *out_list, int32_t *count_dev, void *stream);
+
+/* extract_level_start_box_nrs + host fix-up (traversal.py:361-392, 2073-2098) */
+int bt_trav_level_starts(int nlevels, const int32_t *level_start_box_nrs, const int32_t *box_list,
+                         int nlist, int32_t *out /*[nlevels+1]*/, void *stream);
+
+/* List builders (pyopencl ListOfListsBuilder: count, scan, write).
+ * kind: 0 same_level_non_well_sep_boxes (traversal.py:398-464)
+ *       1 neighbor_source_boxes / list 1 (:470-550)
+ *       2 from_sep_siblings / list 2     (:556-601)
+ *       4 from_sep_bigger / list 4 (+close) (:931-1146)
+ * phase 0 writes per-row counts then turns them into starts[nrows+1] in place and
+ * stores the total at totals_dev[0] (and [1] for the close list), int64; phase 1 fills. */
+typedef struct {
+    const int32_t *row_boxes;           /* target_boxes / target_or_target_parent_boxes; NULL = all boxes */
+    const int32_t *coll_starts;         /* same_level_non_well_sep_boxes */
+    const int32_t *coll_lists;
+    double stick_out_factor;
+    int32_t with_extent;
+} bt_list_args;
+
+int bt_trav_build_list(int dtype, int kind, int phase, const bt_tree_view *tree,
+                       const bt_list_args *args, int nrows, int32_t *starts, int32_t *lists,
+                       int32_t *close_starts, int32_t *close_lists, int64_t *totals_dev,
+                       void *stream);
+
+/* from_sep_smaller for ALL source levels in one walk (+ list 3 close), traversal.py:607-875.
+ * G, C: int32 [nlevels + 1, ntarget_boxes + 1] (+1 trailing entry); row l < nlevels is
+ * source level l, row nlevels is the close list.
+ * phase 0: per-(level,row) counts, then ONE flattened exclusive scan in place (G holds
+ *          global offsets into the concatenated lists), C = flattened exclusive scan of
+ *          the non-empty flags; summary_dev (int64 [2*(nlevels+2)]) = G[l][0], C[l][0].
+ * phase 1: fill `lists` (all levels concatenated, level l at offset G[l][0]). */
+typedef struct {
+    const int32_t *target_boxes;
+    const int32_t *coll_starts;
+    const int32_t *coll_lists;
+    double stick_out_factor;
+    int32_t targets_have_extent;
+    int32_t sources_have_extent;
+    int32_t crit;                       /* 0 static_linf, 1 precise_linf, 2 static_l2 */
+    const void *box_target_bounding_box_min;
+    const void *box_target_bounding_box_max;
+    const int32_t *box_source_counts_cumul;
+    int32_t min_nsources_cumul;
+} bt_list3_args;
+
+int bt_trav_list3(int dtype, int phase, const bt_tree_view *tree, const bt_list3_args *args,
+                  int ntarget_boxes, int32_t *G, int32_t *C, int32_t *lists, int64_t *summary_dev,
+                  void *stream);
+
+/* eliminate_empty_output_lists bookkeeping for all levels in one launch: compressed
+ * starts (level l at offset C[l][0] + l), nonempty_indices and
+ * target_boxes[nonempty_indices] (level l at offset C[l][0]; traversal.py:2211-2215),
+ * compressed_indices [nlevels, ntarget_boxes + 1] and the close list's starts. */
+int bt_trav_list3_compress(int nlevels, int ntarget_boxes, const int32_t *G, const int32_t *C,
+                           const int32_t *target_boxes, int32_t *compressed_starts,
+                           int32_t *nonempty_indices, int32_t *target_boxes_nonempty,
+                           int32_t *compressed_indices, int32_t *close_starts, void *stream);
+
+/* _ListMerger (traversal.py:1153-1344): phase 0 -> new_starts[noutput+1], total at
+ * totals_dev[0]; phase 1 -> new_lists.  starts/lists: HOST arrays of nlists device pointers. */
+int bt_trav_merge_lists(int phase, int noutput, const int32_t *output_to_input_box, int nlists,
+                        const int32_t *const *starts, const int32_t *const *lists,
+                        int32_t *new_starts, int32_t *new_lists, int64_t *totals_dev, void *stream);
+
+/* out[i] = src[idx[i]]  (the take / fancy-index glue of traversal.py:1298-1302) */
+int bt_gather_i32(int64_t n, const int32_t *src, const int32_t *idx, int32_t *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BOXTREE_B200_H */

@@ -38,7 +38,7 @@ def build(force: bool = False, verbose: bool = False) -> None:
         if not force and not _needs_rebuild(out):
             continue
         cmd = ["gcc", "-O2", "-fPIC", "-shared", "-fopenmp", "-std=gnu11",
-               "-ffp-contract=off", "-fno-fast-math", "-Wall", "-Wno-unused-function",
+               "-ffp-contract=off", "-fno-fast-math", "-Wall", "-Wno-unused-function", "-Wno-maybe-uninitialized",
                define, *[os.path.join(HERE, s) for s in SOURCES], "-o", out, "-lm"]
         if verbose:
             print(" ".join(cmd))

@@ -520,6 +520,9 @@ void orc_box_info(
         particle_id_t nc = nc_src + nc_tgt;
         box_flags_t fl = 0;
         if (box_has_children[b]) {
+            /* :1256 -- BOX_HAS_SOURCE_OR_TARGET_CHILD_BOXES (= both child bits) is set
+               unconditionally for every non-leaf box */
+            fl |= BOX_HAS_SOURCE_CHILD_BOXES | BOX_HAS_TARGET_CHILD_BOXES;
             if (sources_are_targets) {
                 if (particle_count - nc)
                     fl |= BOX_HAS_SOURCE_CHILD_BOXES | BOX_HAS_TARGET_CHILD_BOXES;

@@ -1,0 +1,160 @@
+"""Parity sweep (needs a GPU): CUDA path vs CPU oracle over many option combinations.
+
+``python tests/gpu_sweep.py [--quick]`` prints one line per case; exit status 1 if any
+case differs.  Used during development and by ``tests/test_gpu_parity.py``.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+import traceback
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from oracle.traversal import build_traversal as oracle_traversal  # noqa: E402
+from oracle.tree_build import MaxLevelsExceeded as OracleMaxLevels  # noqa: E402
+from oracle.tree_build import build_tree as oracle_tree  # noqa: E402
+from tests.parity_util import (normal_particles, trav_mismatches, tree_mismatches,  # noqa: E402
+                               uniform_particles)
+
+
+def make_cases(quick=False):
+    cases = []
+    dims_list = (2, 3) if quick else (1, 2, 3)
+    for dims in dims_list:
+        for dt in (np.float64, np.float32):
+            base = dict(dims=dims, dtype=dt, n=3000 if quick else 20000)
+            cases.append(dict(base, name="adaptive", tree={"max_particles_in_box": 30}))
+            cases.append(dict(base, name="adaptive-5", tree={"max_particles_in_box": 5}))
+            cases.append(dict(base, name="single-box", n=4, tree={"max_particles_in_box": 30}))
+            cases.append(dict(base, name="two-level", n=50, tree={"max_particles_in_box": 30}))
+            cases.append(dict(base, name="skip-prune", tree={"max_particles_in_box": 30,
+                                                             "skip_prune": True}, trav=None))
+            cases.append(dict(base, name="tiny-guess", tree={"max_particles_in_box": 30,
+                                                             "nboxes_guess": 5}))
+            cases.append(dict(base, name="non-adaptive", n=3000,
+                              tree={"max_particles_in_box": 30, "kind": "non-adaptive"}))
+            cases.append(dict(base, name="weights", weights=True,
+                              tree={"max_leaf_refine_weight": 100}))
+            cases.append(dict(base, name="lr", tree={"max_particles_in_box": 30,
+                                                     "kind": "adaptive-level-restricted"}))
+            cases.append(dict(base, name="lr-skip-prune",
+                              tree={"max_particles_in_box": 30, "skip_prune": True,
+                                    "kind": "adaptive-level-restricted"}, trav=None))
+            cases.append(dict(base, name="src-tgt", ntargets=15000,
+                              tree={"max_particles_in_box": 30}))
+            cases.append(dict(base, name="uniform", uniform=True,
+                              tree={"max_particles_in_box": 30}))
+            for nsep in (1, 2):
+                cases.append(dict(base, name=f"nsep{nsep}", tree={"max_particles_in_box": 30},
+                                  trav={"well_sep_is_n_away": nsep}))
+                for norm, crit in (("linf", "static_linf"), ("linf", "precise_linf"),
+                                   ("l2", "static_l2"), ("l2", "precise_linf")):
+                    cases.append(dict(
+                        base, name=f"ext-{norm}-{crit}-n{nsep}", ntargets=15000, radii=True,
+                        tree={"max_particles_in_box": 30, "stick_out_factor": 0.25,
+                              "extent_norm": norm},
+                        trav={"well_sep_is_n_away": nsep, "from_sep_smaller_crit": crit}))
+                cases.append(dict(
+                    base, name=f"ext-lr-n{nsep}", ntargets=15000, radii=True,
+                    tree={"max_particles_in_box": 30, "stick_out_factor": 0.25,
+                          "extent_norm": "linf", "kind": "adaptive-level-restricted"},
+                    trav={"well_sep_is_n_away": nsep}))
+            cases.append(dict(
+                base, name="ext-minsrc", ntargets=15000, radii=True,
+                tree={"max_particles_in_box": 30, "stick_out_factor": 0.25},
+                trav={"_from_sep_smaller_min_nsources_cumul": 40}))
+            cases.append(dict(base, name="coincident", n=11, coincident=True,
+                              tree={"max_particles_in_box": 10}, expect_max_levels=True))
+    return cases
+
+
+def make_inputs(case):
+    dims, dt, n = case["dims"], case["dtype"], case["n"]
+    if case.get("coincident"):
+        src = [np.full(n, 0.25 + 0.1 * ax, dtype=dt) for ax in range(dims)]
+        src[0][0] = 1.0   # one distinct point so the bounding box is not degenerate
+    elif case.get("uniform"):
+        src = uniform_particles(n, dims, dt, seed=15)
+    else:
+        src = normal_particles(n, dims, dt, seed=15)
+    kw = dict(case["tree"])
+    tgt = None
+    if case.get("ntargets"):
+        tgt = normal_particles(case["ntargets"], dims, dt, seed=18)
+        kw["targets"] = tgt
+        if case.get("radii"):
+            rng = np.random.default_rng(13)
+            kw["target_radii"] = (0.05 * 2 ** rng.uniform(-10, 0, case["ntargets"])).astype(dt)
+    if case.get("weights"):
+        kw["refine_weights"] = np.random.default_rng(10).integers(
+            0, 10, n + (case.get("ntargets") or 0), dtype=np.int32)
+    return src, kw
+
+
+def run_case(case, actx, tb, travs):
+    from boxtree_b200 import FMMTraversalBuilder, MaxLevelsExceeded
+    src, kw = make_inputs(case)
+    t0 = time.time()
+    try:
+        ref_tree = oracle_tree(src, **kw)
+        ref_err = None
+    except OracleMaxLevels as e:
+        ref_tree, ref_err = None, e
+
+    dev_kw = {k: (actx.from_numpy(v) if isinstance(v, np.ndarray) else
+                  [actx.from_numpy(x) for x in v] if k == "targets" else v)
+              for k, v in kw.items()}
+    try:
+        got_tree_dev, _ = tb(actx, [actx.from_numpy(s) for s in src], **dev_kw)
+    except MaxLevelsExceeded:
+        if case.get("expect_max_levels") or ref_err is not None:
+            return []
+        raise
+    if ref_tree is None:
+        return ["oracle raised MaxLevelsExceeded, CUDA path did not"]
+    got_tree = actx.to_numpy(got_tree_dev)
+    bad = ["tree." + b for b in tree_mismatches(ref_tree, got_tree)]
+    if case.get("trav", {}) is not None and not bad:
+        tkw = dict(case.get("trav") or {})
+        ctor = {k: tkw.pop(k) for k in ("well_sep_is_n_away", "from_sep_smaller_crit")
+                if k in tkw}
+        ref_trav = oracle_traversal(ref_tree, **ctor, **tkw)
+        key = tuple(sorted(ctor.items()))
+        if key not in travs:
+            travs[key] = FMMTraversalBuilder(actx, **ctor)
+        got_trav_dev, _ = travs[key](actx, got_tree_dev, **tkw)
+        got_trav = actx.to_numpy(got_trav_dev)
+        bad += ["trav." + b for b in trav_mismatches(ref_trav, got_trav)]
+    case["_info"] = (f"nboxes={ref_tree.nboxes} nlevels={ref_tree.nlevels} "
+                     f"{time.time() - t0:.2f}s")
+    return bad
+
+
+def main(quick=False):
+    from boxtree_b200 import TorchArrayContext, TreeBuilder
+    actx = TorchArrayContext()
+    tb = TreeBuilder(actx)
+    travs = {}
+    nbad = 0
+    cases = make_cases(quick)
+    for case in cases:
+        label = f"{case['dims']}d {np.dtype(case['dtype']).name:8s} {case['name']}"
+        try:
+            bad = run_case(case, actx, tb, travs)
+        except Exception:  # noqa: BLE001
+            bad = ["EXCEPTION: " + traceback.format_exc(limit=6).replace("\n", " | ")]
+        if bad:
+            nbad += 1
+            print(f"FAIL {label}: {bad[:8]}", flush=True)
+        else:
+            print(f"ok   {label} {case.get('_info', '')}", flush=True)
+    print(f"{len(cases) - nbad}/{len(cases)} cases match the oracle bit for bit")
+    return nbad
+
+
+if __name__ == "__main__":
+    sys.exit(1 if main("--quick" in sys.argv) else 0)
