@@ -120,8 +120,35 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.argtypes = argtypes
             fn.restype = C.c_int
+        lib.bt_launch_count.argtypes = []
+        lib.bt_launch_count.restype = C.c_longlong
+        lib.bt_prof_enable.argtypes = [C.c_int]
+        lib.bt_prof_enable.restype = None
+        lib.bt_prof_reset.argtypes = []
+        lib.bt_prof_reset.restype = None
+        lib.bt_prof_report.argtypes = [C.c_char_p, C.c_int]
+        lib.bt_prof_report.restype = C.c_int
         _lib = lib
     return _lib
+
+
+def launch_count() -> int:
+    """Number of kernels this library has launched so far in this process."""
+    return int(load().bt_launch_count())
+
+
+def profile_report() -> dict:
+    """``{scope: (calls, total_ms)}`` of the scopes recorded since ``bt_prof_reset``;
+    the stream must be synchronised."""
+    lib = load()
+    need = lib.bt_prof_report(None, 0)
+    buf = C.create_string_buffer(need + 16)
+    lib.bt_prof_report(buf, need + 16)
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, calls, ms = line.split("\t")
+        out[name] = (int(calls), float(ms))
+    return out
 
 
 def check(code: int, what: str) -> None:

@@ -12,7 +12,11 @@
         cudaError_t bt_e_ = (call);                      \
         if (bt_e_ != cudaSuccess) return (int)bt_e_;     \
     } while (0)
-#define BT_LAUNCH_CHECK() BT_CHECK(cudaGetLastError())
+#define BT_LAUNCH_CHECK()                                \
+    do {                                                 \
+        ++bt::g_launch_count;                            \
+        BT_CHECK(cudaGetLastError());                    \
+    } while (0)
 #define BT_TRY(expr)                                     \
     do {                                                 \
         int bt_r_ = (expr);                              \
@@ -21,7 +25,41 @@
 
 namespace bt {
 
+// ---- instrumentation (bench.py): kernel launch counter and optional per-scope
+// CUDA-event timing on the launching stream.  Defined in tree_build.cu.
+extern long long g_launch_count;
+extern int g_prof_enabled;
+int prof_begin(const char* name, cudaStream_t s);
+void prof_end(int slot, cudaStream_t s);
+
+struct ProfScope {
+    int slot; cudaStream_t s;
+    ProfScope(const char* name, cudaStream_t st) : slot(-1), s(st)
+    { if (g_prof_enabled) slot = prof_begin(name, st); }
+    ~ProfScope() { if (slot >= 0) prof_end(slot, s); }
+};
+#define BT_PROF(name, stream) bt::ProfScope bt_prof_scope_(name, stream)
+
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
+
+// Stream-ordered scratch memory.  The default pool's release threshold is raised once so
+// that scratch survives the host synchronisations of the level loop instead of being
+// returned to the OS (and re-mapped) at every sync.
+static inline cudaError_t temp_alloc(void** p, size_t bytes, cudaStream_t s)
+{
+    static bool configured = false;
+    if (!configured) {
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        configured = true;
+    }
+    return cudaMallocAsync(p, bytes ? bytes : 16, s);
+}
 
 // Grid for a grid-stride loop over n items: enough blocks to cover n, capped at
 // a multiple of the SM count so the tail wave stays balanced.

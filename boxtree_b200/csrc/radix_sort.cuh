@@ -221,14 +221,17 @@ static int radix_sort_pairs(int64_t n, unsigned long long* keys, unsigned long l
     const size_t hist_bytes = (size_t)npasses * kRsRadix * sizeof(unsigned);
     const size_t desc_bytes = (size_t)ntiles * kRsRadix * sizeof(unsigned) + 16;
     unsigned char* tmp = nullptr;
-    BT_CHECK(cudaMallocAsync((void**)&tmp, hist_bytes + desc_bytes, stream));
+    BT_CHECK(bt::temp_alloc((void**)&tmp, hist_bytes + desc_bytes, stream));
     unsigned* ghist = reinterpret_cast<unsigned*>(tmp);
     unsigned* desc = reinterpret_cast<unsigned*>(tmp + hist_bytes);
     unsigned* ticket = desc + (size_t)ntiles * kRsRadix;
     BT_CHECK(cudaMemsetAsync(ghist, 0, hist_bytes, stream));
+    {
+    BT_PROF("rs_histogram", stream);
     rs_histogram_kernel<<<grid_for(n, 256, 4), 256, 0, stream>>>(keys, n, begin_bit, end_bit,
                                                                  npasses, ghist);
     BT_LAUNCH_CHECK();
+    }
 
     static bool attr_set = false;
     if (!attr_set) {
@@ -246,6 +249,7 @@ static int radix_sort_pairs(int64_t n, unsigned long long* keys, unsigned long l
         const int bits = (end_bit - shift < kRsBits) ? (end_bit - shift) : kRsBits;
         const unsigned mask = (1u << bits) - 1u;
         BT_CHECK(cudaMemsetAsync(desc, 0, desc_bytes, stream));
+        BT_PROF("rs_onesweep_pass", stream);
         if (p == 0 && identity_vals)
             rs_onesweep_kernel<true><<<(unsigned)ntiles, kRsThreads, sizeof(RsSmem), stream>>>(
                 kin, kout, vin, vout, n, shift, mask, ghist + p * kRsRadix, desc, ticket);

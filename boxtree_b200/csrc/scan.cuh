@@ -159,7 +159,7 @@ static int scan_exclusive(int64_t n_upper, const int* n_dev, InOp in, OutOp out,
     if (ntiles < 1) ntiles = 1;
     unsigned long long* tmp = nullptr;
     const size_t bytes = (size_t)(ntiles + 1) * sizeof(unsigned long long);
-    BT_CHECK(cudaMallocAsync((void**)&tmp, bytes, stream));
+    BT_CHECK(bt::temp_alloc((void**)&tmp, bytes, stream));
     BT_CHECK(cudaMemsetAsync(tmp, 0, bytes, stream));
     unsigned* ticket = reinterpret_cast<unsigned*>(tmp + ntiles);
     scan_kernel<InOp, OutOp><<<(unsigned)ntiles, kScanBlock, 0, stream>>>(

@@ -108,8 +108,12 @@ __device__ __forceinline__ void gen_colleagues(const TreeView<T, DIM>& t, const 
         const int wb = t.child(w.parent, w.mnr);
         if (wb) {
             T wc[DIM]; t.center(wb, wc);
-            if (adj_nbhd<T, DIM>(rad, center, level, nbhd, wc, t.levels[wb])) {
-                if (w.ssize + 1 == level && wb != box_id) e.e0(wb);
+            // The reference also descends into box_id itself (traversal.py:438-452) and
+            // walks its whole subtree, which can never append (deeper levels only):
+            // skipping that descent leaves the output unchanged and removes a serial
+            // walk over up to nboxes/2^d boxes by a single thread.
+            if (wb != box_id && adj_nbhd<T, DIM>(rad, center, level, nbhd, wc, t.levels[wb])) {
+                if (w.ssize + 1 == level) e.e0(wb);
                 else { w.push(wb); continue; }
             }
         }
@@ -599,6 +603,7 @@ extern "C" {
 int bt_trav_box_list(int which, int nboxes, const uint8_t* box_flags, const int8_t* mask,
                      int32_t* out_list, int32_t* count_dev, void* stream)
 {
+    BT_PROF("bt_trav_box_list", (cudaStream_t)stream);
     bt::BoxListIn in{box_flags, (const signed char*)mask, which};
     bt::BoxListOut out{in, out_list, count_dev};
     return bt::scan_exclusive(nboxes, nullptr, in, out, (cudaStream_t)stream);
@@ -607,6 +612,7 @@ int bt_trav_box_list(int which, int nboxes, const uint8_t* box_flags, const int8
 int bt_trav_level_starts(int nlevels, const int32_t* level_start_box_nrs, const int32_t* box_list,
                          int nlist, int32_t* out, void* stream)
 {
+    BT_PROF("bt_trav_level_starts", (cudaStream_t)stream);
     bt::level_starts_kernel<<<(nlevels + 1 + 63) / 64, 64, 0, (cudaStream_t)stream>>>(
         nlevels, level_start_box_nrs, box_list, nlist, out);
     BT_LAUNCH_CHECK();
@@ -617,6 +623,10 @@ int bt_trav_build_list(int dtype, int kind, int phase, const bt_tree_view* tree,
                        int nrows, int32_t* starts, int32_t* lists, int32_t* close_starts,
                        int32_t* close_lists, int64_t* totals_dev, void* stream)
 {
+    static const char* const kNames[2][5] = {
+        {"trav_colleagues_count", "trav_list1_count", "trav_list2_count", "?", "trav_list4_count"},
+        {"trav_colleagues_fill", "trav_list1_fill", "trav_list2_fill", "?", "trav_list4_fill"}};
+    BT_PROF(kNames[phase ? 1 : 0][(kind >= 0 && kind <= 4) ? kind : 3], (cudaStream_t)stream);
     BT_DISPATCH(dtype, tree->dim, build_list_impl, kind, phase, tree, args, nrows, starts, lists,
                 close_starts, close_lists, (long long*)totals_dev, (cudaStream_t)stream);
 }
@@ -625,6 +635,7 @@ int bt_trav_list3(int dtype, int phase, const bt_tree_view* tree, const bt_list3
                   int ntarget_boxes, int32_t* G, int32_t* C, int32_t* lists, int64_t* summary_dev,
                   void* stream)
 {
+    BT_PROF(phase ? "trav_list3_fill" : "trav_list3_count", (cudaStream_t)stream);
     BT_DISPATCH(dtype, tree->dim, list3_impl, phase, tree, args, ntarget_boxes, G, C, lists,
                 (long long*)summary_dev, (cudaStream_t)stream);
 }
@@ -634,6 +645,7 @@ int bt_trav_list3_compress(int nlevels, int ntarget_boxes, const int32_t* G, con
                            int32_t* nonempty_indices, int32_t* target_boxes_nonempty,
                            int32_t* compressed_indices, int32_t* close_starts, void* stream)
 {
+    BT_PROF("bt_trav_list3_compress", (cudaStream_t)stream);
     const int64_t total = ((int64_t)ntarget_boxes + 1) * (nlevels + 1);
     bt::list3_compress_kernel<<<bt::grid_for(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(
         nlevels, ntarget_boxes, G, C, target_boxes, compressed_starts, nonempty_indices,
@@ -651,6 +663,7 @@ __global__ void bt_gather_i32_kernel(int64_t n, const int* __restrict__ src, con
 
 int bt_gather_i32(int64_t n, const int32_t* src, const int32_t* idx, int32_t* out, void* stream)
 {
+    BT_PROF("bt_gather_i32", (cudaStream_t)stream);
     if (n <= 0) return BT_OK;
     bt_gather_i32_kernel<<<bt::grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(n, src, idx, out);
     BT_LAUNCH_CHECK();
@@ -661,6 +674,7 @@ int bt_trav_merge_lists(int phase, int noutput, const int32_t* output_to_input_b
                         const int32_t* const* starts, const int32_t* const* lists, int32_t* new_starts,
                         int32_t* new_lists, int64_t* totals_dev, void* stream)
 {
+    BT_PROF("bt_trav_merge_lists", (cudaStream_t)stream);
     if (nlists < 1 || nlists > 3) return BT_ERR_BAD_ARG;
     bt::MergeArgs m;
     m.nlists = nlists;

@@ -16,7 +16,30 @@
 #include "radix_sort.cuh"
 #include "../../include/boxtree_b200.h"
 
+#include <string.h>
+#include <stdio.h>
+#include <vector>
+#include <string>
+
 namespace bt {
+
+// ---------------------------------------------------------------------------
+// instrumentation
+// ---------------------------------------------------------------------------
+long long g_launch_count = 0;
+int g_prof_enabled = 0;
+struct ProfRec { std::string name; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof;
+
+int prof_begin(const char* name, cudaStream_t s)
+{
+    ProfRec r; r.name = name;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return -1;
+    cudaEventRecord(r.a, s);
+    g_prof.push_back(r);
+    return (int)g_prof.size() - 1;
+}
+void prof_end(int slot, cudaStream_t s) { cudaEventRecord(g_prof[slot].b, s); }
 
 // ---------------------------------------------------------------------------
 // key layout
@@ -766,7 +789,7 @@ static int bbox_impl(const bt_particles* p, void* out, cudaStream_t s)
     const int have_radii = (p->source_radii || p->target_radii) ? 1 : 0;
     const int grid = grid_for(P.n, 256, 4);
     T* partial = nullptr;
-    BT_CHECK(cudaMallocAsync((void**)&partial, sizeof(T) * 2 * DIM * grid, s));
+    BT_CHECK(bt::temp_alloc((void**)&partial, sizeof(T) * 2 * DIM * grid, s));
     bbox_partial_kernel<T, DIM><<<grid, 256, 0, s>>>(P, have_radii, partial);
     BT_LAUNCH_CHECK();
     bbox_final_kernel<T, DIM><<<1, 32, 0, s>>>(partial, grid, (T*)out);
@@ -857,8 +880,8 @@ static int finalize_boxes_impl(const bt_pool* pool, int nboxes, int level_restri
         unsigned long long *k0 = nullptr, *k1 = nullptr; unsigned *v0 = nullptr, *v1 = nullptr;
         if (level_restrict) {
             // pool order -> level-major, stable: creation order inside a level
-            BT_CHECK(cudaMallocAsync((void**)&k0, sizeof(unsigned long long) * nboxes * 2, s));
-            BT_CHECK(cudaMallocAsync((void**)&v0, sizeof(unsigned) * nboxes * 2, s));
+            BT_CHECK(bt::temp_alloc((void**)&k0, sizeof(unsigned long long) * nboxes * 2, s));
+            BT_CHECK(bt::temp_alloc((void**)&v0, sizeof(unsigned) * nboxes * 2, s));
             k1 = k0 + nboxes; v1 = v0 + nboxes;
             level_keys_kernel<<<grid_for(nboxes, 256), 256, 0, s>>>(pool->level, nboxes, k0);
             BT_LAUNCH_CHECK();
@@ -926,6 +949,36 @@ static int box_extents_impl(int start, int stop, int aligned, const int* child_i
 
 extern "C" {
 
+long long bt_launch_count(void) { return bt::g_launch_count; }
+void bt_prof_enable(int on) { bt::g_prof_enabled = on; }
+void bt_prof_reset(void)
+{
+    for (auto& r : bt::g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    bt::g_prof.clear();
+}
+// Writes "name\tcalls\ttotal_ms\n" lines (scopes aggregated by name) into buf; the
+// caller must have synchronised the stream.  Returns the number of bytes needed.
+int bt_prof_report(char* buf, int len)
+{
+    std::vector<std::string> names; std::vector<double> ms; std::vector<int> calls;
+    for (auto& r : bt::g_prof) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) continue;
+        size_t k = 0;
+        for (; k < names.size(); ++k) if (names[k] == r.name) break;
+        if (k == names.size()) { names.push_back(r.name); ms.push_back(0); calls.push_back(0); }
+        ms[k] += t; calls[k] += 1;
+    }
+    std::string out;
+    char line[256];
+    for (size_t k = 0; k < names.size(); ++k) {
+        snprintf(line, sizeof line, "%s\t%d\t%.6f\n", names[k].c_str(), calls[k], ms[k]);
+        out += line;
+    }
+    if (buf && len > 0) { strncpy(buf, out.c_str(), (size_t)len - 1); buf[len - 1] = 0; }
+    return (int)out.size() + 1;
+}
+
 int bt_max_key_level(int dim)
 {
     if (dim == 1) return 31;
@@ -935,11 +988,13 @@ int bt_max_key_level(int dim)
 }
 
 int bt_bounding_box(int dtype, int dim, const bt_particles* p, void* out_minmax, void* stream)
-{ BT_DISPATCH(dtype, dim, bbox_impl, p, out_minmax, (cudaStream_t)stream); }
+{
+    BT_PROF("bt_bounding_box", (cudaStream_t)stream); BT_DISPATCH(dtype, dim, bbox_impl, p, out_minmax, (cudaStream_t)stream); }
 
 int bt_make_keys(int dtype, int dim, const bt_particles* p, const double* bbox_min, const double* bbox_max,
                  int extent_norm, double stick_out_factor, uint64_t* keys, void* stream)
 {
+    BT_PROF("bt_make_keys", (cudaStream_t)stream);
     BT_DISPATCH(dtype, dim, make_keys_impl, p, bbox_min, bbox_max, extent_norm, stick_out_factor,
                 bt_max_key_level(dim), (unsigned long long*)keys, (cudaStream_t)stream);
 }
@@ -947,6 +1002,7 @@ int bt_make_keys(int dtype, int dim, const bt_particles* p, const double* bbox_m
 int bt_sort_particles(int64_t n, int dim, int have_extent, uint64_t* keys, uint64_t* keys_alt,
                       uint32_t* ids, uint32_t* ids_alt, int* result_in_alt, void* stream)
 {
+    BT_PROF("bt_sort_particles", (cudaStream_t)stream);
     const int D = bt_max_key_level(dim);
     const int begin_bit = have_extent ? 0 : bt::kStopBits;
     const int end_bit = bt::kStopBits + D * dim;
@@ -957,6 +1013,7 @@ int bt_sort_particles(int64_t n, int dim, int have_extent, uint64_t* keys, uint6
 int bt_weight_prefix(int64_t n, const uint32_t* sorted_ids, const int32_t* weights, int64_t* wprefix,
                      void* stream)
 {
+    BT_PROF("bt_weight_prefix", (cudaStream_t)stream);
     bt::WeightIn in{sorted_ids, weights};
     bt::WeightOut out{(long long*)wprefix, n};
     return bt::scan_exclusive(n, nullptr, in, out, (cudaStream_t)stream);
@@ -965,6 +1022,7 @@ int bt_weight_prefix(int64_t n, const uint32_t* sorted_ids, const int32_t* weigh
 int bt_pool_init(int dtype, int dim, const bt_pool* pool, int64_t n, int have_extent,
                  const uint64_t* keys, const double* root_center, int32_t* ctl, void* stream)
 {
+    BT_PROF("bt_pool_init", (cudaStream_t)stream);
     BT_DISPATCH(dtype, dim, pool_init_impl, pool, n, have_extent, (const unsigned long long*)keys,
                 root_center, ctl, (cudaStream_t)stream);
 }
@@ -974,6 +1032,7 @@ int bt_level_step(int dtype, int dim, const bt_pool* pool, const uint64_t* keys,
                   int maxw, int adaptive, int level_restrict, int have_extent, int skip_if_no_regular,
                   double root_extent, int run_decide, void* stream)
 {
+    BT_PROF("bt_level_step", (cudaStream_t)stream);
     BT_DISPATCH(dtype, dim, level_step_impl, pool, (const unsigned long long*)keys,
                 (const long long*)wprefix, ctl, split_list, flag, lo, nboxes, level,
                 bt_max_key_level(dim), maxw, adaptive, level_restrict, have_extent, skip_if_no_regular,
@@ -983,6 +1042,7 @@ int bt_level_step(int dtype, int dim, const bt_pool* pool, const uint64_t* keys,
 int bt_level_restrict(int dtype, int dim, const bt_pool* pool, int32_t* ctl, int built_level,
                       int nboxes_upper, double root_extent, void* stream)
 {
+    BT_PROF("bt_level_restrict", (cudaStream_t)stream);
     BT_DISPATCH(dtype, dim, level_restrict_impl, pool, ctl, built_level, nboxes_upper, root_extent,
                 (cudaStream_t)stream);
 }
@@ -991,6 +1051,7 @@ int bt_finalize_numbering(int dtype, int dim, const bt_pool* pool, int nboxes, i
                           int skip_prune, int32_t* ctl, int32_t* map_old2new, int32_t* src_of_new,
                           int32_t* level_start, void* stream)
 {
+    BT_PROF("bt_finalize_numbering", (cudaStream_t)stream);
     BT_DISPATCH(dtype, dim, finalize_boxes_impl, pool, nboxes, level_restrict, skip_prune, 0, ctl,
                 map_old2new, src_of_new, level_start, 0, 0, 0, nullptr, (cudaStream_t)stream);
 }
@@ -999,6 +1060,7 @@ int bt_gather_boxes(int dtype, int dim, const bt_pool* pool, int have_extent, co
                     const int32_t* map_old2new, int nfinal, int aligned, const bt_box_out* out,
                     void* stream)
 {
+    BT_PROF("bt_gather_boxes", (cudaStream_t)stream);
     BT_DISPATCH(dtype, dim, finalize_boxes_impl, pool, 0, 0, 0, have_extent, nullptr,
                 (int*)map_old2new, (int*)src_of_new, nullptr, 1, nfinal, aligned, out,
                 (cudaStream_t)stream);
@@ -1008,6 +1070,7 @@ int bt_leaf_fixup(int nboxes, const int32_t* box_start, const int32_t* box_count
                   const uint8_t* real_children, uint32_t* ids, int32_t* ctl, int32_t* big_list,
                   int big_cap, int32_t* huge_list, void* stream)
 {
+    BT_PROF("bt_leaf_fixup", (cudaStream_t)stream);
     cudaStream_t s = (cudaStream_t)stream;
     if (nboxes <= 0) return BT_OK;
     bt::leaf_fixup_kernel<<<bt::grid_for((int64_t)nboxes * 32, bt::kFixBlock, 8), bt::kFixBlock, 0, s>>>(
@@ -1021,12 +1084,13 @@ int bt_leaf_fixup(int nboxes, const int32_t* box_start, const int32_t* box_count
 
 int bt_sort_u32_segment(int64_t n, uint32_t* ids, void* stream)
 {
+    BT_PROF("bt_sort_u32_segment", (cudaStream_t)stream);
     // ascending sort of one oversized leaf's ids (keys = ids widened to 64 bit)
     cudaStream_t s = (cudaStream_t)stream;
     if (n < 2) return BT_OK;
     unsigned long long* k = nullptr; unsigned* v = nullptr;
-    BT_CHECK(cudaMallocAsync((void**)&k, sizeof(unsigned long long) * n * 2, s));
-    BT_CHECK(cudaMallocAsync((void**)&v, sizeof(unsigned) * n * 2, s));
+    BT_CHECK(bt::temp_alloc((void**)&k, sizeof(unsigned long long) * n * 2, s));
+    BT_CHECK(bt::temp_alloc((void**)&v, sizeof(unsigned) * n * 2, s));
     bt::widen_ids_kernel<<<bt::grid_for(n, 256), 256, 0, s>>>(ids, (int)n, k);
     BT_LAUNCH_CHECK();
     int in_alt = 0;
@@ -1042,6 +1106,7 @@ int bt_split_sources_targets(int64_t n, int64_t nsources, const uint32_t* sorted
                              int32_t* source_numbers, int32_t* user_source_ids,
                              int32_t* srcntgt_target_ids, int32_t* sorted_target_ids, void* stream)
 {
+    BT_PROF("bt_split_sources_targets", (cudaStream_t)stream);
     bt::SourceIn in{sorted_ids, (unsigned)nsources};
     bt::SourceOut out{sorted_ids, (unsigned)nsources, source_numbers, user_source_ids,
                       srcntgt_target_ids, sorted_target_ids, n};
@@ -1050,6 +1115,7 @@ int bt_split_sources_targets(int64_t n, int64_t nsources, const uint32_t* sorted
 
 int bt_reverse_index(int64_t n, const uint32_t* ids, int32_t* out, void* stream)
 {
+    BT_PROF("bt_reverse_index", (cudaStream_t)stream);
     if (n <= 0) return BT_OK;
     bt::reverse_index_kernel<<<bt::grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(ids, (int)n, out);
     BT_LAUNCH_CHECK();
@@ -1058,7 +1124,8 @@ int bt_reverse_index(int64_t n, const uint32_t* ids, int32_t* out, void* stream)
 
 int bt_permute(int dtype, int dim, const bt_particles* p, const int32_t* from_ids, int64_t n,
                void* const* outs, void* out_radii, void* stream)
-{ BT_DISPATCH(dtype, dim, permute_impl, p, from_ids, (int)n, outs, out_radii, (cudaStream_t)stream); }
+{
+    BT_PROF("bt_permute", (cudaStream_t)stream); BT_DISPATCH(dtype, dim, permute_impl, p, from_ids, (int)n, outs, out_radii, (cudaStream_t)stream); }
 
 int bt_box_info(int nboxes, int sources_are_targets, int have_extent, const int32_t* box_start,
                 const int32_t* box_count, const int32_t* box_nonchild, const uint8_t* has_children,
@@ -1066,6 +1133,7 @@ int bt_box_info(int nboxes, int sources_are_targets, int have_extent, const int3
                 int32_t* src_cumul, int32_t* tgt_starts, int32_t* tgt_nonchild, int32_t* tgt_cumul,
                 uint8_t* box_flags, void* stream)
 {
+    BT_PROF("bt_box_info", (cudaStream_t)stream);
     if (nboxes <= 0) return BT_OK;
     bt::box_info_kernel<<<bt::grid_for(nboxes, 256, 8), 256, 0, (cudaStream_t)stream>>>(
         nboxes, sources_are_targets, have_extent, box_start, box_count, box_nonchild, has_children,
@@ -1079,6 +1147,7 @@ int bt_box_extents(int dtype, int dim, int start, int stop, int aligned, const i
                    const void* box_centers, const int32_t* pstarts, const int32_t* pcounts,
                    void* const* particles, const void* radii, void* bb_min, void* bb_max, void* stream)
 {
+    BT_PROF("bt_box_extents", (cudaStream_t)stream);
     BT_DISPATCH(dtype, dim, box_extents_impl, start, stop, aligned, box_child_ids, box_centers, pstarts,
                 pcounts, particles, radii, bb_min, bb_max, (cudaStream_t)stream);
 }

@@ -81,6 +81,13 @@ typedef struct {
     uint8_t *real_children;
 } bt_box_out;
 
+/* instrumentation used by bench.py: kernels launched so far; optional CUDA-event
+ * timing of every entry point / sort pass on its launching stream */
+long long bt_launch_count(void);
+void bt_prof_enable(int on);
+void bt_prof_reset(void);
+int bt_prof_report(char *buf, int len);   /* "name\tcalls\ttotal_ms" lines */
+
 /* deepest level the 64-bit sort key resolves for `dim` (MaxLevelsExceeded above) */
 int bt_max_key_level(int dim);
 

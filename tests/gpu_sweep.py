@@ -67,7 +67,7 @@ def make_cases(quick=False):
                 base, name="ext-minsrc", ntargets=15000, radii=True,
                 tree={"max_particles_in_box": 30, "stick_out_factor": 0.25},
                 trav={"_from_sep_smaller_min_nsources_cumul": 40}))
-            cases.append(dict(base, name="coincident", n=11, coincident=True,
+            cases.append(dict(base, name="coincident", n=12, coincident=True,
                               tree={"max_particles_in_box": 10}, expect_max_levels=True))
     return cases
 
@@ -75,8 +75,11 @@ def make_cases(quick=False):
 def make_inputs(case):
     dims, dt, n = case["dims"], case["dtype"], case["n"]
     if case.get("coincident"):
+        # 11 coincident points (> max_particles_in_box) and one distinct point so the
+        # bounding box is not degenerate: both implementations must give up
         src = [np.full(n, 0.25 + 0.1 * ax, dtype=dt) for ax in range(dims)]
-        src[0][0] = 1.0   # one distinct point so the bounding box is not degenerate
+        for ax in range(dims):
+            src[ax][0] = 1.0
     elif case.get("uniform"):
         src = uniform_particles(n, dims, dt, seed=15)
     else:

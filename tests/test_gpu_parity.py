@@ -1,0 +1,188 @@
+"""GPU parity tests: the CUDA path (through the public API, which calls the C ABI) against
+the CPU oracle, the committed golden fixtures, and size-independent properties at the
+BASELINE sizes.  Bar: bit-exact integers, 0-ULP floats."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests.golden.make_golden import digest, digest_cases, flatten
+from tests.gpu_sweep import make_cases, run_case
+from tests.invariants import check_against_brute_force, check_traversal, check_tree
+from tests.parity_util import config3_inputs, normal_particles, uniform_particles
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+_CASES = make_cases(quick=False)
+
+
+@pytest.fixture(scope="module")
+def builders(actx):
+    from boxtree_b200 import TreeBuilder
+    return TreeBuilder(actx), {}
+
+
+@pytest.mark.parametrize(
+    "case", _CASES, ids=[f"{c['dims']}d-{np.dtype(c['dtype']).name}-{c['name']}" for c in _CASES])
+def test_parity_sweep(actx, builders, case):
+    tb, travs = builders
+    bad = run_case(dict(case), actx, tb, travs)
+    assert not bad, bad[:10]
+
+
+def _build(actx, src, tkw, vkw):
+    from boxtree_b200 import FMMTraversalBuilder, TreeBuilder
+    dkw = {k: (actx.from_numpy(v) if isinstance(v, np.ndarray) else
+               [actx.from_numpy(x) for x in v] if k == "targets" else v) for k, v in tkw.items()}
+    tree, _ = TreeBuilder(actx)(actx, [actx.from_numpy(s) for s in src], **dkw)
+    ctor = {k: vkw[k] for k in ("well_sep_is_n_away", "from_sep_smaller_crit") if k in vkw}
+    trav, _ = FMMTraversalBuilder(actx, **ctor)(actx, tree)
+    return tree, trav
+
+
+def test_golden_config1(actx):
+    src, tkw, vkw = digest_cases()["config1_2d_1e4"]
+    tree, trav = _build(actx, src, tkw, vkw)
+    got = flatten(actx.to_numpy(tree), actx.to_numpy(trav))
+    want = np.load(os.path.join(GOLDEN, "config1_2d_1e4.npz"))
+    assert set(got) == set(want.files)
+    for k in want.files:
+        assert got[k].dtype == want[k].dtype and got[k].shape == want[k].shape, k
+        assert np.array_equal(got[k].view(np.uint8), want[k].view(np.uint8)), k
+
+
+@pytest.mark.parametrize("name", sorted(digest_cases()))
+def test_golden_digests(actx, name):
+    want = json.load(open(os.path.join(GOLDEN, "digests.json")))[name]
+    src, tkw, vkw = digest_cases()[name]
+    tree, trav = _build(actx, src, tkw, vkw)
+    got = {k: digest(v) for k, v in flatten(actx.to_numpy(tree), actx.to_numpy(trav)).items()}
+    assert got == want
+
+
+def test_config2_full_size_parity(actx):
+    """BASELINE config 2 at full size (3-D, 1e6 uniform fp64): every array vs the oracle."""
+    from oracle.traversal import build_traversal
+    from oracle.tree_build import build_tree
+    from tests.parity_util import trav_mismatches, tree_mismatches
+    src = uniform_particles(1_000_000, 3, np.float64)
+    tree, trav = _build(actx, src, dict(max_particles_in_box=30), {})
+    rt = build_tree(src, max_particles_in_box=30)
+    assert not tree_mismatches(rt, actx.to_numpy(tree))
+    assert not trav_mismatches(build_traversal(rt), actx.to_numpy(trav))
+
+
+def test_config3_properties_full_size(actx):
+    """BASELINE config 3 at full size (1e7 points): size-independent properties on device."""
+    import torch
+    ns = nt = 5_000_000
+    src, tgt, radii = config3_inputs(ns, nt)
+    tkw = dict(max_particles_in_box=30, targets=tgt, target_radii=radii, stick_out_factor=0.25,
+               extent_norm="linf", kind="adaptive-level-restricted")
+    tree, trav = _build(actx, src, tkw, {})
+    dsrc = [actx.from_numpy(s) for s in src]
+    dtgt = [actx.from_numpy(t) for t in tgt]
+    usi = tree.user_source_ids.long()
+    sti = tree.sorted_target_ids.long()
+    # orderings are permutations and the permuted coordinates are exact copies
+    assert int(torch.bincount(usi, minlength=ns).max()) == 1 and usi.numel() == ns
+    assert int(torch.bincount(sti, minlength=nt).max()) == 1 and sti.numel() == nt
+    for ax in range(3):
+        assert torch.equal(tree.sources[ax], dsrc[ax][usi])
+        assert torch.equal(tree.targets[ax][sti], dtgt[ax])
+    assert torch.equal(tree.target_radii[sti], actx.from_numpy(radii))
+    nb = tree.nboxes
+    lev = tree.box_levels.long()
+    par = tree.box_parent_ids.long()
+    assert bool((lev[par[1:]] + 1 == lev[1:]).all())
+    assert bool((lev[1:] >= lev[:-1]).all())                       # level-major numbering
+    ls = tree.level_start_box_nrs.long()
+    assert int(ls[0]) == 0 and int(ls[-1]) == nb
+    # counts: root holds everything; nonchild + children's cumul == cumul
+    assert int(tree.box_source_counts_cumul[0]) == ns and int(tree.box_target_counts_cumul[0]) == nt
+    ch = tree.box_child_ids[:, :nb].long()
+    for cum, non in ((tree.box_source_counts_cumul, tree.box_source_counts_nonchild),
+                     (tree.box_target_counts_cumul, tree.box_target_counts_nonchild)):
+        kid = torch.where(ch != 0, cum.long()[ch], torch.zeros_like(ch)).sum(0)
+        assert bool((non.long() + kid == cum.long()).all())
+    # 2:1 balance of the level-restricted tree through list 1 (adjacent leaves differ by <= 1
+    # level is only promised for boxes without own extent-particles; check colleagues instead):
+    cs, cl = trav.same_level_non_well_sep_boxes_starts.long(), \
+        trav.same_level_non_well_sep_boxes_lists.long()
+    rows = torch.repeat_interleave(torch.arange(nb, device=cs.device), cs[1:] - cs[:-1])
+    assert bool((lev[rows] == lev[cl]).all())
+    # list 2: same level, never adjacent
+    tp = trav.target_or_target_parent_boxes.long()
+    s2, l2 = trav.from_sep_siblings_starts.long(), trav.from_sep_siblings_lists.long()
+    r2 = tp[torch.repeat_interleave(torch.arange(tp.numel(), device=s2.device), s2[1:] - s2[:-1])]
+    assert bool((lev[r2] == lev[l2]).all())
+    cen = tree.box_centers[:, :nb]
+    dist = (cen[:, r2] - cen[:, l2]).abs().amax(0)
+    size = float(tree.root_extent) * 0.5 ** lev[r2].double()
+    assert bool((dist > 1.5 * size).all())
+
+
+def test_invariants_and_brute_force_on_cuda_result(actx):
+    src = normal_particles(2500, 3, np.float64)
+    tree, trav = _build(actx, src, dict(max_particles_in_box=10), {})
+    tree, trav = actx.to_numpy(tree), actx.to_numpy(trav)
+    check_tree(tree, src, max_particles_in_box=10)
+    check_traversal(tree, trav, True)
+    check_against_brute_force(tree, trav)
+
+
+def test_constant_one_fmm_on_cuda_result(actx):
+    from oracle.fmm import constant_one_fmm
+    src, tgt, radii = config3_inputs(30000, 30000)
+    tkw = dict(max_particles_in_box=30, targets=tgt, target_radii=radii, stick_out_factor=0.25,
+               extent_norm="linf", kind="adaptive-level-restricted")
+    tree, trav = _build(actx, src, tkw, {})
+    merged = trav.merge_close_lists(actx)
+    tree, trav, merged = actx.to_numpy(tree), actx.to_numpy(trav), actx.to_numpy(merged)
+    w = np.random.default_rng(1).integers(1, 5, 30000).astype(np.float64)
+    assert np.all(constant_one_fmm(tree, trav, w) == w.sum())
+    assert np.all(constant_one_fmm(tree, merged, w) == w.sum())
+
+
+def test_error_behaviour(actx):
+    from boxtree_b200 import FMMTraversalBuilder, MaxLevelsExceeded, TreeBuilder
+    tb = TreeBuilder(actx)
+    src = [actx.from_numpy(s) for s in normal_particles(100, 2, np.float64)]
+    with pytest.raises(ValueError):
+        tb(actx, src, kind="bogus", max_particles_in_box=10)
+    with pytest.raises(ValueError):
+        tb(actx, src)
+    with pytest.raises(ValueError):
+        tb(actx, src, max_particles_in_box=10, refine_weights=actx.from_numpy(
+            np.ones(100, np.int32)), max_leaf_refine_weight=5)
+    with pytest.raises(ValueError):
+        tb(actx, src, source_radii=actx.from_numpy(np.ones(100)), max_particles_in_box=10)
+    with pytest.raises(ValueError):
+        tb(actx, src, targets=src, target_radii=actx.from_numpy(np.ones(100)),
+           max_particles_in_box=10)
+    with pytest.raises(TypeError):
+        tb(actx, src, targets=src, target_radii=actx.from_numpy(np.ones(100, np.float32)),
+           stick_out_factor=0.1, max_particles_in_box=10)
+    with pytest.raises(TypeError):
+        tb(actx, src, refine_weights=actx.from_numpy(np.ones(100, np.int64)),
+           max_leaf_refine_weight=5)
+    with pytest.raises(ValueError):
+        tb(actx, src, refine_weights=actx.from_numpy(np.full(100, 7, np.int32)),
+           max_leaf_refine_weight=5)
+    with pytest.warns(DeprecationWarning):
+        tb(actx, src, max_particles_in_box=10, allocator=object())
+    tree, _ = tb(actx, src, max_particles_in_box=10, skip_prune=True)
+    with pytest.raises(ValueError):
+        FMMTraversalBuilder(actx)(actx, tree)
+    with pytest.raises(ValueError):
+        FMMTraversalBuilder(actx, from_sep_smaller_crit="bogus")(
+            actx, tb(actx, src, max_particles_in_box=10)[0])
+    pts = np.array([0.5] * 11 + [1.0])
+    with pytest.raises(MaxLevelsExceeded):
+        tb(actx, [actx.from_numpy(pts), actx.from_numpy(pts.copy())], max_particles_in_box=10)
+    tree_se, _ = tb(actx, src, targets=src, source_radii=actx.from_numpy(np.full(100, 1e-3)),
+                    stick_out_factor=0.1, max_particles_in_box=10)
+    with pytest.raises(NotImplementedError):
+        FMMTraversalBuilder(actx)(actx, tree_se)

@@ -1,0 +1,172 @@
+"""CPU tests of the oracle (the restatement of the reference algorithm): the reference's own
+structural tests, the constant-one FMM completeness test, an independent brute-force list
+definition, the committed golden fixtures, and error behaviour."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle.fmm import constant_one_fmm
+from oracle.traversal import build_traversal, merge_close_lists
+from oracle.tree_build import MaxLevelsExceeded, build_tree
+from tests.golden.make_golden import digest, digest_cases, flatten
+from tests.invariants import check_against_brute_force, check_traversal, check_tree
+from tests.parity_util import normal_particles
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("case", [
+    dict(n=4, max_particles_in_box=30),                      # test_tree.py:236
+    dict(n=50, max_particles_in_box=30),                     # :247
+    dict(n=20000, max_particles_in_box=30, skip_prune=True),  # :258
+    dict(n=20000, max_particles_in_box=30, nboxes_guess=5),   # :270
+    dict(n=20000, max_particles_in_box=5),                   # :282
+    dict(n=20000, max_particles_in_box=30),                  # :294
+    dict(n=5000, max_particles_in_box=30, kind="non-adaptive"),  # :325
+    dict(n=20000, max_particles_in_box=30, kind="adaptive-level-restricted"),
+])
+def test_tree_invariants(dims, dtype, case):
+    case = dict(case)
+    n = case.pop("n")
+    src = normal_particles(n, dims, dtype)
+    tree = build_tree(src, debug=True, **case)
+    check_tree(tree, src, max_particles_in_box=case["max_particles_in_box"])
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_tree_refine_weights(dims):   # test_tree.py:305
+    n = 20000
+    src = normal_particles(n, dims, np.float64)
+    w = np.random.default_rng(10).integers(1, 10, n, dtype=np.int32)
+    tree = build_tree(src, refine_weights=w, max_leaf_refine_weight=100, debug=True)
+    check_tree(tree, src, refine_weights=w, max_leaf_refine_weight=100)
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_source_target_tree(dims):    # test_tree.py:341
+    src = normal_particles(20000, dims, np.float64, seed=12)
+    tgt = normal_particles(30000, dims, np.float64, seed=19)
+    tree = build_tree(src, targets=tgt, max_particles_in_box=10, debug=True)
+    check_tree(tree, src, unsorted_targets=tgt)
+    nb = tree.nboxes
+    assert np.all(tree.box_source_counts_cumul[:nb] + tree.box_target_counts_cumul[:nb] > 0)
+
+
+def test_max_levels_exceeded():       # test_tree.py:1103-1112
+    pts = [np.zeros(11), np.zeros(11)]
+    pts[0][0] = 1.0
+    with pytest.raises(MaxLevelsExceeded):
+        build_tree([np.array([0.5] * 11 + [1.0]), np.array([0.5] * 11 + [1.0])],
+                   max_particles_in_box=10)
+
+
+def test_argument_errors():
+    src = normal_particles(100, 2, np.float64)
+    with pytest.raises(ValueError):
+        build_tree(src, kind="bogus", max_particles_in_box=10)
+    with pytest.raises(ValueError):
+        build_tree(src)
+    with pytest.raises(ValueError):
+        build_tree(src, max_particles_in_box=10, refine_weights=np.ones(100, np.int32),
+                   max_leaf_refine_weight=5)
+    with pytest.raises(ValueError):
+        build_tree(src, source_radii=np.ones(100), max_particles_in_box=10)
+    with pytest.raises(ValueError):
+        build_tree(src, targets=src, target_radii=np.ones(100), max_particles_in_box=10)
+    tree = build_tree(src, max_particles_in_box=10, skip_prune=True)
+    with pytest.raises(ValueError):
+        build_traversal(tree)
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+@pytest.mark.parametrize("sources_are_targets", [True, False])
+def test_traversal_connectivity(dims, sources_are_targets):   # test_traversal.py:58
+    src = normal_particles(20000, dims, np.float64)
+    tgt = None if sources_are_targets else normal_particles(30000, dims, np.float64, seed=18)
+    tree = build_tree(src, targets=tgt, max_particles_in_box=30, debug=True)
+    trav = build_traversal(tree)
+    check_traversal(tree, trav, sources_are_targets)
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+@pytest.mark.parametrize("kind", ["adaptive", "adaptive-level-restricted"])
+def test_lists_against_brute_force(dims, kind):
+    src = normal_particles(2500, dims, np.float64)
+    tree = build_tree(src, max_particles_in_box=10, kind=kind)
+    check_against_brute_force(tree, build_traversal(tree))
+
+
+FMM_CASES = [   # modelled on test/test_fmm.py:141-164 (dims, nsources, ntargets, extents, ...)
+    dict(dims=1, ns=3000, nt=0),
+    dict(dims=2, ns=5000, nt=0),
+    dict(dims=3, ns=5000, nt=0),
+    dict(dims=2, ns=5000, nt=4000),
+    dict(dims=3, ns=5000, nt=4000),
+    dict(dims=2, ns=5000, nt=4000, radii=True, norm="linf", crit="static_linf"),
+    dict(dims=2, ns=5000, nt=4000, radii=True, norm="linf", crit="precise_linf"),
+    dict(dims=2, ns=5000, nt=4000, radii=True, norm="l2", crit="static_l2"),
+    dict(dims=3, ns=5000, nt=4000, radii=True, norm="linf", crit="static_linf"),
+    dict(dims=3, ns=5000, nt=4000, radii=True, norm="linf", crit="precise_linf"),
+    dict(dims=3, ns=5000, nt=4000, radii=True, norm="l2", crit="static_l2"),
+    dict(dims=3, ns=5000, nt=4000, radii=True, norm="l2", crit="precise_linf"),
+    dict(dims=3, ns=5000, nt=4000, radii=True, norm="linf", crit=None,
+         kind="adaptive-level-restricted"),
+    dict(dims=3, ns=5000, nt=0, kind="adaptive-level-restricted"),
+]
+
+
+@pytest.mark.parametrize("well_sep_is_n_away", [1, 2])
+@pytest.mark.parametrize("case", FMM_CASES)
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_constant_one_fmm(case, well_sep_is_n_away, dtype):   # test/test_fmm.py:166-391
+    dims, ns, nt = case["dims"], case["ns"], case["nt"]
+    src = normal_particles(ns, dims, dtype, seed=12)
+    kw = dict(max_particles_in_box=30, kind=case.get("kind", "adaptive"))
+    if nt:
+        kw["targets"] = [0.7 * t for t in normal_particles(nt, dims, dtype, seed=19)]
+        if case.get("radii"):
+            rng = np.random.default_rng(13)
+            kw.update(target_radii=(0.1 * 2 ** rng.uniform(-10, 0, nt)).astype(dtype),
+                      stick_out_factor=0.25, extent_norm=case["norm"])
+    tree = build_tree(src, debug=True, **kw)
+    trav = build_traversal(tree, well_sep_is_n_away=well_sep_is_n_away,
+                           from_sep_smaller_crit=case.get("crit"))
+    weights = np.random.default_rng(1).integers(1, 5, ns).astype(np.float64)
+    assert np.all(constant_one_fmm(tree, trav, weights) == weights.sum())
+    if case.get("radii"):
+        assert np.all(constant_one_fmm(tree, merge_close_lists(trav), weights) == weights.sum())
+
+
+def test_min_nsources_threshold():    # test/test_fmm.py:618-665
+    src = normal_particles(5000, 3, np.float64, seed=12)
+    tgt = normal_particles(4000, 3, np.float64, seed=19)
+    radii = (0.05 * 2 ** np.random.default_rng(13).uniform(-10, 0, 4000))
+    tree = build_tree(src, targets=tgt, target_radii=radii, stick_out_factor=0.25,
+                      max_particles_in_box=30)
+    trav = build_traversal(tree, _from_sep_smaller_min_nsources_cumul=40)
+    assert np.all(constant_one_fmm(tree, trav, np.ones(5000)) == 5000)
+
+
+def test_golden_config1():
+    src, tkw, vkw = digest_cases()["config1_2d_1e4"]
+    tree = build_tree(src, **tkw)
+    trav = build_traversal(tree, **vkw)
+    got = flatten(tree, trav)
+    want = np.load(os.path.join(GOLDEN, "config1_2d_1e4.npz"))
+    assert set(got) == set(want.files)
+    for k in want.files:
+        assert got[k].dtype == want[k].dtype and got[k].shape == want[k].shape, k
+        assert np.array_equal(got[k].view(np.uint8), want[k].view(np.uint8)), k
+
+
+def test_golden_digests():
+    want = json.load(open(os.path.join(GOLDEN, "digests.json")))
+    for name, (src, tkw, vkw) in digest_cases().items():
+        tree = build_tree(src, **tkw)
+        trav = build_traversal(tree, **vkw)
+        got = {k: digest(v) for k, v in flatten(tree, trav).items()}
+        assert got == want[name], name
