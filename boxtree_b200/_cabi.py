@@ -68,6 +68,16 @@ class bt_list3_args(C.Structure):
                 ("box_source_counts_cumul", vp), ("min_nsources_cumul", C.c_int32)]
 
 
+class bt_heavy_ws(C.Structure):
+    _fields_ = [("walk_budget", C.c_int32), ("row_heavy", vp), ("heavy_rows", vp), ("hctl", vp),
+                ("heavy_total", vp), ("frontier", vp * 2), ("frontier_cap", C.c_int64),
+                ("dfs_rank", vp), ("ekeys", vp * 2), ("evals", vp * 2), ("ecap", C.c_int64)]
+
+
+HCTL_SIZE = 64
+HCTL_NHEAVY = 0
+HCTL_OVERFLOW = 1
+
 # every exported symbol of include/boxtree_b200.h with its argument types
 _i, _i64, _d = C.c_int, C.c_int64, C.c_double
 _P = C.POINTER
@@ -94,7 +104,10 @@ SIGNATURES = {
     "bt_trav_level_starts": [_i, vp, vp, _i, vp, vp],
     "bt_trav_build_list": [_i, _i, _i, _P(bt_tree_view), _P(bt_list_args), _i, vp, vp, vp, vp,
                            vp, vp],
-    "bt_trav_list3": [_i, _i, _P(bt_tree_view), _P(bt_list3_args), _i, vp, vp, vp, vp, vp],
+    "bt_trav_list3": [_i, _i, _P(bt_tree_view), _P(bt_list3_args), _i, vp, vp, vp, vp,
+                      _P(bt_heavy_ws), _i64, vp],
+    "bt_trav_list1": [_i, _i, _P(bt_tree_view), vp, _i, vp, vp, vp, _P(bt_heavy_ws), _i64, vp],
+    "bt_trav_dfs_rank": [_i, _i, _i, _i, vp, vp, vp, vp, vp],
     "bt_trav_list3_compress": [_i, _i, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "bt_trav_merge_lists": [_i, _i, vp, _i, _P(vp), _P(vp), vp, vp, vp, vp],
     "bt_gather_i32": [_i64, vp, vp, vp, vp],

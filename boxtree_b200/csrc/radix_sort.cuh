@@ -70,7 +70,7 @@ __device__ __forceinline__ unsigned block_excl_scan_256(unsigned v, unsigned* tm
 }
 
 // histograms of all passes in one read of the keys
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 rs_histogram_kernel(const unsigned long long* __restrict__ keys, int64_t n, int begin_bit,
                     int end_bit, int npasses, unsigned* __restrict__ ghist)
 {

@@ -10,6 +10,7 @@
 // walk nlevels(+1) times, traversal.py:2203-2228).
 #include "common.cuh"
 #include "scan.cuh"
+#include "radix_sort.cuh"
 #include "../../include/boxtree_b200.h"
 
 namespace bt {
@@ -122,26 +123,41 @@ __device__ __forceinline__ void gen_colleagues(const TreeView<T, DIM>& t, const 
 }
 
 // ---- b4 list 1: traversal.py:470-550 ---------------------------------------
+constexpr int kVisitPush = 1, kVisitEmit = 2, kVisitClose = 4;
+
+// one child visit of the list-1 walk (traversal.py:508-539)
+template <typename T, int DIM>
+__device__ __forceinline__ int list1_visit(const TreeView<T, DIM>& t, const T* rad, const T* center,
+                                           int level, int wb)
+{
+    if (!wb) return 0;
+    T wc[DIM]; t.center(wb, wc);
+    if (!adj_nbhd<T, DIM>(rad, center, level, (T)1, wc, t.levels[wb])) return 0;
+    const unsigned char fl = t.flags[wb];
+    return ((fl & BT_BOX_IS_SOURCE_BOX) ? kVisitEmit : 0) |
+           ((fl & BT_BOX_HAS_SOURCE_CHILD_BOXES) ? kVisitPush : 0);
+}
+
+// returns false when the walk exceeded `budget` child visits (row becomes "heavy")
 template <typename T, int DIM, class E>
-__device__ __forceinline__ void gen_list1(const TreeView<T, DIM>& t, const T* rad, int box_id, E& e)
+__device__ __forceinline__ bool gen_list1(const TreeView<T, DIM>& t, const T* rad, int box_id, E& e,
+                                          int budget)
 {
     constexpr int NB = 1 << DIM;
     T center[DIM]; t.center(box_id, center);
     const int level = t.levels[box_id];
     if (t.flags[0] & BT_BOX_IS_SOURCE_BOX) e.e0(0);
     Walk w; w.init(0);
+    int visits = 0;
     while (w.cont) {
+        if (++visits > budget) return false;
         const int wb = t.child(w.parent, w.mnr);
-        if (wb) {
-            T wc[DIM]; t.center(wb, wc);
-            if (adj_nbhd<T, DIM>(rad, center, level, (T)1, wc, t.levels[wb])) {
-                const unsigned char fl = t.flags[wb];
-                if (fl & BT_BOX_IS_SOURCE_BOX) e.e0(wb);
-                if (fl & BT_BOX_HAS_SOURCE_CHILD_BOXES) { w.push(wb); continue; }
-            }
-        }
+        const int act = list1_visit<T, DIM>(t, rad, center, level, wb);
+        if (act & kVisitEmit) e.e0(wb);
+        if (act & kVisitPush) { w.push(wb); continue; }
         w.template advance<NB>();
     }
+    return true;
 }
 
 // ---- b5 list 2: traversal.py:556-601 ---------------------------------------
@@ -221,7 +237,7 @@ __device__ __forceinline__ void gen_list4(const TreeView<T, DIM>& t, const T* ra
     }
 }
 
-// generic row kernel; KIND: 0 colleagues, 1 list1, 2 list2, 4 list4
+// generic row kernel; KIND: 0 colleagues, 2 list2, 4 list4 (list 1 and 3 have their own)
 template <typename T, int DIM, int KIND, bool FILL>
 __global__ void __launch_bounds__(kTravBlock)
 list_kernel(TreeView<T, DIM> t, const int* __restrict__ row_boxes, const int* __restrict__ coll_starts,
@@ -237,13 +253,11 @@ list_kernel(TreeView<T, DIM> t, const int* __restrict__ row_boxes, const int* __
         if (FILL) {
             FillEmit e{lists + starts[r], close_lists ? close_lists + close_starts[r] : nullptr};
             if (KIND == 0) gen_colleagues<T, DIM>(t, rad, box, e);
-            if (KIND == 1) gen_list1<T, DIM>(t, rad, box, e);
             if (KIND == 2) gen_list2<T, DIM>(t, rad, coll_starts, coll_lists, box, e);
             if (KIND == 4) gen_list4<T, DIM>(t, rad, coll_starts, coll_lists, with_extent, stick_out_factor, box, e);
         } else {
             CountEmit e;
             if (KIND == 0) gen_colleagues<T, DIM>(t, rad, box, e);
-            if (KIND == 1) gen_list1<T, DIM>(t, rad, box, e);
             if (KIND == 2) gen_list2<T, DIM>(t, rad, coll_starts, coll_lists, box, e);
             if (KIND == 4) gen_list4<T, DIM>(t, rad, coll_starts, coll_lists, with_extent, stick_out_factor, box, e);
             starts[r] = e.c0;
@@ -286,7 +300,6 @@ static int build_list_impl(int kind, int phase, const bt_tree_view* tv, const bt
         if (phase == 0) {
             switch (kind) {
             case 0: BT_LAUNCH_LIST(0, false); break;
-            case 1: BT_LAUNCH_LIST(1, false); break;
             case 2: BT_LAUNCH_LIST(2, false); break;
             case 4: BT_LAUNCH_LIST(4, false); break;
             default: return BT_ERR_BAD_ARG;
@@ -294,7 +307,6 @@ static int build_list_impl(int kind, int phase, const bt_tree_view* tv, const bt
         } else {
             switch (kind) {
             case 0: BT_LAUNCH_LIST(0, true); break;
-            case 1: BT_LAUNCH_LIST(1, true); break;
             case 2: BT_LAUNCH_LIST(2, true); break;
             case 4: BT_LAUNCH_LIST(4, true); break;
             default: return BT_ERR_BAD_ARG;
@@ -318,80 +330,101 @@ struct List3Args {
     const T* bb_min; const T* bb_max; const int* box_source_counts_cumul; int min_nsources_cumul;
 };
 
-// E must provide append(level, box) and close(box)
-template <typename T, int DIM, class E>
-__device__ __forceinline__ void gen_list3(const TreeView<T, DIM>& t, const T* rad, const List3Args<T, DIM>& x,
-                                          int tgt_box_id, E& e)
+// per-target-box constants of the list-3 walk (traversal.py:614-630)
+template <typename T, int DIM>
+struct L3Ctx { T tc[DIM]; int tgt_level; T stickout; T ext_center[DIM]; T radii_vec[DIM]; };
+
+template <typename T, int DIM>
+__device__ __forceinline__ void l3_make_ctx(const TreeView<T, DIM>& t, const T* rad,
+                                            const List3Args<T, DIM>& x, int tgt_box_id, L3Ctx<T, DIM>& c)
 {
-    constexpr int NB = 1 << DIM;
-    T tc[DIM]; t.center(tgt_box_id, tc);
-    const int tgt_level = t.levels[tgt_box_id];
-    T tgt_stickout_l_inf_rad = 0, ext_center[DIM], radii_vec[DIM];
+    t.center(tgt_box_id, c.tc);
+    c.tgt_level = t.levels[tgt_box_id];
+    c.stickout = 0;
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) { c.ext_center[a] = 0; c.radii_vec[a] = 0; }
     if (x.targets_have_extent) {
         if (x.crit == 0 || x.crit == 2)
-            tgt_stickout_l_inf_rad = (1 + x.stick_out_factor) * rad[tgt_level];
+            c.stickout = (1 + x.stick_out_factor) * rad[c.tgt_level];
         else {   // load_true_box_extent, traversal.py:177-198
 #pragma unroll
             for (int a = 0; a < DIM; ++a) {
                 const T mn = x.bb_min[a * t.aligned + tgt_box_id], mx = x.bb_max[a * t.aligned + tgt_box_id];
-                ext_center[a] = ((T)0.5) * (mn + mx);
-                radii_vec[a] = ((T)0.5) * (mx - mn);
+                c.ext_center[a] = ((T)0.5) * (mn + mx);
+                c.radii_vec[a] = ((T)0.5) * (mx - mn);
             }
         }
     }
-    const bool close_lists_exist = x.sources_have_extent || x.targets_have_extent;
+}
+
+// one child visit of the list-3 walk (traversal.py:673-870), all source levels at once:
+// kVisitEmit appends wb to the list of source level levels[wb], kVisitClose to list 3 close.
+template <typename T, int DIM>
+__device__ __forceinline__ int list3_visit(const TreeView<T, DIM>& t, const T* rad,
+                                           const List3Args<T, DIM>& x, const L3Ctx<T, DIM>& c, int wb)
+{
+    const unsigned char cfl = t.flags[wb];
+    if (!(wb && (cfl & (BT_BOX_IS_SOURCE_BOX | BT_BOX_HAS_SOURCE_CHILD_BOXES)))) return 0;
+    T wc[DIM]; t.center(wb, wc);
+    const int walk_level = t.levels[wb];
+    if (adj_nbhd<T, DIM>(rad, c.tc, c.tgt_level, (T)1, wc, walk_level))
+        return (cfl & BT_BOX_HAS_SOURCE_CHILD_BOXES) ? kVisitPush : 0;
     const T two_minus = (2 - 8 * CoordTraits<T>::eps());
+    bool meets;
+    if (!x.targets_have_extent) meets = true;
+    else if (x.crit == 0) {
+        const T source_rad = rad[walk_level];
+        T d = 0;
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) d = fmax(d, fabs(c.tc[a] - wc[a]) - c.stickout - source_rad);
+        meets = d >= two_minus * source_rad;
+    } else if (x.crit == 1) {
+        const T source_rad = rad[walk_level];
+        T d = 0;
+#pragma unroll
+        for (int a = 0; a < DIM; ++a)
+            d = fmax(d, fabs(c.ext_center[a] - wc[a]) - c.radii_vec[a] - source_rad);
+        meets = d >= two_minus * source_rad;
+    } else {
+        const T source_rad = rad[walk_level];
+        T l2sq = 0;
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) l2sq = l2sq + (c.tc[a] - wc[a]) * (c.tc[a] - wc[a]);
+        const T rhs = sqrt(l2sq) - sqrt((T)DIM) * c.stickout - source_rad;
+        meets = (two_minus * source_rad <= rhs);
+    }
+    const bool close_lists_exist = x.sources_have_extent || x.targets_have_extent;
+    const bool force_close = close_lists_exist && (x.box_source_counts_cumul[wb] < x.min_nsources_cumul);
+    if (meets && !force_close) return kVisitEmit;
+    if (!close_lists_exist) return 0;
+    return ((cfl & BT_BOX_IS_SOURCE_BOX) ? kVisitClose : 0) |
+           ((cfl & BT_BOX_HAS_SOURCE_CHILD_BOXES) ? kVisitPush : 0);
+}
+
+// E must provide append(level, box) and close(box); false = budget exceeded
+template <typename T, int DIM, class E>
+__device__ __forceinline__ bool gen_list3(const TreeView<T, DIM>& t, const T* rad, const List3Args<T, DIM>& x,
+                                          int tgt_box_id, E& e, int budget)
+{
+    constexpr int NB = 1 << DIM;
+    L3Ctx<T, DIM> c; l3_make_ctx<T, DIM>(t, rad, x, tgt_box_id, c);
+    int visits = 0;
     const int s = x.coll_starts[tgt_box_id], en = x.coll_starts[tgt_box_id + 1];
     for (int i = s; i < en; ++i) {
         const int same_lev_nws_box = x.coll_lists[i];
         if (same_lev_nws_box == tgt_box_id) continue;
         Walk w; w.init(same_lev_nws_box);
         while (w.cont) {
+            if (++visits > budget) return false;
             const int wb = t.child(w.parent, w.mnr);
-            const unsigned char cfl = t.flags[wb];
-            if (wb && (cfl & (BT_BOX_IS_SOURCE_BOX | BT_BOX_HAS_SOURCE_CHILD_BOXES))) {
-                T wc[DIM]; t.center(wb, wc);
-                const int walk_level = t.levels[wb];
-                if (adj_nbhd<T, DIM>(rad, tc, tgt_level, (T)1, wc, walk_level)) {
-                    // single walk for all source levels: always descend
-                    if (cfl & BT_BOX_HAS_SOURCE_CHILD_BOXES) { w.push(wb); continue; }
-                } else {
-                    bool meets;
-                    if (!x.targets_have_extent) meets = true;
-                    else if (x.crit == 0) {
-                        const T source_rad = rad[walk_level];
-                        T d = 0;
-#pragma unroll
-                        for (int a = 0; a < DIM; ++a)
-                            d = fmax(d, fabs(tc[a] - wc[a]) - tgt_stickout_l_inf_rad - source_rad);
-                        meets = d >= two_minus * source_rad;
-                    } else if (x.crit == 1) {
-                        const T source_rad = rad[walk_level];
-                        T d = 0;
-#pragma unroll
-                        for (int a = 0; a < DIM; ++a)
-                            d = fmax(d, fabs(ext_center[a] - wc[a]) - radii_vec[a] - source_rad);
-                        meets = d >= two_minus * source_rad;
-                    } else {
-                        const T source_rad = rad[walk_level];
-                        T l2sq = 0;
-#pragma unroll
-                        for (int a = 0; a < DIM; ++a) l2sq = l2sq + (tc[a] - wc[a]) * (tc[a] - wc[a]);
-                        const T rhs = sqrt(l2sq) - sqrt((T)DIM) * tgt_stickout_l_inf_rad - source_rad;
-                        meets = (two_minus * source_rad <= rhs);
-                    }
-                    const bool force_close = close_lists_exist &&
-                        (x.box_source_counts_cumul[wb] < x.min_nsources_cumul);
-                    if (meets && !force_close) e.append(walk_level, wb);
-                    else if (close_lists_exist) {
-                        if (cfl & BT_BOX_IS_SOURCE_BOX) e.close(wb);
-                        if (cfl & BT_BOX_HAS_SOURCE_CHILD_BOXES) { w.push(wb); continue; }
-                    }
-                }
-            }
+            const int act = list3_visit<T, DIM>(t, rad, x, c, wb);
+            if (act & kVisitEmit) e.append(t.levels[wb], wb);
+            if (act & kVisitClose) e.close(wb);
+            if (act & kVisitPush) { w.push(wb); continue; }
             w.template advance<NB>();
         }
     }
+    return true;
 }
 
 struct L3Count {
@@ -405,10 +438,235 @@ struct L3Fill {
     __device__ __forceinline__ void close(int v) { lists[cur[nlevels]++] = v; }
 };
 
+// ---- heavy rows -------------------------------------------------------------
+// A row whose walk needs more than `walk_budget` child visits (an upper-level box with its
+// own targets can have a list 1 of ~1e5..1e6 entries) is taken out of the one-thread-per-row
+// kernels.  All heavy rows are expanded together by a level-synchronous BFS over the same
+// child visits (same predicates, hence the same set of appended boxes); the append ORDER of
+// the reference's depth-first, Morton-ordered walk is the global DFS pre-order of the tree,
+// so the appended boxes are sorted by (list, row, pre-order rank) with the one-sweep radix
+// sort and copied to their CSR positions.
+struct HeavyWs {
+    int budget; unsigned char* row_heavy; int* heavy_rows; int* hctl; long long* heavy_total;
+    unsigned long long* frontier[2]; long long frontier_cap; const int* dfs_rank;
+    unsigned long long* ekeys[2]; unsigned* evals[2]; long long ecap;
+};
+constexpr int kHctlNHeavy = 0, kHctlOverflow = 1, kHctlECount = 2, kHctlFrontier = 8;
+
+static HeavyWs make_ws(const bt_heavy_ws* w)
+{
+    HeavyWs h;
+    h.budget = w->walk_budget; h.row_heavy = w->row_heavy; h.heavy_rows = w->heavy_rows;
+    h.hctl = w->hctl; h.heavy_total = (long long*)w->heavy_total;
+    h.frontier[0] = (unsigned long long*)w->frontier[0]; h.frontier[1] = (unsigned long long*)w->frontier[1];
+    h.frontier_cap = w->frontier_cap; h.dfs_rank = w->dfs_rank;
+    h.ekeys[0] = (unsigned long long*)w->ekeys[0]; h.ekeys[1] = (unsigned long long*)w->ekeys[1];
+    h.evals[0] = w->evals[0]; h.evals[1] = w->evals[1]; h.ecap = w->ecap;
+    return h;
+}
+
+__device__ __forceinline__ int bits_for(int n)   // bits needed for values in [0, n)
+{ return n <= 1 ? 1 : 32 - __clz(n - 1); }
+
+// warp-aggregated append: returns the slot of this lane's item (or -1)
+__device__ __forceinline__ long long warp_append(bool want, int* counter)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (!m) return -1;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return want ? (long long)base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u)) : -1;
+}
+
+// light pass of list 1: one thread per row, budgeted
+template <typename T, int DIM, bool FILL>
+__global__ void __launch_bounds__(kTravBlock)
+list1_kernel(TreeView<T, DIM> t, const int* __restrict__ target_boxes, int nrows, int* __restrict__ starts,
+             int* __restrict__ lists, HeavyWs ws)
+{
+    __shared__ T rad[kMaxWalkLevels];
+    fill_rad_table(rad, t.root_extent);
+    const int stride = gridDim.x * blockDim.x;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += stride) {
+        const int box = target_boxes[r];
+        if (FILL) {
+            if (ws.row_heavy[r]) continue;
+            FillEmit e{lists + starts[r], nullptr};
+            gen_list1<T, DIM>(t, rad, box, e, 0x7fffffff);
+        } else {
+            CountEmit e;
+            const bool ok = gen_list1<T, DIM>(t, rad, box, e, ws.budget);
+            starts[r] = ok ? e.c0 : 0;
+            ws.row_heavy[r] = ok ? 0 : 1;
+            if (!ok) ws.heavy_rows[atomicAdd(ws.hctl + kHctlNHeavy, 1)] = r;
+        }
+    }
+}
+
+// BFS seed: one frontier item (row, walk parent = root) per heavy row + the root's own append
+template <typename T, int DIM, bool FILL>
+__global__ void list1_heavy_seed_kernel(TreeView<T, DIM> t, int nrows, int* __restrict__ starts, HeavyWs ws)
+{
+    const int nheavy = ws.hctl[kHctlNHeavy];
+    const int rank_bits = bits_for(t.nboxes);
+    const int stride = gridDim.x * blockDim.x;
+    for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < nheavy; h += stride) {
+        const int r = ws.heavy_rows[h];
+        ws.frontier[0][h] = ((unsigned long long)r << 32);      // walk parent = box 0
+        if (t.flags[0] & BT_BOX_IS_SOURCE_BOX) {
+            if (FILL) {
+                const int k = atomicAdd(ws.hctl + kHctlECount, 1);
+                ws.ekeys[0][k] = ((unsigned long long)r << rank_bits) | (unsigned)ws.dfs_rank[0];
+                ws.evals[0][k] = 0;
+            } else atomicAdd(starts + r, 1);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) ws.hctl[kHctlFrontier] = nheavy;
+}
+
+template <typename T, int DIM, bool FILL>
+__global__ void __launch_bounds__(256)
+list1_heavy_step_kernel(TreeView<T, DIM> t, const int* __restrict__ target_boxes, int step,
+                        int* __restrict__ starts, HeavyWs ws)
+{
+    constexpr int NB = 1 << DIM;
+    __shared__ T rad[kMaxWalkLevels];
+    fill_rad_table(rad, t.root_extent);
+    const unsigned long long* fin = ws.frontier[step & 1];
+    unsigned long long* fout = ws.frontier[(step + 1) & 1];
+    long long nitems = ws.hctl[kHctlFrontier + step];
+    if (nitems > ws.frontier_cap) nitems = ws.frontier_cap;
+    const long long total = nitems * NB;
+    const int rank_bits = bits_for(t.nboxes);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x; tid < ((total + 31) & ~31ll);
+         tid += stride) {
+        int act = 0, wb = 0, r = 0;
+        if (tid < total) {
+            const unsigned long long item = fin[tid / NB];
+            r = (int)(item >> 32);
+            const int parent = (int)(unsigned)item, m = (int)(tid % NB);
+            const int box = target_boxes[r];
+            T center[DIM]; t.center(box, center);
+            wb = t.child(parent, m);
+            act = list1_visit<T, DIM>(t, rad, center, t.levels[box], wb);
+        }
+        if (FILL) {
+            const long long k = warp_append(act & kVisitEmit, ws.hctl + kHctlECount);
+            if (k >= 0 && k < ws.ecap) {
+                ws.ekeys[0][k] = ((unsigned long long)r << rank_bits) | (unsigned)ws.dfs_rank[wb];
+                ws.evals[0][k] = (unsigned)wb;
+            }
+        } else if (act & kVisitEmit) atomicAdd(starts + r, 1);
+        const long long q = warp_append(act & kVisitPush, ws.hctl + kHctlFrontier + step + 1);
+        if (q >= 0) {
+            if (q < ws.frontier_cap) fout[q] = ((unsigned long long)r << 32) | (unsigned)wb;
+            else ws.hctl[kHctlOverflow] = 1;
+        }
+    }
+}
+
+// heavy_total = sum of the counts of heavy rows (sizes the sort buffers of the fill phase)
+__global__ void heavy_total_kernel(const int* __restrict__ counts, int64_t rowlen, int nslots, HeavyWs ws)
+{
+    const int nheavy = ws.hctl[kHctlNHeavy];
+    long long acc = 0;
+    for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < nheavy; h += gridDim.x * blockDim.x) {
+        const int r = ws.heavy_rows[h];
+        for (int sl = 0; sl < nslots; ++sl) acc += counts[sl * rowlen + r];
+    }
+    acc = warp_sum_ll(acc);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd((unsigned long long*)ws.heavy_total, (unsigned long long)acc);
+}
+
+// sorted (list slot, row, pre-order rank) records -> CSR positions
+__global__ void __launch_bounds__(256)
+heavy_scatter_kernel(const unsigned long long* __restrict__ keys, const unsigned* __restrict__ vals,
+                     const int* __restrict__ ecount_dev, int rank_bits, int row_bits, int64_t rowlen,
+                     const int* __restrict__ dest_base, int* __restrict__ lists)
+{
+    const int n = *ecount_dev;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long key = keys[i];
+        const unsigned long long group = (key >> rank_bits) << rank_bits;
+        int lo = 0, hi = i;                       // first record of this (slot, row) group
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < group) lo = mid + 1; else hi = mid; }
+        const long long row = (long long)((key >> rank_bits) & ((1ull << row_bits) - 1ull));
+        const long long slot = (long long)(key >> (rank_bits + row_bits));
+        lists[dest_base[slot * rowlen + row] + (i - lo)] = (int)vals[i];
+    }
+}
+
+static int heavy_sort_and_scatter(const HeavyWs& ws, long long ecount_host, int nboxes, int nrows,
+                                  int nslots, int64_t rowlen, const int* dest_base, int* lists,
+                                  cudaStream_t s)
+{
+    if (ecount_host <= 0) return BT_OK;
+    int rank_bits = 1; while ((1ll << rank_bits) < nboxes) ++rank_bits;
+    int row_bits = 1; while ((1ll << row_bits) < nrows) ++row_bits;
+    int slot_bits = 0; while ((1ll << slot_bits) < nslots) ++slot_bits;
+    if (rank_bits + row_bits + slot_bits > 64) return BT_ERR_UNSUPPORTED;
+    int in_alt = 0;
+    BT_TRY(radix_sort_pairs(ecount_host, ws.ekeys[0], ws.ekeys[1], ws.evals[0], ws.evals[1], 0, 0,
+                            rank_bits + row_bits + slot_bits, &in_alt, s));
+    heavy_scatter_kernel<<<grid_for(ecount_host, 256, 8), 256, 0, s>>>(
+        ws.ekeys[in_alt], ws.evals[in_alt], ws.hctl + kHctlECount, rank_bits, row_bits, rowlen,
+        dest_base, lists);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+
+template <typename T, int DIM>
+static int list1_impl(int phase, const bt_tree_view* tv, const int* target_boxes, int nrows, int* starts,
+                      int* lists, long long* totals, const bt_heavy_ws* w, long long heavy_total_host,
+                      cudaStream_t s)
+{
+    TreeView<T, DIM> t = make_view<T, DIM>(tv);
+    HeavyWs ws = make_ws(w);
+    const int grid = grid_for(nrows, kTravBlock, 16);
+    const int nsteps = t.nlevels;
+    if (phase == 0) {
+        BT_CHECK(cudaMemsetAsync(ws.hctl, 0, sizeof(int) * BT_HCTL_SIZE, s));
+        BT_CHECK(cudaMemsetAsync(ws.heavy_total, 0, sizeof(long long), s));
+        if (nrows > 0) {
+            list1_kernel<T, DIM, false><<<grid, kTravBlock, 0, s>>>(t, target_boxes, nrows, starts, nullptr, ws);
+            BT_LAUNCH_CHECK();
+            list1_heavy_seed_kernel<T, DIM, false><<<kNumSMs, 256, 0, s>>>(t, nrows, starts, ws);
+            BT_LAUNCH_CHECK();
+            for (int st = 0; st < nsteps; ++st) {
+                list1_heavy_step_kernel<T, DIM, false><<<kNumSMs * 8, 256, 0, s>>>(t, target_boxes, st, starts, ws);
+                BT_LAUNCH_CHECK();
+            }
+            heavy_total_kernel<<<kNumSMs, 256, 0, s>>>(starts, 0, 1, ws);
+            BT_LAUNCH_CHECK();
+        }
+        BT_TRY(counts_to_starts(starts, nrows, totals, s));
+        return BT_OK;
+    }
+    if (nrows <= 0) return BT_OK;
+    list1_kernel<T, DIM, true><<<grid, kTravBlock, 0, s>>>(t, target_boxes, nrows, starts, lists, ws);
+    BT_LAUNCH_CHECK();
+    if (heavy_total_host > 0) {
+        BT_CHECK(cudaMemsetAsync(ws.hctl + kHctlECount, 0, sizeof(int) * (BT_HCTL_SIZE - kHctlECount), s));
+        list1_heavy_seed_kernel<T, DIM, true><<<kNumSMs, 256, 0, s>>>(t, nrows, starts, ws);
+        BT_LAUNCH_CHECK();
+        for (int st = 0; st < nsteps; ++st) {
+            list1_heavy_step_kernel<T, DIM, true><<<kNumSMs * 8, 256, 0, s>>>(t, target_boxes, st, starts, ws);
+            BT_LAUNCH_CHECK();
+        }
+        BT_TRY(heavy_sort_and_scatter(ws, heavy_total_host, t.nboxes, nrows, 1, 0, starts, lists, s));
+    }
+    return BT_OK;
+}
+
+// light pass of list 3
 template <typename T, int DIM, bool FILL>
 __global__ void __launch_bounds__(kTravBlock)
 list3_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, int ntgt, int* __restrict__ G /*[nlevels+1][ntgt+1]*/,
-             int* __restrict__ lists)
+             int* __restrict__ lists, HeavyWs ws)
 {
     __shared__ T rad[kMaxWalkLevels];
     fill_rad_table(rad, t.root_extent);
@@ -418,14 +676,81 @@ list3_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, int ntgt, int* __restrict_
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < ntgt; r += stride) {
         const int box = x.target_boxes[r];
         if (FILL) {
+            if (ws.row_heavy[r]) continue;
             L3Fill e; e.nlevels = nl; e.lists = lists;
             for (int l = 0; l <= nl; ++l) e.cur[l] = G[l * rowlen + r];
-            gen_list3<T, DIM>(t, rad, x, box, e);
+            gen_list3<T, DIM>(t, rad, x, box, e, 0x7fffffff);
         } else {
             L3Count e; e.nlevels = nl;
             for (int l = 0; l <= nl; ++l) e.cnt[l] = 0;
-            gen_list3<T, DIM>(t, rad, x, box, e);
-            for (int l = 0; l <= nl; ++l) G[l * rowlen + r] = e.cnt[l];
+            const bool ok = gen_list3<T, DIM>(t, rad, x, box, e, ws.budget);
+            for (int l = 0; l <= nl; ++l) G[l * rowlen + r] = ok ? e.cnt[l] : 0;
+            ws.row_heavy[r] = ok ? 0 : 1;
+            if (!ok) ws.heavy_rows[atomicAdd(ws.hctl + kHctlNHeavy, 1)] = r;
+        }
+    }
+}
+
+// BFS seed of list 3: one frontier item per (heavy row, colleague != row box)
+template <typename T, int DIM>
+__global__ void list3_heavy_seed_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, HeavyWs ws)
+{
+    const int nheavy = ws.hctl[kHctlNHeavy];
+    const int stride = gridDim.x * blockDim.x;
+    for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < nheavy; h += stride) {
+        const int r = ws.heavy_rows[h];
+        const int box = x.target_boxes[r];
+        for (int i = x.coll_starts[box]; i < x.coll_starts[box + 1]; ++i) {
+            const int c = x.coll_lists[i];
+            if (c == box) continue;
+            const int q = atomicAdd(ws.hctl + kHctlFrontier, 1);
+            if (q < ws.frontier_cap) ws.frontier[0][q] = ((unsigned long long)r << 32) | (unsigned)c;
+            else ws.hctl[kHctlOverflow] = 1;
+        }
+    }
+}
+
+template <typename T, int DIM, bool FILL>
+__global__ void __launch_bounds__(256)
+list3_heavy_step_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, int ntgt, int step, int* __restrict__ G,
+                        HeavyWs ws)
+{
+    constexpr int NB = 1 << DIM;
+    __shared__ T rad[kMaxWalkLevels];
+    fill_rad_table(rad, t.root_extent);
+    const unsigned long long* fin = ws.frontier[step & 1];
+    unsigned long long* fout = ws.frontier[(step + 1) & 1];
+    long long nitems = ws.hctl[kHctlFrontier + step];
+    if (nitems > ws.frontier_cap) nitems = ws.frontier_cap;
+    const long long total = nitems * NB;
+    const int rank_bits = bits_for(t.nboxes), row_bits = bits_for(ntgt);
+    const int64_t rowlen = (int64_t)ntgt + 1;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x; tid < ((total + 31) & ~31ll);
+         tid += stride) {
+        int act = 0, wb = 0, r = 0;
+        if (tid < total) {
+            const unsigned long long item = fin[tid / NB];
+            r = (int)(item >> 32);
+            const int parent = (int)(unsigned)item, m = (int)(tid % NB);
+            L3Ctx<T, DIM> c; l3_make_ctx<T, DIM>(t, rad, x, x.target_boxes[r], c);
+            wb = t.child(parent, m);
+            act = list3_visit<T, DIM>(t, rad, x, c, wb);
+        }
+        const bool emits = (act & (kVisitEmit | kVisitClose)) != 0;
+        const int slot = (act & kVisitEmit) ? (int)t.levels[wb] : t.nlevels;
+        if (FILL) {
+            const long long k = warp_append(emits, ws.hctl + kHctlECount);
+            if (k >= 0 && k < ws.ecap) {
+                ws.ekeys[0][k] = ((unsigned long long)slot << (rank_bits + row_bits))
+                                 | ((unsigned long long)r << rank_bits) | (unsigned)ws.dfs_rank[wb];
+                ws.evals[0][k] = (unsigned)wb;
+            }
+        } else if (emits) atomicAdd(G + slot * rowlen + r, 1);
+        const long long q = warp_append(act & kVisitPush, ws.hctl + kHctlFrontier + step + 1);
+        if (q >= 0) {
+            if (q < ws.frontier_cap) fout[q] = ((unsigned long long)r << 32) | (unsigned)wb;
+            else ws.hctl[kHctlOverflow] = 1;
         }
     }
 }
@@ -458,10 +783,12 @@ __global__ void list3_summary_kernel(const int* __restrict__ G, const int* __res
 
 template <typename T, int DIM>
 static int list3_impl(int phase, const bt_tree_view* tv, const bt_list3_args* a, int ntgt, int* G, int* C,
-                      int* lists, long long* summary, cudaStream_t s)
+                      int* lists, long long* summary, const bt_heavy_ws* w, long long heavy_total_host,
+                      cudaStream_t s)
 {
     TreeView<T, DIM> t = make_view<T, DIM>(tv);
     if (t.nlevels > kMaxWalkLevels) return BT_ERR_UNSUPPORTED;
+    HeavyWs ws = make_ws(w);
     List3Args<T, DIM> x{a->target_boxes, a->coll_starts, a->coll_lists, (T)a->stick_out_factor,
                         a->targets_have_extent, a->sources_have_extent, a->crit,
                         (const T*)a->box_target_bounding_box_min, (const T*)a->box_target_bounding_box_max,
@@ -470,10 +797,21 @@ static int list3_impl(int phase, const bt_tree_view* tv, const bt_list3_args* a,
     const int64_t rowlen = (int64_t)ntgt + 1;
     const int64_t total_len = rowlen * nrows;
     const int grid = grid_for(ntgt, kTravBlock, 16);
+    const int nsteps = t.nlevels;
     if (phase == 0) {
         BT_CHECK(cudaMemsetAsync(G, 0, sizeof(int) * (total_len + 1), s));
+        BT_CHECK(cudaMemsetAsync(ws.hctl, 0, sizeof(int) * BT_HCTL_SIZE, s));
+        BT_CHECK(cudaMemsetAsync(ws.heavy_total, 0, sizeof(long long), s));
         if (ntgt > 0) {
-            list3_kernel<T, DIM, false><<<grid, kTravBlock, 0, s>>>(t, x, ntgt, G, nullptr);
+            list3_kernel<T, DIM, false><<<grid, kTravBlock, 0, s>>>(t, x, ntgt, G, nullptr, ws);
+            BT_LAUNCH_CHECK();
+            list3_heavy_seed_kernel<T, DIM><<<kNumSMs, 256, 0, s>>>(t, x, ws);
+            BT_LAUNCH_CHECK();
+            for (int st = 0; st < nsteps; ++st) {
+                list3_heavy_step_kernel<T, DIM, false><<<kNumSMs * 8, 256, 0, s>>>(t, x, ntgt, st, G, ws);
+                BT_LAUNCH_CHECK();
+            }
+            heavy_total_kernel<<<kNumSMs, 256, 0, s>>>(G, rowlen, nrows, ws);
             BT_LAUNCH_CHECK();
         }
         InPlaceIn in{G};
@@ -485,10 +823,53 @@ static int list3_impl(int phase, const bt_tree_view* tv, const bt_list3_args* a,
         list3_summary_kernel<<<1, 64, 0, s>>>(G, C, nrows, rowlen, summary);
         BT_LAUNCH_CHECK();
     } else if (ntgt > 0) {
-        list3_kernel<T, DIM, true><<<grid, kTravBlock, 0, s>>>(t, x, ntgt, G, lists);
+        list3_kernel<T, DIM, true><<<grid, kTravBlock, 0, s>>>(t, x, ntgt, G, lists, ws);
         BT_LAUNCH_CHECK();
+        if (heavy_total_host > 0) {
+            BT_CHECK(cudaMemsetAsync(ws.hctl + kHctlECount, 0, sizeof(int) * (BT_HCTL_SIZE - kHctlECount), s));
+            list3_heavy_seed_kernel<T, DIM><<<kNumSMs, 256, 0, s>>>(t, x, ws);
+            BT_LAUNCH_CHECK();
+            for (int st = 0; st < nsteps; ++st) {
+                list3_heavy_step_kernel<T, DIM, true><<<kNumSMs * 8, 256, 0, s>>>(t, x, ntgt, st, G, ws);
+                BT_LAUNCH_CHECK();
+            }
+            BT_TRY(heavy_sort_and_scatter(ws, heavy_total_host, t.nboxes, ntgt, nrows, rowlen, G, lists, s));
+        }
     }
     return BT_OK;
+}
+
+// global DFS pre-order rank of every box (children in Morton order): the append order of
+// every reference walk is this order restricted to the appended boxes
+template <int DIM>
+__global__ void subtree_size_kernel(const int* __restrict__ level_start, int lev, int aligned,
+                                    const int* __restrict__ child_ids, int* __restrict__ size)
+{
+    constexpr int NB = 1 << DIM;
+    const int lo = level_start[lev], hi = level_start[lev + 1];
+    for (int b = lo + blockIdx.x * blockDim.x + threadIdx.x; b < hi; b += gridDim.x * blockDim.x) {
+        int sz = 1;
+#pragma unroll
+        for (int m = 0; m < NB; ++m) { const int c = child_ids[m * aligned + b]; if (c) sz += size[c]; }
+        size[b] = sz;
+    }
+}
+template <int DIM>
+__global__ void dfs_rank_kernel(const int* __restrict__ level_start, int lev, int aligned,
+                                const int* __restrict__ child_ids, const int* __restrict__ size,
+                                int* __restrict__ rank)
+{
+    constexpr int NB = 1 << DIM;
+    const int lo = level_start[lev], hi = level_start[lev + 1];
+    for (int b = lo + blockIdx.x * blockDim.x + threadIdx.x; b < hi; b += gridDim.x * blockDim.x) {
+        int r = (b == 0 ? 0 : rank[b]) + 1;
+        if (b == 0) rank[0] = 0;
+#pragma unroll
+        for (int m = 0; m < NB; ++m) {
+            const int c = child_ids[m * aligned + b];
+            if (c) { rank[c] = r; r += size[c]; }
+        }
+    }
 }
 
 // per-level compressed CSR (eliminate_empty_output_lists) -- one kernel for all levels
@@ -624,20 +1005,52 @@ int bt_trav_build_list(int dtype, int kind, int phase, const bt_tree_view* tree,
                        int32_t* close_lists, int64_t* totals_dev, void* stream)
 {
     static const char* const kNames[2][5] = {
-        {"trav_colleagues_count", "trav_list1_count", "trav_list2_count", "?", "trav_list4_count"},
-        {"trav_colleagues_fill", "trav_list1_fill", "trav_list2_fill", "?", "trav_list4_fill"}};
+        {"trav_colleagues_count", "?", "trav_list2_count", "?", "trav_list4_count"},
+        {"trav_colleagues_fill", "?", "trav_list2_fill", "?", "trav_list4_fill"}};
     BT_PROF(kNames[phase ? 1 : 0][(kind >= 0 && kind <= 4) ? kind : 3], (cudaStream_t)stream);
     BT_DISPATCH(dtype, tree->dim, build_list_impl, kind, phase, tree, args, nrows, starts, lists,
                 close_starts, close_lists, (long long*)totals_dev, (cudaStream_t)stream);
 }
 
+int bt_trav_list1(int dtype, int phase, const bt_tree_view* tree, const int32_t* target_boxes,
+                  int ntarget_boxes, int32_t* starts, int32_t* lists, int64_t* totals_dev,
+                  const bt_heavy_ws* ws, int64_t heavy_total, void* stream)
+{
+    BT_PROF(phase ? "trav_list1_fill" : "trav_list1_count", (cudaStream_t)stream);
+    BT_DISPATCH(dtype, tree->dim, list1_impl, phase, tree, target_boxes, ntarget_boxes, starts, lists,
+                (long long*)totals_dev, ws, (long long)heavy_total, (cudaStream_t)stream);
+}
+
 int bt_trav_list3(int dtype, int phase, const bt_tree_view* tree, const bt_list3_args* args,
                   int ntarget_boxes, int32_t* G, int32_t* C, int32_t* lists, int64_t* summary_dev,
-                  void* stream)
+                  const bt_heavy_ws* ws, int64_t heavy_total, void* stream)
 {
     BT_PROF(phase ? "trav_list3_fill" : "trav_list3_count", (cudaStream_t)stream);
     BT_DISPATCH(dtype, tree->dim, list3_impl, phase, tree, args, ntarget_boxes, G, C, lists,
-                (long long*)summary_dev, (cudaStream_t)stream);
+                (long long*)summary_dev, ws, (long long)heavy_total, (cudaStream_t)stream);
+}
+
+int bt_trav_dfs_rank(int dim, int nboxes, int aligned_nboxes, int nlevels,
+                     const int32_t* level_start_box_nrs, const int32_t* box_child_ids,
+                     int32_t* subtree_size, int32_t* dfs_rank, void* stream)
+{
+    BT_PROF("bt_trav_dfs_rank", (cudaStream_t)stream);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (nboxes <= 0) return BT_OK;
+    const int grid = bt::grid_for(nboxes, 256, 4);
+    for (int lev = nlevels - 1; lev >= 0; --lev) {
+        if (dim == 1) bt::subtree_size_kernel<1><<<grid, 256, 0, s>>>(level_start_box_nrs, lev, aligned_nboxes, box_child_ids, subtree_size);
+        else if (dim == 2) bt::subtree_size_kernel<2><<<grid, 256, 0, s>>>(level_start_box_nrs, lev, aligned_nboxes, box_child_ids, subtree_size);
+        else bt::subtree_size_kernel<3><<<grid, 256, 0, s>>>(level_start_box_nrs, lev, aligned_nboxes, box_child_ids, subtree_size);
+        BT_LAUNCH_CHECK();
+    }
+    for (int lev = 0; lev < nlevels; ++lev) {
+        if (dim == 1) bt::dfs_rank_kernel<1><<<grid, 256, 0, s>>>(level_start_box_nrs, lev, aligned_nboxes, box_child_ids, subtree_size, dfs_rank);
+        else if (dim == 2) bt::dfs_rank_kernel<2><<<grid, 256, 0, s>>>(level_start_box_nrs, lev, aligned_nboxes, box_child_ids, subtree_size, dfs_rank);
+        else bt::dfs_rank_kernel<3><<<grid, 256, 0, s>>>(level_start_box_nrs, lev, aligned_nboxes, box_child_ids, subtree_size, dfs_rank);
+        BT_LAUNCH_CHECK();
+    }
+    return BT_OK;
 }
 
 int bt_trav_list3_compress(int nlevels, int ntarget_boxes, const int32_t* G, const int32_t* C,

@@ -9,6 +9,7 @@ order of the reference's tree walks, so every CSR array is identical.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, replace
 from typing import Any
 
@@ -16,11 +17,66 @@ import numpy as np
 import torch
 
 from . import _cabi
-from ._cabi import bt_list3_args, bt_list_args, bt_tree_view, check, dptr
+from ._cabi import (HCTL_NHEAVY, HCTL_OVERFLOW, HCTL_SIZE, bt_heavy_ws, bt_list3_args,
+                    bt_list_args, bt_tree_view, check, dptr)
 from .array_context import TorchArrayContext, make_obj_array
 from .tree import Tree, TreeOfBoxes
 
 CRIT_CODE = {"static_linf": 0, "precise_linf": 1, "static_l2": 2}
+
+#: child visits one thread may spend on one row of list 1 / list 3 before the row is handed
+#: to the grid-wide "heavy row" path (csrc/traversal.cu); BT_WALK_BUDGET overrides (tests)
+DEFAULT_WALK_BUDGET = 4096
+
+
+class _HeavyWorkspace:
+    """Device buffers of the heavy-row path for one list (lists 1 and 3)."""
+
+    def __init__(self, actx, nrows, nboxes, dfs_rank, budget):
+        self.actx = actx
+        self.nrows = nrows
+        self.row_heavy = actx.empty(max(nrows, 1), np.uint8)
+        self.heavy_rows = actx.empty(max(nrows, 1), np.int32)
+        self.hctl = actx.zeros(HCTL_SIZE, np.int32)
+        self.heavy_total = actx.zeros(1, np.int64)
+        self.dfs_rank = dfs_rank
+        self.budget = budget
+        self.frontier = None
+        self.ekeys = self.evals = None
+        self.ecap = 0
+        self._alloc_frontier(max(nrows, 2 * nboxes, 1 << 16))
+
+    def _alloc_frontier(self, cap):
+        self.frontier_cap = cap
+        self.frontier = [self.actx.empty(cap, np.int64), self.actx.empty(cap, np.int64)]
+
+    def grow_frontier(self):
+        self._alloc_frontier(4 * self.frontier_cap)
+
+    def alloc_entries(self, n):
+        self.ecap = n
+        if n > 0:
+            self.ekeys = [self.actx.empty(n, np.int64), self.actx.empty(n, np.int64)]
+            self.evals = [self.actx.empty(n, np.int32), self.actx.empty(n, np.int32)]
+
+    def struct(self) -> bt_heavy_ws:
+        w = bt_heavy_ws()
+        w.walk_budget = self.budget
+        w.row_heavy = dptr(self.row_heavy)
+        w.heavy_rows = dptr(self.heavy_rows)
+        w.hctl = dptr(self.hctl)
+        w.heavy_total = dptr(self.heavy_total)
+        w.frontier[0] = dptr(self.frontier[0])
+        w.frontier[1] = dptr(self.frontier[1])
+        w.frontier_cap = self.frontier_cap
+        w.dfs_rank = dptr(self.dfs_rank)
+        if self.ekeys is not None:
+            w.ekeys[0], w.ekeys[1] = dptr(self.ekeys[0]), dptr(self.ekeys[1])
+            w.evals[0], w.evals[1] = dptr(self.evals[0]), dptr(self.evals[1])
+        w.ecap = self.ecap
+        return w
+
+
 _INT32_MAX = 2**31 - 1
 
 
@@ -151,6 +207,7 @@ class FMMTraversalBuilder:
         self.well_sep_is_n_away = well_sep_is_n_away
         self.from_sep_smaller_crit = from_sep_smaller_crit
         self._lib = _cabi.load()
+        self.last_stats: dict = {}
 
     def _resolve_crit(self, extent_norm, sources_have_extent, targets_have_extent) -> str:
         # traversal.py:1776-1805
@@ -307,11 +364,24 @@ class FMMTraversalBuilder:
 
             # {{{ count phases of lists 1-4, then ONE readback
 
+            # pre-order rank of every box: orders the entries of heavy rows
+            budget = int(os.environ.get("BT_WALK_BUDGET", DEFAULT_WALK_BUDGET))
+            subtree_size = actx.empty(max(nboxes, 1), np.int32)
+            dfs_rank = actx.empty(max(nboxes, 1), np.int32)
+            check(lib.bt_trav_dfs_rank(dimensions, nboxes, tv.aligned_nboxes, nlevels,
+                                       dptr(level_start_box_nrs), dptr(box_child_ids),
+                                       dptr(subtree_size), dptr(dfs_rank), sh), "bt_trav_dfs_rank")
+            del subtree_size
+            ws1 = _HeavyWorkspace(actx, ntb, nboxes, dfs_rank, budget)
+            ws3 = _HeavyWorkspace(actx, ntb, nboxes, dfs_rank, budget)
+
             l1_starts = actx.empty(ntb + 1, np.int32)
-            a1 = list_args(target_boxes)
-            check(lib.bt_trav_build_list(dcode, 1, 0, C.byref(tv), C.byref(a1), ntb,
-                                         dptr(l1_starts), None, None, None, dptr(totals[0:]), sh),
-                  "list 1 count")
+
+            def count_list1():
+                check(lib.bt_trav_list1(dcode, 0, C.byref(tv), dptr(target_boxes), ntb,
+                                        dptr(l1_starts), None, dptr(totals[0:]),
+                                        C.byref(ws1.struct()), 0, sh), "list 1 count")
+            count_list1()
 
             l2_starts = actx.empty(ntp + 1, np.int32)
             a2 = list_args(target_or_target_parent_boxes, coll)
@@ -348,12 +418,35 @@ class FMMTraversalBuilder:
             G = actx.empty((nlevels + 1) * rowlen + 1, np.int32)
             Cc = actx.empty((nlevels + 1) * rowlen + 1, np.int32)
             summary = actx.zeros(2 * (nlevels + 2), np.int64)
-            check(lib.bt_trav_list3(dcode, 0, C.byref(tv), C.byref(a3), ntb, dptr(G), dptr(Cc),
-                                    None, dptr(summary), sh), "list 3 count")
 
-            both = _read_i64(actx, torch.cat([totals, summary]))
-            tot = both[:8]
-            summ = both[8:]
+            def count_list3():
+                check(lib.bt_trav_list3(dcode, 0, C.byref(tv), C.byref(a3), ntb, dptr(G), dptr(Cc),
+                                        None, dptr(summary), C.byref(ws3.struct()), 0, sh),
+                      "list 3 count")
+            count_list3()
+
+            def read_counts():
+                both = _read_i64(actx, torch.cat([
+                    totals, summary, ws1.heavy_total, ws3.heavy_total,
+                    ws1.hctl[:2].to(torch.int64), ws3.hctl[:2].to(torch.int64)]))
+                ns = summary.shape[0]
+                return both[:8], both[8:8 + ns], both[8 + ns:]
+
+            tot, summ, heavy = read_counts()
+            # frontier overflow of the heavy-row BFS: enlarge and count again (rare)
+            while heavy[2 + HCTL_OVERFLOW] or heavy[4 + HCTL_OVERFLOW]:
+                if heavy[2 + HCTL_OVERFLOW]:
+                    ws1.grow_frontier()
+                    count_list1()
+                if heavy[4 + HCTL_OVERFLOW]:
+                    ws3.grow_frontier()
+                    count_list3()
+                tot, summ, heavy = read_counts()
+            heavy1_total, heavy3_total = int(heavy[0]), int(heavy[1])
+            self.last_stats = {"heavy_rows_list1": int(heavy[2 + HCTL_NHEAVY]),
+                               "heavy_rows_list3": int(heavy[4 + HCTL_NHEAVY]),
+                               "heavy_entries_list1": heavy1_total,
+                               "heavy_entries_list3": heavy3_total}
             g0 = summ[:nlevels + 2]              # G[l][0], l = 0..nlevels, then grand total
             c0 = summ[nlevels + 2:]
             _check_int32(int(tot[0]), "neighbor_source_boxes")
@@ -366,9 +459,11 @@ class FMMTraversalBuilder:
             # {{{ fill phases
 
             l1_lists = actx.empty(int(tot[0]), np.int32)
-            check(lib.bt_trav_build_list(dcode, 1, 1, C.byref(tv), C.byref(a1), ntb,
-                                         dptr(l1_starts), dptr(l1_lists), None, None, None, sh),
-                  "list 1 fill")
+            ws1.alloc_entries(heavy1_total)
+            check(lib.bt_trav_list1(dcode, 1, C.byref(tv), dptr(target_boxes), ntb,
+                                    dptr(l1_starts), dptr(l1_lists), None,
+                                    C.byref(ws1.struct()), heavy1_total, sh), "list 1 fill")
+            del ws1
             l2_lists = actx.empty(int(tot[1]), np.int32)
             check(lib.bt_trav_build_list(dcode, 2, 1, C.byref(tv), C.byref(a2), ntp,
                                          dptr(l2_starts), dptr(l2_lists), None, None, None, sh),
@@ -380,8 +475,11 @@ class FMMTraversalBuilder:
                                          dptr(l4c_lists_raw), None, sh), "list 4 fill")
 
             l3_all = actx.empty(int(g0[nlevels + 1]), np.int32)
+            ws3.alloc_entries(heavy3_total)
             check(lib.bt_trav_list3(dcode, 1, C.byref(tv), C.byref(a3), ntb, dptr(G), dptr(Cc),
-                                    dptr(l3_all), dptr(summary), sh), "list 3 fill")
+                                    dptr(l3_all), dptr(summary), C.byref(ws3.struct()),
+                                    heavy3_total, sh), "list 3 fill")
+            del ws3
             nne_total = int(c0[nlevels])         # non-empty rows over all source levels
             cstarts = actx.empty(nne_total + nlevels, np.int32)
             nonempty_all = actx.empty(max(nne_total, 1), np.int32)

@@ -203,7 +203,6 @@ int bt_trav_level_starts(int nlevels, const int32_t *level_start_box_nrs, const 
 
 /* List builders (pyopencl ListOfListsBuilder: count, scan, write).
  * kind: 0 same_level_non_well_sep_boxes (traversal.py:398-464)
- *       1 neighbor_source_boxes / list 1 (:470-550)
  *       2 from_sep_siblings / list 2     (:556-601)
  *       4 from_sep_bigger / list 4 (+close) (:931-1146)
  * phase 0 writes per-row counts then turns them into starts[nrows+1] in place and
@@ -220,6 +219,39 @@ int bt_trav_build_list(int dtype, int kind, int phase, const bt_tree_view *tree,
                        const bt_list_args *args, int nrows, int32_t *starts, int32_t *lists,
                        int32_t *close_starts, int32_t *close_lists, int64_t *totals_dev,
                        void *stream);
+
+/* Workspace of the "heavy row" path of lists 1 and 3.  A row whose walk needs more than
+ * walk_budget child visits (an upper-level box holding its own targets can have ~1e6 list
+ * entries) is expanded by a grid-wide breadth-first pass over the same child visits; its
+ * entries are then ordered by the tree's global DFS pre-order rank (= the append order of
+ * the reference's walk) with the radix sort and copied into the CSR arrays. */
+#define BT_HCTL_SIZE 64
+#define BT_HCTL_NHEAVY 0
+#define BT_HCTL_OVERFLOW 1
+typedef struct {
+    int32_t walk_budget;
+    uint8_t *row_heavy;          /* [nrows] */
+    int32_t *heavy_rows;         /* [nrows] */
+    int32_t *hctl;               /* [BT_HCTL_SIZE] */
+    int64_t *heavy_total;        /* [1]: entries of all heavy rows (count phase output) */
+    uint64_t *frontier[2];       /* [frontier_cap] each, frontier_cap >= nrows */
+    int64_t frontier_cap;
+    const int32_t *dfs_rank;     /* [nboxes], from bt_trav_dfs_rank */
+    uint64_t *ekeys[2];          /* fill phase: [heavy_total] each */
+    uint32_t *evals[2];
+    int64_t ecap;
+} bt_heavy_ws;
+
+/* pre-order (depth first, children in Morton order) rank of every box */
+int bt_trav_dfs_rank(int dim, int nboxes, int aligned_nboxes, int nlevels,
+                     const int32_t *level_start_box_nrs, const int32_t *box_child_ids,
+                     int32_t *subtree_size, int32_t *dfs_rank, void *stream);
+
+/* neighbor_source_boxes / list 1 (traversal.py:470-550).  phase 0: starts[ntarget_boxes+1],
+ * total at totals_dev[0], ws->heavy_total; phase 1 (heavy_total = HOST copy): lists. */
+int bt_trav_list1(int dtype, int phase, const bt_tree_view *tree, const int32_t *target_boxes,
+                  int ntarget_boxes, int32_t *starts, int32_t *lists, int64_t *totals_dev,
+                  const bt_heavy_ws *ws, int64_t heavy_total, void *stream);
 
 /* from_sep_smaller for ALL source levels in one walk (+ list 3 close), traversal.py:607-875.
  * G, C: int32 [nlevels + 1, ntarget_boxes + 1] (+1 trailing entry); row l < nlevels is
@@ -244,7 +276,7 @@ typedef struct {
 
 int bt_trav_list3(int dtype, int phase, const bt_tree_view *tree, const bt_list3_args *args,
                   int ntarget_boxes, int32_t *G, int32_t *C, int32_t *lists, int64_t *summary_dev,
-                  void *stream);
+                  const bt_heavy_ws *ws, int64_t heavy_total, void *stream);
 
 /* eliminate_empty_output_lists bookkeeping for all levels in one launch: compressed
  * starts (level l at offset C[l][0] + l), nonempty_indices and

@@ -32,6 +32,26 @@ def test_parity_sweep(actx, builders, case):
     assert not bad, bad[:10]
 
 
+_HEAVY_CASES = [c for c in _CASES if c["name"] in (
+    "adaptive", "src-tgt", "lr", "ext-linf-precise_linf-n1", "ext-l2-static_l2-n2", "ext-lr-n1",
+    "ext-lr-n2", "ext-minsrc", "two-level", "single-box")]
+
+
+@pytest.mark.parametrize("budget", [1, 8, 100])
+@pytest.mark.parametrize(
+    "case", _HEAVY_CASES,
+    ids=[f"{c['dims']}d-{np.dtype(c['dtype']).name}-{c['name']}" for c in _HEAVY_CASES])
+def test_parity_heavy_row_path(actx, builders, case, budget, monkeypatch):
+    """Force (almost) every row of lists 1 and 3 through the grid-wide heavy-row path."""
+    monkeypatch.setenv("BT_WALK_BUDGET", str(budget))
+    tb, travs = builders
+    bad = run_case(dict(case), actx, tb, travs)
+    assert not bad, bad[:10]
+    some = next(iter(travs.values()))
+    if case["n"] > 1000 and case["dims"] >= 2 and budget <= 8:
+        assert some.last_stats["heavy_rows_list1"] > 0
+
+
 def _build(actx, src, tkw, vkw):
     from boxtree_b200 import FMMTraversalBuilder, TreeBuilder
     dkw = {k: (actx.from_numpy(v) if isinstance(v, np.ndarray) else
