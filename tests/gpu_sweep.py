@@ -130,6 +130,7 @@ def run_case(case, actx, tb, travs):
         if key not in travs:
             travs[key] = FMMTraversalBuilder(actx, **ctor)
         got_trav_dev, _ = travs[key](actx, got_tree_dev, **tkw)
+        case["_trav_stats"] = dict(travs[key].last_stats)
         got_trav = actx.to_numpy(got_trav_dev)
         bad += ["trav." + b for b in trav_mismatches(ref_trav, got_trav)]
     case["_info"] = (f"nboxes={ref_tree.nboxes} nlevels={ref_tree.nlevels} "
