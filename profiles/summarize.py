@@ -1,0 +1,57 @@
+"""Turn the raw ncu captures in gpurun_out/ into the committed summaries under profiles/.
+
+    python profiles/summarize.py r01 config3
+"""
+import collections
+import csv
+import re
+import subprocess
+import sys
+
+tag, wl = sys.argv[1], sys.argv[2]
+src = f"gpurun_out/launches_{tag}_{wl}.csv"
+lines = [ln for ln in open(src) if ln.startswith('"')]
+r = csv.reader(lines)
+hdr = next(r)
+idx = {h: i for i, h in enumerate(hdr)}
+agg = collections.OrderedDict()
+tot = 0.0
+n = 0
+for row in r:
+    if len(row) < len(hdr):
+        continue
+    name = row[idx["Kernel Name"]]
+    val = float(row[idx["Metric Value"]].replace(",", ""))
+    unit = row[idx["Metric Unit"]]
+    val *= {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}.get(unit, 1.0)
+    short = re.sub(r"\(.*", "", re.sub(r"<.*", "", name)).replace("bt::", "").replace("void ", "")
+    a = agg.setdefault(short, [0, 0.0])
+    a[0] += 1
+    a[1] += val
+    tot += val
+    n += 1
+with open(f"profiles/{tag}_launches_{wl}.txt", "w") as f:
+    f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none (profiles/run_ncu.sh {tag} {wl})\n")
+    f.write(f"# {n} launches captured (~2 steps), serialised + cold cache: compare SHARES, not absolutes\n")
+    f.write(f"# total {tot / 1e6:.3f} ms\n")
+    f.write(f"{'kernel':42s} {'launches':>8s} {'total ms':>10s} {'share':>7s}\n")
+    for k, (c, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        f.write(f"{k:42s} {c:8d} {v / 1e6:10.3f} {100 * v / tot:6.1f}%\n")
+
+raw = subprocess.run(["ncu", "-i", f"gpurun_out/prof_{tag}_{wl}.ncu-rep", "--page", "raw", "--csv"],
+                     capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, units = rows[0], rows[1]
+want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+        "launch__grid_size", "launch__block_size", "l1tex__t_sector_hit_rate.pct",
+        "lts__t_sector_hit_rate.pct", "smsp__warps_eligible.avg.per_cycle_active"]
+cols = [hdr.index(w) for w in want if w in hdr]
+with open(f"profiles/{tag}_ncu_full_{wl}.csv", "w") as f:
+    w = csv.writer(f)
+    w.writerow([f"{hdr[c]} [{units[c]}]" for c in cols])
+    for row in rows[2:]:
+        w.writerow([row[c][:60] for c in cols])
+print(open(f"profiles/{tag}_launches_{wl}.txt").read())
