@@ -99,7 +99,7 @@ SIGNATURES = {
     "bt_reverse_index": [_i64, vp, vp, vp],
     "bt_permute": [_i, _i, _P(bt_particles), vp, _i64, _P(vp), vp, vp],
     "bt_box_info": [_i, _i, _i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
-    "bt_box_extents": [_i, _i, _i, _i, _i, vp, vp, vp, vp, _P(vp), vp, vp, vp, vp],
+    "bt_box_extents": [_i, _i, _i, _i, _i, _P(C.c_int32), vp, vp, vp, vp, _P(vp), vp, vp, vp, vp],
     "bt_trav_box_list": [_i, _i, vp, vp, vp, vp, vp],
     "bt_trav_level_starts": [_i, vp, vp, _i, vp, vp],
     "bt_trav_build_list": [_i, _i, _i, _P(bt_tree_view), _P(bt_list_args), _i, vp, vp, vp, vp,

@@ -693,22 +693,26 @@ box_info_kernel(int nboxes, int sources_are_targets, int have_ext,
 // a14: box particle extents -- boxtree/tree_build_kernels.py:1311-1399,
 // launched per level bottom-up like boxtree/tree_build.py:1751-1802
 // ---------------------------------------------------------------------------
+// Phase A (all boxes at once, one warp per box): min/max over the box's own particles,
+// seeded with the box centre.  min/max are exact and order-free, so the warp-parallel
+// reduction returns the same bits as the reference's serial loop (:1345-1368).
 template <typename T, int DIM>
-__global__ void __launch_bounds__(128)
-box_extents_kernel(int start, int stop, int aligned, const int* __restrict__ box_child_ids,
-                   const T* __restrict__ box_centers, const int* __restrict__ pstarts,
-                   const int* __restrict__ pcounts, const T* p0, const T* p1, const T* p2,
-                   const T* __restrict__ radii, T* __restrict__ bb_min, T* __restrict__ bb_max)
+__global__ void __launch_bounds__(256)
+box_extents_own_kernel(int nboxes, int aligned, const T* __restrict__ box_centers,
+                       const int* __restrict__ pstarts, const int* __restrict__ pcounts,
+                       const T* p0, const T* p1, const T* p2, const T* __restrict__ radii,
+                       T* __restrict__ bb_min, T* __restrict__ bb_max)
 {
-    constexpr int NB = 1 << DIM;
     const T* parts[3] = {p0, p1, p2};
-    const int stride = gridDim.x * blockDim.x;
-    for (int ibox = start + blockIdx.x * blockDim.x + threadIdx.x; ibox < stop; ibox += stride) {
+    const int lane = threadIdx.x & 31;
+    const int wglobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int ibox = wglobal; ibox < nboxes; ibox += nwarps) {
         T mn[DIM], mx[DIM];
 #pragma unroll
         for (int a = 0; a < DIM; ++a) mn[a] = mx[a] = box_centers[a * aligned + ibox];
         const int s = pstarts[ibox], e = s + pcounts[ibox];
-        for (int ip = s; ip < e; ++ip) {
+        for (int ip = s + lane; ip < e; ip += 32) {
             const T rad = radii ? radii[ip] : (T)0;
 #pragma unroll
             for (int a = 0; a < DIM; ++a) {
@@ -719,9 +723,37 @@ box_extents_kernel(int start, int stop, int aligned, const int* __restrict__ box
             }
         }
 #pragma unroll
+        for (int a = 0; a < DIM; ++a) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const T lo = __shfl_xor_sync(0xffffffffu, mn[a], o);
+                const T hi = __shfl_xor_sync(0xffffffffu, mx[a], o);
+                mn[a] = (lo < mn[a]) ? lo : mn[a];
+                mx[a] = (mx[a] < hi) ? hi : mx[a];
+            }
+            if (lane == 0) { bb_min[a * aligned + ibox] = mn[a]; bb_max[a * aligned + ibox] = mx[a]; }
+        }
+    }
+}
+
+// Phase B (one launch per level, bottom-up): merge the children's boxes (:1370-1389)
+template <typename T, int DIM>
+__global__ void __launch_bounds__(128)
+box_extents_merge_kernel(int start, int stop, int aligned, const int* __restrict__ box_child_ids,
+                         T* __restrict__ bb_min, T* __restrict__ bb_max)
+{
+    constexpr int NB = 1 << DIM;
+    const int stride = gridDim.x * blockDim.x;
+    for (int ibox = start + blockIdx.x * blockDim.x + threadIdx.x; ibox < stop; ibox += stride) {
+        T mn[DIM], mx[DIM];
+        bool any = false;
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) { mn[a] = bb_min[a * aligned + ibox]; mx[a] = bb_max[a * aligned + ibox]; }
+#pragma unroll
         for (int m = 0; m < NB; ++m) {
             const int child = box_child_ids[m * aligned + ibox];
             if (child == 0) continue;
+            any = true;
 #pragma unroll
             for (int a = 0; a < DIM; ++a) {
                 const T cmn = bb_min[a * aligned + child], cmx = bb_max[a * aligned + child];
@@ -729,8 +761,10 @@ box_extents_kernel(int start, int stop, int aligned, const int* __restrict__ box
                 mx[a] = (mx[a] < cmx) ? cmx : mx[a];
             }
         }
+        if (any) {
 #pragma unroll
-        for (int a = 0; a < DIM; ++a) { bb_min[a * aligned + ibox] = mn[a]; bb_max[a * aligned + ibox] = mx[a]; }
+            for (int a = 0; a < DIM; ++a) { bb_min[a * aligned + ibox] = mn[a]; bb_max[a * aligned + ibox] = mx[a]; }
+        }
     }
 }
 
@@ -918,16 +952,24 @@ static int permute_impl(const bt_particles* p, const int* from_ids, int n, void*
 }
 
 template <typename T, int DIM>
-static int box_extents_impl(int start, int stop, int aligned, const int* child_ids, const void* centers,
-                            const int* pstarts, const int* pcounts, void* const* parts,
-                            const void* radii, void* bmin, void* bmax, cudaStream_t s)
+static int box_extents_impl(int nboxes, int aligned, int nlevels, const int* level_start_host,
+                            const int* child_ids, const void* centers, const int* pstarts,
+                            const int* pcounts, void* const* parts, const void* radii, void* bmin,
+                            void* bmax, cudaStream_t s)
 {
-    if (stop <= start) return BT_OK;
-    box_extents_kernel<T, DIM><<<grid_for(stop - start, 128, 8), 128, 0, s>>>(
-        start, stop, aligned, child_ids, (const T*)centers, pstarts, pcounts, (const T*)parts[0],
+    if (nboxes <= 0) return BT_OK;
+    box_extents_own_kernel<T, DIM><<<grid_for((int64_t)nboxes * 32, 256, 8), 256, 0, s>>>(
+        nboxes, aligned, (const T*)centers, pstarts, pcounts, (const T*)parts[0],
         DIM > 1 ? (const T*)parts[1] : nullptr, DIM > 2 ? (const T*)parts[2] : nullptr,
         (const T*)radii, (T*)bmin, (T*)bmax);
     BT_LAUNCH_CHECK();
+    for (int lev = nlevels - 2; lev >= 0; --lev) {       // the deepest level has no children
+        const int start = level_start_host[lev], stop = level_start_host[lev + 1];
+        if (stop <= start) continue;
+        box_extents_merge_kernel<T, DIM><<<grid_for(stop - start, 128, 8), 128, 0, s>>>(
+            start, stop, aligned, child_ids, (T*)bmin, (T*)bmax);
+        BT_LAUNCH_CHECK();
+    }
     return BT_OK;
 }
 
@@ -1143,13 +1185,15 @@ int bt_box_info(int nboxes, int sources_are_targets, int have_extent, const int3
     return BT_OK;
 }
 
-int bt_box_extents(int dtype, int dim, int start, int stop, int aligned, const int32_t* box_child_ids,
+int bt_box_extents(int dtype, int dim, int nboxes, int aligned, int nlevels,
+                   const int32_t* level_start_box_nrs_host, const int32_t* box_child_ids,
                    const void* box_centers, const int32_t* pstarts, const int32_t* pcounts,
                    void* const* particles, const void* radii, void* bb_min, void* bb_max, void* stream)
 {
     BT_PROF("bt_box_extents", (cudaStream_t)stream);
-    BT_DISPATCH(dtype, dim, box_extents_impl, start, stop, aligned, box_child_ids, box_centers, pstarts,
-                pcounts, particles, radii, bb_min, bb_max, (cudaStream_t)stream);
+    BT_DISPATCH(dtype, dim, box_extents_impl, nboxes, aligned, nlevels, level_start_box_nrs_host,
+                box_child_ids, box_centers, pstarts, pcounts, particles, radii, bb_min, bb_max,
+                (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -26,7 +26,7 @@ CRIT_CODE = {"static_linf": 0, "precise_linf": 1, "static_l2": 2}
 
 #: child visits one thread may spend on one row of list 1 / list 3 before the row is handed
 #: to the grid-wide "heavy row" path (csrc/traversal.cu); BT_WALK_BUDGET overrides (tests)
-DEFAULT_WALK_BUDGET = 4096
+DEFAULT_WALK_BUDGET = 1024
 
 
 class _HeavyWorkspace:
@@ -44,7 +44,7 @@ class _HeavyWorkspace:
         self.frontier = None
         self.ekeys = self.evals = None
         self.ecap = 0
-        self._alloc_frontier(max(nrows, 2 * nboxes, 1 << 16))
+        self._alloc_frontier(max(nrows, 8 * nboxes, 1 << 16))
 
     def _alloc_frontier(self, cap):
         self.frontier_cap = cap

@@ -582,14 +582,13 @@ class TreeBuilder:
                 rounds.append((tgts, out_target_radii if targets_have_extent else None,
                                box_target_starts, box_target_counts_nonchild, bb_tgt_min,
                                bb_tgt_max))
-            for lev in range(nlevels - 1, -1, -1):
-                start, stop = int(level_start_box_nrs[lev]), int(level_start_box_nrs[lev + 1])
-                for parts, radii, pstarts, pcounts, bmin, bmax in rounds:
-                    check(lib.bt_box_extents(
-                        dcode, dimensions, start, stop, aligned_nboxes, dptr(box_child_ids),
-                        dptr(box_centers), dptr(pstarts), dptr(pcounts),
-                        _cabi.ptr_array(list(parts)), dptr(radii), dptr(bmin), dptr(bmax), sh),
-                        "bt_box_extents")
+            ls_host = (C.c_int32 * (nlevels + 1))(*[int(x) for x in level_start_box_nrs])
+            for parts, radii, pstarts, pcounts, bmin, bmax in rounds:
+                check(lib.bt_box_extents(
+                    dcode, dimensions, nfinal, aligned_nboxes, nlevels, ls_host,
+                    dptr(box_child_ids), dptr(box_centers), dptr(pstarts), dptr(pcounts),
+                    _cabi.ptr_array(list(parts)), dptr(radii), dptr(bmin), dptr(bmax), sh),
+                    "bt_box_extents")
 
             # }}}
 

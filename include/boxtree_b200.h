@@ -168,12 +168,15 @@ int bt_box_info(int nboxes, int sources_are_targets, int have_extent, const int3
                 int32_t *src_cumul, int32_t *tgt_starts, int32_t *tgt_nonchild, int32_t *tgt_cumul,
                 uint8_t *box_flags, void *stream);
 
-/* find_box_extents for boxes [start, stop) of one level (tree_build_kernels.py:1311-1399).
- * particles: HOST array of dim device pointers (tree-ordered coordinates) */
-int bt_box_extents(int dtype, int dim, int start, int stop, int aligned,
-                   const int32_t *box_child_ids, const void *box_centers, const int32_t *pstarts,
-                   const int32_t *pcounts, void *const *particles, const void *radii, void *bb_min,
-                   void *bb_max, void *stream);
+/* find_box_extents for all levels (tree_build_kernels.py:1311-1399, launched per level
+ * bottom-up at tree_build.py:1751-1802): own-particle min/max for every box in one launch,
+ * then one child-merge launch per level.  particles: HOST array of dim device pointers
+ * (tree-ordered coordinates); level_start_box_nrs_host: HOST [nlevels+1] */
+int bt_box_extents(int dtype, int dim, int nboxes, int aligned, int nlevels,
+                   const int32_t *level_start_box_nrs_host, const int32_t *box_child_ids,
+                   const void *box_centers, const int32_t *pstarts, const int32_t *pcounts,
+                   void *const *particles, const void *radii, void *bb_min, void *bb_max,
+                   void *stream);
 
 /* ---------------------------------------------------------------- traversal */
 
