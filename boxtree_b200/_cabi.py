@@ -111,6 +111,16 @@ SIGNATURES = {
     "bt_trav_list3_compress": [_i, _i, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "bt_trav_merge_lists": [_i, _i, vp, _i, _P(vp), _P(vp), vp, vp, vp, vp],
     "bt_gather_i32": [_i64, vp, vp, vp, vp],
+    "bt_dist_dfs_order": [_i, _i, _i, _i, vp, vp, vp, vp, vp, vp],
+    "bt_dist_mask_from_list": [_i, vp, vp, vp],
+    "bt_dist_ancestor_mask": [_i, vp, vp, vp, vp],
+    "bt_dist_add_list_boxes": [_i, vp, vp, vp, vp, vp, vp, vp],
+    "bt_dist_particle_mask": [_i, vp, vp, vp, vp, vp],
+    "bt_dist_mask_scan": [_i64, vp, vp, vp],
+    "bt_dist_fetch_local_particles": [_i, _i, _i64, vp, vp, _P(vp), vp, _P(vp), vp, vp, vp],
+    "bt_dist_local_lists": [_i, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    "bt_dist_modify_target_flags": [_i, vp, vp, vp, vp],
+    "bt_dist_box_to_user_rank": [_i, _i, _i, vp, vp, vp, vp, vp],
 }
 
 _lib = None

@@ -1,0 +1,89 @@
+"""Distributed tree/traversal setup (``boxtree/distributed/``), B200-native.
+
+One process per GPU; the plumbing is ``torch.distributed`` (NCCL over NVLink 5 /
+NVSwitch), the per-rank work is CUDA kernels of ``csrc/distributed.cu``.  Mirrors the
+reference's setup functions: ``partition_work``, ``get_box_masks``,
+``generate_local_tree``, ``generate_local_travs``
+(``boxtree/distributed/__init__.py:156-266`` without the FMM wrangler)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .comm import SingleProcessComm, TorchDistComm
+from .local_traversal import generate_local_travs
+from .local_tree import LocalTree, box_to_user_rank, generate_local_tree
+from .partition import (BoxMasks, get_box_ids_dfs_order, get_box_masks, partition_segments,
+                        partition_work)
+
+__all__ = [
+    "SingleProcessComm", "TorchDistComm", "LocalTree", "BoxMasks", "get_box_ids_dfs_order",
+    "partition_segments", "partition_work", "get_box_masks", "generate_local_tree",
+    "box_to_user_rank", "generate_local_travs", "broadcast_tree", "distributed_setup",
+]
+
+
+def broadcast_tree(actx, tree, comm, root=0):
+    """Ship the global tree from the root to every rank (``distributed/__init__.py:185-199``
+    does this with a pickled ``comm.bcast``); arrays travel as raw buffers."""
+    import dataclasses
+
+    from ..tree import Tree
+    if comm.Get_size() == 1:
+        return tree
+    meta = None
+    if comm.Get_rank() == root:
+        meta = {f.name: getattr(tree, f.name) for f in dataclasses.fields(Tree)}
+    names = [f.name for f in dataclasses.fields(Tree)]
+    out = {}
+    for name in names:
+        v = meta[name] if meta is not None else None
+        kind = [None]
+        if comm.Get_rank() == root:
+            if isinstance(v, torch.Tensor):
+                kind = ["tensor"]
+            elif isinstance(v, np.ndarray) and v.dtype == object:
+                kind = ["objarray", len(v)]
+            elif isinstance(v, tuple) and all(isinstance(x, np.ndarray) for x in v):
+                kind = ["nptuple", len(v)]
+            else:
+                kind = ["object", v]
+        comm.dist.broadcast_object_list(kind, src=root, group=comm.group)
+        if kind[0] == "tensor":
+            arr = comm.bcast_array(actx.to_numpy(v) if v is not None else None, root)
+            out[name] = actx.from_numpy(arr)
+        elif kind[0] == "objarray":
+            from ..array_context import make_obj_array
+            items = []
+            for i in range(kind[1]):
+                arr = comm.bcast_array(actx.to_numpy(v[i]) if v is not None else None, root)
+                items.append(actx.from_numpy(arr))
+            out[name] = make_obj_array(items)
+        elif kind[0] == "nptuple":
+            out[name] = tuple(comm.bcast_array(v[i] if v is not None else None, root)
+                              for i in range(kind[1]))
+        else:
+            out[name] = kind[1]
+    if out["sources_are_targets"]:
+        out["targets"] = out["sources"]
+    return Tree(**out)
+
+
+def distributed_setup(actx, global_tree, traversal_builder, comm, cost_per_box=None,
+                      merge_close_lists=False):
+    """The tree/traversal part of ``make_distributed_wrangler``
+    (``distributed/__init__.py:156-266``): broadcast the root's global tree, build the
+    global traversal on every rank, partition the boxes by cost in DFS order, build the
+    rank's local tree and local traversal.
+
+    *cost_per_box* (root only) defaults to ``1 + own source count + own target count``.
+    Returns ``(local_tree, local_trav, src_idx, tgt_idx, global_trav)``."""
+    tree = broadcast_tree(actx, global_tree, comm)
+    global_trav, _ = traversal_builder(actx, tree)
+    if cost_per_box is None and comm.Get_rank() == 0:
+        cost_per_box = (1.0 + tree.box_source_counts_nonchild.double()
+                        + tree.box_target_counts_nonchild.double()).cpu().numpy()
+    responsible = partition_work(actx, cost_per_box, global_trav, comm)
+    local_tree, src_idx, tgt_idx = generate_local_tree(actx, global_trav, responsible, comm)
+    local_trav = generate_local_travs(actx, local_tree, traversal_builder, merge_close_lists)
+    return local_tree, local_trav, src_idx, tgt_idx, global_trav

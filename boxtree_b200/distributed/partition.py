@@ -1,0 +1,138 @@
+"""Work partition and box masks: ``boxtree/distributed/partition.py`` on B200."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any
+
+import numpy as np
+import torch
+
+from .. import _cabi
+from .._cabi import check, dptr
+
+
+def get_box_ids_dfs_order(actx, tree):
+    """``partition.py:38-57``: box ids in depth-first order, HIGHEST Morton child first (the
+    reference pops a stack).  Computed on the device; returns a device int32 tensor."""
+    lib = _cabi.load()
+    nboxes = int(tree.nboxes)
+    with torch.cuda.stream(actx.stream):
+        child_ids = _dev(actx, tree.box_child_ids)
+        ls = _dev(actx, tree.level_start_box_nrs).to(torch.int32)
+        size = actx.empty(max(nboxes, 1), np.int32)
+        rank = actx.empty(max(nboxes, 1), np.int32)
+        order = actx.empty(max(nboxes, 1), np.int32)
+        check(lib.bt_dist_dfs_order(int(tree.dimensions), nboxes, int(child_ids.shape[-1]),
+                                    int(tree.nlevels), dptr(ls), dptr(child_ids), dptr(size),
+                                    dptr(rank), dptr(order), actx.stream_handle),
+              "bt_dist_dfs_order")
+    return order[:nboxes]
+
+
+def _dev(actx, a):
+    if isinstance(a, np.ndarray):
+        a = actx.from_numpy(np.ascontiguousarray(a))
+    return a.contiguous()
+
+
+def partition_segments(cost_in_dfs_order, mpi_size):
+    """The root-rank loop of ``partition.py:81-116`` on the costs already arranged in DFS
+    order: returns the ``(mpi_size, 2)`` int32 array of ``[start, end)`` DFS positions.
+
+    The running sum is a sequential float accumulation exactly like the reference's
+    ``workload_count += cost``; the thresholds use the reference's expression."""
+    cost = np.asarray(cost_in_dfs_order)
+    nboxes = len(cost)
+    total_workload = np.sum(cost)
+    segments = np.empty((mpi_size, 2), dtype=np.int32)
+    cum = np.cumsum(cost)                       # sequential, like the += loop
+    monotone = bool(np.all(cost >= 0))
+    start = 0
+    for segment_idx in range(mpi_size - 1):
+        thr = (segment_idx + 1) * total_workload / mpi_size
+        if monotone:
+            i = int(np.searchsorted(cum, thr, side="right"))
+        else:
+            hit = np.nonzero(cum[start:] > thr)[0]
+            i = start + int(hit[0]) if len(hit) else nboxes - 1
+        i = min(max(i, start), nboxes - 1)
+        segments[segment_idx] = [start, i + 1]
+        start = i + 1
+    segments[mpi_size - 1] = [start, nboxes]
+    return segments
+
+
+def partition_work(actx, cost_per_box, traversal, comm):
+    """``partition.py:60-121``.  *cost_per_box* (numpy) is only significant on the root rank.
+    Returns the numpy array of boxes the calling rank is responsible for."""
+    tree = traversal.tree
+    mpi_rank, mpi_size = comm.Get_rank(), comm.Get_size()
+    if mpi_size > tree.nboxes:
+        raise RuntimeError("Fail to partition work because the number of boxes is "
+                           "less than the number of processes.")
+    dfs_order = get_box_ids_dfs_order(actx, tree).cpu().numpy()
+    segments = None
+    if mpi_rank == 0:
+        cost = np.asarray(actx.to_numpy(cost_per_box) if isinstance(cost_per_box, torch.Tensor)
+                          else cost_per_box)
+        segments = partition_segments(cost[dfs_order], mpi_size)
+    mine = comm.scatter_rows(segments, root=0)
+    return dfs_order[int(mine[0]):int(mine[1])]
+
+
+@dataclass(frozen=True)
+class BoxMasks:
+    """``partition.py:300-327``: int8 device masks of length ``tree.nboxes``."""
+    responsible_boxes: Any
+    ancestor_boxes: Any
+    point_src_boxes: Any
+    multipole_src_boxes: Any
+
+
+def get_box_masks(actx, traversal, responsible_boxes_list) -> BoxMasks:
+    """``partition.py:330-357``."""
+    lib = _cabi.load()
+    tree = traversal.tree
+    nb = int(tree.nboxes)
+    sh = actx.stream_handle
+    with torch.cuda.stream(actx.stream):
+        resp_list = _dev(actx, np.asarray(responsible_boxes_list, np.int32)
+                         if not isinstance(responsible_boxes_list, torch.Tensor)
+                         else responsible_boxes_list.to(torch.int32))
+        responsible = actx.zeros(nb, np.int8)
+        check(lib.bt_dist_mask_from_list(int(resp_list.shape[0]), dptr(resp_list),
+                                         dptr(responsible), sh), "bt_dist_mask_from_list")
+        ancestors = actx.zeros(nb, np.int8)
+        check(lib.bt_dist_ancestor_mask(nb, dptr(responsible), dptr(_dev(actx, tree.box_parent_ids)),
+                                        dptr(ancestors), sh), "bt_dist_ancestor_mask")
+
+        def add(box_list, mask_a, mask_b, starts, lists, out):
+            check(lib.bt_dist_add_list_boxes(int(box_list.shape[0]), dptr(_dev(actx, box_list)),
+                                             dptr(mask_a), dptr(mask_b), dptr(_dev(actx, starts)),
+                                             dptr(_dev(actx, lists)), dptr(out), sh),
+                  "bt_dist_add_list_boxes")
+
+        # point sources: partition.py:197-252
+        src = responsible.clone()
+        add(traversal.target_boxes, responsible, None, traversal.neighbor_source_boxes_starts,
+            traversal.neighbor_source_boxes_lists, src)
+        add(traversal.target_or_target_parent_boxes, responsible, ancestors,
+            traversal.from_sep_bigger_starts, traversal.from_sep_bigger_lists, src)
+        if tree.targets_have_extent:
+            if traversal.from_sep_close_smaller_starts is not None:
+                add(traversal.target_boxes, responsible, None,
+                    traversal.from_sep_close_smaller_starts,
+                    traversal.from_sep_close_smaller_lists, src)
+            if traversal.from_sep_close_bigger_starts is not None:
+                add(traversal.target_boxes, responsible, ancestors,
+                    traversal.from_sep_close_bigger_starts,
+                    traversal.from_sep_close_bigger_lists, src)
+        # multipole sources: partition.py:255-297
+        mpole = actx.zeros(nb, np.int8)
+        add(traversal.target_or_target_parent_boxes, responsible, ancestors,
+            traversal.from_sep_siblings_starts, traversal.from_sep_siblings_lists, mpole)
+        for ilevel in range(int(tree.nlevels)):
+            bl = traversal.from_sep_smaller_by_level[ilevel]
+            add(traversal.target_boxes_sep_smaller_by_source_level[ilevel], responsible, None,
+                bl.starts, bl.lists, mpole)
+    return BoxMasks(responsible, ancestors, src, mpole)

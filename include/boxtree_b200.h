@@ -299,6 +299,44 @@ int bt_trav_merge_lists(int phase, int noutput, const int32_t *output_to_input_b
 /* out[i] = src[idx[i]]  (the take / fancy-index glue of traversal.py:1298-1302) */
 int bt_gather_i32(int64_t n, const int32_t *src, const int32_t *idx, int32_t *out, void *stream);
 
+/* ------------------------------------------------- distributed setup (rows c1-c4) */
+
+/* get_box_ids_dfs_order (distributed/partition.py:38-57): pre-order with the HIGHEST
+ * Morton child first (the reference pops an explicit stack).  dfs_order[i] = box id */
+int bt_dist_dfs_order(int dim, int nboxes, int aligned_nboxes, int nlevels,
+                      const int32_t *level_start_box_nrs, const int32_t *box_child_ids,
+                      int32_t *subtree_size, int32_t *rank_tmp, int32_t *dfs_order, void *stream);
+
+/* get_box_masks (distributed/partition.py:124-357) building blocks: int8 masks [nboxes] */
+int bt_dist_mask_from_list(int n, const int32_t *list, int8_t *mask, void *stream);
+int bt_dist_ancestor_mask(int nboxes, const int8_t *responsible, const int32_t *box_parent_ids,
+                          int8_t *ancestor_mask, void *stream);
+/* add_interaction_list_boxes (:135-162): rows whose box is in mask_a | mask_b mark their entries */
+int bt_dist_add_list_boxes(int nrows, const int32_t *box_list, const int8_t *mask_a,
+                           const int8_t *mask_b, const int32_t *starts, const int32_t *lists,
+                           int8_t *out_mask, void *stream);
+
+/* construct_local_particles_and_lists (distributed/local_tree.py:70-151, 198-284) */
+int bt_dist_particle_mask(int nboxes, const int8_t *box_mask, const int32_t *starts,
+                          const int32_t *counts_nonchild, int32_t *particle_mask, void *stream);
+int bt_dist_mask_scan(int64_t n, const int32_t *particle_mask, int32_t *global_to_local,
+                      void *stream);
+int bt_dist_fetch_local_particles(int dtype, int dim, int64_t n, const int32_t *particle_mask,
+                                  const int32_t *global_to_local, void *const *particles,
+                                  const void *radii, void *const *local_particles,
+                                  void *local_radii, int64_t *particle_idx, void *stream);
+int bt_dist_local_lists(int nboxes, const int8_t *box_mask, const int32_t *global_to_local,
+                        const int32_t *starts, const int32_t *counts_nonchild,
+                        const int32_t *counts_cumul, int32_t *local_starts,
+                        int32_t *local_nonchild, int32_t *local_cumul, void *stream);
+/* modify_target_flags (local_tree.py:163-185) */
+int bt_dist_modify_target_flags(int nboxes, const int32_t *tgt_nonchild, const int32_t *tgt_cumul,
+                                uint8_t *box_flags, void *stream);
+/* MaskCompressorKernel 2-D (tools.py:647-740) on the gathered multipole masks
+ * [nranks, nboxes]: phase 0 starts[nboxes+1] + total, phase 1 lists (ascending ranks) */
+int bt_dist_box_to_user_rank(int phase, int nboxes, int nranks, const int8_t *masks_all_ranks,
+                             int32_t *starts, int32_t *lists, int64_t *total_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

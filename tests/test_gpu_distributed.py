@@ -1,0 +1,101 @@
+"""GPU parity of the distributed setup rows (partition, masks, local tree, local traversal)
+against the oracle, emulating the ranks one after the other in a single process."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import distributed as od
+from oracle.traversal import build_traversal
+from oracle.tree_build import build_tree
+from tests.parity_util import (bits_equal, config3_inputs, normal_particles, trav_mismatches)
+
+pytestmark = pytest.mark.gpu
+
+
+class FakeComm:
+    """One emulated rank of *size*; the root's segments are computed by every emulated rank."""
+
+    def __init__(self, rank, size):
+        self.rank, self.size = rank, size
+
+    def Get_rank(self):  # noqa: N802
+        return 0            # every emulated rank holds the costs, so each acts as the root
+
+    def Get_size(self):  # noqa: N802
+        return self.size
+
+    def scatter_rows(self, rows, root=0):
+        return np.asarray(rows[self.rank])
+
+
+CASES = {
+    "points": lambda: (normal_particles(20000, 3, np.float64), dict(max_particles_in_box=30), {}),
+    "points2d-f32-2away": lambda: (normal_particles(20000, 2, np.float32),
+                                   dict(max_particles_in_box=30), dict(well_sep_is_n_away=2)),
+    "config3": lambda: (lambda s, t, r: (s, dict(
+        max_particles_in_box=30, targets=t, target_radii=r, stick_out_factor=0.25,
+        extent_norm="linf", kind="adaptive-level-restricted"), {}))(*config3_inputs(20000, 20000)),
+}
+
+
+@pytest.mark.parametrize("nranks", [1, 3, 4])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_distributed_rows_match_oracle(actx, name, nranks):
+    from boxtree_b200 import FMMTraversalBuilder, TreeBuilder
+    from boxtree_b200 import distributed as bd
+    src, tkw, vkw = CASES[name]()
+    rtree = build_tree(src, **tkw)
+    rtrav = build_traversal(rtree, **vkw)
+    dkw = {k: (actx.from_numpy(v) if isinstance(v, np.ndarray) else
+               [actx.from_numpy(x) for x in v] if k == "targets" else v) for k, v in tkw.items()}
+    tree, _ = TreeBuilder(actx)(actx, [actx.from_numpy(s) for s in src], **dkw)
+    tg = FMMTraversalBuilder(actx, **vkw)
+    trav, _ = tg(actx, tree)
+
+    nb = rtree.nboxes
+    cost = (1.0 + rtree.box_source_counts_nonchild[:nb] + rtree.box_target_counts_nonchild[:nb])
+    cost = cost.astype(np.float64)
+    want_resp, _ = od.partition_work(cost, rtree, nranks)
+    assert np.array_equal(bd.get_box_ids_dfs_order(actx, tree).cpu().numpy(),
+                          od.get_box_ids_dfs_order(rtree))
+
+    got_resp = [bd.partition_work(actx, cost, trav, FakeComm(r, nranks)) for r in range(nranks)]
+    for r in range(nranks):
+        assert np.array_equal(got_resp[r], want_resp[r])
+    want_masks = [od.get_box_masks(rtrav, want_resp[r]) for r in range(nranks)]
+    got_masks = [bd.get_box_masks(actx, trav, got_resp[r]) for r in range(nranks)]
+    for r in range(nranks):
+        for f in ("responsible_boxes", "ancestor_boxes", "point_src_boxes", "multipole_src_boxes"):
+            assert np.array_equal(getattr(got_masks[r], f).cpu().numpy(),
+                                  getattr(want_masks[r], f)), (r, f)
+    want_mp = np.stack([m.multipole_src_boxes for m in want_masks])
+    got_mp = torch.stack([m.multipole_src_boxes for m in got_masks])
+
+    ntgt_total = 0
+    for r in range(nranks):
+        wt, wsrc_idx, wtgt_idx = od.generate_local_tree(rtrav, want_resp[r], want_mp)
+        gt, gsrc_idx, gtgt_idx = bd.generate_local_tree(actx, trav, got_resp[r], FakeComm(r, nranks),
+                                                        multipole_masks_all_ranks=got_mp)
+        assert np.array_equal(gsrc_idx.cpu().numpy(), wsrc_idx)
+        assert np.array_equal(gtgt_idx.cpu().numpy(), wtgt_idx)
+        ntgt_total += len(wtgt_idx)
+        g = actx.to_numpy(gt)
+        for f in ("box_source_starts", "box_source_counts_nonchild", "box_source_counts_cumul",
+                  "box_target_starts", "box_target_counts_nonchild", "box_target_counts_cumul",
+                  "box_flags", "box_parent_ids", "box_levels", "box_child_ids"):
+            a, b = np.asarray(getattr(g, f)), np.asarray(getattr(wt, f))
+            assert a.dtype == b.dtype and np.array_equal(a, b), (r, f)
+        for ax in range(rtree.dimensions):
+            assert bits_equal(g.sources[ax], wt.sources[ax]) and bits_equal(g.targets[ax], wt.targets[ax])
+        if rtree.targets_have_extent:
+            assert bits_equal(g.target_radii, wt.target_radii)
+        assert g.user_source_ids is None and g.sorted_target_ids is None
+        for f in ("box_to_user_rank_starts", "box_to_user_rank_lists", "responsible_boxes_mask",
+                  "ancestor_mask"):
+            assert np.array_equal(np.asarray(getattr(g, f)), wt.extra[f]), (r, f)
+        assert np.array_equal(np.asarray(g.responsible_boxes_list), want_resp[r])
+
+        wtrav = od.generate_local_travs(wt, **vkw)
+        gtrav = bd.generate_local_travs(actx, gt, tg)
+        assert not trav_mismatches(wtrav, actx.to_numpy(gtrav)), r
+    assert ntgt_total == rtree.ntargets
