@@ -28,44 +28,46 @@ def broadcast_tree(actx, tree, comm, root=0):
     does this with a pickled ``comm.bcast``); arrays travel as raw buffers."""
     import dataclasses
 
+    from ..array_context import make_obj_array
     from ..tree import Tree
     if comm.Get_size() == 1:
         return tree
-    meta = None
-    if comm.Get_rank() == root:
-        meta = {f.name: getattr(tree, f.name) for f in dataclasses.fields(Tree)}
     names = [f.name for f in dataclasses.fields(Tree)]
+    is_root = comm.Get_rank() == root
+
+    def kind_of(v):
+        if isinstance(v, torch.Tensor):
+            return ("tensor", None)
+        if isinstance(v, np.ndarray) and v.dtype == object:
+            return ("objarray", len(v))
+        if isinstance(v, tuple) and all(isinstance(x, np.ndarray) for x in v):
+            return ("nptuple", len(v))
+        return ("object", v)
+
+    manifest = [[(name, *kind_of(getattr(tree, name))) for name in names]] if is_root else [None]
+    comm.dist.broadcast_object_list(manifest, src=root, group=comm.group)
     out = {}
-    for name in names:
-        v = meta[name] if meta is not None else None
-        kind = [None]
-        if comm.Get_rank() == root:
-            if isinstance(v, torch.Tensor):
-                kind = ["tensor"]
-            elif isinstance(v, np.ndarray) and v.dtype == object:
-                kind = ["objarray", len(v)]
-            elif isinstance(v, tuple) and all(isinstance(x, np.ndarray) for x in v):
-                kind = ["nptuple", len(v)]
-            else:
-                kind = ["object", v]
-        comm.dist.broadcast_object_list(kind, src=root, group=comm.group)
-        if kind[0] == "tensor":
-            arr = comm.bcast_array(actx.to_numpy(v) if v is not None else None, root)
-            out[name] = actx.from_numpy(arr)
-        elif kind[0] == "objarray":
-            from ..array_context import make_obj_array
-            items = []
-            for i in range(kind[1]):
-                arr = comm.bcast_array(actx.to_numpy(v[i]) if v is not None else None, root)
-                items.append(actx.from_numpy(arr))
-            out[name] = make_obj_array(items)
-        elif kind[0] == "nptuple":
-            out[name] = tuple(comm.bcast_array(v[i] if v is not None else None, root)
-                              for i in range(kind[1]))
+    for name, kind, extra in manifest[0]:
+        v = getattr(tree, name) if is_root else None
+        if kind == "tensor":
+            out[name] = actx.from_numpy(comm.bcast_array(actx.to_numpy(v) if is_root else None, root))
+        elif kind == "objarray":
+            out[name] = make_obj_array([
+                actx.from_numpy(comm.bcast_array(actx.to_numpy(v[i]) if is_root else None, root))
+                for i in range(extra)])
+        elif kind == "nptuple":
+            out[name] = tuple(comm.bcast_array(v[i] if is_root else None, root)
+                              for i in range(extra))
         else:
-            out[name] = kind[1]
+            out[name] = extra
     if out["sources_are_targets"]:
-        out["targets"] = out["sources"]
+        # keep the reference's aliasing (tree_build.py:1469-1474, 1572, 1739-1741)
+        for a, b in (("targets", "sources"), ("box_target_starts", "box_source_starts"),
+                     ("box_target_counts_nonchild", "box_source_counts_nonchild"),
+                     ("box_target_counts_cumul", "box_source_counts_cumul"),
+                     ("box_target_bounding_box_min", "box_source_bounding_box_min"),
+                     ("box_target_bounding_box_max", "box_source_bounding_box_max")):
+            out[a] = out[b]
     return Tree(**out)
 
 

@@ -58,6 +58,54 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+class _HostActx:
+    """numpy <-> CPU torch stand-in so broadcast_tree can be exercised without a GPU."""
+
+    def from_numpy(self, a):
+        return torch.from_numpy(np.ascontiguousarray(a))
+
+    def to_numpy(self, t):
+        return t.numpy()
+
+
+def _tree_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from boxtree_b200 import Tree
+    from boxtree_b200.array_context import make_obj_array
+    from boxtree_b200.distributed import TorchDistComm, broadcast_tree
+    import dataclasses
+    actx = _HostActx()
+    tree = None
+    if rank == 0:
+        ot = build_tree(normal_particles(500, 2, np.float64), max_particles_in_box=20)
+        vals = {}
+        for f in dataclasses.fields(Tree):
+            v = getattr(ot, f.name)
+            if isinstance(v, np.ndarray):
+                v = torch.from_numpy(np.ascontiguousarray(v))
+            elif isinstance(v, list):
+                v = make_obj_array([torch.from_numpy(np.ascontiguousarray(x)) for x in v])
+            vals[f.name] = v
+        tree = Tree(**vals)
+    got = broadcast_tree(actx, tree, TorchDistComm(), root=0)
+    out[rank] = (got.nboxes, got.nlevels, got.box_child_ids.sum().item(),
+                 float(got.sources[1].sum()), got.targets is got.sources,
+                 float(got.root_extent), got.bounding_box[0].tolist(), got._is_pruned)
+    dist.destroy_process_group()
+
+
+def test_broadcast_tree_gloo_world_size_2():
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_tree_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] == out[1]
+    assert out[1][4] is True and out[1][0] > 1
+
+
 def test_torch_dist_comm_gloo_world_size_2():
     port = _free_port()
     mgr = mp.Manager()
