@@ -151,6 +151,10 @@ def load() -> C.CDLL:
         lib.bt_prof_reset.restype = None
         lib.bt_prof_report.argtypes = [C.c_char_p, C.c_int]
         lib.bt_prof_report.restype = C.c_int
+        lib.bt_set_walk_mode.argtypes = [C.c_int]
+        lib.bt_set_walk_mode.restype = None
+        if os.environ.get("BT_WALK_MODE"):
+            lib.bt_set_walk_mode(int(os.environ["BT_WALK_MODE"]))
         _lib = lib
     return _lib
 

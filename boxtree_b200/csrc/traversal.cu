@@ -160,6 +160,138 @@ __device__ __forceinline__ bool gen_list1(const TreeView<T, DIM>& t, const T* ra
     return true;
 }
 
+// ---- cooperative walks --------------------------------------------------------
+// The reference walks a row with one work-item.  Here a row is walked by a GROUP of 2^d
+// lanes (32 / 2^d rows per warp): when a walk node is expanded, lane m evaluates child m
+// (the same child visit as the reference, `list*_visit`), ballots turn the results into
+// bit masks, and the masks are consumed in Morton order -- a child's append precedes the
+// descent into it, later children wait in a per-group shared-memory stack -- so the
+// APPEND order is exactly the order of the reference's depth-first walk while the
+// dependent-load chain per row is ~2^d times shorter and appends of sibling boxes are
+// written by several lanes at once.
+// Which mapping each builder uses (bit set = group/warp-cooperative, clear = one thread per
+// row); the defaults are the faster choice measured on B200 (profiles/README.md).
+constexpr int kModeColl = 1, kModeList1 = 2, kModeList3 = 4, kModeList3Auto = 8,
+              kModeList2Count = 16, kModeList2Fill = 32;
+int g_walk_mode = kModeList1 | kModeList3Auto | kModeList2Fill;
+
+struct CoopFrame { int parent; unsigned bits; };
+
+// Policy P (one object per lane, group-uniform state):
+//   void init(int row, bool valid);               (called by ALL lanes of the warp)
+//   bool next_root(int& parent); int visit(int wb);
+//   void emit(unsigned eb, unsigned cb, int c, int gl, int parent);   (ALL lanes)
+//   void finish(int row, bool valid, bool ok, int gl);                (ALL lanes)
+template <typename T, int DIM, class P>
+__device__ __forceinline__ void coop_walk_rows(const TreeView<T, DIM>& t, P& pol, int nrows, int budget,
+                                               CoopFrame* frames /* [groups per block][kMaxWalkLevels] */)
+{
+    constexpr int NB = 1 << DIM;
+    constexpr int GPW = 32 / NB;
+    constexpr unsigned gmask = (1u << NB) - 1u;
+    const int lane = threadIdx.x & 31, g = lane / NB, gl = lane % NB, gshift = g * NB;
+    CoopFrame* stack = frames + (threadIdx.x / NB) * kMaxWalkLevels;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int max_exp = budget / NB + 1;
+    for (int rbase = warp_global * GPW; rbase < nrows; rbase += nwarps * GPW) {
+        const int row = rbase + g;
+        bool active = row < nrows, ok = true, need_eval = false, reload = false;
+        int parent = 0, sp = 0, c = 0, expansions = 0;
+        unsigned emit = 0, close = 0, push = 0;
+        pol.init(row, active);
+        if (active) {
+            active = pol.next_root(parent);
+            need_eval = active;
+        }
+        while (__any_sync(0xffffffffu, active)) {
+            int act = 0;
+            if (active && (need_eval || reload)) c = t.child(parent, gl);
+            if (active && need_eval) act = pol.visit(c);
+            reload = false;
+            const unsigned be = (__ballot_sync(0xffffffffu, act & kVisitEmit) >> gshift) & gmask;
+            const unsigned bc = (__ballot_sync(0xffffffffu, act & kVisitClose) >> gshift) & gmask;
+            const unsigned bp = (__ballot_sync(0xffffffffu, act & kVisitPush) >> gshift) & gmask;
+            if (active && need_eval) {
+                emit = be; close = bc; push = bp; need_eval = false;
+                if (++expansions > max_exp) { ok = false; active = false; }
+            }
+            const int first_push = push ? (__ffs(push) - 1) : NB;
+            const unsigned lowmask = (first_push >= NB) ? gmask : ((2u << first_push) - 1u);
+            const unsigned eb = active ? (emit & lowmask) : 0u, cb = active ? (close & lowmask) : 0u;
+            pol.emit(eb, cb, c, gl, parent);
+            emit &= ~eb; close &= ~cb;
+            const int cm = __shfl_sync(0xffffffffu, c, gshift + (first_push < NB ? first_push : 0));
+            if (active) {
+                if (first_push < NB) {
+                    push &= ~(1u << first_push);
+                    if (emit | close | push) {
+                        stack[sp].parent = parent;
+                        stack[sp].bits = emit | (close << 8) | (push << 16);
+                        ++sp;
+                    }
+                    emit = close = push = 0;
+                    parent = cm; need_eval = true;
+                } else if (sp > 0) {
+                    --sp;
+                    parent = stack[sp].parent;
+                    const unsigned b = stack[sp].bits;
+                    emit = b & 0xffu; close = (b >> 8) & 0xffu; push = (b >> 16) & 0xffu;
+                    reload = true;
+                } else {
+                    active = pol.next_root(parent);
+                    need_eval = active;
+                }
+            }
+        }
+        pol.finish(row, row < nrows, ok, gl);
+    }
+}
+
+// colleagues (traversal.py:398-464)
+template <typename T, int DIM, bool FILL>
+struct CollPolicy {
+    const TreeView<T, DIM>& t; const T* rad; int* starts; int* lists;
+    T center[DIM]; int box, level, count; bool rooted; T nbhd; int* out;
+    __device__ CollPolicy(const TreeView<T, DIM>& t_, const T* rad_, int* st, int* li)
+        : t(t_), rad(rad_), starts(st), lists(li) {}
+    __device__ __forceinline__ void init(int row, bool valid)
+    {
+        count = 0; rooted = false; nbhd = (T)t.n_away; box = 0; level = 0; out = nullptr;
+        if (!valid) return;
+        box = row; t.center(box, center); level = t.levels[box];
+        out = FILL ? lists + starts[row] : nullptr;
+    }
+    __device__ __forceinline__ bool next_root(int& parent)
+    { if (rooted || box == 0) return false; rooted = true; parent = 0; return true; }
+    __device__ __forceinline__ int visit(int wb) const
+    {
+        if (!wb || wb == box) return 0;     // no descent into the box's own subtree (see gen_colleagues)
+        T wc[DIM]; t.center(wb, wc);
+        const int wl = t.levels[wb];
+        if (!adj_nbhd<T, DIM>(rad, center, level, nbhd, wc, wl)) return 0;
+        return (wl == level) ? kVisitEmit : kVisitPush;
+    }
+    __device__ __forceinline__ void emit(unsigned eb, unsigned, int c, int gl, int)
+    {
+        if (FILL && ((eb >> gl) & 1u)) out[count + __popc(eb & ((1u << gl) - 1u))] = c;
+        count += __popc(eb);
+    }
+    __device__ __forceinline__ void finish(int row, bool valid, bool, int gl)
+    { if (valid && !FILL && gl == 0) starts[row] = count; }
+};
+
+template <typename T, int DIM, bool FILL>
+__global__ void __launch_bounds__(kTravBlock)
+coll_coop_kernel(TreeView<T, DIM> t, int nrows, int* __restrict__ starts, int* __restrict__ lists)
+{
+    __shared__ T rad[kMaxWalkLevels];
+    __shared__ CoopFrame frames[(kTravBlock >> DIM) * kMaxWalkLevels];
+    fill_rad_table(rad, t.root_extent);
+    CollPolicy<T, DIM, FILL> pol(t, rad, starts, lists);
+    coop_walk_rows<T, DIM>(t, pol, nrows, 0x7ffffff0, frames);
+}
+
 // ---- b5 list 2: traversal.py:556-601 ---------------------------------------
 template <typename T, int DIM, class E>
 __device__ __forceinline__ void gen_list2(const TreeView<T, DIM>& t, const T* rad, const int* coll_starts,
@@ -181,6 +313,49 @@ __device__ __forceinline__ void gen_list2(const TreeView<T, DIM>& t, const T* ra
             T sc[DIM]; t.center(sib, sc);
             if (!adj_nbhd<T, DIM>(rad, center, level, nbhd, sc, t.levels[sib])) e.e0(sib);
         }
+    }
+}
+
+// list 2, one warp per row: lane k tests candidate k = (colleague of the parent, Morton
+// child) -- the order of the reference's two loops -- and the separated ones are written
+// with one coalesced store per 32 candidates.
+template <typename T, int DIM, bool FILL>
+__global__ void __launch_bounds__(256)
+list2_warp_kernel(TreeView<T, DIM> t, const int* __restrict__ row_boxes, const int* __restrict__ coll_starts,
+                  const int* __restrict__ coll_lists, int nrows, int* __restrict__ starts,
+                  int* __restrict__ lists)
+{
+    constexpr int NB = 1 << DIM;
+    __shared__ T rad[kMaxWalkLevels];
+    fill_rad_table(rad, t.root_extent);
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const T nbhd = (T)t.n_away;
+    for (int r = w; r < nrows; r += nw) {
+        const int box = row_boxes[r];
+        const int parent = t.parents[box];
+        int pos = FILL ? starts[r] : 0;
+        if (parent != box) {
+            T center[DIM]; t.center(box, center);
+            const int level = t.levels[box];
+            const int s = coll_starts[parent];
+            const int ncand = (coll_starts[parent + 1] - s) * NB;
+            for (int k0 = 0; k0 < ncand; k0 += 32) {
+                const int k = k0 + lane;
+                bool sep = false; int sib = 0;
+                if (k < ncand) {
+                    sib = t.child(coll_lists[s + k / NB], k % NB);
+                    if (sib) {
+                        T sc[DIM]; t.center(sib, sc);
+                        sep = !adj_nbhd<T, DIM>(rad, center, level, nbhd, sc, t.levels[sib]);
+                    }
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, sep);
+                if (FILL && sep) lists[pos + __popc(bal & ((1u << lane) - 1u))] = sib;
+                pos += __popc(bal);
+            }
+        }
+        if (!FILL && lane == 0) starts[r] = pos;
     }
 }
 
@@ -299,15 +474,27 @@ static int build_list_impl(int kind, int phase, const bt_tree_view* tv, const bt
     if (nrows > 0) {
         if (phase == 0) {
             switch (kind) {
-            case 0: BT_LAUNCH_LIST(0, false); break;
-            case 2: BT_LAUNCH_LIST(2, false); break;
+            case 0:
+                if (g_walk_mode & kModeColl) coll_coop_kernel<T, DIM, false><<<grid_for((int64_t)nrows << DIM, kTravBlock, 16), kTravBlock, 0, s>>>(t, nrows, starts, lists);
+                else BT_LAUNCH_LIST(0, false);
+                break;
+            case 2:
+                if (g_walk_mode & kModeList2Count) list2_warp_kernel<T, DIM, false><<<grid_for((int64_t)nrows * 32, 256, 8), 256, 0, s>>>(t, a->row_boxes, a->coll_starts, a->coll_lists, nrows, starts, lists);
+                else BT_LAUNCH_LIST(2, false);
+                break;
             case 4: BT_LAUNCH_LIST(4, false); break;
             default: return BT_ERR_BAD_ARG;
             }
         } else {
             switch (kind) {
-            case 0: BT_LAUNCH_LIST(0, true); break;
-            case 2: BT_LAUNCH_LIST(2, true); break;
+            case 0:
+                if (g_walk_mode & kModeColl) coll_coop_kernel<T, DIM, true><<<grid_for((int64_t)nrows << DIM, kTravBlock, 16), kTravBlock, 0, s>>>(t, nrows, starts, lists);
+                else BT_LAUNCH_LIST(0, true);
+                break;
+            case 2:
+                if (g_walk_mode & kModeList2Fill) list2_warp_kernel<T, DIM, true><<<grid_for((int64_t)nrows * 32, 256, 8), 256, 0, s>>>(t, a->row_boxes, a->coll_starts, a->coll_lists, nrows, starts, lists);
+                else BT_LAUNCH_LIST(2, true);
+                break;
             case 4: BT_LAUNCH_LIST(4, true); break;
             default: return BT_ERR_BAD_ARG;
             }
@@ -505,6 +692,58 @@ list1_kernel(TreeView<T, DIM> t, const int* __restrict__ target_boxes, int nrows
     }
 }
 
+// list 1, cooperative light pass
+template <typename T, int DIM, bool FILL>
+struct L1Policy {
+    const TreeView<T, DIM>& t; const T* rad; const int* target_boxes; int* starts; int* lists; HeavyWs ws;
+    T center[DIM]; int box, level, count; bool rooted, skip; int* out;
+    __device__ L1Policy(const TreeView<T, DIM>& t_, const T* rad_, const int* tb, int* st, int* li, const HeavyWs& w)
+        : t(t_), rad(rad_), target_boxes(tb), starts(st), lists(li), ws(w) {}
+    __device__ __forceinline__ void init(int row, bool valid)
+    {
+        count = 0; rooted = false; skip = true; box = 0; level = 0; out = nullptr;
+        if (!valid) return;
+        box = target_boxes[row]; t.center(box, center); level = t.levels[box];
+        skip = FILL && ws.row_heavy[row];
+        out = FILL ? lists + starts[row] : nullptr;
+    }
+    __device__ __forceinline__ bool next_root(int& parent)
+    {
+        if (rooted || skip) return false;
+        rooted = true; parent = 0;
+        if (t.flags[0] & BT_BOX_IS_SOURCE_BOX) {        // the root is checked up front (:489-495)
+            if (FILL && (threadIdx.x & ((1 << DIM) - 1)) == 0) out[0] = 0;
+            count = 1;
+        }
+        return true;
+    }
+    __device__ __forceinline__ int visit(int wb) const { return list1_visit<T, DIM>(t, rad, center, level, wb); }
+    __device__ __forceinline__ void emit(unsigned eb, unsigned, int c, int gl, int)
+    {
+        if (FILL && ((eb >> gl) & 1u)) out[count + __popc(eb & ((1u << gl) - 1u))] = c;
+        count += __popc(eb);
+    }
+    __device__ __forceinline__ void finish(int row, bool valid, bool ok, int gl)
+    {
+        if (FILL || gl != 0 || !valid) return;
+        starts[row] = ok ? count : 0;
+        ws.row_heavy[row] = ok ? 0 : 1;
+        if (!ok) ws.heavy_rows[atomicAdd(ws.hctl + kHctlNHeavy, 1)] = row;
+    }
+};
+
+template <typename T, int DIM, bool FILL>
+__global__ void __launch_bounds__(kTravBlock)
+list1_coop_kernel(TreeView<T, DIM> t, const int* __restrict__ target_boxes, int nrows,
+                  int* __restrict__ starts, int* __restrict__ lists, HeavyWs ws)
+{
+    __shared__ T rad[kMaxWalkLevels];
+    __shared__ CoopFrame frames[(kTravBlock >> DIM) * kMaxWalkLevels];
+    fill_rad_table(rad, t.root_extent);
+    L1Policy<T, DIM, FILL> pol(t, rad, target_boxes, starts, lists, ws);
+    coop_walk_rows<T, DIM>(t, pol, nrows, FILL ? 0x7ffffff0 : ws.budget, frames);
+}
+
 // BFS seed: one frontier item (row, walk parent = root) per heavy row + the root's own append
 template <typename T, int DIM, bool FILL>
 __global__ void list1_heavy_seed_kernel(TreeView<T, DIM> t, int nrows, int* __restrict__ starts, HeavyWs ws)
@@ -627,12 +866,16 @@ static int list1_impl(int phase, const bt_tree_view* tv, const int* target_boxes
     TreeView<T, DIM> t = make_view<T, DIM>(tv);
     HeavyWs ws = make_ws(w);
     const int grid = grid_for(nrows, kTravBlock, 16);
+    const int cgrid = grid_for((int64_t)nrows << DIM, kTravBlock, 16);
     const int nsteps = t.nlevels;
     if (phase == 0) {
         BT_CHECK(cudaMemsetAsync(ws.hctl, 0, sizeof(int) * BT_HCTL_SIZE, s));
         BT_CHECK(cudaMemsetAsync(ws.heavy_total, 0, sizeof(long long), s));
         if (nrows > 0) {
-            list1_kernel<T, DIM, false><<<grid, kTravBlock, 0, s>>>(t, target_boxes, nrows, starts, nullptr, ws);
+            if (g_walk_mode & kModeList1)
+                list1_coop_kernel<T, DIM, false><<<cgrid, kTravBlock, 0, s>>>(t, target_boxes, nrows, starts, nullptr, ws);
+            else
+                list1_kernel<T, DIM, false><<<grid, kTravBlock, 0, s>>>(t, target_boxes, nrows, starts, nullptr, ws);
             BT_LAUNCH_CHECK();
             list1_heavy_seed_kernel<T, DIM, false><<<kNumSMs, 256, 0, s>>>(t, nrows, starts, ws);
             BT_LAUNCH_CHECK();
@@ -647,7 +890,10 @@ static int list1_impl(int phase, const bt_tree_view* tv, const int* target_boxes
         return BT_OK;
     }
     if (nrows <= 0) return BT_OK;
-    list1_kernel<T, DIM, true><<<grid, kTravBlock, 0, s>>>(t, target_boxes, nrows, starts, lists, ws);
+    if (g_walk_mode & kModeList1)
+        list1_coop_kernel<T, DIM, true><<<cgrid, kTravBlock, 0, s>>>(t, target_boxes, nrows, starts, lists, ws);
+    else
+        list1_kernel<T, DIM, true><<<grid, kTravBlock, 0, s>>>(t, target_boxes, nrows, starts, lists, ws);
     BT_LAUNCH_CHECK();
     if (heavy_total_host > 0) {
         BT_CHECK(cudaMemsetAsync(ws.hctl + kHctlECount, 0, sizeof(int) * (BT_HCTL_SIZE - kHctlECount), s));
@@ -689,6 +935,86 @@ list3_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, int ntgt, int* __restrict_
             if (!ok) ws.heavy_rows[atomicAdd(ws.hctl + kHctlNHeavy, 1)] = r;
         }
     }
+}
+
+// list 3, cooperative light pass: per-group slot counters / cursors live in shared memory
+template <typename T, int DIM, bool FILL>
+struct L3Policy {
+    const TreeView<T, DIM>& t; const T* rad; const List3Args<T, DIM>& x; int ntgt; int* G; int* lists;
+    HeavyWs ws; int* slots;      // [nlevels + 1] of this group (shared memory)
+    L3Ctx<T, DIM> c; int box, icoll, ecoll; bool skip;
+    __device__ L3Policy(const TreeView<T, DIM>& t_, const T* rad_, const List3Args<T, DIM>& x_, int n, int* g,
+                        int* li, const HeavyWs& w, int* sl)
+        : t(t_), rad(rad_), x(x_), ntgt(n), G(g), lists(li), ws(w), slots(sl) {}
+    __device__ __forceinline__ void init(int row, bool valid)
+    {
+        box = 0; icoll = ecoll = 0; skip = true;
+        if (valid) {
+            box = x.target_boxes[row];
+            l3_make_ctx<T, DIM>(t, rad, x, box, c);
+            icoll = x.coll_starts[box]; ecoll = x.coll_starts[box + 1];
+            skip = FILL && ws.row_heavy[row];
+        }
+        const int gl = threadIdx.x & ((1 << DIM) - 1);
+        const int64_t rowlen = (int64_t)ntgt + 1;
+        __syncwarp();
+        if (valid)
+            for (int l = gl; l <= t.nlevels; l += (1 << DIM)) slots[l] = FILL ? G[l * rowlen + row] : 0;
+        __syncwarp();
+    }
+    __device__ __forceinline__ bool next_root(int& parent)
+    {
+        if (skip) return false;
+        while (icoll < ecoll) {
+            const int cb = x.coll_lists[icoll++];
+            if (cb == box) continue;
+            parent = cb;
+            return true;
+        }
+        return false;
+    }
+    __device__ __forceinline__ int visit(int wb) const { return list3_visit<T, DIM>(t, rad, x, c, wb); }
+    __device__ __forceinline__ void emit(unsigned eb, unsigned cb, int ch, int gl, int parent)
+    {
+        // called by every lane of the warp (eb = cb = 0 for idle groups)
+        int lev = 0, base_e = 0, base_c = 0;
+        if (eb | cb) {
+            lev = t.levels[parent] + 1;          // siblings share their level
+            base_e = slots[lev]; base_c = slots[t.nlevels];
+        }
+        __syncwarp();
+        if (FILL) {
+            if ((eb >> gl) & 1u) lists[base_e + __popc(eb & ((1u << gl) - 1u))] = ch;
+            if ((cb >> gl) & 1u) lists[base_c + __popc(cb & ((1u << gl) - 1u))] = ch;
+        }
+        if (gl == 0 && (eb | cb)) { slots[lev] = base_e + __popc(eb); slots[t.nlevels] = base_c + __popc(cb); }
+        __syncwarp();
+    }
+    __device__ __forceinline__ void finish(int row, bool valid, bool ok, int gl)
+    {
+        __syncwarp();
+        if (FILL || !valid) return;
+        const int64_t rowlen = (int64_t)ntgt + 1;
+        for (int l = gl; l <= t.nlevels; l += (1 << DIM)) G[l * rowlen + row] = ok ? slots[l] : 0;
+        if (gl == 0) {
+            ws.row_heavy[row] = ok ? 0 : 1;
+            if (!ok) ws.heavy_rows[atomicAdd(ws.hctl + kHctlNHeavy, 1)] = row;
+        }
+    }
+};
+
+template <typename T, int DIM, bool FILL>
+__global__ void __launch_bounds__(kTravBlock)
+list3_coop_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, int ntgt, int* __restrict__ G,
+                  int* __restrict__ lists, HeavyWs ws)
+{
+    __shared__ T rad[kMaxWalkLevels];
+    __shared__ CoopFrame frames[(kTravBlock >> DIM) * kMaxWalkLevels];
+    __shared__ int slots[(kTravBlock >> DIM) * (kMaxWalkLevels + 1)];
+    fill_rad_table(rad, t.root_extent);
+    L3Policy<T, DIM, FILL> pol(t, rad, x, ntgt, G, lists, ws,
+                               slots + (threadIdx.x >> DIM) * (kMaxWalkLevels + 1));
+    coop_walk_rows<T, DIM>(t, pol, ntgt, FILL ? 0x7ffffff0 : ws.budget, frames);
 }
 
 // BFS seed of list 3: one frontier item per (heavy row, colleague != row box)
@@ -797,13 +1123,20 @@ static int list3_impl(int phase, const bt_tree_view* tv, const bt_list3_args* a,
     const int64_t rowlen = (int64_t)ntgt + 1;
     const int64_t total_len = rowlen * nrows;
     const int grid = grid_for(ntgt, kTravBlock, 16);
+    const int cgrid = grid_for((int64_t)ntgt << DIM, kTravBlock, 16);
+    // with target extents the list-3 walks are deep (close lists): cooperative wins there
+    const bool coop3 = (g_walk_mode & kModeList3) ||
+                       ((g_walk_mode & kModeList3Auto) && a->targets_have_extent);
     const int nsteps = t.nlevels;
     if (phase == 0) {
         BT_CHECK(cudaMemsetAsync(G, 0, sizeof(int) * (total_len + 1), s));
         BT_CHECK(cudaMemsetAsync(ws.hctl, 0, sizeof(int) * BT_HCTL_SIZE, s));
         BT_CHECK(cudaMemsetAsync(ws.heavy_total, 0, sizeof(long long), s));
         if (ntgt > 0) {
-            list3_kernel<T, DIM, false><<<grid, kTravBlock, 0, s>>>(t, x, ntgt, G, nullptr, ws);
+            if (coop3)
+                list3_coop_kernel<T, DIM, false><<<cgrid, kTravBlock, 0, s>>>(t, x, ntgt, G, nullptr, ws);
+            else
+                list3_kernel<T, DIM, false><<<grid, kTravBlock, 0, s>>>(t, x, ntgt, G, nullptr, ws);
             BT_LAUNCH_CHECK();
             list3_heavy_seed_kernel<T, DIM><<<kNumSMs, 256, 0, s>>>(t, x, ws);
             BT_LAUNCH_CHECK();
@@ -823,7 +1156,10 @@ static int list3_impl(int phase, const bt_tree_view* tv, const bt_list3_args* a,
         list3_summary_kernel<<<1, 64, 0, s>>>(G, C, nrows, rowlen, summary);
         BT_LAUNCH_CHECK();
     } else if (ntgt > 0) {
-        list3_kernel<T, DIM, true><<<grid, kTravBlock, 0, s>>>(t, x, ntgt, G, lists, ws);
+        if (coop3)
+            list3_coop_kernel<T, DIM, true><<<cgrid, kTravBlock, 0, s>>>(t, x, ntgt, G, lists, ws);
+        else
+            list3_kernel<T, DIM, true><<<grid, kTravBlock, 0, s>>>(t, x, ntgt, G, lists, ws);
         BT_LAUNCH_CHECK();
         if (heavy_total_host > 0) {
             BT_CHECK(cudaMemsetAsync(ws.hctl + kHctlECount, 0, sizeof(int) * (BT_HCTL_SIZE - kHctlECount), s));
@@ -980,6 +1316,8 @@ merge_write_kernel(MergeArgs m, const int* __restrict__ o2i, int nout, const int
     } while (0)
 
 extern "C" {
+
+void bt_set_walk_mode(int mode) { bt::g_walk_mode = mode; }
 
 int bt_trav_box_list(int which, int nboxes, const uint8_t* box_flags, const int8_t* mask,
                      int32_t* out_list, int32_t* count_dev, void* stream)

@@ -87,6 +87,10 @@ long long bt_launch_count(void);
 void bt_prof_enable(int on);
 void bt_prof_reset(void);
 int bt_prof_report(char *buf, int len);   /* "name\tcalls\ttotal_ms" lines */
+/* Bit mask choosing, per builder, the group/warp-cooperative mapping (bit set) or one thread
+ * per row (the reference's mapping): 1 colleagues, 2 list 1, 4 list 3, 8 list 3 only with
+ * target extents, 16 list-2 count, 32 list-2 fill.  Default 2|8|32.  Same output either way. */
+void bt_set_walk_mode(int mode);
 
 /* deepest level the 64-bit sort key resolves for `dim` (MaxLevelsExceeded above) */
 int bt_max_key_level(int dim);

@@ -52,6 +52,23 @@ def test_parity_heavy_row_path(actx, builders, case, budget, monkeypatch):
         assert case["_trav_stats"]["heavy_rows_list1"] > 0
 
 
+@pytest.mark.parametrize("mode", [0, 1 | 2 | 4 | 16 | 32])
+@pytest.mark.parametrize(
+    "case", _HEAVY_CASES,
+    ids=[f"{c['dims']}d-{np.dtype(c['dtype']).name}-{c['name']}" for c in _HEAVY_CASES])
+def test_parity_all_walk_mappings(actx, builders, case, mode):
+    """Every builder in its one-thread-per-row mapping (0) and its cooperative mapping."""
+    from boxtree_b200 import _cabi
+    lib = _cabi.load()
+    tb, travs = builders
+    try:
+        lib.bt_set_walk_mode(mode)
+        bad = run_case(dict(case), actx, tb, travs)
+    finally:
+        lib.bt_set_walk_mode(2 | 8 | 32)
+    assert not bad, bad[:10]
+
+
 def _build(actx, src, tkw, vkw):
     from boxtree_b200 import FMMTraversalBuilder, TreeBuilder
     dkw = {k: (actx.from_numpy(v) if isinstance(v, np.ndarray) else
