@@ -202,7 +202,10 @@ def run_ours(args):
     recipe, n, dtype, desc = WORKLOADS[args.workload]
     if args.n:
         n = args.n
-    src, kw = make_inputs(recipe, n, dtype, seed_shift=rank)
+    sharded = world > 1 and args.parallelism == "sharded"
+    # replicas: every rank owns an independent problem (rank-specific seed);
+    # sharded: ONE global problem, rank r starts with the r-th slice of every particle array
+    src, kw = make_inputs(recipe, n, dtype, seed_shift=0 if sharded else rank)
     dims = len(src)
     s_bytes = 4 if dtype == "f32" else 8
 
@@ -222,6 +225,31 @@ def run_ours(args):
         tree, _ = tb(actx, dsrc, **dkw)
         trav, _ = tg(actx, tree)
         return tree, trav
+
+    if sharded:
+        from boxtree_b200 import distributed as bd
+        comm = bd.TorchDistComm()
+
+        def my_slice(t):
+            m = int(t.shape[0])
+            return t[rank * m // world:(rank + 1) * m // world].contiguous()
+
+        ssrc = [my_slice(x) for x in dsrc]
+        skw = {k: (my_slice(v) if isinstance(v, torch.Tensor) else
+                   [my_slice(x) for x in v] if k == "targets" else v) for k, v in dkw.items()}
+
+        def step_resident():  # noqa: F811
+            # NCCL all-gather of the particle slices -> replicated tree build -> only this
+            # rank's share of the traversal (masks, local tree, local traversal)
+            g = bd.allgather_particles(actx, comm, ssrc)
+            gk = dict(skw)
+            if "targets" in skw:
+                gk["targets"] = bd.allgather_particles(actx, comm, skw["targets"])
+            if "target_radii" in skw:
+                gk["target_radii"] = bd.allgather_particles(actx, comm, [skw["target_radii"]])[0]
+            tree, _ = tb(actx, g, **gk)
+            local_tree, local_trav, _, _ = bd.sharded_setup(actx, tree, tg, comm)
+            return local_tree, local_trav
 
     # pinned host copies for the end-to-end arm
     def pin(a):
@@ -282,15 +310,28 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     tree, trav = out
     ms_per_step = ms / args.steps
-    value = world * n / (ms_per_step * 1e-3) / 1e6
+    npoints_job = n if sharded else world * n
+    value = npoints_job / (ms_per_step * 1e-3) / 1e6
 
     # end to end (host buffers in, result summary out)
     e2e_steps = max(1, min(args.steps, 3))
+    if sharded:
+        def step_e2e():  # noqa: F811
+            nonlocal ssrc, skw
+            ssrc = [my_slice(x.to(device, non_blocking=True)) for x in hsrc]
+            skw = {k: (my_slice(v.to(device, non_blocking=True)) if isinstance(v, torch.Tensor) else
+                       [my_slice(x.to(device, non_blocking=True)) for x in v] if k == "targets"
+                       else v) for k, v in hkw.items()}
+            lt, ltrav = step_resident()
+            summary = torch.cat([lt.level_start_box_nrs.to(torch.int64),
+                                 ltrav.from_sep_siblings_starts[-1:].to(torch.int64),
+                                 ltrav.neighbor_source_boxes_starts[-1:].to(torch.int64)]).cpu()
+            return lt, ltrav, summary
     o = step_e2e()
     del o
     ms_e2e, o = timed(step_e2e, e2e_steps)
     d2h_bytes = int(o[2].numel() * 8)
-    e2e_value = world * n / (ms_e2e / e2e_steps * 1e-3) / 1e6
+    e2e_value = npoints_job / (ms_e2e / e2e_steps * 1e-3) / 1e6
     del o
 
     # dominant kernel, timed live with CUDA events on the launching stream
@@ -339,13 +380,17 @@ def run_ours(args):
         line = {
             "metric": "Mpoints/s TreeBuilder+FMMTraversalBuilder", "value": value,
             "unit": "Mpoints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if sharded else "weak",
             "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}" + (f" (n={n})" if args.n else ""),
                        "points_per_gpu": n, "nboxes": tree.nboxes, "nlevels": tree.nlevels,
                        "l2_policy": "inputs larger than L2" if n * dims * s_bytes > 126e6
                        else "inputs smaller than L2 (no flush)",
-                       "parallelism": "replicas" if world > 1 else "single"},
+                       "parallelism": ("sharded: NCCL all-gather of particle slices, replicated "
+                                       "tree build, traversal rows sharded by the reference's "
+                                       "DFS-order work partition" if sharded else
+                                       "replicas" if world > 1 else "single")},
             "e2e": {"value": e2e_value, "unit": "Mpoints/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
@@ -390,6 +435,9 @@ def main():
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
     ap.add_argument("--n", type=int, default=0, help="override the number of points")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parallelism", default="replicas", choices=["replicas", "sharded"],
+                    help="N > 1: independent replicas per rank (weak scaling, default) or one "
+                         "global problem with a sharded traversal (strong scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -57,7 +57,7 @@ class bt_tree_view(C.Structure):
 
 class bt_list_args(C.Structure):
     _fields_ = [("row_boxes", vp), ("coll_starts", vp), ("coll_lists", vp),
-                ("stick_out_factor", C.c_double), ("with_extent", C.c_int32)]
+                ("stick_out_factor", C.c_double), ("with_extent", C.c_int32), ("row_mask", vp)]
 
 
 class bt_list3_args(C.Structure):
@@ -121,6 +121,7 @@ SIGNATURES = {
     "bt_dist_local_lists": [_i, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "bt_dist_modify_target_flags": [_i, vp, vp, vp, vp],
     "bt_dist_box_to_user_rank": [_i, _i, _i, vp, vp, vp, vp, vp],
+    "bt_dist_restrict_target_flags": [_i, vp, vp, vp, vp, vp, vp],
 }
 
 _lib = None

@@ -152,6 +152,23 @@ __global__ void dist_modify_target_flags_kernel(int nboxes, const int* __restric
     }
 }
 
+// flags with the target bits kept only for boxes of mask_a | mask_b (sharded setup: the
+// rows of the partial traversal); need_mask = mask_a | mask_b
+__global__ void dist_restrict_target_flags_kernel(int nboxes, const unsigned char* __restrict__ flags,
+                                                  const signed char* __restrict__ mask_a,
+                                                  const signed char* __restrict__ mask_b,
+                                                  unsigned char* __restrict__ out_flags,
+                                                  signed char* __restrict__ need_mask)
+{
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nboxes; b += gridDim.x * blockDim.x) {
+        const bool need = mask_a[b] || mask_b[b];
+        unsigned char f = flags[b];
+        if (!need) f &= (unsigned char)~(BT_BOX_IS_TARGET_BOX | BT_BOX_HAS_TARGET_CHILD_BOXES);
+        out_flags[b] = f;
+        need_mask[b] = need ? 1 : 0;
+    }
+}
+
 // MaskCompressorKernel, 2-D case (tools.py:647-740): masks[nranks][nboxes] -> per box the
 // ascending list of ranks whose mask is set
 struct RankCountIn {
@@ -305,6 +322,18 @@ int bt_dist_modify_target_flags(int nboxes, const int32_t* tgt_nonchild, const i
     if (nboxes <= 0) return BT_OK;
     bt::dist_modify_target_flags_kernel<<<bt::grid_for(nboxes, 256), 256, 0, (cudaStream_t)stream>>>(
         nboxes, tgt_nonchild, tgt_cumul, box_flags);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+
+int bt_dist_restrict_target_flags(int nboxes, const uint8_t* box_flags, const int8_t* mask_a,
+                                  const int8_t* mask_b, uint8_t* out_flags, int8_t* need_mask, void* stream)
+{
+    BT_PROF("bt_dist_restrict_target_flags", (cudaStream_t)stream);
+    if (nboxes <= 0) return BT_OK;
+    bt::dist_restrict_target_flags_kernel<<<bt::grid_for(nboxes, 256), 256, 0, (cudaStream_t)stream>>>(
+        nboxes, box_flags, (const signed char*)mask_a, (const signed char*)mask_b, out_flags,
+        (signed char*)need_mask);
     BT_LAUNCH_CHECK();
     return BT_OK;
 }

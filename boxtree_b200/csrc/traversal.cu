@@ -251,16 +251,17 @@ __device__ __forceinline__ void coop_walk_rows(const TreeView<T, DIM>& t, P& pol
 // colleagues (traversal.py:398-464)
 template <typename T, int DIM, bool FILL>
 struct CollPolicy {
-    const TreeView<T, DIM>& t; const T* rad; int* starts; int* lists;
+    const TreeView<T, DIM>& t; const T* rad; int* starts; int* lists; const signed char* row_mask;
     T center[DIM]; int box, level, count; bool rooted; T nbhd; int* out;
-    __device__ CollPolicy(const TreeView<T, DIM>& t_, const T* rad_, int* st, int* li)
-        : t(t_), rad(rad_), starts(st), lists(li) {}
+    __device__ CollPolicy(const TreeView<T, DIM>& t_, const T* rad_, int* st, int* li, const signed char* rm)
+        : t(t_), rad(rad_), starts(st), lists(li), row_mask(rm) {}
     __device__ __forceinline__ void init(int row, bool valid)
     {
         count = 0; rooted = false; nbhd = (T)t.n_away; box = 0; level = 0; out = nullptr;
         if (!valid) return;
         box = row; t.center(box, center); level = t.levels[box];
         out = FILL ? lists + starts[row] : nullptr;
+        if (row_mask && !row_mask[box]) rooted = true;      // row not needed: empty list
     }
     __device__ __forceinline__ bool next_root(int& parent)
     { if (rooted || box == 0) return false; rooted = true; parent = 0; return true; }
@@ -283,12 +284,13 @@ struct CollPolicy {
 
 template <typename T, int DIM, bool FILL>
 __global__ void __launch_bounds__(kTravBlock)
-coll_coop_kernel(TreeView<T, DIM> t, int nrows, int* __restrict__ starts, int* __restrict__ lists)
+coll_coop_kernel(TreeView<T, DIM> t, int nrows, int* __restrict__ starts, int* __restrict__ lists,
+                 const signed char* __restrict__ row_mask)
 {
     __shared__ T rad[kMaxWalkLevels];
     __shared__ CoopFrame frames[(kTravBlock >> DIM) * kMaxWalkLevels];
     fill_rad_table(rad, t.root_extent);
-    CollPolicy<T, DIM, FILL> pol(t, rad, starts, lists);
+    CollPolicy<T, DIM, FILL> pol(t, rad, starts, lists, row_mask);
     coop_walk_rows<T, DIM>(t, pol, nrows, 0x7ffffff0, frames);
 }
 
@@ -418,13 +420,17 @@ __global__ void __launch_bounds__(kTravBlock)
 list_kernel(TreeView<T, DIM> t, const int* __restrict__ row_boxes, const int* __restrict__ coll_starts,
             const int* __restrict__ coll_lists, int with_extent, T stick_out_factor, int nrows,
             int* __restrict__ starts, int* __restrict__ lists, int* __restrict__ close_starts,
-            int* __restrict__ close_lists)
+            int* __restrict__ close_lists, const signed char* __restrict__ row_mask)
 {
     __shared__ T rad[kMaxWalkLevels];
     fill_rad_table(rad, t.root_extent);
     const int stride = gridDim.x * blockDim.x;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += stride) {
         const int box = row_boxes ? row_boxes[r] : r;
+        if (row_mask && !row_mask[box]) {          // row not needed by the caller: empty list
+            if (!FILL) { starts[r] = 0; if (close_starts) close_starts[r] = 0; }
+            continue;
+        }
         if (FILL) {
             FillEmit e{lists + starts[r], close_lists ? close_lists + close_starts[r] : nullptr};
             if (KIND == 0) gen_colleagues<T, DIM>(t, rad, box, e);
@@ -470,12 +476,12 @@ static int build_list_impl(int kind, int phase, const bt_tree_view* tv, const bt
 #define BT_LAUNCH_LIST(KIND, FILL)                                                              \
     list_kernel<T, DIM, KIND, FILL><<<grid, kTravBlock, 0, s>>>(                                \
         t, a->row_boxes, a->coll_starts, a->coll_lists, a->with_extent, sof, nrows, starts, lists, \
-        close_starts, close_lists)
+        close_starts, close_lists, (const signed char*)a->row_mask)
     if (nrows > 0) {
         if (phase == 0) {
             switch (kind) {
             case 0:
-                if (g_walk_mode & kModeColl) coll_coop_kernel<T, DIM, false><<<grid_for((int64_t)nrows << DIM, kTravBlock, 16), kTravBlock, 0, s>>>(t, nrows, starts, lists);
+                if (g_walk_mode & kModeColl) coll_coop_kernel<T, DIM, false><<<grid_for((int64_t)nrows << DIM, kTravBlock, 16), kTravBlock, 0, s>>>(t, nrows, starts, lists, (const signed char*)a->row_mask);
                 else BT_LAUNCH_LIST(0, false);
                 break;
             case 2:
@@ -488,7 +494,7 @@ static int build_list_impl(int kind, int phase, const bt_tree_view* tv, const bt
         } else {
             switch (kind) {
             case 0:
-                if (g_walk_mode & kModeColl) coll_coop_kernel<T, DIM, true><<<grid_for((int64_t)nrows << DIM, kTravBlock, 16), kTravBlock, 0, s>>>(t, nrows, starts, lists);
+                if (g_walk_mode & kModeColl) coll_coop_kernel<T, DIM, true><<<grid_for((int64_t)nrows << DIM, kTravBlock, 16), kTravBlock, 0, s>>>(t, nrows, starts, lists, (const signed char*)a->row_mask);
                 else BT_LAUNCH_LIST(0, true);
                 break;
             case 2:

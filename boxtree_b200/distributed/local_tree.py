@@ -73,10 +73,11 @@ def box_to_user_rank(actx, multipole_masks_all_ranks):
 
 
 def generate_local_tree(actx, global_traversal, responsible_boxes_list, comm,
-                        multipole_masks_all_ranks=None):
+                        multipole_masks_all_ranks=None, box_masks=None):
     """``local_tree.py:316-495``.  Collective on *comm* (an all-gather of the int8 multipole
     masks replaces the reference's Gather to the root + bcast) unless
-    *multipole_masks_all_ranks* ``[nranks, nboxes]`` is supplied.
+    *multipole_masks_all_ranks* ``[nranks, nboxes]`` is supplied.  *box_masks* may carry
+    precomputed masks (sharded setup); then only ``global_traversal.tree`` is used.
 
     :returns: ``(local_tree, src_idx, tgt_idx)``; the index arrays (int64, device) give the
         position of every local source/target in the global tree's particle order."""
@@ -85,7 +86,8 @@ def generate_local_tree(actx, global_traversal, responsible_boxes_list, comm,
     nb = int(gt.nboxes)
     dims = int(gt.dimensions)
     with torch.cuda.stream(actx.stream):
-        masks = get_box_masks(actx, global_traversal, responsible_boxes_list)
+        masks = box_masks if box_masks is not None else \
+            get_box_masks(actx, global_traversal, responsible_boxes_list)
         src = _local_particles_and_lists(
             actx, lib, dims, nb, int(gt.nsources), gt.coord_dtype, gt.sources_have_extent,
             masks.point_src_boxes, gt.sources, gt.source_radii, gt.box_source_starts,

@@ -89,50 +89,86 @@ class BoxMasks:
     multipole_src_boxes: Any
 
 
-def get_box_masks(actx, traversal, responsible_boxes_list) -> BoxMasks:
-    """``partition.py:330-357``."""
-    lib = _cabi.load()
+def _responsible_and_ancestors(actx, lib, tree, responsible_boxes_list):
+    nb = int(tree.nboxes)
+    sh = actx.stream_handle
+    resp_list = _dev(actx, np.asarray(responsible_boxes_list, np.int32)
+                     if not isinstance(responsible_boxes_list, torch.Tensor)
+                     else responsible_boxes_list.to(torch.int32))
+    responsible = actx.zeros(nb, np.int8)
+    check(lib.bt_dist_mask_from_list(int(resp_list.shape[0]), dptr(resp_list),
+                                     dptr(responsible), sh), "bt_dist_mask_from_list")
+    ancestors = actx.zeros(nb, np.int8)
+    check(lib.bt_dist_ancestor_mask(nb, dptr(responsible), dptr(_dev(actx, tree.box_parent_ids)),
+                                    dptr(ancestors), sh), "bt_dist_ancestor_mask")
+    return responsible, ancestors
+
+
+def _masks_from_traversal(actx, lib, traversal, responsible, ancestors) -> BoxMasks:
+    """Point-source and multipole-source masks from the rows of *traversal* that belong to
+    responsible boxes / their ancestors (``partition.py:197-297``)."""
     tree = traversal.tree
     nb = int(tree.nboxes)
     sh = actx.stream_handle
-    with torch.cuda.stream(actx.stream):
-        resp_list = _dev(actx, np.asarray(responsible_boxes_list, np.int32)
-                         if not isinstance(responsible_boxes_list, torch.Tensor)
-                         else responsible_boxes_list.to(torch.int32))
-        responsible = actx.zeros(nb, np.int8)
-        check(lib.bt_dist_mask_from_list(int(resp_list.shape[0]), dptr(resp_list),
-                                         dptr(responsible), sh), "bt_dist_mask_from_list")
-        ancestors = actx.zeros(nb, np.int8)
-        check(lib.bt_dist_ancestor_mask(nb, dptr(responsible), dptr(_dev(actx, tree.box_parent_ids)),
-                                        dptr(ancestors), sh), "bt_dist_ancestor_mask")
 
-        def add(box_list, mask_a, mask_b, starts, lists, out):
-            check(lib.bt_dist_add_list_boxes(int(box_list.shape[0]), dptr(_dev(actx, box_list)),
-                                             dptr(mask_a), dptr(mask_b), dptr(_dev(actx, starts)),
-                                             dptr(_dev(actx, lists)), dptr(out), sh),
-                  "bt_dist_add_list_boxes")
+    def add(box_list, mask_a, mask_b, starts, lists, out):
+        check(lib.bt_dist_add_list_boxes(int(box_list.shape[0]), dptr(_dev(actx, box_list)),
+                                         dptr(mask_a), dptr(mask_b), dptr(_dev(actx, starts)),
+                                         dptr(_dev(actx, lists)), dptr(out), sh),
+              "bt_dist_add_list_boxes")
 
-        # point sources: partition.py:197-252
-        src = responsible.clone()
-        add(traversal.target_boxes, responsible, None, traversal.neighbor_source_boxes_starts,
-            traversal.neighbor_source_boxes_lists, src)
-        add(traversal.target_or_target_parent_boxes, responsible, ancestors,
-            traversal.from_sep_bigger_starts, traversal.from_sep_bigger_lists, src)
-        if tree.targets_have_extent:
-            if traversal.from_sep_close_smaller_starts is not None:
-                add(traversal.target_boxes, responsible, None,
-                    traversal.from_sep_close_smaller_starts,
-                    traversal.from_sep_close_smaller_lists, src)
-            if traversal.from_sep_close_bigger_starts is not None:
-                add(traversal.target_boxes, responsible, ancestors,
-                    traversal.from_sep_close_bigger_starts,
-                    traversal.from_sep_close_bigger_lists, src)
-        # multipole sources: partition.py:255-297
-        mpole = actx.zeros(nb, np.int8)
-        add(traversal.target_or_target_parent_boxes, responsible, ancestors,
-            traversal.from_sep_siblings_starts, traversal.from_sep_siblings_lists, mpole)
-        for ilevel in range(int(tree.nlevels)):
-            bl = traversal.from_sep_smaller_by_level[ilevel]
-            add(traversal.target_boxes_sep_smaller_by_source_level[ilevel], responsible, None,
-                bl.starts, bl.lists, mpole)
+    src = responsible.clone()
+    add(traversal.target_boxes, responsible, None, traversal.neighbor_source_boxes_starts,
+        traversal.neighbor_source_boxes_lists, src)
+    add(traversal.target_or_target_parent_boxes, responsible, ancestors,
+        traversal.from_sep_bigger_starts, traversal.from_sep_bigger_lists, src)
+    if tree.targets_have_extent:
+        if traversal.from_sep_close_smaller_starts is not None:
+            add(traversal.target_boxes, responsible, None,
+                traversal.from_sep_close_smaller_starts,
+                traversal.from_sep_close_smaller_lists, src)
+        if traversal.from_sep_close_bigger_starts is not None:
+            add(traversal.target_boxes, responsible, ancestors,
+                traversal.from_sep_close_bigger_starts,
+                traversal.from_sep_close_bigger_lists, src)
+    mpole = actx.zeros(nb, np.int8)
+    add(traversal.target_or_target_parent_boxes, responsible, ancestors,
+        traversal.from_sep_siblings_starts, traversal.from_sep_siblings_lists, mpole)
+    for ilevel in range(int(tree.nlevels)):
+        bl = traversal.from_sep_smaller_by_level[ilevel]
+        add(traversal.target_boxes_sep_smaller_by_source_level[ilevel], responsible, None,
+            bl.starts, bl.lists, mpole)
     return BoxMasks(responsible, ancestors, src, mpole)
+
+
+def get_box_masks(actx, traversal, responsible_boxes_list) -> BoxMasks:
+    """``partition.py:330-357``."""
+    lib = _cabi.load()
+    with torch.cuda.stream(actx.stream):
+        responsible, ancestors = _responsible_and_ancestors(actx, lib, traversal.tree,
+                                                            responsible_boxes_list)
+        return _masks_from_traversal(actx, lib, traversal, responsible, ancestors)
+
+
+def get_box_masks_sharded(actx, tree, responsible_boxes_list, traversal_builder):
+    """The same masks WITHOUT the global traversal (which every rank of the reference
+    builds in full, ``distributed/__init__.py:201``): only the rows ``get_box_masks`` reads
+    -- those of the rank's responsible boxes and their ancestors -- are built, by running
+    the traversal builder on a copy of the tree whose target flags are cleared elsewhere.
+    Row contents depend on geometry and source flags only, so the masks are identical.
+
+    :returns: ``(BoxMasks, partial_traversal, need_mask)``"""
+    import dataclasses
+    lib = _cabi.load()
+    nb = int(tree.nboxes)
+    with torch.cuda.stream(actx.stream):
+        responsible, ancestors = _responsible_and_ancestors(actx, lib, tree, responsible_boxes_list)
+        flags = actx.empty(nb, np.uint8)
+        need = actx.empty(nb, np.int8)
+        check(lib.bt_dist_restrict_target_flags(nb, dptr(_dev(actx, tree.box_flags)), dptr(responsible),
+                                                dptr(ancestors), dptr(flags), dptr(need),
+                                                actx.stream_handle), "bt_dist_restrict_target_flags")
+        partial_tree = dataclasses.replace(tree, box_flags=flags)
+        partial_trav, _ = traversal_builder(actx, partial_tree, _colleague_row_mask=need)
+        masks = _masks_from_traversal(actx, lib, partial_trav, responsible, ancestors)
+    return masks, partial_trav, need

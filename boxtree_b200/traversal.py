@@ -230,8 +230,13 @@ class FMMTraversalBuilder:
 
     def __call__(self, actx: TorchArrayContext, tree: Tree | TreeOfBoxes, wait_for=None,
                  debug: bool = False, _from_sep_smaller_min_nsources_cumul: int | None = None,
-                 source_boxes_mask=None, source_parent_boxes_mask=None):
+                 source_boxes_mask=None, source_parent_boxes_mask=None,
+                 _colleague_row_mask=None):
         """See ``boxtree/traversal.py:1969-1990``.
+
+        :arg _colleague_row_mask: (internal, used by the sharded distributed setup) int8
+            ``[nboxes]``; same-level non-well-separated boxes are only computed for boxes
+            with a non-zero entry -- the caller guarantees that no other row is read.
 
         :returns: ``(trav, event)``; *event* is a :class:`torch.cuda.Event`.
         """
@@ -336,8 +341,11 @@ class FMMTraversalBuilder:
 
             totals = actx.zeros(8, np.int64)
 
-            def list_args(row_boxes, coll=None):
+            crm = None if _colleague_row_mask is None else dev(_colleague_row_mask, np.int8)
+
+            def list_args(row_boxes, coll=None, row_mask=None):
                 a = bt_list_args()
+                a.row_mask = dptr(row_mask)
                 a.row_boxes = dptr(row_boxes)
                 a.coll_starts = dptr(coll[0]) if coll else None
                 a.coll_lists = dptr(coll[1]) if coll else None
@@ -348,7 +356,7 @@ class FMMTraversalBuilder:
             # {{{ b3: same-level non-well-separated boxes (traversal.py:2135-2141)
 
             coll_starts = actx.empty(nboxes + 1, np.int32)
-            a_coll = list_args(None)
+            a_coll = list_args(None, row_mask=crm)
             check(lib.bt_trav_build_list(dcode, 0, 0, C.byref(tv), C.byref(a_coll), nboxes,
                                          dptr(coll_starts), None, None, None, dptr(totals), sh),
                   "colleagues count")

@@ -220,6 +220,7 @@ typedef struct {
     const int32_t *coll_lists;
     double stick_out_factor;
     int32_t with_extent;
+    const int8_t *row_mask;             /* optional [nboxes]: rows of boxes with mask 0 stay empty */
 } bt_list_args;
 
 int bt_trav_build_list(int dtype, int kind, int phase, const bt_tree_view *tree,
@@ -336,6 +337,12 @@ int bt_dist_local_lists(int nboxes, const int8_t *box_mask, const int32_t *globa
 /* modify_target_flags (local_tree.py:163-185) */
 int bt_dist_modify_target_flags(int nboxes, const int32_t *tgt_nonchild, const int32_t *tgt_cumul,
                                 uint8_t *box_flags, void *stream);
+/* sharded setup (no reference counterpart): box flags whose target bits survive only on
+ * boxes of mask_a | mask_b, so that a traversal of the result has exactly the rows
+ * get_box_masks reads; need_mask = mask_a | mask_b */
+int bt_dist_restrict_target_flags(int nboxes, const uint8_t *box_flags, const int8_t *mask_a,
+                                  const int8_t *mask_b, uint8_t *out_flags, int8_t *need_mask,
+                                  void *stream);
 /* MaskCompressorKernel 2-D (tools.py:647-740) on the gathered multipole masks
  * [nranks, nboxes]: phase 0 starts[nboxes+1] + total, phase 1 lists (ascending ranks) */
 int bt_dist_box_to_user_rank(int phase, int nboxes, int nranks, const int8_t *masks_all_ranks,

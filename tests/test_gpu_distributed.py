@@ -99,3 +99,56 @@ def test_distributed_rows_match_oracle(actx, name, nranks):
         gtrav = bd.generate_local_travs(actx, gt, tg)
         assert not trav_mismatches(wtrav, actx.to_numpy(gtrav)), r
     assert ntgt_total == rtree.ntargets
+
+
+@pytest.mark.parametrize("nranks", [1, 4])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_sharded_setup_matches_oracle(actx, name, nranks):
+    """The scalable setup (no global traversal) yields the reference flow's masks, local tree
+    and local traversal; only the colleague CSR is restricted to the rows that are read."""
+    from boxtree_b200 import FMMTraversalBuilder, TreeBuilder
+    from boxtree_b200 import distributed as bd
+    src, tkw, vkw = CASES[name]()
+    rtree = build_tree(src, **tkw)
+    rtrav = build_traversal(rtree, **vkw)
+    dkw = {k: (actx.from_numpy(v) if isinstance(v, np.ndarray) else
+               [actx.from_numpy(x) for x in v] if k == "targets" else v) for k, v in tkw.items()}
+    tree, _ = TreeBuilder(actx)(actx, [actx.from_numpy(s) for s in src], **dkw)
+    tg = FMMTraversalBuilder(actx, **vkw)
+    nb = rtree.nboxes
+    cost = (1.0 + rtree.box_source_counts_nonchild[:nb]
+            + rtree.box_target_counts_nonchild[:nb]).astype(np.float64)
+    want_resp, _ = od.partition_work(cost, rtree, nranks)
+    want_mp = np.stack([od.get_box_masks(rtrav, want_resp[r]).multipole_src_boxes
+                        for r in range(nranks)])
+
+    class Comm(FakeComm):
+        def Get_rank(self):  # noqa: N802
+            return self.rank
+
+        def allgather_tensor(self, t):
+            return actx.from_numpy(want_mp)
+
+    for r in range(nranks):
+        wt, wsrc, wtgt = od.generate_local_tree(rtrav, want_resp[r], want_mp)
+        wtrav = od.generate_local_travs(wt, **vkw)
+        lt, ltrav, sidx, tidx = bd.sharded_setup(actx, tree, tg, Comm(r, nranks))
+        g = actx.to_numpy(lt)
+        assert np.array_equal(np.asarray(g.responsible_boxes_list), want_resp[r])
+        assert np.array_equal(sidx.cpu().numpy(), wsrc) and np.array_equal(tidx.cpu().numpy(), wtgt)
+        for f in ("box_source_starts", "box_source_counts_nonchild", "box_source_counts_cumul",
+                  "box_target_starts", "box_target_counts_nonchild", "box_target_counts_cumul",
+                  "box_flags"):
+            assert np.array_equal(np.asarray(getattr(g, f)), np.asarray(getattr(wt, f))), (r, f)
+        for f in ("box_to_user_rank_starts", "box_to_user_rank_lists", "responsible_boxes_mask",
+                  "ancestor_mask"):
+            assert np.array_equal(np.asarray(getattr(g, f)), wt.extra[f]), (r, f)
+        gtrav = actx.to_numpy(ltrav)
+        bad = [b for b in trav_mismatches(wtrav, gtrav) if "same_level_non_well_sep" not in b]
+        assert not bad, (r, bad[:8])
+        # colleague rows of the boxes that are read
+        need = np.nonzero(wt.extra["responsible_boxes_mask"] | wt.extra["ancestor_mask"])[0]
+        ws, wl = wtrav.same_level_non_well_sep_boxes_starts, wtrav.same_level_non_well_sep_boxes_lists
+        gs, gl = gtrav.same_level_non_well_sep_boxes_starts, gtrav.same_level_non_well_sep_boxes_lists
+        for b in need[:: max(1, len(need) // 500)]:
+            assert np.array_equal(wl[ws[b]:ws[b + 1]], gl[gs[b]:gs[b + 1]]), (r, b)
