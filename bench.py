@@ -21,9 +21,12 @@ configuration the metric is quoted on.
   reference algorithm; the reference itself cannot run here) timed
   on the host cores on a bounded sample of the same recipe.
 
-With N > 1 (torchrun) every rank builds its own replica of the workload with a
-rank-specific seed (no data-path collective yet: the spatially decomposed
-distributed build is not part of this round) and the value is the aggregate.
+With N > 1 (torchrun) the default is ``--parallelism replicas``: every rank builds its
+own replica of the workload with a rank-specific seed, no data-path collective, the value
+is the aggregate (weak scaling).  ``--parallelism sharded`` runs ONE global problem: NCCL
+all-gather of the ranks' particle slices, replicated tree build, and only the rank's share
+of the traversal (box masks, local tree, local traversal of the reference's distributed
+setup) -- strong scaling.
 """
 from __future__ import annotations
 
@@ -336,13 +339,15 @@ def run_ours(args):
 
     # dominant kernel, timed live with CUDA events on the launching stream
     roofline = None
+    prof_steps = 2
     if rank == 0:
         lib.bt_prof_reset()
         lib.bt_prof_enable(1)
-        prof_steps = 2
+    if rank == 0 or sharded:          # sharded steps are collective: every rank takes part
         for _ in range(prof_steps):
             tree, trav = step_resident()
         torch.cuda.synchronize()
+    if rank == 0:
         lib.bt_prof_enable(0)
         rep = _cabi.profile_report()
         nested_parents = {"bt_sort_particles"}

@@ -66,17 +66,21 @@ __global__ void dist_ancestor_mask_kernel(int nboxes, const signed char* __restr
     }
 }
 
-// add_interaction_list_boxes, partition.py:135-162; row_mask2 (optional) is OR-ed in
-__global__ void dist_add_list_boxes_kernel(int nrows, const int* __restrict__ box_list,
-                                           const signed char* __restrict__ mask_a,
-                                           const signed char* __restrict__ mask_b,
-                                           const int* __restrict__ starts, const int* __restrict__ lists,
-                                           signed char* __restrict__ out_mask)
+// add_interaction_list_boxes, partition.py:135-162 (mask_b, optional, is OR-ed in).  One
+// thread per list ENTRY (its row is found by binary search in `starts`), so rows with ~1e6
+// entries do not serialise on one thread.
+__global__ void __launch_bounds__(256)
+dist_add_list_boxes_kernel(int nrows, const int* __restrict__ box_list,
+                           const signed char* __restrict__ mask_a, const signed char* __restrict__ mask_b,
+                           const int* __restrict__ starts, const int* __restrict__ lists,
+                           signed char* __restrict__ out_mask)
 {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += gridDim.x * blockDim.x) {
-        const int box = box_list[i];
-        if (!(mask_a[box] || (mask_b && mask_b[box]))) continue;
-        for (int k = starts[i]; k < starts[i + 1]; ++k) out_mask[lists[k]] = 1;
+    const int nentries = starts[nrows];
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nentries; k += gridDim.x * blockDim.x) {
+        int lo = 0, hi = nrows;                // last row with starts[row] <= k
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (starts[mid] <= k) lo = mid; else hi = mid; }
+        const int box = box_list[lo];
+        if (mask_a[box] || (mask_b && mask_b[box])) out_mask[lists[k]] = 1;
     }
 }
 
@@ -260,7 +264,7 @@ int bt_dist_add_list_boxes(int nrows, const int32_t* box_list, const int8_t* mas
 {
     BT_PROF("bt_dist_add_list_boxes", (cudaStream_t)stream);
     if (nrows <= 0) return BT_OK;
-    bt::dist_add_list_boxes_kernel<<<bt::grid_for(nrows, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+    bt::dist_add_list_boxes_kernel<<<bt::kNumSMs * 16, 256, 0, (cudaStream_t)stream>>>(
         nrows, box_list, (const signed char*)mask_a, (const signed char*)mask_b, starts, lists,
         (signed char*)out_mask);
     BT_LAUNCH_CHECK();

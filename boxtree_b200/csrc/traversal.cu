@@ -643,6 +643,7 @@ struct HeavyWs {
     int budget; unsigned char* row_heavy; int* heavy_rows; int* hctl; long long* heavy_total;
     unsigned long long* frontier[2]; long long frontier_cap; const int* dfs_rank;
     unsigned long long* ekeys[2]; unsigned* evals[2]; long long ecap;
+    const signed char* row_mask;     // optional [nboxes]: rows of boxes with mask 0 stay empty
 };
 constexpr int kHctlNHeavy = 0, kHctlOverflow = 1, kHctlECount = 2, kHctlFrontier = 8;
 
@@ -655,6 +656,7 @@ static HeavyWs make_ws(const bt_heavy_ws* w)
     h.frontier_cap = w->frontier_cap; h.dfs_rank = w->dfs_rank;
     h.ekeys[0] = (unsigned long long*)w->ekeys[0]; h.ekeys[1] = (unsigned long long*)w->ekeys[1];
     h.evals[0] = w->evals[0]; h.evals[1] = w->evals[1]; h.ecap = w->ecap;
+    h.row_mask = (const signed char*)w->row_mask;
     return h;
 }
 
@@ -684,6 +686,10 @@ list1_kernel(TreeView<T, DIM> t, const int* __restrict__ target_boxes, int nrows
     const int stride = gridDim.x * blockDim.x;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += stride) {
         const int box = target_boxes[r];
+        if (ws.row_mask && !ws.row_mask[box]) {
+            if (!FILL) { starts[r] = 0; ws.row_heavy[r] = 0; }
+            continue;
+        }
         if (FILL) {
             if (ws.row_heavy[r]) continue;
             FillEmit e{lists + starts[r], nullptr};
@@ -710,7 +716,7 @@ struct L1Policy {
         count = 0; rooted = false; skip = true; box = 0; level = 0; out = nullptr;
         if (!valid) return;
         box = target_boxes[row]; t.center(box, center); level = t.levels[box];
-        skip = FILL && ws.row_heavy[row];
+        skip = (FILL && ws.row_heavy[row]) || (ws.row_mask && !ws.row_mask[box]);
         out = FILL ? lists + starts[row] : nullptr;
     }
     __device__ __forceinline__ bool next_root(int& parent)
@@ -927,6 +933,13 @@ list3_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, int ntgt, int* __restrict_
     const int stride = gridDim.x * blockDim.x;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < ntgt; r += stride) {
         const int box = x.target_boxes[r];
+        if (ws.row_mask && !ws.row_mask[box]) {
+            if (!FILL) {
+                for (int l = 0; l <= nl; ++l) G[l * rowlen + r] = 0;
+                ws.row_heavy[r] = 0;
+            }
+            continue;
+        }
         if (FILL) {
             if (ws.row_heavy[r]) continue;
             L3Fill e; e.nlevels = nl; e.lists = lists;
@@ -959,7 +972,7 @@ struct L3Policy {
             box = x.target_boxes[row];
             l3_make_ctx<T, DIM>(t, rad, x, box, c);
             icoll = x.coll_starts[box]; ecoll = x.coll_starts[box + 1];
-            skip = FILL && ws.row_heavy[row];
+            skip = (FILL && ws.row_heavy[row]) || (ws.row_mask && !ws.row_mask[box]);
         }
         const int gl = threadIdx.x & ((1 << DIM) - 1);
         const int64_t rowlen = (int64_t)ntgt + 1;

@@ -32,8 +32,9 @@ DEFAULT_WALK_BUDGET = 1024
 class _HeavyWorkspace:
     """Device buffers of the heavy-row path for one list (lists 1 and 3)."""
 
-    def __init__(self, actx, nrows, nboxes, dfs_rank, budget):
+    def __init__(self, actx, nrows, nboxes, dfs_rank, budget, row_mask=None):
         self.actx = actx
+        self.row_mask = row_mask
         self.nrows = nrows
         self.row_heavy = actx.empty(max(nrows, 1), np.uint8)
         self.heavy_rows = actx.empty(max(nrows, 1), np.int32)
@@ -74,6 +75,7 @@ class _HeavyWorkspace:
             w.ekeys[0], w.ekeys[1] = dptr(self.ekeys[0]), dptr(self.ekeys[1])
             w.evals[0], w.evals[1] = dptr(self.evals[0]), dptr(self.evals[1])
         w.ecap = self.ecap
+        w.row_mask = dptr(self.row_mask)
         return w
 
 
@@ -231,12 +233,14 @@ class FMMTraversalBuilder:
     def __call__(self, actx: TorchArrayContext, tree: Tree | TreeOfBoxes, wait_for=None,
                  debug: bool = False, _from_sep_smaller_min_nsources_cumul: int | None = None,
                  source_boxes_mask=None, source_parent_boxes_mask=None,
-                 _colleague_row_mask=None):
+                 _colleague_row_mask=None, _list13_row_mask=None):
         """See ``boxtree/traversal.py:1969-1990``.
 
         :arg _colleague_row_mask: (internal, used by the sharded distributed setup) int8
             ``[nboxes]``; same-level non-well-separated boxes are only computed for boxes
             with a non-zero entry -- the caller guarantees that no other row is read.
+        :arg _list13_row_mask: (internal) likewise for the rows of lists 1 and 3 (and list 3
+            close): rows of target boxes with a zero entry are left empty.
 
         :returns: ``(trav, event)``; *event* is a :class:`torch.cuda.Event`.
         """
@@ -380,8 +384,9 @@ class FMMTraversalBuilder:
                                        dptr(level_start_box_nrs), dptr(box_child_ids),
                                        dptr(subtree_size), dptr(dfs_rank), sh), "bt_trav_dfs_rank")
             del subtree_size
-            ws1 = _HeavyWorkspace(actx, ntb, nboxes, dfs_rank, budget)
-            ws3 = _HeavyWorkspace(actx, ntb, nboxes, dfs_rank, budget)
+            rm13 = None if _list13_row_mask is None else dev(_list13_row_mask, np.int8)
+            ws1 = _HeavyWorkspace(actx, ntb, nboxes, dfs_rank, budget, rm13)
+            ws3 = _HeavyWorkspace(actx, ntb, nboxes, dfs_rank, budget, rm13)
 
             l1_starts = actx.empty(ntb + 1, np.int32)
 

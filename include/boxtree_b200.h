@@ -248,6 +248,7 @@ typedef struct {
     uint64_t *ekeys[2];          /* fill phase: [heavy_total] each */
     uint32_t *evals[2];
     int64_t ecap;
+    const int8_t *row_mask;      /* optional [nboxes]: rows of boxes with mask 0 stay empty */
 } bt_heavy_ws;
 
 /* pre-order (depth first, children in Morton order) rank of every box */
