@@ -291,6 +291,7 @@ def run_ours(args):
         e0.record()
         out = None
         for _ in range(steps):
+            out = None          # drop the previous step's outputs before building the next
             out = fn()
         e1.record()
         barrier()

@@ -109,7 +109,11 @@ SIGNATURES = {
                       _P(bt_heavy_ws), _i64, vp],
     "bt_trav_list1": [_i, _i, _P(bt_tree_view), vp, _i, vp, vp, vp, _P(bt_heavy_ws), _i64, vp],
     "bt_trav_dfs_rank": [_i, _i, _i, _i, vp, vp, vp, vp, vp],
-    "bt_trav_list3_compress": [_i, _i, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    "bt_trav_colleagues": [_i, _i, _P(bt_tree_view), vp, vp, vp, _i, vp, vp, vp, vp, vp, vp, vp],
+    "bt_trav_list2_starts": [_i, vp, vp, vp, vp, vp],
+    "bt_trav_list3_compress": [_i, _i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    "bt_trav_list13": [_i, _i, _P(bt_tree_view), _P(bt_list3_args), vp, _i, vp, vp, vp, vp,
+                       _P(bt_heavy_ws), _i64, vp],
     "bt_trav_merge_lists": [_i, _i, vp, _i, _P(vp), _P(vp), vp, vp, vp, vp],
     "bt_gather_i32": [_i64, vp, vp, vp, vp],
     "bt_dist_dfs_order": [_i, _i, _i, _i, vp, vp, vp, vp, vp, vp],
@@ -155,6 +159,8 @@ def load() -> C.CDLL:
         lib.bt_prof_report.restype = C.c_int
         lib.bt_set_walk_mode.argtypes = [C.c_int]
         lib.bt_set_walk_mode.restype = None
+        lib.bt_get_walk_mode.argtypes = []
+        lib.bt_get_walk_mode.restype = C.c_int
         if os.environ.get("BT_WALK_MODE"):
             lib.bt_set_walk_mode(int(os.environ["BT_WALK_MODE"]))
         _lib = lib

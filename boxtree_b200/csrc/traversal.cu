@@ -123,7 +123,7 @@ __device__ __forceinline__ void gen_colleagues(const TreeView<T, DIM>& t, const 
 }
 
 // ---- b4 list 1: traversal.py:470-550 ---------------------------------------
-constexpr int kVisitPush = 1, kVisitEmit = 2, kVisitClose = 4;
+constexpr int kVisitPush = 1, kVisitEmit = 2, kVisitClose = 4, kVisitNear = 8;
 
 // one child visit of the list-1 walk (traversal.py:508-539)
 template <typename T, int DIM>
@@ -172,15 +172,17 @@ __device__ __forceinline__ bool gen_list1(const TreeView<T, DIM>& t, const T* ra
 // Which mapping each builder uses (bit set = group/warp-cooperative, clear = one thread per
 // row); the defaults are the faster choice measured on B200 (profiles/README.md).
 constexpr int kModeColl = 1, kModeList1 = 2, kModeList3 = 4, kModeList3Auto = 8,
-              kModeList2Count = 16, kModeList2Fill = 32;
-int g_walk_mode = kModeList1 | kModeList3Auto | kModeList2Fill;
+              kModeList2Count = 16, kModeList2Fill = 32, kModeCollTopDown = 64, kModeFused13 = 128,
+              kModeNearCapZero = 256;   // testing: rows with near-field boxes above their level go heavy
+int g_walk_mode = kModeList1 | kModeList3Auto | kModeList2Fill | kModeCollTopDown | kModeFused13;
 
 struct CoopFrame { int parent; unsigned bits; };
 
 // Policy P (one object per lane, group-uniform state):
 //   void init(int row, bool valid);               (called by ALL lanes of the warp)
 //   bool next_root(int& parent); int visit(int wb);
-//   void emit(unsigned eb, unsigned cb, int c, int gl, int parent);   (ALL lanes)
+//   void emit(unsigned eb, unsigned cb, unsigned qb, int c, int gl, int parent);   (ALL lanes;
+//        eb/cb/qb = children whose visit returned kVisitEmit / kVisitClose / kVisitNear)
 //   void finish(int row, bool valid, bool ok, int gl);                (ALL lanes)
 template <typename T, int DIM, class P>
 __device__ __forceinline__ void coop_walk_rows(const TreeView<T, DIM>& t, P& pol, int nrows, int budget,
@@ -198,7 +200,7 @@ __device__ __forceinline__ void coop_walk_rows(const TreeView<T, DIM>& t, P& pol
         const int row = rbase + g;
         bool active = row < nrows, ok = true, need_eval = false, reload = false;
         int parent = 0, sp = 0, c = 0, expansions = 0;
-        unsigned emit = 0, close = 0, push = 0;
+        unsigned emit = 0, close = 0, push = 0, near = 0;
         pol.init(row, active);
         if (active) {
             active = pol.next_root(parent);
@@ -212,31 +214,33 @@ __device__ __forceinline__ void coop_walk_rows(const TreeView<T, DIM>& t, P& pol
             const unsigned be = (__ballot_sync(0xffffffffu, act & kVisitEmit) >> gshift) & gmask;
             const unsigned bc = (__ballot_sync(0xffffffffu, act & kVisitClose) >> gshift) & gmask;
             const unsigned bp = (__ballot_sync(0xffffffffu, act & kVisitPush) >> gshift) & gmask;
+            const unsigned bq = (__ballot_sync(0xffffffffu, act & kVisitNear) >> gshift) & gmask;
             if (active && need_eval) {
-                emit = be; close = bc; push = bp; need_eval = false;
+                emit = be; close = bc; push = bp; near = bq; need_eval = false;
                 if (++expansions > max_exp) { ok = false; active = false; }
             }
             const int first_push = push ? (__ffs(push) - 1) : NB;
             const unsigned lowmask = (first_push >= NB) ? gmask : ((2u << first_push) - 1u);
             const unsigned eb = active ? (emit & lowmask) : 0u, cb = active ? (close & lowmask) : 0u;
-            pol.emit(eb, cb, c, gl, parent);
-            emit &= ~eb; close &= ~cb;
+            const unsigned qb = active ? (near & lowmask) : 0u;
+            pol.emit(eb, cb, qb, c, gl, parent);
+            emit &= ~eb; close &= ~cb; near &= ~qb;
             const int cm = __shfl_sync(0xffffffffu, c, gshift + (first_push < NB ? first_push : 0));
             if (active) {
                 if (first_push < NB) {
                     push &= ~(1u << first_push);
-                    if (emit | close | push) {
+                    if (emit | close | push | near) {
                         stack[sp].parent = parent;
-                        stack[sp].bits = emit | (close << 8) | (push << 16);
+                        stack[sp].bits = emit | (close << 8) | (push << 16) | (near << 24);
                         ++sp;
                     }
-                    emit = close = push = 0;
+                    emit = close = push = near = 0;
                     parent = cm; need_eval = true;
                 } else if (sp > 0) {
                     --sp;
                     parent = stack[sp].parent;
                     const unsigned b = stack[sp].bits;
-                    emit = b & 0xffu; close = (b >> 8) & 0xffu; push = (b >> 16) & 0xffu;
+                    emit = b & 0xffu; close = (b >> 8) & 0xffu; push = (b >> 16) & 0xffu; near = b >> 24;
                     reload = true;
                 } else {
                     active = pol.next_root(parent);
@@ -273,7 +277,7 @@ struct CollPolicy {
         if (!adj_nbhd<T, DIM>(rad, center, level, nbhd, wc, wl)) return 0;
         return (wl == level) ? kVisitEmit : kVisitPush;
     }
-    __device__ __forceinline__ void emit(unsigned eb, unsigned, int c, int gl, int)
+    __device__ __forceinline__ void emit(unsigned eb, unsigned, unsigned, int c, int gl, int)
     {
         if (FILL && ((eb >> gl) & 1u)) out[count + __popc(eb & ((1u << gl) - 1u))] = c;
         count += __popc(eb);
@@ -359,6 +363,148 @@ list2_warp_kernel(TreeView<T, DIM> t, const int* __restrict__ row_boxes, const i
         }
         if (!FILL && lane == 0) starts[r] = pos;
     }
+}
+
+static int counts_to_starts(int* a, int64_t n, long long* total_out, cudaStream_t s);
+
+// ---- b3 colleagues, top-down (+ list-2 counts) -------------------------------
+// The reference finds the colleagues of every box with a walk from the root
+// (traversal.py:398-464).  The set it produces is {c on b's level, c != b, adjacent to b with
+// the n-away neighbourhood}, in depth-first (Morton) order.  Every such c is a child of a
+// colleague of parent(b) or of parent(b) itself (|i_b - i_c| <= n implies the same for the
+// parents), so the lists are built level by level from the parent's list: one warp per box
+// tests the (|coll(parent)| + 1) * 2^d candidate children with the reference's predicate;
+// parent(b) is merged into its colleague list at its depth-first rank, so candidates are
+// visited -- and appended -- in the reference's order.  The candidates that are NOT adjacent
+// and stem from a colleague of the parent are exactly list 2 of b (traversal.py:556-601):
+// their count comes for free.  Rows are staged with a fixed stride of (2n+1)^d - 1 entries
+// and compacted to CSR afterwards.
+constexpr int kXfCollSource = 1;   // b or one of its colleagues is a source box
+constexpr int kXfHasChild = 2;     // b has at least one child
+
+template <typename T, int DIM>
+__global__ void __launch_bounds__(256)
+coll_topdown_kernel(TreeView<T, DIM> t, const int* __restrict__ level_start, int lev, int stride,
+                    int* __restrict__ tmp, int* __restrict__ counts, const int* __restrict__ dfs_rank,
+                    const signed char* __restrict__ row_mask, int* __restrict__ l2cnt,
+                    unsigned char* __restrict__ xflags)
+{
+    constexpr int NB = 1 << DIM;
+    constexpr int U = 4;
+    __shared__ T rad[kMaxWalkLevels];
+    fill_rad_table(rad, t.root_extent);
+    const int lo = level_start[lev], hi = level_start[lev + 1];
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const T nbhd = (T)t.n_away;
+    for (int b = lo + w; b < hi; b += nw) {
+        const int mychild = (lane < NB) ? t.child(b, lane) : 0;
+        const unsigned char myfl = t.flags[b];
+        const bool has_child = __any_sync(0xffffffffu, mychild != 0);
+        unsigned char xf = (unsigned char)((has_child ? kXfHasChild : 0) |
+                                           ((myfl & BT_BOX_IS_SOURCE_BOX) ? kXfCollSource : 0));
+        const int p = t.parents[b];
+        if (p == b || (row_mask && !row_mask[b])) {       // root / row not needed: empty list
+            if (lane == 0) { counts[b] = 0; if (l2cnt) l2cnt[b] = 0; xflags[b] = xf; }
+            continue;
+        }
+        T center[DIM]; t.center(b, center);
+        const int level = t.levels[b];
+        const int np = counts[p];
+        const int* prow = tmp + (int64_t)p * stride;
+        // rank of the parent among its own colleagues in depth-first order
+        const int prank = dfs_rank[p];
+        int pos = 0;
+        for (int j = lane; j < np; j += 32) pos += (dfs_rank[prow[j]] < prank) ? 1 : 0;
+        pos = __reduce_add_sync(0xffffffffu, pos);
+        const int ncand = (np + 1) * NB;
+        int out = 0, n2 = 0;
+        bool src_coll = false;
+        int* orow = tmp + (int64_t)b * stride;
+        for (int k0 = 0; k0 < ncand; k0 += 32 * U) {
+            int c[U]; bool fromcoll[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = k0 + u * 32 + lane;
+                c[u] = 0; fromcoll[u] = false;
+                if (k < ncand) {
+                    const int j = k / NB, m = k % NB;
+                    const int P = (j == pos) ? p : prow[j - (j > pos ? 1 : 0)];
+                    fromcoll[u] = (j != pos);
+                    c[u] = t.child(P, m);
+                }
+            }
+            T cc[U][DIM];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                for (int a = 0; a < DIM; ++a) cc[u][a] = c[u] ? t.centers[t.aligned * a + c[u]] : (T)0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                bool adj = false, sep = false;
+                if (c[u] && c[u] != b) {
+                    adj = adj_nbhd<T, DIM>(rad, center, level, nbhd, cc[u], level);
+                    sep = !adj && fromcoll[u];
+                }
+                if (adj && (t.flags[c[u]] & BT_BOX_IS_SOURCE_BOX)) src_coll = true;
+                const unsigned ba = __ballot_sync(0xffffffffu, adj);
+                const int slot = out + __popc(ba & ((1u << lane) - 1u));
+                if (adj && slot < stride) orow[slot] = c[u];
+                out += __popc(ba);
+                n2 += __popc(__ballot_sync(0xffffffffu, sep));
+            }
+        }
+        if (__any_sync(0xffffffffu, src_coll)) xf |= kXfCollSource;
+        if (lane == 0) {
+            counts[b] = out < stride ? out : stride;
+            if (l2cnt) l2cnt[b] = n2;
+            xflags[b] = xf;
+        }
+    }
+}
+
+// staged rows -> CSR lists
+__global__ void __launch_bounds__(256)
+coll_compact_kernel(int nboxes, int stride, const int* __restrict__ tmp, const int* __restrict__ starts,
+                    int* __restrict__ lists)
+{
+    const int64_t total = (int64_t)nboxes * stride;
+    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gstride) {
+        const int b = (int)(i / stride), j = (int)(i % stride);
+        const int s = starts[b];
+        if (j < starts[b + 1] - s) lists[s + j] = tmp[i];
+    }
+}
+
+struct GatherCountIn {
+    const int* by_box; const int* rows;
+    __device__ int operator()(int64_t i) const { return by_box[rows[i]]; }
+};
+
+template <typename T, int DIM>
+static int colleagues_topdown_impl(int phase, const bt_tree_view* tv, const int* level_start,
+                                   const int* dfs_rank, const signed char* row_mask, int stride, int* tmp,
+                                   int* starts, int* lists, int* l2cnt, unsigned char* xflags,
+                                   long long* totals, cudaStream_t s)
+{
+    TreeView<T, DIM> t = make_view<T, DIM>(tv);
+    if (t.nboxes <= 0) return BT_OK;
+    if (phase == 0) {
+        const int grid = grid_for((int64_t)t.nboxes * 32, 256, 8);
+        for (int lev = 0; lev < t.nlevels; ++lev) {
+            coll_topdown_kernel<T, DIM><<<grid, 256, 0, s>>>(t, level_start, lev, stride, tmp, starts, dfs_rank,
+                                                             row_mask, l2cnt, xflags);
+            BT_LAUNCH_CHECK();
+        }
+        BT_TRY(counts_to_starts(starts, t.nboxes, totals, s));
+    } else {
+        coll_compact_kernel<<<grid_for((int64_t)t.nboxes * stride, 256, 8), 256, 0, s>>>(t.nboxes, stride, tmp,
+                                                                                        starts, lists);
+        BT_LAUNCH_CHECK();
+    }
+    return BT_OK;
 }
 
 // ---- b7 list 4 (+close): traversal.py:931-1146 -----------------------------
@@ -560,8 +706,9 @@ __device__ __forceinline__ int list3_visit(const TreeView<T, DIM>& t, const T* r
     if (!(wb && (cfl & (BT_BOX_IS_SOURCE_BOX | BT_BOX_HAS_SOURCE_CHILD_BOXES)))) return 0;
     T wc[DIM]; t.center(wb, wc);
     const int walk_level = t.levels[wb];
-    if (adj_nbhd<T, DIM>(rad, c.tc, c.tgt_level, (T)1, wc, walk_level))
-        return (cfl & BT_BOX_HAS_SOURCE_CHILD_BOXES) ? kVisitPush : 0;
+    if (adj_nbhd<T, DIM>(rad, c.tc, c.tgt_level, (T)1, wc, walk_level))   // what list 1 does here (:508-539)
+        return ((cfl & BT_BOX_HAS_SOURCE_CHILD_BOXES) ? kVisitPush : 0) |
+               ((cfl & BT_BOX_IS_SOURCE_BOX) ? kVisitNear : 0);
     const T two_minus = (2 - 8 * CoordTraits<T>::eps());
     bool meets;
     if (!x.targets_have_extent) meets = true;
@@ -730,7 +877,7 @@ struct L1Policy {
         return true;
     }
     __device__ __forceinline__ int visit(int wb) const { return list1_visit<T, DIM>(t, rad, center, level, wb); }
-    __device__ __forceinline__ void emit(unsigned eb, unsigned, int c, int gl, int)
+    __device__ __forceinline__ void emit(unsigned eb, unsigned, unsigned, int c, int gl, int)
     {
         if (FILL && ((eb >> gl) & 1u)) out[count + __popc(eb & ((1u << gl) - 1u))] = c;
         count += __popc(eb);
@@ -993,7 +1140,7 @@ struct L3Policy {
         return false;
     }
     __device__ __forceinline__ int visit(int wb) const { return list3_visit<T, DIM>(t, rad, x, c, wb); }
-    __device__ __forceinline__ void emit(unsigned eb, unsigned cb, int ch, int gl, int parent)
+    __device__ __forceinline__ void emit(unsigned eb, unsigned cb, unsigned, int ch, int gl, int parent)
     {
         // called by every lane of the warp (eb = cb = 0 for idle groups)
         int lev = 0, base_e = 0, base_c = 0;
@@ -1194,6 +1341,361 @@ static int list3_impl(int phase, const bt_tree_view* tv, const bt_list3_args* a,
     return BT_OK;
 }
 
+// ---- lists 1 and 3 from ONE walk ---------------------------------------------
+// The list-3 walk of a target box b starts at b's colleagues and descends through the boxes
+// adjacent to b (traversal.py:673-870); the list-1 walk (traversal.py:470-550) starts at the
+// root and descends through the same adjacent boxes, appending the source boxes among them.
+// Below b's level the two walks visit the same boxes with the same adjacency test, so one
+// walk over the roots coll(b) U {b} (in depth-first order) yields both lists: an adjacent
+// source box goes to list 1 (kVisitNear), a non-adjacent one is handled by the list-3 rules.
+// What the list-1 walk appends ABOVE b's level -- source boxes among the colleagues of b's
+// ancestors (and the ancestors themselves) that are adjacent to b -- is collected by climbing
+// the parent chain (skipping ancestors whose xflags say there is no source box around) and
+// merged in by depth-first rank between the roots' subtrees, which restores the append order
+// of the reference's walk.  Slot nlevels+1 of the G array holds list 1.
+constexpr int kNearMax = 24;      // near-field boxes above the target's level kept per row
+
+template <typename T, int DIM, bool FILL>
+struct L13Policy {
+    static constexpr int NB = 1 << DIM;
+    const TreeView<T, DIM>& t; const T* rad; const List3Args<T, DIM>& x; int ntgt; int* G; int* lists;
+    HeavyWs ws; const unsigned char* xflags; int* slots; int* abox; int* arank;
+    L3Ctx<T, DIM> c; int box, icoll, nroots, selfpos, iroot, nA, ia, l1cur, near_cap; bool skip, l1ok, aovf;
+    __device__ L13Policy(const TreeView<T, DIM>& t_, const T* rad_, const List3Args<T, DIM>& x_, int n, int* g,
+                         int* li, const HeavyWs& w, const unsigned char* xf, int* sl, int* ab, int* ar, int cap)
+        : t(t_), rad(rad_), x(x_), ntgt(n), G(g), lists(li), ws(w), xflags(xf), slots(sl), abox(ab), arank(ar),
+          near_cap(cap) {}
+    __device__ __forceinline__ void init(int row, bool valid)
+    {
+        const int lane = threadIdx.x & 31, gl = lane % NB;
+        const unsigned gm = ((1u << NB) - 1u) << (lane - gl);
+        box = 0; icoll = 0; nroots = 0; selfpos = 0; iroot = 0; nA = 0; ia = 0; l1cur = 0;
+        skip = true; l1ok = false; aovf = false;
+        if (valid) {
+            box = x.target_boxes[row];
+            l3_make_ctx<T, DIM>(t, rad, x, box, c);
+            skip = (FILL && ws.row_heavy[row]) || (ws.row_mask && !ws.row_mask[box]);
+        }
+        const int64_t rowlen = (int64_t)ntgt + 1;
+        __syncwarp();
+        if (valid) {
+            for (int l = gl; l <= t.nlevels; l += NB) slots[l] = FILL ? G[l * rowlen + row] : 0;
+            if (FILL) l1cur = G[(int64_t)(t.nlevels + 1) * rowlen + row];
+        }
+        __syncwarp();
+        if (!valid || skip) return;
+        // from here on the groups of a warp diverge; every lane of a group does the same
+        icoll = x.coll_starts[box];
+        const int ncoll = x.coll_starts[box + 1] - icoll;
+        nroots = ncoll + 1;
+        const int brank = ws.dfs_rank[box];
+        int pos = 0;
+        for (int j = gl; j < ncoll; j += NB) pos += (ws.dfs_rank[x.coll_lists[icoll + j]] < brank) ? 1 : 0;
+#pragma unroll
+        for (int o = NB >> 1; o > 0; o >>= 1) pos += __shfl_xor_sync(gm, pos, o);
+        selfpos = pos;
+        // near-field source boxes above b's level: colleagues of the ancestors (+ the ancestors)
+        int a = box;
+        for (int lv = c.tgt_level - 1; lv >= 0; --lv) {
+            a = t.parents[a];
+            if (!(xflags[a] & kXfCollSource)) continue;
+            const int cs = x.coll_starts[a], n = x.coll_starts[a + 1] - cs;
+            for (int j0 = 0; j0 <= n; j0 += NB) {
+                const int j = j0 + gl;
+                const int sbox = (j < n) ? x.coll_lists[cs + j] : (j == n ? a : -1);
+                bool take = false;
+                if (sbox >= 0 && (t.flags[sbox] & BT_BOX_IS_SOURCE_BOX)) {
+                    if (sbox == 0) take = true;             // the root is appended up front (:489-495)
+                    else {
+                        T sc[DIM]; t.center(sbox, sc);
+                        take = adj_nbhd<T, DIM>(rad, c.tc, c.tgt_level, (T)1, sc, lv);
+                    }
+                }
+                const unsigned m = (__ballot_sync(gm, take) >> (lane - gl)) & ((1u << NB) - 1u);
+                if (take) {
+                    const int idx = nA + __popc(m & ((1u << gl) - 1u));
+                    if (idx < near_cap) { abox[idx] = sbox; arank[idx] = ws.dfs_rank[sbox]; }
+                }
+                nA += __popc(m);
+            }
+        }
+        if (nA > near_cap) { aovf = true; skip = true; nA = 0; return; }   // -> heavy-row path
+        __syncwarp(gm);
+        if (FILL && nA > 1) {
+            if (gl == 0) {
+                for (int i = 1; i < nA; ++i) {
+                    const int rk = arank[i], bx = abox[i];
+                    int j = i - 1;
+                    while (j >= 0 && arank[j] > rk) { arank[j + 1] = arank[j]; abox[j + 1] = abox[j]; --j; }
+                    arank[j + 1] = rk; abox[j + 1] = bx;
+                }
+            }
+            __syncwarp(gm);
+        }
+    }
+    __device__ __forceinline__ void flush_near(int limit, bool writer)
+    {
+        while (ia < nA && arank[ia] < limit) {
+            if (writer) lists[l1cur] = abox[ia];
+            ++l1cur; ++ia;
+        }
+    }
+    __device__ __forceinline__ bool next_root(int& parent)
+    {
+        if (skip) return false;
+        const bool writer = FILL && (threadIdx.x % NB) == 0;
+        while (iroot < nroots) {
+            const int j = iroot++;
+            const int cb = (j == selfpos) ? box : x.coll_lists[icoll + j - (j > selfpos ? 1 : 0)];
+            if (FILL) flush_near(ws.dfs_rank[cb], writer);
+            const unsigned char fl = t.flags[cb];
+            bool adj = true;
+            if (cb != box && t.n_away != 1) {
+                T sc[DIM]; t.center(cb, sc);
+                adj = adj_nbhd<T, DIM>(rad, c.tc, c.tgt_level, (T)1, sc, c.tgt_level);
+            }
+            if (adj && (fl & BT_BOX_IS_SOURCE_BOX)) {
+                if (writer) lists[l1cur] = cb;
+                ++l1cur;
+            }
+            if (cb == box) {
+                // the list-3 walk never enters b itself; list 1 does if there are sources below
+                if (!(fl & BT_BOX_HAS_SOURCE_CHILD_BOXES)) continue;
+                l1ok = true;
+            } else {
+                if (!(xflags[cb] & kXfHasChild)) continue;     // a leaf: its walk visits nothing
+                l1ok = adj && (fl & BT_BOX_HAS_SOURCE_CHILD_BOXES);
+            }
+            parent = cb;
+            return true;
+        }
+        if (FILL) flush_near(0x7fffffff, writer);
+        else { l1cur += nA - ia; ia = nA; }
+        return false;
+    }
+    __device__ __forceinline__ int visit(int wb) const
+    {
+        const int act = list3_visit<T, DIM>(t, rad, x, c, wb);
+        return l1ok ? act : (act & ~kVisitNear);
+    }
+    __device__ __forceinline__ void emit(unsigned eb, unsigned cb, unsigned qb, int ch, int gl, int parent)
+    {
+        // called by every lane of the warp (all masks 0 for idle groups)
+        int lev = 0, base_e = 0, base_c = 0;
+        if (eb | cb) {
+            lev = t.levels[parent] + 1;          // siblings share their level
+            base_e = slots[lev]; base_c = slots[t.nlevels];
+        }
+        __syncwarp();
+        if (FILL) {
+            if ((eb >> gl) & 1u) lists[base_e + __popc(eb & ((1u << gl) - 1u))] = ch;
+            if ((cb >> gl) & 1u) lists[base_c + __popc(cb & ((1u << gl) - 1u))] = ch;
+            if ((qb >> gl) & 1u) lists[l1cur + __popc(qb & ((1u << gl) - 1u))] = ch;
+        }
+        l1cur += __popc(qb);
+        if (gl == 0 && (eb | cb)) { slots[lev] = base_e + __popc(eb); slots[t.nlevels] = base_c + __popc(cb); }
+        __syncwarp();
+    }
+    __device__ __forceinline__ void finish(int row, bool valid, bool ok, int gl)
+    {
+        __syncwarp();
+        if (FILL || !valid) return;
+        const bool good = ok && !aovf;
+        const int64_t rowlen = (int64_t)ntgt + 1;
+        for (int l = gl; l <= t.nlevels; l += NB) G[l * rowlen + row] = good ? slots[l] : 0;
+        if (gl == 0) {
+            G[(int64_t)(t.nlevels + 1) * rowlen + row] = good ? l1cur : 0;
+            ws.row_heavy[row] = good ? 0 : 1;
+            if (!good) ws.heavy_rows[atomicAdd(ws.hctl + kHctlNHeavy, 1)] = row;
+        }
+    }
+};
+
+template <typename T, int DIM, bool FILL>
+__global__ void __launch_bounds__(kTravBlock)
+list13_coop_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, const unsigned char* __restrict__ xflags, int ntgt,
+                   int* __restrict__ G, int* __restrict__ lists, HeavyWs ws, int near_cap)
+{
+    __shared__ T rad[kMaxWalkLevels];
+    __shared__ CoopFrame frames[(kTravBlock >> DIM) * kMaxWalkLevels];
+    __shared__ int slots[(kTravBlock >> DIM) * (kMaxWalkLevels + 1)];
+    __shared__ int near_box[(kTravBlock >> DIM) * kNearMax], near_rank[(kTravBlock >> DIM) * kNearMax];
+    fill_rad_table(rad, t.root_extent);
+    const int grp = threadIdx.x >> DIM;
+    L13Policy<T, DIM, FILL> pol(t, rad, x, ntgt, G, lists, ws, xflags, slots + grp * (kMaxWalkLevels + 1),
+                                near_box + grp * kNearMax, near_rank + grp * kNearMax, near_cap);
+    coop_walk_rows<T, DIM>(t, pol, ntgt, FILL ? 0x7ffffff0 : ws.budget, frames);
+}
+
+// heavy rows of the fused walk: frontier item = row << 32 | near-ok << 31 | walk parent
+template <typename T, int DIM, bool FILL>
+__global__ void __launch_bounds__(256)
+list13_heavy_seed_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, const unsigned char* __restrict__ xflags,
+                         int ntgt, int* __restrict__ G, HeavyWs ws)
+{
+    __shared__ T rad[kMaxWalkLevels];
+    fill_rad_table(rad, t.root_extent);
+    const int nheavy = ws.hctl[kHctlNHeavy];
+    const int rank_bits = bits_for(t.nboxes), row_bits = bits_for(ntgt);
+    const int64_t rowlen = (int64_t)ntgt + 1;
+    const int l1slot = t.nlevels + 1;
+    const int stride = gridDim.x * blockDim.x;
+    for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < nheavy; h += stride) {
+        const int r = ws.heavy_rows[h];
+        const int box = x.target_boxes[r];
+        T tc[DIM]; t.center(box, tc);
+        const int level = t.levels[box];
+        auto near = [&](int sbox) {
+            if (FILL) {
+                const int k = atomicAdd(ws.hctl + kHctlECount, 1);
+                if (k < ws.ecap) {
+                    ws.ekeys[0][k] = ((unsigned long long)l1slot << (rank_bits + row_bits))
+                                     | ((unsigned long long)r << rank_bits) | (unsigned)ws.dfs_rank[sbox];
+                    ws.evals[0][k] = (unsigned)sbox;
+                }
+            } else atomicAdd(G + l1slot * rowlen + r, 1);
+        };
+        int a = box;
+        for (int lv = level - 1; lv >= 0; --lv) {
+            a = t.parents[a];
+            if (!(xflags[a] & kXfCollSource)) continue;
+            const int cs = x.coll_starts[a], n = x.coll_starts[a + 1] - cs;
+            for (int j = 0; j <= n; ++j) {
+                const int sbox = (j < n) ? x.coll_lists[cs + j] : a;
+                if (!(t.flags[sbox] & BT_BOX_IS_SOURCE_BOX)) continue;
+                bool take = (sbox == 0);
+                if (!take) { T sc[DIM]; t.center(sbox, sc); take = adj_nbhd<T, DIM>(rad, tc, level, (T)1, sc, lv); }
+                if (take) near(sbox);
+            }
+        }
+        const int cs = x.coll_starts[box], n = x.coll_starts[box + 1] - cs;
+        for (int j = 0; j <= n; ++j) {
+            const int cb = (j < n) ? x.coll_lists[cs + j] : box;
+            const unsigned char fl = t.flags[cb];
+            bool adj = true;
+            if (cb != box && t.n_away != 1) {
+                T sc[DIM]; t.center(cb, sc);
+                adj = adj_nbhd<T, DIM>(rad, tc, level, (T)1, sc, level);
+            }
+            if (adj && (fl & BT_BOX_IS_SOURCE_BOX)) near(cb);
+            bool nearok;
+            if (cb == box) { if (!(fl & BT_BOX_HAS_SOURCE_CHILD_BOXES)) continue; nearok = true; }
+            else { if (!(xflags[cb] & kXfHasChild)) continue; nearok = adj && (fl & BT_BOX_HAS_SOURCE_CHILD_BOXES); }
+            const int q = atomicAdd(ws.hctl + kHctlFrontier, 1);
+            if (q < ws.frontier_cap)
+                ws.frontier[0][q] = ((unsigned long long)r << 32) | (nearok ? 0x80000000ull : 0ull) | (unsigned)cb;
+            else ws.hctl[kHctlOverflow] = 1;
+        }
+    }
+}
+
+template <typename T, int DIM, bool FILL>
+__global__ void __launch_bounds__(256)
+list13_heavy_step_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, int ntgt, int step, int* __restrict__ G,
+                         HeavyWs ws)
+{
+    constexpr int NB = 1 << DIM;
+    __shared__ T rad[kMaxWalkLevels];
+    fill_rad_table(rad, t.root_extent);
+    const unsigned long long* fin = ws.frontier[step & 1];
+    unsigned long long* fout = ws.frontier[(step + 1) & 1];
+    long long nitems = ws.hctl[kHctlFrontier + step];
+    if (nitems > ws.frontier_cap) nitems = ws.frontier_cap;
+    const long long total = nitems * NB;
+    const int rank_bits = bits_for(t.nboxes), row_bits = bits_for(ntgt);
+    const int64_t rowlen = (int64_t)ntgt + 1;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x; tid < ((total + 31) & ~31ll);
+         tid += stride) {
+        int act = 0, wb = 0, r = 0;
+        unsigned long long nearok = 0;
+        if (tid < total) {
+            const unsigned long long item = fin[tid / NB];
+            r = (int)(item >> 32);
+            nearok = item & 0x80000000ull;
+            const int parent = (int)(item & 0x7fffffffull), m = (int)(tid % NB);
+            L3Ctx<T, DIM> c; l3_make_ctx<T, DIM>(t, rad, x, x.target_boxes[r], c);
+            wb = t.child(parent, m);
+            act = list3_visit<T, DIM>(t, rad, x, c, wb);
+            if (!nearok) act &= ~kVisitNear;
+        }
+        const bool emits = (act & (kVisitEmit | kVisitClose | kVisitNear)) != 0;
+        const int slot = (act & kVisitNear) ? t.nlevels + 1 : (act & kVisitEmit) ? (int)t.levels[wb] : t.nlevels;
+        if (FILL) {
+            const long long k = warp_append(emits, ws.hctl + kHctlECount);
+            if (k >= 0 && k < ws.ecap) {
+                ws.ekeys[0][k] = ((unsigned long long)slot << (rank_bits + row_bits))
+                                 | ((unsigned long long)r << rank_bits) | (unsigned)ws.dfs_rank[wb];
+                ws.evals[0][k] = (unsigned)wb;
+            }
+        } else if (emits) atomicAdd(G + slot * rowlen + r, 1);
+        const long long q = warp_append(act & kVisitPush, ws.hctl + kHctlFrontier + step + 1);
+        if (q >= 0) {
+            if (q < ws.frontier_cap) fout[q] = ((unsigned long long)r << 32) | nearok | (unsigned)wb;
+            else ws.hctl[kHctlOverflow] = 1;
+        }
+    }
+}
+
+template <typename T, int DIM>
+static int list13_impl(int phase, const bt_tree_view* tv, const bt_list3_args* a, const unsigned char* xflags,
+                       int ntgt, int* G, int* C, int* lists, long long* summary, const bt_heavy_ws* w,
+                       long long heavy_total_host, cudaStream_t s)
+{
+    TreeView<T, DIM> t = make_view<T, DIM>(tv);
+    if (t.nlevels + 1 > kMaxWalkLevels) return BT_ERR_UNSUPPORTED;
+    HeavyWs ws = make_ws(w);
+    List3Args<T, DIM> x{a->target_boxes, a->coll_starts, a->coll_lists, (T)a->stick_out_factor,
+                        a->targets_have_extent, a->sources_have_extent, a->crit,
+                        (const T*)a->box_target_bounding_box_min, (const T*)a->box_target_bounding_box_max,
+                        a->box_source_counts_cumul, a->min_nsources_cumul};
+    const int nrows = t.nlevels + 2;             // source levels, close list, list 1
+    const int near_cap = (g_walk_mode & kModeNearCapZero) ? 0 : kNearMax;
+    const int64_t rowlen = (int64_t)ntgt + 1;
+    const int64_t total_len = rowlen * nrows;
+    const int cgrid = grid_for((int64_t)ntgt << DIM, kTravBlock, 16);
+    const int nsteps = t.nlevels;
+    if (phase == 0) {
+        BT_CHECK(cudaMemsetAsync(G, 0, sizeof(int) * (total_len + 1), s));
+        BT_CHECK(cudaMemsetAsync(ws.hctl, 0, sizeof(int) * BT_HCTL_SIZE, s));
+        BT_CHECK(cudaMemsetAsync(ws.heavy_total, 0, sizeof(long long), s));
+        if (ntgt > 0) {
+            list13_coop_kernel<T, DIM, false><<<cgrid, kTravBlock, 0, s>>>(t, x, xflags, ntgt, G, nullptr, ws, near_cap);
+            BT_LAUNCH_CHECK();
+            list13_heavy_seed_kernel<T, DIM, false><<<kNumSMs, 256, 0, s>>>(t, x, xflags, ntgt, G, ws);
+            BT_LAUNCH_CHECK();
+            for (int st = 0; st < nsteps; ++st) {
+                list13_heavy_step_kernel<T, DIM, false><<<kNumSMs * 8, 256, 0, s>>>(t, x, ntgt, st, G, ws);
+                BT_LAUNCH_CHECK();
+            }
+            heavy_total_kernel<<<kNumSMs, 256, 0, s>>>(G, rowlen, nrows, ws);
+            BT_LAUNCH_CHECK();
+        }
+        InPlaceIn in{G};
+        PlainOut out{G, summary + 2 * (nrows + 1), total_len};
+        BT_TRY(scan_exclusive(total_len, nullptr, in, out, s));
+        NonemptyIn nin{G, total_len, rowlen};
+        PlainOut nout{C, nullptr, total_len};
+        BT_TRY(scan_exclusive(total_len, nullptr, nin, nout, s));
+        list3_summary_kernel<<<1, 64, 0, s>>>(G, C, nrows, rowlen, summary);
+        BT_LAUNCH_CHECK();
+    } else if (ntgt > 0) {
+        list13_coop_kernel<T, DIM, true><<<cgrid, kTravBlock, 0, s>>>(t, x, xflags, ntgt, G, lists, ws, near_cap);
+        BT_LAUNCH_CHECK();
+        if (heavy_total_host > 0) {
+            BT_CHECK(cudaMemsetAsync(ws.hctl + kHctlECount, 0, sizeof(int) * (BT_HCTL_SIZE - kHctlECount), s));
+            list13_heavy_seed_kernel<T, DIM, true><<<kNumSMs, 256, 0, s>>>(t, x, xflags, ntgt, G, ws);
+            BT_LAUNCH_CHECK();
+            for (int st = 0; st < nsteps; ++st) {
+                list13_heavy_step_kernel<T, DIM, true><<<kNumSMs * 8, 256, 0, s>>>(t, x, ntgt, st, G, ws);
+                BT_LAUNCH_CHECK();
+            }
+            BT_TRY(heavy_sort_and_scatter(ws, heavy_total_host, t.nboxes, ntgt, nrows, rowlen, G, lists, s));
+        }
+    }
+    return BT_OK;
+}
+
 // global DFS pre-order rank of every box (children in Morton order): the append order of
 // every reference walk is this order restricted to the appended boxes
 template <int DIM>
@@ -1233,16 +1735,18 @@ list3_compress_kernel(int nlevels, int ntgt, const int* __restrict__ G, const in
                       const int* __restrict__ target_boxes, int* __restrict__ cstarts,
                       int* __restrict__ nonempty_indices, int* __restrict__ tb_nonempty,
                       int* __restrict__ compressed_indices /*[nlevels][ntgt+1]*/,
-                      int* __restrict__ close_starts /*[ntgt+1] or null*/)
+                      int* __restrict__ close_starts /*[ntgt+1] or null*/,
+                      int* __restrict__ list1_starts /*[ntgt+1] or null (G has a list-1 row)*/)
 {
     const int64_t rowlen = (int64_t)ntgt + 1;
-    const int64_t total = rowlen * (nlevels + 1);
+    const int64_t total = rowlen * (nlevels + (list1_starts ? 2 : 1));
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         const int l = (int)(i / rowlen), tt = (int)(i % rowlen);
         const int g0 = G[(int64_t)l * rowlen];
         const int local_start = G[i] - g0;
         if (l == nlevels) { if (close_starts) close_starts[tt] = local_start; continue; }
+        if (l == nlevels + 1) { list1_starts[tt] = local_start; continue; }
         const int c0 = C[(int64_t)l * rowlen];
         const int ci = C[i] - c0;
         compressed_indices[i] = ci;
@@ -1337,6 +1841,27 @@ merge_write_kernel(MergeArgs m, const int* __restrict__ o2i, int nout, const int
 extern "C" {
 
 void bt_set_walk_mode(int mode) { bt::g_walk_mode = mode; }
+int bt_get_walk_mode(void) { return bt::g_walk_mode; }
+
+int bt_trav_colleagues(int dtype, int phase, const bt_tree_view* tree, const int32_t* level_start_box_nrs,
+                       const int32_t* dfs_rank, const int8_t* row_mask, int stride, int32_t* staging,
+                       int32_t* starts, int32_t* lists, int32_t* list2_count_by_box, uint8_t* xflags,
+                       int64_t* totals_dev, void* stream)
+{
+    BT_PROF(phase ? "trav_colleagues_fill" : "trav_colleagues_count", (cudaStream_t)stream);
+    BT_DISPATCH(dtype, tree->dim, colleagues_topdown_impl, phase, tree, level_start_box_nrs, dfs_rank,
+                (const signed char*)row_mask, stride, staging, starts, lists, list2_count_by_box, xflags,
+                (long long*)totals_dev, (cudaStream_t)stream);
+}
+
+int bt_trav_list2_starts(int nrows, const int32_t* row_boxes, const int32_t* list2_count_by_box,
+                         int32_t* starts, int64_t* totals_dev, void* stream)
+{
+    BT_PROF("trav_list2_count", (cudaStream_t)stream);
+    bt::GatherCountIn in{list2_count_by_box, row_boxes};
+    bt::PlainOut out{starts, (long long*)totals_dev, nrows};
+    return bt::scan_exclusive(nrows, nullptr, in, out, (cudaStream_t)stream);
+}
 
 int bt_trav_box_list(int which, int nboxes, const uint8_t* box_flags, const int8_t* mask,
                      int32_t* out_list, int32_t* count_dev, void* stream)
@@ -1387,6 +1912,15 @@ int bt_trav_list3(int dtype, int phase, const bt_tree_view* tree, const bt_list3
                 (long long*)summary_dev, ws, (long long)heavy_total, (cudaStream_t)stream);
 }
 
+int bt_trav_list13(int dtype, int phase, const bt_tree_view* tree, const bt_list3_args* args,
+                   const uint8_t* xflags, int ntarget_boxes, int32_t* G, int32_t* C, int32_t* lists,
+                   int64_t* summary_dev, const bt_heavy_ws* ws, int64_t heavy_total, void* stream)
+{
+    BT_PROF(phase ? "trav_list13_fill" : "trav_list13_count", (cudaStream_t)stream);
+    BT_DISPATCH(dtype, tree->dim, list13_impl, phase, tree, args, xflags, ntarget_boxes, G, C, lists,
+                (long long*)summary_dev, ws, (long long)heavy_total, (cudaStream_t)stream);
+}
+
 int bt_trav_dfs_rank(int dim, int nboxes, int aligned_nboxes, int nlevels,
                      const int32_t* level_start_box_nrs, const int32_t* box_child_ids,
                      int32_t* subtree_size, int32_t* dfs_rank, void* stream)
@@ -1413,13 +1947,14 @@ int bt_trav_dfs_rank(int dim, int nboxes, int aligned_nboxes, int nlevels,
 int bt_trav_list3_compress(int nlevels, int ntarget_boxes, const int32_t* G, const int32_t* C,
                            const int32_t* target_boxes, int32_t* compressed_starts,
                            int32_t* nonempty_indices, int32_t* target_boxes_nonempty,
-                           int32_t* compressed_indices, int32_t* close_starts, void* stream)
+                           int32_t* compressed_indices, int32_t* close_starts, int32_t* list1_starts,
+                           void* stream)
 {
     BT_PROF("bt_trav_list3_compress", (cudaStream_t)stream);
-    const int64_t total = ((int64_t)ntarget_boxes + 1) * (nlevels + 1);
+    const int64_t total = ((int64_t)ntarget_boxes + 1) * (nlevels + (list1_starts ? 2 : 1));
     bt::list3_compress_kernel<<<bt::grid_for(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(
         nlevels, ntarget_boxes, G, C, target_boxes, compressed_starts, nonempty_indices,
-        target_boxes_nonempty, compressed_indices, close_starts);
+        target_boxes_nonempty, compressed_indices, close_starts, list1_starts);
     BT_LAUNCH_CHECK();
     return BT_OK;
 }

@@ -28,6 +28,10 @@ CRIT_CODE = {"static_linf": 0, "precise_linf": 1, "static_l2": 2}
 #: to the grid-wide "heavy row" path (csrc/traversal.cu); BT_WALK_BUDGET overrides (tests)
 DEFAULT_WALK_BUDGET = 1024
 
+# bits of bt_set_walk_mode (include/boxtree_b200.h) that select a different host sequence
+WALK_MODE_COLL_TOPDOWN = 64
+WALK_MODE_FUSED13 = 128
+
 
 class _HeavyWorkspace:
     """Device buffers of the heavy-row path for one list (lists 1 and 3)."""
@@ -357,26 +361,7 @@ class FMMTraversalBuilder:
                 a.with_extent = int(with_extent)
                 return a
 
-            # {{{ b3: same-level non-well-separated boxes (traversal.py:2135-2141)
-
-            coll_starts = actx.empty(nboxes + 1, np.int32)
-            a_coll = list_args(None, row_mask=crm)
-            check(lib.bt_trav_build_list(dcode, 0, 0, C.byref(tv), C.byref(a_coll), nboxes,
-                                         dptr(coll_starts), None, None, None, dptr(totals), sh),
-                  "colleagues count")
-            total = int(_read_i64(actx, totals)[0])
-            _check_int32(total, "same_level_non_well_sep_boxes")
-            coll_lists = actx.empty(total, np.int32)
-            check(lib.bt_trav_build_list(dcode, 0, 1, C.byref(tv), C.byref(a_coll), nboxes,
-                                         dptr(coll_starts), dptr(coll_lists), None, None,
-                                         dptr(totals), sh), "colleagues fill")
-            coll = (coll_starts, coll_lists)
-
-            # }}}
-
-            # {{{ count phases of lists 1-4, then ONE readback
-
-            # pre-order rank of every box: orders the entries of heavy rows
+            # pre-order rank of every box: orders colleagues and the entries of heavy rows
             budget = int(os.environ.get("BT_WALK_BUDGET", DEFAULT_WALK_BUDGET))
             subtree_size = actx.empty(max(nboxes, 1), np.int32)
             dfs_rank = actx.empty(max(nboxes, 1), np.int32)
@@ -384,8 +369,50 @@ class FMMTraversalBuilder:
                                        dptr(level_start_box_nrs), dptr(box_child_ids),
                                        dptr(subtree_size), dptr(dfs_rank), sh), "bt_trav_dfs_rank")
             del subtree_size
+
+            # {{{ b3: same-level non-well-separated boxes (traversal.py:2135-2141)
+
+            walk_mode = int(lib.bt_get_walk_mode())
+            topdown = bool(walk_mode & WALK_MODE_COLL_TOPDOWN)
+            coll_starts = actx.empty(nboxes + 1, np.int32)
+            l2_count_by_box = xflags = None
+            if topdown:
+                # level by level from the parent's colleagues; list-2 counts come for free
+                stride = (2 * int(self.well_sep_is_n_away) + 1) ** dimensions - 1
+                staging = actx.empty(max(nboxes, 1) * stride, np.int32)
+                l2_count_by_box = actx.empty(max(nboxes, 1), np.int32)
+                xflags = actx.empty(max(nboxes, 1), np.uint8)
+
+                def colleagues(phase, lists):
+                    check(lib.bt_trav_colleagues(
+                        dcode, phase, C.byref(tv), dptr(level_start_box_nrs), dptr(dfs_rank),
+                        dptr(crm), stride, dptr(staging), dptr(coll_starts), dptr(lists),
+                        dptr(l2_count_by_box), dptr(xflags), dptr(totals), sh),
+                        "bt_trav_colleagues")
+            else:
+                a_coll = list_args(None, row_mask=crm)
+
+                def colleagues(phase, lists):
+                    check(lib.bt_trav_build_list(dcode, 0, phase, C.byref(tv), C.byref(a_coll),
+                                                 nboxes, dptr(coll_starts), dptr(lists), None,
+                                                 None, dptr(totals), sh), "colleagues")
+            colleagues(0, None)
+            total = int(_read_i64(actx, totals)[0])
+            _check_int32(total, "same_level_non_well_sep_boxes")
+            coll_lists = actx.empty(total, np.int32)
+            colleagues(1, coll_lists)
+            if topdown:
+                del staging
+            coll = (coll_starts, coll_lists)
+
+            # }}}
+
+            # {{{ count phases of lists 1-4, then ONE readback
+
+            # lists 1 and 3 from one fused walk (needs the top-down colleagues' xflags)
+            fused13 = topdown and bool(walk_mode & WALK_MODE_FUSED13)
             rm13 = None if _list13_row_mask is None else dev(_list13_row_mask, np.int8)
-            ws1 = _HeavyWorkspace(actx, ntb, nboxes, dfs_rank, budget, rm13)
+            ws1 = None if fused13 else _HeavyWorkspace(actx, ntb, nboxes, dfs_rank, budget, rm13)
             ws3 = _HeavyWorkspace(actx, ntb, nboxes, dfs_rank, budget, rm13)
 
             l1_starts = actx.empty(ntb + 1, np.int32)
@@ -394,13 +421,19 @@ class FMMTraversalBuilder:
                 check(lib.bt_trav_list1(dcode, 0, C.byref(tv), dptr(target_boxes), ntb,
                                         dptr(l1_starts), None, dptr(totals[0:]),
                                         C.byref(ws1.struct()), 0, sh), "list 1 count")
-            count_list1()
+            if not fused13:
+                count_list1()
 
             l2_starts = actx.empty(ntp + 1, np.int32)
             a2 = list_args(target_or_target_parent_boxes, coll)
-            check(lib.bt_trav_build_list(dcode, 2, 0, C.byref(tv), C.byref(a2), ntp,
-                                         dptr(l2_starts), None, None, None, dptr(totals[1:]), sh),
-                  "list 2 count")
+            if topdown:
+                check(lib.bt_trav_list2_starts(ntp, dptr(target_or_target_parent_boxes),
+                                               dptr(l2_count_by_box), dptr(l2_starts),
+                                               dptr(totals[1:]), sh), "list 2 starts")
+            else:
+                check(lib.bt_trav_build_list(dcode, 2, 0, C.byref(tv), C.byref(a2), ntp,
+                                             dptr(l2_starts), None, None, None, dptr(totals[1:]),
+                                             sh), "list 2 count")
 
             l4_starts = actx.empty(ntp + 1, np.int32)
             l4c_starts_raw = actx.empty(ntp + 1, np.int32) if with_extent else None
@@ -428,20 +461,30 @@ class FMMTraversalBuilder:
                 a3.box_source_counts_cumul = dptr(bsc)
             a3.min_nsources_cumul = int(min_nsrc)
             rowlen = ntb + 1
-            G = actx.empty((nlevels + 1) * rowlen + 1, np.int32)
-            Cc = actx.empty((nlevels + 1) * rowlen + 1, np.int32)
-            summary = actx.zeros(2 * (nlevels + 2), np.int64)
+            nslots = nlevels + (2 if fused13 else 1)     # source levels, close list[, list 1]
+            G = actx.empty(nslots * rowlen + 1, np.int32)
+            Cc = actx.empty(nslots * rowlen + 1, np.int32)
+            summary = actx.zeros(2 * (nslots + 1) + 1, np.int64)
 
             def count_list3():
-                check(lib.bt_trav_list3(dcode, 0, C.byref(tv), C.byref(a3), ntb, dptr(G), dptr(Cc),
-                                        None, dptr(summary), C.byref(ws3.struct()), 0, sh),
-                      "list 3 count")
+                if fused13:
+                    check(lib.bt_trav_list13(dcode, 0, C.byref(tv), C.byref(a3), dptr(xflags), ntb,
+                                             dptr(G), dptr(Cc), None, dptr(summary),
+                                             C.byref(ws3.struct()), 0, sh), "list 1+3 count")
+                else:
+                    check(lib.bt_trav_list3(dcode, 0, C.byref(tv), C.byref(a3), ntb, dptr(G),
+                                            dptr(Cc), None, dptr(summary), C.byref(ws3.struct()),
+                                            0, sh), "list 3 count")
             count_list3()
+
+            zero1 = actx.zeros(1, np.int64)
+            zero2 = actx.zeros(2, np.int64)
 
             def read_counts():
                 both = _read_i64(actx, torch.cat([
-                    totals, summary, ws1.heavy_total, ws3.heavy_total,
-                    ws1.hctl[:2].to(torch.int64), ws3.hctl[:2].to(torch.int64)]))
+                    totals, summary, zero1 if fused13 else ws1.heavy_total, ws3.heavy_total,
+                    zero2 if fused13 else ws1.hctl[:2].to(torch.int64),
+                    ws3.hctl[:2].to(torch.int64)]))
                 ns = summary.shape[0]
                 return both[:8], both[8:8 + ns], both[8 + ns:]
 
@@ -460,22 +503,29 @@ class FMMTraversalBuilder:
                                "heavy_rows_list3": int(heavy[4 + HCTL_NHEAVY]),
                                "heavy_entries_list1": heavy1_total,
                                "heavy_entries_list3": heavy3_total}
-            g0 = summ[:nlevels + 2]              # G[l][0], l = 0..nlevels, then grand total
-            c0 = summ[nlevels + 2:]
-            _check_int32(int(tot[0]), "neighbor_source_boxes")
+            g0 = summ[:nslots + 1]               # G[l][0], l = 0..nslots-1, then grand total
+            c0 = summ[nslots + 1:2 * (nslots + 1)]
+            if fused13:
+                # the flattened scan is int32: the 64-bit grand total tells whether it wrapped
+                _check_int32(int(summ[2 * (nslots + 1)]), "from_sep_smaller + neighbor_source_boxes")
+                l1_total = int(g0[nlevels + 2] - g0[nlevels + 1])
+            else:
+                l1_total = int(tot[0])
+            _check_int32(l1_total, "neighbor_source_boxes")
             _check_int32(int(tot[1]), "from_sep_siblings")
             _check_int32(int(tot[2]), "from_sep_bigger")
-            _check_int32(int(g0[nlevels + 1]), "from_sep_smaller")
+            _check_int32(int(g0[nslots]), "from_sep_smaller")
 
             # }}}
 
             # {{{ fill phases
 
-            l1_lists = actx.empty(int(tot[0]), np.int32)
-            ws1.alloc_entries(heavy1_total)
-            check(lib.bt_trav_list1(dcode, 1, C.byref(tv), dptr(target_boxes), ntb,
-                                    dptr(l1_starts), dptr(l1_lists), None,
-                                    C.byref(ws1.struct()), heavy1_total, sh), "list 1 fill")
+            if not fused13:
+                l1_lists = actx.empty(l1_total, np.int32)
+                ws1.alloc_entries(heavy1_total)
+                check(lib.bt_trav_list1(dcode, 1, C.byref(tv), dptr(target_boxes), ntb,
+                                        dptr(l1_starts), dptr(l1_lists), None,
+                                        C.byref(ws1.struct()), heavy1_total, sh), "list 1 fill")
             del ws1
             l2_lists = actx.empty(int(tot[1]), np.int32)
             check(lib.bt_trav_build_list(dcode, 2, 1, C.byref(tv), C.byref(a2), ntp,
@@ -487,11 +537,17 @@ class FMMTraversalBuilder:
                                          dptr(l4_starts), dptr(l4_lists), dptr(l4c_starts_raw),
                                          dptr(l4c_lists_raw), None, sh), "list 4 fill")
 
-            l3_all = actx.empty(int(g0[nlevels + 1]), np.int32)
+            l3_all = actx.empty(int(g0[nslots]), np.int32)
             ws3.alloc_entries(heavy3_total)
-            check(lib.bt_trav_list3(dcode, 1, C.byref(tv), C.byref(a3), ntb, dptr(G), dptr(Cc),
-                                    dptr(l3_all), dptr(summary), C.byref(ws3.struct()),
-                                    heavy3_total, sh), "list 3 fill")
+            if fused13:
+                check(lib.bt_trav_list13(dcode, 1, C.byref(tv), C.byref(a3), dptr(xflags), ntb,
+                                         dptr(G), dptr(Cc), dptr(l3_all), dptr(summary),
+                                         C.byref(ws3.struct()), heavy3_total, sh), "list 1+3 fill")
+                l1_lists = l3_all[int(g0[nlevels + 1]):int(g0[nlevels + 2])]
+            else:
+                check(lib.bt_trav_list3(dcode, 1, C.byref(tv), C.byref(a3), ntb, dptr(G), dptr(Cc),
+                                        dptr(l3_all), dptr(summary), C.byref(ws3.struct()),
+                                        heavy3_total, sh), "list 3 fill")
             del ws3
             nne_total = int(c0[nlevels])         # non-empty rows over all source levels
             cstarts = actx.empty(nne_total + nlevels, np.int32)
@@ -502,7 +558,9 @@ class FMMTraversalBuilder:
             check(lib.bt_trav_list3_compress(nlevels, ntb, dptr(G), dptr(Cc), dptr(target_boxes),
                                              dptr(cstarts), dptr(nonempty_all),
                                              dptr(tb_nonempty_all), dptr(comp_idx),
-                                             dptr(close3_starts), sh), "list 3 compress")
+                                             dptr(close3_starts),
+                                             dptr(l1_starts) if fused13 else None, sh),
+                  "list 3 compress")
 
             from_sep_smaller_by_level = []
             target_boxes_sep_smaller_by_source_level = []

@@ -89,8 +89,11 @@ void bt_prof_reset(void);
 int bt_prof_report(char *buf, int len);   /* "name\tcalls\ttotal_ms" lines */
 /* Bit mask choosing, per builder, the group/warp-cooperative mapping (bit set) or one thread
  * per row (the reference's mapping): 1 colleagues, 2 list 1, 4 list 3, 8 list 3 only with
- * target extents, 16 list-2 count, 32 list-2 fill.  Default 2|8|32.  Same output either way. */
+ * target extents, 16 list-2 count, 32 list-2 fill; 64 = colleagues built top-down
+ * (bt_trav_colleagues) instead of by walks, 128 = lists 1 and 3 from one fused walk
+ * (bt_trav_list13).  Same output either way. */
 void bt_set_walk_mode(int mode);
+int bt_get_walk_mode(void);
 
 /* deepest level the 64-bit sort key resolves for `dim` (MaxLevelsExceeded above) */
 int bt_max_key_level(int dim);
@@ -228,6 +231,24 @@ int bt_trav_build_list(int dtype, int kind, int phase, const bt_tree_view *tree,
                        int32_t *close_starts, int32_t *close_lists, int64_t *totals_dev,
                        void *stream);
 
+/* same_level_non_well_sep_boxes built top-down instead of by the reference's walk from the
+ * root (traversal.py:398-464; same set, same depth-first order): the colleagues of b are the
+ * adjacent children of parent(b) and of parent(b)'s colleagues.  One launch per level.
+ * phase 0: rows staged in `staging` [nboxes * stride], stride = (2n+1)^d - 1; starts[nboxes+1]
+ *          (total at totals_dev[0]); list2_count_by_box[nboxes] = number of from_sep_siblings
+ *          entries of every box (traversal.py:556-601, the non-adjacent candidates);
+ *          xflags[nboxes]: bit 0 = the box or one of its colleagues is a source box,
+ *          bit 1 = the box has a child.
+ * phase 1: staging -> lists.   dfs_rank from bt_trav_dfs_rank. */
+int bt_trav_colleagues(int dtype, int phase, const bt_tree_view *tree,
+                       const int32_t *level_start_box_nrs, const int32_t *dfs_rank,
+                       const int8_t *row_mask, int stride, int32_t *staging, int32_t *starts,
+                       int32_t *lists, int32_t *list2_count_by_box, uint8_t *xflags,
+                       int64_t *totals_dev, void *stream);
+/* starts[nrows+1] of from_sep_siblings from the per-box counts of bt_trav_colleagues */
+int bt_trav_list2_starts(int nrows, const int32_t *row_boxes, const int32_t *list2_count_by_box,
+                         int32_t *starts, int64_t *totals_dev, void *stream);
+
 /* Workspace of the "heavy row" path of lists 1 and 3.  A row whose walk needs more than
  * walk_budget child visits (an upper-level box holding its own targets can have ~1e6 list
  * entries) is expanded by a grid-wide breadth-first pass over the same child visits; its
@@ -290,11 +311,26 @@ int bt_trav_list3(int dtype, int phase, const bt_tree_view *tree, const bt_list3
 /* eliminate_empty_output_lists bookkeeping for all levels in one launch: compressed
  * starts (level l at offset C[l][0] + l), nonempty_indices and
  * target_boxes[nonempty_indices] (level l at offset C[l][0]; traversal.py:2211-2215),
- * compressed_indices [nlevels, ntarget_boxes + 1] and the close list's starts. */
+ * compressed_indices [nlevels, ntarget_boxes + 1] and the close list's starts (and list 1's
+ * when G carries the extra row of bt_trav_list13; NULL otherwise). */
 int bt_trav_list3_compress(int nlevels, int ntarget_boxes, const int32_t *G, const int32_t *C,
                            const int32_t *target_boxes, int32_t *compressed_starts,
                            int32_t *nonempty_indices, int32_t *target_boxes_nonempty,
-                           int32_t *compressed_indices, int32_t *close_starts, void *stream);
+                           int32_t *compressed_indices, int32_t *close_starts,
+                           int32_t *list1_starts, void *stream);
+
+/* Lists 1 and 3 (+ list 3 close) from ONE walk per target box: below the target's level the
+ * reference's list-1 walk (traversal.py:470-550) and list-3 walk (:607-875) visit the same
+ * boxes; the near-field boxes above that level come from the colleagues of the ancestors
+ * and are merged in by depth-first rank.  Needs bt_trav_colleagues' lists and xflags.
+ * G, C: int32 [nlevels + 2, ntarget_boxes + 1] (+1): rows as in bt_trav_list3, row nlevels+1
+ * is list 1.  summary_dev: int64 [2*(nlevels+3) + 1] = G[l][0], C[l][0], then the grand
+ * total in 64 bits.  bt_trav_list3_compress (list1_starts != NULL) yields the list-1 starts;
+ * its lists are lists[G[nlevels+1][0] .. G[nlevels+2][0]). */
+int bt_trav_list13(int dtype, int phase, const bt_tree_view *tree, const bt_list3_args *args,
+                   const uint8_t *xflags, int ntarget_boxes, int32_t *G, int32_t *C,
+                   int32_t *lists, int64_t *summary_dev, const bt_heavy_ws *ws,
+                   int64_t heavy_total, void *stream);
 
 /* _ListMerger (traversal.py:1153-1344): phase 0 -> new_starts[noutput+1], total at
  * totals_dev[0]; phase 1 -> new_lists.  starts/lists: HOST arrays of nlists device pointers. */

@@ -12,7 +12,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 450 --csv \
     python bench.py --workload $WL $NARG --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
 # (2) full metric set of the walk kernels and one sort pass
 ncu --set full --clock-control none --import-source on \
-    -k regex:'list3_kernel|list1_kernel|list_kernel|rs_onesweep|box_extents' -s 40 -c 12 \
+    -k regex:'list3_coop|list1_coop|coll_coop|list2_warp|list_kernel|rs_onesweep|box_extents|heavy_step' -s 300 -c 110 \
     -o gpurun_out/prof_${TAG}_${WL} \
     python bench.py --workload $WL $NARG --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu_full_${TAG}.log 2>&1
 ls -la gpurun_out/

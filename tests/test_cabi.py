@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} is declared in the header but not exported"
     # and the binding table covers the header
     bound = set(_cabi.SIGNATURES) | {"bt_launch_count", "bt_prof_enable", "bt_prof_reset",
-                                     "bt_prof_report", "bt_set_walk_mode"}
+                                     "bt_prof_report", "bt_set_walk_mode", "bt_get_walk_mode"}
     assert set(declared_symbols()) == bound
 
 
