@@ -52,7 +52,8 @@ class bt_tree_view(C.Structure):
     _fields_ = [("dim", C.c_int32), ("nboxes", C.c_int32), ("aligned_nboxes", C.c_int32),
                 ("nlevels", C.c_int32), ("root_extent", C.c_double), ("box_centers", vp),
                 ("box_levels", vp), ("box_child_ids", vp), ("box_flags", vp),
-                ("box_parent_ids", vp), ("well_sep_is_n_away", C.c_int32)]
+                ("box_parent_ids", vp), ("well_sep_is_n_away", C.c_int32),
+                ("box_child_ids_t", vp)]
 
 
 class bt_list_args(C.Structure):
@@ -109,11 +110,14 @@ SIGNATURES = {
                       _P(bt_heavy_ws), _i64, vp],
     "bt_trav_list1": [_i, _i, _P(bt_tree_view), vp, _i, vp, vp, vp, _P(bt_heavy_ws), _i64, vp],
     "bt_trav_dfs_rank": [_i, _i, _i, _i, vp, vp, vp, vp, vp],
-    "bt_trav_colleagues": [_i, _i, _P(bt_tree_view), vp, vp, vp, _i, vp, vp, vp, vp, vp, vp, vp],
+    "bt_trav_transpose_children": [_i, _i, vp, vp, vp],
+    "bt_trav_colleagues": [_i, _i, _P(bt_tree_view), vp, vp, vp, _i, vp, vp, vp, vp, vp, vp, _i,
+                           vp, vp],
+    "bt_trav_list2_fill_masked": [_i, _i, vp, vp, vp, vp, vp, vp, _i, vp, vp, vp],
     "bt_trav_list2_starts": [_i, vp, vp, vp, vp, vp],
     "bt_trav_list3_compress": [_i, _i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "bt_trav_list13": [_i, _i, _P(bt_tree_view), _P(bt_list3_args), vp, _i, vp, vp, vp, vp,
-                       _P(bt_heavy_ws), _i64, vp],
+                       _P(bt_heavy_ws), _i64, _i, vp],
     "bt_trav_merge_lists": [_i, _i, vp, _i, _P(vp), _P(vp), vp, vp, vp, vp],
     "bt_gather_i32": [_i64, vp, vp, vp, vp],
     "bt_dist_dfs_order": [_i, _i, _i, _i, vp, vp, vp, vp, vp, vp],

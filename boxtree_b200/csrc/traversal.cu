@@ -20,7 +20,7 @@ constexpr int kTravBlock = 128;
 
 template <typename T, int DIM>
 struct TreeView {
-    const T* centers; const unsigned char* levels; const int* child_ids;
+    const T* centers; const unsigned char* levels; const int* child_ids; const int* child_t;
     const unsigned char* flags; const int* parents;
     int aligned; int nboxes; int nlevels; T root_extent; int n_away;
     __device__ __forceinline__ void center(int b, T* c) const
@@ -29,7 +29,7 @@ struct TreeView {
         for (int a = 0; a < DIM; ++a) c[a] = centers[aligned * a + b];
     }
     __device__ __forceinline__ int child(int parent, int mnr) const
-    { return child_ids[mnr * aligned + parent]; }
+    { return child_t ? child_t[((int64_t)parent << DIM) + mnr] : child_ids[mnr * aligned + parent]; }
 };
 
 template <typename T, int DIM>
@@ -40,6 +40,7 @@ static TreeView<T, DIM> make_view(const bt_tree_view* v)
     t.flags = v->box_flags; t.parents = v->box_parent_ids; t.aligned = v->aligned_nboxes;
     t.nboxes = v->nboxes; t.nlevels = v->nlevels; t.root_extent = (T)v->root_extent;
     t.n_away = v->well_sep_is_n_away;
+    t.child_t = v->box_child_ids_t;
     return t;
 }
 
@@ -387,7 +388,7 @@ __global__ void __launch_bounds__(256)
 coll_topdown_kernel(TreeView<T, DIM> t, const int* __restrict__ level_start, int lev, int stride,
                     int* __restrict__ tmp, int* __restrict__ counts, const int* __restrict__ dfs_rank,
                     const signed char* __restrict__ row_mask, int* __restrict__ l2cnt,
-                    unsigned char* __restrict__ xflags)
+                    unsigned char* __restrict__ xflags, unsigned* __restrict__ l2mask, int mask_words)
 {
     constexpr int NB = 1 << DIM;
     constexpr int U = 4;
@@ -421,6 +422,8 @@ coll_topdown_kernel(TreeView<T, DIM> t, const int* __restrict__ level_start, int
         int out = 0, n2 = 0;
         bool src_coll = false;
         int* orow = tmp + (int64_t)b * stride;
+        unsigned* mrow = l2mask ? l2mask + (int64_t)b * mask_words : nullptr;
+        if (mrow && lane == 0) mrow[mask_words - 1] = (unsigned)pos;
         for (int k0 = 0; k0 < ncand; k0 += 32 * U) {
             int c[U]; bool fromcoll[U];
 #pragma unroll
@@ -452,7 +455,10 @@ coll_topdown_kernel(TreeView<T, DIM> t, const int* __restrict__ level_start, int
                 const int slot = out + __popc(ba & ((1u << lane) - 1u));
                 if (adj && slot < stride) orow[slot] = c[u];
                 out += __popc(ba);
-                n2 += __popc(__ballot_sync(0xffffffffu, sep));
+                const unsigned bs = __ballot_sync(0xffffffffu, sep);
+                n2 += __popc(bs);
+                // candidate k = (position in the merged parent list) * 2^d + Morton child
+                if (mrow && lane == 0 && k0 + u * 32 < ncand) mrow[(k0 >> 5) + u] = bs;
             }
         }
         if (__any_sync(0xffffffffu, src_coll)) xf |= kXfCollSource;
@@ -478,6 +484,40 @@ coll_compact_kernel(int nboxes, int stride, const int* __restrict__ tmp, const i
     }
 }
 
+// list 2 from the separation masks the colleague pass left behind: no geometry, the set bits
+// are the candidates (colleague of the parent, Morton child) in the reference's loop order
+template <int DIM>
+__global__ void __launch_bounds__(256)
+list2_masked_fill_kernel(int nrows, const int* __restrict__ row_boxes, const int* __restrict__ parents,
+                         const int* __restrict__ coll_starts, const int* __restrict__ coll_lists,
+                         const int* __restrict__ child_t, const unsigned* __restrict__ l2mask, int mask_words,
+                         const int* __restrict__ starts, int* __restrict__ lists)
+{
+    constexpr int NB = 1 << DIM;
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int r = w; r < nrows; r += nw) {
+        const int box = row_boxes[r];
+        const int p = parents[box];
+        if (p == box) continue;
+        const int cs = coll_starts[p];
+        const int ncand = (coll_starts[p + 1] - cs + 1) * NB;
+        const unsigned* mrow = l2mask + (int64_t)box * mask_words;
+        const int pos = (int)mrow[mask_words - 1];
+        int out = starts[r];
+        for (int k0 = 0; k0 < ncand; k0 += 32) {
+            const unsigned word = mrow[k0 >> 5];
+            if (!word) continue;
+            if ((word >> lane) & 1u) {
+                const int k = k0 + lane, j = k / NB, m = k % NB;
+                const int P = coll_lists[cs + j - (j > pos ? 1 : 0)];
+                lists[out + __popc(word & ((1u << lane) - 1u))] = child_t[((int64_t)P << DIM) + m];
+            }
+            out += __popc(word);
+        }
+    }
+}
+
 struct GatherCountIn {
     const int* by_box; const int* rows;
     __device__ int operator()(int64_t i) const { return by_box[rows[i]]; }
@@ -487,7 +527,7 @@ template <typename T, int DIM>
 static int colleagues_topdown_impl(int phase, const bt_tree_view* tv, const int* level_start,
                                    const int* dfs_rank, const signed char* row_mask, int stride, int* tmp,
                                    int* starts, int* lists, int* l2cnt, unsigned char* xflags,
-                                   long long* totals, cudaStream_t s)
+                                   unsigned* l2mask, int mask_words, long long* totals, cudaStream_t s)
 {
     TreeView<T, DIM> t = make_view<T, DIM>(tv);
     if (t.nboxes <= 0) return BT_OK;
@@ -495,7 +535,7 @@ static int colleagues_topdown_impl(int phase, const bt_tree_view* tv, const int*
         const int grid = grid_for((int64_t)t.nboxes * 32, 256, 8);
         for (int lev = 0; lev < t.nlevels; ++lev) {
             coll_topdown_kernel<T, DIM><<<grid, 256, 0, s>>>(t, level_start, lev, stride, tmp, starts, dfs_rank,
-                                                             row_mask, l2cnt, xflags);
+                                                             row_mask, l2cnt, xflags, l2mask, mask_words);
             BT_LAUNCH_CHECK();
         }
         BT_TRY(counts_to_starts(starts, t.nboxes, totals, s));
@@ -1360,7 +1400,8 @@ struct L13Policy {
     static constexpr int NB = 1 << DIM;
     const TreeView<T, DIM>& t; const T* rad; const List3Args<T, DIM>& x; int ntgt; int* G; int* lists;
     HeavyWs ws; const unsigned char* xflags; int* slots; int* abox; int* arank;
-    L3Ctx<T, DIM> c; int box, icoll, nroots, selfpos, iroot, nA, ia, l1cur, near_cap; bool skip, l1ok, aovf;
+    L3Ctx<T, DIM> c; int box, icoll, nroots, selfpos, jb, jb_next, my_cb, my_rank, nA, ia, l1cur, near_cap;
+    unsigned nearm, expm, okm; bool skip, l1ok, aovf;
     __device__ L13Policy(const TreeView<T, DIM>& t_, const T* rad_, const List3Args<T, DIM>& x_, int n, int* g,
                          int* li, const HeavyWs& w, const unsigned char* xf, int* sl, int* ab, int* ar, int cap)
         : t(t_), rad(rad_), x(x_), ntgt(n), G(g), lists(li), ws(w), xflags(xf), slots(sl), abox(ab), arank(ar),
@@ -1369,7 +1410,8 @@ struct L13Policy {
     {
         const int lane = threadIdx.x & 31, gl = lane % NB;
         const unsigned gm = ((1u << NB) - 1u) << (lane - gl);
-        box = 0; icoll = 0; nroots = 0; selfpos = 0; iroot = 0; nA = 0; ia = 0; l1cur = 0;
+        box = 0; icoll = 0; nroots = 0; selfpos = 0; jb = 0; jb_next = 0; my_cb = 0; my_rank = 0;
+        nA = 0; ia = 0; l1cur = 0; nearm = expm = okm = 0;
         skip = true; l1ok = false; aovf = false;
         if (valid) {
             box = x.target_boxes[row];
@@ -1440,34 +1482,79 @@ struct L13Policy {
             ++l1cur; ++ia;
         }
     }
-    __device__ __forceinline__ bool next_root(int& parent)
+    // the roots coll(b) U {b} are classified 2^d at a time, one root per lane of the group:
+    // near = the root itself belongs to list 1, exp = its children have to be visited
+    __device__ __forceinline__ void load_roots(int gl, unsigned gm, int gshift)
     {
-        if (skip) return false;
-        const bool writer = FILL && (threadIdx.x % NB) == 0;
-        while (iroot < nroots) {
-            const int j = iroot++;
+        const int j = jb + gl;
+        my_cb = 0; my_rank = 0;
+        bool near = false, exp = false, ok = false;
+        if (j < nroots) {
             const int cb = (j == selfpos) ? box : x.coll_lists[icoll + j - (j > selfpos ? 1 : 0)];
-            if (FILL) flush_near(ws.dfs_rank[cb], writer);
+            my_cb = cb;
             const unsigned char fl = t.flags[cb];
+            if (FILL && nA > 0) my_rank = ws.dfs_rank[cb];
             bool adj = true;
             if (cb != box && t.n_away != 1) {
                 T sc[DIM]; t.center(cb, sc);
                 adj = adj_nbhd<T, DIM>(rad, c.tc, c.tgt_level, (T)1, sc, c.tgt_level);
             }
-            if (adj && (fl & BT_BOX_IS_SOURCE_BOX)) {
-                if (writer) lists[l1cur] = cb;
-                ++l1cur;
-            }
+            near = adj && (fl & BT_BOX_IS_SOURCE_BOX);
             if (cb == box) {
                 // the list-3 walk never enters b itself; list 1 does if there are sources below
-                if (!(fl & BT_BOX_HAS_SOURCE_CHILD_BOXES)) continue;
-                l1ok = true;
+                exp = (fl & BT_BOX_HAS_SOURCE_CHILD_BOXES) != 0; ok = true;
             } else {
-                if (!(xflags[cb] & kXfHasChild)) continue;     // a leaf: its walk visits nothing
-                l1ok = adj && (fl & BT_BOX_HAS_SOURCE_CHILD_BOXES);
+                exp = (xflags[cb] & kXfHasChild) != 0;       // a leaf: its walk visits nothing
+                ok = adj && (fl & BT_BOX_HAS_SOURCE_CHILD_BOXES);
             }
-            parent = cb;
-            return true;
+        }
+        constexpr unsigned gmask = (1u << NB) - 1u;
+        nearm = (__ballot_sync(gm, near) >> gshift) & gmask;
+        expm = (__ballot_sync(gm, exp) >> gshift) & gmask;
+        okm = (__ballot_sync(gm, ok) >> gshift) & gmask;
+    }
+    __device__ __forceinline__ bool next_root(int& parent)
+    {
+        if (skip) return false;
+        constexpr unsigned gmask = (1u << NB) - 1u;
+        const int lane = threadIdx.x & 31, gl = lane % NB, gshift = lane - gl;
+        const unsigned gm = gmask << gshift;
+        const bool writer = FILL && gl == 0;
+        while (true) {
+            if (!(nearm | expm)) {
+                if (jb_next >= nroots) break;
+                jb = jb_next; jb_next += NB;
+                load_roots(gl, gm, gshift);
+                continue;
+            }
+            const int first_exp = expm ? (__ffs(expm) - 1) : NB;
+            const unsigned low = (first_exp >= NB) ? gmask : ((2u << first_exp) - 1u);
+            const unsigned nb = nearm & low;     // near roots up to (and including) the next expanded one
+            if (nb) {
+                if (FILL && ia < nA) {
+                    // near-field boxes from above the level are pending: merge by depth-first rank
+                    for (unsigned m = nb; m; m &= m - 1) {
+                        const int i = __ffs(m) - 1;
+                        const int rk = __shfl_sync(gm, my_rank, gshift + i);
+                        const int cbi = __shfl_sync(gm, my_cb, gshift + i);
+                        flush_near(rk, writer);
+                        if (writer) lists[l1cur] = cbi;
+                        ++l1cur;
+                    }
+                } else {
+                    if (FILL && ((nb >> gl) & 1u)) lists[l1cur + __popc(nb & ((1u << gl) - 1u))] = my_cb;
+                    l1cur += __popc(nb);
+                }
+                nearm &= ~nb;
+            }
+            if (first_exp < NB) {
+                expm &= ~(1u << first_exp);
+                const int cbi = __shfl_sync(gm, my_cb, gshift + first_exp);
+                if (FILL && ia < nA) flush_near(__shfl_sync(gm, my_rank, gshift + first_exp), writer);
+                l1ok = ((okm >> first_exp) & 1u) != 0;
+                parent = cbi;
+                return true;
+            }
         }
         if (FILL) flush_near(0x7fffffff, writer);
         else { l1cur += nA - ia; ia = nA; }
@@ -1527,7 +1614,15 @@ list13_coop_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, const unsigned char*
     coop_walk_rows<T, DIM>(t, pol, ntgt, FILL ? 0x7ffffff0 : ws.budget, frames);
 }
 
-// heavy rows of the fused walk: frontier item = row << 32 | near-ok << 31 | walk parent
+// heavy rows of the fused walk: frontier item = heavy-row index << 32 | near-ok << 31 | walk
+// parent; sort key = slot | heavy-row index | depth-first rank (the index keeps the key short)
+__device__ __forceinline__ void heavy_count_add(int* G, int64_t rowlen, bool emits, int slot, int r)
+{   // one atomic per distinct (slot, row) of the warp; called by full warps
+    const unsigned long long ckey = emits ? (((unsigned long long)slot << 32) | (unsigned)r) : ~0ull;
+    const unsigned peers = __match_any_sync(0xffffffffu, ckey);
+    if (emits && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(G + slot * rowlen + r, __popc(peers));
+}
+
 template <typename T, int DIM, bool FILL>
 __global__ void __launch_bounds__(256)
 list13_heavy_seed_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, const unsigned char* __restrict__ xflags,
@@ -1536,7 +1631,7 @@ list13_heavy_seed_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, const unsigned
     __shared__ T rad[kMaxWalkLevels];
     fill_rad_table(rad, t.root_extent);
     const int nheavy = ws.hctl[kHctlNHeavy];
-    const int rank_bits = bits_for(t.nboxes), row_bits = bits_for(ntgt);
+    const int rank_bits = bits_for(t.nboxes), row_bits = bits_for(nheavy);
     const int64_t rowlen = (int64_t)ntgt + 1;
     const int l1slot = t.nlevels + 1;
     const int stride = gridDim.x * blockDim.x;
@@ -1550,7 +1645,7 @@ list13_heavy_seed_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, const unsigned
                 const int k = atomicAdd(ws.hctl + kHctlECount, 1);
                 if (k < ws.ecap) {
                     ws.ekeys[0][k] = ((unsigned long long)l1slot << (rank_bits + row_bits))
-                                     | ((unsigned long long)r << rank_bits) | (unsigned)ws.dfs_rank[sbox];
+                                     | ((unsigned long long)h << rank_bits) | (unsigned)ws.dfs_rank[sbox];
                     ws.evals[0][k] = (unsigned)sbox;
                 }
             } else atomicAdd(G + l1slot * rowlen + r, 1);
@@ -1583,7 +1678,7 @@ list13_heavy_seed_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, const unsigned
             else { if (!(xflags[cb] & kXfHasChild)) continue; nearok = adj && (fl & BT_BOX_HAS_SOURCE_CHILD_BOXES); }
             const int q = atomicAdd(ws.hctl + kHctlFrontier, 1);
             if (q < ws.frontier_cap)
-                ws.frontier[0][q] = ((unsigned long long)r << 32) | (nearok ? 0x80000000ull : 0ull) | (unsigned)cb;
+                ws.frontier[0][q] = ((unsigned long long)h << 32) | (nearok ? 0x80000000ull : 0ull) | (unsigned)cb;
             else ws.hctl[kHctlOverflow] = 1;
         }
     }
@@ -1602,16 +1697,17 @@ list13_heavy_step_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, int ntgt, int 
     long long nitems = ws.hctl[kHctlFrontier + step];
     if (nitems > ws.frontier_cap) nitems = ws.frontier_cap;
     const long long total = nitems * NB;
-    const int rank_bits = bits_for(t.nboxes), row_bits = bits_for(ntgt);
+    const int rank_bits = bits_for(t.nboxes), row_bits = bits_for(ws.hctl[kHctlNHeavy]);
     const int64_t rowlen = (int64_t)ntgt + 1;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x; tid < ((total + 31) & ~31ll);
          tid += stride) {
-        int act = 0, wb = 0, r = 0;
+        int act = 0, wb = 0, r = 0, h = 0;
         unsigned long long nearok = 0;
         if (tid < total) {
             const unsigned long long item = fin[tid / NB];
-            r = (int)(item >> 32);
+            h = (int)(item >> 32);
+            r = ws.heavy_rows[h];
             nearok = item & 0x80000000ull;
             const int parent = (int)(item & 0x7fffffffull), m = (int)(tid % NB);
             L3Ctx<T, DIM> c; l3_make_ctx<T, DIM>(t, rad, x, x.target_boxes[r], c);
@@ -1625,22 +1721,74 @@ list13_heavy_step_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, int ntgt, int 
             const long long k = warp_append(emits, ws.hctl + kHctlECount);
             if (k >= 0 && k < ws.ecap) {
                 ws.ekeys[0][k] = ((unsigned long long)slot << (rank_bits + row_bits))
-                                 | ((unsigned long long)r << rank_bits) | (unsigned)ws.dfs_rank[wb];
+                                 | ((unsigned long long)h << rank_bits) | (unsigned)ws.dfs_rank[wb];
                 ws.evals[0][k] = (unsigned)wb;
             }
-        } else if (emits) atomicAdd(G + slot * rowlen + r, 1);
+        } else heavy_count_add(G, rowlen, emits, slot, r);
         const long long q = warp_append(act & kVisitPush, ws.hctl + kHctlFrontier + step + 1);
         if (q >= 0) {
-            if (q < ws.frontier_cap) fout[q] = ((unsigned long long)r << 32) | nearok | (unsigned)wb;
+            if (q < ws.frontier_cap) fout[q] = ((unsigned long long)h << 32) | nearok | (unsigned)wb;
             else ws.hctl[kHctlOverflow] = 1;
         }
     }
 }
 
+// start of every (slot, heavy row) group in the sorted entry array = exclusive scan of the
+// groups' sizes, which the count phase left in G
+struct HeavyGroupIn {
+    const int* G; const int* heavy_rows; int nheavy; int64_t rowlen;
+    __device__ int operator()(int64_t i) const
+    {
+        const int64_t slot = i / nheavy; const int r = heavy_rows[i % nheavy];
+        return G[slot * rowlen + r + 1] - G[slot * rowlen + r];
+    }
+};
+
+__global__ void __launch_bounds__(256)
+heavy_scatter_groups_kernel(const unsigned long long* __restrict__ keys, const unsigned* __restrict__ vals,
+                            const int* __restrict__ ecount_dev, int rank_bits, int row_bits, int nheavy,
+                            const int* __restrict__ heavy_rows, const int* __restrict__ group_start,
+                            int64_t rowlen, const int* __restrict__ G, int* __restrict__ lists)
+{
+    const int n = *ecount_dev;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long key = ld_stream_u64(keys + i);
+        const int h = (int)((key >> rank_bits) & ((1ull << row_bits) - 1ull));
+        const int64_t slot = (int64_t)(key >> (rank_bits + row_bits));
+        lists[G[slot * rowlen + heavy_rows[h]] + (i - group_start[slot * nheavy + h])] = (int)vals[i];
+    }
+}
+
+static int heavy_sort_and_scatter_groups(const HeavyWs& ws, long long ecount_host, int nboxes, int nheavy,
+                                         int nslots, int64_t rowlen, const int* G, int* lists, cudaStream_t s)
+{
+    if (ecount_host <= 0 || nheavy <= 0) return BT_OK;
+    int rank_bits = 1; while ((1ll << rank_bits) < nboxes) ++rank_bits;
+    int row_bits = 1; while ((1ll << row_bits) < nheavy) ++row_bits;
+    int slot_bits = 0; while ((1ll << slot_bits) < nslots) ++slot_bits;
+    if (rank_bits + row_bits + slot_bits > 64) return BT_ERR_UNSUPPORTED;
+    int in_alt = 0;
+    BT_TRY(radix_sort_pairs(ecount_host, ws.ekeys[0], ws.ekeys[1], ws.evals[0], ws.evals[1], 0, 0,
+                            rank_bits + row_bits + slot_bits, &in_alt, s));
+    int* group_start = nullptr;
+    const int64_t ngroups = (int64_t)nslots * nheavy;
+    BT_CHECK(temp_alloc((void**)&group_start, sizeof(int) * (ngroups + 1), s));
+    HeavyGroupIn in{G, ws.heavy_rows, nheavy, rowlen};
+    PlainOut out{group_start, nullptr, ngroups};
+    BT_TRY(scan_exclusive(ngroups, nullptr, in, out, s));
+    heavy_scatter_groups_kernel<<<grid_for(ecount_host, 256, 8), 256, 0, s>>>(
+        ws.ekeys[in_alt], ws.evals[in_alt], ws.hctl + kHctlECount, rank_bits, row_bits, nheavy, ws.heavy_rows,
+        group_start, rowlen, G, lists);
+    BT_LAUNCH_CHECK();
+    BT_CHECK(cudaFreeAsync(group_start, s));
+    return BT_OK;
+}
+
 template <typename T, int DIM>
 static int list13_impl(int phase, const bt_tree_view* tv, const bt_list3_args* a, const unsigned char* xflags,
                        int ntgt, int* G, int* C, int* lists, long long* summary, const bt_heavy_ws* w,
-                       long long heavy_total_host, cudaStream_t s)
+                       long long heavy_total_host, int nheavy_host, cudaStream_t s)
 {
     TreeView<T, DIM> t = make_view<T, DIM>(tv);
     if (t.nlevels + 1 > kMaxWalkLevels) return BT_ERR_UNSUPPORTED;
@@ -1690,7 +1838,8 @@ static int list13_impl(int phase, const bt_tree_view* tv, const bt_list3_args* a
                 list13_heavy_step_kernel<T, DIM, true><<<kNumSMs * 8, 256, 0, s>>>(t, x, ntgt, st, G, ws);
                 BT_LAUNCH_CHECK();
             }
-            BT_TRY(heavy_sort_and_scatter(ws, heavy_total_host, t.nboxes, ntgt, nrows, rowlen, G, lists, s));
+            BT_TRY(heavy_sort_and_scatter_groups(ws, heavy_total_host, t.nboxes, nheavy_host, nrows, rowlen, G,
+                                                 lists, s));
         }
     }
     return BT_OK;
@@ -1846,12 +1995,30 @@ int bt_get_walk_mode(void) { return bt::g_walk_mode; }
 int bt_trav_colleagues(int dtype, int phase, const bt_tree_view* tree, const int32_t* level_start_box_nrs,
                        const int32_t* dfs_rank, const int8_t* row_mask, int stride, int32_t* staging,
                        int32_t* starts, int32_t* lists, int32_t* list2_count_by_box, uint8_t* xflags,
-                       int64_t* totals_dev, void* stream)
+                       uint32_t* list2_masks, int mask_words, int64_t* totals_dev, void* stream)
 {
     BT_PROF(phase ? "trav_colleagues_fill" : "trav_colleagues_count", (cudaStream_t)stream);
+    if (list2_masks && mask_words < ((stride + 1) * (1 << tree->dim) + 31) / 32 + 1) return BT_ERR_BAD_ARG;
     BT_DISPATCH(dtype, tree->dim, colleagues_topdown_impl, phase, tree, level_start_box_nrs, dfs_rank,
                 (const signed char*)row_mask, stride, staging, starts, lists, list2_count_by_box, xflags,
-                (long long*)totals_dev, (cudaStream_t)stream);
+                list2_masks, mask_words, (long long*)totals_dev, (cudaStream_t)stream);
+}
+
+int bt_trav_list2_fill_masked(int dim, int nrows, const int32_t* row_boxes, const int32_t* box_parent_ids,
+                              const int32_t* coll_starts, const int32_t* coll_lists,
+                              const int32_t* box_child_ids_t, const uint32_t* list2_masks, int mask_words,
+                              const int32_t* starts, int32_t* lists, void* stream)
+{
+    BT_PROF("trav_list2_fill", (cudaStream_t)stream);
+    if (nrows <= 0) return BT_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int grid = bt::grid_for((int64_t)nrows * 32, 256, 8);
+    if (dim == 1) bt::list2_masked_fill_kernel<1><<<grid, 256, 0, s>>>(nrows, row_boxes, box_parent_ids, coll_starts, coll_lists, box_child_ids_t, list2_masks, mask_words, starts, lists);
+    else if (dim == 2) bt::list2_masked_fill_kernel<2><<<grid, 256, 0, s>>>(nrows, row_boxes, box_parent_ids, coll_starts, coll_lists, box_child_ids_t, list2_masks, mask_words, starts, lists);
+    else if (dim == 3) bt::list2_masked_fill_kernel<3><<<grid, 256, 0, s>>>(nrows, row_boxes, box_parent_ids, coll_starts, coll_lists, box_child_ids_t, list2_masks, mask_words, starts, lists);
+    else return BT_ERR_BAD_ARG;
+    BT_LAUNCH_CHECK();
+    return BT_OK;
 }
 
 int bt_trav_list2_starts(int nrows, const int32_t* row_boxes, const int32_t* list2_count_by_box,
@@ -1912,13 +2079,37 @@ int bt_trav_list3(int dtype, int phase, const bt_tree_view* tree, const bt_list3
                 (long long*)summary_dev, ws, (long long)heavy_total, (cudaStream_t)stream);
 }
 
+__global__ void transpose_children_kernel(int nb, int aligned, const int* __restrict__ in, int* __restrict__ out)
+{
+    const int64_t total = (int64_t)aligned * nb;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        // i enumerates the OUTPUT (coalesced stores); the nb input rows are read at stride `aligned`
+        const int64_t b = i / nb; const int m = (int)(i % nb);
+        out[i] = in[(int64_t)m * aligned + b];
+    }
+}
+
+int bt_trav_transpose_children(int dim, int aligned_nboxes, const int32_t* box_child_ids,
+                               int32_t* box_child_ids_t, void* stream)
+{
+    BT_PROF("bt_trav_transpose_children", (cudaStream_t)stream);
+    if (aligned_nboxes <= 0) return BT_OK;
+    const int nb = 1 << dim;
+    transpose_children_kernel<<<bt::grid_for((int64_t)aligned_nboxes * nb, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        nb, aligned_nboxes, box_child_ids, box_child_ids_t);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+
 int bt_trav_list13(int dtype, int phase, const bt_tree_view* tree, const bt_list3_args* args,
                    const uint8_t* xflags, int ntarget_boxes, int32_t* G, int32_t* C, int32_t* lists,
-                   int64_t* summary_dev, const bt_heavy_ws* ws, int64_t heavy_total, void* stream)
+                   int64_t* summary_dev, const bt_heavy_ws* ws, int64_t heavy_total, int nheavy,
+                   void* stream)
 {
     BT_PROF(phase ? "trav_list13_fill" : "trav_list13_count", (cudaStream_t)stream);
     BT_DISPATCH(dtype, tree->dim, list13_impl, phase, tree, args, xflags, ntarget_boxes, G, C, lists,
-                (long long*)summary_dev, ws, (long long)heavy_total, (cudaStream_t)stream);
+                (long long*)summary_dev, ws, (long long)heavy_total, nheavy, (cudaStream_t)stream);
 }
 
 int bt_trav_dfs_rank(int dim, int nboxes, int aligned_nboxes, int nlevels,

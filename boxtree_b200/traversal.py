@@ -311,6 +311,11 @@ class FMMTraversalBuilder:
             tv.well_sep_is_n_away = int(self.well_sep_is_n_away)
             if int(box_centers.shape[-1]) != tv.aligned_nboxes:
                 raise ValueError("box_centers and box_child_ids must share their padded length")
+            # scratch copy of the child table with the children of a box side by side
+            child_t = actx.empty(max(tv.aligned_nboxes, 1) * 2 ** dimensions, np.int32)
+            check(lib.bt_trav_transpose_children(dimensions, tv.aligned_nboxes, dptr(box_child_ids),
+                                                 dptr(child_t), sh), "bt_trav_transpose_children")
+            tv.box_child_ids_t = dptr(child_t)
 
             # {{{ b1/b2: box lists and their level starts (traversal.py:2054-2124)
 
@@ -382,13 +387,15 @@ class FMMTraversalBuilder:
                 staging = actx.empty(max(nboxes, 1) * stride, np.int32)
                 l2_count_by_box = actx.empty(max(nboxes, 1), np.int32)
                 xflags = actx.empty(max(nboxes, 1), np.uint8)
+                mask_words = ((stride + 1) * 2 ** dimensions + 31) // 32 + 1
+                l2_masks = actx.empty(max(nboxes, 1) * mask_words, np.int32)
 
                 def colleagues(phase, lists):
                     check(lib.bt_trav_colleagues(
                         dcode, phase, C.byref(tv), dptr(level_start_box_nrs), dptr(dfs_rank),
                         dptr(crm), stride, dptr(staging), dptr(coll_starts), dptr(lists),
-                        dptr(l2_count_by_box), dptr(xflags), dptr(totals), sh),
-                        "bt_trav_colleagues")
+                        dptr(l2_count_by_box), dptr(xflags), dptr(l2_masks), mask_words,
+                        dptr(totals), sh), "bt_trav_colleagues")
             else:
                 a_coll = list_args(None, row_mask=crm)
 
@@ -470,7 +477,7 @@ class FMMTraversalBuilder:
                 if fused13:
                     check(lib.bt_trav_list13(dcode, 0, C.byref(tv), C.byref(a3), dptr(xflags), ntb,
                                              dptr(G), dptr(Cc), None, dptr(summary),
-                                             C.byref(ws3.struct()), 0, sh), "list 1+3 count")
+                                             C.byref(ws3.struct()), 0, 0, sh), "list 1+3 count")
                 else:
                     check(lib.bt_trav_list3(dcode, 0, C.byref(tv), C.byref(a3), ntb, dptr(G),
                                             dptr(Cc), None, dptr(summary), C.byref(ws3.struct()),
@@ -528,9 +535,16 @@ class FMMTraversalBuilder:
                                         C.byref(ws1.struct()), heavy1_total, sh), "list 1 fill")
             del ws1
             l2_lists = actx.empty(int(tot[1]), np.int32)
-            check(lib.bt_trav_build_list(dcode, 2, 1, C.byref(tv), C.byref(a2), ntp,
-                                         dptr(l2_starts), dptr(l2_lists), None, None, None, sh),
-                  "list 2 fill")
+            if topdown:
+                check(lib.bt_trav_list2_fill_masked(
+                    dimensions, ntp, dptr(target_or_target_parent_boxes), dptr(box_parent_ids),
+                    dptr(coll_starts), dptr(coll_lists), dptr(child_t), dptr(l2_masks), mask_words,
+                    dptr(l2_starts), dptr(l2_lists), sh), "list 2 fill")
+                del l2_masks
+            else:
+                check(lib.bt_trav_build_list(dcode, 2, 1, C.byref(tv), C.byref(a2), ntp,
+                                             dptr(l2_starts), dptr(l2_lists), None, None, None, sh),
+                      "list 2 fill")
             l4_lists = actx.empty(int(tot[2]), np.int32)
             l4c_lists_raw = actx.empty(int(tot[3]), np.int32) if with_extent else None
             check(lib.bt_trav_build_list(dcode, 4, 1, C.byref(tv), C.byref(a4), ntp,
@@ -542,7 +556,8 @@ class FMMTraversalBuilder:
             if fused13:
                 check(lib.bt_trav_list13(dcode, 1, C.byref(tv), C.byref(a3), dptr(xflags), ntb,
                                          dptr(G), dptr(Cc), dptr(l3_all), dptr(summary),
-                                         C.byref(ws3.struct()), heavy3_total, sh), "list 1+3 fill")
+                                         C.byref(ws3.struct()), heavy3_total,
+                                         int(heavy[4 + HCTL_NHEAVY]), sh), "list 1+3 fill")
                 l1_lists = l3_all[int(g0[nlevels + 1]):int(g0[nlevels + 2])]
             else:
                 check(lib.bt_trav_list3(dcode, 1, C.byref(tv), C.byref(a3), ntb, dptr(G), dptr(Cc),

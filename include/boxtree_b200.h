@@ -199,7 +199,13 @@ typedef struct {
     const uint8_t *box_flags;
     const int32_t *box_parent_ids;
     int32_t well_sep_is_n_away;
+    const int32_t *box_child_ids_t;     /* optional scratch copy [aligned, 2^dim] (bt_trav_transpose_children):
+                                           the 2^dim children of a box share one 32-byte sector */
 } bt_tree_view;
+
+/* box_child_ids [2^dim, aligned] -> [aligned, 2^dim] */
+int bt_trav_transpose_children(int dim, int aligned_nboxes, const int32_t *box_child_ids,
+                               int32_t *box_child_ids_t, void *stream);
 
 /* sources_parents_and_targets (traversal.py:326-355): which = 0 source_parent_boxes,
  * 1 source_boxes, 2 target_or_target_parent_boxes, 3 target_boxes.  Writes the
@@ -238,13 +244,23 @@ int bt_trav_build_list(int dtype, int kind, int phase, const bt_tree_view *tree,
  *          (total at totals_dev[0]); list2_count_by_box[nboxes] = number of from_sep_siblings
  *          entries of every box (traversal.py:556-601, the non-adjacent candidates);
  *          xflags[nboxes]: bit 0 = the box or one of its colleagues is a source box,
- *          bit 1 = the box has a child.
+ *          bit 1 = the box has a child; list2_masks (optional) [nboxes, mask_words],
+ *          mask_words >= ceil((stride + 1) * 2^d / 32) + 1: bit k of a row = candidate k
+ *          (k / 2^d-th box of the parent's colleagues with the parent merged in at its
+ *          depth-first position, Morton child k % 2^d) belongs to list 2; the row's last word is
+ *          the parent's position.
  * phase 1: staging -> lists.   dfs_rank from bt_trav_dfs_rank. */
 int bt_trav_colleagues(int dtype, int phase, const bt_tree_view *tree,
                        const int32_t *level_start_box_nrs, const int32_t *dfs_rank,
                        const int8_t *row_mask, int stride, int32_t *staging, int32_t *starts,
                        int32_t *lists, int32_t *list2_count_by_box, uint8_t *xflags,
-                       int64_t *totals_dev, void *stream);
+                       uint32_t *list2_masks, int mask_words, int64_t *totals_dev, void *stream);
+/* from_sep_siblings lists from the masks of bt_trav_colleagues (no geometry is re-evaluated) */
+int bt_trav_list2_fill_masked(int dim, int nrows, const int32_t *row_boxes,
+                              const int32_t *box_parent_ids, const int32_t *coll_starts,
+                              const int32_t *coll_lists, const int32_t *box_child_ids_t,
+                              const uint32_t *list2_masks, int mask_words, const int32_t *starts,
+                              int32_t *lists, void *stream);
 /* starts[nrows+1] of from_sep_siblings from the per-box counts of bt_trav_colleagues */
 int bt_trav_list2_starts(int nrows, const int32_t *row_boxes, const int32_t *list2_count_by_box,
                          int32_t *starts, int64_t *totals_dev, void *stream);
@@ -330,7 +346,7 @@ int bt_trav_list3_compress(int nlevels, int ntarget_boxes, const int32_t *G, con
 int bt_trav_list13(int dtype, int phase, const bt_tree_view *tree, const bt_list3_args *args,
                    const uint8_t *xflags, int ntarget_boxes, int32_t *G, int32_t *C,
                    int32_t *lists, int64_t *summary_dev, const bt_heavy_ws *ws,
-                   int64_t heavy_total, void *stream);
+                   int64_t heavy_total, int nheavy /* HOST copies, phase 1 */, void *stream);
 
 /* _ListMerger (traversal.py:1153-1344): phase 0 -> new_starts[noutput+1], total at
  * totals_dev[0]; phase 1 -> new_lists.  starts/lists: HOST arrays of nlists device pointers. */

@@ -1,18 +1,24 @@
 #!/bin/bash
-# Run under gpurun (1 GPU).  Writes raw captures to gpurun_out/; the summaries that are
-# judged are copied (by hand / profiles/summarize.py) into profiles/.
-#   profiles/run_ncu.sh <tag> <workload> [n]
+# Run under gpurun (1 GPU).  Raw captures go to gpurun_out/ (scratch); profiles/summarize.py turns
+# them into the committed summaries.   profiles/run_ncu.sh <tag> <spec> [full-kernel-regex] [count]
+#   spec: tests/perf_probe.py workload spec, e.g. config3:10000000 or uniform:10000000:f64
 set -u
-TAG=${1:-r01}; WL=${2:-config3}; N=${3:-0}
+TAG=${1:-r01}; SPEC=${2:-config3:10000000}
+REGEX=${3:-'list13_coop|coll_topdown|list2_warp|rs_onesweep|box_extents|permute_kernel|make_keys'}
+COUNT=${4:-24}
+NAME=$(echo "$SPEC" | tr ':' '_')
 mkdir -p gpurun_out
-NARG=""; [ "$N" != "0" ] && NARG="--n $N"
-# (1) every launch of ~2 steps with its device time (cold cache, serialised: compare SHARES)
-ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 450 --csv \
-    --log-file gpurun_out/launches_${TAG}_${WL}.csv \
-    python bench.py --workload $WL $NARG --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
-# (2) full metric set of the walk kernels and one sort pass
-ncu --set full --clock-control none --import-source on \
-    -k regex:'list3_coop|list1_coop|coll_coop|list2_warp|list_kernel|rs_onesweep|box_extents|heavy_step' -s 300 -c 110 \
-    -o gpurun_out/prof_${TAG}_${WL} \
-    python bench.py --workload $WL $NARG --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu_full_${TAG}.log 2>&1
+# (1) every launch of ONE warm step (tests/ncu_driver.py brackets it with cudaProfilerStart/Stop)
+#     with its device time; serialised: compare SHARES with the bench's live numbers
+ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+    --log-file gpurun_out/launches_${TAG}_${NAME}.csv \
+    python tests/ncu_driver.py $SPEC > gpurun_out/ncu_launches_${TAG}.log 2>&1
+# (2) full metric set of the top kernels of the same warm step
+ncu --profile-from-start off --set full --clock-control none --import-source on \
+    -k regex:"$REGEX" -c $COUNT -f -o gpurun_out/prof_${TAG}_${NAME} \
+    python tests/ncu_driver.py $SPEC > gpurun_out/ncu_full_${TAG}.log 2>&1
+ncu -i gpurun_out/prof_${TAG}_${NAME}.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_${NAME}_raw.csv 2>/dev/null
+# the report itself only travels back when it is small (gpurun_out/ is capped at 64 MiB)
+SZ=$(stat -c %s gpurun_out/prof_${TAG}_${NAME}.ncu-rep 2>/dev/null || echo 0)
+if [ "$SZ" -gt 30000000 ]; then rm -f gpurun_out/prof_${TAG}_${NAME}.ncu-rep; fi
 ls -la gpurun_out/

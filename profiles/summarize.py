@@ -8,7 +8,7 @@ import re
 import subprocess
 import sys
 
-tag, wl = sys.argv[1], sys.argv[2]
+tag, wl = sys.argv[1], sys.argv[2].replace(":", "_")
 src = f"gpurun_out/launches_{tag}_{wl}.csv"
 lines = [ln for ln in open(src) if ln.startswith('"')]
 r = csv.reader(lines)
@@ -32,14 +32,19 @@ for row in r:
     n += 1
 with open(f"profiles/{tag}_launches_{wl}.txt", "w") as f:
     f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none (profiles/run_ncu.sh {tag} {wl})\n")
-    f.write(f"# {n} launches captured (~2 steps), serialised + cold cache: compare SHARES, not absolutes\n")
+    f.write(f"# {n} launches captured (one warm step), serialised: compare SHARES, not absolutes\n")
     f.write(f"# total {tot / 1e6:.3f} ms\n")
     f.write(f"{'kernel':42s} {'launches':>8s} {'total ms':>10s} {'share':>7s}\n")
     for k, (c, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write(f"{k:42s} {c:8d} {v / 1e6:10.3f} {100 * v / tot:6.1f}%\n")
 
-raw = subprocess.run(["ncu", "-i", f"gpurun_out/prof_{tag}_{wl}.ncu-rep", "--page", "raw", "--csv"],
-                     capture_output=True, text=True).stdout
+import os
+raw_csv = f"gpurun_out/prof_{tag}_{wl}_raw.csv"
+if os.path.exists(raw_csv):
+    raw = open(raw_csv).read()
+else:
+    raw = subprocess.run(["ncu", "-i", f"gpurun_out/prof_{tag}_{wl}.ncu-rep", "--page", "raw", "--csv"],
+                         capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
 want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
