@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libboxtree_b200.so")
+# BT_LIB_PATH selects another build of the same sources (kernel tuning experiments)
+LIB_PATH = os.environ.get("BT_LIB_PATH") or os.path.join(HERE, "libboxtree_b200.so")
 
 BT_F32, BT_F64 = 0, 1
 
@@ -73,9 +74,10 @@ class bt_heavy_ws(C.Structure):
     _fields_ = [("walk_budget", C.c_int32), ("row_heavy", vp), ("heavy_rows", vp), ("hctl", vp),
                 ("heavy_total", vp), ("frontier", vp * 2), ("frontier_cap", C.c_int64),
                 ("dfs_rank", vp), ("ekeys", vp * 2), ("evals", vp * 2), ("ecap", C.c_int64),
-                ("row_mask", vp)]
+                ("row_mask", vp), ("stage", vp), ("stage_cap", C.c_int32), ("stage_count", vp)]
 
 
+HCTL_NWALK = 3
 HCTL_SIZE = 64
 HCTL_NHEAVY = 0
 HCTL_OVERFLOW = 1
@@ -117,7 +119,7 @@ SIGNATURES = {
     "bt_trav_list2_starts": [_i, vp, vp, vp, vp, vp],
     "bt_trav_list3_compress": [_i, _i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "bt_trav_list13": [_i, _i, _P(bt_tree_view), _P(bt_list3_args), vp, _i, vp, vp, vp, vp,
-                       _P(bt_heavy_ws), _i64, _i, vp],
+                       _P(bt_heavy_ws), _i64, _i, _i, vp],
     "bt_trav_merge_lists": [_i, _i, vp, _i, _P(vp), _P(vp), vp, vp, vp, vp],
     "bt_gather_i32": [_i64, vp, vp, vp, vp],
     "bt_dist_dfs_order": [_i, _i, _i, _i, vp, vp, vp, vp, vp, vp],

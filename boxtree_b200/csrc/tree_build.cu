@@ -693,9 +693,13 @@ box_info_kernel(int nboxes, int sources_are_targets, int have_ext,
 // a14: box particle extents -- boxtree/tree_build_kernels.py:1311-1399,
 // launched per level bottom-up like boxtree/tree_build.py:1751-1802
 // ---------------------------------------------------------------------------
-// Phase A (all boxes at once, one warp per box): min/max over the box's own particles,
-// seeded with the box centre.  min/max are exact and order-free, so the warp-parallel
-// reduction returns the same bits as the reference's serial loop (:1345-1368).
+// Phase A (all boxes at once): min/max over the box's own particles, seeded with the box
+// centre.  min/max are exact and order-free, so the parallel reduction returns the same bits
+// as the reference's serial loop (:1345-1368).  Four boxes per warp (8 lanes each: a leaf
+// holds at most a few dozen particles); a box with many own particles (upper-level boxes of
+// a tree with extents) is taken by the whole warp.
+constexpr int kExtGroup = 8, kExtBig = 128;
+
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256)
 box_extents_own_kernel(int nboxes, int aligned, const T* __restrict__ box_centers,
@@ -703,35 +707,74 @@ box_extents_own_kernel(int nboxes, int aligned, const T* __restrict__ box_center
                        const T* p0, const T* p1, const T* p2, const T* __restrict__ radii,
                        T* __restrict__ bb_min, T* __restrict__ bb_max)
 {
+    constexpr int GPW = 32 / kExtGroup;
     const T* parts[3] = {p0, p1, p2};
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, g = lane / kExtGroup, gl = lane % kExtGroup;
     const int wglobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int ibox = wglobal; ibox < nboxes; ibox += nwarps) {
+    for (int base = wglobal * GPW; base < nboxes; base += nwarps * GPW) {
+        const int ibox = base + g;
+        const bool valid = ibox < nboxes;
         T mn[DIM], mx[DIM];
 #pragma unroll
-        for (int a = 0; a < DIM; ++a) mn[a] = mx[a] = box_centers[a * aligned + ibox];
-        const int s = pstarts[ibox], e = s + pcounts[ibox];
-        for (int ip = s + lane; ip < e; ip += 32) {
-            const T rad = radii ? radii[ip] : (T)0;
+        for (int a = 0; a < DIM; ++a) mn[a] = mx[a] = valid ? box_centers[a * aligned + ibox] : (T)0;
+        const int s = valid ? pstarts[ibox] : 0, e = valid ? s + pcounts[ibox] : 0;
+        const bool big = (e - s) > kExtBig;
+        if (!big) {
+            for (int ip = s + gl; ip < e; ip += kExtGroup) {
+                const T rad = radii ? radii[ip] : (T)0;
+#pragma unroll
+                for (int a = 0; a < DIM; ++a) {
+                    const T c = parts[a][ip];
+                    const T lo = c - rad, hi = c + rad;
+                    mn[a] = (lo < mn[a]) ? lo : mn[a];
+                    mx[a] = (mx[a] < hi) ? hi : mx[a];
+                }
+            }
+        }
+        // boxes with many own particles: all 32 lanes, one such box after the other
+        unsigned bigm = __ballot_sync(0xffffffffu, big && gl == 0);
+        while (bigm) {
+            const int src = __ffs(bigm) - 1;
+            bigm &= bigm - 1;
+            const int bs = __shfl_sync(0xffffffffu, s, src), be = __shfl_sync(0xffffffffu, e, src);
+            T wmn[DIM], wmx[DIM];
 #pragma unroll
             for (int a = 0; a < DIM; ++a) {
-                const T c = parts[a][ip];
-                const T lo = c - rad, hi = c + rad;
-                mn[a] = (lo < mn[a]) ? lo : mn[a];
-                mx[a] = (mx[a] < hi) ? hi : mx[a];
+                wmn[a] = __shfl_sync(0xffffffffu, mn[a], src); wmx[a] = __shfl_sync(0xffffffffu, mx[a], src);
+            }
+            for (int ip = bs + lane; ip < be; ip += 32) {
+                const T rad = radii ? radii[ip] : (T)0;
+#pragma unroll
+                for (int a = 0; a < DIM; ++a) {
+                    const T c = parts[a][ip];
+                    const T lo = c - rad, hi = c + rad;
+                    wmn[a] = (lo < wmn[a]) ? lo : wmn[a];
+                    wmx[a] = (wmx[a] < hi) ? hi : wmx[a];
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) {
+#pragma unroll
+                for (int o = 16; o >= kExtGroup; o >>= 1) {     // across groups; the rest below
+                    const T lo = __shfl_xor_sync(0xffffffffu, wmn[a], o);
+                    const T hi = __shfl_xor_sync(0xffffffffu, wmx[a], o);
+                    wmn[a] = (lo < wmn[a]) ? lo : wmn[a];
+                    wmx[a] = (wmx[a] < hi) ? hi : wmx[a];
+                }
+                if (g == src / kExtGroup) { mn[a] = wmn[a]; mx[a] = wmx[a]; }
             }
         }
 #pragma unroll
         for (int a = 0; a < DIM; ++a) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
+            for (int o = kExtGroup / 2; o > 0; o >>= 1) {
                 const T lo = __shfl_xor_sync(0xffffffffu, mn[a], o);
                 const T hi = __shfl_xor_sync(0xffffffffu, mx[a], o);
                 mn[a] = (lo < mn[a]) ? lo : mn[a];
                 mx[a] = (mx[a] < hi) ? hi : mx[a];
             }
-            if (lane == 0) { bb_min[a * aligned + ibox] = mn[a]; bb_max[a * aligned + ibox] = mx[a]; }
+            if (valid && gl == 0) { bb_min[a * aligned + ibox] = mn[a]; bb_max[a * aligned + ibox] = mx[a]; }
         }
     }
 }
@@ -958,7 +1001,7 @@ static int box_extents_impl(int nboxes, int aligned, int nlevels, const int* lev
                             void* bmax, cudaStream_t s)
 {
     if (nboxes <= 0) return BT_OK;
-    box_extents_own_kernel<T, DIM><<<grid_for((int64_t)nboxes * 32, 256, 8), 256, 0, s>>>(
+    box_extents_own_kernel<T, DIM><<<grid_for((int64_t)nboxes * kExtGroup, 256, 8), 256, 0, s>>>(
         nboxes, aligned, (const T*)centers, pstarts, pcounts, (const T*)parts[0],
         DIM > 1 ? (const T*)parts[1] : nullptr, DIM > 2 ? (const T*)parts[2] : nullptr,
         (const T*)radii, (T*)bmin, (T*)bmax);

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from ._cabi import (HCTL_NHEAVY, HCTL_OVERFLOW, HCTL_SIZE, bt_heavy_ws, bt_list3_args,
+from ._cabi import (HCTL_NHEAVY, HCTL_NWALK, HCTL_OVERFLOW, HCTL_SIZE, bt_heavy_ws, bt_list3_args,
                     bt_list_args, bt_tree_view, check, dptr)
 from .array_context import TorchArrayContext, make_obj_array
 from .tree import Tree, TreeOfBoxes
@@ -27,6 +27,11 @@ CRIT_CODE = {"static_linf": 0, "precise_linf": 1, "static_l2": 2}
 #: child visits one thread may spend on one row of list 1 / list 3 before the row is handed
 #: to the grid-wide "heavy row" path (csrc/traversal.cu); BT_WALK_BUDGET overrides (tests)
 DEFAULT_WALK_BUDGET = 1024
+
+#: entries per row the count pass of the fused list-1+3 walk may stage for the fill pass
+#: (rows with more are walked a second time); BT_STAGE_STRIDE overrides, 0 disables
+DEFAULT_STAGE_STRIDE = 64
+_STAGE_MAX_BYTES = 16 << 30
 
 # bits of bt_set_walk_mode (include/boxtree_b200.h) that select a different host sequence
 WALK_MODE_COLL_TOPDOWN = 64
@@ -49,7 +54,16 @@ class _HeavyWorkspace:
         self.frontier = None
         self.ekeys = self.evals = None
         self.ecap = 0
+        self.stage = self.stage_count = None
+        self.stage_cap = 0
         self._alloc_frontier(max(nrows, 8 * nboxes, 1 << 16))
+
+    def enable_staging(self, stride):
+        """Fused list-1+3 walk: room for *stride* staged entries per row (count pass)."""
+        if stride > 0 and self.nrows > 0:
+            self.stage_cap = int(stride)
+            self.stage = self.actx.empty(self.nrows * self.stage_cap, np.int32)
+            self.stage_count = self.actx.empty(self.nrows, np.int32)
 
     def _alloc_frontier(self, cap):
         self.frontier_cap = cap
@@ -80,6 +94,9 @@ class _HeavyWorkspace:
             w.evals[0], w.evals[1] = dptr(self.evals[0]), dptr(self.evals[1])
         w.ecap = self.ecap
         w.row_mask = dptr(self.row_mask)
+        w.stage = dptr(self.stage)
+        w.stage_cap = self.stage_cap
+        w.stage_count = dptr(self.stage_count)
         return w
 
 
@@ -421,6 +438,10 @@ class FMMTraversalBuilder:
             rm13 = None if _list13_row_mask is None else dev(_list13_row_mask, np.int8)
             ws1 = None if fused13 else _HeavyWorkspace(actx, ntb, nboxes, dfs_rank, budget, rm13)
             ws3 = _HeavyWorkspace(actx, ntb, nboxes, dfs_rank, budget, rm13)
+            if fused13 and nboxes < (1 << 27) and nlevels + 2 <= 31:
+                stage_stride = int(os.environ.get("BT_STAGE_STRIDE", DEFAULT_STAGE_STRIDE))
+                if ntb * stage_stride * 4 <= _STAGE_MAX_BYTES:
+                    ws3.enable_staging(stage_stride)
 
             l1_starts = actx.empty(ntb + 1, np.int32)
 
@@ -477,7 +498,7 @@ class FMMTraversalBuilder:
                 if fused13:
                     check(lib.bt_trav_list13(dcode, 0, C.byref(tv), C.byref(a3), dptr(xflags), ntb,
                                              dptr(G), dptr(Cc), None, dptr(summary),
-                                             C.byref(ws3.struct()), 0, 0, sh), "list 1+3 count")
+                                             C.byref(ws3.struct()), 0, 0, 0, sh), "list 1+3 count")
                 else:
                     check(lib.bt_trav_list3(dcode, 0, C.byref(tv), C.byref(a3), ntb, dptr(G),
                                             dptr(Cc), None, dptr(summary), C.byref(ws3.struct()),
@@ -491,7 +512,7 @@ class FMMTraversalBuilder:
                 both = _read_i64(actx, torch.cat([
                     totals, summary, zero1 if fused13 else ws1.heavy_total, ws3.heavy_total,
                     zero2 if fused13 else ws1.hctl[:2].to(torch.int64),
-                    ws3.hctl[:2].to(torch.int64)]))
+                    ws3.hctl[:4].to(torch.int64)]))
                 ns = summary.shape[0]
                 return both[:8], both[8:8 + ns], both[8 + ns:]
 
@@ -509,7 +530,9 @@ class FMMTraversalBuilder:
             self.last_stats = {"heavy_rows_list1": int(heavy[2 + HCTL_NHEAVY]),
                                "heavy_rows_list3": int(heavy[4 + HCTL_NHEAVY]),
                                "heavy_entries_list1": heavy1_total,
-                               "heavy_entries_list3": heavy3_total}
+                               "heavy_entries_list3": heavy3_total,
+                               "rewalked_rows_list13": int(heavy[4 + HCTL_NWALK]) if fused13 else 0,
+                               "fused13": fused13}
             g0 = summ[:nslots + 1]               # G[l][0], l = 0..nslots-1, then grand total
             c0 = summ[nslots + 1:2 * (nslots + 1)]
             if fused13:
@@ -557,7 +580,8 @@ class FMMTraversalBuilder:
                 check(lib.bt_trav_list13(dcode, 1, C.byref(tv), C.byref(a3), dptr(xflags), ntb,
                                          dptr(G), dptr(Cc), dptr(l3_all), dptr(summary),
                                          C.byref(ws3.struct()), heavy3_total,
-                                         int(heavy[4 + HCTL_NHEAVY]), sh), "list 1+3 fill")
+                                         int(heavy[4 + HCTL_NHEAVY]), int(heavy[4 + HCTL_NWALK]),
+                                         sh), "list 1+3 fill")
                 l1_lists = l3_all[int(g0[nlevels + 1]):int(g0[nlevels + 2])]
             else:
                 check(lib.bt_trav_list3(dcode, 1, C.byref(tv), C.byref(a3), ntb, dptr(G), dptr(Cc),

@@ -273,6 +273,7 @@ int bt_trav_list2_starts(int nrows, const int32_t *row_boxes, const int32_t *lis
 #define BT_HCTL_SIZE 64
 #define BT_HCTL_NHEAVY 0
 #define BT_HCTL_OVERFLOW 1
+#define BT_HCTL_NWALK 3
 typedef struct {
     int32_t walk_budget;
     uint8_t *row_heavy;          /* [nrows] */
@@ -286,6 +287,13 @@ typedef struct {
     uint32_t *evals[2];
     int64_t ecap;
     const int8_t *row_mask;      /* optional [nboxes]: rows of boxes with mask 0 stay empty */
+    /* bt_trav_list13 only: the count pass also stages every light row's entries (tagged with
+     * their slot, in append order) so that the fill pass copies instead of walking again.
+     * stage [nrows * stage_cap] (0 = off; needs nboxes < 2^27, nlevels <= 29), stage_count
+     * [nrows].  Rows with more than stage_cap entries are walked again (hctl[3] counts them). */
+    uint32_t *stage;
+    int32_t stage_cap;
+    int32_t *stage_count;
 } bt_heavy_ws;
 
 /* pre-order (depth first, children in Morton order) rank of every box */
@@ -346,7 +354,8 @@ int bt_trav_list3_compress(int nlevels, int ntarget_boxes, const int32_t *G, con
 int bt_trav_list13(int dtype, int phase, const bt_tree_view *tree, const bt_list3_args *args,
                    const uint8_t *xflags, int ntarget_boxes, int32_t *G, int32_t *C,
                    int32_t *lists, int64_t *summary_dev, const bt_heavy_ws *ws,
-                   int64_t heavy_total, int nheavy /* HOST copies, phase 1 */, void *stream);
+                   int64_t heavy_total, int nheavy, int nwalk /* HOST copies, phase 1 */,
+                   void *stream);
 
 /* _ListMerger (traversal.py:1153-1344): phase 0 -> new_starts[noutput+1], total at
  * totals_dev[0]; phase 1 -> new_lists.  starts/lists: HOST arrays of nlists device pointers. */

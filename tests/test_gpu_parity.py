@@ -53,6 +53,22 @@ def test_parity_heavy_row_path(actx, builders, case, budget, monkeypatch):
         assert st["heavy_rows_list1"] > 0 or st["heavy_rows_list3"] > 0
 
 
+@pytest.mark.parametrize("stride", [0, 3, 16])
+@pytest.mark.parametrize(
+    "case", _HEAVY_CASES,
+    ids=[f"{c['dims']}d-{np.dtype(c['dtype']).name}-{c['name']}" for c in _HEAVY_CASES])
+def test_parity_stage_stride(actx, builders, case, stride, monkeypatch):
+    """Fused list-1+3 walk: staging off (every row walked twice), and strides so small that
+    most rows overflow their staging area and are walked again by the fill pass."""
+    monkeypatch.setenv("BT_STAGE_STRIDE", str(stride))
+    tb, travs = builders
+    case = dict(case)
+    bad = run_case(case, actx, tb, travs)
+    assert not bad, bad[:10]
+    if case["n"] > 1000 and case["dims"] >= 2:
+        assert case["_trav_stats"]["rewalked_rows_list13"] > 0
+
+
 @pytest.mark.parametrize("mode", [0, 1 | 2 | 4 | 16 | 32, 64 | 2 | 8 | 32, 64 | 1 | 4 | 16, 64 | 128,
                                   64 | 128 | 256])
 @pytest.mark.parametrize(
