@@ -146,7 +146,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def algorithmic_bytes(scope, tree, trav, n, dims, s):
+def algorithmic_bytes(scope, tree, trav, n, dims, s, heavy_entries=0):
     """Compulsory bytes of one launch of the scope's kernel ('Kernels')."""
     nb = 2 ** dims
     B, aB = tree.nboxes, tree.aligned_nboxes
@@ -162,18 +162,19 @@ def algorithmic_bytes(scope, tree, trav, n, dims, s):
     l3_lists = sum(int(b.lists.shape[0]) for b in trav.from_sep_smaller_by_level)
     l3_close = 0 if trav.from_sep_close_smaller_lists is None else \
         int(trav.from_sep_close_smaller_lists.shape[0])
+    l1 = csr(trav.neighbor_source_boxes_starts, trav.neighbor_source_boxes_lists)
+    g_counts = 4 * (nl + 2) * (T + 1)                    # per-(slot, row) counts / offsets
     table = {
-        "trav_colleagues_count": tree_read + 4 * (B + 1),
-        "trav_colleagues_fill": tree_read + coll,
-        "trav_list1_count": tree_read + 4 * T + 4 * (T + 1),
-        "trav_list1_fill": tree_read + 4 * T + csr(trav.neighbor_source_boxes_starts,
-                                                   trav.neighbor_source_boxes_lists),
-        "trav_list2_count": tree_read + coll + 4 * TP + 4 * (TP + 1),
-        "trav_list2_fill": tree_read + coll + 4 * TP + csr(trav.from_sep_siblings_starts,
-                                                           trav.from_sep_siblings_lists),
-        "trav_list3_count": tree_read + coll + 4 * T + 4 * (nl + 1) * (T + 1),
-        "trav_list3_fill": tree_read + coll + 4 * T + 4 * (nl + 1) * (T + 1)
-        + 4 * (l3_lists + l3_close),
+        # top-down colleagues: box geometry + child table in, staged rows + list-2 counts/masks out
+        "trav_colleagues_count": tree_read + coll + 4 * B + 32 * B,
+        "trav_colleagues_fill": 2 * coll,
+        "trav_list2_count": 4 * TP + 4 * B + 4 * (TP + 1),
+        "trav_list2_fill": coll + 32 * B + 4 * TP + aB * 4 * nb
+        + csr(trav.from_sep_siblings_starts, trav.from_sep_siblings_lists),
+        # fused list-1+3 walk (count pass also stages the entries the fill pass copies)
+        "l13_walk_count": tree_read + coll + 4 * T + g_counts + 4 * (l3_lists + l3_close) + l1,
+        "l13_walk_fill": tree_read + coll + 4 * T + g_counts + 4 * (l3_lists + l3_close) + l1,
+        "l13_unstage": 2 * (4 * (l3_lists + l3_close) + l1) + g_counts,
         "trav_list4_count": tree_read + coll + 4 * TP + 4 * (TP + 1),
         "trav_list4_fill": tree_read + coll + 4 * TP + csr(trav.from_sep_bigger_starts,
                                                            trav.from_sep_bigger_lists),
@@ -183,7 +184,12 @@ def algorithmic_bytes(scope, tree, trav, n, dims, s):
         "bt_make_keys": n * (dims * s + 8),
         "bt_permute": n * (4 + 2 * dims * s),
         "bt_bounding_box": n * dims * s,
+        "bt_box_extents": n * dims * s + 2 * aB * dims * s,
     }
+    if heavy_entries:
+        table["l13_heavy_sort_pass"] = 2 * 12 * heavy_entries
+        table["l13_heavy_scatter"] = 16 * heavy_entries
+        table["l13_heavy_steps_fill"] = 12 * heavy_entries
     return table.get(scope)
 
 
@@ -229,19 +235,29 @@ def run_ours(args):
         trav, _ = tg(actx, tree)
         return tree, trav
 
-    if sharded:
+    step_sharded = None
+    if world > 1:
         from boxtree_b200 import distributed as bd
         comm = bd.TorchDistComm()
+        # ONE global problem = rank 0's particle set; rank r starts with its r-th slice
+        gsrc, gkw_np = (src, kw) if sharded else make_inputs(recipe, n, dtype, seed_shift=0)
+        if sharded:
+            gd, gdk = dsrc, dkw
+        else:
+            gd = [to_dev(x) for x in gsrc]
+            gdk = {k: (to_dev(v) if isinstance(v, np.ndarray) else
+                       [to_dev(x) for x in v] if k == "targets" else v) for k, v in gkw_np.items()}
 
         def my_slice(t):
             m = int(t.shape[0])
             return t[rank * m // world:(rank + 1) * m // world].contiguous()
 
-        ssrc = [my_slice(x) for x in dsrc]
+        ssrc = [my_slice(x) for x in gd]
         skw = {k: (my_slice(v) if isinstance(v, torch.Tensor) else
-                   [my_slice(x) for x in v] if k == "targets" else v) for k, v in dkw.items()}
+                   [my_slice(x) for x in v] if k == "targets" else v) for k, v in gdk.items()}
+        del gd, gdk
 
-        def step_resident():  # noqa: F811
+        def step_sharded():
             # NCCL all-gather of the particle slices -> replicated tree build -> only this
             # rank's share of the traversal (masks, local tree, local traversal)
             g = bd.allgather_particles(actx, comm, ssrc)
@@ -253,6 +269,9 @@ def run_ours(args):
             tree, _ = tb(actx, g, **gk)
             local_tree, local_trav, _, _ = bd.sharded_setup(actx, tree, tg, comm)
             return local_tree, local_trav
+
+        if sharded:
+            step_resident = step_sharded  # noqa: F811
 
     # pinned host copies for the end-to-end arm
     def pin(a):
@@ -317,6 +336,22 @@ def run_ours(args):
     npoints_job = n if sharded else world * n
     value = npoints_job / (ms_per_step * 1e-3) / 1e6
 
+    # N > 1, replicas as the main arm: also time the distributed path (ONE global problem of
+    # the same workload, strong scaling) so that both numbers come from the same run
+    distributed = None
+    if world > 1 and not sharded:
+        o = step_sharded()
+        del o
+        dsteps = max(1, min(args.steps, 3))
+        ms_d, o = timed(step_sharded, dsteps)
+        del o
+        distributed = {"value": n / (ms_d / dsteps * 1e-3) / 1e6, "unit": "Mpoints/s",
+                       "ms_per_step": ms_d / dsteps, "steps": dsteps, "scaling": "strong",
+                       "points_total": n,
+                       "parallelism": "sharded: NCCL all-gather of particle slices, replicated tree "
+                                      "build, traversal rows sharded by the reference's DFS-order "
+                                      "work partition (boxtree.distributed setup)"}
+
     # end to end (host buffers in, result summary out)
     e2e_steps = max(1, min(args.steps, 3))
     if sharded:
@@ -351,13 +386,15 @@ def run_ours(args):
     if rank == 0:
         lib.bt_prof_enable(0)
         rep = _cabi.profile_report()
-        nested_parents = {"bt_sort_particles"}
+        # scopes that only wrap other scopes
+        nested_parents = {"bt_sort_particles", "trav_list13_count", "trav_list13_fill"}
         leaf = {k: v for k, v in rep.items() if k not in nested_parents}
         total_ms = sum(v[1] for v in leaf.values())
         top = max(leaf.items(), key=lambda kv: kv[1][1])
         scope, (calls, tot) = top
         avg_ms = tot / calls
-        abytes = algorithmic_bytes(scope, tree, trav, n, dims, s_bytes)
+        abytes = algorithmic_bytes(scope, tree, trav, n, dims, s_bytes,
+                                   heavy_entries=int(tg.last_stats.get("heavy_entries_list3", 0)))
         peaks_path = os.path.join(HERE, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             peak = float(json.load(open(peaks_path))["hbm_gbs"])
@@ -402,6 +439,8 @@ def run_ours(args):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu_baseline,
         }
+        if distributed is not None:
+            line["distributed"] = distributed
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -211,7 +211,8 @@ rs_onesweep_kernel(const unsigned long long* __restrict__ kin, unsigned long lon
 // vals may be generated as the identity permutation (vals == nullptr on input).
 static int radix_sort_pairs(int64_t n, unsigned long long* keys, unsigned long long* keys_alt,
                             unsigned* vals, unsigned* vals_alt, int identity_vals,
-                            int begin_bit, int end_bit, int* result_in_alt, cudaStream_t stream)
+                            int begin_bit, int end_bit, int* result_in_alt, cudaStream_t stream,
+                            const char* pass_scope = "rs_onesweep_pass")
 {
     *result_in_alt = 0;
     if (n <= 0 || end_bit <= begin_bit) {
@@ -254,7 +255,7 @@ static int radix_sort_pairs(int64_t n, unsigned long long* keys, unsigned long l
         const int bits = (end_bit - shift < kRsBits) ? (end_bit - shift) : kRsBits;
         const unsigned mask = (1u << bits) - 1u;
         BT_CHECK(cudaMemsetAsync(desc, 0, desc_bytes, stream));
-        BT_PROF("rs_onesweep_pass", stream);
+        BT_PROF(pass_scope, stream);
         if (p == 0 && identity_vals)
             rs_onesweep_kernel<true><<<(unsigned)ntiles, kRsThreads, sizeof(RsSmem), stream>>>(
                 kin, kout, vin, vout, n, shift, mask, ghist + p * kRsRadix, desc, ticket);

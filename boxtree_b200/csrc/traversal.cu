@@ -374,14 +374,18 @@ static int counts_to_starts(int* a, int64_t n, long long* total_out, cudaStream_
 // the n-away neighbourhood}, in depth-first (Morton) order.  Every such c is a child of a
 // colleague of parent(b) or of parent(b) itself (|i_b - i_c| <= n implies the same for the
 // parents), so the lists are built level by level from the parent's list: one warp per box
-// tests the (|coll(parent)| + 1) * 2^d candidate children with the reference's predicate;
-// parent(b) is merged into its colleague list at its depth-first rank, so candidates are
-// visited -- and appended -- in the reference's order.  The candidates that are NOT adjacent
-// and stem from a colleague of the parent are exactly list 2 of b (traversal.py:556-601):
-// their count comes for free.  Rows are staged with a fixed stride of (2n+1)^d - 1 entries
+// first applies the reference's descend test to the |coll(parent)| + 1 parent-level boxes
+// (one per lane), then tests the children of those that pass -- densely packed over the lanes
+// -- with the reference's predicate; parent(b) is merged into its colleague list at its
+// depth-first rank, so candidates are visited -- and appended -- in the reference's order.
+// The candidates that are NOT adjacent and stem from a colleague of the parent (all children
+// of the parent-level boxes that fail the descend test, plus the failing children of the
+// others) are exactly list 2 of b (traversal.py:556-601): count and membership mask come for free.  Rows are staged with a fixed stride of (2n+1)^d - 1 entries
 // and compacted to CSR afterwards.
 constexpr int kXfCollSource = 1;   // b or one of its colleagues is a source box
 constexpr int kXfHasChild = 2;     // b has at least one child
+
+constexpr int kCollMaskWordsMax = 40;     // (2n+1)^d * 2^d / 32 + 1 for n <= 2 in 3-D
 
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256)
@@ -391,11 +395,12 @@ coll_topdown_kernel(TreeView<T, DIM> t, const int* __restrict__ level_start, int
                     unsigned char* __restrict__ xflags, unsigned* __restrict__ l2mask, int mask_words)
 {
     constexpr int NB = 1 << DIM;
-    constexpr int U = 4;
     __shared__ T rad[kMaxWalkLevels];
+    __shared__ unsigned smask_all[8][kCollMaskWordsMax];
     fill_rad_table(rad, t.root_extent);
     const int lo = level_start[lev], hi = level_start[lev + 1];
     const int lane = threadIdx.x & 31;
+    unsigned* smask = smask_all[threadIdx.x >> 5];
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     const T nbhd = (T)t.n_away;
     for (int b = lo + w; b < hi; b += nw) {
@@ -418,55 +423,77 @@ coll_topdown_kernel(TreeView<T, DIM> t, const int* __restrict__ level_start, int
         int pos = 0;
         for (int j = lane; j < np; j += 32) pos += (dfs_rank[prow[j]] < prank) ? 1 : 0;
         pos = __reduce_add_sync(0xffffffffu, pos);
-        const int ncand = (np + 1) * NB;
+        const int nparents = np + 1;                      // the parent merged into its colleagues
+        const int nwords = (nparents * NB + 31) >> 5;
+        for (int i = lane; i < nwords; i += 32) smask[i] = 0u;
+        __syncwarp();
         int out = 0, n2 = 0;
         bool src_coll = false;
         int* orow = tmp + (int64_t)b * stride;
-        unsigned* mrow = l2mask ? l2mask + (int64_t)b * mask_words : nullptr;
-        if (mrow && lane == 0) mrow[mask_words - 1] = (unsigned)pos;
-        for (int k0 = 0; k0 < ncand; k0 += 32 * U) {
-            int c[U]; bool fromcoll[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int k = k0 + u * 32 + lane;
-                c[u] = 0; fromcoll[u] = false;
-                if (k < ncand) {
-                    const int j = k / NB, m = k % NB;
-                    const int P = (j == pos) ? p : prow[j - (j > pos ? 1 : 0)];
-                    fromcoll[u] = (j != pos);
-                    c[u] = t.child(P, m);
+        for (int j0 = 0; j0 < nparents; j0 += 32) {
+            // (1) one parent-level box per lane: can any of its children be adjacent to b?  This is
+            //     the test the reference's walk makes before it descends into the box (:429-452).
+            const int j = j0 + lane;
+            const bool valid = j < nparents;
+            const int P = valid ? ((j == pos) ? p : prow[j - (j > pos ? 1 : 0)]) : 0;
+            bool padj = false;
+            if (valid) {
+                if (j == pos) padj = true;
+                else {
+                    T pc[DIM]; t.center(P, pc);
+                    padj = adj_nbhd<T, DIM>(rad, center, level, nbhd, pc, level - 1);
                 }
             }
-            T cc[U][DIM];
+            const unsigned adjm = __ballot_sync(0xffffffffu, padj);
+            // (2) far parent-level boxes: all their children are list-2 entries of b
+            if (valid && !padj) {
+                unsigned bits = 0;
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-#pragma unroll
-                for (int a = 0; a < DIM; ++a) cc[u][a] = c[u] ? t.centers[t.aligned * a + c[u]] : (T)0;
+                for (int m = 0; m < NB; ++m) bits |= (t.child(P, m) != 0) ? (1u << m) : 0u;
+                if (bits) atomicOr(&smask[(j * NB) >> 5], bits << ((j * NB) & 31));
+                n2 += __popc(bits);
             }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
+            // (3) children of the near ones, densely packed: lane q <-> (q / 2^d-th near box, child q % 2^d)
+            const int ncand = __popc(adjm) * NB;
+            for (int q0 = 0; q0 < ncand; q0 += 32) {
+                const int q = q0 + lane;
+                const bool act = q < ncand;
+                const int src = act ? (int)__fns(adjm, 0, q / NB + 1) : 0;
+                const int Pq = __shfl_sync(0xffffffffu, P, src & 31);
+                const int jq = j0 + src, m = q % NB;
+                const int c = act ? t.child(Pq, m) : 0;
                 bool adj = false, sep = false;
-                if (c[u] && c[u] != b) {
-                    adj = adj_nbhd<T, DIM>(rad, center, level, nbhd, cc[u], level);
-                    sep = !adj && fromcoll[u];
+                if (c && c != b) {
+                    T cc[DIM]; t.center(c, cc);
+                    adj = adj_nbhd<T, DIM>(rad, center, level, nbhd, cc, level);
+                    sep = !adj && (jq != pos);
                 }
-                if (adj && (t.flags[c[u]] & BT_BOX_IS_SOURCE_BOX)) src_coll = true;
+                if (adj && (t.flags[c] & BT_BOX_IS_SOURCE_BOX)) src_coll = true;
                 const unsigned ba = __ballot_sync(0xffffffffu, adj);
                 const int slot = out + __popc(ba & ((1u << lane) - 1u));
-                if (adj && slot < stride) orow[slot] = c[u];
+                if (adj && slot < stride) orow[slot] = c;
                 out += __popc(ba);
-                const unsigned bs = __ballot_sync(0xffffffffu, sep);
-                n2 += __popc(bs);
-                // candidate k = (position in the merged parent list) * 2^d + Morton child
-                if (mrow && lane == 0 && k0 + u * 32 < ncand) mrow[(k0 >> 5) + u] = bs;
+                if (sep) {
+                    atomicOr(&smask[(jq * NB + m) >> 5], 1u << ((jq * NB + m) & 31));
+                    ++n2;
+                }
             }
         }
         if (__any_sync(0xffffffffu, src_coll)) xf |= kXfCollSource;
+        n2 = __reduce_add_sync(0xffffffffu, n2);
+        __syncwarp();
+        if (l2mask) {
+            // bit k of the row = candidate k (k / 2^d-th box of the merged parent list, child k % 2^d)
+            unsigned* mrow = l2mask + (int64_t)b * mask_words;
+            for (int i = lane; i < nwords; i += 32) mrow[i] = smask[i];
+            if (lane == 0) mrow[mask_words - 1] = (unsigned)pos;
+        }
         if (lane == 0) {
             counts[b] = out < stride ? out : stride;
             if (l2cnt) l2cnt[b] = n2;
             xflags[b] = xf;
         }
+        __syncwarp();
     }
 }
 
@@ -1838,7 +1865,8 @@ static int heavy_sort_and_scatter_groups(const HeavyWs& ws, long long ecount_hos
     if (rank_bits + row_bits + slot_bits > 64) return BT_ERR_UNSUPPORTED;
     int in_alt = 0;
     BT_TRY(radix_sort_pairs(ecount_host, ws.ekeys[0], ws.ekeys[1], ws.evals[0], ws.evals[1], 0, 0,
-                            rank_bits + row_bits + slot_bits, &in_alt, s));
+                            rank_bits + row_bits + slot_bits, &in_alt, s, "l13_heavy_sort_pass"));
+    BT_PROF("l13_heavy_scatter", s);
     int* group_start = nullptr;
     const int64_t ngroups = (int64_t)nslots * nheavy;
     BT_CHECK(temp_alloc((void**)&group_start, sizeof(int) * (ngroups + 1), s));
@@ -1877,8 +1905,12 @@ static int list13_impl(int phase, const bt_tree_view* tv, const bt_list3_args* a
         BT_CHECK(cudaMemsetAsync(ws.hctl, 0, sizeof(int) * BT_HCTL_SIZE, s));
         BT_CHECK(cudaMemsetAsync(ws.heavy_total, 0, sizeof(long long), s));
         if (ntgt > 0) {
-            list13_coop_kernel<T, DIM, false><<<cgrid, kTravBlock, 0, s>>>(t, x, xflags, ntgt, G, nullptr, ws, near_cap);
-            BT_LAUNCH_CHECK();
+            {
+                BT_PROF("l13_walk_count", s);
+                list13_coop_kernel<T, DIM, false><<<cgrid, kTravBlock, 0, s>>>(t, x, xflags, ntgt, G, nullptr, ws, near_cap);
+                BT_LAUNCH_CHECK();
+            }
+            BT_PROF("l13_heavy_steps_count", s);
             list13_heavy_seed_kernel<T, DIM, false><<<kNumSMs, 256, 0, s>>>(t, x, xflags, ntgt, G, ws);
             BT_LAUNCH_CHECK();
             for (int st = 0; st < nsteps; ++st) {
@@ -1898,21 +1930,26 @@ static int list13_impl(int phase, const bt_tree_view* tv, const bt_list3_args* a
         BT_LAUNCH_CHECK();
     } else if (ntgt > 0) {
         if (ws.stage_cap > 0) {
+            BT_PROF("l13_unstage", s);
             list13_unstage_kernel<<<grid_for((int64_t)ntgt * 32, 256, 8), 256, 0, s>>>(
                 ntgt, nrows, G, ws.row_heavy, ws.stage, ws.stage_cap, ws.stage_count, lists);
             BT_LAUNCH_CHECK();
         }
         if (nwalk_host > 0) {        // rows the count pass could not stage are walked again
+            BT_PROF("l13_walk_fill", s);
             list13_coop_kernel<T, DIM, true><<<cgrid, kTravBlock, 0, s>>>(t, x, xflags, ntgt, G, lists, ws, near_cap);
             BT_LAUNCH_CHECK();
         }
         if (heavy_total_host > 0) {
-            BT_CHECK(cudaMemsetAsync(ws.hctl + kHctlECount, 0, sizeof(int) * (BT_HCTL_SIZE - kHctlECount), s));
-            list13_heavy_seed_kernel<T, DIM, true><<<kNumSMs, 256, 0, s>>>(t, x, xflags, ntgt, G, ws);
-            BT_LAUNCH_CHECK();
-            for (int st = 0; st < nsteps; ++st) {
-                list13_heavy_step_kernel<T, DIM, true><<<kNumSMs * 8, 256, 0, s>>>(t, x, ntgt, st, G, ws);
+            {
+                BT_PROF("l13_heavy_steps_fill", s);
+                BT_CHECK(cudaMemsetAsync(ws.hctl + kHctlECount, 0, sizeof(int) * (BT_HCTL_SIZE - kHctlECount), s));
+                list13_heavy_seed_kernel<T, DIM, true><<<kNumSMs, 256, 0, s>>>(t, x, xflags, ntgt, G, ws);
                 BT_LAUNCH_CHECK();
+                for (int st = 0; st < nsteps; ++st) {
+                    list13_heavy_step_kernel<T, DIM, true><<<kNumSMs * 8, 256, 0, s>>>(t, x, ntgt, st, G, ws);
+                    BT_LAUNCH_CHECK();
+                }
             }
             BT_TRY(heavy_sort_and_scatter_groups(ws, heavy_total_host, t.nboxes, nheavy_host, nrows, rowlen, G,
                                                  lists, s));
@@ -2075,6 +2112,7 @@ int bt_trav_colleagues(int dtype, int phase, const bt_tree_view* tree, const int
 {
     BT_PROF(phase ? "trav_colleagues_fill" : "trav_colleagues_count", (cudaStream_t)stream);
     if (list2_masks && mask_words < ((stride + 1) * (1 << tree->dim) + 31) / 32 + 1) return BT_ERR_BAD_ARG;
+    if (((stride + 1) * (1 << tree->dim) + 31) / 32 + 1 > bt::kCollMaskWordsMax) return BT_ERR_UNSUPPORTED;
     BT_DISPATCH(dtype, tree->dim, colleagues_topdown_impl, phase, tree, level_start_box_nrs, dfs_rank,
                 (const signed char*)row_mask, stride, staging, starts, lists, list2_count_by_box, xflags,
                 list2_masks, mask_words, (long long*)totals_dev, (cudaStream_t)stream);

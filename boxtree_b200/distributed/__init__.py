@@ -14,7 +14,7 @@ from .comm import SingleProcessComm, TorchDistComm
 from .local_traversal import generate_local_travs
 from .local_tree import LocalTree, box_to_user_rank, generate_local_tree
 from .partition import (BoxMasks, get_box_ids_dfs_order, get_box_masks, get_box_masks_sharded,
-                        partition_segments, partition_work)
+                        partition_segments, partition_segments_device, partition_work)
 
 __all__ = [
     "SingleProcessComm", "TorchDistComm", "LocalTree", "BoxMasks", "get_box_ids_dfs_order",
@@ -125,9 +125,15 @@ def sharded_setup(actx, tree, traversal_builder, comm, cost_per_box=None,
     rank, size = comm.Get_rank(), comm.Get_size()
     if cost_per_box is None:
         cost_per_box = (1.0 + tree.box_source_counts_nonchild.double()
-                        + tree.box_target_counts_nonchild.double()).cpu().numpy()
-    dfs_order = get_box_ids_dfs_order(actx, tree).cpu().numpy()
-    seg = partition_segments(np.asarray(cost_per_box)[dfs_order], size)[rank]
+                        + tree.box_target_counts_nonchild.double())
+    dfs_order = get_box_ids_dfs_order(actx, tree)
+    with torch.cuda.stream(actx.stream):
+        segs = partition_segments_device(actx, cost_per_box, dfs_order, size)
+    if segs is None:      # general float costs: the reference's sequential accumulation, on the host
+        cost_host = cost_per_box.cpu().numpy() if isinstance(cost_per_box, torch.Tensor) \
+            else np.asarray(cost_per_box)
+        segs = partition_segments(cost_host[dfs_order.cpu().numpy()], size)
+    seg = segs[rank]
     responsible = dfs_order[int(seg[0]):int(seg[1])]
     masks, _partial, need = get_box_masks_sharded(actx, tree, responsible, traversal_builder)
     local_tree, src_idx, tgt_idx = generate_local_tree(

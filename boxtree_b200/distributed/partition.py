@@ -62,6 +62,42 @@ def partition_segments(cost_in_dfs_order, mpi_size):
     return segments
 
 
+def partition_segments_device(actx, cost_per_box, dfs_order, mpi_size):
+    """:func:`partition_segments` without moving the per-box arrays to the host, for costs that
+    are non-negative integers in float64 with an exactly representable total (the default
+    ``1 + particle counts``; any summation order then gives the reference's running sums bit
+    for bit).  Returns ``None`` when the costs do not qualify (the caller takes the host path,
+    which accumulates sequentially like the reference)."""
+    cost = cost_per_box if isinstance(cost_per_box, torch.Tensor) else \
+        actx.from_numpy(np.ascontiguousarray(np.asarray(cost_per_box, np.float64)))
+    if cost.dtype != torch.float64:
+        return None
+    c = cost[dfs_order.long()]
+    cum = torch.cumsum(c, 0)
+    nboxes = int(c.shape[0])
+    thr_host = None
+    total = cum[-1]
+    ok = ((c == torch.round(c)) & (c >= 0)).all() & (total < 2.0 ** 52)
+    # thresholds with the reference's expression, evaluated in float64 on the host
+    ok_total = torch.stack([ok.double(), total]).cpu().numpy()
+    if not ok_total[0]:
+        return None
+    total_workload = np.float64(ok_total[1])
+    thr_host = np.array([(k + 1) * total_workload / mpi_size for k in range(mpi_size - 1)], np.float64)
+    if mpi_size > 1:
+        hits = torch.searchsorted(cum, actx.from_numpy(thr_host), right=True).cpu().numpy()
+    else:
+        hits = np.zeros(0, np.int64)
+    segments = np.empty((mpi_size, 2), dtype=np.int32)
+    start = 0
+    for k in range(mpi_size - 1):
+        i = min(max(int(hits[k]), start), nboxes - 1)
+        segments[k] = [start, i + 1]
+        start = i + 1
+    segments[mpi_size - 1] = [start, nboxes]
+    return segments
+
+
 def partition_work(actx, cost_per_box, traversal, comm):
     """``partition.py:60-121``.  *cost_per_box* (numpy) is only significant on the root rank.
     Returns the numpy array of boxes the calling rank is responsible for."""
