@@ -74,7 +74,8 @@ class bt_heavy_ws(C.Structure):
     _fields_ = [("walk_budget", C.c_int32), ("row_heavy", vp), ("heavy_rows", vp), ("hctl", vp),
                 ("heavy_total", vp), ("frontier", vp * 2), ("frontier_cap", C.c_int64),
                 ("dfs_rank", vp), ("ekeys", vp * 2), ("evals", vp * 2), ("ecap", C.c_int64),
-                ("row_mask", vp), ("stage", vp), ("stage_cap", C.c_int32), ("stage_count", vp)]
+                ("row_mask", vp), ("stage", vp), ("stage_cap", C.c_int32), ("stage_count", vp),
+                ("dfs_order", vp)]
 
 
 HCTL_NWALK = 3

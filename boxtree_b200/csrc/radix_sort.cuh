@@ -99,7 +99,7 @@ rs_histogram_kernel(const unsigned long long* __restrict__ keys, int64_t n, int 
 #ifndef BT_RS_MIN_BLOCKS
 #define BT_RS_MIN_BLOCKS 3
 #endif
-template <bool kIdentityVals>
+template <bool kIdentityVals, bool kKeysOnly = false>
 __global__ void __launch_bounds__(kRsThreads, BT_RS_MIN_BLOCKS)
 rs_onesweep_kernel(const unsigned long long* __restrict__ kin, unsigned long long* __restrict__ kout,
                    const unsigned* __restrict__ vin, unsigned* __restrict__ vout, int64_t n,
@@ -187,12 +187,14 @@ rs_onesweep_kernel(const unsigned long long* __restrict__ kin, unsigned long lon
         sm.keys[pos[j]] = key[j];
     }
     // values ride along
+    if (!kKeysOnly) {
 #pragma unroll
-    for (int j = 0; j < kRsItems; ++j) {
-        const int idx = wbase + j * 32 + lane;
-        unsigned v = 0;
-        if (idx < cnt) v = kIdentityVals ? (unsigned)(base + idx) : ld_stream_u32(vin + base + idx);
-        sm.vals[pos[j]] = v;
+        for (int j = 0; j < kRsItems; ++j) {
+            const int idx = wbase + j * 32 + lane;
+            unsigned v = 0;
+            if (idx < cnt) v = kIdentityVals ? (unsigned)(base + idx) : ld_stream_u32(vin + base + idx);
+            sm.vals[pos[j]] = v;
+        }
     }
     __syncthreads();
 
@@ -202,13 +204,14 @@ rs_onesweep_kernel(const unsigned long long* __restrict__ kin, unsigned long lon
         const unsigned dg = (unsigned)(k >> shift) & mask;
         const long long g = sm.gbase[dg] + i;
         kout[g] = k;
-        vout[g] = sm.vals[i];
+        if (!kKeysOnly) vout[g] = sm.vals[i];
     }
 }
 
 // Sort pairs by key bits [begin_bit, end_bit).  Buffers ping-pong; returns in
 // *result_in_alt whether the sorted data ended in (keys_alt, vals_alt).
-// vals may be generated as the identity permutation (vals == nullptr on input).
+// vals may be generated as the identity permutation (identity_vals, vals == nullptr on input);
+// vals == vals_alt == nullptr without identity_vals sorts the keys alone.
 static int radix_sort_pairs(int64_t n, unsigned long long* keys, unsigned long long* keys_alt,
                             unsigned* vals, unsigned* vals_alt, int identity_vals,
                             int begin_bit, int end_bit, int* result_in_alt, cudaStream_t stream,
@@ -245,6 +248,8 @@ static int radix_sort_pairs(int64_t n, unsigned long long* keys, unsigned long l
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
         BT_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<false>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
+        BT_CHECK(cudaFuncSetAttribute((rs_onesweep_kernel<false, true>),
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
         attr_set = true;
     }
 
@@ -256,7 +261,10 @@ static int radix_sort_pairs(int64_t n, unsigned long long* keys, unsigned long l
         const unsigned mask = (1u << bits) - 1u;
         BT_CHECK(cudaMemsetAsync(desc, 0, desc_bytes, stream));
         BT_PROF(pass_scope, stream);
-        if (p == 0 && identity_vals)
+        if (!identity_vals && vals == nullptr)      // keys only
+            rs_onesweep_kernel<false, true><<<(unsigned)ntiles, kRsThreads, sizeof(RsSmem), stream>>>(
+                kin, kout, nullptr, nullptr, n, shift, mask, ghist + p * kRsRadix, desc, ticket);
+        else if (p == 0 && identity_vals)
             rs_onesweep_kernel<true><<<(unsigned)ntiles, kRsThreads, sizeof(RsSmem), stream>>>(
                 kin, kout, vin, vout, n, shift, mask, ghist + p * kRsRadix, desc, ticket);
         else

@@ -859,6 +859,7 @@ struct HeavyWs {
     unsigned long long* ekeys[2]; unsigned* evals[2]; long long ecap;
     const signed char* row_mask;     // optional [nboxes]: rows of boxes with mask 0 stay empty
     unsigned* stage; int stage_cap; int* stage_count;   // fused walk: entries staged by the count pass
+    const int* dfs_order;            // fused walk: box of every depth-first rank (keys-only heavy sort)
 };
 constexpr int kHctlNHeavy = 0, kHctlOverflow = 1, kHctlECount = 2, kHctlNWalk = 3, kHctlFrontier = 8;
 // row states left by the count pass of the fused walk (row_heavy[]): 0 = the fill pass walks
@@ -876,6 +877,7 @@ static HeavyWs make_ws(const bt_heavy_ws* w)
     h.evals[0] = w->evals[0]; h.evals[1] = w->evals[1]; h.ecap = w->ecap;
     h.row_mask = (const signed char*)w->row_mask;
     h.stage = w->stage; h.stage_cap = w->stage_cap; h.stage_count = w->stage_count;
+    h.dfs_order = w->dfs_order;
     return h;
 }
 
@@ -1738,11 +1740,9 @@ list13_heavy_seed_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, const unsigned
         auto near = [&](int sbox) {
             if (FILL) {
                 const int k = atomicAdd(ws.hctl + kHctlECount, 1);
-                if (k < ws.ecap) {
+                if (k < ws.ecap)       // the box is recovered from its rank after the sort
                     ws.ekeys[0][k] = ((unsigned long long)l1slot << (rank_bits + row_bits))
                                      | ((unsigned long long)h << rank_bits) | (unsigned)ws.dfs_rank[sbox];
-                    ws.evals[0][k] = (unsigned)sbox;
-                }
             } else atomicAdd(G + l1slot * rowlen + r, 1);
         };
         int a = box;
@@ -1814,11 +1814,9 @@ list13_heavy_step_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, int ntgt, int 
         const int slot = (act & kVisitNear) ? t.nlevels + 1 : (act & kVisitEmit) ? (int)t.levels[wb] : t.nlevels;
         if (FILL) {
             const long long k = warp_append(emits, ws.hctl + kHctlECount);
-            if (k >= 0 && k < ws.ecap) {
+            if (k >= 0 && k < ws.ecap)
                 ws.ekeys[0][k] = ((unsigned long long)slot << (rank_bits + row_bits))
                                  | ((unsigned long long)h << rank_bits) | (unsigned)ws.dfs_rank[wb];
-                ws.evals[0][k] = (unsigned)wb;
-            }
         } else heavy_count_add(G, rowlen, emits, slot, r);
         const long long q = warp_append(act & kVisitPush, ws.hctl + kHctlFrontier + step + 1);
         if (q >= 0) {
@@ -1840,7 +1838,7 @@ struct HeavyGroupIn {
 };
 
 __global__ void __launch_bounds__(256)
-heavy_scatter_groups_kernel(const unsigned long long* __restrict__ keys, const unsigned* __restrict__ vals,
+heavy_scatter_groups_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ dfs_order,
                             const int* __restrict__ ecount_dev, int rank_bits, int row_bits, int nheavy,
                             const int* __restrict__ heavy_rows, const int* __restrict__ group_start,
                             int64_t rowlen, const int* __restrict__ G, int* __restrict__ lists)
@@ -1851,7 +1849,8 @@ heavy_scatter_groups_kernel(const unsigned long long* __restrict__ keys, const u
         const unsigned long long key = ld_stream_u64(keys + i);
         const int h = (int)((key >> rank_bits) & ((1ull << row_bits) - 1ull));
         const int64_t slot = (int64_t)(key >> (rank_bits + row_bits));
-        lists[G[slot * rowlen + heavy_rows[h]] + (i - group_start[slot * nheavy + h])] = (int)vals[i];
+        lists[G[slot * rowlen + heavy_rows[h]] + (i - group_start[slot * nheavy + h])] =
+            dfs_order[(int)(key & ((1ull << rank_bits) - 1ull))];
     }
 }
 
@@ -1864,7 +1863,7 @@ static int heavy_sort_and_scatter_groups(const HeavyWs& ws, long long ecount_hos
     int slot_bits = 0; while ((1ll << slot_bits) < nslots) ++slot_bits;
     if (rank_bits + row_bits + slot_bits > 64) return BT_ERR_UNSUPPORTED;
     int in_alt = 0;
-    BT_TRY(radix_sort_pairs(ecount_host, ws.ekeys[0], ws.ekeys[1], ws.evals[0], ws.evals[1], 0, 0,
+    BT_TRY(radix_sort_pairs(ecount_host, ws.ekeys[0], ws.ekeys[1], nullptr, nullptr, 0, 0,
                             rank_bits + row_bits + slot_bits, &in_alt, s, "l13_heavy_sort_pass"));
     BT_PROF("l13_heavy_scatter", s);
     int* group_start = nullptr;
@@ -1874,7 +1873,7 @@ static int heavy_sort_and_scatter_groups(const HeavyWs& ws, long long ecount_hos
     PlainOut out{group_start, nullptr, ngroups};
     BT_TRY(scan_exclusive(ngroups, nullptr, in, out, s));
     heavy_scatter_groups_kernel<<<grid_for(ecount_host, 256, 8), 256, 0, s>>>(
-        ws.ekeys[in_alt], ws.evals[in_alt], ws.hctl + kHctlECount, rank_bits, row_bits, nheavy, ws.heavy_rows,
+        ws.ekeys[in_alt], ws.dfs_order, ws.hctl + kHctlECount, rank_bits, row_bits, nheavy, ws.heavy_rows,
         group_start, rowlen, G, lists);
     BT_LAUNCH_CHECK();
     BT_CHECK(cudaFreeAsync(group_start, s));

@@ -30,8 +30,8 @@ DEFAULT_WALK_BUDGET = 1024
 
 #: entries per row the count pass of the fused list-1+3 walk may stage for the fill pass
 #: (rows with more are walked a second time); BT_STAGE_STRIDE overrides, 0 disables
-DEFAULT_STAGE_STRIDE = 64
-_STAGE_MAX_BYTES = 16 << 30
+DEFAULT_STAGE_STRIDE = 256
+_STAGE_MAX_BYTES = 8 << 30
 
 # bits of bt_set_walk_mode (include/boxtree_b200.h) that select a different host sequence
 WALK_MODE_COLL_TOPDOWN = 64
@@ -56,6 +56,8 @@ class _HeavyWorkspace:
         self.ecap = 0
         self.stage = self.stage_count = None
         self.stage_cap = 0
+        self.dfs_order = None
+        self.keys_only = False
         self._alloc_frontier(max(nrows, 8 * nboxes, 1 << 16))
 
     def enable_staging(self, stride):
@@ -76,7 +78,8 @@ class _HeavyWorkspace:
         self.ecap = n
         if n > 0:
             self.ekeys = [self.actx.empty(n, np.int64), self.actx.empty(n, np.int64)]
-            self.evals = [self.actx.empty(n, np.int32), self.actx.empty(n, np.int32)]
+            if not self.keys_only:
+                self.evals = [self.actx.empty(n, np.int32), self.actx.empty(n, np.int32)]
 
     def struct(self) -> bt_heavy_ws:
         w = bt_heavy_ws()
@@ -91,7 +94,9 @@ class _HeavyWorkspace:
         w.dfs_rank = dptr(self.dfs_rank)
         if self.ekeys is not None:
             w.ekeys[0], w.ekeys[1] = dptr(self.ekeys[0]), dptr(self.ekeys[1])
+        if self.evals is not None:
             w.evals[0], w.evals[1] = dptr(self.evals[0]), dptr(self.evals[1])
+        w.dfs_order = dptr(self.dfs_order)
         w.ecap = self.ecap
         w.row_mask = dptr(self.row_mask)
         w.stage = dptr(self.stage)
@@ -438,8 +443,17 @@ class FMMTraversalBuilder:
             rm13 = None if _list13_row_mask is None else dev(_list13_row_mask, np.int8)
             ws1 = None if fused13 else _HeavyWorkspace(actx, ntb, nboxes, dfs_rank, budget, rm13)
             ws3 = _HeavyWorkspace(actx, ntb, nboxes, dfs_rank, budget, rm13)
+            if fused13:
+                # the heavy rows sort (slot, row, rank) keys alone; the box comes back from its rank
+                dfs_order = actx.empty(max(nboxes, 1), np.int32)
+                check(lib.bt_reverse_index(nboxes, dptr(dfs_rank), dptr(dfs_order), sh),
+                      "bt_reverse_index")
+                ws3.dfs_order = dfs_order
+                ws3.keys_only = True
             if fused13 and nboxes < (1 << 27) and nlevels + 2 <= 31:
                 stage_stride = int(os.environ.get("BT_STAGE_STRIDE", DEFAULT_STAGE_STRIDE))
+                while stage_stride > 32 and ntb * stage_stride * 4 > _STAGE_MAX_BYTES:
+                    stage_stride //= 2
                 if ntb * stage_stride * 4 <= _STAGE_MAX_BYTES:
                     ws3.enable_staging(stage_stride)
 

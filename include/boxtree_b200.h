@@ -294,6 +294,8 @@ typedef struct {
     uint32_t *stage;
     int32_t stage_cap;
     int32_t *stage_count;
+    const int32_t *dfs_order;    /* bt_trav_list13: box id of every depth-first rank (inverse of
+                                    dfs_rank); its heavy rows sort keys only, evals stay unused */
 } bt_heavy_ws;
 
 /* pre-order (depth first, children in Morton order) rank of every box */
