@@ -402,9 +402,15 @@ def run_ours(args):
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = (abytes / (avg_ms * 1e-3) / 1e9) if abytes else None
+        # DRAM bytes of the same scope from the committed ncu --set full capture of this build
+        traffic = None
+        tkey = {"config3": "config3_10000000", "uniform1e7": "uniform_10000000_f64"}.get(args.workload)
+        tpath = os.path.join(HERE, "profiles", "r01_traffic.json")
+        if tkey and not args.n and os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(tkey, {}).get("bytes_per_launch", {}).get(scope)
         roofline = {"bound": "hbm", "kernel": scope, "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                    "traffic": None, "peak_source": peak_src,
+                    "traffic": traffic, "peak_source": peak_src,
                     "avg_launch_ms": avg_ms, "launches_per_step": calls / prof_steps,
                     "share_of_step": tot / total_ms if total_ms else None,
                     "algorithmic_bytes_per_launch": abytes,

@@ -60,3 +60,35 @@ with open(f"profiles/{tag}_ncu_full_{wl}.csv", "w") as f:
     for row in rows[2:]:
         w.writerow([row[c][:60] for c in cols])
 print(open(f"profiles/{tag}_launches_{wl}.txt").read())
+
+# per-scope DRAM traffic of one step (bench.py's roofline.traffic): kernel -> bench scope
+import json
+SCOPE_OF = [("list13_coop_kernel<double, 3, 0>", "l13_walk_count"), ("list13_coop_kernel<double, 3, 1>", "l13_walk_fill"),
+            ("list13_coop_kernel<float, 3, 0>", "l13_walk_count"), ("list13_coop_kernel<float, 3, 1>", "l13_walk_fill"),
+            ("coll_topdown_kernel", "trav_colleagues_count"), ("list2_masked_fill_kernel", "trav_list2_fill"),
+            ("list13_unstage_kernel", "l13_unstage"), ("rs_onesweep_kernel<0, 1>", "l13_heavy_sort_pass"),
+            ("rs_onesweep_kernel", "rs_onesweep_pass"), ("permute_kernel", "bt_permute"),
+            ("make_keys_kernel", "bt_make_keys"), ("box_extents_own_kernel", "bt_box_extents")]
+PER_CALL = {"trav_colleagues_count"}          # scopes whose one call launches the kernel once per level
+ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+acc = {}
+for row in rows[2:]:
+    for pat, scope in SCOPE_OF:
+        if pat in row[ki]:
+            b = float(row[ri].replace(",", "")) * mult.get(units[ri], 1.0) + \
+                float(row[wi].replace(",", "")) * mult.get(units[wi], 1.0)
+            a = acc.setdefault(scope, [0, 0.0])
+            a[0] += 1
+            a[1] += b
+            break
+traffic = {sc: (v[1] if sc in PER_CALL else v[1] / v[0]) for sc, v in acc.items()}
+path = f"profiles/{tag}_traffic.json"
+try:
+    allt = json.load(open(path))
+except (OSError, ValueError):
+    allt = {}
+allt[wl] = {"source": f"ncu --set full, profiles/{tag}_ncu_full_{wl}.csv (dram__bytes_read.sum + dram__bytes_write.sum)",
+            "bytes_per_launch": traffic}
+json.dump(allt, open(path, "w"), indent=1, sort_keys=True)
+print(json.dumps(allt[wl], indent=1))

@@ -178,6 +178,23 @@ def test_config3_properties_full_size(actx):
     dist = (cen[:, r2] - cen[:, l2]).abs().amax(0)
     size = float(tree.root_extent) * 0.5 ** lev[r2].double()
     assert bool((dist > 1.5 * size).all())
+    # completeness of the interaction lists at full size: every target hears every source once
+    from boxtree_b200.constant_one import constant_one_fmm
+    w = torch.randint(1, 5, (ns,), device=cs.device)
+    assert bool((constant_one_fmm(tree, trav, w) == w.sum()).all())
+    assert bool((constant_one_fmm(tree, trav.merge_close_lists(actx), w) == w.sum()).all())
+
+
+@pytest.mark.parametrize("spec", ["uniform:4000000:f64", "plummer:4000000:f32"])
+def test_constant_one_fmm_on_device_large(actx, spec):
+    """Constant-one FMM evaluated on the device on multi-million-point trees."""
+    import torch
+    from boxtree_b200.constant_one import constant_one_fmm
+    from tests.perf_probe import make
+    src, kw = make(spec)
+    tree, trav = _build(actx, src, kw, {})
+    w = torch.randint(1, 5, (len(src[0]),), device=tree.box_flags.device)
+    assert bool((constant_one_fmm(tree, trav, w) == w.sum()).all())
 
 
 def test_invariants_and_brute_force_on_cuda_result(actx):
@@ -200,6 +217,21 @@ def test_constant_one_fmm_on_cuda_result(actx):
     w = np.random.default_rng(1).integers(1, 5, 30000).astype(np.float64)
     assert np.all(constant_one_fmm(tree, trav, w) == w.sum())
     assert np.all(constant_one_fmm(tree, merged, w) == w.sum())
+
+
+def test_device_constant_one_fmm_matches_host(actx):
+    """The device evaluation (boxtree_b200.constant_one) against the oracle's host evaluation."""
+    import torch
+    from boxtree_b200.constant_one import constant_one_fmm as dev_fmm
+    from oracle.fmm import constant_one_fmm
+    src, tgt, radii = config3_inputs(30000, 30000)
+    tkw = dict(max_particles_in_box=30, targets=tgt, target_radii=radii, stick_out_factor=0.25,
+               extent_norm="linf", kind="adaptive-level-restricted")
+    tree, trav = _build(actx, src, tkw, {})
+    w = np.random.default_rng(2).integers(1, 9, 30000)
+    got = dev_fmm(tree, trav, torch.from_numpy(w)).cpu().numpy()
+    want = constant_one_fmm(actx.to_numpy(tree), actx.to_numpy(trav), w.astype(np.float64))
+    assert np.array_equal(got, want.astype(np.int64)) and np.all(got == w.sum())
 
 
 def test_error_behaviour(actx):
