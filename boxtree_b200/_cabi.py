@@ -75,7 +75,9 @@ class bt_heavy_ws(C.Structure):
                 ("heavy_total", vp), ("frontier", vp * 2), ("frontier_cap", C.c_int64),
                 ("dfs_rank", vp), ("ekeys", vp * 2), ("evals", vp * 2), ("ecap", C.c_int64),
                 ("row_mask", vp), ("stage", vp), ("stage_cap", C.c_int32), ("stage_count", vp),
-                ("dfs_order", vp)]
+                ("dfs_order", vp), ("subtree_size", vp), ("hrow_base", vp), ("hplan", vp),
+                ("seg_stride", C.c_int32), ("hseg_rank", vp), ("hseg_prefix", vp), ("hseg_kind", vp),
+                ("hseg_n", vp), ("hmap", vp), ("hmap_cap", C.c_int64), ("chunk_cnt", vp)]
 
 
 HCTL_NWALK = 3

@@ -174,7 +174,8 @@ __device__ __forceinline__ bool gen_list1(const TreeView<T, DIM>& t, const T* ra
 // row); the defaults are the faster choice measured on B200 (profiles/README.md).
 constexpr int kModeColl = 1, kModeList1 = 2, kModeList3 = 4, kModeList3Auto = 8,
               kModeList2Count = 16, kModeList2Fill = 32, kModeCollTopDown = 64, kModeFused13 = 128,
-              kModeNearCapZero = 256;   // testing: rows with near-field boxes above their level go heavy
+              kModeNearCapZero = 256,   // testing: rows with near-field boxes above their level go heavy
+              kModeHeavySort = 512;     // heavy rows of the fused walk by radix sort instead of the position map
 int g_walk_mode = kModeList1 | kModeList3Auto | kModeList2Fill | kModeCollTopDown | kModeFused13;
 
 struct CoopFrame { int parent; unsigned bits; };
@@ -860,6 +861,10 @@ struct HeavyWs {
     const signed char* row_mask;     // optional [nboxes]: rows of boxes with mask 0 stay empty
     unsigned* stage; int stage_cap; int* stage_count;   // fused walk: entries staged by the count pass
     const int* dfs_order;            // fused walk: box of every depth-first rank (keys-only heavy sort)
+    // fused walk, map mode (heavy rows without a sort), see "heavy rows by position map" below
+    const int* subtree_size; long long* hrow_base; long long* hplan; int seg_stride;
+    int* hseg_rank; int* hseg_prefix; unsigned char* hseg_kind; int* hseg_n;
+    unsigned char* hmap; long long hmap_cap; int* chunk_cnt;
 };
 constexpr int kHctlNHeavy = 0, kHctlOverflow = 1, kHctlECount = 2, kHctlNWalk = 3, kHctlFrontier = 8;
 // row states left by the count pass of the fused walk (row_heavy[]): 0 = the fill pass walks
@@ -878,6 +883,10 @@ static HeavyWs make_ws(const bt_heavy_ws* w)
     h.row_mask = (const signed char*)w->row_mask;
     h.stage = w->stage; h.stage_cap = w->stage_cap; h.stage_count = w->stage_count;
     h.dfs_order = w->dfs_order;
+    h.subtree_size = w->subtree_size; h.hrow_base = (long long*)w->hrow_base; h.hplan = (long long*)w->hplan;
+    h.seg_stride = w->seg_stride; h.hseg_rank = w->hseg_rank; h.hseg_prefix = w->hseg_prefix;
+    h.hseg_kind = w->hseg_kind; h.hseg_n = w->hseg_n; h.hmap = w->hmap; h.hmap_cap = w->hmap_cap;
+    h.chunk_cnt = w->chunk_cnt;
     return h;
 }
 
@@ -1880,6 +1889,281 @@ static int heavy_sort_and_scatter_groups(const HeavyWs& ws, long long ecount_hos
     return BT_OK;
 }
 
+// ---- heavy rows by position map (no sort) ------------------------------------
+// The entries of a heavy row are boxes below its roots coll(b) U {b} (plus the few near-field
+// boxes above b's level), and their order in every list is the depth-first rank.  The rank
+// ranges of the roots' subtrees are disjoint, so "depth-first order inside the row" is a
+// position in the concatenation of those ranges: a row owns a byte map over that
+// concatenation (row h: segments sorted by rank, each a root's subtree or one near-field box
+// from above), the breadth-first expansion stores slot + 1 at the position of every box it
+// appends -- one byte store, no atomics, no keys -- and one ordered pass over the map writes
+// the lists.  Rows are padded to whole chunks of kMapChunk positions; chunk histograms give
+// the per-(row, slot) counts (-> G) and the offsets of every chunk inside its row's lists.
+constexpr int kMapChunk = 1024;
+constexpr int kMapNearExtra = 136;       // >= 7 near-field boxes per level above b (3-D), 19 levels
+
+// phase 0: size of every heavy row's map
+template <typename T, int DIM>
+__global__ void __launch_bounds__(256)
+heavy_map_size_kernel(List3Args<T, DIM> x, int* __restrict__ row_len, HeavyWs ws)
+{
+    const int nheavy = ws.hctl[kHctlNHeavy];
+    const int stride = gridDim.x * blockDim.x;
+    for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < nheavy; h += stride) {
+        const int box = x.target_boxes[ws.heavy_rows[h]];
+        long long tot = ws.subtree_size[box] + kMapNearExtra;
+        for (int i = x.coll_starts[box]; i < x.coll_starts[box + 1]; ++i) tot += ws.subtree_size[x.coll_lists[i]];
+        tot = (tot + kMapChunk - 1) / kMapChunk * kMapChunk;
+        row_len[h] = (int)(tot / kMapChunk);                 // in chunks
+    }
+}
+struct RowLenIn {
+    const int* len;
+    __device__ int operator()(int64_t i) const { return len[i]; }
+};
+struct RowBaseOut {
+    long long* base; long long* total_out; const int* n_dev;
+    __device__ void operator()(int64_t i, long long excl) const { base[i] = excl * kMapChunk; }
+    __device__ void total(long long t) const { base[*n_dev] = t * kMapChunk; *total_out = t * kMapChunk; }
+};
+
+// segment table of every heavy row: roots in depth-first order, near-field boxes from above
+// (kind 1) inserted by rank; then the row's roots are seeded into the frontier
+template <typename T, int DIM>
+__global__ void __launch_bounds__(128)
+heavy_map_plan_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, const unsigned char* __restrict__ xflags,
+                      HeavyWs ws)
+{
+    __shared__ T rad[kMaxWalkLevels];
+    fill_rad_table(rad, t.root_extent);
+    const int nheavy = ws.hctl[kHctlNHeavy];
+    const int S = ws.seg_stride;
+    const int stride = gridDim.x * blockDim.x;
+    for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < nheavy; h += stride) {
+        const int r = ws.heavy_rows[h];
+        const int box = x.target_boxes[r];
+        T tc[DIM]; t.center(box, tc);
+        const int level = t.levels[box];
+        int* srank = ws.hseg_rank + (int64_t)h * S;
+        int* spre = ws.hseg_prefix + (int64_t)h * S;
+        unsigned char* skind = ws.hseg_kind + (int64_t)h * S;
+        // roots, self merged in by rank
+        const int cs = x.coll_starts[box], n = x.coll_starts[box + 1] - cs;
+        const int brank = ws.dfs_rank[box];
+        int ns = 0;
+        bool self_done = false;
+        for (int j = 0; j < n; ++j) {
+            const int rk = ws.dfs_rank[x.coll_lists[cs + j]];
+            if (!self_done && brank < rk) { srank[ns] = brank; skind[ns] = 0; ++ns; self_done = true; }
+            srank[ns] = rk; skind[ns] = 0; ++ns;
+        }
+        if (!self_done) { srank[ns] = brank; skind[ns] = 0; ++ns; }
+        // near-field boxes above the level (what list 1's walk appends before it reaches b's level)
+        int a = box;
+        for (int lv = level - 1; lv >= 0; --lv) {
+            a = t.parents[a];
+            if (!(xflags[a] & kXfCollSource)) continue;
+            const int as = x.coll_starts[a], an = x.coll_starts[a + 1] - as;
+            for (int j = 0; j <= an; ++j) {
+                const int sbox = (j < an) ? x.coll_lists[as + j] : a;
+                if (!(t.flags[sbox] & BT_BOX_IS_SOURCE_BOX)) continue;
+                bool take = (sbox == 0);
+                if (!take) { T sc[DIM]; t.center(sbox, sc); take = adj_nbhd<T, DIM>(rad, tc, level, (T)1, sc, lv); }
+                if (!take || ns >= S) continue;
+                const int rk = ws.dfs_rank[sbox];
+                int k = ns;
+                while (k > 0 && srank[k - 1] > rk) { srank[k] = srank[k - 1]; skind[k] = skind[k - 1]; --k; }
+                srank[k] = rk; skind[k] = 1; ++ns;
+            }
+        }
+        int pre = 0;
+        for (int k = 0; k < ns; ++k) {
+            spre[k] = pre;
+            pre += skind[k] ? 1 : ws.subtree_size[ws.dfs_order[srank[k]]];
+        }
+        ws.hseg_n[h] = ns;
+    }
+}
+
+// position of the box with depth-first rank rk in the map of heavy row h
+__device__ __forceinline__ long long heavy_map_pos(const HeavyWs& ws, int h, int rk)
+{
+    const int* srank = ws.hseg_rank + (int64_t)h * ws.seg_stride;
+    int lo = 0, hi = ws.hseg_n[h];                 // last segment with srank <= rk
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (srank[mid] <= rk) lo = mid; else hi = mid; }
+    return ws.hrow_base[h] + ws.hseg_prefix[(int64_t)h * ws.seg_stride + lo] + (rk - srank[lo]);
+}
+
+template <typename T, int DIM>
+__global__ void __launch_bounds__(256)
+heavy_map_seed_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, const unsigned char* __restrict__ xflags,
+                      HeavyWs ws)
+{
+    __shared__ T rad[kMaxWalkLevels];
+    fill_rad_table(rad, t.root_extent);
+    const int nheavy = ws.hctl[kHctlNHeavy];
+    const int S = ws.seg_stride;
+    const unsigned char l1code = (unsigned char)(t.nlevels + 2);        // slot nlevels + 1, plus 1
+    // one thread per (heavy row, segment)
+    const long long total = (long long)nheavy * S;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int h = (int)(i / S), k = (int)(i % S);
+        if (k >= ws.hseg_n[h]) continue;
+        const long long pos = ws.hrow_base[h] + ws.hseg_prefix[i];
+        if (ws.hseg_kind[i]) { ws.hmap[pos] = l1code; continue; }        // near-field box from above
+        const int cb = ws.dfs_order[ws.hseg_rank[i]];
+        const int box = x.target_boxes[ws.heavy_rows[h]];
+        const unsigned char fl = t.flags[cb];
+        bool adj = true;
+        if (cb != box && t.n_away != 1) {
+            T tc[DIM], sc[DIM]; t.center(box, tc); t.center(cb, sc);
+            const int level = t.levels[box];
+            adj = adj_nbhd<T, DIM>(rad, tc, level, (T)1, sc, level);
+        }
+        if (adj && (fl & BT_BOX_IS_SOURCE_BOX)) ws.hmap[pos] = l1code;
+        bool nearok;
+        if (cb == box) { if (!(fl & BT_BOX_HAS_SOURCE_CHILD_BOXES)) continue; nearok = true; }
+        else { if (!(xflags[cb] & kXfHasChild)) continue; nearok = adj && (fl & BT_BOX_HAS_SOURCE_CHILD_BOXES); }
+        const int q = atomicAdd(ws.hctl + kHctlFrontier, 1);
+        if (q < ws.frontier_cap)
+            ws.frontier[0][q] = ((unsigned long long)h << 32) | (nearok ? 0x80000000ull : 0ull) | (unsigned)cb;
+        else ws.hctl[kHctlOverflow] = 1;
+    }
+}
+
+template <typename T, int DIM>
+__global__ void __launch_bounds__(256)
+heavy_map_step_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, int step, HeavyWs ws)
+{
+    constexpr int NB = 1 << DIM;
+    __shared__ T rad[kMaxWalkLevels];
+    fill_rad_table(rad, t.root_extent);
+    const unsigned long long* fin = ws.frontier[step & 1];
+    unsigned long long* fout = ws.frontier[(step + 1) & 1];
+    long long nitems = ws.hctl[kHctlFrontier + step];
+    if (nitems > ws.frontier_cap) nitems = ws.frontier_cap;
+    const long long total = nitems * NB;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x; tid < ((total + 31) & ~31ll);
+         tid += stride) {
+        int act = 0, wb = 0, h = 0;
+        unsigned long long nearok = 0;
+        if (tid < total) {
+            const unsigned long long item = fin[tid / NB];
+            h = (int)(item >> 32);
+            nearok = item & 0x80000000ull;
+            const int parent = (int)(item & 0x7fffffffull), m = (int)(tid % NB);
+            L3Ctx<T, DIM> c; l3_make_ctx<T, DIM>(t, rad, x, x.target_boxes[ws.heavy_rows[h]], c);
+            wb = t.child(parent, m);
+            act = list3_visit<T, DIM>(t, rad, x, c, wb);
+            if (!nearok) act &= ~kVisitNear;
+        }
+        if (act & (kVisitEmit | kVisitClose | kVisitNear)) {
+            const int slot = (act & kVisitNear) ? t.nlevels + 1 : (act & kVisitEmit) ? (int)t.levels[wb] : t.nlevels;
+            ws.hmap[heavy_map_pos(ws, h, ws.dfs_rank[wb])] = (unsigned char)(slot + 1);
+        }
+        const long long q = warp_append(act & kVisitPush, ws.hctl + kHctlFrontier + step + 1);
+        if (q >= 0) {
+            if (q < ws.frontier_cap) fout[q] = ((unsigned long long)h << 32) | nearok | (unsigned)wb;
+            else ws.hctl[kHctlOverflow] = 1;
+        }
+    }
+}
+
+__device__ __forceinline__ int heavy_row_of_chunk(const HeavyWs& ws, int nheavy, long long chunk)
+{
+    const long long p = chunk * kMapChunk;
+    int lo = 0, hi = nheavy;                              // last row with base <= p
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ws.hrow_base[mid] <= p) lo = mid; else hi = mid; }
+    return lo;
+}
+
+// per-chunk histogram of the slots (one warp per chunk)
+__global__ void __launch_bounds__(256)
+heavy_map_hist_kernel(int nslots, HeavyWs ws)
+{
+    __shared__ int cnt[8][kMaxWalkLevels + 2];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long nchunks = ws.hplan[0] / kMapChunk;
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long c = w; c < nchunks; c += nw) {
+        for (int l = lane; l < nslots; l += 32) cnt[wib][l] = 0;
+        __syncwarp();
+        const unsigned* src = reinterpret_cast<const unsigned*>(ws.hmap + c * kMapChunk);
+        for (int i = lane; i < kMapChunk / 4; i += 32) {
+            unsigned v = src[i];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) { const unsigned code = (v >> (8 * b)) & 0xffu; if (code) atomicAdd(&cnt[wib][code - 1], 1); }
+        }
+        __syncwarp();
+        for (int l = lane; l < nslots; l += 32) ws.chunk_cnt[c * nslots + l] = cnt[wib][l];
+        __syncwarp();
+    }
+}
+
+// per heavy row: chunk counts -> exclusive offsets inside the row; row totals -> G (one warp per row)
+__global__ void __launch_bounds__(256)
+heavy_map_rowscan_kernel(int nslots, int64_t rowlen, int* __restrict__ G, HeavyWs ws)
+{
+    const int nheavy = ws.hctl[kHctlNHeavy];
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int h = w; h < nheavy; h += nw) {
+        const long long c0 = ws.hrow_base[h] / kMapChunk, c1 = ws.hrow_base[h + 1] / kMapChunk;
+        const int r = ws.heavy_rows[h];
+        for (int sl = lane; sl < nslots; sl += 32) {
+            int run = 0;
+            for (long long c = c0; c < c1; ++c) {
+                const int v = ws.chunk_cnt[c * nslots + sl];
+                ws.chunk_cnt[c * nslots + sl] = run;
+                run += v;
+            }
+            G[sl * rowlen + r] = run;
+        }
+    }
+}
+
+// fill: ordered pass over the map (one warp per chunk)
+__global__ void __launch_bounds__(256)
+heavy_map_extract_kernel(int nslots, int64_t rowlen, const int* __restrict__ G, int* __restrict__ lists,
+                         HeavyWs ws)
+{
+    __shared__ int run[8][kMaxWalkLevels + 2];
+    const int nheavy = ws.hctl[kHctlNHeavy];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long nchunks = ws.hplan[0] / kMapChunk;
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long c = w; c < nchunks; c += nw) {
+        const int h = heavy_row_of_chunk(ws, nheavy, c);
+        const int r = ws.heavy_rows[h];
+        const int S = ws.seg_stride, ns = ws.hseg_n[h];
+        const int* spre = ws.hseg_prefix + (int64_t)h * S;
+        const int* srank = ws.hseg_rank + (int64_t)h * S;
+        for (int l = lane; l < nslots; l += 32) run[wib][l] = ws.chunk_cnt[c * nslots + l];
+        __syncwarp();
+        const long long base = c * kMapChunk;
+        for (int i0 = 0; i0 < kMapChunk; i0 += 32) {
+            const unsigned code = ws.hmap[base + i0 + lane];
+            if (!__any_sync(0xffffffffu, code != 0)) continue;
+            const int sl = code ? (int)code - 1 : 63;
+            const unsigned peers = __match_any_sync(0xffffffffu, sl);
+            const int prior = code ? run[wib][sl] : 0;
+            __syncwarp();
+            if (code) {
+                const int local = (int)(base + i0 + lane - ws.hrow_base[h]);
+                int lo = 0, hi = ns;                  // last segment with prefix <= local
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (spre[mid] <= local) lo = mid; else hi = mid; }
+                const int box = ws.dfs_order[srank[lo] + (local - spre[lo])];
+                lists[G[sl * rowlen + r] + prior + __popc(peers & ((1u << lane) - 1u))] = box;
+                if (lane == __ffs(peers) - 1) run[wib][sl] = prior + __popc(peers);
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+    }
+}
+
 template <typename T, int DIM>
 static int list13_impl(int phase, const bt_tree_view* tv, const bt_list3_args* a, const unsigned char* xflags,
                        int ntgt, int* G, int* C, int* lists, long long* summary, const bt_heavy_ws* w,
@@ -1895,19 +2179,46 @@ static int list13_impl(int phase, const bt_tree_view* tv, const bt_list3_args* a
                         a->box_source_counts_cumul, a->min_nsources_cumul};
     const int nrows = t.nlevels + 2;             // source levels, close list, list 1
     const int near_cap = (g_walk_mode & kModeNearCapZero) ? 0 : kNearMax;
+    const bool use_map = ws.hrow_base != nullptr;   // heavy rows by position map (else: radix sort)
     const int64_t rowlen = (int64_t)ntgt + 1;
     const int64_t total_len = rowlen * nrows;
     const int cgrid = grid_for((int64_t)ntgt << DIM, kTravBlock, 16);
     const int nsteps = t.nlevels;
+    // counts -> global offsets (one flattened scan), non-empty ranks, summary for the host
+    auto finish_counts = [&]() -> int {
+        InPlaceIn in{G};
+        PlainOut out{G, summary + 2 * (nrows + 1), total_len};
+        BT_TRY(scan_exclusive(total_len, nullptr, in, out, s));
+        NonemptyIn nin{G, total_len, rowlen};
+        PlainOut nout{C, nullptr, total_len};
+        BT_TRY(scan_exclusive(total_len, nullptr, nin, nout, s));
+        list3_summary_kernel<<<1, 64, 0, s>>>(G, C, nrows, rowlen, summary);
+        BT_LAUNCH_CHECK();
+        return BT_OK;
+    };
     if (phase == 0) {
         BT_CHECK(cudaMemsetAsync(G, 0, sizeof(int) * (total_len + 1), s));
         BT_CHECK(cudaMemsetAsync(ws.hctl, 0, sizeof(int) * BT_HCTL_SIZE, s));
         BT_CHECK(cudaMemsetAsync(ws.heavy_total, 0, sizeof(long long), s));
+        if (use_map) BT_CHECK(cudaMemsetAsync(ws.hplan, 0, 2 * sizeof(long long), s));
         if (ntgt > 0) {
             {
                 BT_PROF("l13_walk_count", s);
                 list13_coop_kernel<T, DIM, false><<<cgrid, kTravBlock, 0, s>>>(t, x, xflags, ntgt, G, nullptr, ws, near_cap);
                 BT_LAUNCH_CHECK();
+            }
+            if (use_map) {
+                // sizes of the heavy rows' maps; the host reads (nheavy, total) and calls phase 2
+                BT_PROF("l13_heavy_plan", s);
+                int* row_len = nullptr;
+                BT_CHECK(temp_alloc((void**)&row_len, sizeof(int) * (size_t)ntgt, s));
+                heavy_map_size_kernel<T, DIM><<<kNumSMs, 256, 0, s>>>(x, row_len, ws);
+                BT_LAUNCH_CHECK();
+                RowLenIn in{row_len};
+                RowBaseOut out{ws.hrow_base, ws.hplan, ws.hctl + kHctlNHeavy};
+                BT_TRY(scan_exclusive(ntgt, ws.hctl + kHctlNHeavy, in, out, s));
+                BT_CHECK(cudaFreeAsync(row_len, s));
+                return BT_OK;
             }
             BT_PROF("l13_heavy_steps_count", s);
             list13_heavy_seed_kernel<T, DIM, false><<<kNumSMs, 256, 0, s>>>(t, x, xflags, ntgt, G, ws);
@@ -1919,14 +2230,30 @@ static int list13_impl(int phase, const bt_tree_view* tv, const bt_list3_args* a
             heavy_total_kernel<<<kNumSMs, 256, 0, s>>>(G, rowlen, nrows, ws);
             BT_LAUNCH_CHECK();
         }
-        InPlaceIn in{G};
-        PlainOut out{G, summary + 2 * (nrows + 1), total_len};
-        BT_TRY(scan_exclusive(total_len, nullptr, in, out, s));
-        NonemptyIn nin{G, total_len, rowlen};
-        PlainOut nout{C, nullptr, total_len};
-        BT_TRY(scan_exclusive(total_len, nullptr, nin, nout, s));
-        list3_summary_kernel<<<1, 64, 0, s>>>(G, C, nrows, rowlen, summary);
-        BT_LAUNCH_CHECK();
+        if (!use_map) BT_TRY(finish_counts());
+    } else if (phase == 2) {
+        // map mode: expand the heavy rows ONCE into their position maps, count from the maps
+        if (!use_map) return BT_ERR_BAD_ARG;
+        if (ntgt > 0 && nheavy_host > 0) {
+            BT_PROF("l13_heavy_expand", s);
+            BT_CHECK(cudaMemsetAsync(ws.hmap, 0, (size_t)ws.hmap_cap, s));
+            heavy_map_plan_kernel<T, DIM><<<grid_for(nheavy_host, 128, 8), 128, 0, s>>>(t, x, xflags, ws);
+            BT_LAUNCH_CHECK();
+            heavy_map_seed_kernel<T, DIM><<<grid_for((int64_t)nheavy_host * ws.seg_stride, 256, 8), 256, 0, s>>>(t, x, xflags, ws);
+            BT_LAUNCH_CHECK();
+            for (int st = 0; st < nsteps; ++st) {
+                heavy_map_step_kernel<T, DIM><<<kNumSMs * 8, 256, 0, s>>>(t, x, st, ws);
+                BT_LAUNCH_CHECK();
+            }
+            const long long nchunks = ws.hmap_cap / kMapChunk;
+            heavy_map_hist_kernel<<<grid_for(nchunks * 32, 256, 8), 256, 0, s>>>(nrows, ws);
+            BT_LAUNCH_CHECK();
+            heavy_map_rowscan_kernel<<<grid_for((int64_t)nheavy_host * 32, 256, 8), 256, 0, s>>>(nrows, rowlen, G, ws);
+            BT_LAUNCH_CHECK();
+            heavy_total_kernel<<<kNumSMs, 256, 0, s>>>(G, rowlen, nrows, ws);
+            BT_LAUNCH_CHECK();
+        }
+        BT_TRY(finish_counts());
     } else if (ntgt > 0) {
         if (ws.stage_cap > 0) {
             BT_PROF("l13_unstage", s);
@@ -1939,7 +2266,14 @@ static int list13_impl(int phase, const bt_tree_view* tv, const bt_list3_args* a
             list13_coop_kernel<T, DIM, true><<<cgrid, kTravBlock, 0, s>>>(t, x, xflags, ntgt, G, lists, ws, near_cap);
             BT_LAUNCH_CHECK();
         }
-        if (heavy_total_host > 0) {
+        if (use_map) {
+            if (nheavy_host > 0) {
+                BT_PROF("l13_heavy_extract", s);
+                const long long nchunks = ws.hmap_cap / kMapChunk;
+                heavy_map_extract_kernel<<<grid_for(nchunks * 32, 256, 8), 256, 0, s>>>(nrows, rowlen, G, lists, ws);
+                BT_LAUNCH_CHECK();
+            }
+        } else if (heavy_total_host > 0) {
             {
                 BT_PROF("l13_heavy_steps_fill", s);
                 BT_CHECK(cudaMemsetAsync(ws.hctl + kHctlECount, 0, sizeof(int) * (BT_HCTL_SIZE - kHctlECount), s));
@@ -2220,7 +2554,7 @@ int bt_trav_list13(int dtype, int phase, const bt_tree_view* tree, const bt_list
                    int64_t* summary_dev, const bt_heavy_ws* ws, int64_t heavy_total, int nheavy,
                    int nwalk, void* stream)
 {
-    BT_PROF(phase ? "trav_list13_fill" : "trav_list13_count", (cudaStream_t)stream);
+    BT_PROF(phase == 1 ? "trav_list13_fill" : "trav_list13_count", (cudaStream_t)stream);
     BT_DISPATCH(dtype, tree->dim, list13_impl, phase, tree, args, xflags, ntarget_boxes, G, C, lists,
                 (long long*)summary_dev, ws, (long long)heavy_total, nheavy, nwalk, (cudaStream_t)stream);
 }

@@ -36,6 +36,7 @@ _STAGE_MAX_BYTES = 8 << 30
 # bits of bt_set_walk_mode (include/boxtree_b200.h) that select a different host sequence
 WALK_MODE_COLL_TOPDOWN = 64
 WALK_MODE_FUSED13 = 128
+WALK_MODE_HEAVY_SORT = 512
 
 
 class _HeavyWorkspace:
@@ -58,7 +59,30 @@ class _HeavyWorkspace:
         self.stage_cap = 0
         self.dfs_order = None
         self.keys_only = False
+        # heavy rows by position map (fused walk)
+        self.subtree_size = self.hrow_base = self.hplan = None
+        self.seg_stride = 0
+        self.hseg_rank = self.hseg_prefix = self.hseg_kind = self.hseg_n = None
+        self.hmap = self.chunk_cnt = None
+        self.hmap_cap = 0
         self._alloc_frontier(max(nrows, 8 * nboxes, 1 << 16))
+
+    def enable_map(self, subtree_size, seg_stride):
+        """Heavy rows of the fused walk by position map instead of a sort."""
+        self.subtree_size = subtree_size
+        self.seg_stride = int(seg_stride)
+        self.hrow_base = self.actx.empty(self.nrows + 1, np.int64)
+        self.hplan = self.actx.zeros(2, np.int64)
+
+    def alloc_map(self, nheavy, map_bytes, nslots):
+        n = max(nheavy, 1) * self.seg_stride
+        self.hseg_rank = self.actx.empty(n, np.int32)
+        self.hseg_prefix = self.actx.empty(n, np.int32)
+        self.hseg_kind = self.actx.empty(n, np.uint8)
+        self.hseg_n = self.actx.empty(max(nheavy, 1), np.int32)
+        self.hmap_cap = int(map_bytes)
+        self.hmap = self.actx.empty(max(self.hmap_cap, 1), np.uint8)
+        self.chunk_cnt = self.actx.empty(max(self.hmap_cap // 1024, 1) * nslots, np.int32)
 
     def enable_staging(self, stride):
         """Fused list-1+3 walk: room for *stride* staged entries per row (count pass)."""
@@ -97,6 +121,17 @@ class _HeavyWorkspace:
         if self.evals is not None:
             w.evals[0], w.evals[1] = dptr(self.evals[0]), dptr(self.evals[1])
         w.dfs_order = dptr(self.dfs_order)
+        w.subtree_size = dptr(self.subtree_size)
+        w.hrow_base = dptr(self.hrow_base)
+        w.hplan = dptr(self.hplan)
+        w.seg_stride = self.seg_stride
+        w.hseg_rank = dptr(self.hseg_rank)
+        w.hseg_prefix = dptr(self.hseg_prefix)
+        w.hseg_kind = dptr(self.hseg_kind)
+        w.hseg_n = dptr(self.hseg_n)
+        w.hmap = dptr(self.hmap)
+        w.hmap_cap = self.hmap_cap
+        w.chunk_cnt = dptr(self.chunk_cnt)
         w.ecap = self.ecap
         w.row_mask = dptr(self.row_mask)
         w.stage = dptr(self.stage)
@@ -395,7 +430,6 @@ class FMMTraversalBuilder:
             check(lib.bt_trav_dfs_rank(dimensions, nboxes, tv.aligned_nboxes, nlevels,
                                        dptr(level_start_box_nrs), dptr(box_child_ids),
                                        dptr(subtree_size), dptr(dfs_rank), sh), "bt_trav_dfs_rank")
-            del subtree_size
 
             # {{{ b3: same-level non-well-separated boxes (traversal.py:2135-2141)
 
@@ -450,6 +484,9 @@ class FMMTraversalBuilder:
                       "bt_reverse_index")
                 ws3.dfs_order = dfs_order
                 ws3.keys_only = True
+                if not (walk_mode & WALK_MODE_HEAVY_SORT):
+                    nroots_max = (2 * int(self.well_sep_is_n_away) + 1) ** dimensions
+                    ws3.enable_map(subtree_size, nroots_max + 136)
             if fused13 and nboxes < (1 << 27) and nlevels + 2 <= 31:
                 stage_stride = int(os.environ.get("BT_STAGE_STRIDE", DEFAULT_STAGE_STRIDE))
                 while stage_stride > 32 and ntb * stage_stride * 4 > _STAGE_MAX_BYTES:
@@ -513,6 +550,15 @@ class FMMTraversalBuilder:
                     check(lib.bt_trav_list13(dcode, 0, C.byref(tv), C.byref(a3), dptr(xflags), ntb,
                                              dptr(G), dptr(Cc), None, dptr(summary),
                                              C.byref(ws3.struct()), 0, 0, 0, sh), "list 1+3 count")
+                    if ws3.hrow_base is not None:
+                        # heavy rows by position map: size the maps, expand the rows once
+                        plan = _read_i64(actx, torch.cat([ws3.hctl[:1].to(torch.int64),
+                                                          ws3.hplan[:1]]))
+                        ws3.alloc_map(int(plan[0]), int(plan[1]), nslots)
+                        check(lib.bt_trav_list13(dcode, 2, C.byref(tv), C.byref(a3), dptr(xflags),
+                                                 ntb, dptr(G), dptr(Cc), None, dptr(summary),
+                                                 C.byref(ws3.struct()), 0, int(plan[0]), 0, sh),
+                              "list 1+3 heavy expansion")
                 else:
                     check(lib.bt_trav_list3(dcode, 0, C.byref(tv), C.byref(a3), ntb, dptr(G),
                                             dptr(Cc), None, dptr(summary), C.byref(ws3.struct()),
@@ -589,7 +635,8 @@ class FMMTraversalBuilder:
                                          dptr(l4c_lists_raw), None, sh), "list 4 fill")
 
             l3_all = actx.empty(int(g0[nslots]), np.int32)
-            ws3.alloc_entries(heavy3_total)
+            if ws3.hrow_base is None:          # sort-based heavy rows need key buffers
+                ws3.alloc_entries(heavy3_total)
             if fused13:
                 check(lib.bt_trav_list13(dcode, 1, C.byref(tv), C.byref(a3), dptr(xflags), ntb,
                                          dptr(G), dptr(Cc), dptr(l3_all), dptr(summary),

@@ -91,7 +91,8 @@ int bt_prof_report(char *buf, int len);   /* "name\tcalls\ttotal_ms" lines */
  * per row (the reference's mapping): 1 colleagues, 2 list 1, 4 list 3, 8 list 3 only with
  * target extents, 16 list-2 count, 32 list-2 fill; 64 = colleagues built top-down
  * (bt_trav_colleagues) instead of by walks, 128 = lists 1 and 3 from one fused walk
- * (bt_trav_list13).  Same output either way. */
+ * (bt_trav_list13), 512 = its heavy rows by radix sort instead of the position map (the host
+ * chooses by leaving bt_heavy_ws.hrow_base NULL); 256 is a test switch.  Same output. */
 void bt_set_walk_mode(int mode);
 int bt_get_walk_mode(void);
 
@@ -296,6 +297,25 @@ typedef struct {
     int32_t *stage_count;
     const int32_t *dfs_order;    /* bt_trav_list13: box id of every depth-first rank (inverse of
                                     dfs_rank); its heavy rows sort keys only, evals stay unused */
+    /* bt_trav_list13, heavy rows by position map (hrow_base != NULL; no sort): a heavy row owns
+     * a byte map over the concatenated depth-first rank ranges of its roots' subtrees; the
+     * breadth-first expansion (phase 2, run once) stores slot + 1 at the position of every
+     * appended box, an ordered pass over the map (phase 1) writes the lists.
+     * phase 0 fills hrow_base [ntarget_boxes + 1] (map offset of every heavy row, multiples of
+     * 1024) and hplan[0] = total map bytes; the host reads hctl[0] (heavy rows) and hplan[0],
+     * allocates hseg_* [nheavy * seg_stride] (seg_stride >= (2n+1)^d + 136), hseg_n [nheavy],
+     * hmap [hmap_cap = hplan[0]], chunk_cnt [hmap_cap / 1024 * (nlevels + 2)], calls phase 2. */
+    const int32_t *subtree_size; /* from bt_trav_dfs_rank */
+    int64_t *hrow_base;
+    int64_t *hplan;              /* [2] */
+    int32_t seg_stride;
+    int32_t *hseg_rank;
+    int32_t *hseg_prefix;
+    uint8_t *hseg_kind;
+    int32_t *hseg_n;
+    uint8_t *hmap;
+    int64_t hmap_cap;
+    int32_t *chunk_cnt;
 } bt_heavy_ws;
 
 /* pre-order (depth first, children in Morton order) rank of every box */
@@ -351,7 +371,9 @@ int bt_trav_list3_compress(int nlevels, int ntarget_boxes, const int32_t *G, con
  * and are merged in by depth-first rank.  Needs bt_trav_colleagues' lists and xflags.
  * G, C: int32 [nlevels + 2, ntarget_boxes + 1] (+1): rows as in bt_trav_list3, row nlevels+1
  * is list 1.  summary_dev: int64 [2*(nlevels+3) + 1] = G[l][0], C[l][0], then the grand
- * total in 64 bits.  bt_trav_list3_compress (list1_starts != NULL) yields the list-1 starts;
+ * total in 64 bits.  Phases: 0 = walk (+ counts and scans, or with the position map of
+ * bt_heavy_ws only the map sizes), 2 = position-map mode: expansion of the heavy rows +
+ * counts and scans, 1 = fill.  bt_trav_list3_compress (list1_starts != NULL) yields the list-1 starts;
  * its lists are lists[G[nlevels+1][0] .. G[nlevels+2][0]). */
 int bt_trav_list13(int dtype, int phase, const bt_tree_view *tree, const bt_list3_args *args,
                    const uint8_t *xflags, int ntarget_boxes, int32_t *G, int32_t *C,

@@ -37,16 +37,26 @@ _HEAVY_CASES = [c for c in _CASES if c["name"] in (
     "ext-lr-n2", "ext-minsrc", "two-level", "single-box")]
 
 
+@pytest.mark.parametrize("heavy_by_sort", [False, True])
 @pytest.mark.parametrize("budget", [1, 8, 100])
 @pytest.mark.parametrize(
     "case", _HEAVY_CASES,
     ids=[f"{c['dims']}d-{np.dtype(c['dtype']).name}-{c['name']}" for c in _HEAVY_CASES])
-def test_parity_heavy_row_path(actx, builders, case, budget, monkeypatch):
-    """Force (almost) every row of lists 1 and 3 through the grid-wide heavy-row path."""
+def test_parity_heavy_row_path(actx, builders, case, budget, heavy_by_sort, monkeypatch):
+    """Force (almost) every row of lists 1 and 3 through the grid-wide heavy-row path, with the
+    position map (default) and with the radix sort."""
+    from boxtree_b200 import _cabi
+    lib = _cabi.load()
     monkeypatch.setenv("BT_WALK_BUDGET", str(budget))
     tb, travs = builders
     case = dict(case)
-    bad = run_case(case, actx, tb, travs)
+    default_mode = lib.bt_get_walk_mode()
+    try:
+        if heavy_by_sort:
+            lib.bt_set_walk_mode(default_mode | 512)
+        bad = run_case(case, actx, tb, travs)
+    finally:
+        lib.bt_set_walk_mode(default_mode)
     assert not bad, bad[:10]
     if case["n"] > 1000 and case["dims"] >= 2 and budget <= 8:
         st = case["_trav_stats"]      # the fused list-1+3 walk reports its heavy rows under list 3
