@@ -698,14 +698,15 @@ box_info_kernel(int nboxes, int sources_are_targets, int have_ext,
 // as the reference's serial loop (:1345-1368).  Four boxes per warp (8 lanes each: a leaf
 // holds at most a few dozen particles); a box with many own particles (upper-level boxes of
 // a tree with extents) is taken by the whole warp.
-constexpr int kExtGroup = 8, kExtBig = 128;
+constexpr int kExtGroup = 8, kExtBig = 128, kExtHuge = 2048;
 
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256)
 box_extents_own_kernel(int nboxes, int aligned, const T* __restrict__ box_centers,
                        const int* __restrict__ pstarts, const int* __restrict__ pcounts,
                        const T* p0, const T* p1, const T* p2, const T* __restrict__ radii,
-                       T* __restrict__ bb_min, T* __restrict__ bb_max)
+                       T* __restrict__ bb_min, T* __restrict__ bb_max, int* __restrict__ huge_list,
+                       int* __restrict__ huge_count)
 {
     constexpr int GPW = 32 / kExtGroup;
     const T* parts[3] = {p0, p1, p2};
@@ -719,7 +720,10 @@ box_extents_own_kernel(int nboxes, int aligned, const T* __restrict__ box_center
 #pragma unroll
         for (int a = 0; a < DIM; ++a) mn[a] = mx[a] = valid ? box_centers[a * aligned + ibox] : (T)0;
         const int s = valid ? pstarts[ibox] : 0, e = valid ? s + pcounts[ibox] : 0;
-        const bool big = (e - s) > kExtBig;
+        // boxes with thousands of own particles go to a list for box_extents_huge_kernel
+        const bool huge = (e - s) > kExtHuge;
+        if (huge && gl == 0) huge_list[atomicAdd(huge_count, 1)] = ibox;
+        const bool big = !huge && (e - s) > kExtBig;
         if (!big) {
             for (int ip = s + gl; ip < e; ip += kExtGroup) {
                 const T rad = radii ? radii[ip] : (T)0;
@@ -774,8 +778,63 @@ box_extents_own_kernel(int nboxes, int aligned, const T* __restrict__ box_center
                 mn[a] = (lo < mn[a]) ? lo : mn[a];
                 mx[a] = (mx[a] < hi) ? hi : mx[a];
             }
-            if (valid && gl == 0) { bb_min[a * aligned + ibox] = mn[a]; bb_max[a * aligned + ibox] = mx[a]; }
+            if (valid && !huge && gl == 0) { bb_min[a * aligned + ibox] = mn[a]; bb_max[a * aligned + ibox] = mx[a]; }
         }
+    }
+}
+
+// boxes with more than kExtHuge own particles: one block per box
+template <typename T, int DIM>
+__global__ void __launch_bounds__(256)
+box_extents_huge_kernel(int aligned, const T* __restrict__ box_centers, const int* __restrict__ pstarts,
+                        const int* __restrict__ pcounts, const T* p0, const T* p1, const T* p2,
+                        const T* __restrict__ radii, T* __restrict__ bb_min, T* __restrict__ bb_max,
+                        const int* __restrict__ huge_list, const int* __restrict__ huge_count)
+{
+    const T* parts[3] = {p0, p1, p2};
+    __shared__ T smn[8][DIM], smx[8][DIM];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nhuge = *huge_count;
+    for (int i = blockIdx.x; i < nhuge; i += gridDim.x) {
+        const int ibox = huge_list[i];
+        T mn[DIM], mx[DIM];
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) mn[a] = mx[a] = box_centers[a * aligned + ibox];
+        const int s = pstarts[ibox], e = s + pcounts[ibox];
+        for (int ip = s + threadIdx.x; ip < e; ip += blockDim.x) {
+            const T rad = radii ? radii[ip] : (T)0;
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) {
+                const T c = parts[a][ip];
+                const T lo = c - rad, hi = c + rad;
+                mn[a] = (lo < mn[a]) ? lo : mn[a];
+                mx[a] = (mx[a] < hi) ? hi : mx[a];
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const T lo = __shfl_xor_sync(0xffffffffu, mn[a], o);
+                const T hi = __shfl_xor_sync(0xffffffffu, mx[a], o);
+                mn[a] = (lo < mn[a]) ? lo : mn[a];
+                mx[a] = (mx[a] < hi) ? hi : mx[a];
+            }
+            if (lane == 0) { smn[warp][a] = mn[a]; smx[warp][a] = mx[a]; }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) {
+                T lo = smn[0][a], hi = smx[0][a];
+                for (int w = 1; w < 8; ++w) {
+                    lo = (smn[w][a] < lo) ? smn[w][a] : lo;
+                    hi = (hi < smx[w][a]) ? smx[w][a] : hi;
+                }
+                bb_min[a * aligned + ibox] = lo; bb_max[a * aligned + ibox] = hi;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -1001,11 +1060,22 @@ static int box_extents_impl(int nboxes, int aligned, int nlevels, const int* lev
                             void* bmax, cudaStream_t s)
 {
     if (nboxes <= 0) return BT_OK;
+    // list of the boxes with more than kExtHuge own particles ([0] = count)
+    int* huge = nullptr;
+    const size_t huge_cap = (size_t)nboxes;
+    BT_CHECK(temp_alloc((void**)&huge, sizeof(int) * (huge_cap + 1), s));
+    BT_CHECK(cudaMemsetAsync(huge, 0, sizeof(int), s));
     box_extents_own_kernel<T, DIM><<<grid_for((int64_t)nboxes * kExtGroup, 256, 8), 256, 0, s>>>(
         nboxes, aligned, (const T*)centers, pstarts, pcounts, (const T*)parts[0],
         DIM > 1 ? (const T*)parts[1] : nullptr, DIM > 2 ? (const T*)parts[2] : nullptr,
-        (const T*)radii, (T*)bmin, (T*)bmax);
+        (const T*)radii, (T*)bmin, (T*)bmax, huge + 1, huge);
     BT_LAUNCH_CHECK();
+    box_extents_huge_kernel<T, DIM><<<(unsigned)(huge_cap < 4 * kNumSMs ? huge_cap : 4 * kNumSMs), 256, 0, s>>>(
+        aligned, (const T*)centers, pstarts, pcounts, (const T*)parts[0],
+        DIM > 1 ? (const T*)parts[1] : nullptr, DIM > 2 ? (const T*)parts[2] : nullptr,
+        (const T*)radii, (T*)bmin, (T*)bmax, huge + 1, huge);
+    BT_LAUNCH_CHECK();
+    BT_CHECK(cudaFreeAsync(huge, s));
     for (int lev = nlevels - 2; lev >= 0; --lev) {       // the deepest level has no children
         const int start = level_start_host[lev], stop = level_start_host[lev + 1];
         if (stop <= start) continue;

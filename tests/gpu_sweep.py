@@ -67,6 +67,10 @@ def make_cases(quick=False):
                 base, name="ext-minsrc", ntargets=15000, radii=True,
                 tree={"max_particles_in_box": 30, "stick_out_factor": 0.25},
                 trav={"_from_sep_smaller_min_nsources_cumul": 40}))
+            # most targets are too fat to leave the top boxes: thousands of own particles per box
+            cases.append(dict(
+                base, name="ext-fat", ntargets=15000, radii=True, radii_scale=(2.0, -3),
+                tree={"max_particles_in_box": 30, "stick_out_factor": 0.25, "extent_norm": "linf"}))
             cases.append(dict(base, name="coincident", n=12, coincident=True,
                               tree={"max_particles_in_box": 10}, expect_max_levels=True))
     return cases
@@ -91,7 +95,8 @@ def make_inputs(case):
         kw["targets"] = tgt
         if case.get("radii"):
             rng = np.random.default_rng(13)
-            kw["target_radii"] = (0.05 * 2 ** rng.uniform(-10, 0, case["ntargets"])).astype(dt)
+            scale, lo = case.get("radii_scale", (0.05, -10))
+            kw["target_radii"] = (scale * 2 ** rng.uniform(lo, 0, case["ntargets"])).astype(dt)
     if case.get("weights"):
         kw["refine_weights"] = np.random.default_rng(10).integers(
             0, 10, n + (case.get("ntargets") or 0), dtype=np.int32)
