@@ -388,6 +388,9 @@ constexpr int kXfHasChild = 2;     // b has at least one child
 
 constexpr int kCollMaskWordsMax = 40;     // (2n+1)^d * 2^d / 32 + 1 for n <= 2 in 3-D
 
+// One warp per PARENT box p: the candidates of all 2^d children of p are the same boxes (the
+// children of p and of p's colleagues), so each candidate's id and centre is loaded once and
+// tested against every child of p.
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256)
 coll_topdown_kernel(TreeView<T, DIM> t, const int* __restrict__ level_start, int lev, int stride,
@@ -396,103 +399,128 @@ coll_topdown_kernel(TreeView<T, DIM> t, const int* __restrict__ level_start, int
                     unsigned char* __restrict__ xflags, unsigned* __restrict__ l2mask, int mask_words)
 {
     constexpr int NB = 1 << DIM;
+    constexpr unsigned nbmask = (1u << NB) - 1u;
     __shared__ T rad[kMaxWalkLevels];
-    __shared__ unsigned smask_all[8][kCollMaskWordsMax];
+    __shared__ T bcen_all[8][NB][DIM];            // centres of p's children, per warp
+    __shared__ unsigned char padj_all[8][128];    // per parent-level box: which children of p it can touch
     fill_rad_table(rad, t.root_extent);
-    const int lo = level_start[lev], hi = level_start[lev + 1];
-    const int lane = threadIdx.x & 31;
-    unsigned* smask = smask_all[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    T (*bcen)[DIM] = bcen_all[wib];
+    unsigned char* padj = padj_all[wib];
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     const T nbhd = (T)t.n_away;
-    for (int b = lo + w; b < hi; b += nw) {
-        const int mychild = (lane < NB) ? t.child(b, lane) : 0;
-        const unsigned char myfl = t.flags[b];
-        const bool has_child = __any_sync(0xffffffffu, mychild != 0);
-        unsigned char xf = (unsigned char)((has_child ? kXfHasChild : 0) |
-                                           ((myfl & BT_BOX_IS_SOURCE_BOX) ? kXfCollSource : 0));
-        const int p = t.parents[b];
-        if (p == b || (row_mask && !row_mask[b])) {       // root / row not needed: empty list
-            if (lane == 0) { counts[b] = 0; if (l2cnt) l2cnt[b] = 0; xflags[b] = xf; }
-            continue;
+    if (lev == 0) {                                // the root: no colleagues
+        if (w == 0) {
+            const int mychild = (lane < NB) ? t.child(0, lane) : 0;
+            const bool has_child = __any_sync(0xffffffffu, mychild != 0);
+            if (lane == 0) {
+                counts[0] = 0; if (l2cnt) l2cnt[0] = 0;
+                xflags[0] = (unsigned char)((has_child ? kXfHasChild : 0) |
+                                            ((t.flags[0] & BT_BOX_IS_SOURCE_BOX) ? kXfCollSource : 0));
+            }
         }
-        T center[DIM]; t.center(b, center);
-        const int level = t.levels[b];
+        return;
+    }
+    const int lo = level_start[lev - 1], hi = level_start[lev];     // parents
+    for (int p = lo + w; p < hi; p += nw) {
+        // children of p (lane m < 2^d holds child m), their own child bit and source bit
+        const int bch = (lane < NB) ? t.child(p, lane) : 0;
+        const unsigned chm = __ballot_sync(0xffffffffu, bch != 0) & nbmask;
+        if (!chm) continue;
+        unsigned char bxf = 0;
+        bool brow = false;                         // row wanted (not masked out)
+        if (bch) {
+            bool hc = false;
+#pragma unroll
+            for (int m = 0; m < NB; ++m) hc = hc || (t.child(bch, m) != 0);
+            bxf = (unsigned char)((hc ? kXfHasChild : 0) | ((t.flags[bch] & BT_BOX_IS_SOURCE_BOX) ? kXfCollSource : 0));
+            brow = !(row_mask && !row_mask[bch]);
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) bcen[lane][a] = t.centers[t.aligned * a + bch];
+        }
+        const unsigned rowm = __ballot_sync(0xffffffffu, brow) & nbmask;
+        const int level = lev;
         const int np = counts[p];
         const int* prow = tmp + (int64_t)p * stride;
-        // rank of the parent among its own colleagues in depth-first order
         const int prank = dfs_rank[p];
         int pos = 0;
         for (int j = lane; j < np; j += 32) pos += (dfs_rank[prow[j]] < prank) ? 1 : 0;
         pos = __reduce_add_sync(0xffffffffu, pos);
-        const int nparents = np + 1;                      // the parent merged into its colleagues
-        const int nwords = (nparents * NB + 31) >> 5;
-        for (int i = lane; i < nwords; i += 32) smask[i] = 0u;
+        const int nparents = np + 1;               // p merged into its colleagues at its rank
         __syncwarp();
-        int out = 0, n2 = 0;
-        bool src_coll = false;
-        int* orow = tmp + (int64_t)b * stride;
-        for (int j0 = 0; j0 < nparents; j0 += 32) {
-            // (1) one parent-level box per lane: can any of its children be adjacent to b?  This is
-            //     the test the reference's walk makes before it descends into the box (:429-452).
-            const int j = j0 + lane;
-            const bool valid = j < nparents;
-            const int P = valid ? ((j == pos) ? p : prow[j - (j > pos ? 1 : 0)]) : 0;
-            bool padj = false;
-            if (valid) {
-                if (j == pos) padj = true;
-                else {
-                    T pc[DIM]; t.center(P, pc);
-                    padj = adj_nbhd<T, DIM>(rad, center, level, nbhd, pc, level - 1);
-                }
-            }
-            const unsigned adjm = __ballot_sync(0xffffffffu, padj);
-            // (2) far parent-level boxes: all their children are list-2 entries of b
-            if (valid && !padj) {
-                unsigned bits = 0;
+        // (1) which children of p can a parent-level box P touch?  The reference's descend test
+        //     (:429-452) of P against every child
+        for (int j = lane; j < nparents; j += 32) {
+            unsigned bits = 0;
+            if (j == pos) bits = nbmask;
+            else {
+                const int P = prow[j - (j > pos ? 1 : 0)];
+                T pc[DIM]; t.center(P, pc);
 #pragma unroll
-                for (int m = 0; m < NB; ++m) bits |= (t.child(P, m) != 0) ? (1u << m) : 0u;
-                if (bits) atomicOr(&smask[(j * NB) >> 5], bits << ((j * NB) & 31));
-                n2 += __popc(bits);
+                for (int m = 0; m < NB; ++m)
+                    if ((rowm >> m) & 1u)
+                        bits |= adj_nbhd<T, DIM>(rad, bcen[m], level, nbhd, pc, level - 1) ? (1u << m) : 0u;
             }
-            // (3) children of the near ones, densely packed: lane q <-> (q / 2^d-th near box, child q % 2^d)
-            const int ncand = __popc(adjm) * NB;
-            for (int q0 = 0; q0 < ncand; q0 += 32) {
-                const int q = q0 + lane;
-                const bool act = q < ncand;
-                const int src = act ? (int)__fns(adjm, 0, q / NB + 1) : 0;
-                const int Pq = __shfl_sync(0xffffffffu, P, src & 31);
-                const int jq = j0 + src, m = q % NB;
-                const int c = act ? t.child(Pq, m) : 0;
-                bool adj = false, sep = false;
-                if (c && c != b) {
-                    T cc[DIM]; t.center(c, cc);
-                    adj = adj_nbhd<T, DIM>(rad, center, level, nbhd, cc, level);
-                    sep = !adj && (jq != pos);
-                }
-                if (adj && (t.flags[c] & BT_BOX_IS_SOURCE_BOX)) src_coll = true;
-                const unsigned ba = __ballot_sync(0xffffffffu, adj);
-                const int slot = out + __popc(ba & ((1u << lane) - 1u));
-                if (adj && slot < stride) orow[slot] = c;
-                out += __popc(ba);
-                if (sep) {
-                    atomicOr(&smask[(jq * NB + m) >> 5], 1u << ((jq * NB + m) & 31));
-                    ++n2;
-                }
-            }
+            padj[j] = (unsigned char)bits;
         }
-        if (__any_sync(0xffffffffu, src_coll)) xf |= kXfCollSource;
-        n2 = __reduce_add_sync(0xffffffffu, n2);
         __syncwarp();
-        if (l2mask) {
-            // bit k of the row = candidate k (k / 2^d-th box of the merged parent list, child k % 2^d)
-            unsigned* mrow = l2mask + (int64_t)b * mask_words;
-            for (int i = lane; i < nwords; i += 32) mrow[i] = smask[i];
-            if (lane == 0) mrow[mask_words - 1] = (unsigned)pos;
+        int out[NB], n2[NB];
+        unsigned srcany = 0;
+#pragma unroll
+        for (int m = 0; m < NB; ++m) { out[m] = 0; n2[m] = 0; }
+        const int ncand = nparents * NB;
+        for (int k0 = 0; k0 < ncand; k0 += 32) {
+            // (2) candidate k = (k / 2^d-th box of the merged parent list, Morton child k % 2^d)
+            const int k = k0 + lane;
+            const int j = k / NB;
+            int c = 0; bool fromcoll = false; unsigned mypadj = 0;
+            if (k < ncand) {
+                const int P = (j == pos) ? p : prow[j - (j > pos ? 1 : 0)];
+                fromcoll = (j != pos);
+                c = t.child(P, k % NB);
+                mypadj = padj[j];
+            }
+            T cc[DIM];
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) cc[a] = c ? t.centers[t.aligned * a + c] : (T)0;
+            const bool csrc = c && (t.flags[c] & BT_BOX_IS_SOURCE_BOX);
+            const unsigned exm = __ballot_sync(0xffffffffu, c != 0 && fromcoll);   // list-2 bits of far children
+            // children of p some candidate of this chunk can touch
+            unsigned touch = mypadj;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) touch |= __shfl_xor_sync(0xffffffffu, touch, o);
+#pragma unroll
+            for (int m = 0; m < NB; ++m) {
+                if (!((rowm >> m) & 1u)) continue;
+                const int b = __shfl_sync(0xffffffffu, bch, m);
+                unsigned bs;
+                if ((touch >> m) & 1u) {
+                    bool adj = false;
+                    if (c && c != b && ((mypadj >> m) & 1u))
+                        adj = adj_nbhd<T, DIM>(rad, bcen[m], level, nbhd, cc, level);
+                    const unsigned ba = __ballot_sync(0xffffffffu, adj);
+                    if (adj) {
+                        const int slot = out[m] + __popc(ba & ((1u << lane) - 1u));
+                        if (slot < stride) tmp[(int64_t)b * stride + slot] = c;
+                    }
+                    out[m] += __popc(ba);
+                    if (__ballot_sync(0xffffffffu, adj && csrc)) srcany |= 1u << m;
+                    bs = exm & ~ba;                 // candidates of colleagues that are not adjacent
+                } else bs = exm;
+                n2[m] += __popc(bs);
+                if (l2mask && lane == 0) l2mask[(int64_t)b * mask_words + (k0 >> 5)] = bs;
+            }
         }
-        if (lane == 0) {
-            counts[b] = out < stride ? out : stride;
-            if (l2cnt) l2cnt[b] = n2;
-            xflags[b] = xf;
+        // results of child m are written by lane m
+#pragma unroll
+        for (int m = 0; m < NB; ++m) {
+            if (lane == m && bch) {
+                const bool row = (rowm >> m) & 1u;
+                counts[bch] = row ? (out[m] < stride ? out[m] : stride) : 0;
+                if (l2cnt) l2cnt[bch] = row ? n2[m] : 0;
+                xflags[bch] = (unsigned char)(bxf | (((srcany >> m) & 1u) ? kXfCollSource : 0));
+                if (l2mask && row) l2mask[(int64_t)bch * mask_words + mask_words - 1] = (unsigned)pos;
+            }
         }
         __syncwarp();
     }
@@ -2445,7 +2473,8 @@ int bt_trav_colleagues(int dtype, int phase, const bt_tree_view* tree, const int
 {
     BT_PROF(phase ? "trav_colleagues_fill" : "trav_colleagues_count", (cudaStream_t)stream);
     if (list2_masks && mask_words < ((stride + 1) * (1 << tree->dim) + 31) / 32 + 1) return BT_ERR_BAD_ARG;
-    if (((stride + 1) * (1 << tree->dim) + 31) / 32 + 1 > bt::kCollMaskWordsMax) return BT_ERR_UNSUPPORTED;
+    if (((stride + 1) * (1 << tree->dim) + 31) / 32 + 1 > bt::kCollMaskWordsMax || stride + 1 > 128)
+        return BT_ERR_UNSUPPORTED;     // well_sep_is_n_away > 2 in 3-D: use the walk-based builder
     BT_DISPATCH(dtype, tree->dim, colleagues_topdown_impl, phase, tree, level_start_box_nrs, dfs_rank,
                 (const signed char*)row_mask, stride, staging, starts, lists, list2_count_by_box, xflags,
                 list2_masks, mask_words, (long long*)totals_dev, (cudaStream_t)stream);
