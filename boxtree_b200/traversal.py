@@ -435,6 +435,11 @@ class FMMTraversalBuilder:
 
             walk_mode = int(lib.bt_get_walk_mode())
             topdown = bool(walk_mode & WALK_MODE_COLL_TOPDOWN)
+            # the top-down builder keeps (2n+1)^d parent-level boxes per warp in shared memory
+            # (n <= 2 in 3-D); wider neighbourhoods use the reference's per-row walks
+            nparents_max = (2 * int(self.well_sep_is_n_away) + 1) ** dimensions
+            if nparents_max > 128 or (nparents_max * 2 ** dimensions + 31) // 32 + 1 > 40:
+                topdown = False
             coll_starts = actx.empty(nboxes + 1, np.int32)
             l2_count_by_box = xflags = None
             if topdown:

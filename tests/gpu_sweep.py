@@ -48,6 +48,9 @@ def make_cases(quick=False):
                               tree={"max_particles_in_box": 30}))
             cases.append(dict(base, name="uniform", uniform=True,
                               tree={"max_particles_in_box": 30}))
+            # n-away 3: beyond the top-down colleague builder's reach in 3-D (walk-based fallback)
+            cases.append(dict(base, name="nsep3", n=3000, tree={"max_particles_in_box": 30},
+                              trav={"well_sep_is_n_away": 3}))
             for nsep in (1, 2):
                 cases.append(dict(base, name=f"nsep{nsep}", tree={"max_particles_in_box": 30},
                                   trav={"well_sep_is_n_away": nsep}))
