@@ -489,8 +489,9 @@ class FMMTraversalBuilder:
                       "bt_reverse_index")
                 ws3.dfs_order = dfs_order
                 ws3.keys_only = True
-                if not (walk_mode & WALK_MODE_HEAVY_SORT):
-                    nroots_max = (2 * int(self.well_sep_is_n_away) + 1) ** dimensions
+                nroots_max = (2 * int(self.well_sep_is_n_away) + 1) ** dimensions
+                # positions inside one row's map are int32: rows can span nroots_max subtrees
+                if not (walk_mode & WALK_MODE_HEAVY_SORT) and nroots_max * nboxes < 2 ** 31 - 2048:
                     ws3.enable_map(subtree_size, nroots_max + 136)
             if fused13 and nboxes < (1 << 27) and nlevels + 2 <= 31:
                 stage_stride = int(os.environ.get("BT_STAGE_STRIDE", DEFAULT_STAGE_STRIDE))
