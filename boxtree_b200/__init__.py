@@ -16,10 +16,13 @@ from .array_context import TorchArrayContext, make_obj_array
 from .tree import Tree, TreeOfBoxes, box_flags_enum
 from .tree_build import MaxLevelsExceeded, TreeBuilder
 from .traversal import BuiltList, FMMTraversalBuilder, FMMTraversalInfo
+from .particle_filter import (FilteredTargetListsInTreeOrder, FilteredTargetListsInUserOrder,
+                              ParticleListFilter)
 
 __all__ = [
     "TorchArrayContext", "make_obj_array",
     "Tree", "TreeOfBoxes", "box_flags_enum",
     "TreeBuilder", "MaxLevelsExceeded",
     "FMMTraversalBuilder", "FMMTraversalInfo", "BuiltList",
+    "ParticleListFilter", "FilteredTargetListsInUserOrder", "FilteredTargetListsInTreeOrder",
 ]

@@ -244,6 +244,35 @@ def test_device_constant_one_fmm_matches_host(actx):
     assert np.array_equal(got, want.astype(np.int64)) and np.all(got == w.sum())
 
 
+@pytest.mark.parametrize("with_targets", [False, True])
+def test_particle_list_filter(actx, with_targets):
+    """ParticleListFilter (boxtree/tree.py:1040-1239) against the oracle's loops."""
+    from boxtree_b200 import ParticleListFilter
+    from oracle import particle_filter as opf
+    src = normal_particles(20000, 3, np.float64)
+    tkw = dict(max_particles_in_box=30)
+    if with_targets:
+        _, tgt, radii = config3_inputs(10, 15000)
+        tkw.update(targets=tgt, target_radii=radii, stick_out_factor=0.25, extent_norm="linf")
+    tree, _ = _build(actx, src, tkw, {})
+    ht = actx.to_numpy(tree)
+    flags = (np.random.default_rng(5).random(ht.ntargets) < 0.3).astype(np.int8)
+    plf = ParticleListFilter(actx)
+    got = actx.to_numpy(plf.filter_target_lists_in_user_order(actx, tree, actx.from_numpy(flags)))
+    n, starts, lists = opf.filter_target_lists_in_user_order(ht, flags)
+    assert got.nfiltered_targets == n == int(flags.sum())
+    assert np.array_equal(got.target_starts, starts) and got.target_starts.dtype == np.int32
+    assert np.array_equal(got.target_lists, lists) and got.target_lists.dtype == np.int32
+    got = actx.to_numpy(plf.filter_target_lists_in_tree_order(actx, tree, actx.from_numpy(flags)))
+    n, bstart, bcount, targets, ufi = opf.filter_target_lists_in_tree_order(ht, flags)
+    assert got.nfiltered_targets == n
+    assert np.array_equal(got.box_target_starts, bstart)
+    assert np.array_equal(got.box_target_counts_nonchild, bcount)
+    assert np.array_equal(got.unfiltered_from_filtered_target_indices, ufi)
+    for a, b in zip(got.targets, targets):
+        assert np.array_equal(a, b)
+
+
 def test_error_behaviour(actx):
     from boxtree_b200 import FMMTraversalBuilder, MaxLevelsExceeded, TreeBuilder
     tb = TreeBuilder(actx)

@@ -170,3 +170,29 @@ def test_golden_digests():
         trav = build_traversal(tree, **vkw)
         got = {k: digest(v) for k, v in flatten(tree, trav).items()}
         assert got == want[name], name
+
+
+def test_particle_list_filter_restatement():
+    """ParticleListFilter (boxtree/tree.py:1040-1239), the properties of test/test_tree.py's
+    filter tests: the filtered lists hold exactly the flagged targets, box by box."""
+    from oracle import particle_filter as opf
+    src = normal_particles(5000, 3, np.float64, seed=12)
+    tgt = normal_particles(4000, 3, np.float64, seed=19)
+    tree = build_tree(src, targets=tgt, max_particles_in_box=30)
+    flags = (np.random.default_rng(5).random(4000) < 0.3).astype(np.int8)
+    n, starts, lists = opf.filter_target_lists_in_user_order(tree, flags)
+    assert n == flags.sum() and sorted(lists) == sorted(np.nonzero(flags)[0])
+    user_target_ids = np.empty(4000, np.int64)
+    user_target_ids[tree.sorted_target_ids] = np.arange(4000)
+    for ibox in range(tree.nboxes):
+        s, c = tree.box_target_starts[ibox], tree.box_target_counts_nonchild[ibox]
+        want = [u for u in user_target_ids[s:s + c] if flags[u]]
+        assert list(lists[starts[ibox]:starts[ibox + 1]]) == want
+    n2, bstart, bcount, ftargets, ufi = opf.filter_target_lists_in_tree_order(tree, flags)
+    assert n2 == n and bcount.sum() == n
+    for ibox in range(tree.nboxes):
+        s, c = tree.box_target_starts[ibox], tree.box_target_counts_nonchild[ibox]
+        mine = [j for j in range(s, s + c) if flags[user_target_ids[j]]]
+        assert list(ufi[bstart[ibox]:bstart[ibox] + bcount[ibox]]) == mine
+    for ax in range(3):
+        assert np.array_equal(ftargets[ax], tree.targets[ax][ufi])
