@@ -77,7 +77,7 @@ class bt_heavy_ws(C.Structure):
                 ("row_mask", vp), ("stage", vp), ("stage_cap", C.c_int32), ("stage_count", vp),
                 ("dfs_order", vp), ("subtree_size", vp), ("hrow_base", vp), ("hplan", vp),
                 ("seg_stride", C.c_int32), ("hseg_rank", vp), ("hseg_prefix", vp), ("hseg_kind", vp),
-                ("hseg_n", vp), ("hmap", vp), ("hmap_cap", C.c_int64), ("chunk_cnt", vp)]
+                ("hseg_n", vp), ("hmap", vp), ("hmap_cap", C.c_int64), ("chunk_cnt", vp), ("hctx", vp)]
 
 
 HCTL_NWALK = 3

@@ -892,7 +892,7 @@ struct HeavyWs {
     // fused walk, map mode (heavy rows without a sort), see "heavy rows by position map" below
     const int* subtree_size; long long* hrow_base; long long* hplan; int seg_stride;
     int* hseg_rank; int* hseg_prefix; unsigned char* hseg_kind; int* hseg_n;
-    unsigned char* hmap; long long hmap_cap; int* chunk_cnt;
+    unsigned char* hmap; long long hmap_cap; int* chunk_cnt; void* hctx;
 };
 constexpr int kHctlNHeavy = 0, kHctlOverflow = 1, kHctlECount = 2, kHctlNWalk = 3, kHctlFrontier = 8;
 // row states left by the count pass of the fused walk (row_heavy[]): 0 = the fill pass walks
@@ -914,7 +914,7 @@ static HeavyWs make_ws(const bt_heavy_ws* w)
     h.subtree_size = w->subtree_size; h.hrow_base = (long long*)w->hrow_base; h.hplan = (long long*)w->hplan;
     h.seg_stride = w->seg_stride; h.hseg_rank = w->hseg_rank; h.hseg_prefix = w->hseg_prefix;
     h.hseg_kind = w->hseg_kind; h.hseg_n = w->hseg_n; h.hmap = w->hmap; h.hmap_cap = w->hmap_cap;
-    h.chunk_cnt = w->chunk_cnt;
+    h.chunk_cnt = w->chunk_cnt; h.hctx = w->hctx;
     return h;
 }
 
@@ -2010,6 +2010,9 @@ heavy_map_plan_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, const unsigned ch
             pre += skind[k] ? 1 : ws.subtree_size[ws.dfs_order[srank[k]]];
         }
         ws.hseg_n[h] = ns;
+        // the row's walk constants, read by every child visit of the expansion
+        static_assert(sizeof(L3Ctx<T, DIM>) <= 128, "bt_heavy_ws.hctx holds 128 bytes per heavy row");
+        l3_make_ctx<T, DIM>(t, rad, x, box, reinterpret_cast<L3Ctx<T, DIM>*>(ws.hctx)[h]);
     }
 }
 
@@ -2082,7 +2085,7 @@ heavy_map_step_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, int step, HeavyWs
             h = (int)(item >> 32);
             nearok = item & 0x80000000ull;
             const int parent = (int)(item & 0x7fffffffull), m = (int)(tid % NB);
-            L3Ctx<T, DIM> c; l3_make_ctx<T, DIM>(t, rad, x, x.target_boxes[ws.heavy_rows[h]], c);
+            const L3Ctx<T, DIM> c = reinterpret_cast<const L3Ctx<T, DIM>*>(ws.hctx)[h];
             wb = t.child(parent, m);
             act = list3_visit<T, DIM>(t, rad, x, c, wb);
             if (!nearok) act &= ~kVisitNear;
@@ -2130,7 +2133,8 @@ heavy_map_hist_kernel(int nslots, HeavyWs ws)
     }
 }
 
-// per heavy row: chunk counts -> exclusive offsets inside the row; row totals -> G (one warp per row)
+// per heavy row: chunk counts -> exclusive offsets inside the row; row totals -> G.  One warp per
+// row, 32 chunks per step (lane = chunk), one warp scan per slot.
 __global__ void __launch_bounds__(256)
 heavy_map_rowscan_kernel(int nslots, int64_t rowlen, int* __restrict__ G, HeavyWs ws)
 {
@@ -2140,14 +2144,21 @@ heavy_map_rowscan_kernel(int nslots, int64_t rowlen, int* __restrict__ G, HeavyW
     for (int h = w; h < nheavy; h += nw) {
         const long long c0 = ws.hrow_base[h] / kMapChunk, c1 = ws.hrow_base[h + 1] / kMapChunk;
         const int r = ws.heavy_rows[h];
-        for (int sl = lane; sl < nslots; sl += 32) {
-            int run = 0;
-            for (long long c = c0; c < c1; ++c) {
-                const int v = ws.chunk_cnt[c * nslots + sl];
-                ws.chunk_cnt[c * nslots + sl] = run;
-                run += v;
+        for (int sl = 0; sl < nslots; ++sl) {
+            int carry = 0;
+            for (long long cb = c0; cb < c1; cb += 32) {
+                const long long c = cb + lane;
+                const int v = (c < c1) ? ws.chunk_cnt[c * nslots + sl] : 0;
+                int inc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int y = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += y;
+                }
+                if (c < c1) ws.chunk_cnt[c * nslots + sl] = carry + inc - v;
+                carry += __shfl_sync(0xffffffffu, inc, 31);
             }
-            G[sl * rowlen + r] = run;
+            if (lane == 0) G[sl * rowlen + r] = carry;
         }
     }
 }

@@ -698,7 +698,7 @@ box_info_kernel(int nboxes, int sources_are_targets, int have_ext,
 // as the reference's serial loop (:1345-1368).  Four boxes per warp (8 lanes each: a leaf
 // holds at most a few dozen particles); a box with many own particles (upper-level boxes of
 // a tree with extents) is taken by the whole warp.
-constexpr int kExtGroup = 8, kExtBig = 128, kExtHuge = 2048;
+constexpr int kExtGroup = 8, kExtBig = 64, kExtHuge = 256;
 
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256)

@@ -63,7 +63,7 @@ class _HeavyWorkspace:
         self.subtree_size = self.hrow_base = self.hplan = None
         self.seg_stride = 0
         self.hseg_rank = self.hseg_prefix = self.hseg_kind = self.hseg_n = None
-        self.hmap = self.chunk_cnt = None
+        self.hmap = self.chunk_cnt = self.hctx = None
         self.hmap_cap = 0
         self._alloc_frontier(max(nrows, 8 * nboxes, 1 << 16))
 
@@ -80,6 +80,7 @@ class _HeavyWorkspace:
         self.hseg_prefix = self.actx.empty(n, np.int32)
         self.hseg_kind = self.actx.empty(n, np.uint8)
         self.hseg_n = self.actx.empty(max(nheavy, 1), np.int32)
+        self.hctx = self.actx.empty(max(nheavy, 1) * 16, np.float64)     # 128 bytes per row
         self.hmap_cap = int(map_bytes)
         self.hmap = self.actx.empty(max(self.hmap_cap, 1), np.uint8)
         self.chunk_cnt = self.actx.empty(max(self.hmap_cap // 1024, 1) * nslots, np.int32)
@@ -132,6 +133,7 @@ class _HeavyWorkspace:
         w.hmap = dptr(self.hmap)
         w.hmap_cap = self.hmap_cap
         w.chunk_cnt = dptr(self.chunk_cnt)
+        w.hctx = dptr(self.hctx)
         w.ecap = self.ecap
         w.row_mask = dptr(self.row_mask)
         w.stage = dptr(self.stage)

@@ -316,6 +316,7 @@ typedef struct {
     uint8_t *hmap;
     int64_t hmap_cap;
     int32_t *chunk_cnt;
+    void *hctx;                  /* [nheavy * 128 bytes]: per-row walk constants */
 } bt_heavy_ws;
 
 /* pre-order (depth first, children in Morton order) rank of every box */
