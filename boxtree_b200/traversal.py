@@ -350,11 +350,31 @@ class FMMTraversalBuilder:
             box_parent_ids = dev(dev_tree.box_parent_ids)
             box_centers = dev(dev_tree.box_centers)
             box_child_ids = dev(dev_tree.box_child_ids)
+            # a TreeOfBoxes made by boxtree/tree_of_boxes.py carries int32 levels, -1 as the
+            # parent of the root (its kernels then index starts[-1]: here the root is its own
+            # parent, as in a Tree), IS_LEAF_BOX flags and no level starts
+            if box_levels.dtype != torch.uint8:
+                box_levels = box_levels.to(torch.uint8)
+            if box_flags.dtype != torch.uint8:
+                box_flags = box_flags.to(torch.uint8)
+            if box_parent_ids.dtype != torch.int32:
+                box_parent_ids = box_parent_ids.to(torch.int32)
+            if box_child_ids.dtype != torch.int32:
+                box_child_ids = box_child_ids.to(torch.int32)
+            if isinstance(tree, TreeOfBoxes):
+                box_parent_ids = torch.where(
+                    box_parent_ids < 0,
+                    torch.arange(nboxes, dtype=torch.int32, device=box_parent_ids.device),
+                    box_parent_ids)
             if dev_tree.level_start_box_nrs is None:
-                raise ValueError("tree.level_start_box_nrs is required")
-            level_start_box_nrs = dev(dev_tree.level_start_box_nrs, np.int32)
-            if level_start_box_nrs.dtype != torch.int32:
-                level_start_box_nrs = level_start_box_nrs.to(torch.int32)
+                level_start_box_nrs = torch.searchsorted(
+                    box_levels.to(torch.int32).contiguous(),
+                    torch.arange(nlevels + 1, dtype=torch.int32, device=box_levels.device)
+                ).to(torch.int32)
+            else:
+                level_start_box_nrs = dev(dev_tree.level_start_box_nrs, np.int32)
+                if level_start_box_nrs.dtype != torch.int32:
+                    level_start_box_nrs = level_start_box_nrs.to(torch.int32)
 
             tv = bt_tree_view()
             tv.dim = dimensions
