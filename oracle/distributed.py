@@ -1,6 +1,8 @@
 """CPU oracle for the distributed setup rows.
 
-TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED (the reference cannot run here).
+TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED for the device rows (the reference's kernels cannot
+run here); ``get_box_ids_dfs_order`` / ``partition_work`` are pinned against the reference's
+own host code executed in place (``tests/test_reference_consumer.py``).
 numpy restatement of
 * ``boxtree/distributed/partition.py:38-121`` (``get_box_ids_dfs_order``,
   ``partition_work`` without the MPI Scatter: all segments are returned),

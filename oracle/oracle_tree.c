@@ -6,9 +6,12 @@
  * in __graft_entry__.py and the cpu_baseline / --impl reference legs of
  * bench.py use it, and only as the checker / the timed CPU baseline.
  *
- * PARITY UNPINNED: the reference (inducer/boxtree) cannot be executed in this
- * image (no pyopencl / OpenCL ICD / mako) and its test-suite holds no golden
- * vectors for this path.  This file restates, kernel by kernel, the OpenCL
+ * PARITY UNPINNED (bit level): the reference's PyOpenCL path cannot be executed in
+ * this image (no pyopencl / OpenCL ICD / mako) and its test-suite holds no golden
+ * vectors for this path.  What is pinned by reference code run in place
+ * (tests/test_reference_consumer.py, tests/test_tree_of_boxes.py): the meaning of
+ * every list through the reference's own drive_fmm + ConstantOneExpansionWrangler,
+ * TreeOfBoxes inputs made by the reference's tree_of_boxes.py with known answers.  This file restates, kernel by kernel, the OpenCL
  * kernels the reference generates; every function cites the reference
  * file:line it follows (paths relative to /root/reference/).
  *

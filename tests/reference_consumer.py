@@ -53,3 +53,47 @@ def load():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def load_partition():
+    """``get_box_ids_dfs_order`` and ``partition_work`` of the reference's
+    ``boxtree/distributed/partition.py:38-121`` (pure Python host loops).  The module's other
+    imports (mako, arraycontext, pyopencl: only used by the device code further down) are
+    satisfied with empty stand-ins."""
+    names = ("boxtree", "boxtree.distributed", "boxtree.distributed.partition", "mako",
+             "mako.template", "arraycontext", "pyopencl", "pyopencl.elementwise",
+             "pyopencl.tools", "pytools")
+    saved = {k: sys.modules.get(k) for k in names}
+    try:
+        pkg = types.ModuleType("boxtree")
+        pkg.__path__ = [os.path.join(REFERENCE_ROOT, "boxtree")]
+        sys.modules["boxtree"] = pkg
+        dpkg = types.ModuleType("boxtree.distributed")
+        dpkg.__path__ = [os.path.join(REFERENCE_ROOT, "boxtree", "distributed")]
+        sys.modules["boxtree.distributed"] = dpkg
+
+        def stub(name, **attrs):
+            try:
+                importlib.import_module(name)
+            except ImportError:
+                m = types.ModuleType(name)
+                for k, v in attrs.items():
+                    setattr(m, k, v)
+                sys.modules[name] = m
+        stub("mako")
+        stub("mako.template", Template=object)
+        stub("arraycontext", Array=object, ArrayContext=object, PyOpenCLArrayContext=object)
+        stub("pyopencl")
+        stub("pyopencl.elementwise", ElementwiseKernel=object)
+        stub("pyopencl.tools", dtype_to_ctype=lambda dt: str(dt))
+        stub("pytools", memoize_method=lambda f: f, ProcessLogger=object)
+        sys.modules.pop("boxtree.distributed.partition", None)
+        mod = importlib.import_module("boxtree.distributed.partition")
+        assert mod.__file__.startswith(REFERENCE_ROOT)
+        return mod.get_box_ids_dfs_order, mod.partition_work
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v

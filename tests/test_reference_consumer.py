@@ -67,3 +67,45 @@ def test_reference_drive_fmm_on_oracle_lists(name):
         merged = merge_close_lists(trav)
         pot2 = drive_fmm(None, Wrangler(TreeIndep(), merged), (weights,))
         assert np.all(pot2 == weights.sum())
+
+
+class _ScatterComm:
+    """mpi4py-style communicator for one emulated rank; the root's send buffer is shared."""
+
+    def __init__(self, rank, size, shared):
+        self.rank, self.size, self.shared = rank, size, shared
+
+    def Get_rank(self):  # noqa: N802
+        return self.rank
+
+    def Get_size(self):  # noqa: N802
+        return self.size
+
+    def Scatter(self, sendbuf, recvbuf, root=0):  # noqa: N802
+        if self.rank == root:
+            self.shared["segments"] = np.array(sendbuf, copy=True)
+        recvbuf[:] = self.shared["segments"][self.rank]
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3, 5, 8])
+@pytest.mark.parametrize("dims", [2, 3])
+def test_reference_partition_work_matches_oracle(dims, nranks):
+    """Row c1: the reference's own ``get_box_ids_dfs_order`` / ``partition_work``
+    (``boxtree/distributed/partition.py:38-121``, executed in place) against the oracle's
+    restatement, with integer and with fractional costs."""
+    from types import SimpleNamespace
+    from oracle import distributed as od
+    ref_dfs, ref_partition = rc.load_partition()
+    src = normal_particles(6000, dims, np.float64, seed=12)
+    tree = build_tree(src, max_particles_in_box=20)
+    assert np.array_equal(ref_dfs(tree), od.get_box_ids_dfs_order(tree))
+    nb = tree.nboxes
+    rng = np.random.default_rng(4)
+    for cost in ((1.0 + tree.box_source_counts_nonchild[:nb]).astype(np.float64),
+                 rng.random(nb) * 3.0 + 0.01):
+        want, _ = od.partition_work(cost, tree, nranks)
+        shared = {}
+        trav = SimpleNamespace(tree=tree)
+        for r in range(nranks):
+            got = ref_partition(cost if r == 0 else None, trav, _ScatterComm(r, nranks, shared))
+            assert np.array_equal(got, want[r]), (r, nranks)
