@@ -18,6 +18,7 @@ from .tree_build import MaxLevelsExceeded, TreeBuilder
 from .traversal import BuiltList, FMMTraversalBuilder, FMMTraversalInfo
 from .particle_filter import (FilteredTargetListsInTreeOrder, FilteredTargetListsInUserOrder,
                               ParticleListFilter)
+from .point_sources import TreeWithLinkedPointSources, link_point_sources
 
 __all__ = [
     "TorchArrayContext", "make_obj_array",
@@ -25,4 +26,5 @@ __all__ = [
     "TreeBuilder", "MaxLevelsExceeded",
     "FMMTraversalBuilder", "FMMTraversalInfo", "BuiltList",
     "ParticleListFilter", "FilteredTargetListsInUserOrder", "FilteredTargetListsInTreeOrder",
+    "TreeWithLinkedPointSources", "link_point_sources",
 ]

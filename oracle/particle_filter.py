@@ -44,3 +44,43 @@ def filter_target_lists_in_tree_order(tree, flags):
             bcount[i] = fpl - fs
     targets = [np.asarray(t)[unfiltered_from_filtered] for t in tree.targets]
     return nfiltered, bstart, bcount, targets, unfiltered_from_filtered
+
+
+def link_point_sources(tree, point_source_starts, point_sources):
+    """``/root/reference/boxtree/tree.py:773-955`` with the kernels of
+    ``boxtree/tree_build_kernels.py:1872-1950`` as plain loops (every source owns >= 1 point)."""
+    nsources, nboxes = tree.nsources, tree.nboxes
+    pss = np.asarray(point_source_starts, np.int64)
+    usi = tree.user_source_ids
+    tos = np.zeros(nsources, np.int32)
+    toc = np.zeros(nsources, np.int32)
+    run = 0
+    for i in range(nsources):                                    # SOURCE_SCAN_TPL
+        c = int(pss[usi[i] + 1] - pss[usi[i]])
+        tos[i], toc[i] = run, c
+        run += c
+    npoint = run
+    ids = np.ones(npoint, np.int32)                              # tree.py:838-890
+    bnd = np.zeros(npoint, np.int8)
+    for i in range(nsources):
+        ids[tos[i]] = pss[usi[i]]
+        bnd[tos[i]] = 1
+    for j in range(1, npoint):                                   # segmented inclusive scan
+        if not bnd[j]:
+            ids[j] = ids[j - 1] + ids[j]
+    pts = [np.asarray(p)[ids] for p in point_sources]
+    bstart = np.zeros(nboxes, np.int32)
+    bnon = np.zeros(nboxes, np.int32)
+    bcum = np.zeros(nboxes, np.int32)
+    for ibox in range(nboxes):                                   # BOX_POINT_SOURCES
+        s_start = int(tree.box_source_starts[ibox])
+        ps_start = int(tos[s_start]) if s_start < nsources else npoint
+        bstart[ibox] = ps_start
+        for out, cnt in ((bnon, tree.box_source_counts_nonchild), (bcum, tree.box_source_counts_cumul)):
+            s_count = int(cnt[ibox])
+            if s_count:
+                last = s_start + s_count - 1
+                out[ibox] = tos[last] + toc[last] - ps_start
+    return dict(npoint_sources=npoint, point_source_starts=tos, point_source_counts=toc,
+                point_sources=pts, user_point_source_ids=ids, box_point_source_starts=bstart,
+                box_point_source_counts_nonchild=bnon, box_point_source_counts_cumul=bcum)

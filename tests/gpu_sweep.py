@@ -48,6 +48,9 @@ def make_cases(quick=False):
                               tree={"max_particles_in_box": 30}))
             cases.append(dict(base, name="uniform", uniform=True,
                               tree={"max_particles_in_box": 30}))
+            # user-supplied (square, covering) bounding box, tree_build.py:477-508
+            cases.append(dict(base, name="user-bbox", user_bbox=(-7.5, 8.5),
+                              tree={"max_particles_in_box": 30}))
             # n-away 3: beyond the top-down colleague builder's reach in 3-D (walk-based fallback)
             cases.append(dict(base, name="nsep3", n=3000, tree={"max_particles_in_box": 30},
                               trav={"well_sep_is_n_away": 3}))
@@ -92,6 +95,9 @@ def make_inputs(case):
     else:
         src = normal_particles(n, dims, dt, seed=15)
     kw = dict(case["tree"])
+    if case.get("user_bbox"):
+        lo, hi = case["user_bbox"]
+        kw["bbox"] = np.array([[lo, hi]] * dims, dtype=dt)
     tgt = None
     if case.get("ntargets"):
         tgt = normal_particles(case["ntargets"], dims, dt, seed=18)
@@ -116,7 +122,8 @@ def run_case(case, actx, tb, travs):
     except OracleMaxLevels as e:
         ref_tree, ref_err = None, e
 
-    dev_kw = {k: (actx.from_numpy(v) if isinstance(v, np.ndarray) else
+    dev_kw = {k: (v if k == "bbox" else              # the bounding box stays a host array
+                  actx.from_numpy(v) if isinstance(v, np.ndarray) else
                   [actx.from_numpy(x) for x in v] if k == "targets" else v)
               for k, v in kw.items()}
     try:

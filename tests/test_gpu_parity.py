@@ -98,6 +98,14 @@ def test_parity_all_walk_mappings(actx, builders, case, mode):
     assert not bad, bad[:10]
 
 
+def _build_tree_only(actx, src, tkw):
+    from boxtree_b200 import TreeBuilder
+    dkw = {k: (actx.from_numpy(v) if isinstance(v, np.ndarray) else
+               [actx.from_numpy(x) for x in v] if k == "targets" else v) for k, v in tkw.items()}
+    tree, _ = TreeBuilder(actx)(actx, [actx.from_numpy(s) for s in src], **dkw)
+    return tree
+
+
 def _build(actx, src, tkw, vkw):
     from boxtree_b200 import FMMTraversalBuilder, TreeBuilder
     dkw = {k: (actx.from_numpy(v) if isinstance(v, np.ndarray) else
@@ -271,6 +279,39 @@ def test_particle_list_filter(actx, with_targets):
     assert np.array_equal(got.unfiltered_from_filtered_target_indices, ufi)
     for a, b in zip(got.targets, targets):
         assert np.array_equal(a, b)
+
+
+def test_link_point_sources(actx):
+    """link_point_sources (boxtree/tree.py:773-955) against the oracle's loops."""
+    from boxtree_b200 import link_point_sources
+    from oracle import particle_filter as opf
+    ns = 6000
+    src = normal_particles(ns, 3, np.float64)
+    rng = np.random.default_rng(7)
+    radii = 0.05 * 2 ** rng.uniform(-10, 0, ns)
+    tgt = normal_particles(4000, 3, np.float64, seed=19)
+    tree = _build_tree_only(actx, src, dict(max_particles_in_box=30, targets=tgt, source_radii=radii,
+                                            stick_out_factor=0.25, extent_norm="linf"))
+    counts = rng.integers(1, 5, ns)
+    starts = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    npts = int(starts[-1])
+    owner = np.repeat(np.arange(ns), counts)
+    pts = [src[a][owner] + radii[owner] * rng.uniform(-1, 1, npts) for a in range(3)]
+    got = actx.to_numpy(link_point_sources(actx, tree, actx.from_numpy(starts),
+                                           [actx.from_numpy(p) for p in pts]))
+    want = opf.link_point_sources(actx.to_numpy(tree), starts, pts)
+    assert got.npoint_sources == want["npoint_sources"] == npts
+    for k in ("point_source_starts", "point_source_counts", "user_point_source_ids",
+              "box_point_source_starts", "box_point_source_counts_nonchild",
+              "box_point_source_counts_cumul"):
+        a, b = np.asarray(getattr(got, k)), want[k]
+        assert a.dtype == b.dtype and np.array_equal(a, b), k
+    for a, b in zip(got.point_sources, want["point_sources"]):
+        assert np.array_equal(a, b)
+    assert int(np.asarray(got.box_point_source_counts_cumul)[0]) == npts
+    t2 = _build_tree_only(actx, src, dict(max_particles_in_box=30))
+    with pytest.raises(ValueError):
+        link_point_sources(actx, t2, actx.from_numpy(starts), [actx.from_numpy(p) for p in pts])
 
 
 def test_error_behaviour(actx):

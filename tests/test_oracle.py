@@ -196,3 +196,30 @@ def test_particle_list_filter_restatement():
         assert list(ufi[bstart[ibox]:bstart[ibox] + bcount[ibox]]) == mine
     for ax in range(3):
         assert np.array_equal(ftargets[ax], tree.targets[ax][ufi])
+
+
+def test_link_point_sources_restatement():
+    """link_point_sources (boxtree/tree.py:773-955): every box's point sources are contiguous
+    and are exactly those owned by the box's sources (test/test_tree.py's point-source test)."""
+    from oracle import particle_filter as opf
+    ns = 3000
+    src = normal_particles(ns, 3, np.float64)
+    tgt = normal_particles(2000, 3, np.float64, seed=19)
+    rng = np.random.default_rng(7)
+    radii = 0.05 * 2 ** rng.uniform(-10, 0, ns)
+    tree = build_tree(src, targets=tgt, max_particles_in_box=30, source_radii=radii,
+                      stick_out_factor=0.25, extent_norm="linf")
+    counts = rng.integers(1, 5, ns)
+    starts = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    owner = np.repeat(np.arange(ns), counts)
+    pts = [src[a][owner] for a in range(3)]
+    w = opf.link_point_sources(tree, starts, pts)
+    assert w["npoint_sources"] == starts[-1]
+    assert sorted(w["user_point_source_ids"]) == list(range(starts[-1]))
+    assert w["box_point_source_counts_cumul"][0] == starts[-1]
+    for b in range(tree.nboxes):
+        s, c = tree.box_source_starts[b], tree.box_source_counts_nonchild[b]
+        ps, pc = w["box_point_source_starts"][b], w["box_point_source_counts_nonchild"][b]
+        assert set(owner[w["user_point_source_ids"][ps:ps + pc]]) == set(tree.user_source_ids[s:s + c])
+    for a in range(3):
+        assert np.array_equal(w["point_sources"][a], pts[a][w["user_point_source_ids"]])
