@@ -19,6 +19,7 @@ from .traversal import BuiltList, FMMTraversalBuilder, FMMTraversalInfo
 from .particle_filter import (FilteredTargetListsInTreeOrder, FilteredTargetListsInUserOrder,
                               ParticleListFilter)
 from .point_sources import TreeWithLinkedPointSources, link_point_sources
+from .area_query import PeerListFinder, PeerListLookup
 
 __all__ = [
     "TorchArrayContext", "make_obj_array",
@@ -27,4 +28,5 @@ __all__ = [
     "FMMTraversalBuilder", "FMMTraversalInfo", "BuiltList",
     "ParticleListFilter", "FilteredTargetListsInUserOrder", "FilteredTargetListsInTreeOrder",
     "TreeWithLinkedPointSources", "link_point_sources",
+    "PeerListFinder", "PeerListLookup",
 ]

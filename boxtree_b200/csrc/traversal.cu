@@ -656,7 +656,44 @@ __device__ __forceinline__ void gen_list4(const TreeView<T, DIM>& t, const T* ra
     }
 }
 
-// generic row kernel; KIND: 0 colleagues, 2 list2, 4 list4 (list 1 and 3 have their own)
+// ---- N3 peer lists: area_query.py:393-475 (PEER_LIST_FINDER_TEMPLATE) ---------
+// b_k is a peer of b_j if it is adjacent to b_j, at least as large, and none of its children
+// satisfies both (the reference's level-restriction test reads these lists).
+template <typename T, int DIM, class E>
+__device__ __forceinline__ void gen_peers(const TreeView<T, DIM>& t, const T* rad, int box_id, E& e)
+{
+    constexpr int NB = 1 << DIM;
+    if (box_id == 0) { e.e0(0); return; }          // peer of root = self
+    T center[DIM]; t.center(box_id, center);
+    const int level = t.levels[box_id];
+    Walk w; w.init(0);
+    while (w.cont) {
+        const int wb = t.child(w.parent, w.mnr);
+        if (wb) {
+            T wc[DIM]; t.center(wb, wc);
+            // wb lives on level ssize + 1
+            if (adj_nbhd<T, DIM>(rad, center, level, (T)1, wc, w.ssize + 1)) {
+                if (w.ssize + 1 == level) e.e0(wb);
+                else if (!(t.flags[wb] & (BT_BOX_HAS_SOURCE_CHILD_BOXES | BT_BOX_HAS_TARGET_CHILD_BOXES))) e.e0(wb);
+                else {
+                    bool must_be_peer = true;
+                    for (int m = 0; must_be_peer && m < NB; ++m) {
+                        const int c = t.child(wb, m);
+                        if (c) {
+                            T cc[DIM]; t.center(c, cc);
+                            must_be_peer = must_be_peer && !adj_nbhd<T, DIM>(rad, center, level, (T)1, cc, w.ssize + 2);
+                        }
+                    }
+                    if (must_be_peer) e.e0(wb);
+                    else { w.push(wb); continue; }
+                }
+            }
+        }
+        w.template advance<NB>();
+    }
+}
+
+// generic row kernel; KIND: 0 colleagues, 2 list2, 4 list4, 5 peers (list 1 and 3 have their own)
 template <typename T, int DIM, int KIND, bool FILL>
 __global__ void __launch_bounds__(kTravBlock)
 list_kernel(TreeView<T, DIM> t, const int* __restrict__ row_boxes, const int* __restrict__ coll_starts,
@@ -678,11 +715,13 @@ list_kernel(TreeView<T, DIM> t, const int* __restrict__ row_boxes, const int* __
             if (KIND == 0) gen_colleagues<T, DIM>(t, rad, box, e);
             if (KIND == 2) gen_list2<T, DIM>(t, rad, coll_starts, coll_lists, box, e);
             if (KIND == 4) gen_list4<T, DIM>(t, rad, coll_starts, coll_lists, with_extent, stick_out_factor, box, e);
+            if (KIND == 5) gen_peers<T, DIM>(t, rad, box, e);
         } else {
             CountEmit e;
             if (KIND == 0) gen_colleagues<T, DIM>(t, rad, box, e);
             if (KIND == 2) gen_list2<T, DIM>(t, rad, coll_starts, coll_lists, box, e);
             if (KIND == 4) gen_list4<T, DIM>(t, rad, coll_starts, coll_lists, with_extent, stick_out_factor, box, e);
+            if (KIND == 5) gen_peers<T, DIM>(t, rad, box, e);
             starts[r] = e.c0;
             if (close_starts) close_starts[r] = e.c1;
         }
@@ -731,6 +770,7 @@ static int build_list_impl(int kind, int phase, const bt_tree_view* tv, const bt
                 else BT_LAUNCH_LIST(2, false);
                 break;
             case 4: BT_LAUNCH_LIST(4, false); break;
+            case 5: BT_LAUNCH_LIST(5, false); break;
             default: return BT_ERR_BAD_ARG;
             }
         } else {
@@ -744,6 +784,7 @@ static int build_list_impl(int kind, int phase, const bt_tree_view* tv, const bt
                 else BT_LAUNCH_LIST(2, true);
                 break;
             case 4: BT_LAUNCH_LIST(4, true); break;
+            case 5: BT_LAUNCH_LIST(5, true); break;
             default: return BT_ERR_BAD_ARG;
             }
         }
@@ -2540,10 +2581,10 @@ int bt_trav_build_list(int dtype, int kind, int phase, const bt_tree_view* tree,
                        int nrows, int32_t* starts, int32_t* lists, int32_t* close_starts,
                        int32_t* close_lists, int64_t* totals_dev, void* stream)
 {
-    static const char* const kNames[2][5] = {
-        {"trav_colleagues_count", "?", "trav_list2_count", "?", "trav_list4_count"},
-        {"trav_colleagues_fill", "?", "trav_list2_fill", "?", "trav_list4_fill"}};
-    BT_PROF(kNames[phase ? 1 : 0][(kind >= 0 && kind <= 4) ? kind : 3], (cudaStream_t)stream);
+    static const char* const kNames[2][6] = {
+        {"trav_colleagues_count", "?", "trav_list2_count", "?", "trav_list4_count", "peer_lists_count"},
+        {"trav_colleagues_fill", "?", "trav_list2_fill", "?", "trav_list4_fill", "peer_lists_fill"}};
+    BT_PROF(kNames[phase ? 1 : 0][(kind >= 0 && kind <= 5) ? kind : 3], (cudaStream_t)stream);
     BT_DISPATCH(dtype, tree->dim, build_list_impl, kind, phase, tree, args, nrows, starts, lists,
                 close_starts, close_lists, (long long*)totals_dev, (cudaStream_t)stream);
 }

@@ -222,6 +222,7 @@ int bt_trav_level_starts(int nlevels, const int32_t *level_start_box_nrs, const 
  * kind: 0 same_level_non_well_sep_boxes (traversal.py:398-464)
  *       2 from_sep_siblings / list 2     (:556-601)
  *       4 from_sep_bigger / list 4 (+close) (:931-1146)
+ *       5 peer lists of all boxes (area_query.py:393-475, PeerListFinder)
  * phase 0 writes per-row counts then turns them into starts[nrows+1] in place and
  * stores the total at totals_dev[0] (and [1] for the close list), int64; phase 1 fills. */
 typedef struct {

@@ -207,6 +207,42 @@ static void gen_colleagues(const tree_view_t *t, emitter_t *e, box_id_t box_id)
     }
 }
 
+/* N3: peer lists -- area_query.py:393-475 (PEER_LIST_FINDER_TEMPLATE) */
+static void gen_peers(const tree_view_t *t, emitter_t *e, box_id_t box_id)
+{
+    const int nb = 1 << t->d;
+    coord_t center[MAXDIM]; load_center(t, box_id, center);
+    if (box_id == 0) { emit(e, 0, box_id); return; }           /* peer of root = self */
+    int level = t->box_levels[box_id];
+    walk_t w; walk_init(&w, 0);
+    while (w.cont) {
+        box_id_t wb = walk_box(t, &w);
+        if (wb) {
+            coord_t wc[MAXDIM]; load_center(t, wb, wc);
+            /* walk box lives on level stack_size + 1 */
+            int a_or_o = adj(t->d, t->root_extent, center, level, wc, w.stack_size + 1);
+            if (a_or_o) {
+                if (w.stack_size + 1 == level) emit(e, 0, wb);
+                else if (!(t->box_flags[wb] & (BOX_HAS_SOURCE_CHILD_BOXES | BOX_HAS_TARGET_CHILD_BOXES)))
+                    emit(e, 0, wb);
+                else {
+                    int must_be_peer = 1;
+                    for (int m = 0; must_be_peer && m < nb; ++m) {
+                        box_id_t c = t->box_child_ids[m * t->aligned_nboxes + wb];
+                        if (c) {
+                            coord_t cc[MAXDIM]; load_center(t, c, cc);
+                            must_be_peer &= !adj(t->d, t->root_extent, center, level, cc, w.stack_size + 2);
+                        }
+                    }
+                    if (must_be_peer) emit(e, 0, wb);
+                    else { walk_push(&w, wb); continue; }
+                }
+            }
+        }
+        walk_advance(&w, nb);
+    }
+}
+
 /* b4: neighbor_source_boxes (list 1) -- traversal.py:470-550 */
 typedef struct { const box_id_t *target_boxes; } list1_args_t;
 static void gen_list1(const tree_view_t *t, emitter_t *e, const list1_args_t *x, box_id_t target_box_number)
@@ -438,6 +474,7 @@ void orc_build_lists(int kind, const trav_args_t *A, int64_t nrows, int write,
         case 2: gen_list2(&A->tree, &e, &A->l2, (box_id_t)r); break;
         case 3: gen_list3(&A->tree, &e, &A->l3, (box_id_t)r); break;
         case 4: gen_list4(&A->tree, &e, &A->l4, (box_id_t)r); break;
+        case 5: gen_peers(&A->tree, &e, (box_id_t)r); break;
         }
     }
 }

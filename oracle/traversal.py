@@ -355,3 +355,22 @@ def merge_close_lists(trav: OracleTraversal) -> OracleTraversal:
     return replace(trav, neighbor_source_boxes_starts=st, neighbor_source_boxes_lists=li,
                    from_sep_close_smaller_starts=None, from_sep_close_smaller_lists=None,
                    from_sep_close_bigger_starts=None, from_sep_close_bigger_lists=None)
+
+
+def find_peer_lists(tree):
+    """``PeerListFinder.__call__`` (``/root/reference/boxtree/area_query.py:1148-1186``): CSR
+    ``(peer_list_starts, peer_lists)`` over all boxes."""
+    coord_dtype = np.dtype(tree.coord_dtype)
+    lib = lib_for(coord_dtype)
+    TravArgs = _make_structs(coord_dtype)
+    A = TravArgs()
+    arrays = [np.ascontiguousarray(a) for a in (tree.box_centers, tree.box_levels, tree.box_child_ids,
+                                                tree.box_flags, tree.box_parent_ids)]
+    A.tree.d = tree.dimensions
+    A.tree.aligned_nboxes = tree.aligned_nboxes
+    A.tree.root_extent = float(tree.root_extent)
+    (A.tree.box_centers, A.tree.box_levels, A.tree.box_child_ids, A.tree.box_flags,
+     A.tree.box_parent_ids) = (_p(a) for a in arrays)
+    A.tree.well_sep_is_n_away = 1
+    peers, _ = _ListBuilder(lib, A)(5, tree.nboxes)
+    return peers.starts, peers.lists

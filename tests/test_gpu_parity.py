@@ -314,6 +314,22 @@ def test_link_point_sources(actx):
         link_point_sources(actx, t2, actx.from_numpy(starts), [actx.from_numpy(p) for p in pts])
 
 
+@pytest.mark.parametrize("dims,dtype,kind", [(1, np.float64, "adaptive"), (2, np.float32, "adaptive"),
+                                             (3, np.float64, "adaptive-level-restricted"),
+                                             (3, np.float32, "adaptive")])
+def test_peer_lists(actx, dims, dtype, kind):
+    """PeerListFinder (boxtree/area_query.py:1057-1188) against the oracle, array for array."""
+    from boxtree_b200 import PeerListFinder
+    from oracle.traversal import find_peer_lists
+    src = normal_particles(20000, dims, dtype)
+    tree = _build_tree_only(actx, src, dict(max_particles_in_box=10, kind=kind))
+    got, _ = PeerListFinder(actx)(actx, tree)
+    got = actx.to_numpy(got)
+    st, li = find_peer_lists(actx.to_numpy(tree))
+    assert np.array_equal(got.peer_list_starts, st) and got.peer_list_starts.dtype == np.int32
+    assert np.array_equal(got.peer_lists, li) and got.peer_lists.dtype == np.int32
+
+
 def test_error_behaviour(actx):
     from boxtree_b200 import FMMTraversalBuilder, MaxLevelsExceeded, TreeBuilder
     tb = TreeBuilder(actx)

@@ -223,3 +223,22 @@ def test_link_point_sources_restatement():
         assert set(owner[w["user_point_source_ids"][ps:ps + pc]]) == set(tree.user_source_ids[s:s + c])
     for a in range(3):
         assert np.array_equal(w["point_sources"][a], pts[a][w["user_point_source_ids"]])
+
+
+@pytest.mark.parametrize("dims,kind", [(2, "adaptive"), (3, "adaptive-level-restricted")])
+def test_peer_lists_restatement_against_definition(dims, kind):
+    """Peer lists (boxtree/area_query.py:393-475) against the definition quoted in its docstring
+    (adjacent, at least as large, no child with both properties), on integer box coordinates."""
+    from oracle.traversal import find_peer_lists
+    from tests.invariants import integer_box_coords
+    tree = build_tree(normal_particles(2500, dims, np.float64), max_particles_in_box=10, kind=kind)
+    st, li = find_peer_lists(tree)
+    lev, lo, size = integer_box_coords(tree)
+    hi = lo + size[:, None]
+    nb = tree.nboxes
+    adj = np.all((lo[:, None, :] <= hi[None, :, :]) & (lo[None, :, :] <= hi[:, None, :]), axis=2)
+    for b in range(nb):
+        cand = adj[b] & (lev <= lev[b])
+        want = {k for k in np.nonzero(cand)[0]
+                if not any(cand[c] for c in tree.box_child_ids[:, k] if c)}
+        assert set(li[st[b]:st[b + 1]]) == want, b
