@@ -19,7 +19,7 @@ from .traversal import BuiltList, FMMTraversalBuilder, FMMTraversalInfo
 from .particle_filter import (FilteredTargetListsInTreeOrder, FilteredTargetListsInUserOrder,
                               ParticleListFilter)
 from .point_sources import TreeWithLinkedPointSources, link_point_sources
-from .area_query import PeerListFinder, PeerListLookup
+from .area_query import AreaQueryBuilder, AreaQueryResult, PeerListFinder, PeerListLookup
 
 __all__ = [
     "TorchArrayContext", "make_obj_array",
@@ -28,5 +28,5 @@ __all__ = [
     "FMMTraversalBuilder", "FMMTraversalInfo", "BuiltList",
     "ParticleListFilter", "FilteredTargetListsInUserOrder", "FilteredTargetListsInTreeOrder",
     "TreeWithLinkedPointSources", "link_point_sources",
-    "PeerListFinder", "PeerListLookup",
+    "PeerListFinder", "PeerListLookup", "AreaQueryBuilder", "AreaQueryResult",
 ]

@@ -124,6 +124,7 @@ SIGNATURES = {
     "bt_trav_list13": [_i, _i, _P(bt_tree_view), _P(bt_list3_args), vp, _i, vp, vp, vp, vp,
                        _P(bt_heavy_ws), _i64, _i, _i, vp],
     "bt_trav_merge_lists": [_i, _i, vp, _i, _P(vp), _P(vp), vp, vp, vp, vp],
+    "bt_area_query": [_i, _i, _P(bt_tree_view), vp, vp, _i, _P(vp), vp, _P(_d), vp, vp, vp, vp],
     "bt_gather_i32": [_i64, vp, vp, vp, vp],
     "bt_dist_dfs_order": [_i, _i, _i, _i, vp, vp, vp, vp, vp, vp],
     "bt_dist_mask_from_list": [_i, vp, vp, vp],

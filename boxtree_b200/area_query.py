@@ -65,3 +65,75 @@ class PeerListFinder:
             evt = torch.cuda.Event()
             evt.record(actx.stream)
         return actx.freeze(PeerListLookup(tree=tree, peer_list_starts=starts, peer_lists=lists)), evt
+
+
+@dataclass(frozen=True)
+class AreaQueryResult:
+    """``area_query.py:115-140``: the leaf boxes near every ball, CSR over the balls."""
+    tree: Any
+    leaves_near_ball_starts: Any
+    leaves_near_ball_lists: Any
+
+
+def _tree_view(tree):
+    tv = bt_tree_view()
+    tv.dim = int(tree.dimensions)
+    tv.nboxes = int(tree.nboxes)
+    tv.aligned_nboxes = int(tree.box_child_ids.shape[-1])
+    tv.nlevels = int(tree.nlevels)
+    tv.root_extent = float(tree.root_extent)
+    keep = [t.contiguous() for t in (tree.box_centers, tree.box_levels, tree.box_child_ids,
+                                    tree.box_flags, tree.box_parent_ids)]
+    tv.box_centers, tv.box_levels, tv.box_child_ids, tv.box_flags, tv.box_parent_ids = \
+        (dptr(t) for t in keep)
+    tv.well_sep_is_n_away = 1
+    return tv, keep
+
+
+class AreaQueryBuilder:
+    r"""Look-up table from :math:`l^\infty` balls to the leaf boxes that intersect them
+    (``area_query.py:657-807``)."""
+
+    def __init__(self, array_context: TorchArrayContext) -> None:
+        assert isinstance(array_context, TorchArrayContext)
+        self._setup_actx = array_context
+        self.peer_list_finder = PeerListFinder(array_context)
+        self._lib = _cabi.load()
+
+    def __call__(self, actx, tree, ball_centers, ball_radii, peer_lists=None, wait_for=None):
+        assert isinstance(actx, TorchArrayContext)
+        coord_dtype = np.dtype(tree.coord_dtype)
+        tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}[coord_dtype]
+        if any(bc.dtype != tdt for bc in ball_centers):
+            raise TypeError("ball_centers dtype must match tree.coord_dtype")
+        if ball_radii.dtype != tdt:
+            raise TypeError("ball_radii dtype must match tree.coord_dtype")
+        if peer_lists is None:
+            peer_lists, _ = self.peer_list_finder(actx, tree, wait_for=wait_for)
+        if int(peer_lists.peer_list_starts.shape[0]) != int(tree.nboxes) + 1:
+            raise ValueError("size of peer lists must match with number of boxes")
+        lib = self._lib
+        sh = actx.stream_handle
+        nballs = int(ball_radii.shape[0])
+        with torch.cuda.stream(actx.stream), torch.cuda.device(actx.device):
+            tv, keep = _tree_view(tree)
+            centers = [bc.contiguous() for bc in ball_centers]
+            radii = ball_radii.contiguous()
+            dcode = _cabi.dtype_code(coord_dtype)
+            starts = actx.empty(nballs + 1, np.int32)
+            totals = actx.zeros(2, np.int64)
+            cptr = _cabi.ptr_array(centers)
+            bbox_min = _cabi.darray(np.asarray(tree.bounding_box[0], np.float64))
+
+            def run(phase, lists):
+                check(lib.bt_area_query(dcode, phase, C.byref(tv), dptr(peer_lists.peer_list_starts),
+                                        dptr(peer_lists.peer_lists), nballs, cptr, dptr(radii),
+                                        bbox_min, dptr(starts), dptr(lists), dptr(totals), sh),
+                      "bt_area_query")
+            run(0, None)
+            lists = actx.empty(int(totals[0].item()), np.int32)
+            run(1, lists)
+            evt = torch.cuda.Event()
+            evt.record(actx.stream)
+        return actx.freeze(AreaQueryResult(tree=tree, leaves_near_ball_starts=starts,
+                                           leaves_near_ball_lists=lists)), evt

@@ -693,6 +693,116 @@ __device__ __forceinline__ void gen_peers(const TreeView<T, DIM>& t, const T* ra
     }
 }
 
+// ---- N3 area query: area_query.py:168-392 ------------------------------------
+// One row per l^inf ball: find the "guiding box" (the box around the clamped centre whose radius
+// brackets the clamped ball radius, descending with the Morton-digit expression of the tree
+// build), then emit the leaves among its peers' subtrees that overlap the ball
+// (check_l_infty_ball_overlap, traversal.py:200-214).
+template <typename T, int DIM>
+struct Balls { const T* c[3]; const T* r; T bbox_min[3]; };
+
+template <typename T, int DIM>
+__device__ __forceinline__ bool ball_overlaps(const TreeView<T, DIM>& t, const T* rad, int b, const T* bc, T br)
+{
+    T c[DIM]; t.center(b, c);
+    const T size_sum = rad[t.levels[b]] + br;
+    T max_dist = 0;
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) max_dist = fmax(max_dist, fabs(bc[a] - c[a]));
+    return max_dist <= size_sum;
+}
+
+template <typename T, int DIM, bool FILL>
+__global__ void __launch_bounds__(kTravBlock)
+area_query_kernel(TreeView<T, DIM> t, Balls<T, DIM> balls, const int* __restrict__ peer_starts,
+                  const int* __restrict__ peer_lists, int nballs, int* __restrict__ starts,
+                  int* __restrict__ lists)
+{
+    constexpr int NB = 1 << DIM;
+    __shared__ T rad[kMaxWalkLevels];
+    fill_rad_table(rad, t.root_extent);
+    constexpr unsigned char haschild = BT_BOX_HAS_SOURCE_CHILD_BOXES | BT_BOX_HAS_TARGET_CHILD_BOXES;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nballs; i += stride) {
+        T bc[DIM], qc[DIM], bbox_max[DIM];
+        const T br = balls.r[i];
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) {
+            bc[a] = balls.c[a][i];
+            bbox_max[a] = balls.bbox_min[a] + (T)((double)t.root_extent / (1 + 1e-4));
+            qc[a] = fmin(bbox_max[a], fmax(balls.bbox_min[a], bc[a]));
+        }
+        T qr = 0;
+#pragma unroll
+        for (int mnr = 0; mnr < NB; ++mnr) {
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) {
+                const T off = ((1 << (DIM - 1 - a)) & mnr) ? +br : -br;
+                const T corner = fmin(bbox_max[a], fmax(balls.bbox_min[a], bc[a] + off));
+                qr = fmax(qr, fabs(corner - qc[a]));
+            }
+        }
+        int box = 0;
+        if (rad[0] / 2 >= qr) {
+            for (unsigned box_level = 0;; ++box_level) {
+                if (!(t.flags[box] & haschild) || (rad[box_level] / 2 < qr && qr <= rad[box_level])) break;
+                int morton = 0;
+#pragma unroll
+                for (int a = 0; a < DIM; ++a) {
+                    const T off_scaled = (qc[a] - balls.bbox_min[a]) / t.root_extent;
+                    const unsigned bits = (unsigned)(off_scaled * (T)(1U << ((1 + box_level) & 31)));
+                    morton |= (int)(bits & 1U) << (DIM - 1 - a);
+                }
+                const int next = t.child(box, morton);
+                if (next) box = next; else break;
+            }
+        }
+        int n = 0;
+        int* out = FILL ? lists + starts[i] : nullptr;
+        for (int pi = peer_starts[box]; pi < peer_starts[box + 1]; ++pi) {
+            const int peer = peer_lists[pi];
+            if (!(t.flags[peer] & haschild)) {
+                if (ball_overlaps<T, DIM>(t, rad, peer, bc, br)) { if (FILL) out[n] = peer; ++n; }
+            } else {
+                Walk w; w.init(peer);
+                while (w.cont) {
+                    const int wb = t.child(w.parent, w.mnr);
+                    if (wb) {
+                        if (!(t.flags[wb] & haschild)) {
+                            if (ball_overlaps<T, DIM>(t, rad, wb, bc, br)) { if (FILL) out[n] = wb; ++n; }
+                        } else { w.push(wb); continue; }
+                    }
+                    w.template advance<NB>();
+                }
+            }
+        }
+        if (!FILL) starts[i] = n;
+    }
+}
+
+template <typename T, int DIM>
+static int area_query_impl(int phase, const bt_tree_view* tv, const int* peer_starts, const int* peer_lists,
+                           int nballs, void* const* ball_centers, const void* ball_radii,
+                           const double* bbox_min, int* starts, int* lists, long long* totals, cudaStream_t s)
+{
+    TreeView<T, DIM> t = make_view<T, DIM>(tv);
+    if (t.nlevels > kMaxWalkLevels) return BT_ERR_UNSUPPORTED;
+    Balls<T, DIM> b;
+    for (int a = 0; a < 3; ++a) {
+        b.c[a] = a < DIM ? (const T*)ball_centers[a] : nullptr;
+        b.bbox_min[a] = a < DIM ? (T)bbox_min[a] : (T)0;
+    }
+    b.r = (const T*)ball_radii;
+    if (nballs > 0) {
+        const int grid = grid_for(nballs, kTravBlock, 16);
+        if (phase == 0) area_query_kernel<T, DIM, false><<<grid, kTravBlock, 0, s>>>(t, b, peer_starts, peer_lists, nballs, starts, lists);
+        else area_query_kernel<T, DIM, true><<<grid, kTravBlock, 0, s>>>(t, b, peer_starts, peer_lists, nballs, starts, lists);
+        BT_LAUNCH_CHECK();
+    }
+    if (phase == 0) BT_TRY(counts_to_starts(starts, nballs, totals, s));
+    return BT_OK;
+}
+
 // generic row kernel; KIND: 0 colleagues, 2 list2, 4 list4, 5 peers (list 1 and 3 have their own)
 template <typename T, int DIM, int KIND, bool FILL>
 __global__ void __launch_bounds__(kTravBlock)
@@ -2628,6 +2738,15 @@ int bt_trav_transpose_children(int dim, int aligned_nboxes, const int32_t* box_c
         nb, aligned_nboxes, box_child_ids, box_child_ids_t);
     BT_LAUNCH_CHECK();
     return BT_OK;
+}
+
+int bt_area_query(int dtype, int phase, const bt_tree_view* tree, const int32_t* peer_list_starts,
+                  const int32_t* peer_lists, int nballs, void* const* ball_centers, const void* ball_radii,
+                  const double* bbox_min, int32_t* starts, int32_t* lists, int64_t* totals_dev, void* stream)
+{
+    BT_PROF(phase ? "area_query_fill" : "area_query_count", (cudaStream_t)stream);
+    BT_DISPATCH(dtype, tree->dim, area_query_impl, phase, tree, peer_list_starts, peer_lists, nballs, ball_centers,
+                ball_radii, bbox_min, starts, lists, (long long*)totals_dev, (cudaStream_t)stream);
 }
 
 int bt_trav_list13(int dtype, int phase, const bt_tree_view* tree, const bt_list3_args* args,

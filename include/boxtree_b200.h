@@ -383,6 +383,15 @@ int bt_trav_list13(int dtype, int phase, const bt_tree_view *tree, const bt_list
                    int64_t heavy_total, int nheavy, int nwalk /* HOST copies, phase 1 */,
                    void *stream);
 
+/* AreaQueryBuilder (area_query.py:168-392, 657-807): per l^inf ball (centre, radius) the leaf
+ * boxes overlapping it, found from the guiding box's peer lists (bt_trav_build_list kind 5).
+ * ball_centers: HOST array of dim device pointers; bbox_min: HOST [dim] (tree.bounding_box[0]).
+ * phase 0: starts[nballs+1], total at totals_dev[0]; phase 1: lists. */
+int bt_area_query(int dtype, int phase, const bt_tree_view *tree, const int32_t *peer_list_starts,
+                  const int32_t *peer_lists, int nballs, void *const *ball_centers,
+                  const void *ball_radii, const double *bbox_min, int32_t *starts, int32_t *lists,
+                  int64_t *totals_dev, void *stream);
+
 /* _ListMerger (traversal.py:1153-1344): phase 0 -> new_starts[noutput+1], total at
  * totals_dev[0]; phase 1 -> new_lists.  starts/lists: HOST arrays of nlists device pointers. */
 int bt_trav_merge_lists(int phase, int noutput, const int32_t *output_to_input_box, int nlists,

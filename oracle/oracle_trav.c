@@ -479,6 +479,83 @@ void orc_build_lists(int kind, const trav_args_t *A, int64_t nrows, int write,
     }
 }
 
+/* N3: area query -- area_query.py:168-392 (GUIDING_BOX_FINDER_MACRO, AREA_QUERY_WALKER_BODY)
+ * and check_l_infty_ball_overlap (traversal.py:200-214).  One row per ball: the leaves that
+ * overlap the l^inf ball.  write = 0: counts[nballs]; write = 1: lists at starts. */
+static int ball_overlaps(const tree_view_t *t, box_id_t b, const coord_t *bc, coord_t br)
+{
+    coord_t c[MAXDIM]; load_center(t, b, c);
+    coord_t size_sum = level_to_rad(t->root_extent, t->box_levels[b]) + br;
+    coord_t max_dist = 0;
+    for (int a = 0; a < t->d; ++a) max_dist = COORD_FMAX(max_dist, COORD_FABS(bc[a] - c[a]));
+    return max_dist <= size_sum;
+}
+
+void orc_area_query(const tree_view_t *t, const int32_t *peer_starts, const box_id_t *peer_lists,
+                    int64_t nballs, const coord_t *const *ball_centers, const coord_t *ball_radii,
+                    const coord_t *bbox_min, int write, int32_t *counts, const int32_t *starts,
+                    int32_t *lists)
+{
+    const int d = t->d, nb = 1 << d;
+    const int haschild = BOX_HAS_SOURCE_CHILD_BOXES | BOX_HAS_TARGET_CHILD_BOXES;
+    for (int64_t i = 0; i < nballs; ++i) {
+        coord_t bc[MAXDIM]; for (int a = 0; a < d; ++a) bc[a] = ball_centers[a][i];
+        const coord_t br = ball_radii[i];
+        /* find_guiding_box, :168-264 */
+        box_id_t box = 0;
+        coord_t bbox_max[MAXDIM], qc[MAXDIM];
+        for (int a = 0; a < d; ++a) {
+            bbox_max[a] = bbox_min[a] + (coord_t)(t->root_extent / (1 + 1e-4));
+            qc[a] = COORD_FMIN(bbox_max[a], COORD_FMAX(bbox_min[a], bc[a]));
+        }
+        coord_t qr = 0;
+        for (int mnr = 0; mnr < nb; ++mnr) {
+            for (int a = 0; a < d; ++a) {
+                coord_t off = ((1 << (d - 1 - a)) & mnr) ? +br : -br;
+                coord_t corner = COORD_FMIN(bbox_max[a], COORD_FMAX(bbox_min[a], bc[a] + off));
+                qr = COORD_FMAX(qr, COORD_FABS(corner - qc[a]));
+            }
+        }
+        if (level_to_rad(t->root_extent, 0) / 2 >= qr) {
+            for (unsigned box_level = 0;; ++box_level) {
+                if (!(t->box_flags[box] & haschild)
+                    || (level_to_rad(t->root_extent, box_level) / 2 < qr
+                        && qr <= level_to_rad(t->root_extent, box_level)))
+                    break;
+                int morton = 0;
+                for (int a = 0; a < d; ++a) {
+                    coord_t off_scaled = (qc[a] - bbox_min[a]) / t->root_extent;
+                    unsigned bits = (unsigned)(off_scaled * (1U << ((1 + box_level) & 31)));
+                    morton |= (bits & 1U) << (d - 1 - a);
+                }
+                box_id_t next = t->box_child_ids[morton * t->aligned_nboxes + box];
+                if (next) box = next; else break;
+            }
+        }
+        /* walk the peers, :266-365 */
+        int32_t n = 0;
+        int32_t *out = write ? lists + starts[i] : NULL;
+        for (int32_t pi = peer_starts[box]; pi < peer_starts[box + 1]; ++pi) {
+            box_id_t peer = peer_lists[pi];
+            if (!(t->box_flags[peer] & haschild)) {
+                if (ball_overlaps(t, peer, bc, br)) { if (write) out[n] = peer; ++n; }
+            } else {
+                walk_t w; walk_init(&w, peer);
+                while (w.cont) {
+                    box_id_t wb = walk_box(t, &w);
+                    if (wb) {
+                        if (!(t->box_flags[wb] & haschild)) {
+                            if (ball_overlaps(t, wb, bc, br)) { if (write) out[n] = wb; ++n; }
+                        } else { walk_push(&w, wb); continue; }
+                    }
+                    walk_advance(&w, nb);
+                }
+            }
+        }
+        if (!write) counts[i] = n;
+    }
+}
+
 /* list merger -- traversal.py:1153-1214 (count kernel then write kernel) */
 void orc_merge_lists_count(int64_t noutput, const box_id_t *output_to_input_box, int nlists,
                            const box_id_t *const *starts, box_id_t *new_counts /* [noutput+1] */)

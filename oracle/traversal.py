@@ -374,3 +374,37 @@ def find_peer_lists(tree):
     A.tree.well_sep_is_n_away = 1
     peers, _ = _ListBuilder(lib, A)(5, tree.nboxes)
     return peers.starts, peers.lists
+
+
+def area_query(tree, ball_centers, ball_radii, peer_lists=None):
+    """``AreaQueryBuilder.__call__`` (``/root/reference/boxtree/area_query.py:757-807``):
+    ``(leaves_near_ball_starts, leaves_near_ball_lists)``."""
+    coord_dtype = np.dtype(tree.coord_dtype)
+    lib = lib_for(coord_dtype)
+    TravArgs = _make_structs(coord_dtype)
+    A = TravArgs()
+    arrays = [np.ascontiguousarray(a) for a in (tree.box_centers, tree.box_levels, tree.box_child_ids,
+                                                tree.box_flags, tree.box_parent_ids)]
+    A.tree.d = tree.dimensions
+    A.tree.aligned_nboxes = tree.aligned_nboxes
+    A.tree.root_extent = float(tree.root_extent)
+    (A.tree.box_centers, A.tree.box_levels, A.tree.box_child_ids, A.tree.box_flags,
+     A.tree.box_parent_ids) = (_p(a) for a in arrays)
+    A.tree.well_sep_is_n_away = 1
+    if peer_lists is None:
+        peer_lists = find_peer_lists(tree)
+    pst, pli = (np.ascontiguousarray(a, np.int32) for a in peer_lists)
+    centers = [np.ascontiguousarray(c, coord_dtype) for c in ball_centers]
+    radii = np.ascontiguousarray(ball_radii, coord_dtype)
+    nballs = len(radii)
+    cptr = (C.c_void_p * 3)(*[c.ctypes.data for c in centers] + [None] * (3 - len(centers)))
+    bbox_min = np.ascontiguousarray(tree.bounding_box[0], coord_dtype)
+    counts = np.zeros(nballs, np.int32)
+    lib.orc_area_query(C.byref(A.tree), ptr(pst), ptr(pli), i64(nballs), cptr, ptr(radii),
+                       ptr(bbox_min), cint(0), ptr(counts), None, None)
+    starts = np.zeros(nballs + 1, np.int32)
+    np.cumsum(counts, out=starts[1:])
+    lists = np.zeros(int(starts[-1]), np.int32)
+    lib.orc_area_query(C.byref(A.tree), ptr(pst), ptr(pli), i64(nballs), cptr, ptr(radii),
+                       ptr(bbox_min), cint(1), None, ptr(starts), ptr(lists))
+    return starts, lists

@@ -330,6 +330,55 @@ def test_peer_lists(actx, dims, dtype, kind):
     assert np.array_equal(got.peer_lists, li) and got.peer_lists.dtype == np.int32
 
 
+@pytest.mark.parametrize("dims,dtype,kind", [(2, np.float64, "adaptive"), (3, np.float32, "adaptive"),
+                                             (3, np.float64, "adaptive-level-restricted")])
+def test_area_query(actx, dims, dtype, kind):
+    """AreaQueryBuilder (boxtree/area_query.py:657-807) against the oracle, array for array."""
+    from boxtree_b200 import AreaQueryBuilder
+    from oracle.traversal import area_query
+    from tests.test_oracle import _random_balls
+    src = normal_particles(20000, dims, dtype)
+    tree = _build_tree_only(actx, src, dict(max_particles_in_box=10, kind=kind))
+    htree = actx.to_numpy(tree)
+    centers, radii = _random_balls(htree, 3000)
+    got, _ = AreaQueryBuilder(actx)(actx, tree, [actx.from_numpy(c) for c in centers],
+                                    actx.from_numpy(radii))
+    got = actx.to_numpy(got)
+    starts, lists = area_query(htree, centers, radii)
+    assert np.array_equal(got.leaves_near_ball_starts, starts)
+    assert np.array_equal(got.leaves_near_ball_lists, lists)
+    with pytest.raises(TypeError):
+        other = np.float32 if dtype == np.float64 else np.float64
+        AreaQueryBuilder(actx)(actx, tree, [actx.from_numpy(c) for c in centers],
+                               actx.from_numpy(radii.astype(other)))
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_level_restriction_through_area_query(actx, dims):
+    """test/test_tree.py:900-974: in a level-restricted tree the leaves found near every leaf (a
+    ball slightly larger than the leaf) differ from it by at most one level."""
+    from boxtree_b200 import AreaQueryBuilder
+    nparticles = 10 ** 5
+    rng = np.random.default_rng(15)
+    src = [rng.normal(size=nparticles) for _ in range(dims)]
+    tree = _build_tree_only(actx, src, dict(max_particles_in_box=30, kind="adaptive-level-restricted",
+                                            nboxes_guess=10))
+    ht = actx.to_numpy(tree)
+    nb = ht.nboxes
+    leaf_boxes = np.nonzero((ht.box_flags[:nb] & 12) == 0)[0]
+    leaf_radii = float(ht.root_extent) / 2.0 ** (1 + ht.box_levels[leaf_boxes].astype(np.float64))
+    leaf_centers = [np.ascontiguousarray(ht.box_centers[a, leaf_boxes]) for a in range(dims)]
+    ball_radii = np.min(leaf_radii) / 2 + leaf_radii
+    aq, _ = AreaQueryBuilder(actx)(actx, tree, [actx.from_numpy(c) for c in leaf_centers],
+                                   actx.from_numpy(ball_radii))
+    aq = actx.to_numpy(aq)
+    st, li = aq.leaves_near_ball_starts, aq.leaves_near_ball_lists
+    rows = np.repeat(np.arange(len(leaf_boxes)), np.diff(st))
+    diff = np.abs(ht.box_levels[li].astype(int) - ht.box_levels[leaf_boxes[rows]].astype(int))
+    assert np.all(diff <= 1)
+    assert np.all(np.diff(st) >= 1)                       # every leaf finds at least itself
+
+
 def test_error_behaviour(actx):
     from boxtree_b200 import FMMTraversalBuilder, MaxLevelsExceeded, TreeBuilder
     tb = TreeBuilder(actx)

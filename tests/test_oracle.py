@@ -242,3 +242,31 @@ def test_peer_lists_restatement_against_definition(dims, kind):
         want = {k for k in np.nonzero(cand)[0]
                 if not any(cand[c] for c in tree.box_child_ids[:, k] if c)}
         assert set(li[st[b]:st[b + 1]]) == want, b
+
+
+def _random_balls(tree, n, seed=3):
+    rng = np.random.default_rng(seed)
+    lo, hi = tree.bounding_box
+    ext = float(tree.root_extent)
+    centers = [rng.uniform(lo[a] - 0.2 * ext, lo[a] + 1.2 * ext, n).astype(tree.coord_dtype)
+               for a in range(tree.dimensions)]             # some centres outside the bounding box
+    radii = (ext * 2 ** rng.uniform(-9, -0.5, n)).astype(tree.coord_dtype)
+    return centers, radii
+
+
+@pytest.mark.parametrize("dims,kind", [(2, "adaptive"), (3, "adaptive-level-restricted")])
+def test_area_query_restatement_against_definition(dims, kind):
+    """AreaQueryBuilder (boxtree/area_query.py:168-392): the leaves found through the guiding box's
+    peers are exactly the leaves whose box overlaps the ball (test/test_tree.py:645-700)."""
+    from oracle.traversal import area_query
+    tree = build_tree(normal_particles(3000, dims, np.float64), max_particles_in_box=10, kind=kind)
+    centers, radii = _random_balls(tree, 400)
+    starts, lists = area_query(tree, centers, radii)
+    nb = tree.nboxes
+    leaf = (tree.box_flags[:nb] & 12) == 0
+    half = float(tree.root_extent) / 2.0 ** (1 + tree.box_levels[:nb].astype(np.float64))
+    for i in range(len(radii)):
+        dist = np.max(np.abs(tree.box_centers[:, :nb] - np.array([c[i] for c in centers])[:, None]), axis=0)
+        want = set(np.nonzero(leaf & (dist <= half + radii[i]))[0])
+        got = lists[starts[i]:starts[i + 1]]
+        assert len(set(got)) == len(got) and set(got) == want, i
