@@ -19,7 +19,9 @@ from .traversal import BuiltList, FMMTraversalBuilder, FMMTraversalInfo
 from .particle_filter import (FilteredTargetListsInTreeOrder, FilteredTargetListsInUserOrder,
                               ParticleListFilter)
 from .point_sources import TreeWithLinkedPointSources, link_point_sources
-from .area_query import AreaQueryBuilder, AreaQueryResult, PeerListFinder, PeerListLookup
+from .area_query import (AreaQueryBuilder, AreaQueryResult, LeavesToBallsLookup,
+                         LeavesToBallsLookupBuilder, PeerListFinder, PeerListLookup,
+                         SpaceInvaderQueryBuilder)
 
 __all__ = [
     "TorchArrayContext", "make_obj_array",
@@ -29,4 +31,5 @@ __all__ = [
     "ParticleListFilter", "FilteredTargetListsInUserOrder", "FilteredTargetListsInTreeOrder",
     "TreeWithLinkedPointSources", "link_point_sources",
     "PeerListFinder", "PeerListLookup", "AreaQueryBuilder", "AreaQueryResult",
+    "LeavesToBallsLookupBuilder", "LeavesToBallsLookup", "SpaceInvaderQueryBuilder",
 ]

@@ -137,3 +137,74 @@ class AreaQueryBuilder:
             evt.record(actx.stream)
         return actx.freeze(AreaQueryResult(tree=tree, leaves_near_ball_starts=starts,
                                            leaves_near_ball_lists=lists)), evt
+
+
+@dataclass(frozen=True)
+class LeavesToBallsLookup:
+    """``area_query.py:143-163``: the balls overlapping every leaf box, CSR over ALL boxes."""
+    tree: Any
+    balls_near_box_starts: Any
+    balls_near_box_lists: Any
+
+
+class LeavesToBallsLookupBuilder:
+    """``area_query.py:810-905``: the area query turned around (expand the starts, stable
+    key-value sort by leaf box)."""
+
+    def __init__(self, array_context: TorchArrayContext) -> None:
+        self._setup_actx = array_context
+        self.area_query_builder = AreaQueryBuilder(array_context)
+
+    def __call__(self, actx, tree, ball_centers, ball_radii, peer_lists=None, wait_for=None):
+        aq, _ = self.area_query_builder(actx, tree, ball_centers, ball_radii, peer_lists, wait_for)
+        with torch.cuda.stream(actx.stream):
+            nboxes = int(tree.nboxes)
+            starts = aq.leaves_near_ball_starts.long()
+            nballs = int(starts.shape[0]) - 1
+            npairs = int(aq.leaves_near_ball_lists.shape[0])
+            dev = starts.device
+            # STARTS_EXPANDER_TEMPLATE: [0 2 5 6] -> [0 0 1 1 1 2]
+            ball_of_pair = torch.repeat_interleave(torch.arange(nballs, device=dev),
+                                                   starts[1:] - starts[:-1], output_size=npairs)
+            # KeyValueSorter: stable by key, so the balls of a box stay in ascending order
+            keys = aq.leaves_near_ball_lists.long()
+            order = torch.argsort(keys, stable=True)
+            lists = ball_of_pair[order].to(torch.int32)
+            box_starts = torch.zeros(nboxes + 1, dtype=torch.int32, device=dev)
+            box_starts[1:] = torch.cumsum(torch.bincount(keys, minlength=nboxes), 0).to(torch.int32)
+            evt = torch.cuda.Event()
+            evt.record(actx.stream)
+        return actx.freeze(LeavesToBallsLookup(tree=tree, balls_near_box_starts=box_starts,
+                                               balls_near_box_lists=lists)), evt
+
+
+class SpaceInvaderQueryBuilder:
+    r"""``area_query.py:908-1048``: per leaf box the *outer space invader distance*
+    :math:`\max_{b^* \cap b \ne \emptyset} d_\infty(\mathrm{center}(b), \mathrm{center}(b^*))`
+    (0 for other boxes).  Like the reference the maximum is taken in float32 and cast back to the
+    coordinate dtype (``:613-650, 1036-1044``)."""
+
+    def __init__(self, array_context: TorchArrayContext) -> None:
+        self._setup_actx = array_context
+        self.area_query_builder = AreaQueryBuilder(array_context)
+
+    def __call__(self, actx, tree, ball_centers, ball_radii, peer_lists=None, wait_for=None):
+        aq, _ = self.area_query_builder(actx, tree, ball_centers, ball_radii, peer_lists, wait_for)
+        with torch.cuda.stream(actx.stream):
+            nboxes = int(tree.nboxes)
+            starts = aq.leaves_near_ball_starts.long()
+            nballs = int(starts.shape[0]) - 1
+            npairs = int(aq.leaves_near_ball_lists.shape[0])
+            dev = starts.device
+            ball = torch.repeat_interleave(torch.arange(nballs, device=dev), starts[1:] - starts[:-1],
+                                           output_size=npairs)
+            leaf = aq.leaves_near_ball_lists.long()
+            max_dist = torch.zeros(npairs, dtype=ball_radii.dtype, device=dev)
+            for a, bc in enumerate(ball_centers):
+                max_dist = torch.maximum(max_dist, (bc[ball] - tree.box_centers[a][leaf]).abs())
+            out = torch.zeros(nboxes, dtype=torch.float32, device=dev)
+            out.scatter_reduce_(0, leaf, max_dist.to(torch.float32), reduce="amax", include_self=True)
+            out = out.to(ball_radii.dtype)
+            evt = torch.cuda.Event()
+            evt.record(actx.stream)
+        return actx.freeze(out), evt

@@ -408,3 +408,31 @@ def area_query(tree, ball_centers, ball_radii, peer_lists=None):
     lib.orc_area_query(C.byref(A.tree), ptr(pst), ptr(pli), i64(nballs), cptr, ptr(radii),
                        ptr(bbox_min), cint(1), None, ptr(starts), ptr(lists))
     return starts, lists
+
+
+def leaves_to_balls(tree, ball_centers, ball_radii):
+    """``LeavesToBallsLookupBuilder.__call__`` (``area_query.py:844-905``): the area query's pairs
+    sorted (stably) by leaf box."""
+    starts, lists = area_query(tree, ball_centers, ball_radii)
+    nballs = len(starts) - 1
+    ball_of_pair = np.repeat(np.arange(nballs, dtype=np.int32), np.diff(starts))
+    order = np.argsort(lists, kind="stable")
+    box_starts = np.zeros(tree.nboxes + 1, np.int32)
+    np.cumsum(np.bincount(lists, minlength=tree.nboxes), out=box_starts[1:])
+    return box_starts, ball_of_pair[order]
+
+
+def space_invader_query(tree, ball_centers, ball_radii):
+    """``SpaceInvaderQueryBuilder.__call__`` (``area_query.py:613-650, 990-1048``): per leaf the
+    largest centre distance to an overlapping ball, maximum taken in float32."""
+    coord_dtype = np.dtype(tree.coord_dtype)
+    starts, lists = area_query(tree, ball_centers, ball_radii)
+    out = np.zeros(tree.nboxes, np.float32)
+    for i in range(len(starts) - 1):
+        for leaf in lists[starts[i]:starts[i + 1]]:
+            max_dist = coord_dtype.type(0)
+            for a in range(tree.dimensions):
+                max_dist = max(max_dist, abs(coord_dtype.type(ball_centers[a][i])
+                                             - coord_dtype.type(tree.box_centers[a, leaf])))
+            out[leaf] = max(out[leaf], np.float32(max_dist))
+    return out.astype(coord_dtype)

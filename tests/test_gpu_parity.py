@@ -353,6 +353,27 @@ def test_area_query(actx, dims, dtype, kind):
                                actx.from_numpy(radii.astype(other)))
 
 
+@pytest.mark.parametrize("dims,dtype", [(2, np.float64), (3, np.float32)])
+def test_leaves_to_balls_and_space_invaders(actx, dims, dtype):
+    """LeavesToBallsLookupBuilder and SpaceInvaderQueryBuilder (boxtree/area_query.py:810-1048)."""
+    from boxtree_b200 import LeavesToBallsLookupBuilder, SpaceInvaderQueryBuilder
+    from oracle.traversal import leaves_to_balls, space_invader_query
+    from tests.test_oracle import _random_balls
+    src = normal_particles(8000, dims, dtype)
+    tree = _build_tree_only(actx, src, dict(max_particles_in_box=10))
+    htree = actx.to_numpy(tree)
+    centers, radii = _random_balls(htree, 600)
+    dc, dr = [actx.from_numpy(c) for c in centers], actx.from_numpy(radii)
+    got, _ = LeavesToBallsLookupBuilder(actx)(actx, tree, dc, dr)
+    got = actx.to_numpy(got)
+    st, li = leaves_to_balls(htree, centers, radii)
+    assert np.array_equal(got.balls_near_box_starts, st) and np.array_equal(got.balls_near_box_lists, li)
+    sq, _ = SpaceInvaderQueryBuilder(actx)(actx, tree, dc, dr)
+    sq = actx.to_numpy(sq)
+    want = space_invader_query(htree, centers, radii)
+    assert sq.dtype == want.dtype and np.array_equal(sq, want)
+
+
 @pytest.mark.parametrize("dims", [2, 3])
 def test_level_restriction_through_area_query(actx, dims):
     """test/test_tree.py:900-974: in a level-restricted tree the leaves found near every leaf (a
