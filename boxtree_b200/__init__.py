@@ -22,6 +22,8 @@ from .point_sources import TreeWithLinkedPointSources, link_point_sources
 from .area_query import (AreaQueryBuilder, AreaQueryResult, LeavesToBallsLookup,
                          LeavesToBallsLookupBuilder, PeerListFinder, PeerListLookup,
                          SpaceInvaderQueryBuilder)
+from .translation_classes import (RotationClassesBuilder, RotationClassesInfo,
+                                  TranslationClassesBuilder, TranslationClassesInfo)
 
 __all__ = [
     "TorchArrayContext", "make_obj_array",
@@ -32,4 +34,6 @@ __all__ = [
     "TreeWithLinkedPointSources", "link_point_sources",
     "PeerListFinder", "PeerListLookup", "AreaQueryBuilder", "AreaQueryResult",
     "LeavesToBallsLookupBuilder", "LeavesToBallsLookup", "SpaceInvaderQueryBuilder",
+    "TranslationClassesBuilder", "TranslationClassesInfo", "RotationClassesBuilder",
+    "RotationClassesInfo",
 ]

@@ -400,6 +400,33 @@ def test_level_restriction_through_area_query(actx, dims):
     assert np.all(np.diff(st) >= 1)                       # every leaf finds at least itself
 
 
+@pytest.mark.parametrize("dims,dtype,n_away", [(2, np.float64, 1), (3, np.float64, 2), (3, np.float32, 1)])
+def test_translation_and_rotation_classes(actx, dims, dtype, n_away):
+    """TranslationClassesBuilder / RotationClassesBuilder (boxtree/translation_classes.py,
+    boxtree/rotation_classes.py) against the oracle."""
+    from boxtree_b200 import RotationClassesBuilder, TranslationClassesBuilder
+    from oracle import translation_classes as otc
+    from oracle.traversal import build_traversal
+    src = normal_particles(8000, dims, dtype)
+    tree, trav = _build(actx, src, dict(max_particles_in_box=15), dict(well_sep_is_n_away=n_away))
+    ht = actx.to_numpy(tree)
+    htrav = build_traversal(ht, well_sep_is_n_away=n_away)
+    for per_level in (True, False):
+        got, _ = TranslationClassesBuilder(actx)(actx, trav, tree, is_translation_per_level=per_level)
+        got = actx.to_numpy(got)
+        cls, dist, ls = otc.translation_classes(htrav, ht, per_level)
+        assert np.array_equal(got.from_sep_siblings_translation_classes, cls)
+        assert got.from_sep_siblings_translation_classes.dtype == np.int32
+        d = got.from_sep_siblings_translation_class_to_distance_vector
+        assert d.dtype == dist.dtype and np.array_equal(d, dist)
+        assert np.array_equal(got.from_sep_siblings_translation_classes_level_starts, ls)
+    got, _ = RotationClassesBuilder(actx)(actx, trav, tree)
+    got = actx.to_numpy(got)
+    rot, angles = otc.rotation_classes(htrav, ht)
+    assert np.array_equal(got.from_sep_siblings_rotation_classes, rot)
+    assert np.array_equal(got.from_sep_siblings_rotation_class_to_angle, angles)
+
+
 def test_error_behaviour(actx):
     from boxtree_b200 import FMMTraversalBuilder, MaxLevelsExceeded, TreeBuilder
     tb = TreeBuilder(actx)

@@ -270,3 +270,24 @@ def test_area_query_restatement_against_definition(dims, kind):
         want = set(np.nonzero(leaf & (dist <= half + radii[i]))[0])
         got = lists[starts[i]:starts[i + 1]]
         assert len(set(got)) == len(got) and set(got) == want, i
+
+
+@pytest.mark.parametrize("dims,n_away", [(2, 1), (3, 1), (3, 2)])
+def test_translation_and_rotation_classes_restatement(dims, n_away):
+    """translation_classes.py / rotation_classes.py: the class of every list-2 pair maps back to
+    the pair's centre-to-centre vector (test/test_traversal.py's translation-class test) and
+    pairs with parallel vectors share a rotation class."""
+    from oracle import translation_classes as otc
+    tree = build_tree(normal_particles(3000, dims, np.float64), max_particles_in_box=15)
+    trav = build_traversal(tree, well_sep_is_n_away=n_away)
+    cls, dist, level_starts = otc.translation_classes(trav, tree)
+    tp, st, li = trav.target_or_target_parent_boxes, trav.from_sep_siblings_starts, \
+        trav.from_sep_siblings_lists
+    rows = np.repeat(np.arange(len(tp)), np.diff(st))
+    want = tree.box_centers[:, tp[rows]] - tree.box_centers[:, li]
+    assert np.allclose(dist[:, cls], want, rtol=0, atol=1e-12 * float(tree.root_extent))
+    lev = tree.box_levels[li].astype(int)
+    assert np.all((level_starts[lev] <= cls) & (cls < level_starts[lev + 1]))
+    rot, angles = otc.rotation_classes(trav, tree)
+    cosang = want[-1] / np.linalg.norm(want, axis=0)
+    assert np.allclose(np.cos(angles[rot]), cosang, atol=1e-12)
