@@ -24,6 +24,8 @@ from .area_query import (AreaQueryBuilder, AreaQueryResult, LeavesToBallsLookup,
                          SpaceInvaderQueryBuilder)
 from .translation_classes import (RotationClassesBuilder, RotationClassesInfo,
                                   TranslationClassesBuilder, TranslationClassesInfo)
+from .cost import (FMMCostModel, FMMTranslationCostModel, make_pde_aware_translation_cost_model,
+                   make_taylor_translation_cost_model)
 
 __all__ = [
     "TorchArrayContext", "make_obj_array",
@@ -36,4 +38,6 @@ __all__ = [
     "LeavesToBallsLookupBuilder", "LeavesToBallsLookup", "SpaceInvaderQueryBuilder",
     "TranslationClassesBuilder", "TranslationClassesInfo", "RotationClassesBuilder",
     "RotationClassesInfo",
+    "FMMCostModel", "FMMTranslationCostModel", "make_pde_aware_translation_cost_model",
+    "make_taylor_translation_cost_model",
 ]

@@ -73,16 +73,25 @@ def broadcast_tree(actx, tree, comm, root=0):
 
 
 def distributed_setup(actx, global_tree, traversal_builder, comm, cost_per_box=None,
-                      merge_close_lists=False):
+                      merge_close_lists=False, level_orders=None, calibration_params=None):
     """The tree/traversal part of ``make_distributed_wrangler``
     (``distributed/__init__.py:156-266``): broadcast the root's global tree, build the
     global traversal on every rank, partition the boxes by cost in DFS order, build the
     rank's local tree and local traversal.
 
-    *cost_per_box* (root only) defaults to ``1 + own source count + own target count``.
+    *cost_per_box* (root only): with *level_orders* (the wrangler's expansion order per level)
+    it is the reference's choice, ``FMMCostModel().cost_per_box`` on the global traversal with
+    unit calibration parameters unless *calibration_params* is given
+    (``distributed/__init__.py:208-230``); otherwise ``1 + own source count + own target count``.
     Returns ``(local_tree, local_trav, src_idx, tgt_idx, global_trav)``."""
     tree = broadcast_tree(actx, global_tree, comm)
     global_trav, _ = traversal_builder(actx, tree)
+    if cost_per_box is None and level_orders is not None and comm.Get_rank() == 0:
+        from ..cost import FMMCostModel
+        if calibration_params is None:
+            calibration_params = FMMCostModel.get_unit_calibration_params()
+        cost_per_box = FMMCostModel().cost_per_box(
+            actx, global_trav, level_orders, dict(calibration_params)).cpu().numpy()
     if cost_per_box is None and comm.Get_rank() == 0:
         cost_per_box = (1.0 + tree.box_source_counts_nonchild.double()
                         + tree.box_target_counts_nonchild.double()).cpu().numpy()

@@ -427,6 +427,35 @@ def test_translation_and_rotation_classes(actx, dims, dtype, n_away):
     assert np.array_equal(got.from_sep_siblings_rotation_class_to_angle, angles)
 
 
+def test_cost_model_against_reference_golden(actx):
+    """FMMCostModel (boxtree/cost.py) against tests/golden/cost_model.json, which holds the output of
+    the reference's own _PythonFMMCostModel run on the same seeded inputs
+    (tests/golden/make_cost_golden.py).  Tolerance: 1e-12 relative (float64 sums of products of
+    integer counts and cost factors, accumulated in a different order)."""
+    import boxtree_b200
+    from tests.golden.make_cost_golden import CALIBRATION, cases, level_to_order
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "cost_model.json")))
+    for name, (src, tkw, vkw) in cases().items():
+        tree, trav = _build(actx, src, tkw, vkw)
+        for factory in ("make_pde_aware_translation_cost_model", "make_taylor_translation_cost_model"):
+            want = golden[f"{name}/{factory}"]
+            model = boxtree_b200.FMMCostModel(getattr(boxtree_b200, factory))
+            lto = level_to_order(tree.nlevels)
+            per_box = model.cost_per_box(actx, trav, lto, dict(CALIBRATION)).cpu().numpy()
+            assert per_box.shape == (want["nboxes"],) and per_box.dtype == np.float64
+            assert np.allclose(per_box[:64], want["per_box_head"], rtol=1e-12, atol=0)
+            assert np.allclose(per_box[::97], want["per_box_every_97th"], rtol=1e-12, atol=0)
+            assert np.isclose(per_box.sum(), want["per_box_sum"], rtol=1e-12, atol=0)
+            per_stage = model.cost_per_stage(actx, trav, lto, dict(CALIBRATION))
+            assert set(per_stage) == set(want["per_stage"])
+            for k, v in want["per_stage"].items():
+                assert np.isclose(per_stage[k], v, rtol=1e-12, atol=0), k
+    unit = boxtree_b200.FMMCostModel.get_unit_calibration_params()
+    est = boxtree_b200.FMMCostModel().estimate_calibration_params(
+        [per_stage], [{k: {"wall_elapsed": 2.0 * v} for k, v in per_stage.items()}])
+    assert set(est) == set(unit) and all(np.isclose(v, 2.0) or v == 0.0 for v in est.values())
+
+
 def test_error_behaviour(actx):
     from boxtree_b200 import FMMTraversalBuilder, MaxLevelsExceeded, TreeBuilder
     tb = TreeBuilder(actx)
