@@ -152,3 +152,20 @@ def test_sharded_setup_matches_oracle(actx, name, nranks):
         gs, gl = gtrav.same_level_non_well_sep_boxes_starts, gtrav.same_level_non_well_sep_boxes_lists
         for b in need[:: max(1, len(need) // 500)]:
             assert np.array_equal(wl[ws[b]:ws[b + 1]], gl[gs[b]:gs[b + 1]]), (r, b)
+
+
+def test_distributed_setup_with_cost_model_weights(actx):
+    """distributed_setup with the reference's choice of partition weights
+    (distributed/__init__.py:208-230): FMMCostModel().cost_per_box with unit calibration
+    parameters.  One rank: the local tree must hold every particle, the local traversal must be
+    the global one."""
+    from boxtree_b200 import FMMTraversalBuilder, TreeBuilder
+    from boxtree_b200 import distributed as bd
+    src = normal_particles(20000, 3, np.float64)
+    tree, _ = TreeBuilder(actx)(actx, [actx.from_numpy(s) for s in src], max_particles_in_box=30)
+    tg = FMMTraversalBuilder(actx)
+    level_orders = np.full(tree.nlevels, 4, np.int64)
+    lt, ltrav, sidx, tidx, gtrav = bd.distributed_setup(actx, tree, tg, bd.SingleProcessComm(),
+                                                        level_orders=level_orders)
+    assert int(lt.sources[0].shape[0]) == 20000 and int(lt.targets[0].shape[0]) == 20000
+    assert not trav_mismatches(actx.to_numpy(gtrav), actx.to_numpy(ltrav))
