@@ -174,8 +174,9 @@ __device__ __forceinline__ bool gen_list1(const TreeView<T, DIM>& t, const T* ra
 // row); the defaults are the faster choice measured on B200 (profiles/README.md).
 constexpr int kModeColl = 1, kModeList1 = 2, kModeList3 = 4, kModeList3Auto = 8,
               kModeList2Count = 16, kModeList2Fill = 32, kModeCollTopDown = 64, kModeFused13 = 128,
-              kModeNearCapZero = 256,   // testing: rows with near-field boxes above their level go heavy
-              kModeHeavySort = 512;     // heavy rows of the fused walk by radix sort instead of the position map
+              kModeNearCapZero = 256;   // testing: rows with near-field boxes above their level go heavy
+// (bit 512, heavy rows by radix sort instead of the position map, is read by the host:
+//  it leaves bt_heavy_ws.hrow_base NULL)
 int g_walk_mode = kModeList1 | kModeList3Auto | kModeList2Fill | kModeCollTopDown | kModeFused13;
 
 struct CoopFrame { int parent; unsigned bits; };
