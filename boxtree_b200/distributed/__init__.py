@@ -147,9 +147,13 @@ def sharded_setup(actx, tree, traversal_builder, comm, cost_per_box=None,
     masks, _partial, need = get_box_masks_sharded(actx, tree, responsible, traversal_builder)
     local_tree, src_idx, tgt_idx = generate_local_tree(
         actx, SimpleNamespace(tree=tree), responsible, comm, box_masks=masks)
+    # same box geometry, source flags and colleague rows as the partial traversal: its depth-first
+    # ranks, colleagues and list-2 masks are reused
+    shared = getattr(traversal_builder, "last_shared", None)
     local_trav, _ = traversal_builder(
         actx, local_tree, source_boxes_mask=local_tree.responsible_boxes_mask,
-        source_parent_boxes_mask=local_tree.ancestor_mask, _colleague_row_mask=need)
+        source_parent_boxes_mask=local_tree.ancestor_mask, _colleague_row_mask=need, _shared=shared)
+    traversal_builder.last_shared = None
     if merge_close_lists and local_tree.targets_have_extent:
         local_trav = local_trav.merge_close_lists(actx)
     return local_tree, local_trav, src_idx, tgt_idx

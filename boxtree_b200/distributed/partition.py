@@ -207,6 +207,6 @@ def get_box_masks_sharded(actx, tree, responsible_boxes_list, traversal_builder)
         partial_tree = dataclasses.replace(tree, box_flags=flags)
         # lists 1 / 3 are only read on responsible rows (partition.py:214-218, 287-295)
         partial_trav, _ = traversal_builder(actx, partial_tree, _colleague_row_mask=need,
-                                            _list13_row_mask=responsible)
+                                            _list13_row_mask=responsible, _keep_shared=True)
         masks = _masks_from_traversal(actx, lib, partial_trav, responsible, ancestors)
     return masks, partial_trav, need

@@ -273,6 +273,7 @@ class FMMTraversalBuilder:
         self.from_sep_smaller_crit = from_sep_smaller_crit
         self._lib = _cabi.load()
         self.last_stats: dict = {}
+        self.last_shared: dict | None = None
 
     def _resolve_crit(self, extent_norm, sources_have_extent, targets_have_extent) -> str:
         # traversal.py:1776-1805
@@ -296,7 +297,8 @@ class FMMTraversalBuilder:
     def __call__(self, actx: TorchArrayContext, tree: Tree | TreeOfBoxes, wait_for=None,
                  debug: bool = False, _from_sep_smaller_min_nsources_cumul: int | None = None,
                  source_boxes_mask=None, source_parent_boxes_mask=None,
-                 _colleague_row_mask=None, _list13_row_mask=None):
+                 _colleague_row_mask=None, _list13_row_mask=None, _keep_shared=False,
+                 _shared=None):
         """See ``boxtree/traversal.py:1969-1990``.
 
         :arg _colleague_row_mask: (internal, used by the sharded distributed setup) int8
@@ -304,6 +306,11 @@ class FMMTraversalBuilder:
             with a non-zero entry -- the caller guarantees that no other row is read.
         :arg _list13_row_mask: (internal) likewise for the rows of lists 1 and 3 (and list 3
             close): rows of target boxes with a zero entry are left empty.
+        :arg _keep_shared: (internal) keep the flag-independent intermediates of this call
+            (depth-first ranks, transposed child table, colleagues, list-2 counts and masks) in
+            ``self.last_shared``.
+        :arg _shared: (internal) such a dict from a call on the SAME box geometry, source flags
+            and ``_colleague_row_mask`` (the sharded setup's second traversal): reused as is.
 
         :returns: ``(trav, event)``; *event* is a :class:`torch.cuda.Event`.
         """
@@ -391,9 +398,13 @@ class FMMTraversalBuilder:
             if int(box_centers.shape[-1]) != tv.aligned_nboxes:
                 raise ValueError("box_centers and box_child_ids must share their padded length")
             # scratch copy of the child table with the children of a box side by side
-            child_t = actx.empty(max(tv.aligned_nboxes, 1) * 2 ** dimensions, np.int32)
-            check(lib.bt_trav_transpose_children(dimensions, tv.aligned_nboxes, dptr(box_child_ids),
-                                                 dptr(child_t), sh), "bt_trav_transpose_children")
+            if _shared is not None:
+                child_t = _shared["child_t"]
+            else:
+                child_t = actx.empty(max(tv.aligned_nboxes, 1) * 2 ** dimensions, np.int32)
+                check(lib.bt_trav_transpose_children(dimensions, tv.aligned_nboxes,
+                                                     dptr(box_child_ids), dptr(child_t), sh),
+                      "bt_trav_transpose_children")
             tv.box_child_ids_t = dptr(child_t)
 
             # {{{ b1/b2: box lists and their level starts (traversal.py:2054-2124)
@@ -447,11 +458,15 @@ class FMMTraversalBuilder:
 
             # pre-order rank of every box: orders colleagues and the entries of heavy rows
             budget = int(os.environ.get("BT_WALK_BUDGET", DEFAULT_WALK_BUDGET))
-            subtree_size = actx.empty(max(nboxes, 1), np.int32)
-            dfs_rank = actx.empty(max(nboxes, 1), np.int32)
-            check(lib.bt_trav_dfs_rank(dimensions, nboxes, tv.aligned_nboxes, nlevels,
-                                       dptr(level_start_box_nrs), dptr(box_child_ids),
-                                       dptr(subtree_size), dptr(dfs_rank), sh), "bt_trav_dfs_rank")
+            if _shared is not None:
+                subtree_size, dfs_rank = _shared["subtree_size"], _shared["dfs_rank"]
+            else:
+                subtree_size = actx.empty(max(nboxes, 1), np.int32)
+                dfs_rank = actx.empty(max(nboxes, 1), np.int32)
+                check(lib.bt_trav_dfs_rank(dimensions, nboxes, tv.aligned_nboxes, nlevels,
+                                           dptr(level_start_box_nrs), dptr(box_child_ids),
+                                           dptr(subtree_size), dptr(dfs_rank), sh),
+                      "bt_trav_dfs_rank")
 
             # {{{ b3: same-level non-well-separated boxes (traversal.py:2135-2141)
 
@@ -464,7 +479,12 @@ class FMMTraversalBuilder:
                 topdown = False
             coll_starts = actx.empty(nboxes + 1, np.int32)
             l2_count_by_box = xflags = None
-            if topdown:
+            reuse_coll = _shared is not None and _shared.get("topdown") == topdown
+            if reuse_coll:
+                coll_starts, coll_lists = _shared["coll"]
+                l2_count_by_box, xflags = _shared["l2_count_by_box"], _shared["xflags"]
+                l2_masks, mask_words = _shared["l2_masks"], _shared["mask_words"]
+            elif topdown:
                 # level by level from the parent's colleagues; list-2 counts come for free
                 stride = (2 * int(self.well_sep_is_n_away) + 1) ** dimensions - 1
                 staging = actx.empty(max(nboxes, 1) * stride, np.int32)
@@ -486,14 +506,21 @@ class FMMTraversalBuilder:
                     check(lib.bt_trav_build_list(dcode, 0, phase, C.byref(tv), C.byref(a_coll),
                                                  nboxes, dptr(coll_starts), dptr(lists), None,
                                                  None, dptr(totals), sh), "colleagues")
-            colleagues(0, None)
-            total = int(_read_i64(actx, totals)[0])
-            _check_int32(total, "same_level_non_well_sep_boxes")
-            coll_lists = actx.empty(total, np.int32)
-            colleagues(1, coll_lists)
-            if topdown:
-                del staging
+            if not reuse_coll:
+                colleagues(0, None)
+                total = int(_read_i64(actx, totals)[0])
+                _check_int32(total, "same_level_non_well_sep_boxes")
+                coll_lists = actx.empty(total, np.int32)
+                colleagues(1, coll_lists)
+                if topdown:
+                    del staging
             coll = (coll_starts, coll_lists)
+            if _keep_shared:
+                self.last_shared = {
+                    "child_t": child_t, "subtree_size": subtree_size, "dfs_rank": dfs_rank,
+                    "topdown": topdown, "coll": coll, "l2_count_by_box": l2_count_by_box,
+                    "xflags": xflags, "l2_masks": l2_masks if topdown else None,
+                    "mask_words": mask_words if topdown else 0}
 
             # }}}
 
@@ -651,7 +678,8 @@ class FMMTraversalBuilder:
                     dimensions, ntp, dptr(target_or_target_parent_boxes), dptr(box_parent_ids),
                     dptr(coll_starts), dptr(coll_lists), dptr(child_t), dptr(l2_masks), mask_words,
                     dptr(l2_starts), dptr(l2_lists), sh), "list 2 fill")
-                del l2_masks
+                if not _keep_shared:
+                    del l2_masks
             else:
                 check(lib.bt_trav_build_list(dcode, 2, 1, C.byref(tv), C.byref(a2), ntp,
                                              dptr(l2_starts), dptr(l2_lists), None, None, None, sh),
