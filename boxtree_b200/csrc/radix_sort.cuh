@@ -37,7 +37,42 @@ struct RsSmem {
     long long gbase[kRsRadix];
     unsigned scan_tmp[kRsWarps];
     int tile;
+    unsigned long long mbar;       // mbarrier of the TMA bulk load of the tile's keys
 };
+
+// 1-D TMA: cp.async.bulk global -> shared, completion counted in bytes on an mbarrier
+#ifndef BT_RS_TMA
+#define BT_RS_TMA 1
+#endif
+__device__ __forceinline__ unsigned smem_u32(const void* p)
+{ return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, unsigned bytes,
+                                            unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "BT_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra BT_MBAR_DONE;\n"
+        "bra BT_MBAR_WAIT;\n"
+        "BT_MBAR_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
 
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p)
 {
@@ -110,7 +145,10 @@ rs_onesweep_kernel(const unsigned long long* __restrict__ kin, unsigned long lon
     RsSmem& sm = *reinterpret_cast<RsSmem*>(rs_smem_raw);
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
 
-    if (t == 0) sm.tile = (int)atomicAdd(ticket, 1u);
+    if (t == 0) {
+        sm.tile = (int)atomicAdd(ticket, 1u);
+        if (BT_RS_TMA) mbar_init(&sm.mbar, 1);
+    }
     for (int i = t; i < kRsWarps * kRsRadix; i += kRsThreads) (&sm.whist[0][0])[i] = 0;
     __syncthreads();
     const int tile = sm.tile;
@@ -118,14 +156,25 @@ rs_onesweep_kernel(const unsigned long long* __restrict__ kin, unsigned long lon
     if (base >= n) return;
     const int cnt = (int)((n - base < kRsTile) ? (n - base) : kRsTile);
 
-    // ---- load keys, warp-striped: warp w owns [w*512, (w+1)*512) of the tile
+    // ---- load keys, warp-striped: warp w owns [w*512, (w+1)*512) of the tile.  A full tile whose
+    //      32 KB of keys are 16-byte aligned arrives by ONE TMA bulk copy into sm.keys (which is
+    //      only overwritten by the scatter after the ranking barrier); other tiles use plain loads
     unsigned long long key[kRsItems];
     unsigned short rank[kRsItems];
     const int wbase = warp * (32 * kRsItems);
+    const bool by_tma = BT_RS_TMA && cnt == kRsTile &&
+                        ((reinterpret_cast<uintptr_t>(kin + base) & 15u) == 0);
+    if (by_tma) {
+        if (t == 0) tma_load_1d(sm.keys, kin + base, kRsTile * (unsigned)sizeof(unsigned long long), &sm.mbar);
+        mbar_wait(&sm.mbar, 0);
 #pragma unroll
-    for (int j = 0; j < kRsItems; ++j) {
-        const int idx = wbase + j * 32 + lane;
-        key[j] = (idx < cnt) ? ld_stream_u64(kin + base + idx) : ~0ull;
+        for (int j = 0; j < kRsItems; ++j) key[j] = sm.keys[wbase + j * 32 + lane];
+    } else {
+#pragma unroll
+        for (int j = 0; j < kRsItems; ++j) {
+            const int idx = wbase + j * 32 + lane;
+            key[j] = (idx < cnt) ? ld_stream_u64(kin + base + idx) : ~0ull;
+        }
     }
 
     // ---- rank inside the warp, round by round (stable)
