@@ -386,6 +386,52 @@ def run_ours(args):
     e2e_value = npoints_job / (ms_e2e / e2e_steps * 1e-3) / 1e6
     del o
 
+    # the same, double buffered: the H2D copy of step k+1 (copy stream) overlaps the build of step
+    # k; every step still copies its own inputs from pinned memory and reads its summary back
+    e2e_pipelined = None
+    if not sharded:
+        copy_stream = torch.cuda.Stream(device=device)
+        main_stream = actx.stream
+
+        def upload():
+            with torch.cuda.stream(copy_stream):
+                g = [x.to(device, non_blocking=True) for x in hsrc]
+                gk = {k: (v.to(device, non_blocking=True) if isinstance(v, torch.Tensor) else
+                          [x.to(device, non_blocking=True) for x in v] if k == "targets" else v)
+                      for k, v in hkw.items()}
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return g, gk, ev
+
+        def run_pipelined(steps):
+            nxt = upload()
+            last = None
+            for k in range(steps):
+                g, gk, ev = nxt
+                main_stream.wait_event(ev)
+                if k + 1 < steps:
+                    nxt = upload()
+                tree, _ = tb(actx, g, **gk)
+                trav, _ = tg(actx, tree)
+                last = torch.cat([tree.level_start_box_nrs.to(torch.int64),
+                                  trav.from_sep_siblings_starts[-1:].to(torch.int64),
+                                  trav.neighbor_source_boxes_starts[-1:].to(torch.int64)]).cpu()
+                used = list(g)                     # the buffers were allocated on the copy stream
+                for v in gk.values():
+                    used += [v] if isinstance(v, torch.Tensor) else (v if isinstance(v, list) else [])
+                for t_ in used:
+                    t_.record_stream(main_stream)
+                del tree, trav
+            return last
+
+        run_pipelined(2)
+        psteps = max(2, min(args.steps, 5))
+        ms_p, _ = timed(lambda: run_pipelined(psteps), 1)
+        e2e_pipelined = {"value": npoints_job / (ms_p / psteps * 1e-3) / 1e6, "unit": "Mpoints/s",
+                         "steps": psteps, "ms_per_step": ms_p / psteps,
+                         "how": "double buffered: H2D of step k+1 on a copy stream during the build "
+                                "of step k; every step copies its own inputs and reads its summary"}
+
     # dominant kernel, timed live with CUDA events on the launching stream
     roofline = None
     prof_steps = 2
@@ -460,6 +506,8 @@ def run_ours(args):
         }
         if distributed is not None:
             line["distributed"] = distributed
+        if e2e_pipelined is not None:
+            line["e2e"]["pipelined"] = e2e_pipelined
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
