@@ -91,19 +91,19 @@ def make_inputs(case):
         for ax in range(dims):
             src[ax][0] = 1.0
     elif case.get("uniform"):
-        src = uniform_particles(n, dims, dt, seed=15)
+        src = uniform_particles(n, dims, dt, seed=case.get("seed", 15))
     else:
-        src = normal_particles(n, dims, dt, seed=15)
+        src = normal_particles(n, dims, dt, seed=case.get("seed", 15))
     kw = dict(case["tree"])
     if case.get("user_bbox"):
         lo, hi = case["user_bbox"]
         kw["bbox"] = np.array([[lo, hi]] * dims, dtype=dt)
     tgt = None
     if case.get("ntargets"):
-        tgt = normal_particles(case["ntargets"], dims, dt, seed=18)
+        tgt = normal_particles(case["ntargets"], dims, dt, seed=case.get("seed", 15) + 3)
         kw["targets"] = tgt
         if case.get("radii"):
-            rng = np.random.default_rng(13)
+            rng = np.random.default_rng(case.get("seed", 15) - 2)
             scale, lo = case.get("radii_scale", (0.05, -10))
             kw["target_radii"] = (scale * 2 ** rng.uniform(lo, 0, case["ntargets"])).astype(dt)
     if case.get("weights"):

@@ -456,6 +456,23 @@ def test_cost_model_against_reference_golden(actx):
     assert set(est) == set(unit) and all(np.isclose(v, 2.0) or v == 0.0 for v in est.values())
 
 
+def test_random_parity_sweep(actx, builders):
+    """Ten seconds of tests/random_sweep.py (random shapes, options and seeds; ~600 cases): every
+    array bit for bit.  A 140 s run over two master seeds (9210 cases) is recorded in
+    profiles/r01_random_sweep.txt."""
+    import time
+    from tests.random_sweep import random_case
+    tb, travs = builders
+    rng = np.random.default_rng(7)
+    t0, n = time.time(), 0
+    while time.time() - t0 < 10.0:
+        case = random_case(rng)
+        bad = run_case(case, actx, tb, travs)
+        n += 1
+        assert not bad, ({k: v for k, v in case.items() if not k.startswith("_")}, bad[:6])
+    assert n > 50
+
+
 def test_error_behaviour(actx):
     from boxtree_b200 import FMMTraversalBuilder, MaxLevelsExceeded, TreeBuilder
     tb = TreeBuilder(actx)
