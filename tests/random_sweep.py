@@ -12,10 +12,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tests.gpu_sweep import run_case  # noqa: E402
 
 
-def random_case(rng):
+def random_case(rng, nmax=6000):
     dims = int(rng.integers(1, 4))
     dt = [np.float64, np.float32][int(rng.integers(0, 2))]
-    n = int(rng.integers(50, 6000))
+    n = int(rng.integers(50, nmax))
     case = dict(dims=dims, dtype=dt, n=n, seed=int(rng.integers(100, 10 ** 6)), name="random")
     tree = {"max_particles_in_box": int(rng.integers(3, 40))}
     kind = ["adaptive", "adaptive-level-restricted", "non-adaptive"][int(rng.choice(3, p=[0.55, 0.4, 0.05]))]
@@ -27,7 +27,7 @@ def random_case(rng):
     if rng.random() < 0.2:
         case["uniform"] = True
     if rng.random() < 0.6:
-        case["ntargets"] = int(rng.integers(50, 6000))
+        case["ntargets"] = int(rng.integers(50, nmax))
         if rng.random() < 0.7:
             case["radii"] = True
             case["radii_scale"] = (float(10 ** rng.uniform(-2.5, 0.3)), int(rng.integers(-12, -1)))
@@ -45,12 +45,13 @@ def main():
     from boxtree_b200 import TorchArrayContext, TreeBuilder
     master = int(sys.argv[1]) if len(sys.argv) > 1 else 1
     budget = float(sys.argv[2]) if len(sys.argv) > 2 else 60.0
+    nmax = int(sys.argv[3]) if len(sys.argv) > 3 else 6000
     rng = np.random.default_rng(master)
     actx = TorchArrayContext()
     tb, travs = TreeBuilder(actx), {}
     t0, ncase, nbad = time.time(), 0, 0
     while time.time() - t0 < budget:
-        case = random_case(rng)
+        case = random_case(rng, nmax)
         ncase += 1
         try:
             bad = run_case(case, actx, tb, travs)
