@@ -17,7 +17,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle.traversal import build_traversal as oracle_traversal  # noqa: E402
 from oracle.tree_build import MaxLevelsExceeded as OracleMaxLevels  # noqa: E402
 from oracle.tree_build import build_tree as oracle_tree  # noqa: E402
-from tests.parity_util import (normal_particles, trav_mismatches, tree_mismatches,  # noqa: E402
+from tests.parity_util import (digest_mismatches, normal_particles, trav_digests,  # noqa: E402
+                               trav_mismatches, tree_digests, tree_mismatches,
                                uniform_particles)
 
 
@@ -112,7 +113,9 @@ def make_inputs(case):
     return src, kw
 
 
-def run_case(case, actx, tb, travs):
+def run_case(case, actx, tb, travs, ref_digests=None):
+    """CUDA path vs the oracle's arrays, and -- when *ref_digests* (the case's entry of
+    ``tests/golden/refexec_digests.json``) is given -- vs the digests of the reference's own run."""
     from boxtree_b200 import FMMTraversalBuilder, MaxLevelsExceeded
     src, kw = make_inputs(case)
     t0 = time.time()
@@ -136,6 +139,9 @@ def run_case(case, actx, tb, travs):
         return ["oracle raised MaxLevelsExceeded, CUDA path did not"]
     got_tree = actx.to_numpy(got_tree_dev)
     bad = ["tree." + b for b in tree_mismatches(ref_tree, got_tree)]
+    if ref_digests is not None:
+        bad += ["reference.tree." + b
+                for b in digest_mismatches(ref_digests["tree"], tree_digests(got_tree))]
     if case.get("trav", {}) is not None and not bad:
         tkw = dict(case.get("trav") or {})
         ctor = {k: tkw.pop(k) for k in ("well_sep_is_n_away", "from_sep_smaller_crit")
@@ -148,6 +154,9 @@ def run_case(case, actx, tb, travs):
         case["_trav_stats"] = dict(travs[key].last_stats)
         got_trav = actx.to_numpy(got_trav_dev)
         bad += ["trav." + b for b in trav_mismatches(ref_trav, got_trav)]
+        if ref_digests is not None:
+            bad += ["reference.trav." + b
+                    for b in digest_mismatches(ref_digests["trav"], trav_digests(got_trav))]
     case["_info"] = (f"nboxes={ref_tree.nboxes} nlevels={ref_tree.nlevels} "
                      f"{time.time() - t0:.2f}s")
     return bad

@@ -107,6 +107,81 @@ def trav_mismatches(ref, got):
     return bad
 
 
+# ---- digests ---------------------------------------------------------------
+
+def _digest(*arrays):
+    import hashlib
+    h = hashlib.sha256()
+    for a in arrays:
+        a = np.ascontiguousarray(a)
+        h.update(f"{a.dtype.str}{a.shape}".encode())
+        h.update(a.tobytes())
+    return h.hexdigest()[:12]
+
+
+def tree_digests(tree):
+    """Short sha256 per ``Tree`` field (dtype, shape and bytes), the fields and slicing of
+    ``tree_mismatches``.  Used to compare against reference-generated values that cannot travel
+    to the GPU box as arrays (``tests/golden/refexec_digests.json``)."""
+    nb = tree.nboxes
+    out = {"nboxes": int(nb), "nlevels": int(tree.nlevels),
+           "root_extent": _digest(np.asarray(tree.root_extent)),
+           "bounding_box": _digest(*[np.asarray(b) for b in tree.bounding_box])}
+    for name in TREE_INT_FIELDS:
+        a = np.asarray(getattr(tree, name))
+        out[name] = _digest(a[:nb] if name.startswith("box_") else a)
+    for name in TREE_PADDED_INT_FIELDS + TREE_PADDED_FLOAT_FIELDS:
+        out[name] = _digest(np.asarray(getattr(tree, name)))
+    for name in ("sources", "targets"):
+        out[name] = _digest(*[np.asarray(x) for x in getattr(tree, name)])
+    for name in ("source_radii", "target_radii"):
+        v = getattr(tree, name)
+        out[name] = None if v is None else _digest(np.asarray(v))
+    return out
+
+
+def trav_digests(trav):
+    out = {}
+    for name in TRAV_FIELDS:
+        v = getattr(trav, name)
+        out[name] = None if v is None else _digest(np.asarray(v))
+    by_level = []
+    for lev, bl in enumerate(trav.from_sep_smaller_by_level):
+        by_level.append(_digest(
+            np.asarray(bl.starts), np.asarray(bl.lists), np.asarray(bl.nonempty_indices),
+            np.asarray(bl.compressed_indices),
+            np.asarray([int(bl.count), int(bl.num_nonempty_lists)]),
+            np.asarray(trav.target_boxes_sep_smaller_by_source_level[lev])))
+    out["from_sep_smaller_by_level"] = by_level
+    return out
+
+
+def digest_mismatches(ref: dict, got: dict):
+    return [k for k in ref if ref[k] != got.get(k)]
+
+
+def reference_case_key(case, quick):
+    """Key of a ``tests/gpu_sweep.py`` case in ``tests/golden/refexec_digests.json``."""
+    return (f"{'quick' if quick else 'full'}:{case['dims']}d-{np.dtype(case['dtype']).name}-"
+            f"{case['name']}-n{case['n']}")
+
+
+_REFERENCE_DIGESTS = None
+
+
+def reference_digests():
+    """Per-field digests of what the REFERENCE ITSELF produced for the sweep cases
+    (``tests/golden/make_refexec_golden.py``)."""
+    global _REFERENCE_DIGESTS
+    if _REFERENCE_DIGESTS is None:
+        import json
+        import os
+        path = os.path.join(os.path.dirname(__file__), "golden", "refexec_digests.json")
+        with open(path) as f:
+            _REFERENCE_DIGESTS = json.load(f)
+    return _REFERENCE_DIGESTS
+
+
 # ---- input recipes ----------------------------------------------------------
 
 def normal_particles(n, dims, dtype, seed=15):

@@ -1,0 +1,150 @@
+"""Drivers: run the reference's ``FMMTraversalBuilder`` / ``TreeBuilder`` (unmodified host code and
+kernel text, see ``tests/refexec/__init__.py``) and return plain-numpy results."""
+from __future__ import annotations
+
+import dataclasses
+import types
+
+import numpy as np
+
+from . import reference_modules
+
+TRAV_ARRAYS = (
+    "source_boxes", "target_boxes", "source_parent_boxes", "target_or_target_parent_boxes",
+    "level_start_source_box_nrs", "level_start_target_box_nrs",
+    "level_start_source_parent_box_nrs", "level_start_target_or_target_parent_box_nrs",
+    "same_level_non_well_sep_boxes_starts", "same_level_non_well_sep_boxes_lists",
+    "neighbor_source_boxes_starts", "neighbor_source_boxes_lists",
+    "from_sep_siblings_starts", "from_sep_siblings_lists",
+    "from_sep_close_smaller_starts", "from_sep_close_smaller_lists",
+    "from_sep_bigger_starts", "from_sep_bigger_lists",
+    "from_sep_close_bigger_starts", "from_sep_close_bigger_lists",
+)
+
+_TREE_DEVICE_FIELDS = (
+    "level_start_box_nrs", "box_source_starts", "box_source_counts_nonchild",
+    "box_source_counts_cumul", "box_target_starts", "box_target_counts_nonchild",
+    "box_target_counts_cumul", "box_parent_ids", "box_child_ids", "box_centers", "box_levels",
+    "box_flags", "box_source_bounding_box_min", "box_source_bounding_box_max",
+    "box_target_bounding_box_min", "box_target_bounding_box_max",
+)
+
+
+def tree_for_reference(fakecl, tree, actx):
+    """A duck-typed stand-in for ``boxtree.Tree`` holding the arrays of *tree* (anything with the
+    reference's field names, e.g. ``oracle.tree_build.OracleTree``) as device arrays."""
+    ns = types.SimpleNamespace()
+    for name in ("sources_are_targets", "sources_have_extent", "targets_have_extent",
+                 "particle_id_dtype", "box_id_dtype", "coord_dtype", "box_level_dtype",
+                 "root_extent", "stick_out_factor", "extent_norm", "_is_pruned", "dimensions",
+                 "nboxes", "nlevels", "aligned_nboxes", "bounding_box"):
+        if hasattr(tree, name):
+            setattr(ns, name, getattr(tree, name))
+    for name in _TREE_DEVICE_FIELDS:
+        v = getattr(tree, name, None)
+        setattr(ns, name, None if v is None else fakecl.Array(np.ascontiguousarray(v), actx.queue))
+    ns.level_start_box_nrs = np.asarray(tree.level_start_box_nrs)      # host array in the reference
+    return ns
+
+
+def reference_traversal(tree, well_sep_is_n_away=1, from_sep_smaller_crit=None,
+                        _from_sep_smaller_min_nsources_cumul=None,
+                        source_boxes_mask=None, source_parent_boxes_mask=None):
+    """``FMMTraversalBuilder(actx, ...)(actx, tree, ...)`` of ``boxtree/traversal.py:1969-2345``.
+    Returns a namespace of numpy arrays with ``FMMTraversalInfo``'s field names (compare with
+    ``tests.parity_util.trav_mismatches``)."""
+    with reference_modules() as fakecl:
+        import boxtree.traversal as trav_mod
+        return _reference_traversal(
+            fakecl, trav_mod, tree, well_sep_is_n_away, from_sep_smaller_crit,
+            _from_sep_smaller_min_nsources_cumul, source_boxes_mask, source_parent_boxes_mask)
+
+
+def _reference_traversal(fakecl, trav_mod, tree, well_sep_is_n_away, from_sep_smaller_crit,
+                         _from_sep_smaller_min_nsources_cumul, source_boxes_mask,
+                         source_parent_boxes_mask):
+    assert trav_mod.__file__.startswith("/root/reference/")
+    actx = fakecl.PyOpenCLArrayContext()
+    rtree = tree_for_reference(fakecl, tree, actx)
+    builder = trav_mod.FMMTraversalBuilder(
+        actx, well_sep_is_n_away=well_sep_is_n_away, from_sep_smaller_crit=from_sep_smaller_crit)
+    kwargs = {}
+    if source_boxes_mask is not None:
+        kwargs["source_boxes_mask"] = fakecl.Array(np.asarray(source_boxes_mask, np.int8))
+    if source_parent_boxes_mask is not None:
+        kwargs["source_parent_boxes_mask"] = fakecl.Array(
+            np.asarray(source_parent_boxes_mask, np.int8))
+    info, _ = builder(
+        actx, rtree,
+        _from_sep_smaller_min_nsources_cumul=_from_sep_smaller_min_nsources_cumul, **kwargs)
+
+    def host(x):
+        return None if x is None else np.asarray(fakecl._unwrap(x))
+
+    out = types.SimpleNamespace(**{name: host(getattr(info, name)) for name in TRAV_ARRAYS})
+    out.well_sep_is_n_away = info.well_sep_is_n_away
+    out.from_sep_smaller_by_level = [
+        types.SimpleNamespace(**{
+            f.name: (getattr(bl, f.name) if f.name in ("count", "num_nonempty_lists")
+                     else host(getattr(bl, f.name)))
+            for f in dataclasses.fields(bl)})
+        for bl in info.from_sep_smaller_by_level]
+    out.target_boxes_sep_smaller_by_source_level = [
+        host(a) for a in info.target_boxes_sep_smaller_by_source_level]
+    return out
+
+
+# {{{ tree build
+
+_TREE_SCALARS = ("sources_are_targets", "sources_have_extent", "targets_have_extent",
+                 "particle_id_dtype", "box_id_dtype", "coord_dtype", "box_level_dtype",
+                 "root_extent", "stick_out_factor", "extent_norm", "_is_pruned")
+_TREE_ARRAYS = _TREE_DEVICE_FIELDS + ("user_source_ids", "sorted_target_ids", "source_radii",
+                                      "target_radii")
+
+
+def reference_tree(particles, **kwargs):
+    """``TreeBuilder(actx)(actx, particles, **kwargs)`` of ``boxtree/tree_build.py:145-1870``,
+    unmodified host code and kernels.  Returns a namespace of numpy arrays with ``Tree``'s field
+    names (plus ``nboxes``, ``nlevels``, ``dimensions``, ``aligned_nboxes``)."""
+    with reference_modules() as fakecl:
+        import boxtree.tree_build as tb_mod
+        assert tb_mod.__file__.startswith("/root/reference/")
+        actx = fakecl.PyOpenCLArrayContext()
+
+        def dev(x):
+            return None if x is None else fakecl.Array(np.array(x, copy=True), actx.queue)
+
+        from pytools import obj_array
+        kw = dict(kwargs)
+        for name in ("source_radii", "target_radii", "refine_weights"):
+            if kw.get(name) is not None:
+                kw[name] = dev(kw[name])
+        if kw.get("targets") is not None:
+            kw["targets"] = obj_array.new_1d([dev(t) for t in kw["targets"]])
+        parts = obj_array.new_1d([dev(p) for p in particles])
+        tree, _ = tb_mod.TreeBuilder(actx)(actx, parts, **kw)
+
+        def host(x):
+            if x is None:
+                return None
+            if isinstance(x, np.ndarray) and x.dtype == object:
+                return [host(v) for v in x]
+            return np.asarray(fakecl._unwrap(x))
+
+        ns = types.SimpleNamespace()
+        for name in _TREE_SCALARS:
+            v = getattr(tree, name)
+            setattr(ns, name, host(v) if isinstance(v, fakecl.Array) else v)
+        for name in _TREE_ARRAYS:
+            setattr(ns, name, host(getattr(tree, name)))
+        ns.sources = host(tree.sources)
+        ns.targets = host(tree.targets)
+        ns.bounding_box = tuple(np.asarray(b) for b in tree.bounding_box)
+        ns.nboxes = int(tree.nboxes)
+        ns.nlevels = int(tree.nlevels)
+        ns.dimensions = int(tree.dimensions)
+        ns.aligned_nboxes = int(tree.aligned_nboxes)
+        return ns
+
+# }}}

@@ -27,8 +27,20 @@ def builders(actx):
 @pytest.mark.parametrize(
     "case", _CASES, ids=[f"{c['dims']}d-{np.dtype(c['dtype']).name}-{c['name']}" for c in _CASES])
 def test_parity_sweep(actx, builders, case):
+    """CUDA path == oracle (arrays) AND == the reference's own run (digests of
+    ``tests/golden/refexec_digests.json``, made by executing /root/reference's TreeBuilder and
+    FMMTraversalBuilder on the CPU, see ``tests/refexec``)."""
+    from tests.parity_util import reference_case_key, reference_digests
     tb, travs = builders
-    bad = run_case(dict(case), actx, tb, travs)
+    ref = reference_digests()[reference_case_key(case, quick=False)]
+    if "error" in ref:
+        # the reference gives up on coincident points; and its level-restriction kernel does not
+        # compile in 1-D (component access on a scalar coord_vec_t), so those cases have no
+        # reference output and are held to the oracle only
+        assert (ref["error"] == "MaxLevelsExceeded" and case.get("expect_max_levels")) or \
+            (case["dims"] == 1 and "lr" in case["name"])
+        ref = None
+    bad = run_case(dict(case), actx, tb, travs, ref_digests=ref)
     assert not bad, bad[:10]
 
 

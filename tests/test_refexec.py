@@ -1,0 +1,201 @@
+"""The oracle pinned against the REFERENCE ITSELF.
+
+``tests/refexec`` executes the reference's ``TreeBuilder.__call__`` and
+``FMMTraversalBuilder.__call__`` -- host code and kernel templates unmodified, from where they lie
+under ``/root/reference`` -- on the CPU, with stand-ins for the third-party modules that are not
+installed (pyopencl, mako, pytools, arraycontext, cgen).  Two kinds of test:
+
+* live (skipped where ``/root/reference`` is absent): the reference runs here and its arrays are
+  compared with the oracle's, bit for bit including dtypes;
+* committed: ``tests/golden/refexec_digests.json`` / ``refexec_*.npz`` hold what the reference
+  produced for every sweep case (``tests/golden/make_refexec_golden.py``); the oracle must
+  reproduce them.  (The CUDA path is held to the same files in ``tests/test_gpu_parity.py``.)
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(__file__))
+
+from oracle.traversal import build_traversal                    # noqa: E402
+from oracle.tree_build import MaxLevelsExceeded, build_tree     # noqa: E402
+from tests.gpu_sweep import make_cases, make_inputs             # noqa: E402
+from tests.parity_util import (digest_mismatches, reference_case_key,  # noqa: E402
+                               reference_digests, trav_digests, trav_mismatches, tree_digests,
+                               tree_mismatches)
+
+import refexec                                                   # noqa: E402
+from refexec.minimako import Template                            # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+needs_reference = pytest.mark.skipif(not refexec.available(),
+                                     reason="/root/reference is not mounted")
+
+
+def _trav_kwargs(case):
+    tkw = dict(case.get("trav") or {})
+    ctor = {k: tkw.pop(k) for k in ("well_sep_is_n_away", "from_sep_smaller_crit") if k in tkw}
+    return {**ctor, **tkw}
+
+
+# {{{ the template renderer
+
+def test_minimako_subset():
+    t = Template(r"""
+<%def name="decl(name, n=2)">
+    int ${name}[${n}];
+</%def>
+## a comment line
+%if flag:
+    ${decl("a")}
+%elif other:
+    nothing
+%else:
+    ${decl("b", n=3)}
+%endif
+%for i in range(2):
+    x${i} = ${ {"k": i}["k"] + 1 };
+%endfor
+<% y = 5 %>
+#define M(a) \
+    (a + ${y})
+100 %% 7
+""", strict_undefined=True)
+    out = t.render(flag=False, other=False)
+    assert "int b[3];" in out and "int a[2]" not in out and "nothing" not in out
+    assert "x0 = 1;" in out and "x1 = 2;" in out
+    assert "#define M(a)     (a + 5)" in out
+    assert "comment" not in out
+    with pytest.raises(NameError):
+        Template("${missing}").render()
+
+# }}}
+
+
+# {{{ live: the reference runs here
+
+_LIVE = [c for c in make_cases(quick=True) if (c["dims"], np.dtype(c["dtype"]).name, c["name"]) in {
+    (2, "float64", "adaptive"), (3, "float32", "lr"), (3, "float64", "src-tgt"),
+    (2, "float32", "weights"), (3, "float64", "ext-l2-static_l2-n2"), (3, "float32", "ext-lr-n1"),
+    (2, "float64", "ext-minsrc"), (3, "float64", "nsep3"), (2, "float64", "coincident"),
+    (3, "float64", "non-adaptive"), (2, "float64", "user-bbox"), (3, "float32", "tiny-guess")}]
+
+
+@needs_reference
+@pytest.mark.parametrize(
+    "case", _LIVE, ids=[f"{c['dims']}d-{np.dtype(c['dtype']).name}-{c['name']}" for c in _LIVE])
+def test_reference_run_matches_oracle(case):
+    from refexec.run import reference_traversal, reference_tree
+    src, kw = make_inputs(case)
+    if case.get("expect_max_levels"):
+        with pytest.raises(MaxLevelsExceeded):
+            build_tree(src, **kw)
+        with pytest.raises(Exception) as ei:
+            reference_tree(src, **kw)
+        assert type(ei.value).__name__ == "MaxLevelsExceeded"
+        return
+    ref_tree = reference_tree(src, **kw)
+    tree = build_tree(src, **kw)
+    assert tree_mismatches(ref_tree, tree) == []
+    if case.get("trav", {}) is None:
+        return
+    tkw = _trav_kwargs(case)
+    # the reference's traversal of the reference's tree vs the oracle's of the oracle's
+    ref_trav = reference_traversal(ref_tree, **tkw)
+    trav = build_traversal(tree, **tkw)
+    assert trav_mismatches(ref_trav, trav) == []
+    assert trav.from_sep_siblings_lists.size > 0
+    # the comparison is not vacuous
+    broken = np.array(trav.neighbor_source_boxes_lists, copy=True)
+    broken[0] ^= 1
+    trav.neighbor_source_boxes_lists = broken
+    assert trav_mismatches(ref_trav, trav) == ["neighbor_source_boxes_lists"]
+
+
+@needs_reference
+def test_reference_run_with_box_masks():
+    """``source_boxes_mask`` / ``source_parent_boxes_mask`` (the distributed code's entry)."""
+    from refexec.run import reference_traversal
+    rng = np.random.default_rng(5)
+    src = [rng.standard_normal(3000) for _ in range(3)]
+    tree = build_tree(src, max_particles_in_box=20)
+    sm = (rng.random(tree.nboxes) < 0.6).astype(np.int8)
+    pm = (rng.random(tree.nboxes) < 0.7).astype(np.int8)
+    ref = reference_traversal(tree, source_boxes_mask=sm, source_parent_boxes_mask=pm)
+    got = build_traversal(tree, source_boxes_mask=sm, source_parent_boxes_mask=pm)
+    assert trav_mismatches(ref, got) == []
+
+# }}}
+
+
+# {{{ committed outputs of the reference
+
+_QUICK = make_cases(quick=True)
+
+
+@pytest.mark.parametrize(
+    "case", _QUICK, ids=[f"{c['dims']}d-{np.dtype(c['dtype']).name}-{c['name']}" for c in _QUICK])
+def test_oracle_matches_reference_digests(case):
+    ref = reference_digests()[reference_case_key(case, quick=True)]
+    src, kw = make_inputs(case)
+    if "error" in ref:
+        assert ref["error"] == "MaxLevelsExceeded"
+        with pytest.raises(MaxLevelsExceeded):
+            build_tree(src, **kw)
+        return
+    tree = build_tree(src, **kw)
+    assert digest_mismatches(ref["tree"], tree_digests(tree)) == []
+    if "trav" in ref:
+        trav = build_traversal(tree, **_trav_kwargs(case))
+        assert digest_mismatches(ref["trav"], trav_digests(trav)) == []
+
+
+def test_reference_digests_cover_both_sweeps():
+    d = reference_digests()
+    for quick in (True, False):
+        for case in make_cases(quick):
+            entry = d[reference_case_key(case, quick)]
+            if case.get("expect_max_levels"):
+                assert entry == {"error": "MaxLevelsExceeded"}
+            elif case["dims"] == 1 and "lr" in case["name"]:
+                # boxtree/tree_build_kernels.py:825-915 writes `box_center.x` on what is a scalar
+                # in 1-D: the reference cannot build 1-D level-restricted trees at all
+                assert entry == {"error": "RuntimeError"}
+            else:
+                assert "tree" in entry and (("trav" in entry) == (case.get("trav", {}) is not None))
+
+
+@pytest.mark.parametrize("stem,index", [("refexec_2d_f64_adaptive", (2, "float64", "adaptive")),
+                                        ("refexec_3d_f32_ext_lr", (3, "float32", "ext-lr-n1")),
+                                        ("refexec_3d_f64_nsep2", (3, "float64", "nsep2"))])
+def test_oracle_matches_reference_arrays(stem, index):
+    """Three cases with every array the reference produced."""
+    case = next(c for c in _QUICK if (c["dims"], np.dtype(c["dtype"]).name, c["name"]) == index)
+    ref = np.load(os.path.join(GOLDEN, stem + ".npz"))
+    src, kw = make_inputs(case)
+    tree = build_tree(src, **kw)
+    trav = build_traversal(tree, **_trav_kwargs(case))
+    checked = 0
+    for key in ref.files:
+        kind, name = key.split(".", 1)
+        if kind == "tree":
+            got = getattr(tree, name)
+            got = np.stack(got) if isinstance(got, (list, tuple)) else np.asarray(got)
+        elif name.startswith("from_sep_smaller_by_level."):
+            _, lev, fld = name.split(".")
+            got = np.asarray(getattr(trav.from_sep_smaller_by_level[int(lev)], fld))
+        elif name.startswith("target_boxes_sep_smaller_by_source_level."):
+            got = np.asarray(trav.target_boxes_sep_smaller_by_source_level[int(name.split(".")[1])])
+        else:
+            got = np.asarray(getattr(trav, name))
+        want = ref[key]
+        assert got.dtype == want.dtype and got.shape == want.shape, key
+        assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), key
+        checked += 1
+    assert checked > 40
+
+# }}}
