@@ -1,11 +1,11 @@
-"""Regenerates the committed golden fixtures from the CPU oracle.
+"""Regenerates the committed golden fixtures of the BASELINE configurations (reduced sizes).
 
     python tests/golden/make_golden.py
 
-The reference itself cannot be run in this image (no pyopencl / OpenCL ICD), and its test
-suite holds no golden vectors for this path, so these fixtures pin the ORACLE's output
-(the restatement of the reference algorithm), not the reference's: they guard the oracle
-and the CUDA path against regressions and let GPU tests compare against committed data.
+Where ``/root/reference`` is mounted (this container) the arrays come from the REFERENCE ITSELF:
+its ``TreeBuilder`` and ``FMMTraversalBuilder`` executed on the CPU through ``tests/refexec``
+(host code and kernel text unmodified; pyopencl's kernel-launch classes restated).  The oracle
+must reproduce every byte, or the script stops.  Elsewhere the script falls back to the oracle.
 
 * ``config1_2d_1e4.npz``: every Tree / FMMTraversalInfo array of BASELINE config 1
   (2-D, 1e4 uniform fp64 particles, max 30 per box, adaptive, sources are targets).
@@ -82,17 +82,34 @@ def digest_cases():
     return cases
 
 
-def main():
-    src, tkw, vkw = digest_cases()["config1_2d_1e4"]
+def produce(src, tkw, vkw):
+    """The reference's own run when it can be executed here, checked against the oracle."""
     tree = build_tree(src, **tkw)
     trav = build_traversal(tree, **vkw)
-    np.savez_compressed(os.path.join(HERE, "config1_2d_1e4.npz"), **flatten(tree, trav))
+    flat = flatten(tree, trav)
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE)))
+    import refexec
+    if refexec.available():
+        from refexec.run import reference_traversal, reference_tree
+        rtree = reference_tree(src, **tkw)
+        rflat = flatten(rtree, reference_traversal(rtree, **vkw))
+        assert set(rflat) == set(flat)
+        for k in rflat:
+            assert rflat[k].dtype == flat[k].dtype and rflat[k].shape == flat[k].shape, k
+            assert np.array_equal(rflat[k].view(np.uint8), flat[k].view(np.uint8)), k
+        return rtree, rflat, "reference"
+    return tree, flat, "oracle"
+
+
+def main():
+    src, tkw, vkw = digest_cases()["config1_2d_1e4"]
+    _, flat, origin = produce(src, tkw, vkw)
+    np.savez_compressed(os.path.join(HERE, "config1_2d_1e4.npz"), **flat)
     digests = {}
     for name, (src, tkw, vkw) in digest_cases().items():
-        tree = build_tree(src, **tkw)
-        trav = build_traversal(tree, **vkw)
-        digests[name] = {k: digest(v) for k, v in flatten(tree, trav).items()}
-        print(name, "nboxes", tree.nboxes, "nlevels", tree.nlevels)
+        tree, flat, origin = produce(src, tkw, vkw)
+        digests[name] = {k: digest(v) for k, v in flat.items()}
+        print(name, "nboxes", tree.nboxes, "nlevels", tree.nlevels, "from the", origin)
     with open(os.path.join(HERE, "digests.json"), "w") as f:
         json.dump(digests, f, indent=1, sort_keys=True)
 

@@ -156,6 +156,36 @@ def trav_digests(trav):
     return out
 
 
+DIST_MASK_FIELDS = ("responsible_boxes", "ancestor_boxes", "point_src_boxes", "multipole_src_boxes")
+DIST_LOCAL_TREE_FIELDS = (
+    "box_source_starts", "box_source_counts_nonchild", "box_source_counts_cumul",
+    "box_target_starts", "box_target_counts_nonchild", "box_target_counts_cumul", "box_flags",
+    "box_parent_ids", "box_levels", "box_child_ids", "box_to_user_rank_starts",
+    "box_to_user_rank_lists", "responsible_boxes_mask", "ancestor_mask")
+
+
+def distributed_rank_digests(resp, masks, local_tree, src_idx, tgt_idx, local_trav, nboxes):
+    """Digests of one rank's distributed-setup outputs.  *masks*, *local_tree*: mappings
+    field -> numpy array (``sources`` / ``targets``: lists of arrays, ``target_radii`` or None)."""
+    out = {"responsible_boxes_list": _digest(np.asarray(resp)),
+           "src_idx": _digest(np.asarray(src_idx)), "tgt_idx": _digest(np.asarray(tgt_idx))}
+    for f in DIST_MASK_FIELDS:
+        out["mask." + f] = _digest(np.asarray(masks[f]))
+    for f in DIST_LOCAL_TREE_FIELDS:
+        a = np.asarray(local_tree[f])
+        if f in ("box_parent_ids", "box_levels", "box_flags") or f.startswith("box_source") \
+                or f.startswith("box_target"):
+            a = a[:nboxes]
+        out["tree." + f] = _digest(a)
+    out["tree.sources"] = _digest(*[np.asarray(x) for x in local_tree["sources"]])
+    out["tree.targets"] = _digest(*[np.asarray(x) for x in local_tree["targets"]])
+    tr = local_tree.get("target_radii")
+    out["tree.target_radii"] = None if tr is None else _digest(np.asarray(tr))
+    for k, v in trav_digests(local_trav).items():
+        out["trav." + k] = v
+    return out
+
+
 def digest_mismatches(ref: dict, got: dict):
     return [k for k in ref if ref[k] != got.get(k)]
 

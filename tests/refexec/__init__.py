@@ -41,6 +41,18 @@ def reference_modules():
     actx_stub = types.ModuleType("boxtree.array_context")
     actx_stub.dataclass_array_container = lambda cls: cls
     actx_stub.PyOpenCLArrayContext = fakecl.PyOpenCLArrayContext
+    dist_pkg = types.ModuleType("boxtree.distributed")      # its __init__ needs mpi4py: skip it
+    dist_pkg.__path__ = [os.path.join(REFERENCE_ROOT, "boxtree", "distributed")]
+    fakes["boxtree.distributed"] = dist_pkg
+
+    def package_getattr(name):
+        # `from boxtree import Tree, box_flags_enum, ...` of boxtree/__init__.py:26-52
+        for modname in ("boxtree.tree", "boxtree.tree_build", "boxtree.traversal"):
+            mod = importlib.import_module(modname)
+            if hasattr(mod, name):
+                return getattr(mod, name)
+        raise AttributeError(name)
+    pkg.__getattr__ = package_getattr
     fakes["boxtree"] = pkg
     fakes["boxtree.array_context"] = actx_stub
     touched = set(fakes) | {k for k in sys.modules if k == "boxtree" or k.startswith("boxtree.")}

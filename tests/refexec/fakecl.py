@@ -16,6 +16,7 @@ import os
 import re
 import subprocess
 import sys
+import threading
 import types
 from dataclasses import dataclass
 from typing import Any
@@ -108,6 +109,9 @@ class Array:
 
     def reshape(self, *shape, **kw):
         return Array(self._a.reshape(*shape, **kw), self.queue)
+
+    def transpose(self, *axes):
+        return Array(self._a.transpose(*axes), self.queue)
 
     def ravel(self, order="C"):
         return Array(self._a.ravel(order), self.queue)
@@ -496,10 +500,10 @@ def compile_module(source: str):
     key = hashlib.sha256(source.encode() + shim + " ".join(_CXXFLAGS).encode()).hexdigest()[:24]
     so = os.path.join(CACHE_DIR, f"k_{key}.so")
     if not os.path.exists(so):
-        cpp = os.path.join(CACHE_DIR, f"k_{key}.{os.getpid()}.cpp")
+        cpp = os.path.join(CACHE_DIR, f"k_{key}.{os.getpid()}.{threading.get_ident()}.cpp")
         with open(cpp, "w") as f:
             f.write(source)
-        tmp = so + f".tmp{os.getpid()}"
+        tmp = so + f".tmp{os.getpid()}.{threading.get_ident()}"
         proc = subprocess.run(["g++", *_CXXFLAGS, cpp, "-o", tmp], capture_output=True, text=True)
         if proc.returncode != 0:
             raise RuntimeError(f"g++ failed on {cpp}:\n{proc.stderr[:6000]}")
@@ -585,6 +589,9 @@ def _unpack_source(args, type_prefix=""):
 
 # {{{ ListOfListsBuilder (pyopencl.algorithm)
 
+_LIST_BUILDER_LOCK = threading.RLock()
+
+
 @dataclass
 class BuiltList:
     count: int | None = None
@@ -653,6 +660,11 @@ extern "C" void fetch(int k, void *dst) {{
         omit = (ctypes.c_int * len(lists))(*[int(n in omit_lists) for n, _ in lists])
         starts_np = [np.zeros(n_objects + 1, np.int64) for _ in lists]
         starts_ptrs = (ctypes.c_void_p * len(lists))(*[s.ctypes.data for s in starts_np])
+        with _LIST_BUILDER_LOCK:      # the generated module keeps its lists in statics
+            return self._run(queue, n_objects, ptrs, omit, starts_np, starts_ptrs, omit_lists)
+
+    def _run(self, queue, n_objects, ptrs, omit, starts_np, starts_ptrs, omit_lists):
+        lists = self.list_names_and_dtypes
         self.kernel.lib.run(ptrs, ctypes.c_long(n_objects), omit, starts_ptrs)
         index_dtype = np.int32 if n_objects < np.iinfo(np.int32).max else np.int64
         result = {}
@@ -1279,6 +1291,7 @@ def build_modules() -> dict[str, types.ModuleType]:
                   partition=partition, product=product, Record=Record, obj_array=obj_array)
     pytools.__path__ = []
     arraycontext = mod("arraycontext", Array=Array, ArrayContext=ArrayContext,
+                       ArrayOrContainer=object, ArrayOrContainerT=object,
                        PyOpenCLArrayContext=PyOpenCLArrayContext)
     mako = mod("mako")
     mako.__path__ = []

@@ -78,6 +78,10 @@ def _reference_traversal(fakecl, trav_mod, tree, well_sep_is_n_away, from_sep_sm
         actx, rtree,
         _from_sep_smaller_min_nsources_cumul=_from_sep_smaller_min_nsources_cumul, **kwargs)
 
+    return _trav_namespace(fakecl, info)
+
+
+def _trav_namespace(fakecl, info):
     def host(x):
         return None if x is None else np.asarray(fakecl._unwrap(x))
 
@@ -125,6 +129,138 @@ def reference_tree(particles, **kwargs):
         parts = obj_array.new_1d([dev(p) for p in particles])
         tree, _ = tb_mod.TreeBuilder(actx)(actx, parts, **kw)
 
+        return _tree_namespace(fakecl, tree)
+
+
+def _tree_namespace(fakecl, tree):
+    def host(x):
+        if x is None:
+            return None
+        if isinstance(x, np.ndarray) and x.dtype == object:
+            return [host(v) for v in x]
+        return np.asarray(fakecl._unwrap(x))
+
+    ns = types.SimpleNamespace()
+    for name in _TREE_SCALARS:
+        v = getattr(tree, name)
+        setattr(ns, name, host(v) if isinstance(v, fakecl.Array) else v)
+    for name in _TREE_ARRAYS:
+        setattr(ns, name, host(getattr(tree, name)))
+    ns.sources = host(tree.sources)
+    ns.targets = host(tree.targets)
+    ns.bounding_box = tuple(np.asarray(b) for b in tree.bounding_box)
+    ns.nboxes = int(tree.nboxes)
+    ns.nlevels = int(tree.nlevels)
+    ns.dimensions = int(tree.dimensions)
+    ns.aligned_nboxes = int(tree.aligned_nboxes)
+    ns.nsources = int(tree.nsources)
+    ns.ntargets = int(tree.ntargets)
+    return ns
+
+# }}}
+
+
+# {{{ distributed setup
+
+class _World:
+    def __init__(self, size):
+        import threading
+        self.size = size
+        self.barrier = threading.Barrier(size)
+        self.slots = [None] * size
+        self.box = None
+
+
+class ThreadComm:
+    """The handful of mpi4py calls the reference's setup makes, between threads of one process."""
+
+    def __init__(self, world, rank):
+        self.world, self.rank = world, rank
+
+    def Get_rank(self):  # noqa: N802
+        return self.rank
+
+    def Get_size(self):  # noqa: N802
+        return self.world.size
+
+    def Scatter(self, sendbuf, recvbuf, root=0):  # noqa: N802
+        if self.rank == root:
+            self.world.box = np.asarray(sendbuf)
+        self.world.barrier.wait()
+        recvbuf[...] = self.world.box[self.rank]
+        self.world.barrier.wait()
+
+    def Gather(self, sendbuf, recvbuf, root=0):  # noqa: N802
+        self.world.slots[self.rank] = np.array(sendbuf, copy=True)
+        self.world.barrier.wait()
+        if self.rank == root:
+            recvbuf[...] = np.stack(self.world.slots)
+        self.world.barrier.wait()
+
+    def bcast(self, obj, root=0):
+        if self.rank == root:
+            self.world.box = obj
+        self.world.barrier.wait()
+        result = self.world.box
+        self.world.barrier.wait()
+        return result
+
+    def gather(self, obj, root=0):
+        self.world.slots[self.rank] = obj
+        self.world.barrier.wait()
+        result = list(self.world.slots) if self.rank == root else None
+        self.world.barrier.wait()
+        return result
+
+
+_LOCAL_TREE_FIELDS = (
+    "box_source_starts", "box_source_counts_nonchild", "box_source_counts_cumul",
+    "box_target_starts", "box_target_counts_nonchild", "box_target_counts_cumul", "box_flags",
+    "box_parent_ids", "box_levels", "box_child_ids", "box_centers", "source_radii", "target_radii",
+    "box_to_user_rank_starts", "box_to_user_rank_lists", "responsible_boxes_list",
+    "responsible_boxes_mask", "ancestor_mask", "user_source_ids", "sorted_target_ids")
+
+
+def reference_distributed_setup(particles, tree_kwargs, trav_kwargs, nranks, cost_per_box_fn):
+    """The setup half of ``boxtree/distributed/__init__.py:150-265`` with the reference's own
+    ``partition_work`` (partition.py:60-121), ``get_box_masks`` (:124-357), ``generate_local_tree``
+    (local_tree.py:316-495) and ``generate_local_travs`` (local_traversal.py:34-62), one thread
+    per rank.  *cost_per_box_fn(tree namespace)* gives the root rank's cost vector.  Returns
+    ``(global tree, global trav, [per-rank dict])`` as numpy namespaces."""
+    import threading
+    with reference_modules() as fakecl:
+        import boxtree.distributed.local_traversal as lt_mod
+        import boxtree.distributed.local_tree as ltree_mod
+        import boxtree.distributed.partition as part_mod
+        import boxtree.traversal as trav_mod
+        import boxtree.tree_build as tb_mod
+        for m in (lt_mod, ltree_mod, part_mod):
+            assert m.__file__.startswith("/root/reference/")
+        actx = fakecl.PyOpenCLArrayContext()
+        from pytools import obj_array
+
+        def dev(x):
+            return None if x is None else fakecl.Array(np.array(x, copy=True), actx.queue)
+
+        kw = dict(tree_kwargs)
+        for name in ("source_radii", "target_radii", "refine_weights"):
+            if kw.get(name) is not None:
+                kw[name] = dev(kw[name])
+        if kw.get("targets") is not None:
+            kw["targets"] = obj_array.new_1d([dev(t) for t in kw["targets"]])
+        tree, _ = tb_mod.TreeBuilder(actx)(
+            actx, obj_array.new_1d([dev(p) for p in particles]), **kw)
+        ctor = {k: v for k, v in trav_kwargs.items()
+                if k in ("well_sep_is_n_away", "from_sep_smaller_crit")}
+        builder = trav_mod.FMMTraversalBuilder(actx, **ctor)
+        global_trav, _ = builder(actx, tree)
+        global_tree_np = _tree_namespace(fakecl, tree)
+        cost_per_box = cost_per_box_fn(global_tree_np)
+
+        world = _World(nranks)
+        results = [None] * nranks
+        errors = []
+
         def host(x):
             if x is None:
                 return None
@@ -132,19 +268,38 @@ def reference_tree(particles, **kwargs):
                 return [host(v) for v in x]
             return np.asarray(fakecl._unwrap(x))
 
-        ns = types.SimpleNamespace()
-        for name in _TREE_SCALARS:
-            v = getattr(tree, name)
-            setattr(ns, name, host(v) if isinstance(v, fakecl.Array) else v)
-        for name in _TREE_ARRAYS:
-            setattr(ns, name, host(getattr(tree, name)))
-        ns.sources = host(tree.sources)
-        ns.targets = host(tree.targets)
-        ns.bounding_box = tuple(np.asarray(b) for b in tree.bounding_box)
-        ns.nboxes = int(tree.nboxes)
-        ns.nlevels = int(tree.nlevels)
-        ns.dimensions = int(tree.dimensions)
-        ns.aligned_nboxes = int(tree.aligned_nboxes)
-        return ns
+        def rank_main(rank):
+            try:
+                comm = ThreadComm(world, rank)
+                rank_actx = fakecl.PyOpenCLArrayContext()
+                resp = part_mod.partition_work(cost_per_box if rank == 0 else None,
+                                               global_trav, comm)
+                masks = part_mod.get_box_masks(rank_actx, global_trav,
+                                               rank_actx.from_numpy(np.asarray(resp)))
+                local_tree, src_idx, tgt_idx = ltree_mod.generate_local_tree(
+                    rank_actx, global_trav, rank_actx.from_numpy(np.asarray(resp)), comm)
+                local_trav = lt_mod.generate_local_travs(rank_actx, local_tree, builder)
+                out = {"responsible_boxes_list": np.asarray(resp),
+                       "src_idx": host(src_idx), "tgt_idx": host(tgt_idx),
+                       "masks": {f: host(getattr(masks, f)) for f in (
+                           "responsible_boxes", "ancestor_boxes", "point_src_boxes",
+                           "multipole_src_boxes")},
+                       "local_tree": {f: host(getattr(local_tree, f)) for f in _LOCAL_TREE_FIELDS},
+                       "local_trav": _trav_namespace(fakecl, local_trav)}
+                out["local_tree"]["sources"] = host(local_tree.sources)
+                out["local_tree"]["targets"] = host(local_tree.targets)
+                results[rank] = out
+            except BaseException as e:  # noqa: BLE001
+                errors.append(e)
+                world.barrier.abort()
+
+        threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(nranks)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return global_tree_np, _trav_namespace(fakecl, global_trav), results
 
 # }}}

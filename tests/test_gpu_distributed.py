@@ -28,14 +28,7 @@ class FakeComm:
         return np.asarray(rows[self.rank])
 
 
-CASES = {
-    "points": lambda: (normal_particles(20000, 3, np.float64), dict(max_particles_in_box=30), {}),
-    "points2d-f32-2away": lambda: (normal_particles(20000, 2, np.float32),
-                                   dict(max_particles_in_box=30), dict(well_sep_is_n_away=2)),
-    "config3": lambda: (lambda s, t, r: (s, dict(
-        max_particles_in_box=30, targets=t, target_radii=r, stick_out_factor=0.25,
-        extent_norm="linf", kind="adaptive-level-restricted"), {}))(*config3_inputs(20000, 20000)),
-}
+from tests.dist_cases import CASES, box_cost  # noqa: E402
 
 
 @pytest.mark.parametrize("nranks", [1, 3, 4])
@@ -53,8 +46,14 @@ def test_distributed_rows_match_oracle(actx, name, nranks):
     trav, _ = tg(actx, tree)
 
     nb = rtree.nboxes
-    cost = (1.0 + rtree.box_source_counts_nonchild[:nb] + rtree.box_target_counts_nonchild[:nb])
-    cost = cost.astype(np.float64)
+    cost = box_cost(rtree)
+    # what the reference's own distributed setup produced for this case (tests/refexec)
+    import json
+    import os
+    from tests.parity_util import digest_mismatches, distributed_rank_digests
+    with open(os.path.join(os.path.dirname(__file__), "golden",
+                           "refexec_distributed_digests.json")) as f:
+        reference = json.load(f)[f"{name}:{nranks}"]
     want_resp, _ = od.partition_work(cost, rtree, nranks)
     assert np.array_equal(bd.get_box_ids_dfs_order(actx, tree).cpu().numpy(),
                           od.get_box_ids_dfs_order(rtree))
@@ -96,8 +95,20 @@ def test_distributed_rows_match_oracle(actx, name, nranks):
         assert np.array_equal(np.asarray(g.responsible_boxes_list), want_resp[r])
 
         wtrav = od.generate_local_travs(wt, **vkw)
-        gtrav = bd.generate_local_travs(actx, gt, tg)
-        assert not trav_mismatches(wtrav, actx.to_numpy(gtrav)), r
+        gtrav = actx.to_numpy(bd.generate_local_travs(actx, gt, tg))
+        assert not trav_mismatches(wtrav, gtrav), r
+        got_digests = distributed_rank_digests(
+            got_resp[r], {f: getattr(got_masks[r], f).cpu().numpy() for f in (
+                "responsible_boxes", "ancestor_boxes", "point_src_boxes", "multipole_src_boxes")},
+            {**{f: getattr(g, f) for f in (
+                "box_source_starts", "box_source_counts_nonchild", "box_source_counts_cumul",
+                "box_target_starts", "box_target_counts_nonchild", "box_target_counts_cumul",
+                "box_flags", "box_parent_ids", "box_levels", "box_child_ids",
+                "box_to_user_rank_starts", "box_to_user_rank_lists", "responsible_boxes_mask",
+                "ancestor_mask", "sources", "targets")},
+             "target_radii": g.target_radii if rtree.targets_have_extent else None},
+            gsrc_idx.cpu().numpy(), gtgt_idx.cpu().numpy(), gtrav, nb)
+        assert digest_mismatches(reference[r], got_digests) == [], r
     assert ntgt_total == rtree.ntargets
 
 

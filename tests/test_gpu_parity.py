@@ -160,6 +160,34 @@ def test_config2_full_size_parity(actx):
     assert not trav_mismatches(build_traversal(rt), actx.to_numpy(trav))
 
 
+def _full_size_names():
+    with open(os.path.join(GOLDEN, "full_size_digests.json")) as f:
+        return sorted(json.load(f))
+
+
+@pytest.mark.parametrize("name", _full_size_names())
+def test_full_size_matches_reference_run(actx, name):
+    """The bench workloads at FULL size (1e7 points) against the REFERENCE ITSELF: every Tree and
+    FMMTraversalInfo array has the sha256 that the reference's own TreeBuilder and
+    FMMTraversalBuilder produced when executed on the CPU (tests/golden/make_full_size_golden.py,
+    tests/refexec)."""
+    import gc
+    import torch
+    from tests.golden.make_full_size_golden import full_size_cases
+    with open(os.path.join(GOLDEN, "full_size_digests.json")) as f:
+        want = json.load(f)[name]
+    src, tkw, vkw = full_size_cases()[name]()
+    tree, trav = _build(actx, src, tkw, vkw)
+    assert int(tree.nboxes) == want["_nboxes"] and int(tree.nlevels) == want["_nlevels"]
+    flat = flatten(actx.to_numpy(tree), actx.to_numpy(trav))
+    del tree, trav
+    gc.collect()
+    torch.cuda.empty_cache()
+    assert set(flat) == {k for k in want if not k.startswith("_")}
+    bad = [k for k, v in flat.items() if digest(v) != want[k]]
+    assert bad == []
+
+
 def test_config3_properties_full_size(actx):
     """BASELINE config 3 at full size (1e7 points): size-independent properties on device."""
     import torch

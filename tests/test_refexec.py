@@ -132,6 +132,69 @@ def test_reference_run_with_box_masks():
 # }}}
 
 
+# {{{ distributed setup
+
+def _oracle_distributed_digests(src, tkw, vkw, nranks):
+    from oracle import distributed as od
+    from tests.dist_cases import box_cost
+    from tests.parity_util import DIST_LOCAL_TREE_FIELDS, DIST_MASK_FIELDS, distributed_rank_digests
+    tree = build_tree(src, **tkw)
+    trav = build_traversal(tree, **vkw)
+    resp, _ = od.partition_work(box_cost(tree), tree, nranks)
+    masks = [od.get_box_masks(trav, resp[r]) for r in range(nranks)]
+    mp = np.stack([m.multipole_src_boxes for m in masks])
+    out = []
+    for r in range(nranks):
+        lt, src_idx, tgt_idx = od.generate_local_tree(trav, resp[r], mp)
+        fields = {f: (lt.extra[f] if f in lt.extra else getattr(lt, f))
+                  for f in DIST_LOCAL_TREE_FIELDS}
+        fields.update(sources=lt.sources, targets=lt.targets,
+                      target_radii=lt.target_radii if tree.targets_have_extent else None)
+        out.append(distributed_rank_digests(
+            resp[r], {f: getattr(masks[r], f) for f in DIST_MASK_FIELDS}, fields, src_idx, tgt_idx,
+            od.generate_local_travs(lt, **vkw), tree.nboxes))
+    return out
+
+
+@pytest.mark.parametrize("nranks", [1, 3, 4])
+@pytest.mark.parametrize("name", ["points", "points2d-f32-2away", "config3"])
+def test_oracle_distributed_setup_matches_reference_digests(name, nranks):
+    """``tests/golden/refexec_distributed_digests.json``: partition, box masks, local trees,
+    particle indices and local traversals of every rank as the reference's own
+    ``boxtree/distributed`` code produced them."""
+    import json
+    from tests.dist_cases import CASES
+    with open(os.path.join(GOLDEN, "refexec_distributed_digests.json")) as f:
+        want = json.load(f)[f"{name}:{nranks}"]
+    got = _oracle_distributed_digests(*CASES[name](), nranks)
+    assert len(got) == len(want) == nranks
+    for r in range(nranks):
+        assert digest_mismatches(want[r], got[r]) == [], r
+
+
+@needs_reference
+def test_reference_distributed_setup_live():
+    """The reference's distributed setup runs here (3 ranks as threads) and the oracle matches."""
+    from refexec.run import reference_distributed_setup
+    from tests.dist_cases import box_cost
+    from tests.parity_util import DIST_LOCAL_TREE_FIELDS, distributed_rank_digests
+    src, tgt, radii = __import__("tests.parity_util", fromlist=["x"]).config3_inputs(4000, 4000)
+    tkw = dict(max_particles_in_box=30, targets=tgt, target_radii=radii, stick_out_factor=0.25,
+               extent_norm="linf", kind="adaptive-level-restricted")
+    tree, trav, ranks = reference_distributed_setup(src, tkw, {}, 3, box_cost)
+    assert tree_mismatches(tree, build_tree(src, **tkw)) == []
+    want = [distributed_rank_digests(r["responsible_boxes_list"], r["masks"], r["local_tree"],
+                                     r["src_idx"], r["tgt_idx"], r["local_trav"], tree.nboxes)
+            for r in ranks]
+    got = _oracle_distributed_digests(src, tkw, {}, 3)
+    for r in range(3):
+        assert digest_mismatches(want[r], got[r]) == [], r
+    assert sum(len(r["tgt_idx"]) for r in ranks) == 4000
+    assert set(DIST_LOCAL_TREE_FIELDS) <= set(ranks[0]["local_tree"])
+
+# }}}
+
+
 # {{{ committed outputs of the reference
 
 _QUICK = make_cases(quick=True)
