@@ -1,8 +1,9 @@
 """CPU oracle for the distributed setup rows.
 
-TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED for the device rows (the reference's kernels cannot
-run here); ``get_box_ids_dfs_order`` / ``partition_work`` are pinned against the reference's
-own host code executed in place (``tests/test_reference_consumer.py``).
+TEST INFRASTRUCTURE ONLY.  PARITY PINNED: the reference's own ``partition_work``,
+``get_box_masks``, ``generate_local_tree`` and ``generate_local_travs`` run on the CPU through
+``tests/refexec`` (one thread per rank) and every per-rank output equals this restatement's
+(``tests/test_refexec.py``, ``tests/golden/refexec_distributed_digests.json``).
 numpy restatement of
 * ``boxtree/distributed/partition.py:38-121`` (``get_box_ids_dfs_order``,
   ``partition_work`` without the MPI Scatter: all segments are returned),

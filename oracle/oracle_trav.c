@@ -1,9 +1,12 @@
 /*
  * oracle/oracle_trav.c -- CPU restatement of the reference FMM-traversal kernels.
  *
- * TEST INFRASTRUCTURE ONLY (see oracle_tree.c).  PARITY UNPINNED: restated from
- * the kernel sources in /root/reference/boxtree/traversal.py; each function
- * cites the lines it follows.  The list-of-lists builder mirrors the documented
+ * TEST INFRASTRUCTURE ONLY (see oracle_tree.c).  Restated from the kernel sources
+ * in /root/reference/boxtree/traversal.py; each function cites the lines it
+ * follows.  PARITY PINNED against the reference itself: tests/refexec executes
+ * the reference's FMMTraversalBuilder (host code and kernel templates unmodified)
+ * on the CPU and this restatement reproduces every output array, dtype and byte
+ * (tests/test_refexec.py; 156 sweep cases, BASELINE configs up to 1e7 points).  The list-of-lists builder mirrors the documented
  * behaviour of pyopencl.algorithm.ListOfListsBuilder (pyopencl is an unpinned
  * third-party dependency of the reference, `pyopencl>=2022.1`, not vendored):
  * one work-item per row, a count pass, an exclusive scan to `starts`, a write

@@ -6,12 +6,19 @@
  * in __graft_entry__.py and the cpu_baseline / --impl reference legs of
  * bench.py use it, and only as the checker / the timed CPU baseline.
  *
- * PARITY UNPINNED (bit level): the reference's PyOpenCL path cannot be executed in
- * this image (no pyopencl / OpenCL ICD / mako) and its test-suite holds no golden
- * vectors for this path.  What is pinned by reference code run in place
- * (tests/test_reference_consumer.py, tests/test_tree_of_boxes.py): the meaning of
- * every list through the reference's own drive_fmm + ConstantOneExpansionWrangler,
- * TreeOfBoxes inputs made by the reference's tree_of_boxes.py with known answers.  This file restates, kernel by kernel, the OpenCL
+ * PARITY PINNED against the reference itself.  The reference's PyOpenCL path cannot
+ * run as shipped in this image (no pyopencl / OpenCL ICD / mako), so tests/refexec
+ * supplies stand-ins for those third-party modules that execute every kernel the
+ * reference renders, one work item at a time, compiled with g++; the reference's
+ * TreeBuilder.__call__ host code and kernel text run unmodified from
+ * /root/reference.  This restatement reproduces every Tree field (dtype, shape and
+ * bytes) of those runs: 116 + 174 sweep cases (1-3 D, fp32/fp64, all tree kinds,
+ * weights, extents, user bounding box, MaxLevelsExceeded), the BASELINE
+ * configurations including config 3 and uniform at 1e7 points
+ * (tests/test_refexec.py, tests/golden/make_*golden.py).  Also pinned by reference
+ * code run in place: drive_fmm + ConstantOneExpansionWrangler on the oracle's
+ * lists, tree_of_boxes.py inputs (tests/test_reference_consumer.py,
+ * tests/test_tree_of_boxes.py).  This file restates, kernel by kernel, the OpenCL
  * kernels the reference generates; every function cites the reference
  * file:line it follows (paths relative to /root/reference/).
  *

@@ -1,7 +1,8 @@
 """CPU oracle: restatement of ``boxtree.traversal.FMMTraversalBuilder.__call__``.
 
-TEST INFRASTRUCTURE ONLY -- never imported by ``boxtree_b200``.  PARITY
-UNPINNED (see ``oracle_trav.c``).  Follows the host driver at
+TEST INFRASTRUCTURE ONLY -- never imported by ``boxtree_b200``.  PARITY PINNED
+against the reference's own ``FMMTraversalBuilder`` executed on the CPU
+(``tests/refexec``, ``tests/test_refexec.py``; see ``oracle_trav.c``).  Follows the host driver at
 ``/root/reference/boxtree/traversal.py:1969-2345`` and the list merger at
 ``:1222-1344`` on numpy arrays.
 """

@@ -1,8 +1,8 @@
 """CPU oracle: restatement of ``boxtree.tree_build.TreeBuilder.__call__``.
 
-TEST INFRASTRUCTURE ONLY -- never imported by ``boxtree_b200``.  PARITY
-UNPINNED (see ``oracle_tree.c``): the reference cannot run in this image, so
-this driver restates the host control flow of
+TEST INFRASTRUCTURE ONLY -- never imported by ``boxtree_b200``.  PARITY PINNED
+against the reference's own ``TreeBuilder`` executed on the CPU (``tests/refexec``,
+``tests/test_refexec.py``; see ``oracle_tree.c``).  This driver restates the host control flow of
 ``/root/reference/boxtree/tree_build.py:145-1878`` step by step (same arrays,
 same level loop, same reallocation/renumbering bookkeeping) on numpy arrays,
 calling the C restatements of the reference's OpenCL kernels.

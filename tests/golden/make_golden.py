@@ -75,6 +75,10 @@ def digest_cases():
     cases["config3_3d_1e5"] = (s, dict(max_particles_in_box=30, targets=t, target_radii=r,
                                        stick_out_factor=0.25, extent_norm="linf",
                                        kind="adaptive-level-restricted"), {})
+    s, t, r = config3_inputs(20_000, 20_000)        # what __graft_entry__.smoke() builds
+    cases["config3_3d_4e4_smoke"] = (s, dict(max_particles_in_box=30, targets=t, target_radii=r,
+                                             stick_out_factor=0.25, extent_norm="linf",
+                                             kind="adaptive-level-restricted"), {})
     cases["config4_plummer_1e5_f32"] = (plummer_particles(100_000, np.float32), dict(
         max_particles_in_box=30), {})
     cases["normal_3d_f32_2away"] = (normal_particles(30_000, 3, np.float32), dict(

@@ -98,6 +98,9 @@ typedef clvec<double, 4> double4;
 typedef clvec<float, 2> float2;
 typedef clvec<float, 3> float3;
 typedef clvec<float, 4> float4;
+typedef clvec<int, 2> int2;
+typedef clvec<int, 3> int3;
+typedef clvec<int, 4> int4;
 
 // scalar builtins: keep the argument type (OpenCL's fmin(float, float) is a float operation)
 inline float fmin(float a, float b) { return std::fmin(a, b); }
@@ -106,10 +109,26 @@ inline float fabs(float a) { return std::fabs(a); }
 inline double fmin(double a, double b) { return std::fmin(a, b); }
 inline double fmax(double a, double b) { return std::fmax(a, b); }
 inline double fabs(double a) { return std::fabs(a); }
-template <class T> inline T clmin(T a, T b) { return a < b ? a : b; }
+// OpenCL: min(x, y) is y if y < x, otherwise x; max(x, y) is y if x < y, otherwise x
+template <class T> inline T clmin(T a, T b) { return b < a ? b : a; }
 template <class T> inline T clmax(T a, T b) { return a < b ? b : a; }
+template <class T, int N> inline clvec<T, N> clmin(const clvec<T, N> &a, const clvec<T, N> &b) {
+    clvec<T, N> r;
+    for (int i = 0; i < N; ++i) r.v[i] = b.v[i] < a.v[i] ? b.v[i] : a.v[i];
+    return r;
+}
+template <class T, int N> inline clvec<T, N> clmax(const clvec<T, N> &a, const clvec<T, N> &b) {
+    clvec<T, N> r;
+    for (int i = 0; i < N; ++i) r.v[i] = a.v[i] < b.v[i] ? b.v[i] : a.v[i];
+    return r;
+}
 #define min(a, b) clmin(a, b)
 #define max(a, b) clmax(a, b)
+
+// geometric builtins on scalars: distance(a, b) = length(a - b) = |a - b|  (sqrt(x*x) == |x| in
+// binary IEEE arithmetic barring over/underflow, so either formulation gives the same bits)
+inline float distance(float a, float b) { return std::fabs(a - b); }
+inline double distance(double a, double b) { return std::fabs(a - b); }
 
 // saturating integer add (OpenCL add_sat)
 inline int add_sat(int a, int b) {

@@ -489,7 +489,7 @@ def _translate_opencl(src: str) -> str:
     """The two OpenCL C constructs C++ parses differently: vector literals ``(T)(a, b, c)`` and
     ``inline`` free functions (fine as they are).  ``(coord_vec_t)(x, y)`` becomes
     ``coord_vec_t(x, y)``; ``(coord_vec_t) 0.5`` already broadcasts through the constructor."""
-    return re.sub(r"\(\s*(coord_vec_t|double[234]|float[234])\s*\)\s*\(", r"\1(", src)
+    return re.sub(r"\(\s*(\w*coord_vec_t|double[234]|float[234]|int[234])\s*\)\s*\(", r"\1(", src)
 
 
 def compile_module(source: str):
@@ -697,6 +697,20 @@ extern "C" void fetch(int k, void *dst) {{
                 result[name] = BuiltList(count=count, starts=Array(starts.astype(index_dtype), queue),
                                          lists=Array(data, queue))
         return result, Event()
+
+class KeyValueSorter:
+    """pyopencl.algorithm.KeyValueSorter: values grouped by key with a stable sort; returns
+    ``(starts, lists, event)`` with ``nkeys + 1`` starts."""
+
+    def __init__(self, context):
+        self.context = context
+
+    def __call__(self, queue, keys, values, nkeys, starts_dtype, allocator=None, wait_for=None):
+        k, v = _unwrap(keys), _unwrap(values)
+        order = np.argsort(k, kind="stable")
+        starts = np.zeros(int(nkeys) + 1, starts_dtype)
+        np.cumsum(np.bincount(k, minlength=int(nkeys)), out=starts[1:])
+        return Array(starts, queue), Array(v[order], queue), Event()
 
 # }}}
 
@@ -1271,7 +1285,7 @@ def build_modules() -> dict[str, types.ModuleType]:
                 get_or_register_dtype=get_or_register_dtype,
                 match_dtype_to_c_struct=match_dtype_to_c_struct, parse_arg_list=parse_arg_list)
     algorithm = mod("pyopencl.algorithm", ListOfListsBuilder=ListOfListsBuilder,
-                    BuiltList=BuiltList)
+                    BuiltList=BuiltList, KeyValueSorter=KeyValueSorter)
     elementwise = mod("pyopencl.elementwise", ElementwiseKernel=ElementwiseKernel,
                       ElementwiseTemplate=ElementwiseTemplate)
     scan = mod("pyopencl.scan", GenericScanKernel=GenericScanKernel, ScanTemplate=ScanTemplate)

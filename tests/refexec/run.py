@@ -303,3 +303,146 @@ def reference_distributed_setup(particles, tree_kwargs, trav_kwargs, nranks, cos
         return global_tree_np, _trav_namespace(fakecl, global_trav), results
 
 # }}}
+
+
+# {{{ area queries
+
+def reference_area_queries(tree, ball_centers, ball_radii):
+    """``PeerListFinder``, ``AreaQueryBuilder``, ``LeavesToBallsLookupBuilder`` and
+    ``SpaceInvaderQueryBuilder`` of ``boxtree/area_query.py`` on *tree* (any object with ``Tree``'s
+    fields).  Returns a dict of numpy arrays."""
+    with reference_modules() as fakecl:
+        import boxtree.area_query as aq
+        assert aq.__file__.startswith("/root/reference/")
+        actx = fakecl.PyOpenCLArrayContext()
+        rtree = tree_for_reference(fakecl, tree, actx)
+        rtree.bounding_box = tuple(np.asarray(b) for b in tree.bounding_box)
+        from pytools import obj_array
+        centers = obj_array.new_1d([fakecl.Array(np.array(c, copy=True)) for c in ball_centers])
+        radii = fakecl.Array(np.array(ball_radii, copy=True))
+
+        def host(x):
+            return np.asarray(fakecl._unwrap(x))
+
+        peers, _ = aq.PeerListFinder(actx)(actx, rtree)
+        res, _ = aq.AreaQueryBuilder(actx)(actx, rtree, centers, radii, peer_lists=peers)
+        lbl, _ = aq.LeavesToBallsLookupBuilder(actx)(actx, rtree, centers, radii, peer_lists=peers)
+        sq, _ = aq.SpaceInvaderQueryBuilder(actx)(actx, rtree, centers, radii, peer_lists=peers)
+        return {"peer_list_starts": host(peers.peer_list_starts),
+                "peer_lists": host(peers.peer_lists),
+                "leaves_near_ball_starts": host(res.leaves_near_ball_starts),
+                "leaves_near_ball_lists": host(res.leaves_near_ball_lists),
+                "balls_near_box_starts": host(lbl.balls_near_box_starts),
+                "balls_near_box_lists": host(lbl.balls_near_box_lists),
+                "outer_space_invader_dists": host(sq)}
+
+# }}}
+
+
+# {{{ a session: real reference objects for the rows that need them
+
+class Session:
+    """``with Session() as s:`` -- the reference's modules are importable inside; ``s.tree(...)``
+    and ``s.traversal(...)`` return the reference's REAL ``Tree`` / ``FMMTraversalInfo``."""
+
+    def __enter__(self):
+        self._cm = reference_modules()
+        self.fakecl = self._cm.__enter__()
+        self.actx = self.fakecl.PyOpenCLArrayContext()
+        return self
+
+    def __exit__(self, *exc):
+        return self._cm.__exit__(*exc)
+
+    def dev(self, x):
+        return None if x is None else self.fakecl.Array(np.array(x, copy=True), self.actx.queue)
+
+    def dev_vec(self, arrays):
+        from pytools import obj_array
+        return obj_array.new_1d([self.dev(a) for a in arrays])
+
+    def host(self, x):
+        if x is None:
+            return None
+        if isinstance(x, np.ndarray) and x.dtype == object:
+            return [self.host(v) for v in x]
+        return np.asarray(self.fakecl._unwrap(x))
+
+    def tree(self, particles, **kwargs):
+        import boxtree.tree_build as tb_mod
+        kw = dict(kwargs)
+        for name in ("source_radii", "target_radii", "refine_weights"):
+            if kw.get(name) is not None:
+                kw[name] = self.dev(kw[name])
+        if kw.get("targets") is not None:
+            kw["targets"] = self.dev_vec(kw["targets"])
+        tree, _ = tb_mod.TreeBuilder(self.actx)(self.actx, self.dev_vec(particles), **kw)
+        return tree
+
+    def traversal(self, tree, **kwargs):
+        import boxtree.traversal as trav_mod
+        ctor = {k: kwargs.pop(k) for k in ("well_sep_is_n_away", "from_sep_smaller_crit")
+                if k in kwargs}
+        trav, _ = trav_mod.FMMTraversalBuilder(self.actx, **ctor)(self.actx, tree, **kwargs)
+        return trav
+
+
+def reference_particle_filter(particles, tree_kwargs, flags):
+    """``ParticleListFilter`` (``boxtree/tree.py:1057-1239``) on the reference's own tree."""
+    with Session() as s:
+        import boxtree.tree as tree_mod
+        tree = s.tree(particles, **tree_kwargs)
+        plf = tree_mod.ParticleListFilter(s.actx)
+        u = plf.filter_target_lists_in_user_order(s.actx, tree, s.dev(flags))
+        t = plf.filter_target_lists_in_tree_order(s.actx, tree, s.dev(flags))
+        return {"user.nfiltered_targets": int(u.nfiltered_targets),
+                "user.target_starts": s.host(u.target_starts),
+                "user.target_lists": s.host(u.target_lists),
+                "tree.nfiltered_targets": int(t.nfiltered_targets),
+                "tree.box_target_starts": s.host(t.box_target_starts),
+                "tree.box_target_counts_nonchild": s.host(t.box_target_counts_nonchild),
+                "tree.unfiltered_from_filtered_target_indices":
+                    s.host(t.unfiltered_from_filtered_target_indices),
+                "tree.targets": s.host(t.targets)}
+
+
+def reference_link_point_sources(particles, tree_kwargs, point_source_starts, point_sources):
+    """``link_point_sources`` (``boxtree/tree.py:772-955``) on the reference's own tree."""
+    with Session() as s:
+        import boxtree.tree as tree_mod
+        tree = s.tree(particles, **tree_kwargs)
+        linked = tree_mod.link_point_sources(
+            s.actx, tree, s.dev(point_source_starts), s.dev_vec(point_sources))
+        out = {f: s.host(getattr(linked, f)) for f in (
+            "point_source_starts", "point_source_counts", "point_sources",
+            "user_point_source_ids", "box_point_source_starts",
+            "box_point_source_counts_nonchild", "box_point_source_counts_cumul")}
+        out["npoint_sources"] = int(linked.npoint_sources)
+        return out
+
+
+def reference_translation_classes(particles, tree_kwargs, trav_kwargs, per_level=True):
+    """``TranslationClassesBuilder`` (``boxtree/translation_classes.py:244-445``)."""
+    with Session() as s:
+        import boxtree.translation_classes as tc_mod
+        tree = s.tree(particles, **tree_kwargs)
+        trav = s.traversal(tree, **dict(trav_kwargs))
+        info, _ = tc_mod.TranslationClassesBuilder(s.actx)(
+            s.actx, trav, tree, is_translation_per_level=per_level)
+        return {f: s.host(getattr(info, f)) for f in (
+            "from_sep_siblings_translation_classes",
+            "from_sep_siblings_translation_class_to_distance_vector",
+            "from_sep_siblings_translation_classes_level_starts")}
+
+# }}}
+
+
+def reference_rotation_classes(particles, tree_kwargs, trav_kwargs):
+    """``RotationClassesBuilder`` (``boxtree/rotation_classes.py:90-190``)."""
+    with Session() as s:
+        import boxtree.rotation_classes as rc_mod
+        tree = s.tree(particles, **tree_kwargs)
+        trav = s.traversal(tree, **dict(trav_kwargs))
+        info, _ = rc_mod.RotationClassesBuilder(s.actx)(s.actx, trav, tree)
+        return {f: s.host(getattr(info, f)) for f in (
+            "from_sep_siblings_rotation_classes", "from_sep_siblings_rotation_class_to_angle")}

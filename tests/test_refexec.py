@@ -195,6 +195,134 @@ def test_reference_distributed_setup_live():
 # }}}
 
 
+# {{{ the widened rows (N1-N4), live
+
+def _same(a, b):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    return a.dtype == b.dtype and a.shape == b.shape and \
+        np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
+@needs_reference
+@pytest.mark.parametrize("dims,dtype,kind", [(2, np.float64, "adaptive"),
+                                             (3, np.float32, "adaptive-level-restricted"),
+                                             (3, np.float64, "adaptive")])
+def test_reference_area_queries_match_oracle(dims, dtype, kind):
+    """PeerListFinder, AreaQueryBuilder, LeavesToBallsLookupBuilder, SpaceInvaderQueryBuilder of
+    ``boxtree/area_query.py`` executed here vs the oracle's restatement."""
+    from oracle import traversal as ot
+    from refexec.run import reference_area_queries
+    from tests.parity_util import normal_particles
+    tree = build_tree(normal_particles(4000, dims, dtype), max_particles_in_box=20, kind=kind)
+    rng = np.random.default_rng(7)
+    centers = [rng.normal(size=500).astype(dtype) for _ in range(dims)]
+    radii = (0.3 * 2 ** rng.uniform(-6, 0, 500)).astype(dtype)
+    ref = reference_area_queries(tree, centers, radii)
+    got = dict(zip(("peer_list_starts", "peer_lists"), ot.find_peer_lists(tree)))
+    got.update(zip(("leaves_near_ball_starts", "leaves_near_ball_lists"),
+                   ot.area_query(tree, centers, radii)))
+    got.update(zip(("balls_near_box_starts", "balls_near_box_lists"),
+                   ot.leaves_to_balls(tree, centers, radii)))
+    got["outer_space_invader_dists"] = ot.space_invader_query(tree, centers, radii)
+    assert ref["leaves_near_ball_lists"].size > 500
+    for k, v in ref.items():
+        assert _same(v, got[k]), k
+
+
+@needs_reference
+def test_reference_particle_filter_matches_oracle():
+    from oracle import particle_filter as opf
+    from refexec.run import reference_particle_filter
+    from tests.parity_util import normal_particles
+    src = normal_particles(5000, 3, np.float64, seed=12)
+    tgt = normal_particles(4000, 3, np.float64, seed=19)
+    tkw = dict(targets=tgt, max_particles_in_box=30)
+    flags = (np.random.default_rng(5).random(4000) < 0.3).astype(np.int8)
+    ref = reference_particle_filter(src, tkw, flags)
+    tree = build_tree(src, **tkw)
+    n, starts, lists = opf.filter_target_lists_in_user_order(tree, flags)
+    assert n == ref["user.nfiltered_targets"]
+    assert _same(starts, ref["user.target_starts"]) and _same(lists, ref["user.target_lists"])
+    n, bstart, bcount, targets, unfiltered = opf.filter_target_lists_in_tree_order(tree, flags)
+    assert n == ref["tree.nfiltered_targets"]
+    # boxes that start at ntargets (empty, at the very end): the reference's index kernel reads
+    # filtered_from_unfiltered_target_index[ntargets], one past the end of the array
+    # (tree_build_kernels.py:1994-1996), so its value there is undefined; ours is nfiltered
+    defined = np.asarray(tree.box_target_starts) < tree.ntargets
+    assert np.array_equal(bstart[defined], ref["tree.box_target_starts"][defined])
+    assert np.all(bstart[~defined] == n)
+    assert _same(bcount, ref["tree.box_target_counts_nonchild"])
+    assert _same(unfiltered, ref["tree.unfiltered_from_filtered_target_indices"])
+    assert all(_same(a, b) for a, b in zip(targets, ref["tree.targets"]))
+
+
+@needs_reference
+def test_reference_link_point_sources_matches_oracle():
+    from oracle import particle_filter as opf
+    from refexec.run import reference_link_point_sources
+    from tests.parity_util import normal_particles
+    ns = 3000
+    src = normal_particles(ns, 3, np.float64)
+    rng = np.random.default_rng(7)
+    radii = 0.05 * 2 ** rng.uniform(-10, 0, ns)
+    tkw = dict(max_particles_in_box=30, targets=normal_particles(2000, 3, np.float64, seed=19),
+               source_radii=radii, stick_out_factor=0.25, extent_norm="linf")
+    counts = rng.integers(1, 5, ns)
+    starts = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    owner = np.repeat(np.arange(ns), counts)
+    pts = [src[a][owner] + radii[owner] * rng.uniform(-1, 1, len(owner)) for a in range(3)]
+    ref = reference_link_point_sources(src, tkw, starts, pts)
+    want = opf.link_point_sources(build_tree(src, **tkw), starts, pts)
+    assert want["npoint_sources"] == ref["npoint_sources"] == len(owner)
+    for k, v in want.items():
+        if k == "point_sources":
+            assert all(_same(a, b) for a, b in zip(v, ref[k]))
+        elif k != "npoint_sources":
+            assert _same(v, ref[k]), k
+
+
+@needs_reference
+@pytest.mark.parametrize("dims,dtype,n_away,per_level", [
+    (2, np.float64, 1, True), (3, np.float64, 2, True), (3, np.float32, 1, False)])
+def test_reference_translation_classes_match_oracle(dims, dtype, n_away, per_level):
+    from oracle import translation_classes as otc
+    from refexec.run import reference_translation_classes
+    from tests.parity_util import normal_particles
+    src = normal_particles(4000, dims, dtype)
+    ref = reference_translation_classes(src, dict(max_particles_in_box=30),
+                                        dict(well_sep_is_n_away=n_away), per_level)
+    tree = build_tree(src, max_particles_in_box=30)
+    trav = build_traversal(tree, well_sep_is_n_away=n_away)
+    classes, distances, level_starts = otc.translation_classes(trav, tree, per_level)
+    assert _same(classes, ref["from_sep_siblings_translation_classes"])
+    ref_starts = ref["from_sep_siblings_translation_classes_level_starts"]
+    ref_dist = ref["from_sep_siblings_translation_class_to_distance_vector"]
+    count = int(level_starts[-1])
+    assert count == int(ref_starts[-1]) and ref_starts[0] == level_starts[0] == 0
+    # the reference allocates both with np.empty: only the used classes' columns, and (when the
+    # classes are not per level) only the first and last start, are ever written
+    assert _same(distances[:, :count], ref_dist[:, :count])
+    if per_level:
+        assert _same(level_starts, ref_starts)
+
+
+@needs_reference
+@pytest.mark.parametrize("n_away", [1, 2])
+def test_reference_rotation_classes_match_oracle(n_away):
+    from oracle import translation_classes as otc
+    from refexec.run import reference_rotation_classes
+    from tests.parity_util import normal_particles
+    src = normal_particles(4000, 3, np.float64)
+    ref = reference_rotation_classes(src, dict(max_particles_in_box=30),
+                                     dict(well_sep_is_n_away=n_away))
+    tree = build_tree(src, max_particles_in_box=30)
+    classes, angles = otc.rotation_classes(build_traversal(tree, well_sep_is_n_away=n_away), tree)
+    assert _same(classes, ref["from_sep_siblings_rotation_classes"])
+    assert _same(angles, ref["from_sep_siblings_rotation_class_to_angle"])
+
+# }}}
+
+
 # {{{ committed outputs of the reference
 
 _QUICK = make_cases(quick=True)
