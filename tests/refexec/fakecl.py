@@ -275,7 +275,7 @@ def array_min(ary, queue=None):
 
 
 def array_take(ary, indices, out=None, queue=None, wait_for=None):
-    r = _unwrap(ary)[_unwrap(indices)]
+    r = _unwrap(ary).reshape(-1)[_unwrap(indices)]      # pyopencl indexes the flat buffer
     if out is not None:
         out._a[...] = r
         return out
@@ -326,7 +326,13 @@ class CommandQueue:
         pass
 
 
+class Platform:
+    name = "refexec"
+    vendor = "refexec"
+
+
 class Device:
+    platform = Platform()
     name = "refexec serial CPU"
     vendor = "refexec"
     version = "serial"
@@ -1126,6 +1132,24 @@ def memoize(*args, **kw):
     return deco
 
 
+def keyed_memoize_method(key, cache_dict_name=None):
+    """pytools.keyed_memoize_method: memoize on ``key(*args, **kwargs)``."""
+    def deco(f):
+        name = cache_dict_name or f"_memoize_dic_{f.__name__}"
+
+        @functools.wraps(f)
+        def wrapper(self, *args, **kwargs):
+            k = key(*args, **kwargs)
+            dic = self.__dict__.setdefault(name, {})
+            try:
+                return dic[k]
+            except KeyError:
+                dic[k] = r = f(self, *args, **kwargs)
+                return r
+        return wrapper
+    return deco
+
+
 class ProcessLogger:
     def __init__(self, *a, **k):
         pass
@@ -1265,6 +1289,51 @@ class CgenEnum:
 # }}}
 
 
+# {{{ pymbolic (only `var`, arithmetic and `evaluate`, as boxtree/cost.py uses them)
+
+class _Expr:
+    def __init__(self, fn, text):
+        self.fn, self.text = fn, text
+
+    def __repr__(self):
+        return self.text
+
+    @staticmethod
+    def lift(x):
+        return x if isinstance(x, _Expr) else _Expr(lambda ctx: x, repr(x))
+
+
+def _expr_op(symbol, op):
+    def forward(self, other):
+        o = _Expr.lift(other)
+        return _Expr(lambda ctx: op(self.fn(ctx), o.fn(ctx)), f"({self.text} {symbol} {o.text})")
+
+    def backward(self, other):
+        o = _Expr.lift(other)
+        return _Expr(lambda ctx: op(o.fn(ctx), self.fn(ctx)), f"({o.text} {symbol} {self.text})")
+    return forward, backward
+
+
+import operator as _operator  # noqa: E402
+
+for _sym, _name, _op in (("+", "add", _operator.add), ("-", "sub", _operator.sub),
+                         ("*", "mul", _operator.mul), ("/", "truediv", _operator.truediv),
+                         ("**", "pow", _operator.pow)):
+    _f, _b = _expr_op(_sym, _op)
+    setattr(_Expr, f"__{_name}__", _f)
+    setattr(_Expr, f"__r{_name}__", _b)
+
+
+def pymbolic_var(name):
+    return _Expr(lambda ctx: ctx[name], name)
+
+
+def pymbolic_evaluate(expr, context=None, **kw):
+    return _Expr.lift(expr).fn(context or {})
+
+# }}}
+
+
 # {{{ module table
 
 def build_modules() -> dict[str, types.ModuleType]:
@@ -1300,6 +1369,7 @@ def build_modules() -> dict[str, types.ModuleType]:
     cl.__path__ = []
     obj_array = _obj_array_module()
     pytools = mod("pytools", memoize_method=memoize_method, memoize=memoize,
+                  keyed_memoize_method=keyed_memoize_method,
                   ProcessLogger=ProcessLogger, DebugProcessLogger=DebugProcessLogger,
                   log_process=log_process, div_ceil=div_ceil, single_valued=single_valued,
                   partition=partition, product=product, Record=Record, obj_array=obj_array)
@@ -1311,8 +1381,12 @@ def build_modules() -> dict[str, types.ModuleType]:
     mako.__path__ = []
     mako_template = mod("mako.template", Template=MiniMakoTemplate)
     cgen = mod("cgen", Enum=CgenEnum)
+    characterize = mod("pyopencl.characterize", has_struct_arg_count_bug=lambda dev, ctx=None: False)
+    cl.characterize = characterize
+    pymbolic = mod("pymbolic", var=pymbolic_var, evaluate=pymbolic_evaluate)
+    arraycontext.ArrayContextFactory = object
     return {m.__name__: m for m in (cl, cl_array, cltypes, tools, algorithm, elementwise, scan,
                                     reduction, typing_mod, pytools, obj_array, arraycontext,
-                                    mako, mako_template, cgen)}
+                                    mako, mako_template, cgen, characterize, pymbolic)}
 
 # }}}

@@ -132,6 +132,24 @@ def test_reference_run_with_box_masks():
 # }}}
 
 
+# {{{ the reference's own tests, executed through refexec
+
+@needs_reference
+def test_reference_own_tests_pass_under_refexec():
+    """A small selection of ``/root/reference/test`` (the whole files are run by
+    ``tests/refexec/run_reference_tests.py``; log in ``profiles/``): the reference's assertions
+    about its own trees and traversals hold when its kernels are executed by the stand-ins."""
+    from refexec.run_reference_tests import run
+    proc = run(["/root/reference/test/test_traversal.py::test_tree_connectivity",
+                "/root/reference/test/test_tree.py::test_bounding_box",
+                "/root/reference/test/test_tree.py::test_leaves_to_balls_query",
+                "-k", "not 3"])
+    assert proc.returncode == 0, proc.stdout[-3000:]
+    assert " passed" in proc.stdout and "failed" not in proc.stdout
+
+# }}}
+
+
 # {{{ distributed setup
 
 def _oracle_distributed_digests(src, tkw, vkw, nranks):
