@@ -80,11 +80,36 @@ def make_cases(quick=False):
                 tree={"max_particles_in_box": 30, "stick_out_factor": 0.25, "extent_norm": "linf"}))
             cases.append(dict(base, name="coincident", n=12, coincident=True,
                               tree={"max_particles_in_box": 10}, expect_max_levels=True))
+            # the reference's test_max_levels_error (test/test_tree.py:1103-1112): every point at
+            # the origin, a bounding box without extent
+            cases.append(dict(base, name="all-at-origin", n=11, at_origin=True,
+                              tree={"max_particles_in_box": 10}, expect_max_levels=True))
+            if dims > 1:
+                # test_same_tree_with_zero_weight_particles (test/test_tree.py:1050-1097): targets
+                # with weight 0 and radii up to the domain size, stick-out factors 0 .. 1
+                for sof in (0, 0.1, 0.3, 1):
+                    cases.append(dict(base, name=f"zero-weight-sof{sof}", n=20, zero_weight=sof,
+                                      tree={"max_leaf_refine_weight": 10,
+                                            "stick_out_factor": sof}))
     return cases
 
 
 def make_inputs(case):
     dims, dt, n = case["dims"], case["dtype"], case["n"]
+    if case.get("at_origin"):
+        return [np.zeros(n, dtype=dt) for _ in range(dims)], dict(case["tree"])
+    if case.get("zero_weight") is not None:
+        rng = np.random.default_rng(10)
+        sources = rng.random((dims, n)) ** 2
+        sources[:, 0] = -0.1
+        sources[:, 1] = 1.1
+        targets = rng.random((dims, 500))[:, :40].copy()
+        radii = rng.random(500)[:40]
+        weights = np.zeros(n + 40, np.int32)
+        weights[:n] = 1
+        kw = dict(case["tree"], targets=[t.astype(dt) for t in targets],
+                  target_radii=radii.astype(dt), refine_weights=weights)
+        return [s.astype(dt) for s in sources], kw
     if case.get("coincident"):
         # 11 coincident points (> max_particles_in_box) and one distinct point so the
         # bounding box is not degenerate: both implementations must give up
