@@ -109,6 +109,12 @@ inline float fabs(float a) { return std::fabs(a); }
 inline double fmin(double a, double b) { return std::fmin(a, b); }
 inline double fmax(double a, double b) { return std::fmax(a, b); }
 inline double fabs(double a) { return std::fabs(a); }
+// <cmath> leaves only the C (double) versions of these in the global namespace: without the
+// overloads a float argument would silently be evaluated in double, unlike OpenCL C
+inline float sqrt(float a) { return std::sqrt(a); }
+inline float rint(float a) { return std::rint(a); }
+inline float floor(float a) { return std::floor(a); }
+inline float ceil(float a) { return std::ceil(a); }
 // OpenCL: min(x, y) is y if y < x, otherwise x; max(x, y) is y if x < y, otherwise x
 template <class T> inline T clmin(T a, T b) { return b < a ? b : a; }
 template <class T> inline T clmax(T a, T b) { return a < b ? b : a; }
