@@ -251,3 +251,49 @@ def config3_inputs(nsources, ntargets, dtype=np.float64):
     return ([np.ascontiguousarray(s[i]).astype(dtype) for i in range(3)],
             [np.ascontiguousarray(t[i]).astype(dtype) for i in range(3)],
             radii.astype(dtype))
+
+
+# ---- argument validation ----------------------------------------------------
+
+def error_cases():
+    """``(name, particles, TreeBuilder kwargs, traversal ctor kwargs or None, exception name)``:
+    invalid calls and the exception type the REFERENCE raises for them (checked against the
+    reference's own code in ``tests/test_refexec.py``, against the CUDA path in
+    ``tests/test_gpu_parity.py``).  Arrays are numpy; ``targets`` is a list of arrays."""
+    src = normal_particles(100, 2, np.float64)
+    ones = np.ones(100)
+    pts = np.array([0.5] * 11 + [1.0])
+    return [
+        ("unknown kind", src, dict(kind="bogus", max_particles_in_box=10), None, "ValueError"),
+        ("no refinement criterion", src, dict(), None, "ValueError"),
+        ("both criteria", src, dict(max_particles_in_box=10, refine_weights=np.ones(100, np.int32),
+                                    max_leaf_refine_weight=5), None, "ValueError"),
+        ("radii without targets", src, dict(source_radii=ones, max_particles_in_box=10), None,
+         "ValueError"),
+        ("radii without stick_out_factor", src, dict(targets=src, target_radii=ones,
+                                                     max_particles_in_box=10), None, "ValueError"),
+        ("radii dtype", src, dict(targets=src, target_radii=np.ones(100, np.float32),
+                                  stick_out_factor=0.1, max_particles_in_box=10), None, "TypeError"),
+        ("weights dtype", src, dict(refine_weights=np.ones(100, np.int64),
+                                    max_leaf_refine_weight=5), None, "TypeError"),
+        ("weight above the leaf maximum", src, dict(refine_weights=np.full(100, 7, np.int32),
+                                                    max_leaf_refine_weight=5), None, "ValueError"),
+        ("radii shape", src, dict(targets=src, target_radii=np.ones(99), stick_out_factor=0.1,
+                                  max_particles_in_box=10), None, "ValueError"),
+        ("unknown extent norm", src, dict(targets=src, target_radii=ones, stick_out_factor=0.1,
+                                          extent_norm="l7", max_particles_in_box=10), None,
+         "ValueError"),
+        ("coincident points", [pts, pts.copy()], dict(max_particles_in_box=10), None,
+         "MaxLevelsExceeded"),
+        ("traversal of an unpruned tree", src, dict(max_particles_in_box=10, skip_prune=True), {},
+         "ValueError"),
+        ("unknown from_sep_smaller_crit", src, dict(max_particles_in_box=10),
+         dict(from_sep_smaller_crit="bogus"), "ValueError"),
+        ("static_linf with l2 extents", src, dict(targets=src, target_radii=np.full(100, 1e-3),
+                                                  stick_out_factor=0.1, extent_norm="l2",
+                                                  max_particles_in_box=10),
+         dict(from_sep_smaller_crit="static_linf"), "ValueError"),
+        ("traversal with source extents", src, dict(targets=src, source_radii=np.full(100, 1e-3),
+                                                    stick_out_factor=0.1, max_particles_in_box=10),
+         {}, "NotImplementedError"),
+    ]

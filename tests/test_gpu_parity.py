@@ -514,42 +514,21 @@ def test_random_parity_sweep(actx, builders):
 
 
 def test_error_behaviour(actx):
-    from boxtree_b200 import FMMTraversalBuilder, MaxLevelsExceeded, TreeBuilder
+    """Invalid calls raise what the reference raises: the table of
+    ``tests.parity_util.error_cases`` is checked against the reference's own code in
+    ``tests/test_refexec.py``."""
+    import boxtree_b200
+    from boxtree_b200 import FMMTraversalBuilder, TreeBuilder
+    from tests.parity_util import error_cases
     tb = TreeBuilder(actx)
+    for name, particles, tkw, vkw, exc_name in error_cases():
+        exc = getattr(boxtree_b200, exc_name, None) or getattr(__import__("builtins"), exc_name)
+        dkw = {k: (actx.from_numpy(v) if isinstance(v, np.ndarray) else
+                   [actx.from_numpy(x) for x in v] if k == "targets" else v) for k, v in tkw.items()}
+        with pytest.raises(exc):
+            tree, _ = tb(actx, [actx.from_numpy(p) for p in particles], **dkw)
+            assert vkw is not None, f"{name}: the tree was built"
+            FMMTraversalBuilder(actx, **vkw)(actx, tree)
     src = [actx.from_numpy(s) for s in normal_particles(100, 2, np.float64)]
-    with pytest.raises(ValueError):
-        tb(actx, src, kind="bogus", max_particles_in_box=10)
-    with pytest.raises(ValueError):
-        tb(actx, src)
-    with pytest.raises(ValueError):
-        tb(actx, src, max_particles_in_box=10, refine_weights=actx.from_numpy(
-            np.ones(100, np.int32)), max_leaf_refine_weight=5)
-    with pytest.raises(ValueError):
-        tb(actx, src, source_radii=actx.from_numpy(np.ones(100)), max_particles_in_box=10)
-    with pytest.raises(ValueError):
-        tb(actx, src, targets=src, target_radii=actx.from_numpy(np.ones(100)),
-           max_particles_in_box=10)
-    with pytest.raises(TypeError):
-        tb(actx, src, targets=src, target_radii=actx.from_numpy(np.ones(100, np.float32)),
-           stick_out_factor=0.1, max_particles_in_box=10)
-    with pytest.raises(TypeError):
-        tb(actx, src, refine_weights=actx.from_numpy(np.ones(100, np.int64)),
-           max_leaf_refine_weight=5)
-    with pytest.raises(ValueError):
-        tb(actx, src, refine_weights=actx.from_numpy(np.full(100, 7, np.int32)),
-           max_leaf_refine_weight=5)
     with pytest.warns(DeprecationWarning):
         tb(actx, src, max_particles_in_box=10, allocator=object())
-    tree, _ = tb(actx, src, max_particles_in_box=10, skip_prune=True)
-    with pytest.raises(ValueError):
-        FMMTraversalBuilder(actx)(actx, tree)
-    with pytest.raises(ValueError):
-        FMMTraversalBuilder(actx, from_sep_smaller_crit="bogus")(
-            actx, tb(actx, src, max_particles_in_box=10)[0])
-    pts = np.array([0.5] * 11 + [1.0])
-    with pytest.raises(MaxLevelsExceeded):
-        tb(actx, [actx.from_numpy(pts), actx.from_numpy(pts.copy())], max_particles_in_box=10)
-    tree_se, _ = tb(actx, src, targets=src, source_radii=actx.from_numpy(np.full(100, 1e-3)),
-                    stick_out_factor=0.1, max_particles_in_box=10)
-    with pytest.raises(NotImplementedError):
-        FMMTraversalBuilder(actx)(actx, tree_se)

@@ -150,6 +150,30 @@ def test_reference_own_tests_pass_under_refexec():
 # }}}
 
 
+# {{{ argument validation
+
+@needs_reference
+def test_reference_raises_what_the_error_table_says():
+    """``tests.parity_util.error_cases`` (the table the CUDA path is held to) against the
+    reference's own ``TreeBuilder`` / ``FMMTraversalBuilder``; and the oracle agrees."""
+    from refexec.run import Session
+    from tests.parity_util import error_cases
+    for name, particles, tkw, vkw, exc_name in error_cases():
+        with Session() as s:
+            with pytest.raises(Exception) as ei:
+                tree = s.tree(particles, **tkw)
+                assert vkw is not None, f"{name}: the reference built the tree"
+                s.traversal(tree, **dict(vkw))
+            assert type(ei.value).__name__ == exc_name, (name, repr(ei.value))
+        with pytest.raises(Exception) as ei:
+            tree = build_tree(particles, **tkw)
+            assert vkw is not None, f"{name}: the oracle built the tree"
+            build_traversal(tree, **dict(vkw))
+        assert type(ei.value).__name__ == exc_name, (name, "oracle", repr(ei.value))
+
+# }}}
+
+
 # {{{ distributed setup
 
 def _oracle_distributed_digests(src, tkw, vkw, nranks):
