@@ -2,7 +2,9 @@
 ``/root/reference``): the random case generator of ``tests/random_sweep.py`` (dimensions, dtype,
 sizes, tree kind, targets, radii, norms, criteria, n-away 1-3, min-nsources), each case built by
 the reference's ``TreeBuilder`` + ``FMMTraversalBuilder`` through ``tests/refexec`` and by the
-oracle, all arrays compared bit for bit including dtypes.
+oracle, all arrays compared bit for bit including dtypes.  Every fifth case runs the distributed
+setup (``boxtree/distributed``: partition, masks, local trees, local traversals) on 1-6 ranks
+instead and compares every per-rank output.
 
     python tests/refexec/fuzz.py [master_seed] [seconds] [nprocs]
 """
@@ -49,6 +51,12 @@ def one(args):
             if case["dims"] == 1 and kw.get("kind") == "adaptive-level-restricted":
                 return desc, []          # the reference's 1-D level-restriction kernel does not compile
             raise
+        if rtree.nboxes >= 8 and case["seed"] % 5 == 0:
+            # every fifth case: the distributed setup on 1-6 ranks instead
+            from refexec.compare import distributed_mismatches
+            nranks = 1 + case["seed"] % 6
+            desc["nranks"] = nranks
+            return desc, distributed_mismatches(src, kw, ctor, nranks)
         otree = build_tree(src, **kw)
         bad = ["tree." + b for b in tree_mismatches(rtree, otree)]
         if not bad:

@@ -176,26 +176,7 @@ def test_reference_raises_what_the_error_table_says():
 
 # {{{ distributed setup
 
-def _oracle_distributed_digests(src, tkw, vkw, nranks):
-    from oracle import distributed as od
-    from tests.dist_cases import box_cost
-    from tests.parity_util import DIST_LOCAL_TREE_FIELDS, DIST_MASK_FIELDS, distributed_rank_digests
-    tree = build_tree(src, **tkw)
-    trav = build_traversal(tree, **vkw)
-    resp, _ = od.partition_work(box_cost(tree), tree, nranks)
-    masks = [od.get_box_masks(trav, resp[r]) for r in range(nranks)]
-    mp = np.stack([m.multipole_src_boxes for m in masks])
-    out = []
-    for r in range(nranks):
-        lt, src_idx, tgt_idx = od.generate_local_tree(trav, resp[r], mp)
-        fields = {f: (lt.extra[f] if f in lt.extra else getattr(lt, f))
-                  for f in DIST_LOCAL_TREE_FIELDS}
-        fields.update(sources=lt.sources, targets=lt.targets,
-                      target_radii=lt.target_radii if tree.targets_have_extent else None)
-        out.append(distributed_rank_digests(
-            resp[r], {f: getattr(masks[r], f) for f in DIST_MASK_FIELDS}, fields, src_idx, tgt_idx,
-            od.generate_local_travs(lt, **vkw), tree.nboxes))
-    return out
+from refexec.compare import oracle_distributed_digests as _oracle_distributed_digests  # noqa: E402
 
 
 @pytest.mark.parametrize("nranks", [1, 3, 4])
