@@ -583,10 +583,10 @@ def _unpack_source(args, type_prefix=""):
     unpack, codes = [], []
     for i, a in enumerate(args):
         if isinstance(a, VectorArg):
-            unpack.append(f"    {a.ctype()} *{a.name} = ({a.ctype()} *) a[{i}];")
+            unpack.append(f"    {a.ctype()} *{a.name} = ({a.ctype()} *) refexec_args[{i}];")
             codes.append(f"    out[{i}] = 0;")
         else:
-            unpack.append(f"    {a.ctype()} {a.name} = *({a.ctype()} *) a[{i}];")
+            unpack.append(f"    {a.ctype()} {a.name} = *({a.ctype()} *) refexec_args[{i}];")
             codes.append(f"    out[{i}] = scalar_code<{a.ctype()}>();")
     return "\n".join(unpack), "\n".join(codes)
 
@@ -644,7 +644,7 @@ typedef int index_type;
 extern "C" void scalar_codes(int *out) {{
 {codes}
 }}
-extern "C" void run(void **a, long n_objects, const int *omit, long **starts) {{
+extern "C" void run(void **refexec_args, long n_objects, const int *omit, long **starts) {{
 {unpack}
 {"".join(f"    g_{n}.items.clear(); g_{n}.omitted = omit[{k}] != 0; plb_list<{dtype_to_ctype(d)}> *plb_{n} = &g_{n};" + chr(10) for k, (n, d) in enumerate(lists))}
     for (long i = 0; i < n_objects; ++i) {{
@@ -736,7 +736,7 @@ class ElementwiseKernel:
 extern "C" void scalar_codes(int *out) {{
 {codes}
 }}
-extern "C" void run(void **a, long start, long stop, long step, long n) {{
+extern "C" void run(void **refexec_args, long start, long stop, long step, long n) {{
 {unpack}
     for (long i = start; i < stop; i += step) {{
         {operation};
@@ -863,7 +863,7 @@ extern "C" void scalar_codes(int *out) {{
 static inline scan_type scan_op(scan_type a, scan_type b, bool across_seg_boundary) {{
     return {scan_expr};
 }}
-extern "C" void run(void **a, long N_) {{
+extern "C" void run(void **refexec_args, long N_) {{
 {unpack}
     const index_type N = (index_type) N_;
     std::vector<scan_type> items(N_ > 0 ? N_ : 1);
@@ -957,7 +957,7 @@ extern "C" void scalar_codes(int *out) {{
 {codes}
 }}
 static inline out_type reduce_op(out_type a, out_type b) {{ return {reduce_expr}; }}
-extern "C" void run(void **a, long n, void *result) {{
+extern "C" void run(void **refexec_args, long n, void *result) {{
 {unpack}
     out_type acc = {neutral};
     for (long i = 0; i < n; ++i) {{

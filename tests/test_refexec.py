@@ -76,6 +76,75 @@ def test_minimako_subset():
 # }}}
 
 
+# {{{ the kernel-launch stand-ins (pyopencl's published semantics, restated in fakecl.py)
+
+def test_fakecl_list_of_lists_builder():
+    from refexec import fakecl
+    knl = fakecl.ListOfListsBuilder(
+        None, [("mult", np.int32), ("big", np.int64)], """
+        void generate(LIST_ARG_DECL USER_ARG_DECL index_type i)
+        {
+            for (int j = 0; j < reps[i]; ++j) APPEND_mult(i * scale);
+            if (reps[i] > 2) APPEND_big(1000 + i);
+        }""", [fakecl.VectorArg(np.int32, "reps"), fakecl.ScalarArg(np.int32, "scale")],
+        eliminate_empty_output_lists=["big"])
+    reps = fakecl.Array(np.array([2, 0, 3, 1, 0, 4], np.int32))
+    result, _ = knl(None, 6, reps, 10)
+    m, b = result["mult"], result["big"]
+    assert m.count == 10 and np.array_equal(m.starts._a, [0, 2, 2, 5, 6, 6, 10])
+    assert np.array_equal(m.lists._a, [0, 0, 20, 20, 20, 30, 50, 50, 50, 50])
+    assert m.starts.dtype == np.int32 and m.lists.dtype == np.int32
+    assert b.count == 2 and b.num_nonempty_lists == 2 and b.lists.dtype == np.int64
+    assert np.array_equal(b.starts._a, [0, 1, 2]) and np.array_equal(b.lists._a, [1002, 1005])
+    assert np.array_equal(b.nonempty_indices._a, [2, 5])
+    assert np.array_equal(b.compressed_indices._a, [0, 0, 0, 1, 1, 1, 2])
+    result, _ = knl(None, 6, reps, 10, omit_lists=("mult",))
+    assert result["mult"].lists is None and result["big"].count == 2
+
+
+def test_fakecl_scan_elementwise_reduction():
+    from refexec import fakecl
+    scan = fakecl.GenericScanKernel(
+        None, np.int32, arguments="int *x, int *seg, int *excl, int *incl, int *total",
+        input_expr="x[i]", scan_expr="across_seg_boundary ? b : a + b", neutral="0",
+        is_segment_start_expr="seg[i]",
+        output_statement="excl[i] = prev_item; incl[i] = item; if (i == N - 1) *total = last_item;")
+    x = fakecl.Array(np.array([3, 1, 4, 1, 5, 9], np.int32))
+    seg = fakecl.Array(np.array([0, 0, 1, 0, 0, 1], np.int32))
+    excl, incl = fakecl.Array(np.zeros(6, np.int32)), fakecl.Array(np.zeros(6, np.int32))
+    total = fakecl.Array(np.zeros(1, np.int32))
+    scan(x, seg, excl, incl, total)
+    assert np.array_equal(incl._a, [3, 4, 4, 5, 10, 9])
+    assert np.array_equal(excl._a, [0, 3, 0, 4, 5, 0]) and total._a[0] == 9
+    elwise = fakecl.ElementwiseKernel(None, "double *y, double a, int *src",
+                                      "if (src[i] < 0) PYOPENCL_ELWISE_CONTINUE; y[i] = a * src[i]")
+    y = fakecl.Array(np.full(6, -1.0))
+    elwise(y, 0.5, fakecl.Array(np.array([2, -1, 4, 6, 8, 10], np.int32)), range=slice(1, 5))
+    assert np.array_equal(y._a, [-1.0, -1.0, 2.0, 3.0, 4.0, -1.0])
+    red = fakecl.ReductionKernel(None, np.float32, neutral="-FLT_MAX", reduce_expr="fmax(a, b)",
+                                 map_expr="v[i] * v[i]", arguments="float *v")
+    assert red(fakecl.Array(np.array([1, -3, 2], np.float32))).get() == np.float32(9)
+    starts, lists, _ = fakecl.KeyValueSorter(None)(
+        None, fakecl.Array(np.array([2, 0, 2, 1, 0])), fakecl.Array(np.arange(5)), 4, np.int32)
+    assert np.array_equal(starts._a, [0, 2, 3, 5, 5]) and np.array_equal(lists._a, [1, 4, 3, 0, 2])
+
+
+def test_cl_shim_keeps_float_arithmetic_in_float():
+    """The finding of the first fuzz run: ``sqrt(float)`` must not be evaluated in double."""
+    from refexec import fakecl
+    knl = fakecl.ElementwiseKernel(
+        None, "float *x, float *out, int *size",
+        "out[i] = sqrt(x[i]) - x[i]; size[i] = sizeof(sqrt(x[i])) * 100 + sizeof(fmin(x[i], x[i])) "
+        "* 10 + sizeof(rint(x[i]));")
+    x = np.array([0.0034957202, 2.0, 1e-3], np.float32)
+    out, size = fakecl.Array(np.zeros(3, np.float32)), fakecl.Array(np.zeros(3, np.int32))
+    knl(fakecl.Array(x), out, size)
+    assert np.all(size._a == 444)
+    assert np.array_equal(out._a, np.sqrt(x) - x)
+
+# }}}
+
+
 # {{{ live: the reference runs here
 
 _LIVE = [c for c in make_cases(quick=True) if (c["dims"], np.dtype(c["dtype"]).name, c["name"]) in {
