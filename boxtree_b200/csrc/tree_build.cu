@@ -137,7 +137,7 @@ template <typename T> struct BBox { T mn[3]; T mx[3]; };
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256)
 make_keys_kernel(Particles<T, DIM> P, BBox<T> bb, int extent_norm, T stick_out_factor, int D,
-                 unsigned long long* __restrict__ keys)
+                 int points_never_stop, unsigned long long* __restrict__ keys)
 {
     const int stride = gridDim.x * blockDim.x;
     const T one_half = ((T)1) / 2;
@@ -158,8 +158,11 @@ make_keys_kernel(Particles<T, DIM> P, BBox<T> bb, int extent_norm, T stick_out_f
             q[a] = (unsigned long long)(((pos[a] - gmin[a]) / gext[a]) * scaleD);
         }
         unsigned stop = kStopNever;
-        if (extent_norm) {
-            const T radius = P.radius(i);
+        const T radius = extent_norm ? P.radius(i) : (T)0;
+        // A particle without extent lies inside its box at every level; with a stick-out factor
+        // that dwarfs the rounding errors of the tests below (make_keys_impl decides) none of them
+        // can fire for it, so the level loop is skipped with the identical result.
+        if (extent_norm && !(points_never_stop && radius == (T)0)) {
             for (int lev = 0; lev < D; ++lev) {    // lev = level of the box the particle sits in
                 const T size_factor = ((T)1) / ((T)(1u << (1 + lev)));
                 bool st = false;
@@ -943,7 +946,26 @@ static int make_keys_impl(const bt_particles* p, const double* bmin, const doubl
     BBox<T> bb;
     for (int a = 0; a < 3; ++a) { bb.mn[a] = (a < DIM) ? (T)bmin[a] : (T)0; bb.mx[a] = (a < DIM) ? (T)bmax[a] : (T)1; }
     if (P.n == 0) return BT_OK;
-    make_keys_kernel<T, DIM><<<grid_for(P.n, 256, 8), 256, 0, s>>>(P, bb, extent_norm, (T)stick_out, D, keys);
+    // May the stop-level loop be skipped for particles of radius 0?  Such a particle is inside its
+    // level-k box up to the rounding of (x - min) / extent (2 roundings) and of the box centre
+    // (3 roundings), together < 8 eps * M with M = max(|min|, |max|, extent); the tests compare
+    // against the box inflated by stick_out * (half the box size) (linf per axis; l2 the same up to
+    // a factor (1 + O(eps))).  Skipping is exact while that margin, at the finest level D, exceeds
+    // the error bound; a factor 64 is kept in hand.  fp32 builds seldom qualify.
+    int points_never_stop = 0;
+    if (extent_norm && stick_out > 0 && !(getenv("BT_KEYS_NO_SKIP"))) {
+        double min_ext = 1e300, M = 0;
+        for (int a = 0; a < DIM; ++a) {
+            const double ext = (double)bb.mx[a] - (double)bb.mn[a];
+            min_ext = ext < min_ext ? ext : min_ext;
+            M = fmax(M, fmax(fabs((double)bb.mn[a]), fmax(fabs((double)bb.mx[a]), ext)));
+        }
+        const double eps = sizeof(T) == 8 ? 2.220446049250313e-16 : 1.1920928955078125e-07;
+        const double margin = (double)(T)stick_out * min_ext / (double)(1ull << (D + 1));
+        points_never_stop = (min_ext > 0 && margin > 64.0 * eps * M) ? 1 : 0;
+    }
+    make_keys_kernel<T, DIM><<<grid_for(P.n, 256, 8), 256, 0, s>>>(P, bb, extent_norm, (T)stick_out, D,
+                                                                  points_never_stop, keys);
     BT_LAUNCH_CHECK();
     return BT_OK;
 }
