@@ -951,7 +951,7 @@ static int make_keys_impl(const bt_particles* p, const double* bmin, const doubl
     // (3 roundings), together < 8 eps * M with M = max(|min|, |max|, extent); the tests compare
     // against the box inflated by stick_out * (half the box size) (linf per axis; l2 the same up to
     // a factor (1 + O(eps))).  Skipping is exact while that margin, at the finest level D, exceeds
-    // the error bound; a factor 64 is kept in hand.  fp32 builds seldom qualify.
+    // the error bound; the check asks for 64 eps M, 8x the bound.  fp32 builds seldom qualify.
     int points_never_stop = 0;
     if (extent_norm && stick_out > 0 && !(getenv("BT_KEYS_NO_SKIP"))) {
         double min_ext = 1e300, M = 0;
