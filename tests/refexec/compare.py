@@ -50,3 +50,25 @@ def distributed_mismatches(src, tkw, vkw, nranks):
     for r in range(nranks):
         bad += [f"rank{r}.{k}" for k in digest_mismatches(want[r], got[r])]
     return bad
+
+
+def area_query_mismatches(tree, ball_centers, ball_radii):
+    """``boxtree/area_query.py`` (peer lists, area query, leaves-to-balls, space invaders) executed
+    by the reference vs ``oracle/traversal.py``."""
+    from oracle import traversal as ot
+    from refexec.run import reference_area_queries
+    ref = reference_area_queries(tree, ball_centers, ball_radii)
+    got = dict(zip(("peer_list_starts", "peer_lists"), ot.find_peer_lists(tree)))
+    got.update(zip(("leaves_near_ball_starts", "leaves_near_ball_lists"),
+                   ot.area_query(tree, ball_centers, ball_radii)))
+    got.update(zip(("balls_near_box_starts", "balls_near_box_lists"),
+                   ot.leaves_to_balls(tree, ball_centers, ball_radii)))
+    got["outer_space_invader_dists"] = ot.space_invader_query(tree, ball_centers, ball_radii)
+    bad = []
+    for k, v in ref.items():
+        g = np.ascontiguousarray(got[k])
+        v = np.ascontiguousarray(v)
+        if v.dtype != g.dtype or v.shape != g.shape or not np.array_equal(
+                v.view(np.uint8), g.view(np.uint8)):
+            bad.append("area_query." + k)
+    return bad

@@ -4,7 +4,8 @@ sizes, tree kind, targets, radii, norms, criteria, n-away 1-3, min-nsources), ea
 the reference's ``TreeBuilder`` + ``FMMTraversalBuilder`` through ``tests/refexec`` and by the
 oracle, all arrays compared bit for bit including dtypes.  Every fifth case runs the distributed
 setup (``boxtree/distributed``: partition, masks, local trees, local traversals) on 1-6 ranks
-instead and compares every per-rank output.
+instead and compares every per-rank output; every seventh runs the area queries of
+``boxtree/area_query.py`` with random balls.
 
     python tests/refexec/fuzz.py [master_seed] [seconds] [nprocs]
 """
@@ -58,6 +59,18 @@ def one(args):
             desc["nranks"] = nranks
             return desc, distributed_mismatches(src, kw, ctor, nranks)
         otree = build_tree(src, **kw)
+        if case["seed"] % 7 == 0 and case["dims"] > 1:      # (in 1-D the reference's area-query
+            # kernel does not compile: `ball_center.x` on a scalar coord_vec_t)
+            # every seventh case: the area queries of boxtree/area_query.py with random balls,
+            # some of them outside the bounding box
+            from refexec.compare import area_query_mismatches
+            rng = np.random.default_rng(case["seed"])
+            nballs = int(rng.integers(1, 400))
+            dt = np.dtype(case["dtype"])
+            centers = [(rng.normal(size=nballs) * 1.3).astype(dt) for _ in range(case["dims"])]
+            radii = (10 ** rng.uniform(-3, 0.3) * 2 ** rng.uniform(-8, 0, nballs)).astype(dt)
+            desc["nballs"] = nballs
+            return desc, area_query_mismatches(otree, centers, radii)
         bad = ["tree." + b for b in tree_mismatches(rtree, otree)]
         if not bad:
             bad = ["trav." + b for b in trav_mismatches(
