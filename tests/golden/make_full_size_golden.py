@@ -36,7 +36,10 @@ def full_size_cases():
     def uniform():
         return uniform_particles(10_000_000, 3, np.float64), dict(max_particles_in_box=30), {}
 
-    return {"config3_3d_1e7": config3, "uniform_3d_1e7_f64": uniform}
+    def config2():
+        return uniform_particles(1_000_000, 3, np.float64), dict(max_particles_in_box=30), {}
+
+    return {"config2_3d_1e6": config2, "config3_3d_1e7": config3, "uniform_3d_1e7_f64": uniform}
 
 
 def main():
