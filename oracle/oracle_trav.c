@@ -6,7 +6,7 @@
  * follows.  PARITY PINNED against the reference itself: tests/refexec executes
  * the reference's FMMTraversalBuilder (host code and kernel templates unmodified)
  * on the CPU and this restatement reproduces every output array, dtype and byte
- * (tests/test_refexec.py; 156 sweep cases, BASELINE configs up to 1e7 points).  The list-of-lists builder mirrors the documented
+ * (tests/test_refexec.py; 172 sweep cases, random cases, BASELINE configs up to 1e7 points).  The list-of-lists builder mirrors the documented
  * behaviour of pyopencl.algorithm.ListOfListsBuilder (pyopencl is an unpinned
  * third-party dependency of the reference, `pyopencl>=2022.1`, not vendored):
  * one work-item per row, a count pass, an exclusive scan to `starts`, a write

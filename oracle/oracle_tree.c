@@ -12,7 +12,7 @@
  * reference renders, one work item at a time, compiled with g++; the reference's
  * TreeBuilder.__call__ host code and kernel text run unmodified from
  * /root/reference.  This restatement reproduces every Tree field (dtype, shape and
- * bytes) of those runs: 116 + 174 sweep cases (1-3 D, fp32/fp64, all tree kinds,
+ * bytes) of those runs: 136 + 196 sweep cases (1-3 D, fp32/fp64, all tree kinds,
  * weights, extents, user bounding box, MaxLevelsExceeded), the BASELINE
  * configurations including config 3 and uniform at 1e7 points
  * (tests/test_refexec.py, tests/golden/make_*golden.py).  Also pinned by reference
