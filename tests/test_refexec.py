@@ -437,6 +437,19 @@ def test_oracle_matches_reference_digests(case):
         assert digest_mismatches(ref["trav"], trav_digests(trav)) == []
 
 
+def test_full_size_digest_file_matches_its_case_table():
+    """What ``tests/test_gpu_parity.py::test_full_size_matches_reference_run`` parametrises over."""
+    import json
+    from tests.golden.make_full_size_golden import full_size_cases
+    with open(os.path.join(GOLDEN, "full_size_digests.json")) as f:
+        d = json.load(f)
+    assert set(d) == set(full_size_cases())
+    for entry in d.values():
+        assert entry["_nboxes"] > 0 and entry["_nlevels"] > 0
+        assert {"tree.box_child_ids", "trav.from_sep_siblings_lists",
+                "trav.neighbor_source_boxes_lists"} <= set(entry)
+
+
 def test_reference_digests_cover_both_sweeps():
     d = reference_digests()
     for quick in (True, False):
