@@ -49,7 +49,8 @@ def tree_for_reference(fakecl, tree, actx):
 
 def reference_traversal(tree, well_sep_is_n_away=1, from_sep_smaller_crit=None,
                         _from_sep_smaller_min_nsources_cumul=None,
-                        source_boxes_mask=None, source_parent_boxes_mask=None):
+                        source_boxes_mask=None, source_parent_boxes_mask=None,
+                        merge_close_lists=False):
     """``FMMTraversalBuilder(actx, ...)(actx, tree, ...)`` of ``boxtree/traversal.py:1969-2345``.
     Returns a namespace of numpy arrays with ``FMMTraversalInfo``'s field names (compare with
     ``tests.parity_util.trav_mismatches``)."""
@@ -57,12 +58,13 @@ def reference_traversal(tree, well_sep_is_n_away=1, from_sep_smaller_crit=None,
         import boxtree.traversal as trav_mod
         return _reference_traversal(
             fakecl, trav_mod, tree, well_sep_is_n_away, from_sep_smaller_crit,
-            _from_sep_smaller_min_nsources_cumul, source_boxes_mask, source_parent_boxes_mask)
+            _from_sep_smaller_min_nsources_cumul, source_boxes_mask, source_parent_boxes_mask,
+            merge_close_lists)
 
 
 def _reference_traversal(fakecl, trav_mod, tree, well_sep_is_n_away, from_sep_smaller_crit,
                          _from_sep_smaller_min_nsources_cumul, source_boxes_mask,
-                         source_parent_boxes_mask):
+                         source_parent_boxes_mask, merge_close_lists=False):
     assert trav_mod.__file__.startswith("/root/reference/")
     actx = fakecl.PyOpenCLArrayContext()
     rtree = tree_for_reference(fakecl, tree, actx)
@@ -78,6 +80,9 @@ def _reference_traversal(fakecl, trav_mod, tree, well_sep_is_n_away, from_sep_sm
         actx, rtree,
         _from_sep_smaller_min_nsources_cumul=_from_sep_smaller_min_nsources_cumul, **kwargs)
 
+    if merge_close_lists:
+        # FMMTraversalInfo.merge_close_lists (traversal.py:1650-1693)
+        info = info.merge_close_lists(actx)
     return _trav_namespace(fakecl, info)
 
 

@@ -186,6 +186,24 @@ def test_reference_run_matches_oracle(case):
 
 
 @needs_reference
+@pytest.mark.parametrize("n_away", [1, 2])
+def test_reference_merge_close_lists_matches_oracle(n_away):
+    """``FMMTraversalInfo.merge_close_lists`` (the reference's ``_ListMerger`` kernels)."""
+    from oracle.traversal import merge_close_lists
+    from refexec.run import reference_traversal
+    from tests.parity_util import config3_inputs
+    src, tgt, radii = config3_inputs(3000, 3000)
+    tree = build_tree(src, targets=tgt, target_radii=radii * 8, stick_out_factor=0.25,
+                      max_particles_in_box=20, extent_norm="linf")
+    ref = reference_traversal(tree, well_sep_is_n_away=n_away, merge_close_lists=True)
+    got = merge_close_lists(build_traversal(tree, well_sep_is_n_away=n_away))
+    assert ref.from_sep_close_smaller_starts is None and ref.from_sep_close_bigger_lists is None
+    assert trav_mismatches(ref, got) == []
+    plain = build_traversal(tree, well_sep_is_n_away=n_away)
+    assert len(got.neighbor_source_boxes_lists) > len(plain.neighbor_source_boxes_lists)
+
+
+@needs_reference
 def test_reference_run_with_box_masks():
     """``source_boxes_mask`` / ``source_parent_boxes_mask`` (the distributed code's entry)."""
     from refexec.run import reference_traversal
