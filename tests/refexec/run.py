@@ -451,3 +451,17 @@ def reference_rotation_classes(particles, tree_kwargs, trav_kwargs):
         info, _ = rc_mod.RotationClassesBuilder(s.actx)(s.actx, trav, tree)
         return {f: s.host(getattr(info, f)) for f in (
             "from_sep_siblings_rotation_classes", "from_sep_siblings_rotation_class_to_angle")}
+
+
+def reference_cost_model(particles, tree_kwargs, trav_kwargs, factory, level_to_order,
+                         calibration_params):
+    """The reference's DEVICE cost model, ``FMMCostModel`` (``boxtree/cost.py:715-1262``, OpenCL
+    kernels), on the reference's own tree and traversal: ``(cost_per_box, cost_per_stage)``."""
+    with Session() as s:
+        import boxtree.cost as cost
+        tree = s.tree(particles, **tree_kwargs)
+        trav = s.traversal(tree, **dict(trav_kwargs))
+        model = cost.FMMCostModel(getattr(cost, factory))
+        per_box = model.cost_per_box(s.actx, trav, level_to_order, dict(calibration_params))
+        per_stage = model.cost_per_stage(s.actx, trav, level_to_order, dict(calibration_params))
+        return s.host(per_box), {k: float(s.fakecl._unwrap(v)) for k, v in per_stage.items()}

@@ -430,6 +430,33 @@ def test_reference_rotation_classes_match_oracle(n_away):
     assert _same(classes, ref["from_sep_siblings_rotation_classes"])
     assert _same(angles, ref["from_sep_siblings_rotation_class_to_angle"])
 
+
+
+@needs_reference
+@pytest.mark.parametrize("factory", ["make_pde_aware_translation_cost_model",
+                                     "make_taylor_translation_cost_model"])
+@pytest.mark.parametrize("name", ["3d-points", "2d-points-2away", "3d-config3"])
+def test_reference_device_cost_model_matches_the_golden(name, factory):
+    """``tests/golden/cost_model.json`` was written by the reference's ``_PythonFMMCostModel``
+    on the oracle's traversal; here the reference's device ``FMMCostModel`` (its OpenCL kernels,
+    executed through refexec on the reference's own tree and traversal) must give the same."""
+    import json
+    from refexec.run import reference_cost_model
+    from tests.golden.make_cost_golden import CALIBRATION, cases, level_to_order
+    with open(os.path.join(GOLDEN, "cost_model.json")) as f:
+        want = json.load(f)[f"{name}/{factory}"]
+    src, tkw, vkw = cases()[name]
+    nlevels = build_tree(src, **tkw).nlevels
+    per_box, per_stage = reference_cost_model(src, tkw, vkw, factory, level_to_order(nlevels),
+                                              CALIBRATION)
+    assert len(per_box) == want["nboxes"]
+    assert np.allclose(per_box[:64], want["per_box_head"], rtol=1e-12, atol=0)
+    assert np.allclose(per_box[::97], want["per_box_every_97th"], rtol=1e-12, atol=0)
+    assert np.isclose(float(np.sum(per_box)), want["per_box_sum"], rtol=1e-12)
+    assert set(per_stage) == set(want["per_stage"])
+    for k, v in want["per_stage"].items():
+        assert np.isclose(per_stage[k], v, rtol=1e-12), k
+
 # }}}
 
 
