@@ -3,13 +3,19 @@
 ``tests/refexec`` executes the reference's ``TreeBuilder.__call__`` and
 ``FMMTraversalBuilder.__call__`` -- host code and kernel templates unmodified, from where they lie
 under ``/root/reference`` -- on the CPU, with stand-ins for the third-party modules that are not
-installed (pyopencl, mako, pytools, arraycontext, cgen).  Two kinds of test:
+installed (pyopencl, mako, pytools, arraycontext, cgen, pymbolic).  Besides unit tests of the
+stand-ins themselves, two kinds of test:
 
 * live (skipped where ``/root/reference`` is absent): the reference runs here and its arrays are
   compared with the oracle's, bit for bit including dtypes;
 * committed: ``tests/golden/refexec_digests.json`` / ``refexec_*.npz`` hold what the reference
   produced for every sweep case (``tests/golden/make_refexec_golden.py``); the oracle must
-  reproduce them.  (The CUDA path is held to the same files in ``tests/test_gpu_parity.py``.)
+  reproduce them.  (The CUDA path is held to the same files in ``tests/test_gpu_parity.py`` and
+  ``tests/test_gpu_distributed.py``.)
+
+Also live: the distributed setup, area queries, particle filters, point-source linking, translation
+and rotation classes, ``merge_close_lists``, the device cost model, the error table, and a selection
+of the reference's own tests.  ``tests/refexec/fuzz.py`` repeats the comparisons on random cases.
 """
 from __future__ import annotations
 
