@@ -7,7 +7,7 @@ setup (``boxtree/distributed``: partition, masks, local trees, local traversals)
 instead and compares every per-rank output; every seventh runs the area queries of
 ``boxtree/area_query.py`` with random balls.
 
-    python tests/refexec/fuzz.py [master_seed] [seconds] [nprocs]
+    python tests/refexec/fuzz.py [master_seed] [seconds] [nprocs] [max particles per case]
 """
 from __future__ import annotations
 
@@ -25,7 +25,7 @@ sys.path.insert(0, os.path.dirname(HERE))
 
 
 def one(args):
-    seed, deadline = args
+    seed, deadline, nmax = args
     if time.time() > deadline:
         return None
     from oracle.traversal import build_traversal
@@ -34,7 +34,7 @@ def one(args):
     from tests.gpu_sweep import make_inputs
     from tests.parity_util import trav_mismatches, tree_mismatches
     from tests.random_sweep import random_case
-    case = random_case(np.random.default_rng(seed), nmax=4000)
+    case = random_case(np.random.default_rng(seed), nmax=nmax)
     desc = {k: (np.dtype(v).name if k == "dtype" else v) for k, v in case.items()}
     try:
         src, kw = make_inputs(case)
@@ -84,11 +84,12 @@ def main():
     master = int(sys.argv[1]) if len(sys.argv) > 1 else 1
     budget = float(sys.argv[2]) if len(sys.argv) > 2 else 120.0
     nprocs = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+    nmax = int(sys.argv[4]) if len(sys.argv) > 4 else 4000
     t0 = time.time()
     seeds = np.random.default_rng(master).integers(0, 2 ** 31, 100000)
     ncase = nbad = 0
     with ProcessPoolExecutor(nprocs) as pool:
-        for res in pool.map(one, ((int(s), t0 + budget) for s in seeds), chunksize=4):
+        for res in pool.map(one, ((int(s), t0 + budget, nmax) for s in seeds), chunksize=4):
             if res is None:
                 break
             desc, bad = res
