@@ -28,6 +28,7 @@ CTL_NBIG = 7
 CTL_NHUGE = 8
 CTL_LR_FOUND = 16
 CTL_SIZE = 64
+STEP_DECIDE, STEP_CREATE, STEP_COMMIT, STEP_ALL = 1, 2, 4, 7
 
 vp = C.c_void_p
 
@@ -40,13 +41,15 @@ class bt_particles(C.Structure):
 class bt_pool(C.Structure):
     _fields_ = [("start", vp), ("count", vp), ("level", vp), ("parent", vp), ("child0", vp),
                 ("has_children", vp), ("force_split", vp), ("nonchild", vp), ("center", vp * 3),
-                ("capacity", C.c_int32)]
+                ("capacity", C.c_int32), ("gstart", vp), ("gcount", vp), ("gnonchild", vp),
+                ("xch", vp)]
 
 
 class bt_box_out(C.Structure):
     _fields_ = [("box_start", vp), ("box_count", vp), ("box_nonchild", vp), ("box_levels", vp),
                 ("box_parent_ids", vp), ("box_child_ids", vp), ("box_centers", vp),
-                ("has_children", vp), ("real_children", vp)]
+                ("has_children", vp), ("real_children", vp), ("local_start", vp),
+                ("local_count", vp), ("local_nonchild", vp)]
 
 
 class bt_tree_view(C.Structure):
@@ -82,6 +85,7 @@ class bt_heavy_ws(C.Structure):
 
 HCTL_NWALK = 3
 HCTL_SIZE = 64
+STEP_DECIDE, STEP_CREATE, STEP_COMMIT, STEP_ALL = 1, 2, 4, 7
 HCTL_NHEAVY = 0
 HCTL_OVERFLOW = 1
 
@@ -107,6 +111,10 @@ SIGNATURES = {
     "bt_permute": [_i, _i, _P(bt_particles), vp, _i64, _P(vp), vp, vp],
     "bt_box_info": [_i, _i, _i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "bt_box_extents": [_i, _i, _i, _i, _i, _P(C.c_int32), vp, vp, vp, vp, _P(vp), vp, vp, vp, vp],
+    "bt_box_extents_phase": [_i, _i, _i, _i, _i, _P(C.c_int32), vp, vp, vp, vp, _P(vp), vp, vp, vp,
+                             _i, vp],
+    "bt_box_info_local": [_i, _i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    "bt_box_info_global": [_i, _i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "bt_trav_box_list": [_i, _i, vp, vp, vp, vp, vp],
     "bt_trav_level_starts": [_i, vp, vp, _i, vp, vp],
     "bt_trav_build_list": [_i, _i, _i, _P(bt_tree_view), _P(bt_list_args), _i, vp, vp, vp, vp,
@@ -137,6 +145,11 @@ SIGNATURES = {
     "bt_dist_modify_target_flags": [_i, vp, vp, vp, vp],
     "bt_dist_box_to_user_rank": [_i, _i, _i, vp, vp, vp, vp, vp],
     "bt_dist_restrict_target_flags": [_i, vp, vp, vp, vp, vp, vp],
+    "bt_dist_particle_box": [_i, vp, vp, vp, vp],
+    "bt_dist_mask_bits": [_i, _i, vp, vp, vp],
+    "bt_dist_pack_records": [_i, _i, _i, _i64, vp, vp, _P(vp), vp, vp, vp, vp, vp, vp, _i64],
+    "bt_dist_unpack_records": [_i, _i, _i64, _i, vp, vp, vp, _P(vp), vp, vp, vp],
+    "bt_dist_local_ranges": [_i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
 }
 
 _lib = None

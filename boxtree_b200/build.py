@@ -20,8 +20,9 @@ HEADERS = ["common.cuh", "scan.cuh", "radix_sort.cuh", os.path.join("..", "..", 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
+OBJDIR = os.path.join(HERE, "..", "build", "obj")
 
 
 def _nvcc() -> str:
@@ -42,8 +43,26 @@ def needs_rebuild() -> bool:
 def build(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
     if not force and not needs_rebuild():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, *extra_flags,
-           *[os.path.join(CSRC, s) for s in SOURCES], "-o", LIB]
+    # one object per translation unit, compiled concurrently; only stale objects are rebuilt
+    os.makedirs(OBJDIR, exist_ok=True)
+    hdr_t = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS
+                if os.path.exists(os.path.join(CSRC, h)))
+    procs, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
+        objs.append(obj)
+        src_path = os.path.join(CSRC, src)
+        stale = force or extra_flags or not os.path.exists(obj) or \
+            os.path.getmtime(obj) < max(hdr_t, os.path.getmtime(src_path))
+        if stale:
+            cmd = [_nvcc(), *NVCC_FLAGS, *extra_flags, "-c", src_path, "-o", obj]
+            if verbose:
+                print(" ".join(cmd))
+            procs.append((cmd, subprocess.Popen(cmd)))
+    for cmd, pr in procs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, cmd)
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", *objs, "-o", LIB]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
@@ -52,4 +71,4 @@ def build(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
 
 if __name__ == "__main__":
     flags = ["-Xptxas", "-v"] if "--ptxas-v" in sys.argv else []
-    build(force=True, verbose=True, extra_flags=flags)
+    build(force="--force" in sys.argv or bool(flags), verbose=True, extra_flags=flags)

@@ -212,6 +212,139 @@ static int fetch_impl(int dim, int64_t n, const int* mask, const int* g2l, void*
     return BT_OK;
 }
 
+
+// ---- (e): particle exchange of the distributed build ---------------------------------------
+// After the distributed tree build every rank holds the GLOBAL box arrays and its OWN input
+// particles in tree order.  A rank's local tree (local_tree.py:198-284) needs the sources of
+// its point-source boxes and the targets of its responsible boxes, wherever they live: each
+// owner packs, per destination rank, one record per needed particle
+//     [coords (dim) | radius (optional) | box id (i32) | index inside the box's own range (i32)]
+// the records travel in ONE all_to_all, and the receiver scatters them to
+//     local_start[box] + index,
+// which is the particle's place in the global tree order restricted to the rank's boxes (the
+// order construct_local_particles_and_lists produces).
+
+// box id of every local particle (own ranges tile the local array); 8 lanes per box
+__global__ void __launch_bounds__(256)
+dist_particle_box_kernel(int nboxes, const int* __restrict__ lstart, const int* __restrict__ lown,
+                         int* __restrict__ pbox)
+{
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, gl = threadIdx.x & 7;
+    const int ng = (gridDim.x * blockDim.x) >> 3;
+    for (int b = g; b < nboxes; b += ng) {
+        const int s = lstart[b], e = s + lown[b];
+        for (int p = s + gl; p < e; p += 8) pbox[p] = b;
+    }
+}
+
+// dest_bits[b] = OR over ranks r with masks[r][b] != 0 of (1 << r)
+__global__ void dist_mask_bits_kernel(int nboxes, int nranks, const signed char* __restrict__ masks,
+                                      unsigned* __restrict__ bits)
+{
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nboxes; b += gridDim.x * blockDim.x) {
+        unsigned v = 0;
+        for (int r = 0; r < nranks; ++r) if (masks[(int64_t)r * nboxes + b]) v |= 1u << r;
+        bits[b] = v;
+    }
+}
+
+template <typename T>
+struct PackIn {
+    const int* pbox; const unsigned* dest_bits; int64_t n;
+    __device__ int operator()(int64_t k) const
+    {
+        const int d = (int)(k / n); const int64_t p = k - (int64_t)d * n;
+        return (dest_bits[pbox[p]] >> d) & 1u;
+    }
+};
+template <typename T>
+struct PackOut {
+    const int* pbox; const unsigned* dest_bits; int64_t n; int dim; int recbytes;
+    const T* c0; const T* c1; const T* c2; const T* radii;
+    const int* lstart; const int* rank_excl;     // E_r[b]: own particles of lower ranks in box b
+    unsigned char* sendbuf; long long* dest_offsets; /* [nranks + 1] */ int nranks; long long cap;
+    __device__ void operator()(int64_t k, long long excl) const
+    {
+        const int d = (int)(k / n); const int64_t p = k - (int64_t)d * n;
+        if (p == 0) dest_offsets[d] = excl;
+        const int b = pbox[p];
+        if (!((dest_bits[b] >> d) & 1u) || excl >= cap) return;
+        unsigned char* rec = sendbuf + excl * recbytes;
+        T* c = reinterpret_cast<T*>(rec);
+        c[0] = c0[p];
+        if (dim > 1) c[1] = c1[p];
+        if (dim > 2) c[2] = c2[p];
+        int q = dim;
+        if (radii) c[q++] = radii[p];
+        int* tail = reinterpret_cast<int*>(c + q);
+        tail[0] = b;
+        tail[1] = rank_excl[b] + (int)(p - lstart[b]);
+    }
+    __device__ void total(long long t) const { dest_offsets[nranks] = t; }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+dist_unpack_kernel(int64_t nrec, int dim, int recbytes, int has_radii, const unsigned char* __restrict__ recv,
+                   const int* __restrict__ dst_start, const int* __restrict__ gstart,
+                   T* o0, T* o1, T* o2, T* __restrict__ oradii, long long* __restrict__ idx_out)
+{
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nrec;
+         k += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned char* rec = recv + k * recbytes;
+        const T* c = reinterpret_cast<const T*>(rec);
+        int q = dim + (has_radii ? 1 : 0);
+        const int* tail = reinterpret_cast<const int*>(c + q);
+        const int b = tail[0], rel = tail[1];
+        const int64_t pos = (int64_t)dst_start[b] + rel;
+        o0[pos] = c[0];
+        if (dim > 1) o1[pos] = c[1];
+        if (dim > 2) o2[pos] = c[2];
+        if (has_radii) oradii[pos] = c[dim];
+        idx_out[pos] = (long long)gstart[b] + rel;
+    }
+}
+
+// ranges of the rank's local particle arrays (local_tree.py:249-284) without a global particle
+// array: the global tree order is the boxes' pre-order (own particles, then the children in
+// Morton order), so the local start of a box is the prefix, in pre-order, of the own counts of
+// the masked boxes before it
+struct OwnScanIn {
+    const signed char* mask; const int* own; const int* order;
+    __device__ int operator()(int64_t i) const { const int b = order[i]; return mask[b] ? own[b] : 0; }
+};
+struct OwnScanOut {
+    int* prefix; int64_t n;
+    __device__ void operator()(int64_t i, long long excl) const { prefix[i] = (int)excl; }
+    __device__ void total(long long t) const { prefix[n] = (int)t; }
+};
+__global__ void dist_local_ranges_kernel(int nboxes, const signed char* __restrict__ mask,
+                                         const int* __restrict__ own, const int* __restrict__ rank,
+                                         const int* __restrict__ subtree, const int* __restrict__ prefix,
+                                         int* __restrict__ lstarts, int* __restrict__ lnonchild,
+                                         int* __restrict__ lcumul)
+{
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nboxes; b += gridDim.x * blockDim.x) {
+        const int r = rank[b];
+        lstarts[b] = prefix[r];
+        lnonchild[b] = mask[b] ? own[b] : 0;
+        lcumul[b] = prefix[r + subtree[b]] - prefix[r];
+    }
+}
+
+template <typename T>
+static int pack_impl(int nranks, int dim, int64_t n, const int* pbox, const unsigned* dest_bits,
+                     void* const* parts, const void* radii, const int* lstart, const int* rank_excl,
+                     void* sendbuf, long long* dest_offsets, long long cap, cudaStream_t s)
+{
+    const int recbytes = (int)sizeof(T) * (dim + (radii ? 1 : 0)) + 8;
+    PackIn<T> in{pbox, dest_bits, n};
+    PackOut<T> out{pbox, dest_bits, n, dim, recbytes, (const T*)parts[0],
+                   dim > 1 ? (const T*)parts[1] : nullptr, dim > 2 ? (const T*)parts[2] : nullptr,
+                   (const T*)radii, lstart, rank_excl, (unsigned char*)sendbuf, dest_offsets, nranks, cap};
+    return scan_exclusive((int64_t)nranks * n, nullptr, in, out, s);
+}
+
 }  // namespace bt
 
 extern "C" {
@@ -355,6 +488,90 @@ int bt_dist_box_to_user_rank(int phase, int nboxes, int nranks, const int8_t* ma
     if (nboxes <= 0) return BT_OK;
     bt::dist_rank_fill_kernel<<<bt::grid_for(nboxes, 256), 256, 0, s>>>(
         nboxes, nranks, (const signed char*)masks_all_ranks, starts, lists);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+
+int bt_dist_particle_box(int nboxes, const int32_t* local_start, const int32_t* local_own,
+                         int32_t* particle_box, void* stream)
+{
+    BT_PROF("bt_dist_particle_box", (cudaStream_t)stream);
+    if (nboxes <= 0) return BT_OK;
+    bt::dist_particle_box_kernel<<<bt::grid_for((int64_t)nboxes * 8, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        nboxes, local_start, local_own, particle_box);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+
+int bt_dist_mask_bits(int nboxes, int nranks, const int8_t* masks_all_ranks, uint32_t* dest_bits, void* stream)
+{
+    BT_PROF("bt_dist_mask_bits", (cudaStream_t)stream);
+    if (nboxes <= 0) return BT_OK;
+    if (nranks > 32) return BT_ERR_UNSUPPORTED;
+    bt::dist_mask_bits_kernel<<<bt::grid_for(nboxes, 256), 256, 0, (cudaStream_t)stream>>>(
+        nboxes, nranks, (const signed char*)masks_all_ranks, dest_bits);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+
+int bt_dist_pack_records(int dtype, int nranks, int dim, int64_t n, const int32_t* particle_box,
+                         const uint32_t* dest_bits, void* const* particles, const void* radii,
+                         const int32_t* local_start, const int32_t* rank_excl, void* sendbuf,
+                         int64_t* dest_offsets, void* stream, int64_t capacity)
+{
+    BT_PROF("bt_dist_pack_records", (cudaStream_t)stream);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (nranks > 32) return BT_ERR_UNSUPPORTED;
+    if (n <= 0) return (int)cudaMemsetAsync(dest_offsets, 0, sizeof(int64_t) * (nranks + 1), s);
+    if (dtype == BT_F32)
+        return bt::pack_impl<float>(nranks, dim, n, particle_box, dest_bits, particles, radii, local_start,
+                                    rank_excl, sendbuf, (long long*)dest_offsets, (long long)capacity, s);
+    if (dtype == BT_F64)
+        return bt::pack_impl<double>(nranks, dim, n, particle_box, dest_bits, particles, radii, local_start,
+                                     rank_excl, sendbuf, (long long*)dest_offsets, (long long)capacity, s);
+    return BT_ERR_BAD_ARG;
+}
+
+int bt_dist_unpack_records(int dtype, int dim, int64_t nrec, int has_radii, const void* recvbuf,
+                           const int32_t* dst_start, const int32_t* box_global_start,
+                           void* const* local_particles, void* local_radii, int64_t* particle_idx,
+                           void* stream)
+{
+    BT_PROF("bt_dist_unpack_records", (cudaStream_t)stream);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (nrec <= 0) return BT_OK;
+    const int grid = bt::grid_for(nrec, 256, 8);
+    if (dtype == BT_F32) {
+        const int rb = 4 * (dim + (has_radii ? 1 : 0)) + 8;
+        bt::dist_unpack_kernel<float><<<grid, 256, 0, s>>>(
+            nrec, dim, rb, has_radii, (const unsigned char*)recvbuf, dst_start, box_global_start,
+            (float*)local_particles[0], dim > 1 ? (float*)local_particles[1] : nullptr,
+            dim > 2 ? (float*)local_particles[2] : nullptr, (float*)local_radii, (long long*)particle_idx);
+    } else if (dtype == BT_F64) {
+        const int rb = 8 * (dim + (has_radii ? 1 : 0)) + 8;
+        bt::dist_unpack_kernel<double><<<grid, 256, 0, s>>>(
+            nrec, dim, rb, has_radii, (const unsigned char*)recvbuf, dst_start, box_global_start,
+            (double*)local_particles[0], dim > 1 ? (double*)local_particles[1] : nullptr,
+            dim > 2 ? (double*)local_particles[2] : nullptr, (double*)local_radii, (long long*)particle_idx);
+    } else return BT_ERR_BAD_ARG;
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+
+int bt_dist_local_ranges(int nboxes, const int8_t* box_mask, const int32_t* own_counts,
+                         const int32_t* preorder_rank, const int32_t* preorder_boxes,
+                         const int32_t* subtree_size, int32_t* prefix_tmp /*[nboxes+1]*/,
+                         int32_t* local_starts, int32_t* local_nonchild, int32_t* local_cumul, void* stream)
+{
+    BT_PROF("bt_dist_local_ranges", (cudaStream_t)stream);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (nboxes <= 0) return BT_OK;
+    bt::OwnScanIn in{(const signed char*)box_mask, own_counts, preorder_boxes};
+    bt::OwnScanOut out{prefix_tmp, nboxes};
+    BT_TRY(bt::scan_exclusive(nboxes, nullptr, in, out, s));
+    bt::dist_local_ranges_kernel<<<bt::grid_for(nboxes, 256), 256, 0, s>>>(
+        nboxes, (const signed char*)box_mask, own_counts, preorder_rank, subtree_size, prefix_tmp,
+        local_starts, local_nonchild, local_cumul);
     BT_LAUNCH_CHECK();
     return BT_OK;
 }

@@ -209,8 +209,13 @@ make_keys_kernel(Particles<T, DIM> P, BBox<T> bb, int extent_norm, T stick_out_f
 // ---------------------------------------------------------------------------
 template <typename T, int DIM>
 struct Pool {
+    // start/count/nn: the box's range in THIS rank's sorted particle array; gstart/gcount/gnn:
+    // the same over all ranks (alias the local arrays on one GPU).  Split decisions, pruning
+    // and the output box arrays use the global values, child ranges the local ones.
     int* start; int* count; unsigned char* level; int* parent; int* child0;
     unsigned char* has_children; unsigned char* force_split; int* nn;
+    int* gstart; int* gcount; int* gnn;
+    int* xch;           // distributed build: (lower bound, count, nonchild) of the new children
     T* center[DIM];
 };
 
@@ -221,6 +226,10 @@ static Pool<T, DIM> make_pool(const bt_pool* p)
     r.start = p->start; r.count = p->count; r.level = p->level; r.parent = p->parent;
     r.child0 = p->child0; r.has_children = p->has_children; r.force_split = p->force_split;
     r.nn = p->nonchild;
+    r.gstart = p->gstart ? p->gstart : p->start;
+    r.gcount = p->gcount ? p->gcount : p->count;
+    r.gnn = p->gnonchild ? p->gnonchild : p->nonchild;
+    r.xch = p->xch;
     for (int a = 0; a < DIM; ++a) r.center[a] = (T*)p->center[a];
     return r;
 }
@@ -249,6 +258,8 @@ __global__ void pool_init_kernel(Pool<T, DIM> pool, const unsigned long long* __
     if (have_ext && n > 0) nn = upper_bound_key(keys, 0, n, 0ull /* empty prefix, stop level 0 */);
     pool.start[0] = 0; pool.count[0] = n; pool.level[0] = 0; pool.parent[0] = 0; pool.child0[0] = 0;
     pool.has_children[0] = 0; pool.force_split[0] = 0; pool.nn[0] = nn;
+    // distributed build: the host overwrites the global root entries with the all-reduced sums
+    pool.gstart[0] = 0; pool.gcount[0] = n; pool.gnn[0] = nn;
     for (int a = 0; a < DIM; ++a) pool.center[a][0] = center.mn[a];
     for (int i = 0; i < BT_CTL_SIZE; ++i) ctl[i] = 0;
     ctl[BT_CTL_NBOXES] = 1;
@@ -268,7 +279,7 @@ struct DecideIn {
         const int b = lo + (int)i;
         bool split = false, regular = false;
         if (pool.level[b] + 1 == level) {
-            const int a = pool.start[b], c = pool.count[b], nn = pool.nn[b];
+            const int a = pool.gstart[b], c = pool.gcount[b], nn = pool.gnn[b];
             int wdesc;
             if (wprefix) wdesc = (c > 0) ? clamp_weight(wprefix[a + c] - wprefix[a + nn]) : 0;
             else wdesc = c - nn;
@@ -338,7 +349,9 @@ create_children_kernel(Pool<T, DIM> pool, const unsigned long long* __restrict__
         pool.parent[child] = b;
         pool.level[child] = (unsigned char)new_level;
         pool.count[child] = cnt;
-        pool.start[child] = (cnt > 0) ? lb : 0;
+        // distributed build: the local lower bound is kept for empty ranges too (the global
+        // start of a box is the sum of the ranks' lower bounds)
+        pool.start[child] = (cnt > 0 || pool.xch) ? lb : 0;
         pool.child0[child] = 0;
         pool.has_children[child] = 0;
         pool.force_split[child] = 0;
@@ -349,8 +362,13 @@ create_children_kernel(Pool<T, DIM> pool, const unsigned long long* __restrict__
             nn = upper_bound_key(keys, lb, lb_next, kc) - lb;
         }
         pool.nn[child] = nn;
-        const int w = wprefix ? ((cnt > 0) ? clamp_weight(wprefix[lb_next] - wprefix[lb]) : 0) : cnt;
-        if (w > maxw) ctl[BT_CTL_OVERSIZE] = 1;
+        if (pool.xch) {         // sums over ranks follow (children_finish_kernel)
+            int* x = pool.xch + 3ll * (r * NB + m);
+            x[0] = lb; x[1] = cnt; x[2] = nn;
+        } else {
+            const int w = wprefix ? ((cnt > 0) ? clamp_weight(wprefix[lb_next] - wprefix[lb]) : 0) : cnt;
+            if (w > maxw) ctl[BT_CTL_OVERSIZE] = 1;
+        }
         // centre chain: parent +- root_extent / 2^(1+new_level)   (:698-705)
         const T radius = (root_extent * 1 / (T)(1 << (1 + new_level)));
 #pragma unroll
@@ -360,6 +378,26 @@ create_children_kernel(Pool<T, DIM> pool, const unsigned long long* __restrict__
             pool.center[a][child] = has_bit ? pc + radius : pc - radius;
         }
         if (m == 0) pool.child0[b] = base + r * NB;
+    }
+}
+
+// distributed build: the all-reduced (lower bound, count, nonchild) of the new children become
+// their global ranges; the oversize test of the splitter (:690-696) runs on the global count
+template <typename T, int DIM>
+__global__ void __launch_bounds__(256)
+children_finish_kernel(Pool<T, DIM> pool, int* __restrict__ ctl, int maxw, int skip_if_no_regular)
+{
+    constexpr int NB = 1 << DIM;
+    if (ctl[BT_CTL_OVERFLOW]) return;
+    if (skip_if_no_regular && ctl[BT_CTL_NSPLIT_REGULAR] == 0) return;
+    const int total = ctl[BT_CTL_NSPLIT] * NB, base = ctl[BT_CTL_NBOXES];
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
+        const int* x = pool.xch + 3ll * k;
+        const int cnt = x[1];
+        pool.gstart[base + k] = (cnt > 0) ? x[0] : 0;
+        pool.gcount[base + k] = cnt;
+        pool.gnn[base + k] = x[2];
+        if (cnt > maxw) ctl[BT_CTL_OVERSIZE] = 1;
     }
 }
 
@@ -481,15 +519,21 @@ gather_boxes_kernel(Pool<T, DIM> pool, const int* __restrict__ src_of_new,
                     int* __restrict__ out_parent, int* __restrict__ out_child /*[NB, aligned]*/,
                     T* __restrict__ out_center /*[DIM, aligned]*/,
                     unsigned char* __restrict__ out_has_children,
-                    unsigned char* __restrict__ out_real_children)
+                    unsigned char* __restrict__ out_real_children,
+                    int* __restrict__ out_lstart, int* __restrict__ out_lcount, int* __restrict__ out_lnn)
 {
     constexpr int NB = 1 << DIM;
     const int stride = gridDim.x * blockDim.x;
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nfinal; j += stride) {
         const int b = src_of_new[j];
-        out_start[j] = pool.start[b];
-        out_count[j] = pool.count[b];
-        out_nn[j] = have_ext ? pool.nn[b] : 0;
+        out_start[j] = pool.gstart[b];
+        out_count[j] = pool.gcount[b];
+        out_nn[j] = have_ext ? pool.gnn[b] : 0;
+        if (out_lstart) {       // distributed build: the box's range in this rank's particles
+            out_lstart[j] = pool.start[b];
+            out_lcount[j] = pool.count[b];
+            out_lnn[j] = have_ext ? pool.nn[b] : 0;
+        }
         out_level[j] = pool.level[b];
         out_parent[j] = map_old2new[pool.parent[b]];
         const int c0 = pool.child0[b];
@@ -688,6 +732,66 @@ box_info_kernel(int nboxes, int sources_are_targets, int have_ext,
             src_starts[b] = s_st; src_cumul[b] = s_cu; src_nonchild[b] = s_nc;
             tgt_starts[b] = t_st; tgt_cumul[b] = t_cu; tgt_nonchild[b] = t_nc;
         }
+        box_flags[b] = fl;
+    }
+}
+
+// Distributed build, part 1: the source counts of the box's range in THIS rank's particles
+// (lower bounds kept for empty ranges so that the sums over ranks are the global values).
+// out3 = [3][nboxes]: sources before the box, in the box (cumulative), stopping in the box.
+__global__ void __launch_bounds__(256)
+box_info_local_kernel(int nboxes, int have_ext, const int* __restrict__ lstart,
+                      const int* __restrict__ lcount, const int* __restrict__ lnn,
+                      const unsigned char* __restrict__ has_children,
+                      const int* __restrict__ source_numbers, int* __restrict__ out3,
+                      int* __restrict__ src_starts, int* __restrict__ src_nonchild, int* __restrict__ src_cumul,
+                      int* __restrict__ tgt_starts, int* __restrict__ tgt_nonchild, int* __restrict__ tgt_cumul)
+{
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nboxes; b += gridDim.x * blockDim.x) {
+        const int st = lstart[b], c = lcount[b];
+        const int nn = have_ext ? lnn[b] : 0;
+        const int s0 = source_numbers[st];
+        const int s_cu = source_numbers[st + c] - s0;
+        int s_nc = (have_ext && nn > 0) ? source_numbers[st + nn] - s0 : 0;
+        int t_nc = nn - s_nc;
+        if (!has_children[b]) { s_nc = s_cu; t_nc = c - s_cu; }
+        out3[b] = s0; out3[nboxes + b] = s_cu; out3[2 * nboxes + b] = s_nc;
+        src_starts[b] = s0; src_cumul[b] = s_cu; src_nonchild[b] = s_nc;
+        tgt_starts[b] = st - s0; tgt_cumul[b] = c - s_cu; tgt_nonchild[b] = t_nc;
+    }
+}
+
+// Distributed build, part 2: the global tree's per-box ranges and flags from the global
+// srcntgt ranges and the all-reduced source counts (same case analysis as box_info_kernel)
+__global__ void __launch_bounds__(256)
+box_info_global_kernel(int nboxes, int have_ext, const int* __restrict__ gstart,
+                       const int* __restrict__ gcount, const int* __restrict__ gnn,
+                       const unsigned char* __restrict__ has_children, const int* __restrict__ src3,
+                       int* __restrict__ src_starts, int* __restrict__ src_nonchild, int* __restrict__ src_cumul,
+                       int* __restrict__ tgt_starts, int* __restrict__ tgt_nonchild, int* __restrict__ tgt_cumul,
+                       unsigned char* __restrict__ box_flags)
+{
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nboxes; b += gridDim.x * blockDim.x) {
+        const int st = gstart[b], c = gcount[b];
+        const int nn = have_ext ? gnn[b] : 0;
+        int s_st = 0, t_st = 0, s_cu = 0, t_cu = 0, s_nc = 0, t_nc = 0;
+        unsigned char fl = 0;
+        if (c > 0) {
+            s_st = src3[b]; t_st = st - s_st;
+            s_cu = src3[nboxes + b]; t_cu = c - s_cu;
+            s_nc = src3[2 * nboxes + b];
+            t_nc = (has_children[b] ? nn : c) - s_nc;
+        }
+        if (has_children[b]) {
+            fl |= BT_BOX_HAS_SOURCE_CHILD_BOXES | BT_BOX_HAS_TARGET_CHILD_BOXES;
+            if (s_nc) fl |= BT_BOX_IS_SOURCE_BOX;
+            if (t_nc) fl |= BT_BOX_IS_TARGET_BOX;
+        } else {
+            if (s_cu) fl |= BT_BOX_IS_SOURCE_BOX;
+            if (c - s_cu) fl |= BT_BOX_IS_TARGET_BOX;
+        }
+        src_starts[b] = s_st; src_cumul[b] = s_cu; src_nonchild[b] = s_nc;
+        tgt_starts[b] = t_st; tgt_cumul[b] = t_cu; tgt_nonchild[b] = t_nc;
         box_flags[b] = fl;
     }
 }
@@ -986,26 +1090,37 @@ template <typename T, int DIM>
 static int level_step_impl(const bt_pool* pool, const unsigned long long* keys, const long long* wprefix,
                            int* ctl, int* split_list, unsigned char* flag, int lo, int nboxes_host,
                            int level, int max_key_level, int maxw, int adaptive, int level_restrict,
-                           int have_ext, int skip_if_no_regular, double root_extent, int run_decide,
+                           int have_ext, int skip_if_no_regular, double root_extent, int phases,
                            cudaStream_t s)
 {
     Pool<T, DIM> P = make_pool<T, DIM>(pool);
+    const bool decide = phases & BT_STEP_DECIDE, create = phases & BT_STEP_CREATE,
+               commit = phases & BT_STEP_COMMIT;
     // per-iteration control slots: NSPLIT, OVERSIZE, OVERFLOW, NSPLIT_REGULAR, COMMITTED
-    if (run_decide) BT_CHECK(cudaMemsetAsync(ctl + BT_CTL_NSPLIT, 0, sizeof(int) * 5, s));
-    else BT_CHECK(cudaMemsetAsync(ctl + BT_CTL_OVERFLOW, 0, sizeof(int), s));
-    if (run_decide) {
+    if (decide) BT_CHECK(cudaMemsetAsync(ctl + BT_CTL_NSPLIT, 0, sizeof(int) * 5, s));
+    else if (create) BT_CHECK(cudaMemsetAsync(ctl + BT_CTL_OVERFLOW, 0, sizeof(int), s));
+    if (decide) {
         DecideIn<T, DIM> in{P, wprefix, ctl, flag, lo, level, maxw, adaptive, level_restrict};
         DecideOut out{flag, split_list, ctl, lo};
         BT_TRY(scan_exclusive((int64_t)(nboxes_host - lo), nullptr, in, out, s));
     }
     // at most every box in [lo, nboxes) splits
     const int64_t max_threads = (int64_t)(nboxes_host - lo) * (1 << DIM);
-    create_children_kernel<T, DIM><<<grid_for(max_threads, 256, 8), 256, 0, s>>>(
-        P, keys, wprefix, split_list, ctl, pool->capacity, max_key_level, have_ext, maxw,
-        skip_if_no_regular, (T)root_extent);
-    BT_LAUNCH_CHECK();
-    commit_level_kernel<DIM><<<1, 32, 0, s>>>(ctl, skip_if_no_regular);
-    BT_LAUNCH_CHECK();
+    if (create) {
+        create_children_kernel<T, DIM><<<grid_for(max_threads, 256, 8), 256, 0, s>>>(
+            P, keys, wprefix, split_list, ctl, pool->capacity, max_key_level, have_ext, maxw,
+            skip_if_no_regular, (T)root_extent);
+        BT_LAUNCH_CHECK();
+    }
+    if (commit) {
+        if (P.xch) {
+            children_finish_kernel<T, DIM><<<grid_for(max_threads, 256, 8), 256, 0, s>>>(
+                P, ctl, maxw, skip_if_no_regular);
+            BT_LAUNCH_CHECK();
+        }
+        commit_level_kernel<DIM><<<1, 32, 0, s>>>(ctl, skip_if_no_regular);
+        BT_LAUNCH_CHECK();
+    }
     return BT_OK;
 }
 
@@ -1048,8 +1163,8 @@ static int finalize_boxes_impl(const bt_pool* pool, int nboxes, int level_restri
             order = (int*)(in_alt ? v1 : v0);
         }
         // level_start: slots above the deepest level keep the final count (host fills)
-        KeepIn in{order, pool->count, skip_prune};
-        KeepOut out{order, pool->count, pool->level, skip_prune, map_old2new, src_of_new, level_start, ctl};
+        KeepIn in{order, P.gcount, skip_prune};
+        KeepOut out{order, P.gcount, pool->level, skip_prune, map_old2new, src_of_new, level_start, ctl};
         BT_TRY(scan_exclusive(nboxes, nullptr, in, out, s));
         if (k0) { BT_CHECK(cudaFreeAsync(k0, s)); BT_CHECK(cudaFreeAsync(v0, s)); }
         return BT_OK;
@@ -1057,7 +1172,7 @@ static int finalize_boxes_impl(const bt_pool* pool, int nboxes, int level_restri
     gather_boxes_kernel<T, DIM><<<grid_for(nfinal, 256), 256, 0, s>>>(
         P, src_of_new, map_old2new, nfinal, aligned, have_ext, o->box_start, o->box_count, o->box_nonchild,
         o->box_levels, o->box_parent_ids, o->box_child_ids, (T*)o->box_centers, o->has_children,
-        o->real_children);
+        o->real_children, o->local_start, o->local_count, o->local_nonchild);
     BT_LAUNCH_CHECK();
     return BT_OK;
 }
@@ -1079,9 +1194,10 @@ template <typename T, int DIM>
 static int box_extents_impl(int nboxes, int aligned, int nlevels, const int* level_start_host,
                             const int* child_ids, const void* centers, const int* pstarts,
                             const int* pcounts, void* const* parts, const void* radii, void* bmin,
-                            void* bmax, cudaStream_t s)
+                            void* bmax, int phases, cudaStream_t s)
 {
     if (nboxes <= 0) return BT_OK;
+    if (phases & 1) {
     // list of the boxes with more than kExtHuge own particles ([0] = count)
     int* huge = nullptr;
     const size_t huge_cap = (size_t)nboxes;
@@ -1098,6 +1214,8 @@ static int box_extents_impl(int nboxes, int aligned, int nlevels, const int* lev
         (const T*)radii, (T*)bmin, (T*)bmax, huge + 1, huge);
     BT_LAUNCH_CHECK();
     BT_CHECK(cudaFreeAsync(huge, s));
+    }
+    if (!(phases & 2)) return BT_OK;
     for (int lev = nlevels - 2; lev >= 0; --lev) {       // the deepest level has no children
         const int start = level_start_host[lev], stop = level_start_host[lev + 1];
         if (stop <= start) continue;
@@ -1207,13 +1325,13 @@ int bt_pool_init(int dtype, int dim, const bt_pool* pool, int64_t n, int have_ex
 int bt_level_step(int dtype, int dim, const bt_pool* pool, const uint64_t* keys, const int64_t* wprefix,
                   int32_t* ctl, int32_t* split_list, uint8_t* flag, int lo, int nboxes, int level,
                   int maxw, int adaptive, int level_restrict, int have_extent, int skip_if_no_regular,
-                  double root_extent, int run_decide, void* stream)
+                  double root_extent, int phases, void* stream)
 {
     BT_PROF("bt_level_step", (cudaStream_t)stream);
     BT_DISPATCH(dtype, dim, level_step_impl, pool, (const unsigned long long*)keys,
                 (const long long*)wprefix, ctl, split_list, flag, lo, nboxes, level,
                 bt_max_key_level(dim), maxw, adaptive, level_restrict, have_extent, skip_if_no_regular,
-                root_extent, run_decide, (cudaStream_t)stream);
+                root_extent, phases, (cudaStream_t)stream);
 }
 
 int bt_level_restrict(int dtype, int dim, const bt_pool* pool, int32_t* ctl, int built_level,
@@ -1327,8 +1445,50 @@ int bt_box_extents(int dtype, int dim, int nboxes, int aligned, int nlevels,
 {
     BT_PROF("bt_box_extents", (cudaStream_t)stream);
     BT_DISPATCH(dtype, dim, box_extents_impl, nboxes, aligned, nlevels, level_start_box_nrs_host,
-                box_child_ids, box_centers, pstarts, pcounts, particles, radii, bb_min, bb_max,
+                box_child_ids, box_centers, pstarts, pcounts, particles, radii, bb_min, bb_max, 3,
                 (cudaStream_t)stream);
+}
+
+int bt_box_extents_phase(int dtype, int dim, int nboxes, int aligned, int nlevels,
+                         const int32_t* level_start_box_nrs_host, const int32_t* box_child_ids,
+                         const void* box_centers, const int32_t* pstarts, const int32_t* pcounts,
+                         void* const* particles, const void* radii, void* bb_min, void* bb_max,
+                         int phases, void* stream)
+{
+    BT_PROF("bt_box_extents", (cudaStream_t)stream);
+    BT_DISPATCH(dtype, dim, box_extents_impl, nboxes, aligned, nlevels, level_start_box_nrs_host,
+                box_child_ids, box_centers, pstarts, pcounts, particles, radii, bb_min, bb_max, phases,
+                (cudaStream_t)stream);
+}
+
+int bt_box_info_local(int nboxes, int have_extent, const int32_t* local_start, const int32_t* local_count,
+                      const int32_t* local_nonchild, const uint8_t* has_children,
+                      const int32_t* source_numbers, int32_t* src3, int32_t* src_starts,
+                      int32_t* src_nonchild, int32_t* src_cumul, int32_t* tgt_starts,
+                      int32_t* tgt_nonchild, int32_t* tgt_cumul, void* stream)
+{
+    BT_PROF("bt_box_info", (cudaStream_t)stream);
+    if (nboxes <= 0) return BT_OK;
+    bt::box_info_local_kernel<<<bt::grid_for(nboxes, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        nboxes, have_extent, local_start, local_count, local_nonchild, has_children, source_numbers,
+        src3, src_starts, src_nonchild, src_cumul, tgt_starts, tgt_nonchild, tgt_cumul);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+
+int bt_box_info_global(int nboxes, int have_extent, const int32_t* box_start, const int32_t* box_count,
+                       const int32_t* box_nonchild, const uint8_t* has_children, const int32_t* src3,
+                       int32_t* src_starts, int32_t* src_nonchild, int32_t* src_cumul,
+                       int32_t* tgt_starts, int32_t* tgt_nonchild, int32_t* tgt_cumul,
+                       uint8_t* box_flags, void* stream)
+{
+    BT_PROF("bt_box_info", (cudaStream_t)stream);
+    if (nboxes <= 0) return BT_OK;
+    bt::box_info_global_kernel<<<bt::grid_for(nboxes, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        nboxes, have_extent, box_start, box_count, box_nonchild, has_children, src3, src_starts,
+        src_nonchild, src_cumul, tgt_starts, tgt_nonchild, tgt_cumul, box_flags);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
 }
 
 }  // extern "C"

@@ -10,17 +10,20 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .comm import SingleProcessComm, TorchDistComm
+from .comm import SingleProcessComm, ThreadComm, ThreadGroup, TorchDistComm
+from .exchange import exchange_particles, preorder
 from .local_traversal import generate_local_travs
-from .local_tree import LocalTree, box_to_user_rank, generate_local_tree
+from .local_tree import LocalTree, assemble_local_tree, box_to_user_rank, generate_local_tree
 from .partition import (BoxMasks, get_box_ids_dfs_order, get_box_masks, get_box_masks_sharded,
                         partition_segments, partition_segments_device, partition_work)
+from .tree_build import DistributedTree, build_distributed_tree
 
 __all__ = [
     "SingleProcessComm", "TorchDistComm", "LocalTree", "BoxMasks", "get_box_ids_dfs_order",
     "partition_segments", "partition_work", "get_box_masks", "generate_local_tree",
     "box_to_user_rank", "generate_local_travs", "broadcast_tree", "distributed_setup",
-    "get_box_masks_sharded", "allgather_particles", "sharded_setup",
+    "get_box_masks_sharded", "allgather_particles", "sharded_setup", "ThreadComm", "ThreadGroup",
+    "DistributedTree", "build_distributed_tree", "exchange_particles", "distributed_tree_setup",
 ]
 
 
@@ -157,3 +160,64 @@ def sharded_setup(actx, tree, traversal_builder, comm, cost_per_box=None,
     if merge_close_lists and local_tree.targets_have_extent:
         local_trav = local_trav.merge_close_lists(actx)
     return local_tree, local_trav, src_idx, tgt_idx
+
+
+def distributed_tree_setup(actx, dtree, traversal_builder, comm, cost_per_box=None,
+                           merge_close_lists=False):
+    """The tree/traversal part of ``make_distributed_wrangler``
+    (``distributed/__init__.py:156-266``) for a :class:`DistributedTree`: no rank holds all
+    particles and nothing is broadcast.  Collective over *comm*.
+
+    Every rank partitions the boxes itself (``partition.py:60-121``: DFS-order cost prefix, the
+    same deterministic arithmetic on the replicated box arrays), builds the traversal rows of
+    its responsible boxes and their ancestors to derive its box masks (``partition.py:330-357``),
+    all-gathers the masks, receives the sources of its point-source boxes and the targets of its
+    responsible boxes from their owners in one all-to-all each
+    (:func:`exchange_particles`, replacing ``local_tree.py:408-470``) and builds its local
+    traversal (``local_traversal.py:37-60``).  Local tree, local traversal and the index arrays
+    are identical to the reference flow's on the concatenated particle set.
+
+    Returns ``(local_tree, local_trav, src_idx, tgt_idx)``."""
+    from types import SimpleNamespace  # noqa: F401
+    rank, size = comm.Get_rank(), comm.Get_size()
+    with torch.cuda.stream(actx.stream), torch.cuda.device(actx.device):
+        if cost_per_box is None:
+            cost_per_box = (1.0 + dtree.box_source_counts_nonchild.double()
+                            + dtree.box_target_counts_nonchild.double())
+        dfs_order = get_box_ids_dfs_order(actx, dtree)
+        segs = partition_segments_device(actx, cost_per_box, dfs_order, size)
+        if segs is None:
+            cost_host = cost_per_box.cpu().numpy() if isinstance(cost_per_box, torch.Tensor) \
+                else np.asarray(cost_per_box)
+            segs = partition_segments(cost_host[dfs_order.cpu().numpy()], size)
+        seg = segs[rank]
+        responsible = dfs_order[int(seg[0]):int(seg[1])]
+        masks, _partial, need = get_box_masks_sharded(actx, dtree, responsible, traversal_builder)
+        shared = getattr(traversal_builder, "last_shared", None)
+        # every rank's masks: who needs which box's sources / targets / multipoles
+        mine = torch.stack([masks.point_src_boxes, masks.responsible_boxes,
+                            masks.multipole_src_boxes])
+        allm = comm.allgather_tensor(mine)                                   # [size, 3, nboxes]
+        if shared is not None and "dfs_rank" in shared:
+            pre_rank, subtree = shared["dfs_rank"], shared["subtree_size"]
+            pre_boxes = actx.empty(max(int(dtree.nboxes), 1), np.int32)
+            from .._cabi import check, dptr, load
+            check(load().bt_reverse_index(int(dtree.nboxes), dptr(pre_rank), dptr(pre_boxes),
+                                          actx.stream_handle), "bt_reverse_index")
+            pre = (pre_rank, pre_boxes, subtree)
+        else:
+            pre = preorder(actx, dtree)
+        src = exchange_particles(actx, comm, dtree, allm[:, 0].contiguous(),
+                                 masks.point_src_boxes, "source", pre)
+        tgt = exchange_particles(actx, comm, dtree, allm[:, 1].contiguous(),
+                                 masks.responsible_boxes, "target", pre)
+        local_tree = assemble_local_tree(actx, dtree, src, tgt, masks, allm[:, 2].contiguous(),
+                                         responsible)
+        local_trav, _ = traversal_builder(
+            actx, local_tree, source_boxes_mask=local_tree.responsible_boxes_mask,
+            source_parent_boxes_mask=local_tree.ancestor_mask, _colleague_row_mask=need,
+            _shared=shared)
+        traversal_builder.last_shared = None
+        if merge_close_lists and local_tree.targets_have_extent:
+            local_trav = local_trav.merge_close_lists(actx)
+    return local_tree, local_trav, src[5], tgt[5]

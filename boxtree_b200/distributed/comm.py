@@ -29,6 +29,12 @@ class SingleProcessComm:
     def gather_objects(self, obj, root=0):
         return [obj]
 
+    def allreduce_(self, t, op="sum"):
+        return t
+
+    def all_to_all_bytes(self, send, send_splits, recv_splits):
+        return send
+
     def barrier(self):
         pass
 
@@ -107,5 +113,105 @@ class TorchDistComm:
         self.dist.gather_object(obj, out, dst=root, group=self.group)
         return out
 
+    def allreduce_(self, t, op="sum"):
+        """In-place all-reduce (sum / min / max) of a contiguous tensor."""
+        ops = {"sum": self.dist.ReduceOp.SUM, "min": self.dist.ReduceOp.MIN,
+               "max": self.dist.ReduceOp.MAX}
+        assert t.is_contiguous()
+        if t.device == self.device:
+            self.dist.all_reduce(t, op=ops[op], group=self.group)
+        else:
+            staged = t.to(self.device)
+            self.dist.all_reduce(staged, op=ops[op], group=self.group)
+            t.copy_(staged)
+        return t
+
+    def all_to_all_bytes(self, send, send_splits, recv_splits):
+        """Variable all-to-all of a uint8 buffer: ``send_splits[d]`` bytes go to rank *d*,
+        ``recv_splits[s]`` bytes arrive from rank *s* (NCCL: grouped send/recv over NVLink)."""
+        src_device = send.device
+        send = self._stage(send.contiguous())
+        recv = torch.empty(int(sum(recv_splits)), dtype=torch.uint8, device=send.device)
+        self.dist.all_to_all_single(recv, send, output_split_sizes=[int(x) for x in recv_splits],
+                                    input_split_sizes=[int(x) for x in send_splits],
+                                    group=self.group)
+        return recv.to(src_device)
+
     def barrier(self):
         self.dist.barrier(group=self.group)
+
+
+class ThreadGroup:
+    """Shared state of :class:`ThreadComm` ranks (one Python thread per rank)."""
+
+    def __init__(self, size):
+        import threading
+        self.size = size
+        self.slots = [None] * size
+        self.barrier = threading.Barrier(size)
+
+
+class ThreadComm:
+    """In-process communicator: every rank is a thread of this process (all ranks may share one
+    GPU).  Same interface as :class:`TorchDistComm`; used to exercise the collective code paths
+    of the distributed build where only one device is available."""
+
+    def __init__(self, group: ThreadGroup, rank: int):
+        self.g, self.rank = group, rank
+
+    def Get_rank(self):  # noqa: N802
+        return self.rank
+
+    def Get_size(self):  # noqa: N802
+        return self.g.size
+
+    def _exchange(self, obj):
+        if isinstance(obj, torch.Tensor) and obj.is_cuda:
+            torch.cuda.synchronize(obj.device)
+        self.g.slots[self.rank] = obj
+        self.g.barrier.wait()
+        out = list(self.g.slots)
+        self.g.barrier.wait()
+        return out
+
+    def bcast_array(self, arr, root=0):
+        return self._exchange(arr)[root]
+
+    def scatter_rows(self, rows, root=0):
+        return np.asarray(self._exchange(rows)[root][self.rank])
+
+    def allgather_tensor(self, t):
+        return torch.stack([x.to(t.device) for x in self._exchange(t.contiguous().clone())])
+
+    def gather_objects(self, obj, root=0):
+        out = self._exchange(obj)
+        return out if self.rank == root else None
+
+    def allreduce_(self, t, op="sum"):
+        allv = torch.stack([x.to(t.device) for x in self._exchange(t.clone())])
+        if op == "sum":
+            t.copy_(allv.sum(dim=0, dtype=t.dtype))
+        elif op == "min":
+            t.copy_(allv.amin(dim=0))
+        else:
+            t.copy_(allv.amax(dim=0))
+        if t.is_cuda:
+            torch.cuda.synchronize(t.device)
+        self.g.barrier.wait()
+        return t
+
+    def all_to_all_bytes(self, send, send_splits, recv_splits):
+        allv = self._exchange((send.clone(), [int(x) for x in send_splits]))
+        parts = []
+        for s, (buf, splits) in enumerate(allv):
+            off = sum(splits[:self.rank])
+            assert splits[self.rank] == int(recv_splits[s])
+            parts.append(buf[off:off + splits[self.rank]].to(send.device))
+        out = torch.cat(parts) if parts else send[:0]
+        if out.is_cuda:
+            torch.cuda.synchronize(out.device)
+        self.g.barrier.wait()
+        return out
+
+    def barrier(self):
+        self.g.barrier.wait()

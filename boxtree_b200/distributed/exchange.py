@@ -1,0 +1,126 @@
+"""Particle redistribution of the distributed build: ONE all-to-all per particle kind.
+
+Replaces the root-side ``fetch_local_particles`` + scatter of the reference
+(``boxtree/distributed/local_tree.py:124-151, 198-284, 408-495``).  After
+:func:`boxtree_b200.distributed.tree_build.build_distributed_tree` every rank holds the
+global box arrays and its own input particles in tree order.  Rank *d*'s local tree needs
+the sources of its ``point_src_boxes`` and the targets of its ``responsible_boxes``
+(``local_tree.py:430-470``): the owners pack one record per needed particle and destination
+(``bt_dist_pack_records``), the records travel in one variable all-to-all (NCCL grouped
+send/recv over NVLink), and the receiver scatters them to their place in the global tree
+order restricted to its boxes (``bt_dist_unpack_records``).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import _cabi
+from .._cabi import check, dptr
+from ..array_context import make_obj_array
+
+
+def _record_bytes(coord_dtype, dims, have_radii):
+    return np.dtype(coord_dtype).itemsize * (dims + (1 if have_radii else 0)) + 8
+
+
+def preorder(actx, tree):
+    """``(rank, boxes, subtree_size)`` of the boxes' pre-order with children in Morton order:
+    the order of the global tree's particle arrays (own particles, then the children's)."""
+    lib = _cabi.load()
+    nb = int(tree.nboxes)
+    sh = actx.stream_handle
+    size = actx.empty(max(nb, 1), np.int32)
+    rank = actx.empty(max(nb, 1), np.int32)
+    boxes = actx.empty(max(nb, 1), np.int32)
+    check(lib.bt_trav_dfs_rank(int(tree.dimensions), nb, int(tree.aligned_nboxes),
+                               int(tree.nlevels), dptr(tree.level_start_box_nrs.to(torch.int32)),
+                               dptr(tree.box_child_ids), dptr(size), dptr(rank), sh),
+          "bt_trav_dfs_rank")
+    check(lib.bt_reverse_index(nb, dptr(rank), dptr(boxes), sh), "bt_reverse_index")
+    return rank, boxes, size
+
+
+def exchange_particles(actx, comm, dtree, masks_all_ranks, my_mask, kind, pre):
+    """Collective.  *masks_all_ranks* ``[nranks, nboxes]`` int8: rank *d* needs the *kind*
+    (``"source"`` / ``"target"``) particles of the boxes with ``masks_all_ranks[d][b] != 0``;
+    *my_mask* is this rank's row.  *pre* = :func:`preorder` of the tree.
+
+    :returns: ``(particles, radii, local_starts, local_counts_nonchild, local_counts_cumul,
+        idx)`` like ``construct_local_particles_and_lists`` (``local_tree.py:198-284``); *idx*
+        (int64) is every local particle's position in the global tree order."""
+    lib = _cabi.load()
+    sh = actx.stream_handle
+    nb = int(dtree.nboxes)
+    dims = int(dtree.dimensions)
+    nranks, rank = comm.Get_size(), comm.Get_rank()
+    dcode = _cabi.dtype_code(dtree.coord_dtype)
+    src = kind == "source"
+    parts = list(dtree.sources if src else dtree.targets)
+    have_radii = dtree.sources_have_extent if src else dtree.targets_have_extent
+    radii = (dtree.source_radii if src else dtree.target_radii) if have_radii else None
+    lstart = dtree.local_box_source_starts if src else dtree.local_box_target_starts
+    lown = dtree.local_box_source_counts_nonchild if src else \
+        dtree.local_box_target_counts_nonchild
+    rank_excl = dtree.source_rank_offsets if src else dtree.target_rank_offsets
+    gstart = dtree.box_source_starts if src else dtree.box_target_starts
+    gown = dtree.box_source_counts_nonchild if src else dtree.box_target_counts_nonchild
+    n = int(parts[0].shape[0])
+    recbytes = _record_bytes(dtree.coord_dtype, dims, have_radii)
+
+    # {{{ pack: destination-major records of the needed particles this rank owns
+
+    dest_bits = actx.empty(max(nb, 1), np.int32)
+    check(lib.bt_dist_mask_bits(nb, nranks, dptr(masks_all_ranks.contiguous()), dptr(dest_bits), sh),
+          "bt_dist_mask_bits")
+    pbox = actx.empty(max(n, 1), np.int32)
+    check(lib.bt_dist_particle_box(nb, dptr(lstart), dptr(lown), dptr(pbox), sh),
+          "bt_dist_particle_box")
+    # every particle goes to at most all ranks; the usual case is 1 + a thin halo
+    dest_offsets = actx.zeros(nranks + 1, np.int64)
+    sendbuf = None
+    cap = max(n, 1) * 2
+    while True:
+        sendbuf = actx.empty(cap * recbytes, np.uint8)
+        # a record is only written when it fits (the scan clamps nothing): size first
+        check(lib.bt_dist_pack_records(dcode, nranks, dims, n, dptr(pbox), dptr(dest_bits),
+                                       _cabi.ptr_array(parts), dptr(radii), dptr(lstart),
+                                       dptr(rank_excl), dptr(sendbuf), dptr(dest_offsets), sh,
+                                       cap), "bt_dist_pack_records")
+        # all ranks' offsets in one collective, one readback
+        all_off = comm.allgather_tensor(dest_offsets).cpu().numpy()      # [nranks, nranks + 1]
+        need = int(all_off[rank, nranks])
+        if need <= cap:
+            break
+        cap = need
+    counts = np.diff(all_off, axis=1)                                   # [sender, dest]
+
+    # }}}
+
+    send_splits = [int(c) * recbytes for c in counts[rank]]
+    recv_counts = counts[:, rank]
+    recv_splits = [int(c) * recbytes for c in recv_counts]
+    nrecv = int(recv_counts.sum())
+    recvbuf = comm.all_to_all_bytes(sendbuf[:need * recbytes], send_splits, recv_splits)
+
+    # {{{ unpack into the rank's local arrays (global tree order restricted to its boxes)
+
+    pre_rank, pre_boxes, subtree = pre
+    prefix = actx.empty(nb + 1, np.int32)
+    lstarts = actx.empty(nb, np.int32)
+    lnonchild = actx.empty(nb, np.int32)
+    lcumul = actx.empty(nb, np.int32)
+    check(lib.bt_dist_local_ranges(nb, dptr(my_mask), dptr(gown), dptr(pre_rank), dptr(pre_boxes),
+                                   dptr(subtree), dptr(prefix), dptr(lstarts), dptr(lnonchild),
+                                   dptr(lcumul), sh), "bt_dist_local_ranges")
+    coord_dtype = dtree.coord_dtype
+    local = [actx.empty(nrecv, coord_dtype) for _ in range(dims)]
+    local_radii = actx.empty(nrecv, coord_dtype) if have_radii else None
+    idx = actx.empty(nrecv, np.int64)
+    check(lib.bt_dist_unpack_records(dcode, dims, nrecv, int(have_radii), dptr(recvbuf),
+                                     dptr(lstarts), dptr(gstart), _cabi.ptr_array(local),
+                                     dptr(local_radii), dptr(idx), sh), "bt_dist_unpack_records")
+
+    # }}}
+
+    return make_obj_array(local), local_radii, lstarts, lnonchild, lcumul, idx

@@ -98,24 +98,35 @@ def generate_local_tree(actx, global_traversal, responsible_boxes_list, comm,
             gt.box_target_counts_nonchild, gt.box_target_counts_cumul)
         if multipole_masks_all_ranks is None:
             multipole_masks_all_ranks = comm.allgather_tensor(masks.multipole_src_boxes)
-        b2u_starts, b2u_lists = box_to_user_rank(actx, _dev(actx, multipole_masks_all_ranks))
-        local_flags = _dev(actx, gt.box_flags).clone()
-        check(lib.bt_dist_modify_target_flags(nb, dptr(tgt[3]), dptr(tgt[4]), dptr(local_flags),
-                                              actx.stream_handle), "bt_dist_modify_target_flags")
-        base = {f.name: getattr(gt, f.name) for f in fields(Tree)}
-        base.update(
-            sources=src[0], targets=tgt[0],
-            source_radii=src[1] if gt.sources_have_extent else None,
-            target_radii=tgt[1] if gt.targets_have_extent else None,
-            box_source_starts=src[2], box_source_counts_nonchild=src[3],
-            box_source_counts_cumul=src[4], box_target_starts=tgt[2],
-            box_target_counts_nonchild=tgt[3], box_target_counts_cumul=tgt[4],
-            box_flags=local_flags, user_source_ids=None, sorted_target_ids=None)
-        resp = responsible_boxes_list
-        if not isinstance(resp, torch.Tensor):
-            resp = actx.from_numpy(np.asarray(resp, np.int32))
-        local_tree = LocalTree(
-            **base, box_to_user_rank_starts=b2u_starts, box_to_user_rank_lists=b2u_lists,
-            responsible_boxes_list=resp, responsible_boxes_mask=masks.responsible_boxes,
-            ancestor_mask=masks.ancestor_boxes)
+        local_tree = assemble_local_tree(actx, gt, src, tgt, masks, multipole_masks_all_ranks,
+                                         responsible_boxes_list)
     return actx.freeze(local_tree), src[5], tgt[5]
+
+
+def assemble_local_tree(actx, gt, src, tgt, masks, multipole_masks_all_ranks,
+                        responsible_boxes_list):
+    """The :class:`LocalTree` record of ``local_tree.py:430-495`` from the rank's local
+    particles *src* / *tgt* (tuples as returned by ``_local_particles_and_lists``), its box
+    masks and every rank's multipole mask."""
+    lib = _cabi.load()
+    nb = int(gt.nboxes)
+    b2u_starts, b2u_lists = box_to_user_rank(actx, _dev(actx, multipole_masks_all_ranks))
+    local_flags = _dev(actx, gt.box_flags).clone()
+    check(lib.bt_dist_modify_target_flags(nb, dptr(tgt[3]), dptr(tgt[4]), dptr(local_flags),
+                                          actx.stream_handle), "bt_dist_modify_target_flags")
+    base = {f.name: getattr(gt, f.name) for f in fields(Tree)}
+    base.update(
+        sources=src[0], targets=tgt[0],
+        source_radii=src[1] if gt.sources_have_extent else None,
+        target_radii=tgt[1] if gt.targets_have_extent else None,
+        box_source_starts=src[2], box_source_counts_nonchild=src[3],
+        box_source_counts_cumul=src[4], box_target_starts=tgt[2],
+        box_target_counts_nonchild=tgt[3], box_target_counts_cumul=tgt[4],
+        box_flags=local_flags, user_source_ids=None, sorted_target_ids=None)
+    resp = responsible_boxes_list
+    if not isinstance(resp, torch.Tensor):
+        resp = actx.from_numpy(np.asarray(resp, np.int32))
+    return LocalTree(
+        **base, box_to_user_rank_starts=b2u_starts, box_to_user_rank_lists=b2u_lists,
+        responsible_boxes_list=resp, responsible_boxes_mask=masks.responsible_boxes,
+        ancestor_mask=masks.ancestor_boxes)

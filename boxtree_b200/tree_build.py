@@ -21,9 +21,9 @@ import numpy as np
 import torch
 
 from . import _cabi
-from ._cabi import (CTL_LR_FOUND, CTL_NBOXES, CTL_NBOXES_FINAL, CTL_NHUGE, CTL_NSPLIT_REGULAR,
-                    CTL_OVERFLOW, CTL_OVERSIZE, CTL_SIZE, bt_box_out, bt_particles, bt_pool, check,
-                    dptr)
+from ._cabi import (CTL_LR_FOUND, CTL_NBOXES, CTL_NBOXES_FINAL, CTL_NHUGE, CTL_NSPLIT,
+                    CTL_NSPLIT_REGULAR, CTL_OVERFLOW, CTL_OVERSIZE, CTL_SIZE, STEP_ALL, STEP_COMMIT,
+                    STEP_CREATE, STEP_DECIDE, bt_box_out, bt_particles, bt_pool, check, dptr)
 from .array_context import TorchArrayContext, make_obj_array, numpy_dtype_of
 from .tree import Tree, box_flags_enum
 
@@ -39,8 +39,9 @@ _LEAF_SMEM_CAP = 4096
 class _Pool:
     """Creation-order box pool (device), grown by doubling."""
 
-    def __init__(self, actx, dim, coord_torch_dtype, capacity):
+    def __init__(self, actx, dim, coord_torch_dtype, capacity, distributed=False):
         self.actx, self.dim, self.cdt = actx, dim, coord_torch_dtype
+        self.distributed = distributed
         self.capacity = 0
         self.arrays: dict[str, torch.Tensor] = {}
         self.center: list[torch.Tensor] = []
@@ -54,6 +55,9 @@ class _Pool:
         spec = {"start": torch.int32, "count": torch.int32, "level": torch.uint8,
                 "parent": torch.int32, "child0": torch.int32, "has_children": torch.uint8,
                 "force_split": torch.uint8, "nonchild": torch.int32}
+        if self.distributed:
+            # sums over ranks of start/count/nonchild (include/boxtree_b200.h, bt_pool)
+            spec.update(gstart=torch.int32, gcount=torch.int32, gnonchild=torch.int32)
         self.arrays = {}
         for name, dt in spec.items():
             a = torch.zeros(capacity, dtype=dt, device=dev)
@@ -66,8 +70,15 @@ class _Pool:
             if n_old:
                 a[:n_old].copy_(oldc[ax])
             self.center.append(a)
+        # the retry after CTL_OVERFLOW re-reads the split list of the decide scan: keep it
+        old_split, old_flag = getattr(self, "split_list", None), getattr(self, "flag", None)
         self.split_list = torch.empty(capacity, dtype=torch.int32, device=dev)
         self.flag = torch.empty(capacity, dtype=torch.uint8, device=dev)
+        if n_old:
+            self.split_list[:n_old].copy_(old_split)
+            self.flag[:n_old].copy_(old_flag)
+        self.xch = torch.empty(3 * capacity, dtype=torch.int32, device=dev) \
+            if self.distributed else None
         self.capacity = capacity
 
     def ensure(self, capacity):
@@ -85,6 +96,9 @@ class _Pool:
         for ax in range(self.dim):
             p.center[ax] = dptr(self.center[ax])
         p.capacity = self.capacity
+        if self.distributed:
+            p.gstart, p.gcount = dptr(self.arrays["gstart"]), dptr(self.arrays["gcount"])
+            p.gnonchild, p.xch = dptr(self.arrays["gnonchild"]), dptr(self.xch)
         return p
 
 
@@ -216,6 +230,13 @@ class TreeBuilder:
         if nsrcntgts >= 2**30:
             raise NotImplementedError("more than 2**30 particles per device are not supported")
 
+        # distributed build (boxtree_b200/distributed/tree_build.py): the arguments are this
+        # rank's slice of the global particle set; per-box counts are summed over `comm`
+        comm = kwargs.get("comm")
+        dist = comm is not None
+        if dist and refine_weights is not None:
+            raise NotImplementedError("refine weights are not supported by the distributed build")
+
         # }}}
 
         # {{{ refine weights (tree_build.py:405-452)
@@ -250,6 +271,14 @@ class TreeBuilder:
             total_refine_weight = int(refine_weights.sum(dtype=torch.int64))
         else:
             total_refine_weight = nsrcntgts
+        nsrcntgts_global = nsrcntgts
+        if dist:
+            gn = torch.tensor([nsources, ntargets], dtype=torch.int64, device=actx.device)
+            comm.allreduce_(gn, "sum")
+            nsources_global, ntargets_global = (int(x) for x in gn.cpu())
+            nsrcntgts_global = total_refine_weight = nsources_global + ntargets_global
+            if nsrcntgts_global >= 2**31 - 1:
+                raise NotImplementedError("more than 2**31 - 2 particles in a global tree")
         max_leaf_refine_weight = int(max_leaf_refine_weight)
 
         # }}}
@@ -277,12 +306,17 @@ class TreeBuilder:
 
             # {{{ bounding box (tree_build.py:458-508)
 
-            if nsrcntgts == 0:
+            if nsrcntgts_global == 0:
                 raise ValueError("cannot build a tree without particles")
 
             bbox_dev = actx.empty(2 * dimensions, coord_dtype)
             check(lib.bt_bounding_box(dcode, dimensions, C.byref(P), dptr(bbox_dev), sh),
                   "bt_bounding_box")
+            if dist:        # min/max are exact: the all-reduced box is the global one
+                mins, maxs = bbox_dev[0::2].contiguous(), bbox_dev[1::2].contiguous()
+                comm.allreduce_(mins, "min")
+                comm.allreduce_(maxs, "max")
+                bbox_dev = torch.stack([mins, maxs], dim=1).reshape(-1)
             bbox_auto = bbox_dev.cpu().numpy()
             auto_min = bbox_auto[0::2].copy()
             auto_max = bbox_auto[1::2].copy()
@@ -321,9 +355,10 @@ class TreeBuilder:
                                    _cabi.darray(bbox_max), EXTENT_NORM_CODE[srcntgts_extent_norm],
                                    float(stick_out_factor), dptr(key_bufs[0]), sh), "bt_make_keys")
             in_alt = C.c_int(0)
-            check(lib.bt_sort_particles(nsrcntgts, dimensions, have_ext, dptr(key_bufs[0]),
-                                        dptr(key_bufs[1]), dptr(id_bufs[0]), dptr(id_bufs[1]),
-                                        C.byref(in_alt), sh), "bt_sort_particles")
+            if nsrcntgts:
+                check(lib.bt_sort_particles(nsrcntgts, dimensions, have_ext, dptr(key_bufs[0]),
+                                            dptr(key_bufs[1]), dptr(id_bufs[0]), dptr(id_bufs[1]),
+                                            C.byref(in_alt), sh), "bt_sort_particles")
             keys = key_bufs[in_alt.value]
             ids = id_bufs[in_alt.value]
             del key_bufs, id_bufs
@@ -343,12 +378,17 @@ class TreeBuilder:
                 nboxes_guess = int(nb * ((max_leaf_refine_weight + total_refine_weight - 1)
                                          // max_leaf_refine_weight)) + 1
             assert nboxes_guess > 0
-            pool = _Pool(actx, dimensions, coord_tdtype, max(int(nboxes_guess), 2))
+            pool = _Pool(actx, dimensions, coord_tdtype, max(int(nboxes_guess), 2), dist)
             ctl = actx.zeros(CTL_SIZE, np.int32)
             ctl_host = torch.empty(CTL_SIZE, dtype=torch.int32, pin_memory=True)
             check(lib.bt_pool_init(dcode, dimensions, C.byref(pool.struct()), nsrcntgts, have_ext,
                                    dptr(keys), _cabi.darray(root_center), dptr(ctl), sh),
                   "bt_pool_init")
+            if dist:        # the root holds every rank's particles
+                g = torch.stack([pool.arrays["count"][0], pool.arrays["nonchild"][0]])
+                comm.allreduce_(g, "sum")
+                pool.arrays["gcount"][0:1].copy_(g[0:1])
+                pool.arrays["gnonchild"][0:1].copy_(g[1:2])
 
             nlevels_max = 2 * (np.finfo(coord_dtype).nmant + 1)
             max_key_level = lib.bt_max_key_level(dimensions)
@@ -379,29 +419,38 @@ class TreeBuilder:
                     bound = min(ncand, total_refine_weight // (max_leaf_refine_weight + 1) + 1)
                 else:
                     bound = min(ncand, nboxes - level_block_start
-                                + (1024 if level_restrict else 0))
+                                + (int(kwargs.get("_lr_slack", 1024)) if level_restrict else 0))
                 pool.ensure(nboxes + nb * bound)
 
                 skip_if_no_regular = int(bool(srcntgts_have_extent)
                                          and not final_level_restrict_iteration)
 
-                def run_step(run_decide):
+                def run_step(phases):
                     check(lib.bt_level_step(
                         dcode, dimensions, C.byref(pool.struct()), dptr(keys), dptr(wprefix),
                         dptr(ctl), dptr(pool.split_list), dptr(pool.flag), lo, nboxes, level,
                         max_leaf_refine_weight, int(adaptive), int(level_restrict), have_ext,
-                        skip_if_no_regular, float(root_extent), run_decide, sh), "bt_level_step")
-                    if level_restrict and not final_level_restrict_iteration:
+                        skip_if_no_regular, float(root_extent), phases, sh), "bt_level_step")
+                    if phases & STEP_COMMIT and level_restrict \
+                            and not final_level_restrict_iteration:
                         check(lib.bt_level_restrict(dcode, dimensions, C.byref(pool.struct()),
                                                     dptr(ctl), level, pool.capacity,
                                                     float(root_extent), sh), "bt_level_restrict")
 
-                run_step(1)
+                # one GPU: decide + children + commit in one go; distributed: the children's
+                # local (lower bound, count, nonchild) are summed over the ranks before the commit
+                first = STEP_DECIDE | STEP_CREATE if dist else STEP_ALL
+                run_step(first)
                 h = read_ctl()
                 while h[CTL_OVERFLOW]:
                     nreallocs += 1
-                    pool.ensure(nboxes + nb * int(h[_cabi.CTL_NSPLIT]))
-                    run_step(0)
+                    pool.ensure(nboxes + nb * int(h[CTL_NSPLIT]))
+                    run_step(first & ~STEP_DECIDE)
+                    h = read_ctl()
+                if dist:
+                    if h[CTL_NSPLIT] and not (skip_if_no_regular and not h[CTL_NSPLIT_REGULAR]):
+                        comm.allreduce_(pool.xch[:3 * nb * int(h[CTL_NSPLIT])], "sum")
+                    run_step(STEP_COMMIT)
                     h = read_ctl()
 
                 nsplit_regular = int(h[CTL_NSPLIT_REGULAR])
@@ -471,6 +520,15 @@ class TreeBuilder:
             out.box_centers = dptr(box_centers)
             out.has_children = dptr(box_has_children)
             out.real_children = dptr(box_real_children)
+            if dist:        # ranges of the boxes in this rank's particles
+                lbox_start = actx.empty(nfinal, np.int32)
+                lbox_count = actx.empty(nfinal, np.int32)
+                lbox_nonchild = actx.empty(nfinal, np.int32)
+                out.local_start, out.local_count = dptr(lbox_start), dptr(lbox_count)
+                out.local_nonchild = dptr(lbox_nonchild)
+            else:
+                lbox_start, lbox_count = box_srcntgt_starts, box_srcntgt_counts_cumul
+                lbox_nonchild = box_srcntgt_counts_nonchild
             check(lib.bt_gather_boxes(dcode, dimensions, C.byref(pool.struct()), have_ext,
                                       dptr(src_of_new), dptr(map_old2new), nfinal, aligned_nboxes,
                                       C.byref(out), sh), "bt_gather_boxes")
@@ -481,8 +539,8 @@ class TreeBuilder:
 
             big_list = actx.empty(max(nfinal, 1), np.int32)
             huge_list = actx.empty(max(nfinal, 1), np.int32)
-            check(lib.bt_leaf_fixup(nfinal, dptr(box_srcntgt_starts),
-                                    dptr(box_srcntgt_counts_cumul), dptr(box_real_children),
+            check(lib.bt_leaf_fixup(nfinal, dptr(lbox_start),
+                                    dptr(lbox_count), dptr(box_real_children),
                                     dptr(ids), dptr(ctl), dptr(big_list), nfinal, dptr(huge_list),
                                     sh), "bt_leaf_fixup")
             leaves_bounded = (refine_weights is None and not srcntgts_have_extent and adaptive
@@ -492,8 +550,8 @@ class TreeBuilder:
                 nhuge = int(h[CTL_NHUGE])
                 if nhuge:
                     hl = huge_list[:nhuge].cpu().numpy()
-                    st = box_srcntgt_starts.cpu().numpy()
-                    cn = box_srcntgt_counts_cumul.cpu().numpy()
+                    st = lbox_start.cpu().numpy()
+                    cn = lbox_count.cpu().numpy()
                     for b in hl:
                         seg = ids[int(st[b]):int(st[b]) + int(cn[b])]
                         check(lib.bt_sort_u32_segment(int(cn[b]), dptr(seg), sh),
@@ -543,6 +601,7 @@ class TreeBuilder:
             # {{{ per-box particle ranges and flags (tree_build.py:1666-1723)
 
             box_flags = actx.empty(nfinal, box_flags_enum.dtype)
+
             if sources_are_targets:
                 box_source_starts = box_target_starts = box_srcntgt_starts
                 box_source_counts_cumul = box_target_counts_cumul = box_srcntgt_counts_cumul
@@ -555,14 +614,37 @@ class TreeBuilder:
                 box_target_starts = actx.empty(nfinal, np.int32)
                 box_target_counts_cumul = actx.empty(nfinal, np.int32)
                 box_target_counts_nonchild = actx.empty(nfinal, np.int32)
-            check(lib.bt_box_info(
-                nfinal, int(sources_are_targets), have_ext, dptr(box_srcntgt_starts),
-                dptr(box_srcntgt_counts_cumul), dptr(box_srcntgt_counts_nonchild),
-                dptr(box_has_children), dptr(source_numbers),
-                dptr(box_source_starts), dptr(box_source_counts_nonchild),
-                dptr(box_source_counts_cumul), dptr(box_target_starts),
-                dptr(box_target_counts_nonchild), dptr(box_target_counts_cumul),
-                dptr(box_flags), sh), "bt_box_info")
+            local_ranges = None
+            if not dist or sources_are_targets:
+                check(lib.bt_box_info(
+                    nfinal, int(sources_are_targets), have_ext, dptr(box_srcntgt_starts),
+                    dptr(box_srcntgt_counts_cumul), dptr(box_srcntgt_counts_nonchild),
+                    dptr(box_has_children), dptr(source_numbers),
+                    dptr(box_source_starts), dptr(box_source_counts_nonchild),
+                    dptr(box_source_counts_cumul), dptr(box_target_starts),
+                    dptr(box_target_counts_nonchild), dptr(box_target_counts_cumul),
+                    dptr(box_flags), sh), "bt_box_info")
+                if dist:    # the same on the rank's own ranges: only leaves own particles
+                    l_own = torch.where(box_has_children != 0, torch.zeros_like(lbox_count),
+                                        lbox_count)
+                    local_ranges = (lbox_start, l_own, lbox_count) * 2
+            else:
+                # rank-local source counts per box -> sums over ranks -> global ranges and flags
+                src3 = actx.empty(3 * nfinal, np.int32)
+                local_ranges = tuple(actx.empty(nfinal, np.int32) for _ in range(6))
+                check(lib.bt_box_info_local(
+                    nfinal, have_ext, dptr(lbox_start), dptr(lbox_count), dptr(lbox_nonchild),
+                    dptr(box_has_children), dptr(source_numbers), dptr(src3),
+                    *[dptr(a) for a in local_ranges], sh), "bt_box_info_local")
+                comm.allreduce_(src3, "sum")
+                check(lib.bt_box_info_global(
+                    nfinal, have_ext, dptr(box_srcntgt_starts), dptr(box_srcntgt_counts_cumul),
+                    dptr(box_srcntgt_counts_nonchild), dptr(box_has_children), dptr(src3),
+                    dptr(box_source_starts), dptr(box_source_counts_nonchild),
+                    dptr(box_source_counts_cumul), dptr(box_target_starts),
+                    dptr(box_target_counts_nonchild), dptr(box_target_counts_cumul),
+                    dptr(box_flags), sh), "bt_box_info_global")
+                del src3
 
             # }}}
 
@@ -576,19 +658,29 @@ class TreeBuilder:
                 bb_tgt_min = actx.zeros((dimensions, aligned_nboxes), coord_dtype)
                 bb_tgt_max = actx.zeros((dimensions, aligned_nboxes), coord_dtype)
 
+            # own ranges of the boxes in the (rank's) tree-ordered particle arrays
+            own_src = (local_ranges[0], local_ranges[1]) if dist else \
+                (box_source_starts, box_source_counts_nonchild)
+            own_tgt = (local_ranges[3], local_ranges[4]) if dist else \
+                (box_target_starts, box_target_counts_nonchild)
             rounds = [(sources, out_source_radii if sources_have_extent else None,
-                       box_source_starts, box_source_counts_nonchild, bb_src_min, bb_src_max)]
+                       own_src[0], own_src[1], bb_src_min, bb_src_max)]
             if not sources_are_targets:
                 rounds.append((tgts, out_target_radii if targets_have_extent else None,
-                               box_target_starts, box_target_counts_nonchild, bb_tgt_min,
-                               bb_tgt_max))
+                               own_tgt[0], own_tgt[1], bb_tgt_min, bb_tgt_max))
             ls_host = (C.c_int32 * (nlevels + 1))(*[int(x) for x in level_start_box_nrs])
             for parts, radii, pstarts, pcounts, bmin, bmax in rounds:
-                check(lib.bt_box_extents(
-                    dcode, dimensions, nfinal, aligned_nboxes, nlevels, ls_host,
-                    dptr(box_child_ids), dptr(box_centers), dptr(pstarts), dptr(pcounts),
-                    _cabi.ptr_array(list(parts)), dptr(radii), dptr(bmin), dptr(bmax), sh),
-                    "bt_box_extents")
+                # distributed: min/max over the rank's own particles, all-reduced (exact), then
+                # the child merge on the global values
+                for phases in ((1, 2) if dist else (3,)):
+                    check(lib.bt_box_extents_phase(
+                        dcode, dimensions, nfinal, aligned_nboxes, nlevels, ls_host,
+                        dptr(box_child_ids), dptr(box_centers), dptr(pstarts), dptr(pcounts),
+                        _cabi.ptr_array(list(parts)), dptr(radii), dptr(bmin), dptr(bmax), phases,
+                        sh), "bt_box_extents")
+                    if dist and phases == 1:
+                        comm.allreduce_(bmin, "min")
+                        comm.allreduce_(bmax, "max")
 
             # }}}
 
@@ -596,10 +688,36 @@ class TreeBuilder:
             evt = torch.cuda.Event()
             evt.record(stream)
 
+            rank_excl = None
+            if dist:
+                # own particles of lower ranks per box (exclusive scan over ranks): a particle's
+                # place in the global tree order is box start + rank_excl + index in the own range
+                own = torch.stack([own_src[1], own_tgt[1]])
+                allown = comm.allgather_tensor(own)                       # [size, 2, nboxes]
+                r = comm.Get_rank()
+                rank_excl = allown[:r].sum(dim=0, dtype=torch.int32) if r else torch.zeros_like(own)
+                del allown
+
         self.last_stats = {"level_iterations": niterations, "nboxes_pre_prune": nboxes,
                            "reallocs": nreallocs}
 
-        tree = Tree(
+        extra = {}
+        cls = Tree
+        if dist:
+            from .distributed.tree_build import DistributedTree
+            cls = DistributedTree
+            extra = dict(
+                local_box_source_starts=local_ranges[0],
+                local_box_source_counts_nonchild=local_ranges[1],
+                local_box_source_counts_cumul=local_ranges[2],
+                local_box_target_starts=local_ranges[3],
+                local_box_target_counts_nonchild=local_ranges[4],
+                local_box_target_counts_cumul=local_ranges[5],
+                source_rank_offsets=rank_excl[0], target_rank_offsets=rank_excl[1],
+                nsources_global=nsources_global, ntargets_global=ntargets_global,
+                rank=comm.Get_rank(), nranks=comm.Get_size())
+        tree = cls(
+            **extra,
             sources_are_targets=sources_are_targets,
             sources_have_extent=sources_have_extent,
             targets_have_extent=targets_have_extent,

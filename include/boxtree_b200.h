@@ -67,6 +67,15 @@ typedef struct {
     int32_t *nonchild;          /* particles that stop in this box (extents) */
     void *center[3];
     int32_t capacity;
+    /* Distributed build (boxtree_b200/distributed/tree_build.py): start/count/nonchild above
+     * are the box's range in THIS rank's sorted particles; gstart/gcount/gnonchild hold the
+     * sums over all ranks (the global tree's values) and xch [3 * 2^dim * nsplit] receives
+     * (lower bound, count, nonchild) of the children created by BT_STEP_CREATE, which the host
+     * all-reduces before BT_STEP_COMMIT.  All four NULL on one GPU (global == local). */
+    int32_t *gstart;
+    int32_t *gcount;
+    int32_t *gnonchild;
+    int32_t *xch;
 } bt_pool;
 
 typedef struct {
@@ -79,6 +88,9 @@ typedef struct {
     void *box_centers;          /* [dim, aligned_nboxes] */
     uint8_t *has_children;
     uint8_t *real_children;
+    int32_t *local_start;       /* distributed build only (else NULL): the box's range in */
+    int32_t *local_count;       /* this rank's sorted particles                            */
+    int32_t *local_nonchild;
 } bt_box_out;
 
 /* instrumentation used by bench.py: kernels launched so far; optional CUDA-event
@@ -127,12 +139,18 @@ int bt_pool_init(int dtype, int dim, const bt_pool *pool, int64_t n, int have_ex
 
 /* One iteration of the level loop (tree_build.py:698-1121) on per-box data:
  * split_box_id_scan (tree_build_kernels.py:514-640) + box_splitter (:646-711).
- * Boxes [lo, nboxes) of the pool are examined.  run_decide = 0 repeats only the
- * child creation after the caller enlarged the pool (BT_CTL_OVERFLOW). */
+ * Boxes [lo, nboxes) of the pool are examined.  phases: BT_STEP_DECIDE (split decisions),
+ * BT_STEP_CREATE (children; repeat alone after the caller enlarged the pool on
+ * BT_CTL_OVERFLOW), BT_STEP_COMMIT (children become part of the pool; in a distributed build
+ * after the host all-reduced pool->xch).  One GPU: BT_STEP_ALL. */
+#define BT_STEP_DECIDE 1
+#define BT_STEP_CREATE 2
+#define BT_STEP_COMMIT 4
+#define BT_STEP_ALL 7
 int bt_level_step(int dtype, int dim, const bt_pool *pool, const uint64_t *keys,
                   const int64_t *wprefix, int32_t *ctl, int32_t *split_list, uint8_t *flag, int lo,
                   int nboxes, int level, int maxw, int adaptive, int level_restrict,
-                  int have_extent, int skip_if_no_regular, double root_extent, int run_decide,
+                  int have_extent, int skip_if_no_regular, double root_extent, int phases,
                   void *stream);
 
 /* level_restrict kernel + upper-level sweep (tree_build_kernels.py:825-915,
@@ -185,6 +203,29 @@ int bt_box_extents(int dtype, int dim, int nboxes, int aligned, int nlevels,
                    const void *box_centers, const int32_t *pstarts, const int32_t *pcounts,
                    void *const *particles, const void *radii, void *bb_min, void *bb_max,
                    void *stream);
+
+/* Distributed build (no kernel counterpart in the reference, whose tree is built on one rank and
+ * broadcast, distributed/__init__.py:185-203): bt_box_extents split into its two phases
+ * (phases & 1: own-particle min/max per box, phases & 2: child merge per level) so that the
+ * host can all-reduce min/max between them; bt_box_info split into the per-rank source counts
+ * src3 = [3][nboxes] (sources before / in / stopping in the box's range of THIS rank's
+ * particles, plus the rank-local range arrays) and the global ranges + flags from the global
+ * srcntgt ranges and the all-reduced src3. */
+int bt_box_extents_phase(int dtype, int dim, int nboxes, int aligned, int nlevels,
+                         const int32_t *level_start_box_nrs_host, const int32_t *box_child_ids,
+                         const void *box_centers, const int32_t *pstarts, const int32_t *pcounts,
+                         void *const *particles, const void *radii, void *bb_min, void *bb_max,
+                         int phases, void *stream);
+int bt_box_info_local(int nboxes, int have_extent, const int32_t *local_start,
+                      const int32_t *local_count, const int32_t *local_nonchild,
+                      const uint8_t *has_children, const int32_t *source_numbers, int32_t *src3,
+                      int32_t *src_starts, int32_t *src_nonchild, int32_t *src_cumul,
+                      int32_t *tgt_starts, int32_t *tgt_nonchild, int32_t *tgt_cumul, void *stream);
+int bt_box_info_global(int nboxes, int have_extent, const int32_t *box_start,
+                       const int32_t *box_count, const int32_t *box_nonchild,
+                       const uint8_t *has_children, const int32_t *src3, int32_t *src_starts,
+                       int32_t *src_nonchild, int32_t *src_cumul, int32_t *tgt_starts,
+                       int32_t *tgt_nonchild, int32_t *tgt_cumul, uint8_t *box_flags, void *stream);
 
 /* ---------------------------------------------------------------- traversal */
 
@@ -444,6 +485,38 @@ int bt_dist_restrict_target_flags(int nboxes, const uint8_t *box_flags, const in
  * [nranks, nboxes]: phase 0 starts[nboxes+1] + total, phase 1 lists (ascending ranks) */
 int bt_dist_box_to_user_rank(int phase, int nboxes, int nranks, const int8_t *masks_all_ranks,
                              int32_t *starts, int32_t *lists, int64_t *total_dev, void *stream);
+
+
+/* ---- particle exchange of the distributed build: the all-to-all that replaces the root's
+ * fetch_local_particles + scatter (local_tree.py:124-151, 408-495).  Every rank holds the
+ * global box arrays and its own input particles in tree order.
+ * bt_dist_particle_box: box id of every local particle from the boxes' own ranges.
+ * bt_dist_mask_bits: masks [nranks, nboxes] -> one bit per rank and box.
+ * bt_dist_pack_records: for destination rank d = 0..nranks-1 in turn, one record
+ *   [coords (dim) | radius (if radii) | box id i32 | index in the box's own range i32]
+ *   per local particle whose box has bit d set, in tree order; dest_offsets [nranks+1] are
+ *   the record offsets per destination (always complete; records beyond `capacity` are not
+ *   written: enlarge and call again).  rank_excl[b] = own particles of lower ranks in box b.
+ * bt_dist_unpack_records: scatter received records to dst_start[box] + index; particle_idx
+ *   gets the particle's position in the global tree order (box_global_start[box] + index).
+ * bt_dist_local_ranges: per-box ranges of the local particle arrays (local_tree.py:249-284)
+ *   from the masked own counts in box pre-order (own particles precede the children's). */
+int bt_dist_particle_box(int nboxes, const int32_t *local_start, const int32_t *local_own,
+                         int32_t *particle_box, void *stream);
+int bt_dist_mask_bits(int nboxes, int nranks, const int8_t *masks_all_ranks, uint32_t *dest_bits,
+                      void *stream);
+int bt_dist_pack_records(int dtype, int nranks, int dim, int64_t n, const int32_t *particle_box,
+                         const uint32_t *dest_bits, void *const *particles, const void *radii,
+                         const int32_t *local_start, const int32_t *rank_excl, void *sendbuf,
+                         int64_t *dest_offsets, void *stream, int64_t capacity);
+int bt_dist_unpack_records(int dtype, int dim, int64_t nrec, int has_radii, const void *recvbuf,
+                           const int32_t *dst_start, const int32_t *box_global_start,
+                           void *const *local_particles, void *local_radii, int64_t *particle_idx,
+                           void *stream);
+int bt_dist_local_ranges(int nboxes, const int8_t *box_mask, const int32_t *own_counts,
+                         const int32_t *preorder_rank, const int32_t *preorder_boxes,
+                         const int32_t *subtree_size, int32_t *prefix_tmp, int32_t *local_starts,
+                         int32_t *local_nonchild, int32_t *local_cumul, void *stream);
 
 #ifdef __cplusplus
 }

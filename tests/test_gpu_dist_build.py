@@ -1,0 +1,50 @@
+"""GPU parity of the DISTRIBUTED TREE BUILD (per-level all-reduced box counts, particles kept
+on their ranks, one all-to-all to the local trees): several in-process ranks share the GPU
+through ``ThreadComm``.  Every rank's global box arrays must equal the oracle's tree of the
+concatenated input bit for bit; its local tree / local traversal / index arrays must equal the
+oracle's restatement of the reference's distributed flow and the digests of the reference's
+own distributed run (``tests/golden/refexec_distributed_digests.json``)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests.dist_build_util import check_rank, oracle_ranks, run_rank, run_threads
+from tests.dist_cases import CASES
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3, 4])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_distributed_build_matches_reference_flow(actx, name, nranks):
+    src, tkw, vkw = CASES[name]()
+    rtree, want = oracle_ranks(src, tkw, vkw, nranks)
+    with open(os.path.join(os.path.dirname(__file__), "golden",
+                           "refexec_distributed_digests.json")) as f:
+        reference = json.load(f).get(f"{name}:{nranks}")
+    outs = run_threads(nranks, lambda comm: run_rank(actx, comm, src, tkw, vkw))
+    for r in range(nranks):
+        bad = check_rank(actx, r, nranks, outs[r], rtree, want[r],
+                         None if reference is None else reference[r])
+        assert not bad, (r, bad[:10])
+    # every particle reaches exactly one rank as a target
+    assert sum(int(o[4].shape[0]) for o in outs) == rtree.ntargets
+
+
+@pytest.mark.parametrize("kind", ["adaptive", "non-adaptive", "adaptive-level-restricted"])
+@pytest.mark.parametrize("dims", [1, 2, 3])
+def test_distributed_build_kinds(actx, kind, dims):
+    """Tree kinds / dimensions / an empty rank slice / skip_prune through the distributed build."""
+    from tests.parity_util import normal_particles
+    n = 3000 if kind == "non-adaptive" else 20000
+    src = normal_particles(n, dims, np.float64, seed=3)
+    tkw = dict(max_particles_in_box=25, kind=kind)
+    if kind == "non-adaptive":
+        tkw["skip_prune"] = False
+    rtree, want = oracle_ranks(src, tkw, {}, 3)
+    outs = run_threads(3, lambda comm: run_rank(actx, comm, src, tkw, {}))
+    for r in range(3):
+        bad = check_rank(actx, r, 3, outs[r], rtree, want[r])
+        assert not bad, (r, bad[:10])
