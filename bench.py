@@ -21,12 +21,16 @@ configuration the metric is quoted on.
   reference algorithm; the reference itself cannot run here) timed
   on the host cores on a bounded sample of the same recipe.
 
-With N > 1 (torchrun) the default is ``--parallelism replicas``: every rank builds its
-own replica of the workload with a rank-specific seed, no data-path collective, the value
-is the aggregate (weak scaling).  ``--parallelism sharded`` runs ONE global problem: NCCL
-all-gather of the ranks' particle slices, replicated tree build, and only the rank's share
-of the traversal (box masks, local tree, local traversal of the reference's distributed
-setup) -- strong scaling.
+With N > 1 (torchrun) the default is ``--parallelism distributed``: ONE global problem of
+N x the workload's points (weak scaling: rank r contributes the workload generated with seed
+shift r), built by the distributed tree build (all-reduced bounding box and per-level box
+counts over NCCL, particles stay on their ranks), partitioned by the reference's DFS-order
+cost partition, particles sent to the local trees in one NCCL all-to-all, local traversal per
+rank (``boxtree.distributed`` semantics).  The same run also times the STRONG-scaling arm (the
+workload's N=1 problem cut into N slices; its global box arrays are checked against the
+committed digests of the reference's own run) and reports it in ``distributed_strong``.
+``--parallelism replicas`` (independent problems, no collective) and ``--parallelism sharded``
+(round 1: all-gathered particles, replicated tree build) remain selectable.
 """
 from __future__ import annotations
 
@@ -205,6 +209,36 @@ def algorithmic_bytes(scope, tree, trav, n, dims, s, heavy_entries=0):
     return table.get(scope)
 
 
+def whole_path_bytes(tree, trav, nsources, ntargets, dims, s, sources_are_targets, have_radii):
+    """B_tree + B_trav, compulsory bytes of one step, each byte once."""
+    nb = 2 ** dims
+    B, aB = int(tree.nboxes), int(tree.aligned_nboxes)
+    n_in = nsources + ntargets
+    k = 1 if sources_are_targets else 2
+    b_tree = n_in * dims * s + (nsources + (0 if sources_are_targets else ntargets)) * dims * s
+    if have_radii:
+        b_tree += 2 * ntargets * s
+    b_tree += 4 * nsources + 4 * (nsources if sources_are_targets else ntargets)
+    b_tree += B * (k * 12 + 4 + 1 + 1) + aB * (4 * nb + dims * s + 2 * k * dims * s)
+    b_trav = aB * (4 * nb + dims * s) + B * 6
+    import dataclasses
+
+    import torch
+
+    def nbytes(v):
+        if isinstance(v, torch.Tensor):
+            return v.numel() * v.element_size()
+        if isinstance(v, np.ndarray) and v.dtype == object:
+            return sum(nbytes(x) for x in v)
+        if dataclasses.is_dataclass(v):
+            return sum(nbytes(getattr(v, f.name)) for f in dataclasses.fields(v))
+        return 0
+    for f in dataclasses.fields(trav):
+        if f.name != "tree":
+            b_trav += nbytes(getattr(trav, f.name))
+    return b_tree, b_trav
+
+
 def run_ours(args):
     import torch
 
@@ -223,93 +257,79 @@ def run_ours(args):
     recipe, n, dtype, desc = WORKLOADS[args.workload]
     if args.n:
         n = args.n
-    sharded = world > 1 and args.parallelism == "sharded"
-    # replicas: every rank owns an independent problem (rank-specific seed);
-    # sharded: ONE global problem, rank r starts with the r-th slice of every particle array
-    src, kw = make_inputs(recipe, n, dtype, seed_shift=0 if sharded else rank)
-    dims = len(src)
+    mode = args.parallelism if world > 1 else "single"
+    dims = 3
     s_bytes = 4 if dtype == "f32" else 8
 
     actx = TorchArrayContext(device)
     tb = TreeBuilder(actx)
     tg = FMMTraversalBuilder(actx)
     lib = _cabi.load()
+    comm = bd = None
+    if world > 1:
+        from boxtree_b200 import distributed as bd
+        comm = bd.TorchDistComm()
 
     def to_dev(v):
         return actx.from_numpy(v)
 
-    dsrc = [to_dev(x) for x in src]
-    dkw = {k: (to_dev(v) if isinstance(v, np.ndarray) else
-               [to_dev(x) for x in v] if k == "targets" else v) for k, v in kw.items()}
+    def dev_inputs(src, kw):
+        return [to_dev(x) for x in src], {
+            k: (to_dev(v) if isinstance(v, np.ndarray) else
+                [to_dev(x) for x in v] if k == "targets" else v) for k, v in kw.items()}
 
-    def step_resident():
-        tree, _ = tb(actx, dsrc, **dkw)
-        trav, _ = tg(actx, tree)
-        return tree, trav
+    def my_slice(a):
+        m = int(a.shape[0])
+        return a[rank * m // world:(rank + 1) * m // world]
 
-    step_sharded = None
-    if world > 1:
-        from boxtree_b200 import distributed as bd
-        comm = bd.TorchDistComm()
-        # ONE global problem = rank 0's particle set; rank r starts with its r-th slice
-        gsrc, gkw_np = (src, kw) if sharded else make_inputs(recipe, n, dtype, seed_shift=0)
-        if sharded:
-            gd, gdk = dsrc, dkw
+    def slice_inputs(src, kw):
+        return [np.ascontiguousarray(my_slice(x)) for x in src], {
+            k: (np.ascontiguousarray(my_slice(v)) if isinstance(v, np.ndarray) else
+                [np.ascontiguousarray(my_slice(x)) for x in v] if k == "targets" else v)
+            for k, v in kw.items()}
+
+    # {{{ this rank's particles
+    # single / replicas / distributed (weak): the workload generated with seed shift `rank`;
+    # for "distributed" the global problem is the concatenation over ranks (N x n points).
+    # distributed-strong / sharded: the r-th slice of the N=1 problem (n points in total).
+    if mode in ("distributed-strong", "sharded"):
+        src, kw = slice_inputs(*make_inputs(recipe, n, dtype, seed_shift=0))
+        npoints_job = n
+    else:
+        src, kw = make_inputs(recipe, n, dtype, seed_shift=rank)
+        npoints_job = world * n
+    dsrc, dkw = dev_inputs(src, kw)
+    # }}}
+
+    def make_step(dsrc, dkw, mode):
+        if mode in ("single", "replicas"):
+            def step():
+                tree, _ = tb(actx, dsrc, **dkw)
+                trav, _ = tg(actx, tree)
+                return tree, trav
+        elif mode in ("distributed", "distributed-strong"):
+            def step():
+                # all-reduced bounding box + per-level box counts (NCCL), particles stay put;
+                # DFS-order cost partition; ONE all-to-all of particles; local traversal
+                dtree = bd.build_distributed_tree(actx, tb, comm, dsrc, **dkw)
+                lt, ltrav, _, _ = bd.distributed_tree_setup(actx, dtree, tg, comm)
+                return lt, ltrav
         else:
-            gd = [to_dev(x) for x in gsrc]
-            gdk = {k: (to_dev(v) if isinstance(v, np.ndarray) else
-                       [to_dev(x) for x in v] if k == "targets" else v) for k, v in gkw_np.items()}
+            def step():
+                # round 1: NCCL all-gather of the particle slices -> replicated tree build ->
+                # only this rank's share of the traversal
+                g = bd.allgather_particles(actx, comm, dsrc)
+                gk = dict(dkw)
+                if "targets" in dkw:
+                    gk["targets"] = bd.allgather_particles(actx, comm, dkw["targets"])
+                if "target_radii" in dkw:
+                    gk["target_radii"] = bd.allgather_particles(actx, comm, [dkw["target_radii"]])[0]
+                tree, _ = tb(actx, g, **gk)
+                lt, ltrav, _, _ = bd.sharded_setup(actx, tree, tg, comm)
+                return lt, ltrav
+        return step
 
-        def my_slice(t):
-            m = int(t.shape[0])
-            return t[rank * m // world:(rank + 1) * m // world].contiguous()
-
-        ssrc = [my_slice(x) for x in gd]
-        skw = {k: (my_slice(v) if isinstance(v, torch.Tensor) else
-                   [my_slice(x) for x in v] if k == "targets" else v) for k, v in gdk.items()}
-        del gd, gdk
-
-        def step_sharded():
-            # NCCL all-gather of the particle slices -> replicated tree build -> only this
-            # rank's share of the traversal (masks, local tree, local traversal)
-            g = bd.allgather_particles(actx, comm, ssrc)
-            gk = dict(skw)
-            if "targets" in skw:
-                gk["targets"] = bd.allgather_particles(actx, comm, skw["targets"])
-            if "target_radii" in skw:
-                gk["target_radii"] = bd.allgather_particles(actx, comm, [skw["target_radii"]])[0]
-            tree, _ = tb(actx, g, **gk)
-            local_tree, local_trav, _, _ = bd.sharded_setup(actx, tree, tg, comm)
-            return local_tree, local_trav
-
-        if sharded:
-            step_resident = step_sharded  # noqa: F811
-
-    # pinned host copies for the end-to-end arm
-    def pin(a):
-        return torch.from_numpy(a).pin_memory()
-
-    hsrc = [pin(x) for x in src]
-    hkw = {k: (pin(v) if isinstance(v, np.ndarray) else [pin(x) for x in v] if k == "targets"
-               else v) for k, v in kw.items()}
-    h2d_bytes = sum(x.numel() * x.element_size() for x in hsrc)
-    for k, v in hkw.items():
-        if isinstance(v, torch.Tensor):
-            h2d_bytes += v.numel() * v.element_size()
-        elif k == "targets":
-            h2d_bytes += sum(x.numel() * x.element_size() for x in v)
-
-    def step_e2e():
-        g = [x.to(device, non_blocking=True) for x in hsrc]
-        gk = {k: (v.to(device, non_blocking=True) if isinstance(v, torch.Tensor) else
-                  [x.to(device, non_blocking=True) for x in v] if k == "targets" else v)
-              for k, v in hkw.items()}
-        tree, _ = tb(actx, g, **gk)
-        trav, _ = tg(actx, tree)
-        summary = torch.cat([tree.level_start_box_nrs.to(torch.int64),
-                             trav.from_sep_siblings_starts[-1:].to(torch.int64),
-                             trav.neighbor_source_boxes_starts[-1:].to(torch.int64)]).cpu()
-        return tree, trav, summary
+    step_resident = make_step(dsrc, dkw, mode)
 
     def barrier():
         if dist is not None:
@@ -345,40 +365,63 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     tree, trav = out
     ms_per_step = ms / args.steps
-    npoints_job = n if sharded else world * n
     value = npoints_job / (ms_per_step * 1e-3) / 1e6
+    nboxes, nlevels = int(tree.nboxes), int(tree.nlevels)
 
-    # N > 1, replicas as the main arm: also time the distributed path (ONE global problem of
-    # the same workload, strong scaling) so that both numbers come from the same run
-    distributed = None
-    if world > 1 and not sharded:
-        for _ in range(max(args.warmup, 1)):
-            o = step_sharded()
+    # {{{ N > 1, weak arm: also the strong-scaling arm on the N=1 problem, with a parity check
+
+    distributed_strong = None
+    if mode == "distributed" and not args.no_strong:
+        ssrc, skw = dev_inputs(*slice_inputs(*make_inputs(recipe, n, dtype, seed_shift=0)))
+        step_strong = make_step(ssrc, skw, "distributed-strong")
+        for _ in range(max(args.warmup, 3)):
+            o = step_strong()
             del o
-        dsteps = max(1, min(args.steps, 3))
-        ms_d, o = timed(step_sharded, dsteps)
+        ssteps = max(args.steps, 10)
+        ms_s, o = timed(step_strong, ssteps)
         del o
-        distributed = {"value": n / (ms_d / dsteps * 1e-3) / 1e6, "unit": "Mpoints/s",
-                       "ms_per_step": ms_d / dsteps, "steps": dsteps, "scaling": "strong",
-                       "points_total": n,
-                       "parallelism": "sharded: NCCL all-gather of particle slices, replicated tree "
-                                      "build, traversal rows sharded by the reference's DFS-order "
-                                      "work partition (boxtree.distributed setup)"}
+        parity = strong_parity(actx, bd, tb, comm, ssrc, skw, args.workload, n)
+        distributed_strong = {
+            "value": n / (ms_s / ssteps * 1e-3) / 1e6, "unit": "Mpoints/s",
+            "ms_per_step": ms_s / ssteps, "steps": ssteps, "scaling": "strong", "points_total": n,
+            "parity": parity}
+        del ssrc, skw, step_strong
 
-    # end to end (host buffers in, result summary out)
-    e2e_steps = max(1, min(args.steps, 3))
-    if sharded:
-        def step_e2e():  # noqa: F811
-            nonlocal ssrc, skw
-            ssrc = [my_slice(x.to(device, non_blocking=True)) for x in hsrc]
-            skw = {k: (my_slice(v.to(device, non_blocking=True)) if isinstance(v, torch.Tensor) else
-                       [my_slice(x.to(device, non_blocking=True)) for x in v] if k == "targets"
-                       else v) for k, v in hkw.items()}
-            lt, ltrav = step_resident()
-            summary = torch.cat([lt.level_start_box_nrs.to(torch.int64),
-                                 ltrav.from_sep_siblings_starts[-1:].to(torch.int64),
-                                 ltrav.neighbor_source_boxes_starts[-1:].to(torch.int64)]).cpu()
-            return lt, ltrav, summary
+    # }}}
+
+    # {{{ end to end: pinned host buffers in, result summary out, every step
+
+    def pin(a):
+        return torch.from_numpy(a).pin_memory()
+
+    hsrc = [pin(x) for x in src]
+    hkw = {k: (pin(v) if isinstance(v, np.ndarray) else [pin(x) for x in v] if k == "targets"
+               else v) for k, v in kw.items()}
+    h2d_bytes = sum(x.numel() * x.element_size() for x in hsrc)
+    for k, v in hkw.items():
+        if isinstance(v, torch.Tensor):
+            h2d_bytes += v.numel() * v.element_size()
+        elif k == "targets":
+            h2d_bytes += sum(x.numel() * x.element_size() for x in v)
+
+    def upload():
+        g = [x.to(device, non_blocking=True) for x in hsrc]
+        gk = {k: (v.to(device, non_blocking=True) if isinstance(v, torch.Tensor) else
+                  [x.to(device, non_blocking=True) for x in v] if k == "targets" else v)
+              for k, v in hkw.items()}
+        return g, gk
+
+    def summary_of(t, tr):
+        return torch.cat([t.level_start_box_nrs.to(torch.int64),
+                          tr.from_sep_siblings_starts[-1:].to(torch.int64),
+                          tr.neighbor_source_boxes_starts[-1:].to(torch.int64)]).cpu()
+
+    def step_e2e():
+        g, gk = upload()
+        t, tr = make_step(g, gk, mode)()
+        return t, tr, summary_of(t, tr)
+
+    e2e_steps = max(1, min(args.steps, 10))
     o = step_e2e()
     del o
     ms_e2e, o = timed(step_e2e, e2e_steps)
@@ -389,56 +432,55 @@ def run_ours(args):
     # the same, double buffered: the H2D copy of step k+1 (copy stream) overlaps the build of step
     # k; every step still copies its own inputs from pinned memory and reads its summary back
     e2e_pipelined = None
-    if not sharded:
+    if mode in ("single", "replicas"):
         copy_stream = torch.cuda.Stream(device=device)
         main_stream = actx.stream
 
-        def upload():
+        def upload_async():
             with torch.cuda.stream(copy_stream):
-                g = [x.to(device, non_blocking=True) for x in hsrc]
-                gk = {k: (v.to(device, non_blocking=True) if isinstance(v, torch.Tensor) else
-                          [x.to(device, non_blocking=True) for x in v] if k == "targets" else v)
-                      for k, v in hkw.items()}
+                g, gk = upload()
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
             return g, gk, ev
 
         def run_pipelined(steps):
-            nxt = upload()
+            nxt = upload_async()
             last = None
             for k in range(steps):
                 g, gk, ev = nxt
                 main_stream.wait_event(ev)
                 if k + 1 < steps:
-                    nxt = upload()
-                tree, _ = tb(actx, g, **gk)
-                trav, _ = tg(actx, tree)
-                last = torch.cat([tree.level_start_box_nrs.to(torch.int64),
-                                  trav.from_sep_siblings_starts[-1:].to(torch.int64),
-                                  trav.neighbor_source_boxes_starts[-1:].to(torch.int64)]).cpu()
+                    nxt = upload_async()
+                t, _ = tb(actx, g, **gk)
+                tr, _ = tg(actx, t)
+                last = summary_of(t, tr)
                 used = list(g)                     # the buffers were allocated on the copy stream
                 for v in gk.values():
                     used += [v] if isinstance(v, torch.Tensor) else (v if isinstance(v, list) else [])
                 for t_ in used:
                     t_.record_stream(main_stream)
-                del tree, trav
+                del t, tr
             return last
 
         run_pipelined(2)
-        psteps = max(2, min(args.steps, 5))
+        psteps = max(2, min(args.steps, 10))
         ms_p, _ = timed(lambda: run_pipelined(psteps), 1)
         e2e_pipelined = {"value": npoints_job / (ms_p / psteps * 1e-3) / 1e6, "unit": "Mpoints/s",
                          "steps": psteps, "ms_per_step": ms_p / psteps,
                          "how": "double buffered: H2D of step k+1 on a copy stream during the build "
                                 "of step k; every step copies its own inputs and reads its summary"}
 
-    # dominant kernel, timed live with CUDA events on the launching stream
+    # }}}
+
+    # {{{ roofline: per-scope CUDA-event times on the launching stream (rank 0)
+
     roofline = None
     prof_steps = 2
+    collective = mode not in ("single", "replicas")
     if rank == 0:
         lib.bt_prof_reset()
         lib.bt_prof_enable(1)
-    if rank == 0 or sharded:          # sharded steps are collective: every rank takes part
+    if rank == 0 or collective:          # collective steps: every rank takes part
         for _ in range(prof_steps):
             tree, trav = step_resident()
         torch.cuda.synchronize()
@@ -452,6 +494,8 @@ def run_ours(args):
         top = max(leaf.items(), key=lambda kv: kv[1][1])
         scope, (calls, tot) = top
         avg_ms = tot / calls
+        nsrc_l = int(tree.sources[0].shape[0])
+        ntgt_l = 0 if tree.sources_are_targets else int(tree.targets[0].shape[0])
         abytes = algorithmic_bytes(scope, tree, trav, n, dims, s_bytes,
                                    heavy_entries=int(tg.last_stats.get("heavy_entries_list3", 0)))
         peaks_path = os.path.join(HERE, "MEASURED_PEAKS.json")
@@ -461,56 +505,137 @@ def run_ours(args):
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = (abytes / (avg_ms * 1e-3) / 1e9) if abytes else None
-        # DRAM bytes of the same scope from the committed ncu --set full capture of this build
+        # DRAM bytes per launch of every scope, from the committed ncu --set full capture
         traffic = None
+        per_scope_traffic = {}
         tkey = {"config3": "config3_10000000", "uniform1e7": "uniform_10000000_f64"}.get(args.workload)
-        tpath = os.path.join(HERE, "profiles", "r01_traffic.json")
-        if tkey and not args.n and os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(tkey, {}).get("bytes_per_launch", {}).get(scope)
-        roofline = {"bound": "hbm", "kernel": scope, "achieved": achieved, "peak": peak,
+        for tname in ("r02_traffic.json", "r01_traffic.json"):
+            tpath = os.path.join(HERE, "profiles", tname)
+            if tkey and not args.n and os.path.exists(tpath):
+                per_scope_traffic = json.load(open(tpath)).get(tkey, {}).get("bytes_per_launch", {})
+                traffic = per_scope_traffic.get(scope)
+                if per_scope_traffic:
+                    break
+        # walks chase pointers: they are bound by issue slots / latency, not by DRAM bandwidth
+        walk_scopes = ("l13_walk", "l13_heavy_expand", "trav_colleagues", "trav_list4", "bt_level")
+        bound = "issue" if scope.startswith(walk_scopes) else "hbm"
+        # the whole path: (B_tree + B_trav) / step time / peak
+        b_tree, b_trav = whole_path_bytes(tree, trav, nsrc_l, ntgt_l, dims, s_bytes,
+                                          bool(tree.sources_are_targets),
+                                          bool(tree.targets_have_extent))
+        whole = (b_tree + b_trav) / (ms_per_step * 1e-3) / 1e9
+        # time-weighted DRAM fraction of the kernels: sum(ncu dram bytes) / sum(live time) / peak
+        tw = None
+        if per_scope_traffic:
+            tb_, tt_ = 0.0, 0.0
+            for k_, (c_, ms_) in leaf.items():
+                if k_ in per_scope_traffic and per_scope_traffic[k_]:
+                    tb_ += per_scope_traffic[k_] * c_
+                    tt_ += ms_
+            if tt_ > 0:
+                tw = {"dram_gbs": tb_ / (tt_ * 1e-3) / 1e9, "frac": tb_ / (tt_ * 1e-3) / 1e9 / peak,
+                      "covered_share_of_step": tt_ / total_ms}
+        roofline = {"bound": bound, "kernel": scope, "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                     "traffic": traffic, "peak_source": peak_src,
                     "avg_launch_ms": avg_ms, "launches_per_step": calls / prof_steps,
                     "share_of_step": tot / total_ms if total_ms else None,
                     "algorithmic_bytes_per_launch": abytes,
+                    "whole_path": {"b_tree": b_tree, "b_trav": b_trav, "achieved": whole,
+                                   "frac": whole / peak, "unit": "GB/s",
+                                   "how": "(B_tree + B_trav of SURVEY 8d) / ms_per_step / peak"},
+                    "time_weighted_dram": tw,
                     "top_scopes_ms_per_step": {k: round(v[1] / prof_steps, 3) for k, v in
-                                               sorted(leaf.items(), key=lambda kv: -kv[1][1])[:6]}}
+                                               sorted(leaf.items(), key=lambda kv: -kv[1][1])[:8]}}
+
+    # }}}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample_n = min(n, CPU_SAMPLE_POINTS)
         v, dt = time_oracle(recipe, sample_n, dtype, steps=1, warmup=0)
         cpu_baseline = {"value": v, "unit": "Mpoints/s", "cores": host_threads(), "kind": "port",
-                        "sample": f"same recipe at {sample_n} points, 1 step, {dt:.1f} s "
-                                  "(tree-build kernels single-threaded, traversal OpenMP)"}
+                        "sample": f"same recipe at {sample_n} points, 1 step, {dt:.1f} s"}
 
     if rank == 0:
+        par = {"single": "single",
+               "replicas": "replicas: independent problems, no collective",
+               "distributed": "distributed tree build of ONE global problem of n_gpus x points_per_gpu "
+                              "points: all-reduced bbox and per-level box counts (NCCL), DFS-order "
+                              "cost partition, one all-to-all of particles to the local trees, "
+                              "local traversal per rank (boxtree.distributed semantics)",
+               "distributed-strong": "distributed tree build of the N=1 problem cut into n_gpus slices",
+               "sharded": "round 1: NCCL all-gather of particle slices, replicated tree build, "
+                          "traversal rows sharded by the DFS-order work partition"}[mode]
         line = {
             "metric": "Mpoints/s TreeBuilder+FMMTraversalBuilder", "value": value,
             "unit": "Mpoints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong" if sharded else "weak",
+            "scaling": "strong" if mode in ("distributed-strong", "sharded") else "weak",
             "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}" + (f" (n={n})" if args.n else ""),
-                       "points_per_gpu": n, "nboxes": tree.nboxes, "nlevels": tree.nlevels,
-                       "l2_policy": "inputs larger than L2" if n * dims * s_bytes > 126e6
+                       "points_per_gpu": npoints_job // world, "points_total": npoints_job,
+                       "nboxes": nboxes, "nlevels": nlevels,
+                       "l2_policy": "inputs larger than L2"
+                       if (npoints_job // world) * dims * s_bytes > 126e6
                        else "inputs smaller than L2 (no flush)",
-                       "parallelism": ("sharded: NCCL all-gather of particle slices, replicated "
-                                       "tree build, traversal rows sharded by the reference's "
-                                       "DFS-order work partition" if sharded else
-                                       "replicas" if world > 1 else "single")},
+                       "parallelism": par},
             "e2e": {"value": e2e_value, "unit": "Mpoints/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu_baseline,
         }
-        if distributed is not None:
-            line["distributed"] = distributed
+        if distributed_strong is not None:
+            line["distributed_strong"] = distributed_strong
         if e2e_pipelined is not None:
             line["e2e"]["pipelined"] = e2e_pipelined
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def strong_parity(actx, bd, tb, comm, ssrc, skw, workload, n):
+    """Distributed build of the N=1 problem: the global box arrays every rank ends with are
+    hashed and compared with the digests of the REFERENCE's own run on that input
+    (tests/golden/full_size_digests.json); all ranks must agree."""
+    import torch
+    import torch.distributed as dist
+
+    from tests.golden.make_golden import digest
+    key = {"config3": "config3_3d_1e7", "uniform1e7": "uniform_3d_1e7_f64",
+           "config2": "config2_3d_1e6"}.get(workload)
+    full = {"config3": 10_000_000, "uniform1e7": 10_000_000, "config2": 1_000_000}.get(workload)
+    dtree = bd.build_distributed_tree(actx, tb, comm, ssrc, **skw)
+    nb = int(dtree.nboxes)
+    got = {}
+    for f in ("box_source_starts", "box_source_counts_nonchild", "box_source_counts_cumul",
+              "box_target_starts", "box_target_counts_nonchild", "box_target_counts_cumul",
+              "box_parent_ids", "box_levels", "box_flags"):
+        got["tree." + f] = digest(getattr(dtree, f).cpu().numpy()[:nb])
+    for f in ("box_child_ids", "box_centers", "box_source_bounding_box_min",
+              "box_source_bounding_box_max", "box_target_bounding_box_min",
+              "box_target_bounding_box_max", "level_start_box_nrs"):
+        got["tree." + f] = digest(getattr(dtree, f).cpu().numpy())
+    result = {"checked_fields": len(got), "nboxes": nb}
+    ok = 1
+    path = os.path.join(HERE, "tests", "golden", "full_size_digests.json")
+    if key and n == full and os.path.exists(path):
+        want = json.load(open(path))[key]
+        bad = [k for k, v in got.items() if k in want and want[k] != v]
+        missing = [k for k in got if k not in want]
+        ok = int(not bad and nb == want["_nboxes"])
+        result.update(against="reference run digests (tests/golden/full_size_digests.json: "
+                              f"{key})", mismatches=bad, not_in_golden=missing)
+    else:
+        result.update(against="rank agreement only (no committed digest for this size)")
+    # every rank holds the same global box arrays
+    h = int(digest(np.frombuffer("".join(sorted(got.values())).encode(), np.uint8))[:15], 16)
+    t = torch.tensor([h, -h, ok], device=actx.device, dtype=torch.int64)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    agree = int(t[0].item()) == h and int(t[1].item()) == -h
+    result["ranks_agree"] = bool(agree)
+    result["ok"] = bool(agree and int(t[2].item()) == 1)
+    return result
 
 
 def run_reference(args):
@@ -547,9 +672,13 @@ def main():
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
     ap.add_argument("--n", type=int, default=0, help="override the number of points")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--parallelism", default="replicas", choices=["replicas", "sharded"],
-                    help="N > 1: independent replicas per rank (weak scaling, default) or one "
-                         "global problem with a sharded traversal (strong scaling)")
+    ap.add_argument("--no-strong", action="store_true",
+                    help="N > 1: skip the strong-scaling arm of the distributed run")
+    ap.add_argument("--parallelism", default="distributed",
+                    choices=["distributed", "distributed-strong", "replicas", "sharded"],
+                    help="N > 1: distributed tree build of one global problem of N x the workload "
+                         "(weak scaling, default) or of the workload itself (strong); independent "
+                         "replicas; round 1's all-gather + replicated tree build")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -66,9 +66,11 @@ __global__ void dist_ancestor_mask_kernel(int nboxes, const signed char* __restr
     }
 }
 
-// add_interaction_list_boxes, partition.py:135-162 (mask_b, optional, is OR-ed in).  One
-// thread per list ENTRY (its row is found by binary search in `starts`), so rows with ~1e6
-// entries do not serialise on one thread.
+// add_interaction_list_boxes, partition.py:135-162 (mask_b, optional, is OR-ed in).  Rows with
+// ~1e6 entries exist, so the work is cut by ENTRIES: every warp takes a span of kSpan consecutive
+// list entries, finds the row of its first entry by one binary search in `starts` and then walks
+// the rows of its span, 32 coalesced entries at a time.
+constexpr int kMaskSpan = 2048;
 __global__ void __launch_bounds__(256)
 dist_add_list_boxes_kernel(int nrows, const int* __restrict__ box_list,
                            const signed char* __restrict__ mask_a, const signed char* __restrict__ mask_b,
@@ -76,11 +78,62 @@ dist_add_list_boxes_kernel(int nrows, const int* __restrict__ box_list,
                            signed char* __restrict__ out_mask)
 {
     const int nentries = starts[nrows];
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nentries; k += gridDim.x * blockDim.x) {
-        int lo = 0, hi = nrows;                // last row with starts[row] <= k
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (starts[mid] <= k) lo = mid; else hi = mid; }
-        const int box = box_list[lo];
-        if (mask_a[box] || (mask_b && mask_b[box])) out_mask[lists[k]] = 1;
+    const int lane = threadIdx.x & 31;
+    const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t sp = w0 * kMaskSpan; sp < nentries; sp += nw * kMaskSpan) {
+        const int first = (int)sp, last = (int)((sp + kMaskSpan < nentries) ? sp + kMaskSpan : nentries);
+        int lo = 0, hi = nrows;                // last row with starts[row] <= first
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (starts[mid] <= first) lo = mid; else hi = mid; }
+        int row = lo, k = first;
+        while (k < last) {
+            int rend = starts[row + 1];
+            while (rend <= k) { ++row; rend = starts[row + 1]; }       // skip empty rows
+            const int e = rend < last ? rend : last;
+            const int box = box_list[row];
+            if (mask_a[box] || (mask_b && mask_b[box]))
+                for (int q = k + lane; q < e; q += 32) out_mask[lists[q]] = 1;
+            k = e;
+        }
+    }
+}
+
+// every entry of a list marks its box (all rows of the list are rows the mask reads)
+__global__ void __launch_bounds__(256)
+dist_mark_list_boxes_kernel(int64_t n, const int* __restrict__ lists, signed char* __restrict__ out_mask)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t head = ((16 - ((uintptr_t)lists & 15)) & 15) / 4;      // entries before 16-byte alignment
+    const int64_t h = head < n ? head : n;
+    if (tid < h) out_mask[lists[tid]] = 1;
+    const int4* v = reinterpret_cast<const int4*>(lists + h);
+    const int64_t nv = (n - h) / 4;
+    for (int64_t i = tid; i < nv; i += stride) {
+        const int4 x = v[i];
+        out_mask[x.x] = 1; out_mask[x.y] = 1; out_mask[x.z] = 1; out_mask[x.w] = 1;
+    }
+    const int64_t tail = h + nv * 4;
+    if (tid < n - tail) out_mask[lists[tail + tid]] = 1;
+}
+
+// distributed build: target bits that the rank's local flags lack although the global flags
+// have them, on the rows the masks read (responsible boxes and their ancestors) -- the rows of
+// the global traversal that the local traversal does not contain (partition.py:197-297 reads
+// them); source bits are kept.  any_out[0] != 0 if any such row exists.
+__global__ void dist_corner_flags_kernel(int nboxes, const unsigned char* __restrict__ gflags,
+                                         const unsigned char* __restrict__ lflags,
+                                         const signed char* __restrict__ mask_a,
+                                         const signed char* __restrict__ mask_b,
+                                         unsigned char* __restrict__ out_flags, int* __restrict__ any_out)
+{
+    const unsigned char tbits = BT_BOX_IS_TARGET_BOX | BT_BOX_HAS_TARGET_CHILD_BOXES;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nboxes; b += gridDim.x * blockDim.x) {
+        const unsigned char g = gflags[b], l = lflags[b];
+        unsigned char keep = 0;
+        if (mask_a[b] || mask_b[b]) keep = (unsigned char)(g & ~l & tbits);
+        out_flags[b] = (unsigned char)((g & ~tbits) | keep);
+        if (keep) *any_out = 1;
     }
 }
 
@@ -224,19 +277,6 @@ static int fetch_impl(int dim, int64_t n, const int* mask, const int* g2l, void*
 // which is the particle's place in the global tree order restricted to the rank's boxes (the
 // order construct_local_particles_and_lists produces).
 
-// box id of every local particle (own ranges tile the local array); 8 lanes per box
-__global__ void __launch_bounds__(256)
-dist_particle_box_kernel(int nboxes, const int* __restrict__ lstart, const int* __restrict__ lown,
-                         int* __restrict__ pbox)
-{
-    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, gl = threadIdx.x & 7;
-    const int ng = (gridDim.x * blockDim.x) >> 3;
-    for (int b = g; b < nboxes; b += ng) {
-        const int s = lstart[b], e = s + lown[b];
-        for (int p = s + gl; p < e; p += 8) pbox[p] = b;
-    }
-}
-
 // dest_bits[b] = OR over ranks r with masks[r][b] != 0 of (1 << r)
 __global__ void dist_mask_bits_kernel(int nboxes, int nranks, const signed char* __restrict__ masks,
                                       unsigned* __restrict__ bits)
@@ -248,40 +288,63 @@ __global__ void dist_mask_bits_kernel(int nboxes, int nranks, const signed char*
     }
 }
 
-template <typename T>
-struct PackIn {
-    const int* pbox; const unsigned* dest_bits; int64_t n;
+// record offsets per (destination, box): exclusive scan, destination-major, of the own counts
+// of the boxes whose bit is set
+struct PackScanIn {
+    const unsigned* dest_bits; const int* lown; int nboxes;
     __device__ int operator()(int64_t k) const
     {
-        const int d = (int)(k / n); const int64_t p = k - (int64_t)d * n;
-        return (dest_bits[pbox[p]] >> d) & 1u;
+        const int d = (int)(k / nboxes), b = (int)(k - (int64_t)d * nboxes);
+        return ((dest_bits[b] >> d) & 1u) ? lown[b] : 0;
     }
 };
-template <typename T>
-struct PackOut {
-    const int* pbox; const unsigned* dest_bits; int64_t n; int dim; int recbytes;
-    const T* c0; const T* c1; const T* c2; const T* radii;
-    const int* lstart; const int* rank_excl;     // E_r[b]: own particles of lower ranks in box b
-    unsigned char* sendbuf; long long* dest_offsets; /* [nranks + 1] */ int nranks; long long cap;
+struct PackScanOut {
+    int* offs; long long* dest_offsets; /* [nranks + 1] */ int nboxes; int nranks;
     __device__ void operator()(int64_t k, long long excl) const
     {
-        const int d = (int)(k / n); const int64_t p = k - (int64_t)d * n;
-        if (p == 0) dest_offsets[d] = excl;
-        const int b = pbox[p];
-        if (!((dest_bits[b] >> d) & 1u) || excl >= cap) return;
-        unsigned char* rec = sendbuf + excl * recbytes;
-        T* c = reinterpret_cast<T*>(rec);
-        c[0] = c0[p];
-        if (dim > 1) c[1] = c1[p];
-        if (dim > 2) c[2] = c2[p];
-        int q = dim;
-        if (radii) c[q++] = radii[p];
-        int* tail = reinterpret_cast<int*>(c + q);
-        tail[0] = b;
-        tail[1] = rank_excl[b] + (int)(p - lstart[b]);
+        offs[k] = (int)excl;
+        if (k % nboxes == 0) dest_offsets[k / nboxes] = excl;
     }
     __device__ void total(long long t) const { dest_offsets[nranks] = t; }
 };
+
+// 8 lanes per box copy the box's own particles into the record range of every destination
+template <typename T>
+__global__ void __launch_bounds__(256)
+dist_pack_kernel(int nboxes, int nranks, int dim, int recbytes, const unsigned* __restrict__ dest_bits,
+                 const int* __restrict__ lstart, const int* __restrict__ lown,
+                 const int* __restrict__ rank_excl, const int* __restrict__ offs,
+                 const T* c0, const T* c1, const T* c2, const T* __restrict__ radii,
+                 unsigned char* __restrict__ sendbuf, long long cap)
+{
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, gl = threadIdx.x & 7;
+    const int ng = (gridDim.x * blockDim.x) >> 3;
+    for (int b = g; b < nboxes; b += ng) {
+        unsigned bits = dest_bits[b];
+        const int own = lown[b];
+        if (!bits || !own) continue;
+        const int s0 = lstart[b], rel0 = rank_excl[b];
+        while (bits) {
+            const int d = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const long long base = offs[(int64_t)d * nboxes + b];
+            for (int k = gl; k < own; k += 8) {
+                if (base + k >= cap) break;
+                unsigned char* rec = sendbuf + (base + k) * recbytes;
+                T* c = reinterpret_cast<T*>(rec);
+                const int p = s0 + k;
+                c[0] = c0[p];
+                if (dim > 1) c[1] = c1[p];
+                if (dim > 2) c[2] = c2[p];
+                int q = dim;
+                if (radii) c[q++] = radii[p];
+                int* tail = reinterpret_cast<int*>(c + q);
+                tail[0] = b;
+                tail[1] = rel0 + k;
+            }
+        }
+    }
+}
 
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -333,16 +396,23 @@ __global__ void dist_local_ranges_kernel(int nboxes, const signed char* __restri
 }
 
 template <typename T>
-static int pack_impl(int nranks, int dim, int64_t n, const int* pbox, const unsigned* dest_bits,
-                     void* const* parts, const void* radii, const int* lstart, const int* rank_excl,
+static int pack_impl(int nranks, int dim, int nboxes, const unsigned* dest_bits, void* const* parts,
+                     const void* radii, const int* lstart, const int* lown, const int* rank_excl,
                      void* sendbuf, long long* dest_offsets, long long cap, cudaStream_t s)
 {
     const int recbytes = (int)sizeof(T) * (dim + (radii ? 1 : 0)) + 8;
-    PackIn<T> in{pbox, dest_bits, n};
-    PackOut<T> out{pbox, dest_bits, n, dim, recbytes, (const T*)parts[0],
-                   dim > 1 ? (const T*)parts[1] : nullptr, dim > 2 ? (const T*)parts[2] : nullptr,
-                   (const T*)radii, lstart, rank_excl, (unsigned char*)sendbuf, dest_offsets, nranks, cap};
-    return scan_exclusive((int64_t)nranks * n, nullptr, in, out, s);
+    int* offs = nullptr;
+    BT_CHECK(temp_alloc((void**)&offs, sizeof(int) * (size_t)nranks * nboxes, s));
+    PackScanIn in{dest_bits, lown, nboxes};
+    PackScanOut out{offs, dest_offsets, nboxes, nranks};
+    BT_TRY(scan_exclusive((int64_t)nranks * nboxes, nullptr, in, out, s));
+    dist_pack_kernel<T><<<grid_for((int64_t)nboxes * 8, 256, 8), 256, 0, s>>>(
+        nboxes, nranks, dim, recbytes, dest_bits, lstart, lown, rank_excl, offs, (const T*)parts[0],
+        dim > 1 ? (const T*)parts[1] : nullptr, dim > 2 ? (const T*)parts[2] : nullptr,
+        (const T*)radii, (unsigned char*)sendbuf, cap);
+    BT_LAUNCH_CHECK();
+    BT_CHECK(cudaFreeAsync(offs, s));
+    return BT_OK;
 }
 
 }  // namespace bt
@@ -397,7 +467,7 @@ int bt_dist_add_list_boxes(int nrows, const int32_t* box_list, const int8_t* mas
 {
     BT_PROF("bt_dist_add_list_boxes", (cudaStream_t)stream);
     if (nrows <= 0) return BT_OK;
-    bt::dist_add_list_boxes_kernel<<<bt::kNumSMs * 16, 256, 0, (cudaStream_t)stream>>>(
+    bt::dist_add_list_boxes_kernel<<<bt::kNumSMs * 8, 256, 0, (cudaStream_t)stream>>>(
         nrows, box_list, (const signed char*)mask_a, (const signed char*)mask_b, starts, lists,
         (signed char*)out_mask);
     BT_LAUNCH_CHECK();
@@ -475,6 +545,29 @@ int bt_dist_restrict_target_flags(int nboxes, const uint8_t* box_flags, const in
     return BT_OK;
 }
 
+int bt_dist_mark_list_boxes(int64_t nentries, const int32_t* lists, int8_t* out_mask, void* stream)
+{
+    BT_PROF("bt_dist_mark_list_boxes", (cudaStream_t)stream);
+    if (nentries <= 0) return BT_OK;
+    bt::dist_mark_list_boxes_kernel<<<bt::grid_for(nentries / 4 + 1, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        nentries, lists, (signed char*)out_mask);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+
+int bt_dist_corner_flags(int nboxes, const uint8_t* global_flags, const uint8_t* local_flags,
+                         const int8_t* mask_a, const int8_t* mask_b, uint8_t* out_flags, int32_t* any_out,
+                         void* stream)
+{
+    BT_PROF("bt_dist_corner_flags", (cudaStream_t)stream);
+    if (nboxes <= 0) return BT_OK;
+    bt::dist_corner_flags_kernel<<<bt::grid_for(nboxes, 256), 256, 0, (cudaStream_t)stream>>>(
+        nboxes, global_flags, local_flags, (const signed char*)mask_a, (const signed char*)mask_b,
+        out_flags, any_out);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+
 int bt_dist_box_to_user_rank(int phase, int nboxes, int nranks, const int8_t* masks_all_ranks,
                              int32_t* starts, int32_t* lists, int64_t* total_dev, void* stream)
 {
@@ -492,17 +585,6 @@ int bt_dist_box_to_user_rank(int phase, int nboxes, int nranks, const int8_t* ma
     return BT_OK;
 }
 
-int bt_dist_particle_box(int nboxes, const int32_t* local_start, const int32_t* local_own,
-                         int32_t* particle_box, void* stream)
-{
-    BT_PROF("bt_dist_particle_box", (cudaStream_t)stream);
-    if (nboxes <= 0) return BT_OK;
-    bt::dist_particle_box_kernel<<<bt::grid_for((int64_t)nboxes * 8, 256, 8), 256, 0, (cudaStream_t)stream>>>(
-        nboxes, local_start, local_own, particle_box);
-    BT_LAUNCH_CHECK();
-    return BT_OK;
-}
-
 int bt_dist_mask_bits(int nboxes, int nranks, const int8_t* masks_all_ranks, uint32_t* dest_bits, void* stream)
 {
     BT_PROF("bt_dist_mask_bits", (cudaStream_t)stream);
@@ -514,21 +596,23 @@ int bt_dist_mask_bits(int nboxes, int nranks, const int8_t* masks_all_ranks, uin
     return BT_OK;
 }
 
-int bt_dist_pack_records(int dtype, int nranks, int dim, int64_t n, const int32_t* particle_box,
-                         const uint32_t* dest_bits, void* const* particles, const void* radii,
-                         const int32_t* local_start, const int32_t* rank_excl, void* sendbuf,
+int bt_dist_pack_records(int dtype, int nranks, int dim, int nboxes, const uint32_t* dest_bits,
+                         void* const* particles, const void* radii, const int32_t* local_start,
+                         const int32_t* local_own, const int32_t* rank_excl, void* sendbuf,
                          int64_t* dest_offsets, void* stream, int64_t capacity)
 {
     BT_PROF("bt_dist_pack_records", (cudaStream_t)stream);
     cudaStream_t s = (cudaStream_t)stream;
     if (nranks > 32) return BT_ERR_UNSUPPORTED;
-    if (n <= 0) return (int)cudaMemsetAsync(dest_offsets, 0, sizeof(int64_t) * (nranks + 1), s);
+    if (nboxes <= 0) return (int)cudaMemsetAsync(dest_offsets, 0, sizeof(int64_t) * (nranks + 1), s);
     if (dtype == BT_F32)
-        return bt::pack_impl<float>(nranks, dim, n, particle_box, dest_bits, particles, radii, local_start,
-                                    rank_excl, sendbuf, (long long*)dest_offsets, (long long)capacity, s);
+        return bt::pack_impl<float>(nranks, dim, nboxes, dest_bits, particles, radii, local_start,
+                                    local_own, rank_excl, sendbuf, (long long*)dest_offsets,
+                                    (long long)capacity, s);
     if (dtype == BT_F64)
-        return bt::pack_impl<double>(nranks, dim, n, particle_box, dest_bits, particles, radii, local_start,
-                                     rank_excl, sendbuf, (long long*)dest_offsets, (long long)capacity, s);
+        return bt::pack_impl<double>(nranks, dim, nboxes, dest_bits, particles, radii, local_start,
+                                     local_own, rank_excl, sendbuf, (long long*)dest_offsets,
+                                     (long long)capacity, s);
     return BT_ERR_BAD_ARG;
 }
 

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from .comm import SingleProcessComm, ThreadComm, ThreadGroup, TorchDistComm
-from .exchange import exchange_particles, preorder
+from .exchange import _local_ranges, exchange_particles, preorder
 from .local_traversal import generate_local_travs
 from .local_tree import LocalTree, assemble_local_tree, box_to_user_rank, generate_local_tree
 from .partition import (BoxMasks, get_box_ids_dfs_order, get_box_masks, get_box_masks_sharded,
@@ -169,18 +169,30 @@ def distributed_tree_setup(actx, dtree, traversal_builder, comm, cost_per_box=No
     particles and nothing is broadcast.  Collective over *comm*.
 
     Every rank partitions the boxes itself (``partition.py:60-121``: DFS-order cost prefix, the
-    same deterministic arithmetic on the replicated box arrays), builds the traversal rows of
-    its responsible boxes and their ancestors to derive its box masks (``partition.py:330-357``),
-    all-gathers the masks, receives the sources of its point-source boxes and the targets of its
-    responsible boxes from their owners in one all-to-all each
-    (:func:`exchange_particles`, replacing ``local_tree.py:408-470``) and builds its local
-    traversal (``local_traversal.py:37-60``).  Local tree, local traversal and the index arrays
-    are identical to the reference flow's on the concatenated particle set.
+    same deterministic arithmetic on the replicated box arrays) and builds its LOCAL traversal
+    (``local_traversal.py:37-60``) straight away -- the local target flags follow from the
+    responsible boxes and the global per-box target counts, no particle is needed.  Its rows
+    are rows of the global traversal, so the box masks (``partition.py:330-357``) are read off
+    it, plus a small second traversal over the few rows that the global traversal has on
+    responsible boxes / their ancestors and the local one lacks (boxes that are target or
+    target-parent boxes only through other ranks' particles).  The masks are all-gathered, and
+    the sources of the rank's point-source boxes and the targets of its responsible boxes arrive
+    from their owners in one all-to-all each (:func:`exchange_particles`, replacing
+    ``local_tree.py:408-470``).  Local tree, local traversal, masks and index arrays are
+    identical to the reference flow's on the concatenated particle set.
 
     Returns ``(local_tree, local_trav, src_idx, tgt_idx)``."""
-    from types import SimpleNamespace  # noqa: F401
+    import dataclasses
+
+    from .._cabi import check, dptr, load
+    from .._timing import mark
+    from .partition import _masks_from_traversal, _responsible_and_ancestors
+    lib = load()
     rank, size = comm.Get_rank(), comm.Get_size()
+    nb = int(dtree.nboxes)
+    sh = actx.stream_handle
     with torch.cuda.stream(actx.stream), torch.cuda.device(actx.device):
+        mark("start")
         if cost_per_box is None:
             cost_per_box = (1.0 + dtree.box_source_counts_nonchild.double()
                             + dtree.box_target_counts_nonchild.double())
@@ -192,32 +204,65 @@ def distributed_tree_setup(actx, dtree, traversal_builder, comm, cost_per_box=No
             segs = partition_segments(cost_host[dfs_order.cpu().numpy()], size)
         seg = segs[rank]
         responsible = dfs_order[int(seg[0]):int(seg[1])]
-        masks, _partial, need = get_box_masks_sharded(actx, dtree, responsible, traversal_builder)
-        shared = getattr(traversal_builder, "last_shared", None)
+        resp_mask, anc_mask = _responsible_and_ancestors(actx, lib, dtree, responsible)
+        need = resp_mask | anc_mask
+        mark("ds:partition")
+
+        # {{{ local target ranges and flags: targets of the responsible boxes (local_tree.py:163-185)
+
+        pre = preorder(actx, dtree)
+        tgt_ranges = _local_ranges(actx, lib, nb, resp_mask, dtree.box_target_counts_nonchild, pre)
+        local_flags = dtree.box_flags.clone()
+        check(lib.bt_dist_modify_target_flags(nb, dptr(tgt_ranges[1]), dptr(tgt_ranges[2]),
+                                              dptr(local_flags), sh), "bt_dist_modify_target_flags")
+        corner_flags = actx.empty(nb, np.uint8)
+        any_corner = actx.zeros(1, np.int32)
+        check(lib.bt_dist_corner_flags(nb, dptr(dtree.box_flags), dptr(local_flags), dptr(resp_mask),
+                                       dptr(anc_mask), dptr(corner_flags), dptr(any_corner), sh),
+              "bt_dist_corner_flags")
+
+        # }}}
+
+        # {{{ local traversal, then the masks from its rows + the corner rows
+
+        flag_tree = dataclasses.replace(dtree, box_flags=local_flags)
+        local_trav, _ = traversal_builder(
+            actx, flag_tree, source_boxes_mask=resp_mask, source_parent_boxes_mask=anc_mask,
+            _colleague_row_mask=need, _keep_shared=True)
+        shared = traversal_builder.last_shared
+        traversal_builder.last_shared = None
+        mark("ds:local traversal")
+        # every row of the local traversal is a row the masks read: its target boxes are
+        # responsible boxes, its target-or-target-parent boxes responsible boxes or ancestors;
+        # the corner traversal has no list 1 / 3 rows and only rows of such boxes otherwise
+        masks = _masks_from_traversal(actx, lib, local_trav, resp_mask, anc_mask, all_rows=True)
+        if int(any_corner.item()):
+            corner_tree = dataclasses.replace(dtree, box_flags=corner_flags)
+            corner_trav, _ = traversal_builder(
+                actx, corner_tree, _colleague_row_mask=need,
+                _list13_row_mask=actx.zeros(nb, np.int8), _shared=shared)
+            masks = _masks_from_traversal(actx, lib, corner_trav, resp_mask, anc_mask, into=masks,
+                                          all_rows=True)
+            del corner_trav
+        del shared
+        mark("ds:masks")
+
+        # }}}
+
         # every rank's masks: who needs which box's sources / targets / multipoles
         mine = torch.stack([masks.point_src_boxes, masks.responsible_boxes,
                             masks.multipole_src_boxes])
         allm = comm.allgather_tensor(mine)                                   # [size, 3, nboxes]
-        if shared is not None and "dfs_rank" in shared:
-            pre_rank, subtree = shared["dfs_rank"], shared["subtree_size"]
-            pre_boxes = actx.empty(max(int(dtree.nboxes), 1), np.int32)
-            from .._cabi import check, dptr, load
-            check(load().bt_reverse_index(int(dtree.nboxes), dptr(pre_rank), dptr(pre_boxes),
-                                          actx.stream_handle), "bt_reverse_index")
-            pre = (pre_rank, pre_boxes, subtree)
-        else:
-            pre = preorder(actx, dtree)
+        mark("ds:allgather masks")
         src = exchange_particles(actx, comm, dtree, allm[:, 0].contiguous(),
                                  masks.point_src_boxes, "source", pre)
         tgt = exchange_particles(actx, comm, dtree, allm[:, 1].contiguous(),
-                                 masks.responsible_boxes, "target", pre)
+                                 masks.responsible_boxes, "target", pre, ranges=tgt_ranges)
+        mark("ds:exchange")
         local_tree = assemble_local_tree(actx, dtree, src, tgt, masks, allm[:, 2].contiguous(),
                                          responsible)
-        local_trav, _ = traversal_builder(
-            actx, local_tree, source_boxes_mask=local_tree.responsible_boxes_mask,
-            source_parent_boxes_mask=local_tree.ancestor_mask, _colleague_row_mask=need,
-            _shared=shared)
-        traversal_builder.last_shared = None
+        local_trav = dataclasses.replace(local_trav, tree=local_tree)
         if merge_close_lists and local_tree.targets_have_extent:
             local_trav = local_trav.merge_close_lists(actx)
+        mark("ds:local tree")
     return local_tree, local_trav, src[5], tgt[5]

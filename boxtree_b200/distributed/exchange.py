@@ -41,10 +41,25 @@ def preorder(actx, tree):
     return rank, boxes, size
 
 
-def exchange_particles(actx, comm, dtree, masks_all_ranks, my_mask, kind, pre):
+def _local_ranges(actx, lib, nb, mask, own_counts, pre):
+    """``(local_starts, local_counts_nonchild, local_counts_cumul)`` of the rank's local particle
+    arrays for the boxes of *mask* (``local_tree.py:249-284``), from the global own counts."""
+    pre_rank, pre_boxes, subtree = pre
+    prefix = actx.empty(nb + 1, np.int32)
+    lstarts = actx.empty(nb, np.int32)
+    lnonchild = actx.empty(nb, np.int32)
+    lcumul = actx.empty(nb, np.int32)
+    check(lib.bt_dist_local_ranges(nb, dptr(mask), dptr(own_counts), dptr(pre_rank), dptr(pre_boxes),
+                                   dptr(subtree), dptr(prefix), dptr(lstarts), dptr(lnonchild),
+                                   dptr(lcumul), actx.stream_handle), "bt_dist_local_ranges")
+    return lstarts, lnonchild, lcumul
+
+
+def exchange_particles(actx, comm, dtree, masks_all_ranks, my_mask, kind, pre, ranges=None):
     """Collective.  *masks_all_ranks* ``[nranks, nboxes]`` int8: rank *d* needs the *kind*
     (``"source"`` / ``"target"``) particles of the boxes with ``masks_all_ranks[d][b] != 0``;
-    *my_mask* is this rank's row.  *pre* = :func:`preorder` of the tree.
+    *my_mask* is this rank's row.  *pre* = :func:`preorder` of the tree; *ranges*: the result of
+    ``_local_ranges`` for *my_mask* when the caller already has it.
 
     :returns: ``(particles, radii, local_starts, local_counts_nonchild, local_counts_cumul,
         idx)`` like ``construct_local_particles_and_lists`` (``local_tree.py:198-284``); *idx*
@@ -73,20 +88,17 @@ def exchange_particles(actx, comm, dtree, masks_all_ranks, my_mask, kind, pre):
     dest_bits = actx.empty(max(nb, 1), np.int32)
     check(lib.bt_dist_mask_bits(nb, nranks, dptr(masks_all_ranks.contiguous()), dptr(dest_bits), sh),
           "bt_dist_mask_bits")
-    pbox = actx.empty(max(n, 1), np.int32)
-    check(lib.bt_dist_particle_box(nb, dptr(lstart), dptr(lown), dptr(pbox), sh),
-          "bt_dist_particle_box")
     # every particle goes to at most all ranks; the usual case is 1 + a thin halo
     dest_offsets = actx.zeros(nranks + 1, np.int64)
     sendbuf = None
     cap = max(n, 1) * 2
     while True:
         sendbuf = actx.empty(cap * recbytes, np.uint8)
-        # a record is only written when it fits (the scan clamps nothing): size first
-        check(lib.bt_dist_pack_records(dcode, nranks, dims, n, dptr(pbox), dptr(dest_bits),
+        # records are only written while they fit; the offsets are always complete
+        check(lib.bt_dist_pack_records(dcode, nranks, dims, nb, dptr(dest_bits),
                                        _cabi.ptr_array(parts), dptr(radii), dptr(lstart),
-                                       dptr(rank_excl), dptr(sendbuf), dptr(dest_offsets), sh,
-                                       cap), "bt_dist_pack_records")
+                                       dptr(lown), dptr(rank_excl), dptr(sendbuf),
+                                       dptr(dest_offsets), sh, cap), "bt_dist_pack_records")
         # all ranks' offsets in one collective, one readback
         all_off = comm.allgather_tensor(dest_offsets).cpu().numpy()      # [nranks, nranks + 1]
         need = int(all_off[rank, nranks])
@@ -105,14 +117,8 @@ def exchange_particles(actx, comm, dtree, masks_all_ranks, my_mask, kind, pre):
 
     # {{{ unpack into the rank's local arrays (global tree order restricted to its boxes)
 
-    pre_rank, pre_boxes, subtree = pre
-    prefix = actx.empty(nb + 1, np.int32)
-    lstarts = actx.empty(nb, np.int32)
-    lnonchild = actx.empty(nb, np.int32)
-    lcumul = actx.empty(nb, np.int32)
-    check(lib.bt_dist_local_ranges(nb, dptr(my_mask), dptr(gown), dptr(pre_rank), dptr(pre_boxes),
-                                   dptr(subtree), dptr(prefix), dptr(lstarts), dptr(lnonchild),
-                                   dptr(lcumul), sh), "bt_dist_local_ranges")
+    lstarts, lnonchild, lcumul = ranges if ranges is not None else \
+        _local_ranges(actx, lib, nb, my_mask, gown, pre)
     coord_dtype = dtree.coord_dtype
     local = [actx.empty(nrecv, coord_dtype) for _ in range(dims)]
     local_radii = actx.empty(nrecv, coord_dtype) if have_radii else None

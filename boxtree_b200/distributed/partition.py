@@ -140,20 +140,28 @@ def _responsible_and_ancestors(actx, lib, tree, responsible_boxes_list):
     return responsible, ancestors
 
 
-def _masks_from_traversal(actx, lib, traversal, responsible, ancestors) -> BoxMasks:
+def _masks_from_traversal(actx, lib, traversal, responsible, ancestors, into=None,
+                          all_rows=False) -> BoxMasks:
     """Point-source and multipole-source masks from the rows of *traversal* that belong to
-    responsible boxes / their ancestors (``partition.py:197-297``)."""
+    responsible boxes / their ancestors (``partition.py:197-297``).  *into*: masks of an earlier
+    call on other rows of the same global traversal, which this call adds to.  *all_rows*: the
+    caller guarantees that every non-empty row of every list qualifies (a traversal that was
+    built for exactly those rows): entries are marked without looking up their row."""
     tree = traversal.tree
     nb = int(tree.nboxes)
     sh = actx.stream_handle
 
     def add(box_list, mask_a, mask_b, starts, lists, out):
+        if all_rows:
+            check(lib.bt_dist_mark_list_boxes(int(lists.shape[0]), dptr(_dev(actx, lists)),
+                                              dptr(out), sh), "bt_dist_mark_list_boxes")
+            return
         check(lib.bt_dist_add_list_boxes(int(box_list.shape[0]), dptr(_dev(actx, box_list)),
                                          dptr(mask_a), dptr(mask_b), dptr(_dev(actx, starts)),
                                          dptr(_dev(actx, lists)), dptr(out), sh),
               "bt_dist_add_list_boxes")
 
-    src = responsible.clone()
+    src = responsible.clone() if into is None else into.point_src_boxes
     add(traversal.target_boxes, responsible, None, traversal.neighbor_source_boxes_starts,
         traversal.neighbor_source_boxes_lists, src)
     add(traversal.target_or_target_parent_boxes, responsible, ancestors,
@@ -167,7 +175,7 @@ def _masks_from_traversal(actx, lib, traversal, responsible, ancestors) -> BoxMa
             add(traversal.target_boxes, responsible, ancestors,
                 traversal.from_sep_close_bigger_starts,
                 traversal.from_sep_close_bigger_lists, src)
-    mpole = actx.zeros(nb, np.int8)
+    mpole = actx.zeros(nb, np.int8) if into is None else into.multipole_src_boxes
     add(traversal.target_or_target_parent_boxes, responsible, ancestors,
         traversal.from_sep_siblings_starts, traversal.from_sep_siblings_lists, mpole)
     for ilevel in range(int(tree.nlevels)):

@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from . import _cabi
+from ._timing import mark
 from ._cabi import (CTL_LR_FOUND, CTL_NBOXES, CTL_NBOXES_FINAL, CTL_NHUGE, CTL_NSPLIT,
                     CTL_NSPLIT_REGULAR, CTL_OVERFLOW, CTL_OVERSIZE, CTL_SIZE, STEP_ALL, STEP_COMMIT,
                     STEP_CREATE, STEP_DECIDE, bt_box_out, bt_particles, bt_pool, check, dptr)
@@ -291,6 +292,7 @@ class TreeBuilder:
         nb = 2**dimensions
 
         with torch.cuda.stream(stream), torch.cuda.device(actx.device):
+            mark("start")
             # {{{ particle view (virtual concatenation, tree_build.py:328-388)
 
             P = bt_particles()
@@ -347,6 +349,7 @@ class TreeBuilder:
 
             # }}}
 
+            mark("tb:bbox")
             # {{{ keys + sort
 
             key_bufs = [actx.empty(nsrcntgts, np.int64), actx.empty(nsrcntgts, np.int64)]
@@ -371,6 +374,7 @@ class TreeBuilder:
 
             # }}}
 
+            mark("tb:keys+sort")
             # {{{ level loop (tree_build.py:653-1276)
 
             nboxes_guess = kwargs.get("nboxes_guess")
@@ -485,6 +489,7 @@ class TreeBuilder:
 
             # }}}
 
+            mark("tb:level loop")
             # {{{ prune / renumber (tree_build.py:1330-1456)
 
             prune_empty_leaves = not kwargs.get("skip_prune")
@@ -535,6 +540,7 @@ class TreeBuilder:
 
             # }}}
 
+            mark("tb:prune+gather")
             # {{{ particle order inside never-partitioned boxes
 
             big_list = actx.empty(max(nfinal, 1), np.int32)
@@ -598,6 +604,7 @@ class TreeBuilder:
 
             # }}}
 
+            mark("tb:leaf fixup+split+permute")
             # {{{ per-box particle ranges and flags (tree_build.py:1666-1723)
 
             box_flags = actx.empty(nfinal, box_flags_enum.dtype)
@@ -648,6 +655,7 @@ class TreeBuilder:
 
             # }}}
 
+            mark("tb:box info")
             # {{{ box particle extents (tree_build.py:1730-1802)
 
             bb_src_min = actx.zeros((dimensions, aligned_nboxes), coord_dtype)
@@ -688,6 +696,7 @@ class TreeBuilder:
             evt = torch.cuda.Event()
             evt.record(stream)
 
+            mark("tb:extents")
             rank_excl = None
             if dist:
                 # own particles of lower ranks per box (exclusive scan over ranks): a particle's
@@ -697,6 +706,8 @@ class TreeBuilder:
                 r = comm.Get_rank()
                 rank_excl = allown[:r].sum(dim=0, dtype=torch.int32) if r else torch.zeros_like(own)
                 del allown
+
+            mark("tb:rank offsets")
 
         self.last_stats = {"level_iterations": niterations, "nboxes_pre_prune": nboxes,
                            "reallocs": nreallocs}

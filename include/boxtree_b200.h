@@ -481,6 +481,16 @@ int bt_dist_modify_target_flags(int nboxes, const int32_t *tgt_nonchild, const i
 int bt_dist_restrict_target_flags(int nboxes, const uint8_t *box_flags, const int8_t *mask_a,
                                   const int8_t *mask_b, uint8_t *out_flags, int8_t *need_mask,
                                   void *stream);
+/* add_interaction_list_boxes (partition.py:135-162) for a list ALL of whose rows qualify:
+ * out_mask[lists[k]] = 1 for every entry */
+int bt_dist_mark_list_boxes(int64_t nentries, const int32_t *lists, int8_t *out_mask, void *stream);
+/* distributed build (no reference counterpart): out_flags keeps the source bits of the global
+ * flags and, on boxes of mask_a | mask_b, the target bits that the rank's local flags lack --
+ * the rows of the global traversal that get_box_masks reads (partition.py:197-297) but the
+ * local traversal does not contain; *any_out != 0 if there is such a box */
+int bt_dist_corner_flags(int nboxes, const uint8_t *global_flags, const uint8_t *local_flags,
+                         const int8_t *mask_a, const int8_t *mask_b, uint8_t *out_flags,
+                         int32_t *any_out, void *stream);
 /* MaskCompressorKernel 2-D (tools.py:647-740) on the gathered multipole masks
  * [nranks, nboxes]: phase 0 starts[nboxes+1] + total, phase 1 lists (ascending ranks) */
 int bt_dist_box_to_user_rank(int phase, int nboxes, int nranks, const int8_t *masks_all_ranks,
@@ -490,24 +500,23 @@ int bt_dist_box_to_user_rank(int phase, int nboxes, int nranks, const int8_t *ma
 /* ---- particle exchange of the distributed build: the all-to-all that replaces the root's
  * fetch_local_particles + scatter (local_tree.py:124-151, 408-495).  Every rank holds the
  * global box arrays and its own input particles in tree order.
- * bt_dist_particle_box: box id of every local particle from the boxes' own ranges.
  * bt_dist_mask_bits: masks [nranks, nboxes] -> one bit per rank and box.
  * bt_dist_pack_records: for destination rank d = 0..nranks-1 in turn, one record
  *   [coords (dim) | radius (if radii) | box id i32 | index in the box's own range i32]
- *   per local particle whose box has bit d set, in tree order; dest_offsets [nranks+1] are
- *   the record offsets per destination (always complete; records beyond `capacity` are not
- *   written: enlarge and call again).  rank_excl[b] = own particles of lower ranks in box b.
+ *   per own particle of every box that has bit d set (boxes in id order); dest_offsets
+ *   [nranks+1] are the record offsets per destination (always complete; records beyond
+ *   `capacity` are not written: enlarge and call again).  local_start / local_own: the box's
+ *   own range in this rank's tree-ordered particles; rank_excl[b] = own particles of lower
+ *   ranks in box b.
  * bt_dist_unpack_records: scatter received records to dst_start[box] + index; particle_idx
  *   gets the particle's position in the global tree order (box_global_start[box] + index).
  * bt_dist_local_ranges: per-box ranges of the local particle arrays (local_tree.py:249-284)
  *   from the masked own counts in box pre-order (own particles precede the children's). */
-int bt_dist_particle_box(int nboxes, const int32_t *local_start, const int32_t *local_own,
-                         int32_t *particle_box, void *stream);
 int bt_dist_mask_bits(int nboxes, int nranks, const int8_t *masks_all_ranks, uint32_t *dest_bits,
                       void *stream);
-int bt_dist_pack_records(int dtype, int nranks, int dim, int64_t n, const int32_t *particle_box,
-                         const uint32_t *dest_bits, void *const *particles, const void *radii,
-                         const int32_t *local_start, const int32_t *rank_excl, void *sendbuf,
+int bt_dist_pack_records(int dtype, int nranks, int dim, int nboxes, const uint32_t *dest_bits,
+                         void *const *particles, const void *radii, const int32_t *local_start,
+                         const int32_t *local_own, const int32_t *rank_excl, void *sendbuf,
                          int64_t *dest_offsets, void *stream, int64_t capacity);
 int bt_dist_unpack_records(int dtype, int dim, int64_t nrec, int has_radii, const void *recvbuf,
                            const int32_t *dst_start, const int32_t *box_global_start,
