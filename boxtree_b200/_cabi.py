@@ -147,9 +147,14 @@ SIGNATURES = {
     "bt_dist_restrict_target_flags": [_i, vp, vp, vp, vp, vp, vp],
     "bt_dist_corner_flags": [_i, vp, vp, vp, vp, vp, vp, vp],
     "bt_dist_mark_list_boxes": [_i64, vp, vp, vp],
-    "bt_dist_mask_bits": [_i, _i, vp, vp, vp],
-    "bt_dist_pack_records": [_i, _i, _i, _i, vp, _P(vp), vp, vp, vp, vp, vp, vp, vp, _i64],
-    "bt_dist_unpack_records": [_i, _i, _i64, _i, vp, vp, vp, _P(vp), vp, vp, vp],
+    "bt_dist_mask_bits": [_i, _i, _i, vp, vp, vp],
+    "bt_dist_pack_ntiles": [_i64],
+    "bt_dist_pack_count": [_i, _i, _i64, vp, vp, vp, vp, vp, vp, vp, vp],
+    "bt_dist_pack_records": [_i, _i, _i, _i64, vp, vp, vp, _P(vp), vp, vp, vp, vp],
+    "bt_dist_compact_index": [_i, vp, vp, vp, vp],
+    "bt_dist_unpack_records": [_i, _i, _i, _i64, _i, vp, _P(_i64), vp, _i, vp, vp, vp, _P(vp), vp,
+                               vp, vp],
+    "bt_dist_box_to_user_rank_bits": [_i, _i, _i, _i, vp, vp, vp, vp, vp],
     "bt_dist_local_ranges": [_i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
 }
 

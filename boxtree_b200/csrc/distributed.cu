@@ -229,11 +229,11 @@ __global__ void dist_restrict_target_flags_kernel(int nboxes, const unsigned cha
 // MaskCompressorKernel, 2-D case (tools.py:647-740): masks[nranks][nboxes] -> per box the
 // ascending list of ranks whose mask is set
 struct RankCountIn {
-    const signed char* masks; int nranks; int64_t nboxes;
+    const signed char* masks; int nranks; int64_t nboxes; int bitsel;
     __device__ int operator()(int64_t b) const
     {
         int c = 0;
-        for (int r = 0; r < nranks; ++r) c += masks[(int64_t)r * nboxes + b] ? 1 : 0;
+        for (int r = 0; r < nranks; ++r) c += (masks[(int64_t)r * nboxes + b] & bitsel) ? 1 : 0;
         return c;
     }
 };
@@ -242,12 +242,12 @@ struct RankCountOut {
     __device__ void operator()(int64_t b, long long excl) const { starts[b] = (int)excl; }
     __device__ void total(long long t) const { starts[n] = (int)t; *total_out = t; }
 };
-__global__ void dist_rank_fill_kernel(int nboxes, int nranks, const signed char* __restrict__ masks,
+__global__ void dist_rank_fill_kernel(int nboxes, int nranks, int bitsel, const signed char* __restrict__ masks,
                                       const int* __restrict__ starts, int* __restrict__ lists)
 {
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nboxes; b += gridDim.x * blockDim.x) {
         int k = starts[b];
-        for (int r = 0; r < nranks; ++r) if (masks[(int64_t)r * nboxes + b]) lists[k++] = r;
+        for (int r = 0; r < nranks; ++r) if (masks[(int64_t)r * nboxes + b] & bitsel) lists[k++] = r;
     }
 }
 
@@ -271,94 +271,211 @@ static int fetch_impl(int dim, int64_t n, const int* mask, const int* g2l, void*
 // particles in tree order.  A rank's local tree (local_tree.py:198-284) needs the sources of
 // its point-source boxes and the targets of its responsible boxes, wherever they live: each
 // owner packs, per destination rank, one record per needed particle
-//     [coords (dim) | radius (optional) | box id (i32) | index inside the box's own range (i32)]
+//     [coords (dim) | radius (optional) | box id (i32) | index in the owner's own range (i32)]
 // the records travel in ONE all_to_all, and the receiver scatters them to
-//     local_start[box] + index,
-// which is the particle's place in the global tree order restricted to the rank's boxes (the
-// order construct_local_particles_and_lists produces).
+//     local_start[box] + (own particles of the box held by lower ranks) + index,
+// the particle's place in the global tree order restricted to the rank's boxes (the order
+// construct_local_particles_and_lists produces; inside a box's own range the global order is
+// rank-major because global particle ids are).  The per-(sender, box) counts that the middle
+// term needs are counted from the records themselves.
 
-// dest_bits[b] = OR over ranks r with masks[r][b] != 0 of (1 << r)
-__global__ void dist_mask_bits_kernel(int nboxes, int nranks, const signed char* __restrict__ masks,
+// dest_bits[b] = OR over ranks r with (masks[r][b] & bitsel) != 0 of (1 << r)
+__global__ void dist_mask_bits_kernel(int nboxes, int nranks, int bitsel, const signed char* __restrict__ masks,
                                       unsigned* __restrict__ bits)
 {
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nboxes; b += gridDim.x * blockDim.x) {
         unsigned v = 0;
-        for (int r = 0; r < nranks; ++r) if (masks[(int64_t)r * nboxes + b]) v |= 1u << r;
+        for (int r = 0; r < nranks; ++r) if (masks[(int64_t)r * nboxes + b] & bitsel) v |= 1u << r;
         bits[b] = v;
     }
 }
 
-// record offsets per (destination, box): exclusive scan, destination-major, of the own counts
-// of the boxes whose bit is set
-struct PackScanIn {
-    const unsigned* dest_bits; const int* lown; int nboxes;
-    __device__ int operator()(int64_t k) const
-    {
-        const int d = (int)(k / nboxes), b = (int)(k - (int64_t)d * nboxes);
-        return ((dest_bits[b] >> d) & 1u) ? lown[b] : 0;
-    }
-};
-struct PackScanOut {
-    int* offs; long long* dest_offsets; /* [nranks + 1] */ int nboxes; int nranks;
-    __device__ void operator()(int64_t k, long long excl) const
-    {
-        offs[k] = (int)excl;
-        if (k % nboxes == 0) dest_offsets[k / nboxes] = excl;
-    }
-    __device__ void total(long long t) const { dest_offsets[nranks] = t; }
-};
+constexpr int kMaxRanks = 32;
+struct DestBase { long long v[kMaxRanks + 1]; };
 
-// 8 lanes per box copy the box's own particles into the record range of every destination
-template <typename T>
+// box id of every local particle (the boxes' own ranges tile the local array); 8 lanes per box,
+// boxes with many own particles by the whole grid afterwards
+constexpr int kPboxBig = 512;
 __global__ void __launch_bounds__(256)
-dist_pack_kernel(int nboxes, int nranks, int dim, int recbytes, const unsigned* __restrict__ dest_bits,
-                 const int* __restrict__ lstart, const int* __restrict__ lown,
-                 const int* __restrict__ rank_excl, const int* __restrict__ offs,
-                 const T* c0, const T* c1, const T* c2, const T* __restrict__ radii,
-                 unsigned char* __restrict__ sendbuf, long long cap)
+dist_particle_box_kernel(int nboxes, const int* __restrict__ lstart, const int* __restrict__ lown,
+                         int* __restrict__ pbox, int* __restrict__ big_list, int* __restrict__ nbig)
 {
     const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, gl = threadIdx.x & 7;
     const int ng = (gridDim.x * blockDim.x) >> 3;
     for (int b = g; b < nboxes; b += ng) {
-        unsigned bits = dest_bits[b];
-        const int own = lown[b];
-        if (!bits || !own) continue;
-        const int s0 = lstart[b], rel0 = rank_excl[b];
-        while (bits) {
-            const int d = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const long long base = offs[(int64_t)d * nboxes + b];
-            for (int k = gl; k < own; k += 8) {
-                if (base + k >= cap) break;
-                unsigned char* rec = sendbuf + (base + k) * recbytes;
+        const int n = lown[b];
+        if (n > kPboxBig) { if (gl == 0) big_list[atomicAdd(nbig, 1)] = b; continue; }
+        const int s = lstart[b];
+        for (int p = gl; p < n; p += 8) pbox[s + p] = b;
+    }
+}
+__global__ void __launch_bounds__(256)
+dist_particle_box_big_kernel(const int* __restrict__ lstart, const int* __restrict__ lown,
+                             int* __restrict__ pbox, const int* __restrict__ big_list,
+                             const int* __restrict__ nbig)
+{
+    const int n = *nbig;
+    for (int e = 0; e < n; ++e) {
+        const int b = big_list[e], s = lstart[b], c = lown[b];
+        for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < c; p += gridDim.x * blockDim.x) pbox[s + p] = b;
+    }
+}
+
+// Multisplit of the local particles by destination rank (a particle may have several):
+// tiles of kPackTile consecutive particles; pass 1 counts the records per (tile, destination),
+// one scan over the destination-major counts gives every tile's record offset in every
+// destination's chunk, pass 2 writes the records -- in tree order inside each chunk.
+constexpr int kPackBlock = 256;
+constexpr int kPackIters = 4;
+constexpr int kPackTile = kPackBlock * kPackIters;
+
+__global__ void __launch_bounds__(kPackBlock)
+dist_pack_count_kernel(int64_t n, int nranks, int64_t ntiles, const int* __restrict__ pbox,
+                       const unsigned* __restrict__ dest_bits, int* __restrict__ tile_counts /*[nranks][ntiles]*/)
+{
+    __shared__ int sc[kMaxRanks];
+    const int lane = threadIdx.x & 31;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (threadIdx.x < kMaxRanks) sc[threadIdx.x] = 0;
+        __syncthreads();
+        int mine = 0;                 // lane d of every warp accumulates destination d
+        for (int it = 0; it < kPackIters; ++it) {
+            const int64_t p = tile * kPackTile + it * kPackBlock + threadIdx.x;
+            const unsigned bits = (p < n) ? dest_bits[pbox[p]] : 0u;
+            for (int d = 0; d < nranks; ++d) {
+                const unsigned m = __ballot_sync(0xffffffffu, (bits >> d) & 1u);
+                if (lane == d) mine += __popc(m);
+            }
+        }
+        if (lane < nranks && mine) atomicAdd(&sc[lane], mine);
+        __syncthreads();
+        if (threadIdx.x < nranks) tile_counts[(int64_t)threadIdx.x * ntiles + tile] = sc[threadIdx.x];
+        __syncthreads();
+    }
+}
+
+struct TileScanIn {
+    const int* counts;
+    __device__ int operator()(int64_t i) const { return counts[i]; }
+};
+struct TileScanOut {
+    long long* offs; long long* dest_offsets; int64_t ntiles; int nranks;
+    __device__ void operator()(int64_t i, long long excl) const
+    {
+        offs[i] = excl;
+        if (i % ntiles == 0) dest_offsets[i / ntiles] = excl;
+    }
+    __device__ void total(long long t) const { dest_offsets[nranks] = t; }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kPackBlock)
+dist_pack_kernel(int64_t n, int nranks, int64_t ntiles, int dim, int recbytes, const int* __restrict__ pbox,
+                 const unsigned* __restrict__ dest_bits, const long long* __restrict__ tile_offs,
+                 const int* __restrict__ lstart, const T* c0, const T* c1, const T* c2,
+                 const T* __restrict__ radii, unsigned char* __restrict__ sendbuf)
+{
+    __shared__ int swarp[kPackBlock / 32][kMaxRanks];     // per-warp counts of this iteration
+    __shared__ long long srun[kMaxRanks];                 // next record of the tile per destination
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x < nranks) srun[threadIdx.x] = tile_offs[(int64_t)threadIdx.x * ntiles + tile];
+        for (int it = 0; it < kPackIters; ++it) {
+            const int64_t p = tile * kPackTile + it * kPackBlock + threadIdx.x;
+            int b = 0, k = 0;
+            unsigned bits = 0;
+            T v0 = 0, v1 = 0, v2 = 0, vr = 0;
+            if (p < n) {
+                b = pbox[p]; bits = dest_bits[b];
+                if (bits) {
+                    k = (int)(p - lstart[b]);
+                    v0 = c0[p];
+                    if (dim > 1) v1 = c1[p];
+                    if (dim > 2) v2 = c2[p];
+                    if (radii) vr = radii[p];
+                }
+            }
+            for (int d = 0; d < nranks; ++d) {
+                const unsigned m = __ballot_sync(0xffffffffu, (bits >> d) & 1u);
+                if (lane == 0) swarp[warp][d] = __popc(m);
+            }
+            __syncthreads();
+            for (int d = 0; d < nranks; ++d) {
+                const unsigned m = __ballot_sync(0xffffffffu, (bits >> d) & 1u);
+                if (!((bits >> d) & 1u)) continue;
+                long long pos = srun[d] + __popc(m & lt);
+                for (int w = 0; w < warp; ++w) pos += swarp[w][d];
+                unsigned char* rec = sendbuf + pos * recbytes;
                 T* c = reinterpret_cast<T*>(rec);
-                const int p = s0 + k;
-                c[0] = c0[p];
-                if (dim > 1) c[1] = c1[p];
-                if (dim > 2) c[2] = c2[p];
+                c[0] = v0;
+                if (dim > 1) c[1] = v1;
+                if (dim > 2) c[2] = v2;
                 int q = dim;
-                if (radii) c[q++] = radii[p];
+                if (radii) c[q++] = vr;
                 int* tail = reinterpret_cast<int*>(c + q);
                 tail[0] = b;
-                tail[1] = rel0 + k;
+                tail[1] = k;
             }
+            __syncthreads();
+            if (threadIdx.x < nranks) {
+                int t = 0;
+                for (int w = 0; w < kPackBlock / 32; ++w) t += swarp[w][threadIdx.x];
+                srun[threadIdx.x] += t;
+            }
+            __syncthreads();
         }
     }
 }
 
+// receiver, step 1: records per (sender, box of my mask); compact[b] = index of box b among
+// the boxes of the mask
 template <typename T>
 __global__ void __launch_bounds__(256)
-dist_unpack_kernel(int64_t nrec, int dim, int recbytes, int has_radii, const unsigned char* __restrict__ recv,
-                   const int* __restrict__ dst_start, const int* __restrict__ gstart,
-                   T* o0, T* o1, T* o2, T* __restrict__ oradii, long long* __restrict__ idx_out)
+dist_unpack_count_kernel(int64_t nrec, int nranks, int nfields, int recbytes, DestBase chunk,
+                         const unsigned char* __restrict__ recv, const int* __restrict__ compact,
+                         int nmasked, int* __restrict__ cnt /*[nranks][nmasked]*/)
 {
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nrec;
          k += (int64_t)gridDim.x * blockDim.x) {
+        int s = 0;
+        while (s + 1 < nranks && chunk.v[s + 1] <= k) ++s;
+        const int* tail = reinterpret_cast<const int*>(recv + k * recbytes + (size_t)nfields * sizeof(T));
+        atomicAdd(&cnt[(int64_t)s * nmasked + compact[tail[0]]], 1);
+    }
+}
+// step 2: exclusive prefix over the senders, per box
+__global__ void dist_unpack_prefix_kernel(int nranks, int nmasked, int* __restrict__ cnt)
+{
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < nmasked; m += gridDim.x * blockDim.x) {
+        int run = 0;
+        for (int s = 0; s < nranks; ++s) {
+            const int v = cnt[(int64_t)s * nmasked + m];
+            cnt[(int64_t)s * nmasked + m] = run;
+            run += v;
+        }
+    }
+}
+// step 3: scatter
+template <typename T>
+__global__ void __launch_bounds__(256)
+dist_unpack_kernel(int64_t nrec, int nranks, int dim, int recbytes, int has_radii, DestBase chunk,
+                   const unsigned char* __restrict__ recv, const int* __restrict__ compact, int nmasked,
+                   const int* __restrict__ cnt, const int* __restrict__ dst_start,
+                   const int* __restrict__ gstart, T* o0, T* o1, T* o2, T* __restrict__ oradii,
+                   long long* __restrict__ idx_out)
+{
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nrec;
+         k += (int64_t)gridDim.x * blockDim.x) {
+        int s = 0;
+        while (s + 1 < nranks && chunk.v[s + 1] <= k) ++s;
         const unsigned char* rec = recv + k * recbytes;
         const T* c = reinterpret_cast<const T*>(rec);
-        int q = dim + (has_radii ? 1 : 0);
+        const int q = dim + (has_radii ? 1 : 0);
         const int* tail = reinterpret_cast<const int*>(c + q);
-        const int b = tail[0], rel = tail[1];
+        const int b = tail[0];
+        const int rel = cnt[(int64_t)s * nmasked + compact[b]] + tail[1];
         const int64_t pos = (int64_t)dst_start[b] + rel;
         o0[pos] = c[0];
         if (dim > 1) o1[pos] = c[1];
@@ -367,6 +484,17 @@ dist_unpack_kernel(int64_t nrec, int dim, int recbytes, int has_radii, const uns
         idx_out[pos] = (long long)gstart[b] + rel;
     }
 }
+
+// compact index of the boxes of a mask (box-id order)
+struct CompactIn {
+    const signed char* mask;
+    __device__ int operator()(int64_t i) const { return mask[i] ? 1 : 0; }
+};
+struct CompactOut {
+    int* compact; int* total_out;
+    __device__ void operator()(int64_t i, long long excl) const { compact[i] = (int)excl; }
+    __device__ void total(long long t) const { *total_out = (int)t; }
+};
 
 // ranges of the rank's local particle arrays (local_tree.py:249-284) without a global particle
 // array: the global tree order is the boxes' pre-order (own particles, then the children in
@@ -395,23 +523,68 @@ __global__ void dist_local_ranges_kernel(int nboxes, const signed char* __restri
     }
 }
 
-template <typename T>
-static int pack_impl(int nranks, int dim, int nboxes, const unsigned* dest_bits, void* const* parts,
-                     const void* radii, const int* lstart, const int* lown, const int* rank_excl,
-                     void* sendbuf, long long* dest_offsets, long long cap, cudaStream_t s)
+static int pack_count_impl(int nranks, int nboxes, int64_t n, const unsigned* dest_bits, const int* lstart,
+                           const int* lown, int* pbox, int* tile_counts, long long* tile_offs,
+                           long long* dest_offsets, cudaStream_t s)
 {
-    const int recbytes = (int)sizeof(T) * (dim + (radii ? 1 : 0)) + 8;
-    int* offs = nullptr;
-    BT_CHECK(temp_alloc((void**)&offs, sizeof(int) * (size_t)nranks * nboxes, s));
-    PackScanIn in{dest_bits, lown, nboxes};
-    PackScanOut out{offs, dest_offsets, nboxes, nranks};
-    BT_TRY(scan_exclusive((int64_t)nranks * nboxes, nullptr, in, out, s));
-    dist_pack_kernel<T><<<grid_for((int64_t)nboxes * 8, 256, 8), 256, 0, s>>>(
-        nboxes, nranks, dim, recbytes, dest_bits, lstart, lown, rank_excl, offs, (const T*)parts[0],
-        dim > 1 ? (const T*)parts[1] : nullptr, dim > 2 ? (const T*)parts[2] : nullptr,
-        (const T*)radii, (unsigned char*)sendbuf, cap);
+    const int64_t ntiles = (n + kPackTile - 1) / kPackTile;
+    if (n <= 0) return (int)cudaMemsetAsync(dest_offsets, 0, sizeof(long long) * (nranks + 1), s);
+    int* big = nullptr;
+    BT_CHECK(temp_alloc((void**)&big, sizeof(int) * ((size_t)n / kPboxBig + 2), s));
+    BT_CHECK(cudaMemsetAsync(big, 0, sizeof(int), s));
+    dist_particle_box_kernel<<<grid_for((int64_t)nboxes * 8, 256, 8), 256, 0, s>>>(
+        nboxes, lstart, lown, pbox, big + 1, big);
     BT_LAUNCH_CHECK();
-    BT_CHECK(cudaFreeAsync(offs, s));
+    dist_particle_box_big_kernel<<<kNumSMs * 4, 256, 0, s>>>(lstart, lown, pbox, big + 1, big);
+    BT_LAUNCH_CHECK();
+    BT_CHECK(cudaFreeAsync(big, s));
+    dist_pack_count_kernel<<<(unsigned)(ntiles < kNumSMs * 8 ? ntiles : kNumSMs * 8), kPackBlock, 0, s>>>(
+        n, nranks, ntiles, pbox, dest_bits, tile_counts);
+    BT_LAUNCH_CHECK();
+    TileScanIn in{tile_counts};
+    TileScanOut out{tile_offs, dest_offsets, ntiles, nranks};
+    return scan_exclusive((int64_t)nranks * ntiles, nullptr, in, out, s);
+}
+
+template <typename T>
+static int pack_impl(int nranks, int dim, int64_t n, const int* pbox, const unsigned* dest_bits,
+                     const long long* tile_offs, void* const* parts, const void* radii,
+                     const int* lstart, void* sendbuf, cudaStream_t s)
+{
+    if (n <= 0) return BT_OK;
+    const int recbytes = (int)sizeof(T) * (dim + (radii ? 1 : 0)) + 8;
+    const int64_t ntiles = (n + kPackTile - 1) / kPackTile;
+    dist_pack_kernel<T><<<(unsigned)(ntiles < kNumSMs * 8 ? ntiles : kNumSMs * 8), kPackBlock, 0, s>>>(
+        n, nranks, ntiles, dim, recbytes, pbox, dest_bits, tile_offs, lstart, (const T*)parts[0],
+        dim > 1 ? (const T*)parts[1] : nullptr, dim > 2 ? (const T*)parts[2] : nullptr,
+        (const T*)radii, (unsigned char*)sendbuf);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+
+template <typename T>
+static int unpack_impl(int nranks, int dim, int64_t nrec, int has_radii, const void* recvbuf,
+                       const long long* chunk_host, const int* compact, int nmasked, int* cnt,
+                       const int* dst_start, const int* gstart, void* const* outs, void* oradii,
+                       long long* idx_out, cudaStream_t s)
+{
+    const int nfields = dim + (has_radii ? 1 : 0);
+    const int recbytes = (int)sizeof(T) * nfields + 8;
+    DestBase chunk;
+    for (int d = 0; d <= kMaxRanks; ++d) chunk.v[d] = d <= nranks ? chunk_host[d] : 0;
+    BT_CHECK(cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)nranks * (nmasked > 0 ? nmasked : 1), s));
+    if (nrec <= 0) return BT_OK;
+    const int grid = grid_for(nrec, 256, 8);
+    dist_unpack_count_kernel<T><<<grid, 256, 0, s>>>(nrec, nranks, nfields, recbytes, chunk,
+                                                     (const unsigned char*)recvbuf, compact, nmasked, cnt);
+    BT_LAUNCH_CHECK();
+    dist_unpack_prefix_kernel<<<grid_for(nmasked, 256), 256, 0, s>>>(nranks, nmasked, cnt);
+    BT_LAUNCH_CHECK();
+    dist_unpack_kernel<T><<<grid, 256, 0, s>>>(
+        nrec, nranks, dim, recbytes, has_radii, chunk, (const unsigned char*)recvbuf, compact, nmasked,
+        cnt, dst_start, gstart, (T*)outs[0], dim > 1 ? (T*)outs[1] : nullptr,
+        dim > 2 ? (T*)outs[2] : nullptr, (T*)oradii, idx_out);
+    BT_LAUNCH_CHECK();
     return BT_OK;
 }
 
@@ -568,78 +741,74 @@ int bt_dist_corner_flags(int nboxes, const uint8_t* global_flags, const uint8_t*
     return BT_OK;
 }
 
-int bt_dist_box_to_user_rank(int phase, int nboxes, int nranks, const int8_t* masks_all_ranks,
-                             int32_t* starts, int32_t* lists, int64_t* total_dev, void* stream)
-{
-    BT_PROF("bt_dist_box_to_user_rank", (cudaStream_t)stream);
-    cudaStream_t s = (cudaStream_t)stream;
-    if (phase == 0) {
-        bt::RankCountIn in{(const signed char*)masks_all_ranks, nranks, nboxes};
-        bt::RankCountOut out{starts, nboxes, (long long*)total_dev};
-        return bt::scan_exclusive(nboxes, nullptr, in, out, s);
-    }
-    if (nboxes <= 0) return BT_OK;
-    bt::dist_rank_fill_kernel<<<bt::grid_for(nboxes, 256), 256, 0, s>>>(
-        nboxes, nranks, (const signed char*)masks_all_ranks, starts, lists);
-    BT_LAUNCH_CHECK();
-    return BT_OK;
-}
-
-int bt_dist_mask_bits(int nboxes, int nranks, const int8_t* masks_all_ranks, uint32_t* dest_bits, void* stream)
+int bt_dist_mask_bits(int nboxes, int nranks, int bitsel, const int8_t* masks_all_ranks,
+                      uint32_t* dest_bits, void* stream)
 {
     BT_PROF("bt_dist_mask_bits", (cudaStream_t)stream);
     if (nboxes <= 0) return BT_OK;
-    if (nranks > 32) return BT_ERR_UNSUPPORTED;
+    if (nranks > bt::kMaxRanks) return BT_ERR_UNSUPPORTED;
     bt::dist_mask_bits_kernel<<<bt::grid_for(nboxes, 256), 256, 0, (cudaStream_t)stream>>>(
-        nboxes, nranks, (const signed char*)masks_all_ranks, dest_bits);
+        nboxes, nranks, bitsel, (const signed char*)masks_all_ranks, dest_bits);
     BT_LAUNCH_CHECK();
     return BT_OK;
 }
 
-int bt_dist_pack_records(int dtype, int nranks, int dim, int nboxes, const uint32_t* dest_bits,
-                         void* const* particles, const void* radii, const int32_t* local_start,
-                         const int32_t* local_own, const int32_t* rank_excl, void* sendbuf,
-                         int64_t* dest_offsets, void* stream, int64_t capacity)
+int bt_dist_pack_ntiles(int64_t n) { return (int)((n + bt::kPackTile - 1) / bt::kPackTile); }
+
+int bt_dist_pack_count(int nranks, int nboxes, int64_t n, const uint32_t* dest_bits,
+                       const int32_t* local_start, const int32_t* local_own, int32_t* particle_box,
+                       int32_t* tile_counts, int64_t* tile_offsets, int64_t* dest_offsets, void* stream)
+{
+    BT_PROF("bt_dist_pack_count", (cudaStream_t)stream);
+    if (nranks > bt::kMaxRanks) return BT_ERR_UNSUPPORTED;
+    return bt::pack_count_impl(nranks, nboxes, n, dest_bits, local_start, local_own, particle_box,
+                               tile_counts, (long long*)tile_offsets, (long long*)dest_offsets,
+                               (cudaStream_t)stream);
+}
+
+int bt_dist_pack_records(int dtype, int nranks, int dim, int64_t n, const int32_t* particle_box,
+                         const uint32_t* dest_bits, const int64_t* tile_offsets, void* const* particles,
+                         const void* radii, const int32_t* local_start, void* sendbuf, void* stream)
 {
     BT_PROF("bt_dist_pack_records", (cudaStream_t)stream);
     cudaStream_t s = (cudaStream_t)stream;
-    if (nranks > 32) return BT_ERR_UNSUPPORTED;
-    if (nboxes <= 0) return (int)cudaMemsetAsync(dest_offsets, 0, sizeof(int64_t) * (nranks + 1), s);
+    if (nranks > bt::kMaxRanks) return BT_ERR_UNSUPPORTED;
     if (dtype == BT_F32)
-        return bt::pack_impl<float>(nranks, dim, nboxes, dest_bits, particles, radii, local_start,
-                                    local_own, rank_excl, sendbuf, (long long*)dest_offsets,
-                                    (long long)capacity, s);
+        return bt::pack_impl<float>(nranks, dim, n, particle_box, dest_bits, (const long long*)tile_offsets,
+                                    particles, radii, local_start, sendbuf, s);
     if (dtype == BT_F64)
-        return bt::pack_impl<double>(nranks, dim, nboxes, dest_bits, particles, radii, local_start,
-                                     local_own, rank_excl, sendbuf, (long long*)dest_offsets,
-                                     (long long)capacity, s);
+        return bt::pack_impl<double>(nranks, dim, n, particle_box, dest_bits, (const long long*)tile_offsets,
+                                     particles, radii, local_start, sendbuf, s);
     return BT_ERR_BAD_ARG;
 }
 
-int bt_dist_unpack_records(int dtype, int dim, int64_t nrec, int has_radii, const void* recvbuf,
-                           const int32_t* dst_start, const int32_t* box_global_start,
+int bt_dist_compact_index(int nboxes, const int8_t* box_mask, int32_t* compact, int32_t* nmasked_dev,
+                          void* stream)
+{
+    BT_PROF("bt_dist_compact_index", (cudaStream_t)stream);
+    bt::CompactIn in{(const signed char*)box_mask};
+    bt::CompactOut out{compact, nmasked_dev};
+    return bt::scan_exclusive(nboxes, nullptr, in, out, (cudaStream_t)stream);
+}
+
+int bt_dist_unpack_records(int dtype, int nranks, int dim, int64_t nrec, int has_radii, const void* recvbuf,
+                           const int64_t* chunk_offsets_host, const int32_t* compact, int nmasked,
+                           int32_t* count_tmp, const int32_t* dst_start, const int32_t* box_global_start,
                            void* const* local_particles, void* local_radii, int64_t* particle_idx,
                            void* stream)
 {
     BT_PROF("bt_dist_unpack_records", (cudaStream_t)stream);
     cudaStream_t s = (cudaStream_t)stream;
-    if (nrec <= 0) return BT_OK;
-    const int grid = bt::grid_for(nrec, 256, 8);
-    if (dtype == BT_F32) {
-        const int rb = 4 * (dim + (has_radii ? 1 : 0)) + 8;
-        bt::dist_unpack_kernel<float><<<grid, 256, 0, s>>>(
-            nrec, dim, rb, has_radii, (const unsigned char*)recvbuf, dst_start, box_global_start,
-            (float*)local_particles[0], dim > 1 ? (float*)local_particles[1] : nullptr,
-            dim > 2 ? (float*)local_particles[2] : nullptr, (float*)local_radii, (long long*)particle_idx);
-    } else if (dtype == BT_F64) {
-        const int rb = 8 * (dim + (has_radii ? 1 : 0)) + 8;
-        bt::dist_unpack_kernel<double><<<grid, 256, 0, s>>>(
-            nrec, dim, rb, has_radii, (const unsigned char*)recvbuf, dst_start, box_global_start,
-            (double*)local_particles[0], dim > 1 ? (double*)local_particles[1] : nullptr,
-            dim > 2 ? (double*)local_particles[2] : nullptr, (double*)local_radii, (long long*)particle_idx);
-    } else return BT_ERR_BAD_ARG;
-    BT_LAUNCH_CHECK();
-    return BT_OK;
+    if (nranks > bt::kMaxRanks) return BT_ERR_UNSUPPORTED;
+    if (dtype == BT_F32)
+        return bt::unpack_impl<float>(nranks, dim, nrec, has_radii, recvbuf, (const long long*)chunk_offsets_host,
+                                      compact, nmasked, count_tmp, dst_start, box_global_start,
+                                      local_particles, local_radii, (long long*)particle_idx, s);
+    if (dtype == BT_F64)
+        return bt::unpack_impl<double>(nranks, dim, nrec, has_radii, recvbuf, (const long long*)chunk_offsets_host,
+                                       compact, nmasked, count_tmp, dst_start, box_global_start,
+                                       local_particles, local_radii, (long long*)particle_idx, s);
+    return BT_ERR_BAD_ARG;
 }
 
 int bt_dist_local_ranges(int nboxes, const int8_t* box_mask, const int32_t* own_counts,
@@ -658,6 +827,30 @@ int bt_dist_local_ranges(int nboxes, const int8_t* box_mask, const int32_t* own_
         local_starts, local_nonchild, local_cumul);
     BT_LAUNCH_CHECK();
     return BT_OK;
+}
+
+int bt_dist_box_to_user_rank_bits(int phase, int nboxes, int nranks, int bitsel, const int8_t* masks_all_ranks,
+                                  int32_t* starts, int32_t* lists, int64_t* total_dev, void* stream)
+{
+    BT_PROF("bt_dist_box_to_user_rank", (cudaStream_t)stream);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (phase == 0) {
+        bt::RankCountIn in{(const signed char*)masks_all_ranks, nranks, nboxes, bitsel};
+        bt::RankCountOut out{starts, nboxes, (long long*)total_dev};
+        return bt::scan_exclusive(nboxes, nullptr, in, out, s);
+    }
+    if (nboxes <= 0) return BT_OK;
+    bt::dist_rank_fill_kernel<<<bt::grid_for(nboxes, 256), 256, 0, s>>>(
+        nboxes, nranks, bitsel, (const signed char*)masks_all_ranks, starts, lists);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+
+int bt_dist_box_to_user_rank(int phase, int nboxes, int nranks, const int8_t* masks_all_ranks,
+                             int32_t* starts, int32_t* lists, int64_t* total_dev, void* stream)
+{
+    return bt_dist_box_to_user_rank_bits(phase, nboxes, nranks, 0xff, masks_all_ranks, starts, lists,
+                                         total_dev, stream);
 }
 
 }  // extern "C"

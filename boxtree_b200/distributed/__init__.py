@@ -249,18 +249,17 @@ def distributed_tree_setup(actx, dtree, traversal_builder, comm, cost_per_box=No
 
         # }}}
 
-        # every rank's masks: who needs which box's sources / targets / multipoles
-        mine = torch.stack([masks.point_src_boxes, masks.responsible_boxes,
-                            masks.multipole_src_boxes])
-        allm = comm.allgather_tensor(mine)                                   # [size, 3, nboxes]
+        # every rank's masks as one bit field per box: who needs which box's sources (1) /
+        # targets (2) / multipoles (4)
+        mine = (masks.point_src_boxes | (masks.responsible_boxes << 1)
+                | (masks.multipole_src_boxes << 2))
+        allm = comm.allgather_tensor(mine)                                   # [size, nboxes]
         mark("ds:allgather masks")
-        src = exchange_particles(actx, comm, dtree, allm[:, 0].contiguous(),
-                                 masks.point_src_boxes, "source", pre)
-        tgt = exchange_particles(actx, comm, dtree, allm[:, 1].contiguous(),
-                                 masks.responsible_boxes, "target", pre, ranges=tgt_ranges)
+        src = exchange_particles(actx, comm, dtree, allm, 1, masks.point_src_boxes, "source", pre)
+        tgt = exchange_particles(actx, comm, dtree, allm, 2, masks.responsible_boxes, "target",
+                                 pre, ranges=tgt_ranges)
         mark("ds:exchange")
-        local_tree = assemble_local_tree(actx, dtree, src, tgt, masks, allm[:, 2].contiguous(),
-                                         responsible)
+        local_tree = assemble_local_tree(actx, dtree, src, tgt, masks, allm, responsible, bitsel=4)
         local_trav = dataclasses.replace(local_trav, tree=local_tree)
         if merge_close_lists and local_tree.targets_have_extent:
             local_trav = local_trav.merge_close_lists(actx)

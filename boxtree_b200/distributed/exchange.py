@@ -55,15 +55,18 @@ def _local_ranges(actx, lib, nb, mask, own_counts, pre):
     return lstarts, lnonchild, lcumul
 
 
-def exchange_particles(actx, comm, dtree, masks_all_ranks, my_mask, kind, pre, ranges=None):
-    """Collective.  *masks_all_ranks* ``[nranks, nboxes]`` int8: rank *d* needs the *kind*
-    (``"source"`` / ``"target"``) particles of the boxes with ``masks_all_ranks[d][b] != 0``;
-    *my_mask* is this rank's row.  *pre* = :func:`preorder` of the tree; *ranges*: the result of
-    ``_local_ranges`` for *my_mask* when the caller already has it.
+def exchange_particles(actx, comm, dtree, masks_all_ranks, bitsel, my_mask, kind, pre,
+                       ranges=None):
+    """Collective.  *masks_all_ranks* ``[nranks, nboxes]`` int8 bit fields: rank *d* needs the
+    *kind* (``"source"`` / ``"target"``) particles of the boxes with
+    ``masks_all_ranks[d][b] & bitsel``; *my_mask* (int8 0/1) is this rank's row.
+    *pre* = :func:`preorder` of the tree; *ranges*: the result of ``_local_ranges`` for
+    *my_mask* when the caller already has it.
 
     :returns: ``(particles, radii, local_starts, local_counts_nonchild, local_counts_cumul,
         idx)`` like ``construct_local_particles_and_lists`` (``local_tree.py:198-284``); *idx*
         (int64) is every local particle's position in the global tree order."""
+    import ctypes as C
     lib = _cabi.load()
     sh = actx.stream_handle
     nb = int(dtree.nboxes)
@@ -77,55 +80,61 @@ def exchange_particles(actx, comm, dtree, masks_all_ranks, my_mask, kind, pre, r
     lstart = dtree.local_box_source_starts if src else dtree.local_box_target_starts
     lown = dtree.local_box_source_counts_nonchild if src else \
         dtree.local_box_target_counts_nonchild
-    rank_excl = dtree.source_rank_offsets if src else dtree.target_rank_offsets
     gstart = dtree.box_source_starts if src else dtree.box_target_starts
     gown = dtree.box_source_counts_nonchild if src else dtree.box_target_counts_nonchild
-    n = int(parts[0].shape[0])
     recbytes = _record_bytes(dtree.coord_dtype, dims, have_radii)
 
-    # {{{ pack: destination-major records of the needed particles this rank owns
+    # {{{ count, agree on the chunk sizes (one small all-gather + one readback), pack
 
     dest_bits = actx.empty(max(nb, 1), np.int32)
-    check(lib.bt_dist_mask_bits(nb, nranks, dptr(masks_all_ranks.contiguous()), dptr(dest_bits), sh),
+    check(lib.bt_dist_mask_bits(nb, nranks, bitsel, dptr(masks_all_ranks), dptr(dest_bits), sh),
           "bt_dist_mask_bits")
-    # every particle goes to at most all ranks; the usual case is 1 + a thin halo
-    dest_offsets = actx.zeros(nranks + 1, np.int64)
-    sendbuf = None
-    cap = max(n, 1) * 2
-    while True:
-        sendbuf = actx.empty(cap * recbytes, np.uint8)
-        # records are only written while they fit; the offsets are always complete
-        check(lib.bt_dist_pack_records(dcode, nranks, dims, nb, dptr(dest_bits),
-                                       _cabi.ptr_array(parts), dptr(radii), dptr(lstart),
-                                       dptr(lown), dptr(rank_excl), dptr(sendbuf),
-                                       dptr(dest_offsets), sh, cap), "bt_dist_pack_records")
-        # all ranks' offsets in one collective, one readback
-        all_off = comm.allgather_tensor(dest_offsets).cpu().numpy()      # [nranks, nranks + 1]
-        need = int(all_off[rank, nranks])
-        if need <= cap:
-            break
-        cap = need
-    counts = np.diff(all_off, axis=1)                                   # [sender, dest]
+    n = int(parts[0].shape[0])
+    ntiles = max(int(lib.bt_dist_pack_ntiles(n)), 1)
+    pbox = actx.empty(max(n, 1), np.int32)
+    tile_counts = actx.empty(nranks * ntiles, np.int32)
+    tile_offs = actx.empty(nranks * ntiles, np.int64)
+    dest_offsets = actx.empty(nranks + 2, np.int64)
+    check(lib.bt_dist_pack_count(nranks, nb, n, dptr(dest_bits), dptr(lstart), dptr(lown),
+                                 dptr(pbox), dptr(tile_counts), dptr(tile_offs),
+                                 dptr(dest_offsets), sh), "bt_dist_pack_count")
+    # number of boxes of my mask rides along with the offsets (one readback for both)
+    compact = actx.empty(max(nb, 1), np.int32)
+    nmasked_dev = actx.empty(1, np.int32)
+    check(lib.bt_dist_compact_index(nb, dptr(my_mask), dptr(compact), dptr(nmasked_dev), sh),
+          "bt_dist_compact_index")
+    dest_offsets[nranks + 1:].copy_(nmasked_dev)
+    gathered = comm.allgather_tensor(dest_offsets).cpu().numpy()         # [sender, dest + 2]
+    counts, nmasked = np.diff(gathered[:, :nranks + 1], axis=1), int(gathered[rank, nranks + 1])
+    send_counts = counts[rank]
+    recv_counts = counts[:, rank]
+    nsend = int(send_counts.sum())
+    sendbuf = actx.empty(max(nsend, 1) * recbytes, np.uint8)
+    check(lib.bt_dist_pack_records(dcode, nranks, dims, n, dptr(pbox), dptr(dest_bits),
+                                   dptr(tile_offs), _cabi.ptr_array(parts), dptr(radii),
+                                   dptr(lstart), dptr(sendbuf), sh), "bt_dist_pack_records")
 
     # }}}
 
-    send_splits = [int(c) * recbytes for c in counts[rank]]
-    recv_counts = counts[:, rank]
-    recv_splits = [int(c) * recbytes for c in recv_counts]
     nrecv = int(recv_counts.sum())
-    recvbuf = comm.all_to_all_bytes(sendbuf[:need * recbytes], send_splits, recv_splits)
+    recvbuf = comm.all_to_all_bytes(sendbuf[:nsend * recbytes],
+                                    [int(c) * recbytes for c in send_counts],
+                                    [int(c) * recbytes for c in recv_counts])
 
     # {{{ unpack into the rank's local arrays (global tree order restricted to its boxes)
 
     lstarts, lnonchild, lcumul = ranges if ranges is not None else \
         _local_ranges(actx, lib, nb, my_mask, gown, pre)
+    count_tmp = actx.empty(max(nranks * nmasked, 1), np.int32)
     coord_dtype = dtree.coord_dtype
     local = [actx.empty(nrecv, coord_dtype) for _ in range(dims)]
     local_radii = actx.empty(nrecv, coord_dtype) if have_radii else None
     idx = actx.empty(nrecv, np.int64)
-    check(lib.bt_dist_unpack_records(dcode, dims, nrecv, int(have_radii), dptr(recvbuf),
-                                     dptr(lstarts), dptr(gstart), _cabi.ptr_array(local),
-                                     dptr(local_radii), dptr(idx), sh), "bt_dist_unpack_records")
+    chunk = (C.c_int64 * (nranks + 1))(*np.concatenate([[0], np.cumsum(recv_counts)]).tolist())
+    check(lib.bt_dist_unpack_records(dcode, nranks, dims, nrecv, int(have_radii), dptr(recvbuf),
+                                     chunk, dptr(compact), nmasked, dptr(count_tmp), dptr(lstarts),
+                                     dptr(gstart), _cabi.ptr_array(local), dptr(local_radii),
+                                     dptr(idx), sh), "bt_dist_unpack_records")
 
     # }}}
 

@@ -55,20 +55,22 @@ def _local_particles_and_lists(actx, lib, dimensions, nboxes, nparticles, coord_
     return make_obj_array(local), local_radii, lstarts, lnonchild, lcumul, idx
 
 
-def box_to_user_rank(actx, multipole_masks_all_ranks):
+def box_to_user_rank(actx, multipole_masks_all_ranks, bitsel=0xff):
     """MaskCompressorKernel on the gathered masks (``local_tree.py:376-406``,
-    ``tools.py:647-740``): CSR box -> ranks that use the box's multipole expansion."""
+    ``tools.py:647-740``): CSR box -> ranks that use the box's multipole expansion.  The mask
+    entries are tested with ``& bitsel``."""
     lib = _cabi.load()
     masks = multipole_masks_all_ranks.contiguous()
     nranks, nboxes = int(masks.shape[0]), int(masks.shape[1])
     sh = actx.stream_handle
     starts = actx.empty(nboxes + 1, np.int32)
     total = actx.zeros(1, np.int64)
-    check(lib.bt_dist_box_to_user_rank(0, nboxes, nranks, dptr(masks), dptr(starts), None,
-                                       dptr(total), sh), "bt_dist_box_to_user_rank")
+    check(lib.bt_dist_box_to_user_rank_bits(0, nboxes, nranks, bitsel, dptr(masks), dptr(starts),
+                                            None, dptr(total), sh), "bt_dist_box_to_user_rank")
     lists = actx.empty(int(total.item()), np.int32)
-    check(lib.bt_dist_box_to_user_rank(1, nboxes, nranks, dptr(masks), dptr(starts), dptr(lists),
-                                       dptr(total), sh), "bt_dist_box_to_user_rank")
+    check(lib.bt_dist_box_to_user_rank_bits(1, nboxes, nranks, bitsel, dptr(masks), dptr(starts),
+                                            dptr(lists), dptr(total), sh),
+          "bt_dist_box_to_user_rank")
     return starts, lists
 
 
@@ -104,13 +106,13 @@ def generate_local_tree(actx, global_traversal, responsible_boxes_list, comm,
 
 
 def assemble_local_tree(actx, gt, src, tgt, masks, multipole_masks_all_ranks,
-                        responsible_boxes_list):
+                        responsible_boxes_list, bitsel=0xff):
     """The :class:`LocalTree` record of ``local_tree.py:430-495`` from the rank's local
     particles *src* / *tgt* (tuples as returned by ``_local_particles_and_lists``), its box
     masks and every rank's multipole mask."""
     lib = _cabi.load()
     nb = int(gt.nboxes)
-    b2u_starts, b2u_lists = box_to_user_rank(actx, _dev(actx, multipole_masks_all_ranks))
+    b2u_starts, b2u_lists = box_to_user_rank(actx, _dev(actx, multipole_masks_all_ranks), bitsel)
     local_flags = _dev(actx, gt.box_flags).clone()
     check(lib.bt_dist_modify_target_flags(nb, dptr(tgt[3]), dptr(tgt[4]), dptr(local_flags),
                                           actx.stream_handle), "bt_dist_modify_target_flags")

@@ -36,17 +36,15 @@ class DistributedTree(Tree):
     ``targets``, the radii, ``user_source_ids`` and ``sorted_target_ids`` cover only the
     particles this rank contributed, in tree order; ``user_source_ids`` /
     ``sorted_target_ids`` index the rank's input arrays.  ``local_box_*`` give every box's
-    range in those local arrays; ``source_rank_offsets[b]`` is the number of own sources of box
-    *b* that lower ranks hold, so local source ``local_box_source_starts[b] + k`` of box *b*
-    sits at ``box_source_starts[b] + source_rank_offsets[b] + k`` of the global tree order."""
+    range in those local arrays.  Inside a box's own range the global tree order is rank-major
+    (global particle ids are), so local source ``local_box_source_starts[b] + k`` of box *b*
+    sits at ``box_source_starts[b] + (own sources of b on lower ranks) + k`` globally."""
     local_box_source_starts: Any = None
     local_box_source_counts_nonchild: Any = None
     local_box_source_counts_cumul: Any = None
     local_box_target_starts: Any = None
     local_box_target_counts_nonchild: Any = None
     local_box_target_counts_cumul: Any = None
-    source_rank_offsets: Any = None
-    target_rank_offsets: Any = None
     nsources_global: int = 0
     ntargets_global: int = 0
     rank: int = 0

@@ -658,13 +658,14 @@ class TreeBuilder:
             mark("tb:box info")
             # {{{ box particle extents (tree_build.py:1730-1802)
 
-            bb_src_min = actx.zeros((dimensions, aligned_nboxes), coord_dtype)
-            bb_src_max = actx.zeros((dimensions, aligned_nboxes), coord_dtype)
-            if sources_are_targets:
-                bb_tgt_min, bb_tgt_max = bb_src_min, bb_src_max
-            else:
-                bb_tgt_min = actx.zeros((dimensions, aligned_nboxes), coord_dtype)
-                bb_tgt_max = actx.zeros((dimensions, aligned_nboxes), coord_dtype)
+            # source and target boxes side by side: the distributed build all-reduces all minima
+            # (and all maxima) in one collective
+            nsets = 1 if sources_are_targets else 2
+            bb_min_all = actx.zeros((nsets, dimensions, aligned_nboxes), coord_dtype)
+            bb_max_all = actx.zeros((nsets, dimensions, aligned_nboxes), coord_dtype)
+            bb_src_min, bb_src_max = bb_min_all[0], bb_max_all[0]
+            bb_tgt_min, bb_tgt_max = (bb_src_min, bb_src_max) if sources_are_targets else \
+                (bb_min_all[1], bb_max_all[1])
 
             # own ranges of the boxes in the (rank's) tree-ordered particle arrays
             own_src = (local_ranges[0], local_ranges[1]) if dist else \
@@ -677,18 +678,18 @@ class TreeBuilder:
                 rounds.append((tgts, out_target_radii if targets_have_extent else None,
                                own_tgt[0], own_tgt[1], bb_tgt_min, bb_tgt_max))
             ls_host = (C.c_int32 * (nlevels + 1))(*[int(x) for x in level_start_box_nrs])
-            for parts, radii, pstarts, pcounts, bmin, bmax in rounds:
-                # distributed: min/max over the rank's own particles, all-reduced (exact), then
-                # the child merge on the global values
-                for phases in ((1, 2) if dist else (3,)):
+            # distributed: min/max over the rank's own particles, all-reduced (exact), then the
+            # child merge on the global values
+            for phases in ((1, 2) if dist else (3,)):
+                for parts, radii, pstarts, pcounts, bmin, bmax in rounds:
                     check(lib.bt_box_extents_phase(
                         dcode, dimensions, nfinal, aligned_nboxes, nlevels, ls_host,
                         dptr(box_child_ids), dptr(box_centers), dptr(pstarts), dptr(pcounts),
                         _cabi.ptr_array(list(parts)), dptr(radii), dptr(bmin), dptr(bmax), phases,
                         sh), "bt_box_extents")
-                    if dist and phases == 1:
-                        comm.allreduce_(bmin, "min")
-                        comm.allreduce_(bmax, "max")
+                if dist and phases == 1:
+                    comm.allreduce_(bb_min_all, "min")
+                    comm.allreduce_(bb_max_all, "max")
 
             # }}}
 
@@ -697,18 +698,6 @@ class TreeBuilder:
             evt.record(stream)
 
             mark("tb:extents")
-            rank_excl = None
-            if dist:
-                # own particles of lower ranks per box (exclusive scan over ranks): a particle's
-                # place in the global tree order is box start + rank_excl + index in the own range
-                own = torch.stack([own_src[1], own_tgt[1]])
-                allown = comm.allgather_tensor(own)                       # [size, 2, nboxes]
-                r = comm.Get_rank()
-                rank_excl = allown[:r].sum(dim=0, dtype=torch.int32) if r else torch.zeros_like(own)
-                del allown
-
-            mark("tb:rank offsets")
-
         self.last_stats = {"level_iterations": niterations, "nboxes_pre_prune": nboxes,
                            "reallocs": nreallocs}
 
@@ -724,7 +713,6 @@ class TreeBuilder:
                 local_box_target_starts=local_ranges[3],
                 local_box_target_counts_nonchild=local_ranges[4],
                 local_box_target_counts_cumul=local_ranges[5],
-                source_rank_offsets=rank_excl[0], target_rank_offsets=rank_excl[1],
                 nsources_global=nsources_global, ntargets_global=ntargets_global,
                 rank=comm.Get_rank(), nranks=comm.Get_size())
         tree = cls(

@@ -500,25 +500,40 @@ int bt_dist_box_to_user_rank(int phase, int nboxes, int nranks, const int8_t *ma
 /* ---- particle exchange of the distributed build: the all-to-all that replaces the root's
  * fetch_local_particles + scatter (local_tree.py:124-151, 408-495).  Every rank holds the
  * global box arrays and its own input particles in tree order.
- * bt_dist_mask_bits: masks [nranks, nboxes] -> one bit per rank and box.
- * bt_dist_pack_records: for destination rank d = 0..nranks-1 in turn, one record
+ * bt_dist_mask_bits: masks [nranks, nboxes] (entries tested with `& bitsel`) -> one bit per
+ *   rank and box.
+ * bt_dist_pack_count: box id of every local particle (particle_box [n], from the boxes' own
+ *   ranges local_start / local_own) and a multisplit count: tile_counts / tile_offsets
+ *   [nranks * bt_dist_pack_ntiles(n)] scratch, dest_offsets [nranks+1] (device) = first record
+ *   of every destination's chunk.
+ * bt_dist_pack_records: one record
  *   [coords (dim) | radius (if radii) | box id i32 | index in the box's own range i32]
- *   per own particle of every box that has bit d set (boxes in id order); dest_offsets
- *   [nranks+1] are the record offsets per destination (always complete; records beyond
- *   `capacity` are not written: enlarge and call again).  local_start / local_own: the box's
- *   own range in this rank's tree-ordered particles; rank_excl[b] = own particles of lower
- *   ranks in box b.
- * bt_dist_unpack_records: scatter received records to dst_start[box] + index; particle_idx
- *   gets the particle's position in the global tree order (box_global_start[box] + index).
+ *   per local particle and destination d whose bit is set in dest_bits[box], in tree order
+ *   inside the chunk of d.
+ * bt_dist_compact_index: compact[b] = number of boxes of the mask below b; *nmasked_dev = total.
+ * bt_dist_unpack_records: records of sender s occupy [chunk_offsets_host[s],
+ *   chunk_offsets_host[s+1]) of recvbuf (HOST [nranks+1]); a record of box b lands at
+ *   dst_start[b] + (records of b from lower senders) + index; particle_idx gets its position
+ *   in the global tree order (box_global_start[b] + the same offset).  count_tmp: device
+ *   scratch [nranks * nmasked].
  * bt_dist_local_ranges: per-box ranges of the local particle arrays (local_tree.py:249-284)
  *   from the masked own counts in box pre-order (own particles precede the children's). */
-int bt_dist_mask_bits(int nboxes, int nranks, const int8_t *masks_all_ranks, uint32_t *dest_bits,
-                      void *stream);
-int bt_dist_pack_records(int dtype, int nranks, int dim, int nboxes, const uint32_t *dest_bits,
+int bt_dist_mask_bits(int nboxes, int nranks, int bitsel, const int8_t *masks_all_ranks,
+                      uint32_t *dest_bits, void *stream);
+int bt_dist_pack_ntiles(int64_t n);
+int bt_dist_pack_count(int nranks, int nboxes, int64_t n, const uint32_t *dest_bits,
+                       const int32_t *local_start, const int32_t *local_own, int32_t *particle_box,
+                       int32_t *tile_counts, int64_t *tile_offsets, int64_t *dest_offsets,
+                       void *stream);
+int bt_dist_pack_records(int dtype, int nranks, int dim, int64_t n, const int32_t *particle_box,
+                         const uint32_t *dest_bits, const int64_t *tile_offsets,
                          void *const *particles, const void *radii, const int32_t *local_start,
-                         const int32_t *local_own, const int32_t *rank_excl, void *sendbuf,
-                         int64_t *dest_offsets, void *stream, int64_t capacity);
-int bt_dist_unpack_records(int dtype, int dim, int64_t nrec, int has_radii, const void *recvbuf,
+                         void *sendbuf, void *stream);
+int bt_dist_compact_index(int nboxes, const int8_t *box_mask, int32_t *compact,
+                          int32_t *nmasked_dev, void *stream);
+int bt_dist_unpack_records(int dtype, int nranks, int dim, int64_t nrec, int has_radii,
+                           const void *recvbuf, const int64_t *chunk_offsets_host,
+                           const int32_t *compact, int nmasked, int32_t *count_tmp,
                            const int32_t *dst_start, const int32_t *box_global_start,
                            void *const *local_particles, void *local_radii, int64_t *particle_idx,
                            void *stream);
@@ -526,6 +541,10 @@ int bt_dist_local_ranges(int nboxes, const int8_t *box_mask, const int32_t *own_
                          const int32_t *preorder_rank, const int32_t *preorder_boxes,
                          const int32_t *subtree_size, int32_t *prefix_tmp, int32_t *local_starts,
                          int32_t *local_nonchild, int32_t *local_cumul, void *stream);
+/* bt_dist_box_to_user_rank on masks whose entries are bit fields (tested with `& bitsel`) */
+int bt_dist_box_to_user_rank_bits(int phase, int nboxes, int nranks, int bitsel,
+                                  const int8_t *masks_all_ranks, int32_t *starts, int32_t *lists,
+                                  int64_t *total_dev, void *stream);
 
 #ifdef __cplusplus
 }
