@@ -47,16 +47,16 @@ constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
 // returned to the OS (and re-mapped) at every sync.
 static inline cudaError_t temp_alloc(void** p, size_t bytes, cudaStream_t s)
 {
-    static bool configured = false;
-    if (!configured) {
-        int dev = 0;
+    // per device; bounded (2 GiB) so that scratch does not starve torch's caching allocator
+    static unsigned long long configured_devices = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && !((configured_devices >> (dev & 63)) & 1ull)) {
         cudaMemPool_t pool;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            unsigned long long thr = ~0ull;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long thr = 2ull << 30;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
         }
-        configured = true;
+        configured_devices |= 1ull << (dev & 63);
     }
     return cudaMallocAsync(p, bytes ? bytes : 16, s);
 }

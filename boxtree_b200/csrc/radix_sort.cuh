@@ -291,15 +291,18 @@ static int radix_sort_pairs(int64_t n, unsigned long long* keys, unsigned long l
     BT_LAUNCH_CHECK();
     }
 
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the attribute is per device
+    static unsigned long long attr_set_devices = 0;
+    int dev = 0;
+    BT_CHECK(cudaGetDevice(&dev));
+    if (!((attr_set_devices >> (dev & 63)) & 1ull)) {
         BT_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<true>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
         BT_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<false>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
         BT_CHECK(cudaFuncSetAttribute((rs_onesweep_kernel<false, true>),
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
-        attr_set = true;
+        attr_set_devices |= 1ull << (dev & 63);
     }
 
     unsigned long long* kin = keys; unsigned long long* kout = keys_alt;

@@ -137,8 +137,12 @@ template <typename T> struct BBox { T mn[3]; T mx[3]; };
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256)
 make_keys_kernel(Particles<T, DIM> P, BBox<T> bb, int extent_norm, T stick_out_factor, int D,
-                 int points_never_stop, unsigned long long* __restrict__ keys)
+                 int points_never_stop, unsigned long long* __restrict__ keys, T* __restrict__ records)
 {
+    // records (optional): the particle's coordinates and radius side by side (4 values), so
+    // that the later gather into tree order (bt_permute) reads ONE aligned 16/32-byte record per
+    // particle instead of one 32-byte sector per coordinate
+    constexpr int RW = 4;
     const int stride = gridDim.x * blockDim.x;
     const T one_half = ((T)1) / 2;
     const T box_radius_factor = (T)((1. + (double)(extent_norm ? stick_out_factor : (T)0)) * (double)one_half);
@@ -158,7 +162,21 @@ make_keys_kernel(Particles<T, DIM> P, BBox<T> bb, int extent_norm, T stick_out_f
             q[a] = (unsigned long long)(((pos[a] - gmin[a]) / gext[a]) * scaleD);
         }
         unsigned stop = kStopNever;
-        const T radius = extent_norm ? P.radius(i) : (T)0;
+        const T radius = (extent_norm || records) ? P.radius(i) : (T)0;
+        if (records) {
+            T rec[RW] = {0, 0, 0, 0};
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) rec[a] = pos[a];
+            rec[3] = radius;
+            if (sizeof(T) == 8) {
+                double2* dst = reinterpret_cast<double2*>(records + (size_t)i * RW);
+                dst[0] = make_double2((double)rec[0], (double)rec[1]);
+                dst[1] = make_double2((double)rec[2], (double)rec[3]);
+            } else {
+                *reinterpret_cast<float4*>(records + (size_t)i * RW) =
+                    make_float4((float)rec[0], (float)rec[1], (float)rec[2], (float)rec[3]);
+            }
+        }
         // A particle without extent lies inside its box at every level; with a stick-out factor
         // that dwarfs the rounding errors of the tests below (make_keys_impl decides) none of them
         // can fire for it, so the level loop is skipped with the identical result.
@@ -667,16 +685,31 @@ __global__ void reverse_index_kernel(const unsigned* __restrict__ ids, int n, in
 // a12: permute -- boxtree/tree_build_kernels.py:1170-1186 and cl_array.take
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256)
-permute_kernel(Particles<T, DIM> P, const int* __restrict__ from_ids, int n, int want_radii,
-               T* o0, T* o1, T* o2, T* out_radii)
+permute_kernel(Particles<T, DIM> P, const T* __restrict__ records, const int* __restrict__ from_ids, int n,
+               int want_radii, T* o0, T* o1, T* o2, T* out_radii)
 {
     T* outs[3] = {o0, o1, o2};
     const int stride = gridDim.x * blockDim.x;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const int f = from_ids[i];
+        if (records) {      // one aligned record per particle (make_keys_kernel)
+            T rec[4];
+            if (sizeof(T) == 8) {
+                const double2* src = reinterpret_cast<const double2*>(records + (size_t)f * 4);
+                const double2 a = src[0], b = src[1];
+                rec[0] = (T)a.x; rec[1] = (T)a.y; rec[2] = (T)b.x; rec[3] = (T)b.y;
+            } else {
+                const float4 a = *reinterpret_cast<const float4*>(records + (size_t)f * 4);
+                rec[0] = (T)a.x; rec[1] = (T)a.y; rec[2] = (T)a.z; rec[3] = (T)a.w;
+            }
 #pragma unroll
-        for (int a = 0; a < DIM; ++a) outs[a][i] = P.coord(a, f);
-        if (want_radii) out_radii[i] = P.radius(f);
+            for (int a = 0; a < DIM; ++a) outs[a][i] = rec[a];
+            if (want_radii) out_radii[i] = rec[3];
+        } else {
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) outs[a][i] = P.coord(a, f);
+            if (want_radii) out_radii[i] = P.radius(f);
+        }
     }
 }
 
@@ -1044,7 +1077,7 @@ static int bbox_impl(const bt_particles* p, void* out, cudaStream_t s)
 template <typename T, int DIM>
 static int make_keys_impl(const bt_particles* p, const double* bmin, const double* bmax,
                           int extent_norm, double stick_out, int D, unsigned long long* keys,
-                          cudaStream_t s)
+                          void* records, cudaStream_t s)
 {
     Particles<T, DIM> P = make_particles<T, DIM>(p);
     BBox<T> bb;
@@ -1069,7 +1102,7 @@ static int make_keys_impl(const bt_particles* p, const double* bmin, const doubl
         points_never_stop = (min_ext > 0 && margin > 64.0 * eps * M) ? 1 : 0;
     }
     make_keys_kernel<T, DIM><<<grid_for(P.n, 256, 8), 256, 0, s>>>(P, bb, extent_norm, (T)stick_out, D,
-                                                                  points_never_stop, keys);
+                                                                  points_never_stop, keys, (T*)records);
     BT_LAUNCH_CHECK();
     return BT_OK;
 }
@@ -1178,13 +1211,13 @@ static int finalize_boxes_impl(const bt_pool* pool, int nboxes, int level_restri
 }
 
 template <typename T, int DIM>
-static int permute_impl(const bt_particles* p, const int* from_ids, int n, void* const* outs,
-                        void* out_radii, cudaStream_t s)
+static int permute_impl(const bt_particles* p, const void* records, const int* from_ids, int n,
+                        void* const* outs, void* out_radii, cudaStream_t s)
 {
     if (n == 0) return BT_OK;
     Particles<T, DIM> P = make_particles<T, DIM>(p);
     permute_kernel<T, DIM><<<grid_for(n, 256, 8), 256, 0, s>>>(
-        P, from_ids, n, out_radii ? 1 : 0, (T*)outs[0], DIM > 1 ? (T*)outs[1] : nullptr,
+        P, (const T*)records, from_ids, n, out_radii ? 1 : 0, (T*)outs[0], DIM > 1 ? (T*)outs[1] : nullptr,
         DIM > 2 ? (T*)outs[2] : nullptr, (T*)out_radii);
     BT_LAUNCH_CHECK();
     return BT_OK;
@@ -1286,19 +1319,26 @@ int bt_bounding_box(int dtype, int dim, const bt_particles* p, void* out_minmax,
 {
     BT_PROF("bt_bounding_box", (cudaStream_t)stream); BT_DISPATCH(dtype, dim, bbox_impl, p, out_minmax, (cudaStream_t)stream); }
 
+static int key_depth(int dim, int depth)
+{   // levels resolved by the sort key: all the 64-bit key holds unless the caller asks for fewer
+    const int dmax = bt_max_key_level(dim);
+    return (depth > 0 && depth < dmax) ? depth : dmax;
+}
+
 int bt_make_keys(int dtype, int dim, const bt_particles* p, const double* bbox_min, const double* bbox_max,
-                 int extent_norm, double stick_out_factor, uint64_t* keys, void* stream)
+                 int extent_norm, double stick_out_factor, int depth, uint64_t* keys, void* records,
+                 void* stream)
 {
     BT_PROF("bt_make_keys", (cudaStream_t)stream);
     BT_DISPATCH(dtype, dim, make_keys_impl, p, bbox_min, bbox_max, extent_norm, stick_out_factor,
-                bt_max_key_level(dim), (unsigned long long*)keys, (cudaStream_t)stream);
+                key_depth(dim, depth), (unsigned long long*)keys, records, (cudaStream_t)stream);
 }
 
-int bt_sort_particles(int64_t n, int dim, int have_extent, uint64_t* keys, uint64_t* keys_alt,
+int bt_sort_particles(int64_t n, int dim, int have_extent, int depth, uint64_t* keys, uint64_t* keys_alt,
                       uint32_t* ids, uint32_t* ids_alt, int* result_in_alt, void* stream)
 {
     BT_PROF("bt_sort_particles", (cudaStream_t)stream);
-    const int D = bt_max_key_level(dim);
+    const int D = key_depth(dim, depth);
     const int begin_bit = have_extent ? 0 : bt::kStopBits;
     const int end_bit = bt::kStopBits + D * dim;
     return bt::radix_sort_pairs(n, (unsigned long long*)keys, (unsigned long long*)keys_alt, ids, ids_alt,
@@ -1325,12 +1365,12 @@ int bt_pool_init(int dtype, int dim, const bt_pool* pool, int64_t n, int have_ex
 int bt_level_step(int dtype, int dim, const bt_pool* pool, const uint64_t* keys, const int64_t* wprefix,
                   int32_t* ctl, int32_t* split_list, uint8_t* flag, int lo, int nboxes, int level,
                   int maxw, int adaptive, int level_restrict, int have_extent, int skip_if_no_regular,
-                  double root_extent, int phases, void* stream)
+                  double root_extent, int phases, int depth, void* stream)
 {
     BT_PROF("bt_level_step", (cudaStream_t)stream);
     BT_DISPATCH(dtype, dim, level_step_impl, pool, (const unsigned long long*)keys,
                 (const long long*)wprefix, ctl, split_list, flag, lo, nboxes, level,
-                bt_max_key_level(dim), maxw, adaptive, level_restrict, have_extent, skip_if_no_regular,
+                key_depth(dim, depth), maxw, adaptive, level_restrict, have_extent, skip_if_no_regular,
                 root_extent, phases, (cudaStream_t)stream);
 }
 
@@ -1417,10 +1457,12 @@ int bt_reverse_index(int64_t n, const uint32_t* ids, int32_t* out, void* stream)
     return BT_OK;
 }
 
-int bt_permute(int dtype, int dim, const bt_particles* p, const int32_t* from_ids, int64_t n,
-               void* const* outs, void* out_radii, void* stream)
+int bt_permute(int dtype, int dim, const bt_particles* p, const void* records, const int32_t* from_ids,
+               int64_t n, void* const* outs, void* out_radii, void* stream)
 {
-    BT_PROF("bt_permute", (cudaStream_t)stream); BT_DISPATCH(dtype, dim, permute_impl, p, from_ids, (int)n, outs, out_radii, (cudaStream_t)stream); }
+    BT_PROF("bt_permute", (cudaStream_t)stream);
+    BT_DISPATCH(dtype, dim, permute_impl, p, records, from_ids, (int)n, outs, out_radii, (cudaStream_t)stream);
+}
 
 int bt_box_info(int nboxes, int sources_are_targets, int have_extent, const int32_t* box_start,
                 const int32_t* box_count, const int32_t* box_nonchild, const uint8_t* has_children,

@@ -350,140 +350,163 @@ class TreeBuilder:
             # }}}
 
             mark("tb:bbox")
-            # {{{ keys + sort
+            # The sort key resolves `key_depth` levels.  The fewer, the fewer radix passes: a depth
+            # estimated from the particle count is tried first, the full depth of the 64-bit key if
+            # the tree turns out deeper (bt_make_keys; the result is identical either way).
+            max_key_level = int(lib.bt_max_key_level(dimensions))
+            est = 1
+            while (nb ** est) * max_leaf_refine_weight < max(total_refine_weight, 1):
+                est += 1
+            first_depth = int(kwargs.get("_key_depth", 0)) or min(max_key_level, est + 6)
+            # x, y, z, radius of every particle side by side for the gather into tree order
+            records = actx.empty(4 * max(nsrcntgts, 1), coord_dtype)
+            for key_depth in ([first_depth, max_key_level] if first_depth < max_key_level
+                              else [max_key_level]):
+                too_deep = False
+                # {{{ keys + sort
 
-            key_bufs = [actx.empty(nsrcntgts, np.int64), actx.empty(nsrcntgts, np.int64)]
-            id_bufs = [actx.empty(nsrcntgts, np.int32), actx.empty(nsrcntgts, np.int32)]
-            check(lib.bt_make_keys(dcode, dimensions, C.byref(P), _cabi.darray(bbox_min),
-                                   _cabi.darray(bbox_max), EXTENT_NORM_CODE[srcntgts_extent_norm],
-                                   float(stick_out_factor), dptr(key_bufs[0]), sh), "bt_make_keys")
-            in_alt = C.c_int(0)
-            if nsrcntgts:
-                check(lib.bt_sort_particles(nsrcntgts, dimensions, have_ext, dptr(key_bufs[0]),
-                                            dptr(key_bufs[1]), dptr(id_bufs[0]), dptr(id_bufs[1]),
-                                            C.byref(in_alt), sh), "bt_sort_particles")
-            keys = key_bufs[in_alt.value]
-            ids = id_bufs[in_alt.value]
-            del key_bufs, id_bufs
+                key_bufs = [actx.empty(nsrcntgts, np.int64), actx.empty(nsrcntgts, np.int64)]
+                id_bufs = [actx.empty(nsrcntgts, np.int32), actx.empty(nsrcntgts, np.int32)]
+                check(lib.bt_make_keys(dcode, dimensions, C.byref(P), _cabi.darray(bbox_min),
+                                       _cabi.darray(bbox_max), EXTENT_NORM_CODE[srcntgts_extent_norm],
+                                       float(stick_out_factor), key_depth, dptr(key_bufs[0]),
+                                       dptr(records), sh), "bt_make_keys")
+                in_alt = C.c_int(0)
+                if nsrcntgts:
+                    check(lib.bt_sort_particles(nsrcntgts, dimensions, have_ext, key_depth,
+                                                dptr(key_bufs[0]),
+                                                dptr(key_bufs[1]), dptr(id_bufs[0]), dptr(id_bufs[1]),
+                                                C.byref(in_alt), sh), "bt_sort_particles")
+                keys = key_bufs[in_alt.value]
+                ids = id_bufs[in_alt.value]
+                del key_bufs, id_bufs
 
-            wprefix = None
-            if refine_weights is not None:
-                wprefix = actx.empty(nsrcntgts + 1, np.int64)
-                check(lib.bt_weight_prefix(nsrcntgts, dptr(ids), dptr(refine_weights),
-                                           dptr(wprefix), sh), "bt_weight_prefix")
+                wprefix = None
+                if refine_weights is not None:
+                    wprefix = actx.empty(nsrcntgts + 1, np.int64)
+                    check(lib.bt_weight_prefix(nsrcntgts, dptr(ids), dptr(refine_weights),
+                                               dptr(wprefix), sh), "bt_weight_prefix")
 
-            # }}}
+                # }}}
 
-            mark("tb:keys+sort")
-            # {{{ level loop (tree_build.py:653-1276)
+                mark("tb:keys+sort")
+                # {{{ level loop (tree_build.py:653-1276)
 
-            nboxes_guess = kwargs.get("nboxes_guess")
-            if nboxes_guess is None:
-                nboxes_guess = int(nb * ((max_leaf_refine_weight + total_refine_weight - 1)
-                                         // max_leaf_refine_weight)) + 1
-            assert nboxes_guess > 0
-            pool = _Pool(actx, dimensions, coord_tdtype, max(int(nboxes_guess), 2), dist)
-            ctl = actx.zeros(CTL_SIZE, np.int32)
-            ctl_host = torch.empty(CTL_SIZE, dtype=torch.int32, pin_memory=True)
-            check(lib.bt_pool_init(dcode, dimensions, C.byref(pool.struct()), nsrcntgts, have_ext,
-                                   dptr(keys), _cabi.darray(root_center), dptr(ctl), sh),
-                  "bt_pool_init")
-            if dist:        # the root holds every rank's particles
-                g = torch.stack([pool.arrays["count"][0], pool.arrays["nonchild"][0]])
-                comm.allreduce_(g, "sum")
-                pool.arrays["gcount"][0:1].copy_(g[0:1])
-                pool.arrays["gnonchild"][0:1].copy_(g[1:2])
+                nboxes_guess = kwargs.get("nboxes_guess")
+                if nboxes_guess is None:
+                    nboxes_guess = int(nb * ((max_leaf_refine_weight + total_refine_weight - 1)
+                                             // max_leaf_refine_weight)) + 1
+                assert nboxes_guess > 0
+                pool = _Pool(actx, dimensions, coord_tdtype, max(int(nboxes_guess), 2), dist)
+                ctl = actx.zeros(CTL_SIZE, np.int32)
+                ctl_host = torch.empty(CTL_SIZE, dtype=torch.int32, pin_memory=True)
+                check(lib.bt_pool_init(dcode, dimensions, C.byref(pool.struct()), nsrcntgts, have_ext,
+                                       dptr(keys), _cabi.darray(root_center), dptr(ctl), sh),
+                      "bt_pool_init")
+                if dist:        # the root holds every rank's particles
+                    g = torch.stack([pool.arrays["count"][0], pool.arrays["nonchild"][0]])
+                    comm.allreduce_(g, "sum")
+                    pool.arrays["gcount"][0:1].copy_(g[0:1])
+                    pool.arrays["gnonchild"][0:1].copy_(g[1:2])
 
-            nlevels_max = 2 * (np.finfo(coord_dtype).nmant + 1)
-            max_key_level = lib.bt_max_key_level(dimensions)
-            level = 1 if total_refine_weight > max_leaf_refine_weight else 0
-            nboxes = 1
-            level_block_start = 0            # first pool id of the boxes on level-1
-            final_level_restrict_iteration = False
-            nreallocs = 0
-            niterations = 0
+                nlevels_max = 2 * (np.finfo(coord_dtype).nmant + 1)
+                level = 1 if total_refine_weight > max_leaf_refine_weight else 0
+                nboxes = 1
+                level_block_start = 0            # first pool id of the boxes on level-1
+                final_level_restrict_iteration = False
+                nreallocs = 0
+                niterations = 0
 
-            def read_ctl():
-                ctl_host.copy_(ctl, non_blocking=True)
-                stream.synchronize()
-                return ctl_host.numpy()
+                def read_ctl():
+                    ctl_host.copy_(ctl, non_blocking=True)
+                    stream.synchronize()
+                    return ctl_host.numpy()
 
-            while level:
-                niterations += 1
-                if level + 1 >= nlevels_max or level > max_key_level:
-                    raise MaxLevelsExceeded(
-                        "Level count exceeded number of significant "
-                        "bits in coordinate dtype. That means that a large number "
-                        "of particles was indistinguishable up to floating point "
-                        "precision (because they ended up in the same box).")
+                while level:
+                    niterations += 1
+                    if level > key_depth and key_depth < max_key_level \
+                            and level + 1 < nlevels_max:
+                        too_deep = True         # deeper than the key resolves: sort again
+                        break
+                    if level + 1 >= nlevels_max or level > max_key_level:
+                        raise MaxLevelsExceeded(
+                            "Level count exceeded number of significant "
+                            "bits in coordinate dtype. That means that a large number "
+                            "of particles was indistinguishable up to floating point "
+                            "precision (because they ended up in the same box).")
 
-                lo = 0 if level_restrict else level_block_start
-                ncand = nboxes - lo
-                if adaptive and not level_restrict:
-                    bound = min(ncand, total_refine_weight // (max_leaf_refine_weight + 1) + 1)
-                else:
-                    bound = min(ncand, nboxes - level_block_start
-                                + (int(kwargs.get("_lr_slack", 1024)) if level_restrict else 0))
-                pool.ensure(nboxes + nb * bound)
+                    lo = 0 if level_restrict else level_block_start
+                    ncand = nboxes - lo
+                    if adaptive and not level_restrict:
+                        bound = min(ncand, total_refine_weight // (max_leaf_refine_weight + 1) + 1)
+                    else:
+                        bound = min(ncand, nboxes - level_block_start
+                                    + (int(kwargs.get("_lr_slack", 1024)) if level_restrict else 0))
+                    pool.ensure(nboxes + nb * bound)
 
-                skip_if_no_regular = int(bool(srcntgts_have_extent)
-                                         and not final_level_restrict_iteration)
+                    skip_if_no_regular = int(bool(srcntgts_have_extent)
+                                             and not final_level_restrict_iteration)
 
-                def run_step(phases):
-                    check(lib.bt_level_step(
-                        dcode, dimensions, C.byref(pool.struct()), dptr(keys), dptr(wprefix),
-                        dptr(ctl), dptr(pool.split_list), dptr(pool.flag), lo, nboxes, level,
-                        max_leaf_refine_weight, int(adaptive), int(level_restrict), have_ext,
-                        skip_if_no_regular, float(root_extent), phases, sh), "bt_level_step")
-                    if phases & STEP_COMMIT and level_restrict \
-                            and not final_level_restrict_iteration:
-                        check(lib.bt_level_restrict(dcode, dimensions, C.byref(pool.struct()),
-                                                    dptr(ctl), level, pool.capacity,
-                                                    float(root_extent), sh), "bt_level_restrict")
+                    def run_step(phases):
+                        check(lib.bt_level_step(
+                            dcode, dimensions, C.byref(pool.struct()), dptr(keys), dptr(wprefix),
+                            dptr(ctl), dptr(pool.split_list), dptr(pool.flag), lo, nboxes, level,
+                            max_leaf_refine_weight, int(adaptive), int(level_restrict), have_ext,
+                            skip_if_no_regular, float(root_extent), phases, key_depth, sh),
+                              "bt_level_step")
+                        if phases & STEP_COMMIT and level_restrict \
+                                and not final_level_restrict_iteration:
+                            check(lib.bt_level_restrict(dcode, dimensions, C.byref(pool.struct()),
+                                                        dptr(ctl), level, pool.capacity,
+                                                        float(root_extent), sh), "bt_level_restrict")
 
-                # one GPU: decide + children + commit in one go; distributed: the children's
-                # local (lower bound, count, nonchild) are summed over the ranks before the commit
-                first = STEP_DECIDE | STEP_CREATE if dist else STEP_ALL
-                run_step(first)
-                h = read_ctl()
-                while h[CTL_OVERFLOW]:
-                    nreallocs += 1
-                    pool.ensure(nboxes + nb * int(h[CTL_NSPLIT]))
-                    run_step(first & ~STEP_DECIDE)
+                    # one GPU: decide + children + commit in one go; distributed: the children's
+                    # local (lower bound, count, nonchild) are summed over the ranks before the commit
+                    first = STEP_DECIDE | STEP_CREATE if dist else STEP_ALL
+                    run_step(first)
                     h = read_ctl()
-                if dist:
-                    if h[CTL_NSPLIT] and not (skip_if_no_regular and not h[CTL_NSPLIT_REGULAR]):
-                        comm.allreduce_(pool.xch[:3 * nb * int(h[CTL_NSPLIT])], "sum")
-                    run_step(STEP_COMMIT)
-                    h = read_ctl()
+                    while h[CTL_OVERFLOW]:
+                        nreallocs += 1
+                        pool.ensure(nboxes + nb * int(h[CTL_NSPLIT]))
+                        run_step(first & ~STEP_DECIDE)
+                        h = read_ctl()
+                    if dist:
+                        if h[CTL_NSPLIT] and not (skip_if_no_regular and not h[CTL_NSPLIT_REGULAR]):
+                            comm.allreduce_(pool.xch[:3 * nb * int(h[CTL_NSPLIT])], "sum")
+                        run_step(STEP_COMMIT)
+                        h = read_ctl()
 
-                nsplit_regular = int(h[CTL_NSPLIT_REGULAR])
-                have_oversize_split_box = int(h[CTL_OVERSIZE])
+                    nsplit_regular = int(h[CTL_NSPLIT_REGULAR])
+                    have_oversize_split_box = int(h[CTL_OVERSIZE])
 
-                if nsplit_regular == 0:
-                    # no new boxes on the new level (tree_build.py:1016-1025)
-                    if srcntgts_have_extent and not final_level_restrict_iteration:
+                    if nsplit_regular == 0:
+                        # no new boxes on the new level (tree_build.py:1016-1025)
+                        if srcntgts_have_extent and not final_level_restrict_iteration:
+                            level -= 1
+                            break
+                        assert final_level_restrict_iteration
+
+                    level_block_start = nboxes
+                    nboxes = int(h[CTL_NBOXES])
+
+                    if final_level_restrict_iteration:
                         level -= 1
                         break
-                    assert final_level_restrict_iteration
 
-                level_block_start = nboxes
-                nboxes = int(h[CTL_NBOXES])
+                    if level_restrict:
+                        did_upper_level_split = bool(level - 2 >= 1 and h[CTL_LR_FOUND + level - 2])
+                        if have_oversize_split_box == 0 and did_upper_level_split:
+                            final_level_restrict_iteration = True
+                            level += 1
+                            continue
 
-                if final_level_restrict_iteration:
-                    level -= 1
+                    if not have_oversize_split_box:
+                        break
+                    level += 1
+
+                if not too_deep:
                     break
-
-                if level_restrict:
-                    did_upper_level_split = bool(level - 2 >= 1 and h[CTL_LR_FOUND + level - 2])
-                    if have_oversize_split_box == 0 and did_upper_level_split:
-                        final_level_restrict_iteration = True
-                        level += 1
-                        continue
-
-                if not have_oversize_split_box:
-                    break
-                level += 1
+                del keys, ids, pool
 
             nlevels = level + 1
 
@@ -588,7 +611,7 @@ class TreeBuilder:
             def permute(from_ids, n, want_radii):
                 outs = [actx.empty(n, coord_dtype) for _ in range(dimensions)]
                 radii = actx.empty(n, coord_dtype) if want_radii else None
-                check(lib.bt_permute(dcode, dimensions, C.byref(P), dptr(from_ids), n,
+                check(lib.bt_permute(dcode, dimensions, C.byref(P), dptr(records), dptr(from_ids), n,
                                      _cabi.ptr_array(outs), dptr(radii), sh), "bt_permute")
                 return make_obj_array(outs), radii
 
@@ -699,7 +722,7 @@ class TreeBuilder:
 
             mark("tb:extents")
         self.last_stats = {"level_iterations": niterations, "nboxes_pre_prune": nboxes,
-                           "reallocs": nreallocs}
+                           "reallocs": nreallocs, "key_depth": key_depth}
 
         extra = {}
         cls = Tree

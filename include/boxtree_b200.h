@@ -116,17 +116,21 @@ int bt_max_key_level(int dim);
 int bt_bounding_box(int dtype, int dim, const bt_particles *p, void *out_minmax, void *stream);
 
 /* Digit computation of morton_scan (tree_build_kernels.py:308-470) for all levels
- * at once.  bbox_min/bbox_max are HOST arrays [dim].  extent_norm: 0 none, 1 linf, 2 l2. */
+ * at once.  bbox_min/bbox_max are HOST arrays [dim].  extent_norm: 0 none, 1 linf, 2 l2.
+ * depth: levels the key resolves (0 or >= bt_max_key_level(dim): all it can hold); a tree that
+ * turns out deeper must be rebuilt with a larger depth.  records (optional, [n][4] coords):
+ * x, y, z, radius of every particle side by side for bt_permute. */
 int bt_make_keys(int dtype, int dim, const bt_particles *p, const double *bbox_min,
-                 const double *bbox_max, int extent_norm, double stick_out_factor, uint64_t *keys,
-                 void *stream);
+                 const double *bbox_max, int extent_norm, double stick_out_factor, int depth,
+                 uint64_t *keys, void *records, void *stream);
 
 /* Stable radix sort of (key, particle id); replaces the per-level partition
  * morton_scan + renumber_particles (tree_build_kernels.py:247-508, 717-819).
  * ids are generated (identity) by the first pass.  *result_in_alt (HOST) tells
  * which buffer pair holds the result. */
-int bt_sort_particles(int64_t n, int dim, int have_extent, uint64_t *keys, uint64_t *keys_alt,
-                      uint32_t *ids, uint32_t *ids_alt, int *result_in_alt, void *stream);
+int bt_sort_particles(int64_t n, int dim, int have_extent, int depth, uint64_t *keys,
+                      uint64_t *keys_alt, uint32_t *ids, uint32_t *ids_alt, int *result_in_alt,
+                      void *stream);
 
 /* refine weights in sorted order -> exclusive int64 prefix, wprefix[n] = total
  * (the pwt fields of the morton_scan struct, tree_build_kernels.py:462-466) */
@@ -151,7 +155,7 @@ int bt_level_step(int dtype, int dim, const bt_pool *pool, const uint64_t *keys,
                   const int64_t *wprefix, int32_t *ctl, int32_t *split_list, uint8_t *flag, int lo,
                   int nboxes, int level, int maxw, int adaptive, int level_restrict,
                   int have_extent, int skip_if_no_regular, double root_extent, int phases,
-                  void *stream);
+                  int depth, void *stream);
 
 /* level_restrict kernel + upper-level sweep (tree_build_kernels.py:825-915,
  * tree_build.py:1145-1200); the sweep's early exit is a device-side flag chain. */
@@ -183,9 +187,10 @@ int bt_split_sources_targets(int64_t n, int64_t nsources, const uint32_t *sorted
 int bt_reverse_index(int64_t n, const uint32_t *ids, int32_t *out, void *stream);
 
 /* srcntgt_permuter + cl_array.take (tree_build_kernels.py:1170-1186, tree_build.py:1609-1616).
- * outs: HOST array of dim device pointers */
-int bt_permute(int dtype, int dim, const bt_particles *p, const int32_t *from_ids, int64_t n,
-               void *const *outs, void *out_radii, void *stream);
+ * outs: HOST array of dim device pointers; records: the array bt_make_keys wrote, or NULL
+ * (then the coordinates are gathered from *p) */
+int bt_permute(int dtype, int dim, const bt_particles *p, const void *records,
+               const int32_t *from_ids, int64_t n, void *const *outs, void *out_radii, void *stream);
 
 /* find_source_and_target_indices box part + box_info (tree_build_kernels.py:1062-1147, 1192-1305) */
 int bt_box_info(int nboxes, int sources_are_targets, int have_extent, const int32_t *box_start,
