@@ -56,6 +56,10 @@ WORKLOADS = {
     "config4": ("plummer", 100_000_000, "f32", "3D 1e8 Plummer fp32, adaptive, max 30"),
     "uniform1e7": ("uniform", 10_000_000, "f64",
                    "3D 1e7 uniform fp64, sources are targets, adaptive, max 30"),
+    # per GPU; with --gpus 8 the global problem is BASELINE config 5 (5e8 uniform points)
+    "config5": ("uniform", 62_500_000, "f64",
+                "3D 6.25e7 uniform fp64 per GPU (5e8 over 8 GPUs), sources are targets, adaptive, "
+                "max 30"),
 }
 CPU_SAMPLE_POINTS = 2_000_000
 
@@ -305,6 +309,11 @@ def run_ours(args):
         if mode in ("single", "replicas"):
             def step():
                 tree, _ = tb(actx, dsrc, **dkw)
+                if args.chunks != 1:
+                    # large-list mode: the traversal in row pieces with int32 CSR arrays each
+                    pieces = tg.build_in_chunks(actx, tree, nchunks=args.chunks or None)
+                    nonlocal_state["nchunks"] = len(pieces)
+                    return tree, pieces[-1][1]
                 trav, _ = tg(actx, tree)
                 return tree, trav
         elif mode in ("distributed", "distributed-strong"):
@@ -329,6 +338,7 @@ def run_ours(args):
                 return lt, ltrav
         return step
 
+    nonlocal_state = {"nchunks": 1}
     step_resident = make_step(dsrc, dkw, mode)
 
     def barrier():
@@ -451,8 +461,7 @@ def run_ours(args):
                 main_stream.wait_event(ev)
                 if k + 1 < steps:
                     nxt = upload_async()
-                t, _ = tb(actx, g, **gk)
-                tr, _ = tg(actx, t)
+                t, tr = make_step(g, gk, mode)()
                 last = summary_of(t, tr)
                 used = list(g)                     # the buffers were allocated on the copy stream
                 for v in gk.values():
@@ -576,6 +585,7 @@ def run_ours(args):
             "config": {"workload": f"{args.workload}: {desc}" + (f" (n={n})" if args.n else ""),
                        "points_per_gpu": npoints_job // world, "points_total": npoints_job,
                        "nboxes": nboxes, "nlevels": nlevels,
+                       "traversal_row_pieces": nonlocal_state["nchunks"],
                        "l2_policy": "inputs larger than L2"
                        if (npoints_job // world) * dims * s_bytes > 126e6
                        else "inputs smaller than L2 (no flush)",
@@ -672,6 +682,9 @@ def main():
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
     ap.add_argument("--n", type=int, default=0, help="override the number of points")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunks", type=int, default=1,
+                    help="single GPU: build the traversal in this many row pieces (0 = as many as "
+                         "the int32 CSR range needs; config4 needs > 1)")
     ap.add_argument("--no-strong", action="store_true",
                     help="N > 1: skip the strong-scaling arm of the distributed run")
     ap.add_argument("--parallelism", default="distributed",
@@ -680,6 +693,8 @@ def main():
                          "(weak scaling, default) or of the workload itself (strong); independent "
                          "replicas; round 1's all-gather + replicated tree build")
     args = ap.parse_args()
+    if args.workload == "config4" and args.chunks == 1 and not args.n:
+        args.chunks = 0
     if args.impl == "reference":
         run_reference(args)
     else:

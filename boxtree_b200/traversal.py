@@ -294,6 +294,74 @@ class FMMTraversalBuilder:
             raise ValueError(f"unexpected value of 'from_sep_smaller_crit': {crit}")
         return crit
 
+    def build_in_chunks(self, actx: TorchArrayContext, tree: Tree, nchunks: int | None = None,
+                        cost_per_box=None, **kwargs):
+        """Large-list mode: the traversal of *tree* cut by ROWS into *nchunks* pieces, one
+        :class:`FMMTraversalInfo` per piece.
+
+        The reference's ``ListOfListsBuilder`` (``traversal.py:1854, 1950``) indexes every list
+        with int32 ``starts``, so a tree whose ``from_sep_siblings`` (or any other) list has more
+        than 2**31 - 1 entries cannot be traversed at all (BASELINE config 4: 1e8 Plummer points,
+        2.2e9 list-2 entries).  Here the boxes are cut into *nchunks* contiguous segments of the
+        depth-first order of ``boxtree/distributed/partition.py:38-121`` (equal cost; default cost
+        ``1 + own sources + own targets``); piece *k* is the traversal of the tree whose target
+        flags are kept only on the boxes of segment *k*: its rows are exactly the rows of the
+        global traversal that belong to those boxes, every row of the global traversal is in
+        exactly one piece, and every piece has int32 CSR arrays; the box lists of a piece
+        (``source_boxes``, ``target_boxes``, ...) are the segment's boxes of each kind.  With
+        ``nchunks=None`` the number of pieces is doubled until every list fits.
+
+        :returns: a list of ``(boxes, trav)``: the boxes of the segment (device int32, DFS
+            order) and the traversal restricted to their rows.  ``trav.same_level_non_well_sep_boxes``
+            is only filled for the rows the piece reads (segment boxes and their ancestors)."""
+        import dataclasses
+
+        from .distributed.partition import (_responsible_and_ancestors, get_box_ids_dfs_order,
+                                            partition_segments, partition_segments_device)
+        lib = self._lib
+        nb = int(tree.nboxes)
+        if cost_per_box is None:
+            cost_per_box = (1.0 + tree.box_source_counts_nonchild.double()
+                            + tree.box_target_counts_nonchild.double())
+        dfs_order = get_box_ids_dfs_order(actx, tree)
+        tries = [nchunks] if nchunks else [1, 2, 4, 8, 16, 32, 64]
+        for n in tries:
+            try:
+                if n == 1:
+                    trav, _ = self(actx, tree, **kwargs)
+                    return [(dfs_order, trav)]
+                with torch.cuda.stream(actx.stream):
+                    segs = partition_segments_device(actx, cost_per_box, dfs_order, n)
+                if segs is None:
+                    cost_host = cost_per_box.cpu().numpy() if isinstance(
+                        cost_per_box, torch.Tensor) else np.asarray(cost_per_box)
+                    segs = partition_segments(cost_host[dfs_order.cpu().numpy()], n)
+                out = []
+                shared = None
+                for k in range(n):
+                    boxes = dfs_order[int(segs[k][0]):int(segs[k][1])]
+                    with torch.cuda.stream(actx.stream):
+                        mine, anc = _responsible_and_ancestors(actx, lib, tree, boxes)
+                        flags = actx.empty(nb, np.uint8)
+                        need = actx.empty(nb, np.int8)
+                        check(lib.bt_dist_restrict_target_flags(
+                            nb, dptr(tree.box_flags), dptr(mine), dptr(actx.zeros(nb, np.int8)),
+                            dptr(flags), dptr(need), actx.stream_handle),
+                            "bt_dist_restrict_target_flags")
+                        need = mine | anc
+                    piece, _ = self(actx, dataclasses.replace(tree, box_flags=flags),
+                                    source_boxes_mask=mine, source_parent_boxes_mask=mine,
+                                    _colleague_row_mask=need, **kwargs)
+                    out.append((boxes, dataclasses.replace(piece, tree=tree)))
+                    del piece, flags, need
+                del shared
+                return out
+            except OverflowError:
+                if nchunks:
+                    raise
+                torch.cuda.empty_cache()
+        raise OverflowError("a single row piece still exceeds the int32 CSR index range")
+
     def __call__(self, actx: TorchArrayContext, tree: Tree | TreeOfBoxes, wait_for=None,
                  debug: bool = False, _from_sep_smaller_min_nsources_cumul: int | None = None,
                  source_boxes_mask=None, source_parent_boxes_mask=None,
