@@ -163,7 +163,7 @@ def sharded_setup(actx, tree, traversal_builder, comm, cost_per_box=None,
 
 
 def distributed_tree_setup(actx, dtree, traversal_builder, comm, cost_per_box=None,
-                           merge_close_lists=False):
+                           merge_close_lists=False, traversal_pieces=None):
     """The tree/traversal part of ``make_distributed_wrangler``
     (``distributed/__init__.py:156-266``) for a :class:`DistributedTree`: no rank holds all
     particles and nothing is broadcast.  Collective over *comm*.
@@ -181,7 +181,8 @@ def distributed_tree_setup(actx, dtree, traversal_builder, comm, cost_per_box=No
     ``local_tree.py:408-470``).  Local tree, local traversal, masks and index arrays are
     identical to the reference flow's on the concatenated particle set.
 
-    Returns ``(local_tree, local_trav, src_idx, tgt_idx)``."""
+    Returns ``(local_tree, local_trav, src_idx, tgt_idx)``; *local_trav* is a list of row
+    pieces when the rank's lists do not fit the int32 CSR range (or *traversal_pieces* > 1)."""
     import dataclasses
 
     from .._cabi import check, dptr, load
@@ -225,17 +226,60 @@ def distributed_tree_setup(actx, dtree, traversal_builder, comm, cost_per_box=No
 
         # {{{ local traversal, then the masks from its rows + the corner rows
 
-        flag_tree = dataclasses.replace(dtree, box_flags=local_flags)
-        local_trav, _ = traversal_builder(
-            actx, flag_tree, source_boxes_mask=resp_mask, source_parent_boxes_mask=anc_mask,
-            _colleague_row_mask=need, _keep_shared=True)
+        def local_piece(row_mask):
+            # rows of the boxes of row_mask only (None: all rows of the local traversal)
+            fl = local_flags
+            if row_mask is not None:
+                fl = actx.empty(nb, np.uint8)
+                scratch = actx.empty(nb, np.int8)
+                check(lib.bt_dist_restrict_target_flags(
+                    nb, dptr(local_flags), dptr(row_mask), dptr(row_mask), dptr(fl), dptr(scratch),
+                    sh), "bt_dist_restrict_target_flags")
+            prev = traversal_builder.last_shared        # colleagues etc. of an earlier piece
+            return traversal_builder(
+                actx, dataclasses.replace(dtree, box_flags=fl),
+                source_boxes_mask=resp_mask if row_mask is None else (resp_mask & row_mask),
+                source_parent_boxes_mask=anc_mask if row_mask is None else (anc_mask & row_mask),
+                _colleague_row_mask=need, _keep_shared=prev is None, _shared=prev)[0]
+
+        # one piece, or -- when a list of the rank's rows exceeds the int32 CSR range
+        # (``traversal_pieces`` > 1, or on OverflowError) -- row pieces as in
+        # FMMTraversalBuilder.build_in_chunks: piece k holds the rows of the k-th part of the
+        # responsible boxes (depth-first order), piece 0 also those of the ancestors
+        npieces = max(int(traversal_pieces or 1), 1)
+        traversal_builder.last_shared = None
+        while True:
+            try:
+                if npieces == 1:
+                    local_travs = [local_piece(None)]
+                else:
+                    local_travs = []
+                    nresp = int(responsible.shape[0])
+                    for k in range(npieces):
+                        part = responsible[k * nresp // npieces:(k + 1) * nresp // npieces]
+                        pm = actx.zeros(nb, np.int8)
+                        check(lib.bt_dist_mask_from_list(int(part.shape[0]), dptr(part.contiguous()),
+                                                         dptr(pm), sh), "bt_dist_mask_from_list")
+                        if k == 0:
+                            pm = pm | (anc_mask & ~resp_mask)
+                        local_travs.append(local_piece(pm))
+                break
+            except OverflowError:
+                if traversal_pieces:
+                    raise
+                npieces *= 2
+                traversal_builder.last_shared = None
+                torch.cuda.empty_cache()
         shared = traversal_builder.last_shared
         traversal_builder.last_shared = None
         mark("ds:local traversal")
         # every row of the local traversal is a row the masks read: its target boxes are
         # responsible boxes, its target-or-target-parent boxes responsible boxes or ancestors;
         # the corner traversal has no list 1 / 3 rows and only rows of such boxes otherwise
-        masks = _masks_from_traversal(actx, lib, local_trav, resp_mask, anc_mask, all_rows=True)
+        masks = None
+        for piece in local_travs:
+            masks = _masks_from_traversal(actx, lib, piece, resp_mask, anc_mask, into=masks,
+                                          all_rows=True)
         if int(any_corner.item()):
             corner_tree = dataclasses.replace(dtree, box_flags=corner_flags)
             corner_trav, _ = traversal_builder(
@@ -260,8 +304,9 @@ def distributed_tree_setup(actx, dtree, traversal_builder, comm, cost_per_box=No
                                  pre, ranges=tgt_ranges)
         mark("ds:exchange")
         local_tree = assemble_local_tree(actx, dtree, src, tgt, masks, allm, responsible, bitsel=4)
-        local_trav = dataclasses.replace(local_trav, tree=local_tree)
+        local_travs = [dataclasses.replace(t, tree=local_tree) for t in local_travs]
         if merge_close_lists and local_tree.targets_have_extent:
-            local_trav = local_trav.merge_close_lists(actx)
+            local_travs = [t.merge_close_lists(actx) for t in local_travs]
         mark("ds:local tree")
+    local_trav = local_travs[0] if len(local_travs) == 1 else local_travs
     return local_tree, local_trav, src[5], tgt[5]

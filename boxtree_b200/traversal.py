@@ -313,7 +313,7 @@ class FMMTraversalBuilder:
 
         :returns: a list of ``(boxes, trav)``: the boxes of the segment (device int32, DFS
             order) and the traversal restricted to their rows.  ``trav.same_level_non_well_sep_boxes``
-            is only filled for the rows the piece reads (segment boxes and their ancestors)."""
+            is the full list in every piece (built once, shared)."""
         import dataclasses
 
         from .distributed.partition import (_responsible_and_ancestors, get_box_ids_dfs_order,
@@ -337,7 +337,7 @@ class FMMTraversalBuilder:
                         cost_per_box, torch.Tensor) else np.asarray(cost_per_box)
                     segs = partition_segments(cost_host[dfs_order.cpu().numpy()], n)
                 out = []
-                shared = None
+                self.last_shared = None
                 for k in range(n):
                     boxes = dfs_order[int(segs[k][0]):int(segs[k][1])]
                     with torch.cuda.stream(actx.stream):
@@ -348,15 +348,18 @@ class FMMTraversalBuilder:
                             nb, dptr(tree.box_flags), dptr(mine), dptr(actx.zeros(nb, np.int8)),
                             dptr(flags), dptr(need), actx.stream_handle),
                             "bt_dist_restrict_target_flags")
-                        need = mine | anc
+                    # box geometry, source flags and depth-first ranks are the same for every
+                    # piece: colleagues and list-2 masks of ALL boxes are built once
+                    prev = self.last_shared
                     piece, _ = self(actx, dataclasses.replace(tree, box_flags=flags),
                                     source_boxes_mask=mine, source_parent_boxes_mask=mine,
-                                    _colleague_row_mask=need, **kwargs)
+                                    _keep_shared=prev is None, _shared=prev, **kwargs)
                     out.append((boxes, dataclasses.replace(piece, tree=tree)))
                     del piece, flags, need
-                del shared
+                self.last_shared = None
                 return out
             except OverflowError:
+                self.last_shared = None
                 if nchunks:
                     raise
                 torch.cuda.empty_cache()
