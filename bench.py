@@ -321,7 +321,11 @@ def run_ours(args):
                 # all-reduced bounding box + per-level box counts (NCCL), particles stay put;
                 # DFS-order cost partition; ONE all-to-all of particles; local traversal
                 dtree = bd.build_distributed_tree(actx, tb, comm, dsrc, **dkw)
-                lt, ltrav, _, _ = bd.distributed_tree_setup(actx, dtree, tg, comm)
+                lt, ltrav, _, _ = bd.distributed_tree_setup(actx, dtree, tg, comm,
+                                                            traversal_pieces=args.pieces or None)
+                if isinstance(ltrav, list):         # row pieces (int32 CSR range)
+                    nonlocal_state["nchunks"] = len(ltrav)
+                    ltrav = ltrav[-1]
                 return lt, ltrav
         else:
             def step():
@@ -432,17 +436,19 @@ def run_ours(args):
         return t, tr, summary_of(t, tr)
 
     e2e_steps = max(1, min(args.steps, 10))
-    o = step_e2e()
-    del o
-    ms_e2e, o = timed(step_e2e, e2e_steps)
-    d2h_bytes = int(o[2].numel() * 8)
-    e2e_value = npoints_job / (ms_e2e / e2e_steps * 1e-3) / 1e6
-    del o
+    e2e_value, d2h_bytes = None, 0
+    if not args.no_e2e:
+        o = step_e2e()
+        del o
+        ms_e2e, o = timed(step_e2e, e2e_steps)
+        d2h_bytes = int(o[2].numel() * 8)
+        e2e_value = npoints_job / (ms_e2e / e2e_steps * 1e-3) / 1e6
+        del o
 
     # the same, double buffered: the H2D copy of step k+1 (copy stream) overlaps the build of step
     # k; every step still copies its own inputs from pinned memory and reads its summary back
     e2e_pipelined = None
-    if mode in ("single", "replicas"):
+    if mode in ("single", "replicas") and not args.no_e2e:
         copy_stream = torch.cuda.Stream(device=device)
         main_stream = actx.stream
 
@@ -680,11 +686,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
-    ap.add_argument("--n", type=int, default=0, help="override the number of points")
+    ap.add_argument("--n", "--points", dest="n", type=int, default=0,
+                    help="override the number of points (per GPU for weak workloads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunks", type=int, default=1,
                     help="single GPU: build the traversal in this many row pieces (0 = as many as "
                          "the int32 CSR range needs; config4 needs > 1)")
+    ap.add_argument("--pieces", type=int, default=0,
+                    help="N > 1: build every rank's local traversal in this many row pieces "
+                         "(0 = as many as the int32 CSR range needs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end arm")
     ap.add_argument("--no-strong", action="store_true",
                     help="N > 1: skip the strong-scaling arm of the distributed run")
     ap.add_argument("--parallelism", default="distributed",

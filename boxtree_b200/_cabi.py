@@ -119,6 +119,7 @@ SIGNATURES = {
     "bt_trav_level_starts": [_i, vp, vp, _i, vp, vp],
     "bt_trav_build_list": [_i, _i, _i, _P(bt_tree_view), _P(bt_list_args), _i, vp, vp, vp, vp,
                            vp, vp],
+    "bt_trav_mark_rows": [_i, _P(bt_tree_view), _P(bt_list_args), vp, vp, vp],
     "bt_trav_list3": [_i, _i, _P(bt_tree_view), _P(bt_list3_args), _i, vp, vp, vp, vp,
                       _P(bt_heavy_ws), _i64, vp],
     "bt_trav_list1": [_i, _i, _P(bt_tree_view), vp, _i, vp, vp, vp, _P(bt_heavy_ws), _i64, vp],

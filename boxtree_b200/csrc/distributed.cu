@@ -430,7 +430,8 @@ dist_pack_kernel(int64_t n, int nranks, int64_t ntiles, int dim, int recbytes, c
 }
 
 // receiver, step 1: records per (sender, box of my mask); compact[b] = index of box b among
-// the boxes of the mask
+// the boxes of the mask.  The records of one sender arrive in tree order with the indices of a
+// box's own range ascending, so the last record of every (sender, box) run carries the count.
 template <typename T>
 __global__ void __launch_bounds__(256)
 dist_unpack_count_kernel(int64_t nrec, int nranks, int nfields, int recbytes, DestBase chunk,
@@ -442,7 +443,12 @@ dist_unpack_count_kernel(int64_t nrec, int nranks, int nfields, int recbytes, De
         int s = 0;
         while (s + 1 < nranks && chunk.v[s + 1] <= k) ++s;
         const int* tail = reinterpret_cast<const int*>(recv + k * recbytes + (size_t)nfields * sizeof(T));
-        atomicAdd(&cnt[(int64_t)s * nmasked + compact[tail[0]]], 1);
+        bool last = (k + 1 == chunk.v[s + 1]);
+        if (!last) {
+            const int* nxt = reinterpret_cast<const int*>(recv + (k + 1) * recbytes + (size_t)nfields * sizeof(T));
+            last = nxt[0] != tail[0];
+        }
+        if (last) cnt[(int64_t)s * nmasked + compact[tail[0]]] = tail[1] + 1;
     }
 }
 // step 2: exclusive prefix over the senders, per box

@@ -839,6 +839,43 @@ list_kernel(TreeView<T, DIM> t, const int* __restrict__ row_boxes, const int* __
     }
 }
 
+// distributed build: rows of lists 2, 4 and 4-close of the boxes whose (restricted) flags carry
+// a target bit, marked straight into the box masks of partition.py:197-297 -- no lists are
+// built: list 2 -> multipole mask, list 4 and list 4 close -> point-source mask
+struct MarkEmit {
+    signed char* m0; signed char* m1;
+    __device__ __forceinline__ void e0(int v) { m0[v] = 1; }
+    __device__ __forceinline__ void e1(int v) { if (m1) m1[v] = 1; }
+};
+template <typename T, int DIM>
+__global__ void __launch_bounds__(kTravBlock)
+mark_rows_kernel(TreeView<T, DIM> t, const int* __restrict__ coll_starts, const int* __restrict__ coll_lists,
+                 int with_extent, T stick_out_factor, signed char* __restrict__ point_src_mask,
+                 signed char* __restrict__ mpole_mask)
+{
+    __shared__ T rad[kMaxWalkLevels];
+    fill_rad_table(rad, t.root_extent);
+    const int stride = gridDim.x * blockDim.x;
+    for (int box = blockIdx.x * blockDim.x + threadIdx.x; box < t.nboxes; box += stride) {
+        if (!(t.flags[box] & (BT_BOX_IS_TARGET_BOX | BT_BOX_HAS_TARGET_CHILD_BOXES))) continue;
+        MarkEmit e2{mpole_mask, nullptr};
+        gen_list2<T, DIM>(t, rad, coll_starts, coll_lists, box, e2);
+        MarkEmit e4{point_src_mask, point_src_mask};
+        gen_list4<T, DIM>(t, rad, coll_starts, coll_lists, with_extent, stick_out_factor, box, e4);
+    }
+}
+template <typename T, int DIM>
+static int mark_rows_impl(const bt_tree_view* tv, const bt_list_args* a, signed char* point_src_mask,
+                          signed char* mpole_mask, cudaStream_t s)
+{
+    TreeView<T, DIM> t = make_view<T, DIM>(tv);
+    if (t.nboxes <= 0) return BT_OK;
+    mark_rows_kernel<T, DIM><<<grid_for(t.nboxes, kTravBlock, 16), kTravBlock, 0, s>>>(
+        t, a->coll_starts, a->coll_lists, a->with_extent, (T)a->stick_out_factor, point_src_mask, mpole_mask);
+    BT_LAUNCH_CHECK();
+    return BT_OK;
+}
+
 // counts -> starts (in place), total to starts[n] and totals[slot]
 struct InPlaceIn {
     const int* a;
@@ -2698,6 +2735,14 @@ int bt_trav_build_list(int dtype, int kind, int phase, const bt_tree_view* tree,
     BT_PROF(kNames[phase ? 1 : 0][(kind >= 0 && kind <= 5) ? kind : 3], (cudaStream_t)stream);
     BT_DISPATCH(dtype, tree->dim, build_list_impl, kind, phase, tree, args, nrows, starts, lists,
                 close_starts, close_lists, (long long*)totals_dev, (cudaStream_t)stream);
+}
+
+int bt_trav_mark_rows(int dtype, const bt_tree_view* tree, const bt_list_args* args, int8_t* point_src_mask,
+                      int8_t* multipole_mask, void* stream)
+{
+    BT_PROF("bt_trav_mark_rows", (cudaStream_t)stream);
+    BT_DISPATCH(dtype, tree->dim, mark_rows_impl, tree, args, (signed char*)point_src_mask,
+                (signed char*)multipole_mask, (cudaStream_t)stream);
 }
 
 int bt_trav_list1(int dtype, int phase, const bt_tree_view* tree, const int32_t* target_boxes,

@@ -381,8 +381,8 @@ create_children_kernel(Pool<T, DIM> pool, const unsigned long long* __restrict__
         }
         pool.nn[child] = nn;
         if (pool.xch) {         // sums over ranks follow (children_finish_kernel)
-            int* x = pool.xch + 3ll * (r * NB + m);
-            x[0] = lb; x[1] = cnt; x[2] = nn;
+            int* x = pool.xch + 2ll * (r * NB + m);
+            x[0] = cnt; x[1] = nn;
         } else {
             const int w = wprefix ? ((cnt > 0) ? clamp_weight(wprefix[lb_next] - wprefix[lb]) : 0) : cnt;
             if (w > maxw) ctl[BT_CTL_OVERSIZE] = 1;
@@ -399,22 +399,28 @@ create_children_kernel(Pool<T, DIM> pool, const unsigned long long* __restrict__
     }
 }
 
-// distributed build: the all-reduced (lower bound, count, nonchild) of the new children become
-// their global ranges; the oversize test of the splitter (:690-696) runs on the global count
+// distributed build: the all-reduced (count, nonchild) of the new children become their global
+// ranges -- a child starts where the parent's descendants start plus its lower siblings' counts,
+// like the splitter's local ranges; the oversize test (:690-696) runs on the global count
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256)
-children_finish_kernel(Pool<T, DIM> pool, int* __restrict__ ctl, int maxw, int skip_if_no_regular)
+children_finish_kernel(Pool<T, DIM> pool, const int* __restrict__ split_list, int* __restrict__ ctl, int maxw,
+                       int skip_if_no_regular)
 {
     constexpr int NB = 1 << DIM;
     if (ctl[BT_CTL_OVERFLOW]) return;
     if (skip_if_no_regular && ctl[BT_CTL_NSPLIT_REGULAR] == 0) return;
     const int total = ctl[BT_CTL_NSPLIT] * NB, base = ctl[BT_CTL_NBOXES];
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
-        const int* x = pool.xch + 3ll * k;
-        const int cnt = x[1];
-        pool.gstart[base + k] = (cnt > 0) ? x[0] : 0;
+        const int r = k / NB, m = k % NB;
+        const int* x = pool.xch + 2ll * (r * NB);
+        const int b = split_list[r];
+        int start = pool.gstart[b] + pool.gnn[b];
+        for (int q = 0; q < m; ++q) start += x[2 * q];
+        const int cnt = x[2 * m];
+        pool.gstart[base + k] = (cnt > 0) ? start : 0;
         pool.gcount[base + k] = cnt;
-        pool.gnn[base + k] = x[2];
+        pool.gnn[base + k] = x[2 * m + 1];
         if (cnt > maxw) ctl[BT_CTL_OVERSIZE] = 1;
     }
 }
@@ -589,8 +595,9 @@ __device__ __forceinline__ unsigned warp_bitonic_sort(unsigned v)
 constexpr int kFixBlock = 256;
 constexpr int kFixSmemCap = 4096;
 
-// one warp per box for count <= 32; larger boxes are sorted by the whole block
-// in shared memory (bitonic), boxes above kFixSmemCap are listed for the host.
+// every lane looks at one box; the boxes that need work (never partitioned, >= 2 particles) are
+// then sorted one after the other by the whole warp (count <= 32); larger boxes are sorted by a
+// block in shared memory (bitonic), boxes above kFixSmemCap are listed for the host.
 __global__ void __launch_bounds__(kFixBlock)
 leaf_fixup_kernel(const int* __restrict__ box_start, const int* __restrict__ box_count,
                   const unsigned char* __restrict__ real_children, int nboxes,
@@ -600,18 +607,22 @@ leaf_fixup_kernel(const int* __restrict__ box_start, const int* __restrict__ box
     const int lane = threadIdx.x & 31;
     const int wglobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int b = wglobal; b < nboxes; b += nwarps) {
-        if (real_children[b]) continue;
-        const int c = box_count[b];
-        if (c < 2) continue;
-        const int s = box_start[b];
-        if (c <= 32) {
-            unsigned v = (lane < c) ? ids[s + lane] : 0xffffffffu;
-            v = warp_bitonic_sort(v);
-            if (lane < c) ids[s + lane] = v;
-        } else if (lane == 0) {
+    for (int b0 = wglobal * 32; b0 < nboxes; b0 += nwarps * 32) {
+        const int b = b0 + lane;
+        int c = 0, s = 0;
+        if (b < nboxes && !real_children[b]) { c = box_count[b]; s = box_start[b]; }
+        if (c > 32) {
             const int k = atomicAdd(ctl + BT_CTL_NBIG, 1);
             if (k < big_cap) big_list[k] = b;
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, c >= 2 && c <= 32);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int cc = __shfl_sync(0xffffffffu, c, src), ss = __shfl_sync(0xffffffffu, s, src);
+            unsigned v = (lane < cc) ? ids[ss + lane] : 0xffffffffu;
+            v = warp_bitonic_sort(v);
+            if (lane < cc) ids[ss + lane] = v;
         }
     }
 }
@@ -838,9 +849,11 @@ box_info_global_kernel(int nboxes, int have_ext, const int* __restrict__ gstart,
 // as the reference's serial loop (:1345-1368).  Four boxes per warp (8 lanes each: a leaf
 // holds at most a few dozen particles); a box with many own particles (upper-level boxes of
 // a tree with extents) is taken by the whole warp.
-constexpr int kExtGroup = 8, kExtBig = 64, kExtHuge = 256;
+constexpr int kExtBig = 64, kExtHuge = 256;
 
-template <typename T, int DIM>
+// kExtGroup lanes per box: 8 for a tree whose leaves hold a few dozen particles, 1 when most
+// boxes hold at most a couple (a rank's share of the particles in a distributed build)
+template <typename T, int DIM, int kExtGroup>
 __global__ void __launch_bounds__(256)
 box_extents_own_kernel(int nboxes, int aligned, const T* __restrict__ box_centers,
                        const int* __restrict__ pstarts, const int* __restrict__ pcounts,
@@ -863,7 +876,7 @@ box_extents_own_kernel(int nboxes, int aligned, const T* __restrict__ box_center
         // boxes with thousands of own particles go to a list for box_extents_huge_kernel
         const bool huge = (e - s) > kExtHuge;
         if (huge && gl == 0) huge_list[atomicAdd(huge_count, 1)] = ibox;
-        const bool big = !huge && (e - s) > kExtBig;
+        const bool big = !huge && (e - s) > (kExtGroup == 1 ? 8 : kExtBig);
         if (!big) {
             for (int ip = s + gl; ip < e; ip += kExtGroup) {
                 const T rad = radii ? radii[ip] : (T)0;
@@ -900,13 +913,13 @@ box_extents_own_kernel(int nboxes, int aligned, const T* __restrict__ box_center
 #pragma unroll
             for (int a = 0; a < DIM; ++a) {
 #pragma unroll
-                for (int o = 16; o >= kExtGroup; o >>= 1) {     // across groups; the rest below
+                for (int o = 16; o >= (kExtGroup > 1 ? kExtGroup : 1); o >>= 1) {   // across groups; the rest below
                     const T lo = __shfl_xor_sync(0xffffffffu, wmn[a], o);
                     const T hi = __shfl_xor_sync(0xffffffffu, wmx[a], o);
                     wmn[a] = (lo < wmn[a]) ? lo : wmn[a];
                     wmx[a] = (wmx[a] < hi) ? hi : wmx[a];
                 }
-                if (g == src / kExtGroup) { mn[a] = wmn[a]; mx[a] = wmx[a]; }
+                if (lane / kExtGroup == src / kExtGroup) { mn[a] = wmn[a]; mx[a] = wmx[a]; }
             }
         }
 #pragma unroll
@@ -920,6 +933,7 @@ box_extents_own_kernel(int nboxes, int aligned, const T* __restrict__ box_center
             }
             if (valid && !huge && gl == 0) { bb_min[a * aligned + ibox] = mn[a]; bb_max[a * aligned + ibox] = mx[a]; }
         }
+        (void)GPW;
     }
 }
 
@@ -1148,7 +1162,7 @@ static int level_step_impl(const bt_pool* pool, const unsigned long long* keys, 
     if (commit) {
         if (P.xch) {
             children_finish_kernel<T, DIM><<<grid_for(max_threads, 256, 8), 256, 0, s>>>(
-                P, ctl, maxw, skip_if_no_regular);
+                P, split_list, ctl, maxw, skip_if_no_regular);
             BT_LAUNCH_CHECK();
         }
         commit_level_kernel<DIM><<<1, 32, 0, s>>>(ctl, skip_if_no_regular);
@@ -1236,10 +1250,16 @@ static int box_extents_impl(int nboxes, int aligned, int nlevels, const int* lev
     const size_t huge_cap = (size_t)nboxes;
     BT_CHECK(temp_alloc((void**)&huge, sizeof(int) * (huge_cap + 1), s));
     BT_CHECK(cudaMemsetAsync(huge, 0, sizeof(int), s));
-    box_extents_own_kernel<T, DIM><<<grid_for((int64_t)nboxes * kExtGroup, 256, 8), 256, 0, s>>>(
-        nboxes, aligned, (const T*)centers, pstarts, pcounts, (const T*)parts[0],
-        DIM > 1 ? (const T*)parts[1] : nullptr, DIM > 2 ? (const T*)parts[2] : nullptr,
-        (const T*)radii, (T*)bmin, (T*)bmax, huge + 1, huge);
+    if (phases & 4)     // sparse boxes: one lane per box
+        box_extents_own_kernel<T, DIM, 1><<<grid_for((int64_t)nboxes, 256, 8), 256, 0, s>>>(
+            nboxes, aligned, (const T*)centers, pstarts, pcounts, (const T*)parts[0],
+            DIM > 1 ? (const T*)parts[1] : nullptr, DIM > 2 ? (const T*)parts[2] : nullptr,
+            (const T*)radii, (T*)bmin, (T*)bmax, huge + 1, huge);
+    else
+        box_extents_own_kernel<T, DIM, 8><<<grid_for((int64_t)nboxes * 8, 256, 8), 256, 0, s>>>(
+            nboxes, aligned, (const T*)centers, pstarts, pcounts, (const T*)parts[0],
+            DIM > 1 ? (const T*)parts[1] : nullptr, DIM > 2 ? (const T*)parts[2] : nullptr,
+            (const T*)radii, (T*)bmin, (T*)bmax, huge + 1, huge);
     BT_LAUNCH_CHECK();
     box_extents_huge_kernel<T, DIM><<<(unsigned)(huge_cap < 4 * kNumSMs ? huge_cap : 4 * kNumSMs), 256, 0, s>>>(
         aligned, (const T*)centers, pstarts, pcounts, (const T*)parts[0],
@@ -1408,7 +1428,7 @@ int bt_leaf_fixup(int nboxes, const int32_t* box_start, const int32_t* box_count
     BT_PROF("bt_leaf_fixup", (cudaStream_t)stream);
     cudaStream_t s = (cudaStream_t)stream;
     if (nboxes <= 0) return BT_OK;
-    bt::leaf_fixup_kernel<<<bt::grid_for((int64_t)nboxes * 32, bt::kFixBlock, 8), bt::kFixBlock, 0, s>>>(
+    bt::leaf_fixup_kernel<<<bt::grid_for((int64_t)nboxes, bt::kFixBlock, 8), bt::kFixBlock, 0, s>>>(
         box_start, box_count, real_children, nboxes, ids, big_list, ctl, big_cap);
     BT_LAUNCH_CHECK();
     bt::leaf_fixup_big_kernel<<<bt::kNumSMs * 2, bt::kFixBlock, 0, s>>>(

@@ -217,7 +217,7 @@ def distributed_tree_setup(actx, dtree, traversal_builder, comm, cost_per_box=No
         check(lib.bt_dist_modify_target_flags(nb, dptr(tgt_ranges[1]), dptr(tgt_ranges[2]),
                                               dptr(local_flags), sh), "bt_dist_modify_target_flags")
         corner_flags = actx.empty(nb, np.uint8)
-        any_corner = actx.zeros(1, np.int32)
+        any_corner = actx.empty(1, np.int32)
         check(lib.bt_dist_corner_flags(nb, dptr(dtree.box_flags), dptr(local_flags), dptr(resp_mask),
                                        dptr(anc_mask), dptr(corner_flags), dptr(any_corner), sh),
               "bt_dist_corner_flags")
@@ -280,14 +280,26 @@ def distributed_tree_setup(actx, dtree, traversal_builder, comm, cost_per_box=No
         for piece in local_travs:
             masks = _masks_from_traversal(actx, lib, piece, resp_mask, anc_mask, into=masks,
                                           all_rows=True)
-        if int(any_corner.item()):
-            corner_tree = dataclasses.replace(dtree, box_flags=corner_flags)
-            corner_trav, _ = traversal_builder(
-                actx, corner_tree, _colleague_row_mask=need,
-                _list13_row_mask=actx.zeros(nb, np.int8), _shared=shared)
-            masks = _masks_from_traversal(actx, lib, corner_trav, resp_mask, anc_mask, into=masks,
-                                          all_rows=True)
-            del corner_trav
+        # rows of lists 2 / 4 / 4-close that the global traversal has on responsible boxes and
+        # their ancestors but the local one lacks: marked without building the lists
+        import ctypes as C
+
+        from .._cabi import bt_list_args, bt_tree_view, dtype_code
+        tv = bt_tree_view()
+        tv.dim, tv.nboxes, tv.aligned_nboxes = int(dtree.dimensions), nb, int(dtree.aligned_nboxes)
+        tv.nlevels, tv.root_extent = int(dtree.nlevels), float(dtree.root_extent)
+        tv.box_centers, tv.box_levels = dptr(dtree.box_centers), dptr(dtree.box_levels)
+        tv.box_child_ids, tv.box_flags = dptr(dtree.box_child_ids), dptr(corner_flags)
+        tv.box_parent_ids = dptr(dtree.box_parent_ids)
+        tv.well_sep_is_n_away = int(traversal_builder.well_sep_is_n_away)
+        tv.box_child_ids_t = dptr(shared["child_t"])
+        la = bt_list_args()
+        la.coll_starts, la.coll_lists = dptr(shared["coll"][0]), dptr(shared["coll"][1])
+        la.stick_out_factor = float(dtree.stick_out_factor)
+        la.with_extent = int(bool(dtree.sources_have_extent or dtree.targets_have_extent))
+        check(lib.bt_trav_mark_rows(dtype_code(dtree.coord_dtype), C.byref(tv), C.byref(la),
+                                    dptr(masks.point_src_boxes), dptr(masks.multipole_src_boxes),
+                                    sh), "bt_trav_mark_rows")
         del shared
         mark("ds:masks")
 

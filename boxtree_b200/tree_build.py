@@ -78,7 +78,7 @@ class _Pool:
         if n_old:
             self.split_list[:n_old].copy_(old_split)
             self.flag[:n_old].copy_(old_flag)
-        self.xch = torch.empty(3 * capacity, dtype=torch.int32, device=dev) \
+        self.xch = torch.empty(2 * capacity, dtype=torch.int32, device=dev) \
             if self.distributed else None
         self.capacity = capacity
 
@@ -472,7 +472,7 @@ class TreeBuilder:
                         h = read_ctl()
                     if dist:
                         if h[CTL_NSPLIT] and not (skip_if_no_regular and not h[CTL_NSPLIT_REGULAR]):
-                            comm.allreduce_(pool.xch[:3 * nb * int(h[CTL_NSPLIT])], "sum")
+                            comm.allreduce_(pool.xch[:2 * nb * int(h[CTL_NSPLIT])], "sum")
                         run_step(STEP_COMMIT)
                         h = read_ctl()
 
@@ -703,14 +703,16 @@ class TreeBuilder:
             ls_host = (C.c_int32 * (nlevels + 1))(*[int(x) for x in level_start_box_nrs])
             # distributed: min/max over the rank's own particles, all-reduced (exact), then the
             # child merge on the global values
-            for phases in ((1, 2) if dist else (3,)):
+            # (a rank's share of a box is a particle or two: one lane per box, flag 4)
+            sparse = 4 if dist and nsrcntgts < 2 * nfinal else 0
+            for phases in ((1 | sparse, 2) if dist else (3,)):
                 for parts, radii, pstarts, pcounts, bmin, bmax in rounds:
                     check(lib.bt_box_extents_phase(
                         dcode, dimensions, nfinal, aligned_nboxes, nlevels, ls_host,
                         dptr(box_child_ids), dptr(box_centers), dptr(pstarts), dptr(pcounts),
                         _cabi.ptr_array(list(parts)), dptr(radii), dptr(bmin), dptr(bmax), phases,
                         sh), "bt_box_extents")
-                if dist and phases == 1:
+                if dist and phases & 1:
                     comm.allreduce_(bb_min_all, "min")
                     comm.allreduce_(bb_max_all, "max")
 

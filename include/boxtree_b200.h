@@ -69,9 +69,9 @@ typedef struct {
     int32_t capacity;
     /* Distributed build (boxtree_b200/distributed/tree_build.py): start/count/nonchild above
      * are the box's range in THIS rank's sorted particles; gstart/gcount/gnonchild hold the
-     * sums over all ranks (the global tree's values) and xch [3 * 2^dim * nsplit] receives
-     * (lower bound, count, nonchild) of the children created by BT_STEP_CREATE, which the host
-     * all-reduces before BT_STEP_COMMIT.  All four NULL on one GPU (global == local). */
+     * sums over all ranks (the global tree's values) and xch [2 * 2^dim * nsplit] receives
+     * (count, nonchild) of the children created by BT_STEP_CREATE, which the host all-reduces
+     * before BT_STEP_COMMIT.  All four NULL on one GPU (global == local). */
     int32_t *gstart;
     int32_t *gcount;
     int32_t *gnonchild;
@@ -211,7 +211,8 @@ int bt_box_extents(int dtype, int dim, int nboxes, int aligned, int nlevels,
 
 /* Distributed build (no kernel counterpart in the reference, whose tree is built on one rank and
  * broadcast, distributed/__init__.py:185-203): bt_box_extents split into its two phases
- * (phases & 1: own-particle min/max per box, phases & 2: child merge per level) so that the
+ * (phases & 1: own-particle min/max per box -- with phases & 4 one lane per box, for boxes
+ * that hold a particle or two --, phases & 2: child merge per level) so that the
  * host can all-reduce min/max between them; bt_box_info split into the per-rank source counts
  * src3 = [3][nboxes] (sources before / in / stopping in the box's range of THIS rank's
  * particles, plus the rank-local range arrays) and the global ranges + flags from the global
@@ -284,6 +285,14 @@ int bt_trav_build_list(int dtype, int kind, int phase, const bt_tree_view *tree,
                        const bt_list_args *args, int nrows, int32_t *starts, int32_t *lists,
                        int32_t *close_starts, int32_t *close_lists, int64_t *totals_dev,
                        void *stream);
+
+/* distributed build (no reference counterpart): rows of lists 2, 4 and 4-close
+ * (traversal.py:556-601, 931-1146) of every box whose tree->box_flags carry a target bit,
+ * marked straight into the masks of partition.py:197-297 -- list 2 into multipole_mask,
+ * lists 4 / 4-close into point_src_mask -- without building the lists.  args: colleague CSR,
+ * stick_out_factor, with_extent. */
+int bt_trav_mark_rows(int dtype, const bt_tree_view *tree, const bt_list_args *args,
+                      int8_t *point_src_mask, int8_t *multipole_mask, void *stream);
 
 /* same_level_non_well_sep_boxes built top-down instead of by the reference's walk from the
  * root (traversal.py:398-464; same set, same depth-first order): the colleagues of b are the
