@@ -33,6 +33,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <math.h>
 #include <float.h>
 #include <limits.h>
@@ -170,36 +173,97 @@ void orc_morton_count_scan(
 {
     const int have_ext = extent_norm != 0;
     const int w = mbc_width(d, have_ext), nb = 1 << d, off = have_ext ? 1 : 0;
-    int32_t acc[1 + 2 * 8], item[1 + 2 * 8];
-    for (int64_t i = 0; i < n; ++i) {
-        particle_id_t uid = user_srcntgt_ids[i];
-        int mnr = morton_nr_of_particle(d, extent_norm,
-            box_levels[srcntgt_box_ids[i]], bbox_min, bbox_max, uid, coords,
-            radii, stick_out_factor);
-        morton_nrs[i] = (morton_nr_t)mnr;
-        memset(item, 0, sizeof(int32_t) * w);
-        if (have_ext) item[0] = (mnr == -1);
-        for (int m = 0; m < nb; ++m) {
-            item[off + m] = (mnr == m);
-            item[off + nb + m] = (mnr == m) ? refine_weights[uid] : 0;
-        }
-        if (i == 0 || box_start_flags[i]) {
-            memcpy(acc, item, sizeof(int32_t) * w);
-        } else { /* scan_t_add, :277-302 */
-            if (have_ext) acc[0] += item[0];
+    /* The reference's GenericScanKernel is a parallel segmented scan; here the particle range is
+       cut into one chunk per thread: (1) every chunk scans its own particles, (2) the value
+       carried into each chunk is chained serially over the few chunks, (3) the carry is added to
+       the chunk's particles before its first segment start, then the output statement runs.
+       scan_t_add (:277-302) is associative (int adds; saturating adds of non-negative weights),
+       so the result equals the sequential scan's. */
+    enum { W = 1 + 2 * 8 };
+    int nthreads = 1;
+#ifdef _OPENMP
+    nthreads = omp_get_max_threads();
+#endif
+    if (n < 65536) nthreads = 1;
+    int32_t *chunk_end = (int32_t *)calloc((size_t)nthreads * W, sizeof(int32_t));
+    int32_t *carry = (int32_t *)calloc((size_t)nthreads * W, sizeof(int32_t));
+    int64_t *first_flag = (int64_t *)malloc(sizeof(int64_t) * nthreads);
+#pragma omp parallel num_threads(nthreads)
+    {
+        int t = 0;
+#ifdef _OPENMP
+        t = omp_get_thread_num();
+#endif
+        const int64_t lo = n * t / nthreads, hi = n * (t + 1) / nthreads;
+        int32_t acc[W], item[W];
+        memset(acc, 0, sizeof acc);
+        int64_t ff = hi;               /* first segment start inside the chunk */
+        for (int64_t i = lo; i < hi; ++i) {
+            particle_id_t uid = user_srcntgt_ids[i];
+            int mnr = morton_nr_of_particle(d, extent_norm,
+                box_levels[srcntgt_box_ids[i]], bbox_min, bbox_max, uid, coords,
+                radii, stick_out_factor);
+            morton_nrs[i] = (morton_nr_t)mnr;
+            memset(item, 0, sizeof(int32_t) * w);
+            if (have_ext) item[0] = (mnr == -1);
             for (int m = 0; m < nb; ++m) {
-                acc[off + m] = acc[off + m] + item[off + m];
-                acc[off + nb + m] = add_sat_i32(acc[off + nb + m], item[off + nb + m]);
+                item[off + m] = (mnr == m);
+                item[off + nb + m] = (mnr == m) ? refine_weights[uid] : 0;
+            }
+            const int seg = (i == 0 || box_start_flags[i]);
+            if (seg && ff == hi) ff = i;
+            if (seg || i == lo) {
+                memcpy(acc, item, sizeof(int32_t) * w);
+            } else { /* scan_t_add, :277-302 */
+                if (have_ext) acc[0] += item[0];
+                for (int m = 0; m < nb; ++m) {
+                    acc[off + m] = acc[off + m] + item[off + m];
+                    acc[off + nb + m] = add_sat_i32(acc[off + nb + m], item[off + nb + m]);
+                }
+            }
+            memcpy(morton_bin_counts + i * w, acc, sizeof(int32_t) * w);
+        }
+        first_flag[t] = ff;
+        memcpy(chunk_end + (size_t)t * W, acc, sizeof(int32_t) * w);
+#pragma omp barrier
+#pragma omp single
+        {
+            /* carry[t]: scan value just before chunk t, within the segment open at its start */
+            for (int c = 1; c < nthreads; ++c) {
+                const int64_t clo = n * (c - 1) / nthreads, chi = n * c / nthreads;
+                if (chi == clo) { memcpy(carry + (size_t)c * W, carry + (size_t)(c - 1) * W, sizeof(int32_t) * w); continue; }
+                int32_t *dst = carry + (size_t)c * W;
+                memcpy(dst, chunk_end + (size_t)(c - 1) * W, sizeof(int32_t) * w);
+                if (first_flag[c - 1] == chi) {     /* no segment start in chunk c-1: chain */
+                    const int32_t *pc = carry + (size_t)(c - 1) * W;
+                    if (have_ext) dst[0] += pc[0];
+                    for (int m = 0; m < nb; ++m) {
+                        dst[off + m] += pc[off + m];
+                        dst[off + nb + m] = add_sat_i32(dst[off + nb + m], pc[off + nb + m]);
+                    }
+                }
             }
         }
-        /* output statement, :480-508 */
-        particle_id_t my_id_in_my_box = -1;
-        for (int k = 0; k < off + nb; ++k) my_id_in_my_box += acc[k];
-        memcpy(morton_bin_counts + i * w, acc, sizeof(int32_t) * w);
-        box_id_t cur = srcntgt_box_ids[i];
-        if (my_id_in_my_box + 1 == box_srcntgt_counts_cumul[cur])
-            memcpy(box_morton_bin_counts + (int64_t)cur * w, acc, sizeof(int32_t) * w);
+        /* (implicit barrier after single) */
+        const int32_t *cin = carry + (size_t)t * W;
+        for (int64_t i = lo; i < hi; ++i) {
+            int32_t *a = morton_bin_counts + i * w;
+            if (t > 0 && i < ff) {
+                if (have_ext) a[0] += cin[0];
+                for (int m = 0; m < nb; ++m) {
+                    a[off + m] += cin[off + m];
+                    a[off + nb + m] = add_sat_i32(a[off + nb + m], cin[off + nb + m]);
+                }
+            }
+            /* output statement, :480-508 */
+            particle_id_t my_id_in_my_box = -1;
+            for (int k = 0; k < off + nb; ++k) my_id_in_my_box += a[k];
+            box_id_t cur = srcntgt_box_ids[i];
+            if (my_id_in_my_box + 1 == box_srcntgt_counts_cumul[cur])
+                memcpy(box_morton_bin_counts + (int64_t)cur * w, a, sizeof(int32_t) * w);
+        }
     }
+    free(chunk_end); free(carry); free(first_flag);
 }
 
 /* split_box_id_scan -- tree_build_kernels.py:514-640; tree_build.py:740-759
@@ -300,6 +364,8 @@ void orc_particle_renumberer(
     particle_id_t *new_user_srcntgt_ids, box_id_t *new_srcntgt_box_ids)
 {
     const int w = mbc_width(d, have_extent), nb = 1 << d, off = have_extent ? 1 : 0;
+    /* independent work items (every particle writes its own destination) */
+#pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; ++i) {
         box_id_t ibox = srcntgt_box_ids[i];
         int do_split = (box_has_children[ibox] && box_levels[ibox] + 1 == level);
@@ -352,6 +418,9 @@ void orc_level_restrict(
 {
     const int nb = 1 << d;
     enum { MAXLEV = 128 };
+    /* work items only write their own box_force_split entry and read those of the level below
+       (set by the previous launch of the sweep): independent, like the OpenCL kernel */
+#pragma omp parallel for schedule(dynamic, 1024)
     for (int64_t bi = slice_start; bi < slice_start + slice_count; ++bi) {
         box_id_t box_id = (box_id_t)bi;
         if (box_has_children[box_id]) continue;
@@ -380,6 +449,7 @@ void orc_level_restrict(
                         if (child_level == 2 + level ||
                             (child_level == 1 + level && box_force_split[child])) {
                             box_force_split[box_id] = 1;
+#pragma omp atomic
                             *have_upper_level_split_box |= 1;
                             cont = 0;
                         }
@@ -460,6 +530,7 @@ void orc_source_and_target_index_finder(
     particle_id_t *box_target_starts, particle_id_t *box_target_counts_cumul,
     particle_id_t *box_source_counts_nonchild, particle_id_t *box_target_counts_nonchild)
 {
+#pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; ++i) {
         particle_id_t sorted_id = (particle_id_t)i;
         particle_id_t source_nr = source_numbers[i];
@@ -569,6 +640,7 @@ void orc_box_extents(
     coord_t *bbox_min /* [d, aligned] */, coord_t *bbox_max)
 {
     const int nb = 1 << d;
+#pragma omp parallel for schedule(dynamic, 256)
     for (int64_t ibox = start; ibox < stop; ++ibox) {
         coord_t mn[MAXDIM], mx[MAXDIM];
         for (int a = 0; a < d; ++a) mn[a] = mx[a] = box_centers[a * aligned_nboxes + ibox];
