@@ -94,13 +94,15 @@ _i, _i64, _d = C.c_int, C.c_int64, C.c_double
 _P = C.POINTER
 SIGNATURES = {
     "bt_max_key_level": [_i],
+    "bt_max_tree_level": [_i],
     "bt_bounding_box": [_i, _i, _P(bt_particles), vp, vp],
-    "bt_make_keys": [_i, _i, _P(bt_particles), _P(_d), _P(_d), _i, _d, _i, vp, vp, vp],
+    "bt_make_keys": [_i, _i, _P(bt_particles), _P(_d), _P(_d), _i, _d, _i, vp, vp, vp, vp],
+    "bt_sort_particles_deep": [_i64, _i, _i, vp, vp, vp, vp, vp, vp, vp],
     "bt_sort_particles": [_i64, _i, _i, _i, vp, vp, vp, vp, _P(_i), vp],
     "bt_weight_prefix": [_i64, vp, vp, vp, vp],
     "bt_pool_init": [_i, _i, _P(bt_pool), _i64, _i, vp, _P(_d), vp, vp],
     "bt_level_step": [_i, _i, _P(bt_pool), vp, vp, vp, vp, vp, _i, _i, _i, _i, _i, _i, _i, _i,
-                      _d, _i, _i, vp],
+                      _d, _i, _i, vp, vp],
     "bt_level_restrict": [_i, _i, _P(bt_pool), vp, _i, _i, _d, vp],
     "bt_finalize_numbering": [_i, _i, _P(bt_pool), _i, _i, _i, vp, vp, vp, vp, vp],
     "bt_gather_boxes": [_i, _i, _P(bt_pool), _i, vp, vp, _i, _i, _P(bt_box_out), vp],

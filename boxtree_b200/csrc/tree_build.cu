@@ -136,9 +136,12 @@ template <typename T> struct BBox { T mn[3]; T mx[3]; };
 
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256)
-make_keys_kernel(Particles<T, DIM> P, BBox<T> bb, int extent_norm, T stick_out_factor, int D,
-                 int points_never_stop, unsigned long long* __restrict__ keys, T* __restrict__ records)
+make_keys_kernel(Particles<T, DIM> P, BBox<T> bb, int extent_norm, T stick_out_factor, int D, int Dh,
+                 int points_never_stop, unsigned long long* __restrict__ keys,
+                 unsigned long long* __restrict__ keys_lo, T* __restrict__ records)
 {
+    // D levels in total; `keys` resolves the first Dh of them, `keys_lo` (two-word keys, only for
+    // trees deeper than one word holds) levels Dh+1..D.  One word: Dh == D, keys_lo == nullptr.
     // records (optional): the particle's coordinates and radius side by side (4 values), so
     // that the later gather into tree order (bt_permute) reads ONE aligned 16/32-byte record per
     // particle instead of one 32-byte sector per coordinate
@@ -209,16 +212,19 @@ make_keys_kernel(Particles<T, DIM> P, BBox<T> bb, int extent_norm, T stick_out_f
                 if (st) { stop = (unsigned)lev; break; }
             }
         }
-        unsigned long long digits = 0;
+        unsigned long long digits = 0, digits_lo = 0;
         const int maxlev = (stop < (unsigned)D) ? (int)stop : D;
         for (int lev = 1; lev <= maxlev; ++lev) {
             unsigned dg = 0;
 #pragma unroll
             for (int a = 0; a < DIM; ++a)
                 dg |= (unsigned)((q[a] >> (D - lev)) & 1ull) << (DIM - 1 - a);
-            digits |= (unsigned long long)dg << ((D - lev) * DIM);
+            if (lev <= Dh) digits |= (unsigned long long)dg << ((Dh - lev) * DIM);
+            else digits_lo |= (unsigned long long)dg << ((D - lev) * DIM);
         }
-        keys[i] = (digits << kStopBits) | stop;
+        // a particle that stops below the first word's levels does not stop inside them
+        keys[i] = (digits << kStopBits) | ((stop <= (unsigned)Dh) ? stop : kStopNever);
+        if (keys_lo) keys_lo[i] = (digits_lo << kStopBits) | stop;
     }
 }
 
@@ -322,7 +328,8 @@ struct DecideOut {
 // box splitter -- restates boxtree/tree_build_kernels.py:646-711 on the pool
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256)
-create_children_kernel(Pool<T, DIM> pool, const unsigned long long* __restrict__ keys,
+create_children_kernel(Pool<T, DIM> pool, const unsigned long long* __restrict__ keys_hi,
+                       const unsigned long long* __restrict__ keys_lo, int Dlo,
                        const long long* __restrict__ wprefix, const int* __restrict__ split_list,
                        int* __restrict__ ctl, int capacity, int D, int have_ext, int maxw,
                        int skip_if_no_regular, T root_extent)
@@ -342,14 +349,18 @@ create_children_kernel(Pool<T, DIM> pool, const unsigned long long* __restrict__
         const bool active = tid < total;
         const int r = (int)(tid / NB), m = (int)(tid % NB);
         int lb = 0, hi = 0, b = 0, lev = 0;
+        // the key word that resolves the new level (two-word keys: levels above D are in keys_lo)
+        const unsigned long long* keys = keys_hi;
+        int Dw = D, lev_off = 0;
         if (active) {
             b = split_list[r];
             lev = pool.level[b];
+            if (keys_lo && lev + 1 > D) { keys = keys_lo; Dw = Dlo; lev_off = D; }
             const int a = pool.start[b], c = pool.count[b];
             const int lo = a + pool.nn[b];
             hi = a + c;
             // first index in [lo, hi) whose level-(lev+1) digit is >= m
-            const int sh = key_shift(DIM, D, lev + 1);
+            const int sh = key_shift(DIM, Dw, lev + 1 - lev_off);
             int l = lo, h = hi;
             if (m == 0 || c == 0) h = l;
             while (l < h) {
@@ -375,7 +386,7 @@ create_children_kernel(Pool<T, DIM> pool, const unsigned long long* __restrict__
         pool.force_split[child] = 0;
         int nn = 0;
         if (have_ext && cnt > 0) {
-            const int shc = key_shift(DIM, D, new_level);
+            const int shc = key_shift(DIM, Dw, new_level - lev_off);
             const unsigned long long kc = ((keys[lb] >> shc) << shc) | (unsigned long long)new_level;
             nn = upper_bound_key(keys, lb, lb_next, kc) - lb;
         }
@@ -1090,8 +1101,8 @@ static int bbox_impl(const bt_particles* p, void* out, cudaStream_t s)
 
 template <typename T, int DIM>
 static int make_keys_impl(const bt_particles* p, const double* bmin, const double* bmax,
-                          int extent_norm, double stick_out, int D, unsigned long long* keys,
-                          void* records, cudaStream_t s)
+                          int extent_norm, double stick_out, int D, int Dh, unsigned long long* keys,
+                          unsigned long long* keys_lo, void* records, cudaStream_t s)
 {
     Particles<T, DIM> P = make_particles<T, DIM>(p);
     BBox<T> bb;
@@ -1115,8 +1126,9 @@ static int make_keys_impl(const bt_particles* p, const double* bmin, const doubl
         const double margin = (double)(T)stick_out * min_ext / (double)(1ull << (D + 1));
         points_never_stop = (min_ext > 0 && margin > 64.0 * eps * M) ? 1 : 0;
     }
-    make_keys_kernel<T, DIM><<<grid_for(P.n, 256, 8), 256, 0, s>>>(P, bb, extent_norm, (T)stick_out, D,
-                                                                  points_never_stop, keys, (T*)records);
+    make_keys_kernel<T, DIM><<<grid_for(P.n, 256, 8), 256, 0, s>>>(P, bb, extent_norm, (T)stick_out, D, Dh,
+                                                                  points_never_stop, keys, keys_lo,
+                                                                  (T*)records);
     BT_LAUNCH_CHECK();
     return BT_OK;
 }
@@ -1134,7 +1146,8 @@ static int pool_init_impl(const bt_pool* pool, int64_t n, int have_ext, const un
 }
 
 template <typename T, int DIM>
-static int level_step_impl(const bt_pool* pool, const unsigned long long* keys, const long long* wprefix,
+static int level_step_impl(const bt_pool* pool, const unsigned long long* keys,
+                           const unsigned long long* keys_lo, int depth_lo, const long long* wprefix,
                            int* ctl, int* split_list, unsigned char* flag, int lo, int nboxes_host,
                            int level, int max_key_level, int maxw, int adaptive, int level_restrict,
                            int have_ext, int skip_if_no_regular, double root_extent, int phases,
@@ -1155,8 +1168,8 @@ static int level_step_impl(const bt_pool* pool, const unsigned long long* keys, 
     const int64_t max_threads = (int64_t)(nboxes_host - lo) * (1 << DIM);
     if (create) {
         create_children_kernel<T, DIM><<<grid_for(max_threads, 256, 8), 256, 0, s>>>(
-            P, keys, wprefix, split_list, ctl, pool->capacity, max_key_level, have_ext, maxw,
-            skip_if_no_regular, (T)root_extent);
+            P, keys, keys_lo, depth_lo, wprefix, split_list, ctl, pool->capacity, max_key_level, have_ext,
+            maxw, skip_if_no_regular, (T)root_extent);
         BT_LAUNCH_CHECK();
     }
     if (commit) {
@@ -1345,13 +1358,19 @@ static int key_depth(int dim, int depth)
     return (depth > 0 && depth < dmax) ? depth : dmax;
 }
 
+int bt_max_tree_level(int dim) { (void)dim; return 31; }
+
 int bt_make_keys(int dtype, int dim, const bt_particles* p, const double* bbox_min, const double* bbox_max,
-                 int extent_norm, double stick_out_factor, int depth, uint64_t* keys, void* records,
-                 void* stream)
+                 int extent_norm, double stick_out_factor, int depth, uint64_t* keys, uint64_t* keys_lo,
+                 void* records, void* stream)
 {
     BT_PROF("bt_make_keys", (cudaStream_t)stream);
-    BT_DISPATCH(dtype, dim, make_keys_impl, p, bbox_min, bbox_max, extent_norm, stick_out_factor,
-                key_depth(dim, depth), (unsigned long long*)keys, records, (cudaStream_t)stream);
+    // two-word keys: `keys` holds all the levels one word can, keys_lo the rest up to level 31
+    const int Dh = keys_lo ? bt_max_key_level(dim) : key_depth(dim, depth);
+    const int D = keys_lo ? bt_max_tree_level(dim) : Dh;
+    if (keys_lo && D <= Dh) return BT_ERR_BAD_ARG;
+    BT_DISPATCH(dtype, dim, make_keys_impl, p, bbox_min, bbox_max, extent_norm, stick_out_factor, D, Dh,
+                (unsigned long long*)keys, (unsigned long long*)keys_lo, records, (cudaStream_t)stream);
 }
 
 int bt_sort_particles(int64_t n, int dim, int have_extent, int depth, uint64_t* keys, uint64_t* keys_alt,
@@ -1363,6 +1382,56 @@ int bt_sort_particles(int64_t n, int dim, int have_extent, int depth, uint64_t* 
     const int end_bit = bt::kStopBits + D * dim;
     return bt::radix_sort_pairs(n, (unsigned long long*)keys, (unsigned long long*)keys_alt, ids, ids_alt,
                                 1, begin_bit, end_bit, result_in_alt, (cudaStream_t)stream);
+}
+
+namespace bt {
+__global__ void gather_u64_kernel(int64_t n, const unsigned long long* __restrict__ src,
+                                  const unsigned* __restrict__ idx, unsigned long long* __restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = src[idx[i]];
+}
+}  // namespace bt
+
+// Stable sort by the two-word key (keys, keys_lo): LSD over the low word, then over the high
+// word.  On return ids / keys / keys_lo hold the sorted order (no ping-pong flag); *_tmp are
+// scratch of the same sizes.
+int bt_sort_particles_deep(int64_t n, int dim, int have_extent, uint64_t* keys, uint64_t* keys_tmp,
+                           uint64_t* keys_lo, uint64_t* keys_lo_tmp, uint32_t* ids, uint32_t* ids_tmp,
+                           void* stream)
+{
+    BT_PROF("bt_sort_particles", (cudaStream_t)stream);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n <= 0) return BT_OK;
+    typedef unsigned long long u64;
+    const int Dh = bt_max_key_level(dim), Dl = bt_max_tree_level(dim) - Dh;
+    if (Dl <= 0) return BT_ERR_BAD_ARG;
+    const int grid = bt::grid_for(n, 256, 8);
+    // 1. ids ordered by the low word (a copy of it is sorted, the original is gathered from later)
+    BT_CHECK(cudaMemcpyAsync(keys_lo_tmp, keys_lo, sizeof(u64) * n, cudaMemcpyDeviceToDevice, s));
+    u64* scratch = nullptr;
+    BT_CHECK(bt::temp_alloc((void**)&scratch, sizeof(u64) * n, s));
+    int in_alt = 0;
+    BT_TRY(bt::radix_sort_pairs(n, (u64*)keys_lo_tmp, scratch, ids, ids_tmp, 1, have_extent ? 0 : bt::kStopBits,
+                                bt::kStopBits + Dl * dim, &in_alt, s));
+    uint32_t* ids1 = in_alt ? ids_tmp : ids;
+    uint32_t* ids1_alt = in_alt ? ids : ids_tmp;
+    // 2. the high words in that order, 3. stable sort by them (ids ride along)
+    bt::gather_u64_kernel<<<grid, 256, 0, s>>>(n, (const u64*)keys, ids1, (u64*)keys_tmp);
+    BT_LAUNCH_CHECK();
+    int in_alt2 = 0;
+    BT_TRY(bt::radix_sort_pairs(n, (u64*)keys_tmp, scratch, ids1, ids1_alt, 0, have_extent ? 0 : bt::kStopBits,
+                                bt::kStopBits + Dh * dim, &in_alt2, s));
+    const uint32_t* ids2 = in_alt2 ? ids1_alt : ids1;
+    const u64* hi_sorted = in_alt2 ? scratch : (u64*)keys_tmp;
+    // 4. results into the caller's primary buffers
+    bt::gather_u64_kernel<<<grid, 256, 0, s>>>(n, (const u64*)keys_lo, ids2, (u64*)keys_lo_tmp);
+    BT_LAUNCH_CHECK();
+    BT_CHECK(cudaMemcpyAsync(keys_lo, keys_lo_tmp, sizeof(u64) * n, cudaMemcpyDeviceToDevice, s));
+    BT_CHECK(cudaMemcpyAsync(keys, hi_sorted, sizeof(u64) * n, cudaMemcpyDeviceToDevice, s));
+    if (ids2 != ids) BT_CHECK(cudaMemcpyAsync(ids, ids2, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, s));
+    BT_CHECK(cudaFreeAsync(scratch, s));
+    return BT_OK;
 }
 
 int bt_weight_prefix(int64_t n, const uint32_t* sorted_ids, const int32_t* weights, int64_t* wprefix,
@@ -1385,12 +1454,14 @@ int bt_pool_init(int dtype, int dim, const bt_pool* pool, int64_t n, int have_ex
 int bt_level_step(int dtype, int dim, const bt_pool* pool, const uint64_t* keys, const int64_t* wprefix,
                   int32_t* ctl, int32_t* split_list, uint8_t* flag, int lo, int nboxes, int level,
                   int maxw, int adaptive, int level_restrict, int have_extent, int skip_if_no_regular,
-                  double root_extent, int phases, int depth, void* stream)
+                  double root_extent, int phases, int depth, const uint64_t* keys_lo, void* stream)
 {
     BT_PROF("bt_level_step", (cudaStream_t)stream);
+    const int Dh = keys_lo ? bt_max_key_level(dim) : key_depth(dim, depth);
     BT_DISPATCH(dtype, dim, level_step_impl, pool, (const unsigned long long*)keys,
+                (const unsigned long long*)keys_lo, keys_lo ? bt_max_tree_level(dim) - Dh : 0,
                 (const long long*)wprefix, ctl, split_list, flag, lo, nboxes, level,
-                key_depth(dim, depth), maxw, adaptive, level_restrict, have_extent, skip_if_no_regular,
+                Dh, maxw, adaptive, level_restrict, have_extent, skip_if_no_regular,
                 root_extent, phases, (cudaStream_t)stream);
 }
 

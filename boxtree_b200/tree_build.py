@@ -360,26 +360,42 @@ class TreeBuilder:
             first_depth = int(kwargs.get("_key_depth", 0)) or min(max_key_level, est + 6)
             # x, y, z, radius of every particle side by side for the gather into tree order
             records = actx.empty(4 * max(nsrcntgts, 1), coord_dtype)
-            for key_depth in ([first_depth, max_key_level] if first_depth < max_key_level
-                              else [max_key_level]):
+            # ... and two-word keys beyond that, up to level 31, the deepest level the reference's
+            # digit expression `1U << (1 + level)` resolves (deeper: MaxLevelsExceeded in both)
+            max_tree_level = int(lib.bt_max_tree_level(dimensions))
+            depth_tries = ([first_depth] if first_depth < max_key_level else []) + [max_key_level]
+            if max_tree_level > max_key_level:
+                depth_tries.append(max_tree_level)
+            if kwargs.get("_key_depth") == -1:          # testing: two-word keys right away
+                depth_tries = [max_tree_level]
+            for key_depth in depth_tries:
                 too_deep = False
+                deep = key_depth > max_key_level
                 # {{{ keys + sort
 
                 key_bufs = [actx.empty(nsrcntgts, np.int64), actx.empty(nsrcntgts, np.int64)]
                 id_bufs = [actx.empty(nsrcntgts, np.int32), actx.empty(nsrcntgts, np.int32)]
+                lo_bufs = [actx.empty(nsrcntgts, np.int64), actx.empty(nsrcntgts, np.int64)] \
+                    if deep else [None, None]
                 check(lib.bt_make_keys(dcode, dimensions, C.byref(P), _cabi.darray(bbox_min),
                                        _cabi.darray(bbox_max), EXTENT_NORM_CODE[srcntgts_extent_norm],
                                        float(stick_out_factor), key_depth, dptr(key_bufs[0]),
-                                       dptr(records), sh), "bt_make_keys")
+                                       dptr(lo_bufs[0]), dptr(records), sh), "bt_make_keys")
                 in_alt = C.c_int(0)
-                if nsrcntgts:
+                if nsrcntgts and deep:
+                    check(lib.bt_sort_particles_deep(
+                        nsrcntgts, dimensions, have_ext, dptr(key_bufs[0]), dptr(key_bufs[1]),
+                        dptr(lo_bufs[0]), dptr(lo_bufs[1]), dptr(id_bufs[0]), dptr(id_bufs[1]), sh),
+                        "bt_sort_particles_deep")
+                elif nsrcntgts:
                     check(lib.bt_sort_particles(nsrcntgts, dimensions, have_ext, key_depth,
                                                 dptr(key_bufs[0]),
                                                 dptr(key_bufs[1]), dptr(id_bufs[0]), dptr(id_bufs[1]),
                                                 C.byref(in_alt), sh), "bt_sort_particles")
                 keys = key_bufs[in_alt.value]
                 ids = id_bufs[in_alt.value]
-                del key_bufs, id_bufs
+                keys_lo = lo_bufs[0]
+                del key_bufs, id_bufs, lo_bufs
 
                 wprefix = None
                 if refine_weights is not None:
@@ -424,11 +440,11 @@ class TreeBuilder:
 
                 while level:
                     niterations += 1
-                    if level > key_depth and key_depth < max_key_level \
+                    if level > key_depth and key_depth < depth_tries[-1] \
                             and level + 1 < nlevels_max:
                         too_deep = True         # deeper than the key resolves: sort again
                         break
-                    if level + 1 >= nlevels_max or level > max_key_level:
+                    if level + 1 >= nlevels_max or level > key_depth:
                         raise MaxLevelsExceeded(
                             "Level count exceeded number of significant "
                             "bits in coordinate dtype. That means that a large number "
@@ -452,8 +468,8 @@ class TreeBuilder:
                             dcode, dimensions, C.byref(pool.struct()), dptr(keys), dptr(wprefix),
                             dptr(ctl), dptr(pool.split_list), dptr(pool.flag), lo, nboxes, level,
                             max_leaf_refine_weight, int(adaptive), int(level_restrict), have_ext,
-                            skip_if_no_regular, float(root_extent), phases, key_depth, sh),
-                              "bt_level_step")
+                            skip_if_no_regular, float(root_extent), phases,
+                            min(key_depth, max_key_level), dptr(keys_lo), sh), "bt_level_step")
                         if phases & STEP_COMMIT and level_restrict \
                                 and not final_level_restrict_iteration:
                             check(lib.bt_level_restrict(dcode, dimensions, C.byref(pool.struct()),
@@ -506,7 +522,7 @@ class TreeBuilder:
 
                 if not too_deep:
                     break
-                del keys, ids, pool
+                del keys, ids, pool, keys_lo
 
             nlevels = level + 1
 

@@ -108,8 +108,12 @@ int bt_prof_report(char *buf, int len);   /* "name\tcalls\ttotal_ms" lines */
 void bt_set_walk_mode(int mode);
 int bt_get_walk_mode(void);
 
-/* deepest level the 64-bit sort key resolves for `dim` (MaxLevelsExceeded above) */
+/* deepest level ONE 64-bit sort key resolves for `dim`; deeper trees use two-word keys
+ * (keys_lo below) up to bt_max_tree_level = 31, the deepest level the reference's
+ * `1U << (1 + level)` digit expression (tree_build_kernels.py:374-376) can resolve:
+ * beyond it both raise MaxLevelsExceeded */
 int bt_max_key_level(int dim);
+int bt_max_tree_level(int dim);
 
 /* bounding_box.py:54-122 (BBOX_REDUCTION_TPL).  out_minmax: [2*dim] coords,
  * laid out min_x, max_x, min_y, max_y, ... like make_bounding_box_dtype (:35-52) */
@@ -118,11 +122,13 @@ int bt_bounding_box(int dtype, int dim, const bt_particles *p, void *out_minmax,
 /* Digit computation of morton_scan (tree_build_kernels.py:308-470) for all levels
  * at once.  bbox_min/bbox_max are HOST arrays [dim].  extent_norm: 0 none, 1 linf, 2 l2.
  * depth: levels the key resolves (0 or >= bt_max_key_level(dim): all it can hold); a tree that
- * turns out deeper must be rebuilt with a larger depth.  records (optional, [n][4] coords):
- * x, y, z, radius of every particle side by side for bt_permute. */
+ * turns out deeper must be rebuilt with a larger depth.  keys_lo (optional): two-word keys --
+ * `keys` then resolves bt_max_key_level(dim) levels and keys_lo the levels above, up to
+ * bt_max_tree_level(dim) (depth is ignored).  records (optional, [n][4] coords): x, y, z,
+ * radius of every particle side by side for bt_permute. */
 int bt_make_keys(int dtype, int dim, const bt_particles *p, const double *bbox_min,
                  const double *bbox_max, int extent_norm, double stick_out_factor, int depth,
-                 uint64_t *keys, void *records, void *stream);
+                 uint64_t *keys, uint64_t *keys_lo, void *records, void *stream);
 
 /* Stable radix sort of (key, particle id); replaces the per-level partition
  * morton_scan + renumber_particles (tree_build_kernels.py:247-508, 717-819).
@@ -131,6 +137,12 @@ int bt_make_keys(int dtype, int dim, const bt_particles *p, const double *bbox_m
 int bt_sort_particles(int64_t n, int dim, int have_extent, int depth, uint64_t *keys,
                       uint64_t *keys_alt, uint32_t *ids, uint32_t *ids_alt, int *result_in_alt,
                       void *stream);
+
+/* the same for two-word keys: on return keys, keys_lo and ids are in sorted order (the *_tmp
+ * arrays are scratch of the same sizes) */
+int bt_sort_particles_deep(int64_t n, int dim, int have_extent, uint64_t *keys, uint64_t *keys_tmp,
+                           uint64_t *keys_lo, uint64_t *keys_lo_tmp, uint32_t *ids,
+                           uint32_t *ids_tmp, void *stream);
 
 /* refine weights in sorted order -> exclusive int64 prefix, wprefix[n] = total
  * (the pwt fields of the morton_scan struct, tree_build_kernels.py:462-466) */
@@ -155,7 +167,7 @@ int bt_level_step(int dtype, int dim, const bt_pool *pool, const uint64_t *keys,
                   const int64_t *wprefix, int32_t *ctl, int32_t *split_list, uint8_t *flag, int lo,
                   int nboxes, int level, int maxw, int adaptive, int level_restrict,
                   int have_extent, int skip_if_no_regular, double root_extent, int phases,
-                  int depth, void *stream);
+                  int depth, const uint64_t *keys_lo, void *stream);
 
 /* level_restrict kernel + upper-level sweep (tree_build_kernels.py:825-915,
  * tree_build.py:1145-1200); the sweep's early exit is a device-side flag chain. */

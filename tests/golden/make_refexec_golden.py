@@ -81,10 +81,15 @@ def run_one(job):
 
 
 def main():
-    nprocs = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    nprocs = int(args[0]) if args else 8
     from tests.gpu_sweep import make_cases
     jobs = [(quick, i) for quick in (True, False) for i in range(len(make_cases(quick)))]
     digests = {}
+    if "--missing" in sys.argv:         # only the cases the committed file does not hold yet
+        with open(os.path.join(HERE, "refexec_digests.json")) as f:
+            digests = json.load(f)
+        jobs = [(q, i) for q, i in jobs if case_key(make_cases(q)[i], q) not in digests]
     with ProcessPoolExecutor(nprocs) as pool:
         for n, (key, entry, arrays) in enumerate(pool.map(run_one, jobs)):
             digests[key] = entry

@@ -85,6 +85,13 @@ def make_cases(quick=False):
             cases.append(dict(base, name="all-at-origin", n=11, at_origin=True,
                               tree={"max_particles_in_box": 10}, expect_max_levels=True))
             if dims > 1:
+                # a tight cluster next to a sparse cloud: the tree is deeper than ONE 64-bit sort
+                # key resolves (19 levels in 3-D, 28 in 2-D) -- two-word keys, up to the level 31
+                # that the reference's `1U << (1 + level)` digits reach
+                for kind in ("adaptive", "adaptive-level-restricted"):
+                    cases.append(dict(base, name="deep-cluster" + ("-lr" if "restricted" in kind else ""),
+                                      n=60, deep_cluster=22 if dims == 3 else 27,
+                                      tree={"max_particles_in_box": 4, "kind": kind}))
                 # test_same_tree_with_zero_weight_particles (test/test_tree.py:1050-1097): targets
                 # with weight 0 and radii up to the domain size, stick-out factors 0 .. 1
                 for sof in (0, 0.1, 0.3, 1):
@@ -110,6 +117,11 @@ def make_inputs(case):
         kw = dict(case["tree"], targets=[t.astype(dt) for t in targets],
                   target_radii=radii.astype(dt), refine_weights=weights)
         return [s.astype(dt) for s in sources], kw
+    if case.get("deep_cluster"):
+        rng = np.random.default_rng(7)
+        pts = rng.random((dims, n))
+        pts[:, n // 2:] *= 2.0 ** -case["deep_cluster"]
+        return [np.ascontiguousarray(pts[a]).astype(dt) for a in range(dims)], dict(case["tree"])
     if case.get("coincident"):
         # 11 coincident points (> max_particles_in_box) and one distinct point so the
         # bounding box is not degenerate: both implementations must give up

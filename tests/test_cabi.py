@@ -37,6 +37,7 @@ def test_no_compute_entry_point_is_a_stub():
     from boxtree_b200 import _cabi
     assert _cabi.load().bt_max_key_level(3) == 19
     assert _cabi.load().bt_max_key_level(2) == 28
+    assert _cabi.load().bt_max_tree_level(3) == 31
     assert _cabi.launch_count() == 0
 
 

@@ -128,6 +128,38 @@ def _build(actx, src, tkw, vkw):
     return tree, trav
 
 
+@pytest.mark.parametrize("name", ["config1_2d_1e4", "config3_3d_1e5", "config4_plummer_1e5_f32",
+                                  "normal_3d_f32_2away"])
+@pytest.mark.parametrize("key_depth", [-1, 3, 9])
+def test_key_depth_does_not_change_the_tree(actx, name, key_depth):
+    """The sort key may resolve fewer levels than the tree needs at first (the build retries with
+    more) or be a two-word key right away (``_key_depth=-1``, what trees deeper than 19 / 28
+    levels use): every tree array must still have the digest of the reference's own run."""
+    want = json.load(open(os.path.join(GOLDEN, "digests.json")))[name]
+    src, tkw, vkw = digest_cases()[name]
+    tree, trav = _build(actx, src, dict(tkw, _key_depth=key_depth), vkw)
+    got = {k: digest(v) for k, v in flatten(actx.to_numpy(tree), actx.to_numpy(trav)).items()}
+    assert got == want
+
+
+def test_lr_overflow_retry_keeps_the_split_list(actx):
+    """Level-restricted build whose splits exceed the pool (negative ``_lr_slack``): the
+    retry after CTL_OVERFLOW repeats the child creation with the split list of the decide scan,
+    which must survive the pool's reallocation."""
+    from boxtree_b200 import TreeBuilder
+    from oracle.tree_build import build_tree
+    from tests.parity_util import tree_mismatches
+    src, tgt, radii = config3_inputs(20000, 20000)
+    kw = dict(max_particles_in_box=30, stick_out_factor=0.25, extent_norm="linf",
+              kind="adaptive-level-restricted")
+    tb = TreeBuilder(actx)
+    tree, _ = tb(actx, [actx.from_numpy(x) for x in src], targets=[actx.from_numpy(x) for x in tgt],
+                 target_radii=actx.from_numpy(radii), _lr_slack=-10**7, nboxes_guess=2, **kw)
+    assert tb.last_stats["reallocs"] > 0
+    ref = build_tree(src, targets=tgt, target_radii=radii, **kw)
+    assert not tree_mismatches(ref, actx.to_numpy(tree))
+
+
 def test_golden_config1(actx):
     src, tkw, vkw = digest_cases()["config1_2d_1e4"]
     tree, trav = _build(actx, src, tkw, vkw)
