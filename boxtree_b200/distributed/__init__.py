@@ -139,7 +139,7 @@ def sharded_setup(actx, tree, traversal_builder, comm, cost_per_box=None,
         cost_per_box = (1.0 + tree.box_source_counts_nonchild.double()
                         + tree.box_target_counts_nonchild.double())
     dfs_order = get_box_ids_dfs_order(actx, tree)
-    with torch.cuda.stream(actx.stream):
+    with torch.cuda.stream(actx.stream), torch.cuda.device(actx.device):
         segs = partition_segments_device(actx, cost_per_box, dfs_order, size)
     if segs is None:      # general float costs: the reference's sequential accumulation, on the host
         cost_host = cost_per_box.cpu().numpy() if isinstance(cost_per_box, torch.Tensor) \
@@ -202,7 +202,8 @@ def distributed_tree_setup(actx, dtree, traversal_builder, comm, cost_per_box=No
         if segs is None:
             cost_host = cost_per_box.cpu().numpy() if isinstance(cost_per_box, torch.Tensor) \
                 else np.asarray(cost_per_box)
-            segs = partition_segments(cost_host[dfs_order.cpu().numpy()], size)
+            segs = partition_segments(cost_host[dfs_order.cpu().numpy()], size,
+                                      total_workload=np.sum(cost_host))
         seg = segs[rank]
         responsible = dfs_order[int(seg[0]):int(seg[1])]
         resp_mask, anc_mask = _responsible_and_ancestors(actx, lib, dtree, responsible)

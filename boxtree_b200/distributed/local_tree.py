@@ -87,7 +87,7 @@ def generate_local_tree(actx, global_traversal, responsible_boxes_list, comm,
     gt = global_traversal.tree
     nb = int(gt.nboxes)
     dims = int(gt.dimensions)
-    with torch.cuda.stream(actx.stream):
+    with torch.cuda.stream(actx.stream), torch.cuda.device(actx.device):
         masks = box_masks if box_masks is not None else \
             get_box_masks(actx, global_traversal, responsible_boxes_list)
         src = _local_particles_and_lists(

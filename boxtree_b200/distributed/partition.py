@@ -16,7 +16,7 @@ def get_box_ids_dfs_order(actx, tree):
     reference pops a stack).  Computed on the device; returns a device int32 tensor."""
     lib = _cabi.load()
     nboxes = int(tree.nboxes)
-    with torch.cuda.stream(actx.stream):
+    with torch.cuda.stream(actx.stream), torch.cuda.device(actx.device):
         child_ids = _dev(actx, tree.box_child_ids)
         ls = _dev(actx, tree.level_start_box_nrs).to(torch.int32)
         size = actx.empty(max(nboxes, 1), np.int32)
@@ -35,7 +35,7 @@ def _dev(actx, a):
     return a.contiguous()
 
 
-def partition_segments(cost_in_dfs_order, mpi_size):
+def partition_segments(cost_in_dfs_order, mpi_size, total_workload=None):
     """The root-rank loop of ``partition.py:81-116`` on the costs already arranged in DFS
     order: returns the ``(mpi_size, 2)`` int32 array of ``[start, end)`` DFS positions.
 
@@ -43,7 +43,10 @@ def partition_segments(cost_in_dfs_order, mpi_size):
     ``workload_count += cost``; the thresholds use the reference's expression."""
     cost = np.asarray(cost_in_dfs_order)
     nboxes = len(cost)
-    total_workload = np.sum(cost)
+    if total_workload is None:
+        # callers with non-integer costs pass np.sum over the costs in BOX order, the
+        # reference's summation order (partition.py:95; pairwise sums depend on the order)
+        total_workload = np.sum(cost)
     segments = np.empty((mpi_size, 2), dtype=np.int32)
     cum = np.cumsum(cost)                       # sequential, like the += loop
     monotone = bool(np.all(cost >= 0))
@@ -111,7 +114,7 @@ def partition_work(actx, cost_per_box, traversal, comm):
     if mpi_rank == 0:
         cost = np.asarray(actx.to_numpy(cost_per_box) if isinstance(cost_per_box, torch.Tensor)
                           else cost_per_box)
-        segments = partition_segments(cost[dfs_order], mpi_size)
+        segments = partition_segments(cost[dfs_order], mpi_size, total_workload=np.sum(cost))
     mine = comm.scatter_rows(segments, root=0)
     return dfs_order[int(mine[0]):int(mine[1])]
 
@@ -188,7 +191,7 @@ def _masks_from_traversal(actx, lib, traversal, responsible, ancestors, into=Non
 def get_box_masks(actx, traversal, responsible_boxes_list) -> BoxMasks:
     """``partition.py:330-357``."""
     lib = _cabi.load()
-    with torch.cuda.stream(actx.stream):
+    with torch.cuda.stream(actx.stream), torch.cuda.device(actx.device):
         responsible, ancestors = _responsible_and_ancestors(actx, lib, traversal.tree,
                                                             responsible_boxes_list)
         return _masks_from_traversal(actx, lib, traversal, responsible, ancestors)
@@ -205,7 +208,7 @@ def get_box_masks_sharded(actx, tree, responsible_boxes_list, traversal_builder)
     import dataclasses
     lib = _cabi.load()
     nb = int(tree.nboxes)
-    with torch.cuda.stream(actx.stream):
+    with torch.cuda.stream(actx.stream), torch.cuda.device(actx.device):
         responsible, ancestors = _responsible_and_ancestors(actx, lib, tree, responsible_boxes_list)
         flags = actx.empty(nb, np.uint8)
         need = actx.empty(nb, np.int8)

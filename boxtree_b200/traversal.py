@@ -335,7 +335,8 @@ class FMMTraversalBuilder:
                 if segs is None:
                     cost_host = cost_per_box.cpu().numpy() if isinstance(
                         cost_per_box, torch.Tensor) else np.asarray(cost_per_box)
-                    segs = partition_segments(cost_host[dfs_order.cpu().numpy()], n)
+                    segs = partition_segments(cost_host[dfs_order.cpu().numpy()], n,
+                                              total_workload=np.sum(cost_host))
                 out = []
                 self.last_shared = None
                 for k in range(n):
@@ -421,6 +422,12 @@ class FMMTraversalBuilder:
             if isinstance(a, np.ndarray):
                 a = actx.from_numpy(np.ascontiguousarray(a if dt is None else a.astype(dt)))
             return a.contiguous()
+
+        for dep in (wait_for or ()):          # traversal.py:1969-1990
+            if isinstance(dep, torch.cuda.Stream):
+                stream.wait_stream(dep)
+            else:
+                stream.wait_event(dep)
 
         with torch.cuda.stream(stream), torch.cuda.device(actx.device):
             box_flags = dev(dev_tree.box_flags)

@@ -291,6 +291,13 @@ class TreeBuilder:
         have_ext = int(srcntgts_have_extent)
         nb = 2**dimensions
 
+        # wait_for (tree_build.py:193, 229): events (or streams) that produced the inputs
+        for dep in (wait_for or ()):
+            if isinstance(dep, torch.cuda.Stream):
+                stream.wait_stream(dep)
+            else:
+                stream.wait_event(dep)
+
         with torch.cuda.stream(stream), torch.cuda.device(actx.device):
             mark("start")
             # {{{ particle view (virtual concatenation, tree_build.py:328-388)
@@ -331,12 +338,19 @@ class TreeBuilder:
             else:
                 if not isinstance(bbox, np.ndarray):
                     raise NotImplementedError(f"unsupported bounding box type: {type(bbox)}")
-                assert len(bbox) == dimensions
+                # [dimensions][2] (min, max) rows, or the length-1 structured array with fields
+                # min_x, max_x, ... that the reference's bounding box finder returns
+                # (tree_build.py:479-488, bounding_box.py:35-52)
+                structured = bbox.dtype.names is not None
+                if not structured:
+                    assert len(bbox) == dimensions
+                else:
+                    assert len(bbox) == 1
                 bbox_min = np.empty(dimensions, coord_dtype)
                 bbox_max = np.empty(dimensions, coord_dtype)
-                for i in range(dimensions):
-                    bbox_min[i] = bbox[i][0]
-                    bbox_max[i] = bbox[i][1]
+                for i, ax in enumerate("xyz"[:dimensions]):
+                    bbox_min[i] = bbox[f"min_{ax}"][0] if structured else bbox[i][0]
+                    bbox_max[i] = bbox[f"max_{ax}"][0] if structured else bbox[i][1]
                     assert bbox_min[i] < bbox_max[i]
                     assert bbox_min[i] <= auto_min[i]
                     assert bbox_max[i] >= auto_max[i]

@@ -564,3 +564,25 @@ def test_error_behaviour(actx):
     src = [actx.from_numpy(s) for s in normal_particles(100, 2, np.float64)]
     with pytest.warns(DeprecationWarning):
         tb(actx, src, max_particles_in_box=10, allocator=object())
+
+
+def test_structured_bbox_and_wait_for(actx):
+    """The bounding box in the reference's structured form (tree_build.py:479-488) and inputs
+    produced on another stream handed over through ``wait_for``."""
+    import torch
+    from boxtree_b200 import TreeBuilder
+    from tests.parity_util import tree_mismatches
+    from oracle.tree_build import build_tree
+    src = normal_particles(20000, 3, np.float64)
+    lo, hi = -7.5, 8.5
+    sb = np.empty(1, np.dtype([(f"{m}_{ax}", np.float64) for ax in "xyz" for m in ("min", "max")]))
+    for ax in "xyz":
+        sb[f"min_{ax}"], sb[f"max_{ax}"] = lo, hi
+    side = torch.cuda.Stream(device=actx.device)
+    with torch.cuda.stream(side):
+        dsrc = [torch.from_numpy(s).to(actx.device, non_blocking=True) * 1.0 for s in src]
+        ev = torch.cuda.Event()
+        ev.record(side)
+    tree, _ = TreeBuilder(actx)(actx, dsrc, max_particles_in_box=30, bbox=sb, wait_for=[ev])
+    ref = build_tree(src, max_particles_in_box=30, bbox=np.array([[lo, hi]] * 3))
+    assert not tree_mismatches(ref, actx.to_numpy(tree))
