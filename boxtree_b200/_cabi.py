@@ -137,6 +137,20 @@ SIGNATURES = {
     "bt_trav_merge_lists": [_i, _i, vp, _i, _P(vp), _P(vp), vp, vp, vp, vp],
     "bt_area_query": [_i, _i, _P(bt_tree_view), vp, vp, _i, _P(vp), vp, _P(_d), vp, vp, vp, vp],
     "bt_gather_i32": [_i64, vp, vp, vp, vp],
+    "bt_csr_row_sums": [_i, _i, vp, vp, vp, vp, vp, _i, _d, vp],
+    "bt_range_sums_i64": [_i, vp, vp, vp, vp, vp],
+    "bt_add_to_ranges_i64": [_i, vp, vp, vp, vp, vp, vp],
+    "bt_fmm_upward_i64": [_i, _i, vp, vp, _i, vp, vp],
+    "bt_fmm_downward_i64": [_i, vp, vp, vp, vp],
+    "bt_gather_i64": [_i64, vp, vp, vp, vp],
+    "bt_gather_coords": [_i, _i64, vp, vp, vp, vp],
+    "bt_widen_i32": [_i, _i64, vp, vp, vp],
+    "bt_filter_targets_user_order": [_i, _i, vp, vp, vp, vp, vp, vp, vp, vp],
+    "bt_filter_targets_tree_order": [_i, _i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    "bt_link_point_sources": [_i, _i, _i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    "bt_translation_classes": [_i, _i, _i, vp, vp, vp, vp, _i, vp, _d, _i, _i, _i, _i64, vp, vp, vp,
+                               vp],
+    "bt_remap_classes": [_i64, vp, vp, vp],
     "bt_dist_dfs_order": [_i, _i, _i, _i, vp, vp, vp, vp, vp, vp],
     "bt_dist_mask_from_list": [_i, vp, vp, vp],
     "bt_dist_ancestor_mask": [_i, vp, vp, vp, vp],

@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libboxtree_b200.so")
-SOURCES = ["tree_build.cu", "traversal.cu", "distributed.cu"]
+SOURCES = ["tree_build.cu", "traversal.cu", "distributed.cu", "consumers.cu"]
 HEADERS = ["common.cuh", "scan.cuh", "radix_sort.cuh", os.path.join("..", "..", "include", "boxtree_b200.h")]
 
 NVCC_FLAGS = [

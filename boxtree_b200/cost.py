@@ -110,10 +110,17 @@ def make_taylor_translation_cost_model(dim, nlevels):
 
 
 def _row_sums(starts, lists, values):
-    v = values[lists.long()]
-    cs = torch.cat([torch.zeros(1, dtype=values.dtype, device=values.device), torch.cumsum(v, 0)])
-    st = starts.long()
-    return cs[st[1:]] - cs[st[:-1]]
+    """``out[i] = sum(values[lists[starts[i]:starts[i+1]]])`` (``bt_csr_row_sums``, float64)."""
+    from . import _cabi
+    from ._cabi import check, dptr
+    nrows = int(starts.shape[0]) - 1
+    out = torch.zeros(max(nrows, 1), dtype=torch.float64, device=values.device)
+    values = values.to(torch.float64).contiguous()
+    check(_cabi.load().bt_csr_row_sums(1, nrows, dptr(starts.contiguous()), dptr(lists.contiguous()),
+                                       dptr(values), None, dptr(out), 0, 1.0,
+                                       torch.cuda.current_stream(values.device).cuda_stream),
+          "bt_csr_row_sums")
+    return out[:nrows]
 
 
 class FMMCostModel:

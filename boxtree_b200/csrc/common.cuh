@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #define BT_OK 0
 #define BT_ERR_BAD_ARG 10001
@@ -53,7 +54,13 @@ static inline cudaError_t temp_alloc(void** p, size_t bytes, cudaStream_t s)
     if (cudaGetDevice(&dev) == cudaSuccess && !((configured_devices >> (dev & 63)) & 1ull)) {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            unsigned long long thr = 2ull << 30;
+            // scratch kept across synchronisations: 8 GiB unless BT_MEMPOOL_KEEP_GB says otherwise
+            // (0 = everything)
+            unsigned long long thr = 8ull << 30;
+            if (const char* e = getenv("BT_MEMPOOL_KEEP_GB")) {
+                const long long gb = atoll(e);
+                thr = gb > 0 ? (unsigned long long)gb << 30 : ~0ull;
+            }
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
         }
         configured_devices |= 1ull << (dev & 63);

@@ -36,43 +36,51 @@ def link_point_sources(actx, tree, point_source_starts, point_sources, *, debug=
     assert isinstance(actx, TorchArrayContext)
     if not tree.sources_have_extent:
         raise ValueError("only allowed on trees whose sources have extent")
-    with torch.cuda.stream(actx.stream):
-        dev = tree.box_flags.device
+    from . import _cabi
+    from ._cabi import check, dptr
+    lib = _cabi.load()
+    sh = actx.stream_handle
+    with torch.cuda.stream(actx.stream), torch.cuda.device(actx.device):
         nboxes, nsources = int(tree.nboxes), int(tree.nsources)
         pss = point_source_starts
-        pss = (actx.from_numpy(pss) if isinstance(pss, np.ndarray) else pss).long()
-        usi = tree.user_source_ids.long()
-        # POINT_SOURCE_LINKING_SOURCE_SCAN_TPL (:1872-1897)
-        cnt = pss[usi + 1] - pss[usi]
-        incl = torch.cumsum(cnt, 0)
-        tree_order_starts = incl - cnt
-        npoint_sources = int(incl[-1].item()) if nsources else 0
-        # multi_put + segmented scan (:1899-1911, tree.py:838-890): within the segment of tree-order
-        # source i the ids count up from that source's first point source in user order
-        seg_first = pss[usi] - tree_order_starts
-        user_point_source_ids = (torch.repeat_interleave(seg_first, cnt, output_size=npoint_sources)
-                                 + torch.arange(npoint_sources, device=dev)).to(torch.int32)
+        pss = (actx.from_numpy(pss) if isinstance(pss, np.ndarray) else pss).to(torch.int32).contiguous()
+        tree_order_starts = actx.empty(nsources + 1, np.int32)
+        cnt = actx.empty(max(nsources, 1), np.int32)
+        total = actx.zeros(1, np.int32)
+        ps_start = actx.empty(nboxes, np.int32)
+        ps_nonchild = actx.empty(nboxes, np.int32)
+        ps_cumul = actx.empty(nboxes, np.int32)
+
+        def call(phase, ids):
+            # POINT_SOURCE_LINKING_SOURCE_SCAN_TPL (:1872-1897), then multi_put + segmented scan
+            # (:1899-1911, tree.py:838-890) and POINT_SOURCE_LINKING_BOX_POINT_SOURCES (:1913-1950)
+            check(lib.bt_link_point_sources(
+                phase, nboxes, nsources, dptr(pss), dptr(tree.user_source_ids),
+                dptr(tree_order_starts), dptr(cnt), dptr(total), dptr(ids),
+                dptr(tree.box_source_starts), dptr(tree.box_source_counts_nonchild),
+                dptr(tree.box_source_counts_cumul), dptr(ps_start), dptr(ps_nonchild),
+                dptr(ps_cumul), sh), "bt_link_point_sources")
+
+        call(0, None)
+        npoint_sources = int(total.item()) if nsources else 0
+        user_point_source_ids = actx.empty(npoint_sources, np.int32)
+        call(1, user_point_source_ids)
         pts = [actx.from_numpy(p) if isinstance(p, np.ndarray) else p for p in point_sources]
-        tree_order_point_sources = make_obj_array([p[user_point_source_ids.long()] for p in pts])
-        # POINT_SOURCE_LINKING_BOX_POINT_SOURCES (:1913-1950)
-        s_start = tree.box_source_starts[:nboxes].long()
-        tos = torch.cat([tree_order_starts, incl[-1:] if nsources else torch.zeros(1, dtype=torch.long, device=dev)])
-        ps_start = tos[s_start.clamp(max=nsources)]
-
-        def counts(s_count):
-            s_count = s_count[:nboxes].long()
-            last = (s_start + s_count - 1).clamp(min=0, max=max(nsources - 1, 0))
-            beyond = tree_order_starts[last] + cnt[last]
-            return torch.where(s_count == 0, torch.zeros_like(beyond), beyond - ps_start).to(torch.int32)
-
+        dcode = _cabi.dtype_code(tree.coord_dtype)
+        tops = []
+        for p in pts:
+            o = actx.empty(npoint_sources, tree.coord_dtype)
+            check(lib.bt_gather_coords(dcode, npoint_sources, dptr(p.contiguous()),
+                                       dptr(user_point_source_ids), dptr(o), sh), "bt_gather_coords")
+            tops.append(o)
         extra = dict(
             npoint_sources=npoint_sources,
-            point_source_starts=tree_order_starts.to(torch.int32),
-            point_source_counts=cnt.to(torch.int32),
-            point_sources=tree_order_point_sources,
+            point_source_starts=tree_order_starts[:nsources],
+            point_source_counts=cnt[:nsources],
+            point_sources=make_obj_array(tops),
             user_point_source_ids=user_point_source_ids,
-            box_point_source_starts=ps_start.to(torch.int32),
-            box_point_source_counts_nonchild=counts(tree.box_source_counts_nonchild),
-            box_point_source_counts_cumul=counts(tree.box_source_counts_cumul))
+            box_point_source_starts=ps_start,
+            box_point_source_counts_nonchild=ps_nonchild,
+            box_point_source_counts_cumul=ps_cumul)
     base = {f.name: getattr(tree, f.name) for f in fields(Tree)}
     return actx.freeze(TreeWithLinkedPointSources(**base, **extra))

@@ -71,37 +71,29 @@ class TranslationClassesBuilder:
         if not nper <= 1 + np.iinfo(np.int32).max:
             raise ValueError("would overflow")
         ncls = nper * (int(tree.nlevels) if is_translation_per_level else 1)
-        with torch.cuda.stream(actx.stream):
-            starts = trav.from_sep_siblings_starts.long()
-            src = trav.from_sep_siblings_lists.long()
-            dev = src.device
+        from . import _cabi
+        from ._cabi import check, dptr
+        lib = _cabi.load()
+        with torch.cuda.stream(actx.stream), torch.cuda.device(actx.device):
+            starts = trav.from_sep_siblings_starts
+            src = trav.from_sep_siblings_lists
             npairs = int(src.shape[0])
-            rows = torch.repeat_interleave(torch.arange(starts.shape[0] - 1, device=dev),
-                                           starts[1:] - starts[:-1], output_size=npairs)
-            tgt = trav.target_or_target_parent_boxes.long()[rows]
-            lev = tree.box_levels.long()
-            bad = lev[src] != lev[tgt]
-            cdt = tree.box_centers.dtype
-            # LEVEL_TO_RAD(level) = root_extent * 1 / (coord_t)(1 << (level + 1)); diam = 2 * rad
-            root_extent = torch.tensor(float(tree.root_extent), dtype=cdt, device=dev)
-            diam = 2 * (root_extent * 1 / (2 ** (lev[src] + 1)).to(cdt))
-            cls = torch.zeros(npairs, dtype=torch.int64, device=dev)
-            mult = 1
-            bound = 2 * n + 1
-            for a in range(dims):
-                vec = torch.round((tree.box_centers[a][tgt] - tree.box_centers[a][src]) / diam).long()
-                bad = bad | (vec < -bound) | (vec > bound)
-                cls = cls + (bound + vec) * mult
-                mult *= 4 * n + 3
-            if is_translation_per_level:
-                cls = cls + lev[src] * nper
-            if bool(bad.any()):
+            nrows = int(starts.shape[0]) - 1
+            cls = actx.empty(max(npairs, 1), np.int32)
+            used = actx.zeros(ncls, np.int32)
+            err = actx.zeros(1, np.int32)
+            check(lib.bt_translation_classes(
+                _cabi.dtype_code(tree.coord_dtype), dims, nrows,
+                dptr(trav.target_or_target_parent_boxes), dptr(starts), dptr(src),
+                dptr(tree.box_centers), int(tree.aligned_nboxes), dptr(tree.box_levels),
+                float(tree.root_extent), n, int(bool(is_translation_per_level)), nper, npairs,
+                dptr(cls), dptr(used), dptr(err), actx.stream_handle), "bt_translation_classes")
+            if int(err.item()):
                 raise ValueError("could not compute translation classes")
-            used = torch.zeros(ncls, dtype=torch.int32, device=dev)
-            used[cls] = 1
+            cls = cls[:npairs]
             evt = torch.cuda.Event()
             evt.record(actx.stream)
-        return evt, used, cls.to(torch.int32)
+        return evt, used, cls
 
     def __call__(self, actx, trav, tree, wait_for=None, is_translation_per_level=True):
         """``translation_classes.py:368-436``: ``(TranslationClassesInfo, event)``."""
@@ -135,8 +127,13 @@ class TranslationClassesBuilder:
         if not is_translation_per_level:
             level_starts[1:] = count          # one level's worth of classes: the loop sets entry 0 only
         level_starts[nlevels] = count
-        with torch.cuda.stream(actx.stream):
-            cls_lists = actx.from_numpy(used_map)[cls_lists.long()]
+        with torch.cuda.stream(actx.stream), torch.cuda.device(actx.device):
+            from . import _cabi
+            from ._cabi import check, dptr
+            used_map_dev = actx.from_numpy(used_map)
+            check(_cabi.load().bt_remap_classes(int(cls_lists.shape[0]), dptr(used_map_dev),
+                                                dptr(cls_lists), actx.stream_handle),
+                  "bt_remap_classes")
             info = TranslationClassesInfo(
                 traversal=trav, from_sep_siblings_translation_classes=cls_lists,
                 from_sep_siblings_translation_class_to_distance_vector=actx.from_numpy(distances),

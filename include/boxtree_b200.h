@@ -572,6 +572,67 @@ int bt_dist_box_to_user_rank_bits(int phase, int nboxes, int nranks, int bitsel,
                                   const int8_t *masks_all_ranks, int32_t *starts, int32_t *lists,
                                   int64_t *total_dev, void *stream);
 
+/* ------------------------------------------- consumers of Tree / FMMTraversalInfo (rows N1, N2, N4)
+ * bt_csr_row_sums: out[out_index ? out_index[i] : i] (+)= scale * sum of values[lists[k]] over row i
+ *   -- every translation of the constant-one FMM (boxtree/constant_one.py:104-237: p2p, m2l, m2p,
+ *   p2l are additions over an interaction list) and the per-box segmented sums of the cost model
+ *   (boxtree/cost.py:445-525, 715-1262).  value_kind: 0 int64, 1 float64.
+ * bt_range_sums_i64: out[b] = sum of values[starts[b] .. + counts[b]) (form_multipoles,
+ *   constant_one.py:104-116); bt_add_to_ranges_i64: pot[j] += vals[i] over the own range of
+ *   boxes[i] (the eval_* steps); bt_fmm_upward_i64 / bt_fmm_downward_i64: one level of
+ *   coarsen_multipoles / refine_locals (constant_one.py:118-152, 208-224).
+ * bt_gather_i64 / bt_gather_coords: out[i] = src[idx[i]] (reorder_sources / reorder_potentials,
+ *   fmm.py:370-374, 525-528; cl_array.take); bt_widen_i32: int32 -> int64 / float64. */
+int bt_csr_row_sums(int value_kind, int nrows, const int32_t *starts, const int32_t *lists,
+                    const void *values, const int32_t *out_index, void *out, int accumulate,
+                    double scale, void *stream);
+int bt_range_sums_i64(int n, const int32_t *starts, const int32_t *counts, const int64_t *values,
+                      int64_t *out, void *stream);
+int bt_add_to_ranges_i64(int nrows, const int32_t *boxes, const int64_t *vals, const int32_t *starts,
+                         const int32_t *counts, int64_t *pot, void *stream);
+int bt_fmm_upward_i64(int dim, int nrows, const int32_t *boxes, const int32_t *box_child_ids,
+                      int aligned_nboxes, int64_t *mpoles, void *stream);
+int bt_fmm_downward_i64(int nrows, const int32_t *boxes, const int32_t *box_parent_ids,
+                        int64_t *local, void *stream);
+int bt_gather_i64(int64_t n, const int64_t *src, const int32_t *idx, int64_t *out, void *stream);
+int bt_gather_coords(int dtype, int64_t n, const void *src, const int32_t *idx, void *out,
+                     void *stream);
+int bt_widen_i32(int value_kind, int64_t n, const int32_t *src, void *out, void *stream);
+/* ParticleListFilter (boxtree/tree.py:1057-1239): user order = ListOfListsBuilder over boxes
+ * (phase 0: counts -> starts + total, phase 1: lists); tree order = TREE_ORDER_TARGET_FILTER_*
+ * (tree_build_kernels.py:1954-2021).  user_target_ids[tree position] = user id;
+ * flags_user: int8 [ntargets] in user order. */
+int bt_filter_targets_user_order(int phase, int nboxes, const int32_t *box_target_starts,
+                                 const int32_t *box_target_counts_nonchild,
+                                 const int32_t *user_target_ids, const int8_t *flags_user,
+                                 int32_t *starts, int32_t *lists, int64_t *total_dev, void *stream);
+int bt_filter_targets_tree_order(int nboxes, int64_t ntargets, const int32_t *box_target_starts,
+                                 const int32_t *box_target_counts_nonchild,
+                                 const int32_t *user_target_ids, const int8_t *flags_user,
+                                 int32_t *filtered_from_unfiltered, int32_t *unfiltered_from_filtered,
+                                 int32_t *nfiltered_dev, int32_t *filtered_starts,
+                                 int32_t *filtered_counts, void *stream);
+/* link_point_sources (boxtree/tree.py:773-955, POINT_SOURCE_LINKING_* of
+ * tree_build_kernels.py:1872-1950).  phase 0: tree-order starts/counts + total (device);
+ * phase 1: user ids of the point sources in tree order and the per-box ranges. */
+int bt_link_point_sources(int phase, int nboxes, int64_t nsources,
+                          const int32_t *point_source_starts_user, const int32_t *user_source_ids,
+                          int32_t *tree_order_starts, int32_t *point_source_counts,
+                          int32_t *npoint_sources_dev, int32_t *user_point_source_ids,
+                          const int32_t *box_source_starts, const int32_t *box_source_counts_nonchild,
+                          const int32_t *box_source_counts_cumul, int32_t *box_ps_starts,
+                          int32_t *box_ps_nonchild, int32_t *box_ps_cumul, void *stream);
+/* TRANSLATION_CLASS_FINDER_TEMPLATE (boxtree/translation_classes.py:60-196): the class of every
+ * from_sep_siblings entry, used[class] = 1, *error_dev = 1 where the reference raises;
+ * bt_remap_classes: classes[i] = used_map[classes[i]] (:424-426). */
+int bt_translation_classes(int dtype, int dim, int nrows, const int32_t *row_boxes,
+                           const int32_t *starts, const int32_t *lists, const void *box_centers,
+                           int aligned_nboxes, const uint8_t *box_levels, double root_extent,
+                           int well_sep_is_n_away, int per_level, int nclasses_per_level,
+                           int64_t npairs, int32_t *classes, int32_t *used, int32_t *error_dev,
+                           void *stream);
+int bt_remap_classes(int64_t n, const int32_t *used_map, int32_t *classes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,7 +5,7 @@
 set -u
 TAG=${1:-r01}; SPEC=${2:-config3:10000000}
 REGEX=${3:-'list13_coop|coll_topdown|list2_warp|rs_onesweep|box_extents|permute_kernel|make_keys'}
-COUNT=${4:-24}
+COUNT=${4:-60}
 NAME=$(echo "$SPEC" | tr ':' '_')
 mkdir -p gpurun_out
 # (1) every launch of ONE warm step (tests/ncu_driver.py brackets it with cudaProfilerStart/Stop)
