@@ -440,6 +440,14 @@ coll_topdown_kernel(TreeView<T, DIM> t, const int* __restrict__ level_start, int
             for (int a = 0; a < DIM; ++a) bcen[lane][a] = t.centers[t.aligned * a + bch];
         }
         const unsigned rowm = __ballot_sync(0xffffffffu, brow) & nbmask;
+        if (!rowm) {        // no child's row is wanted: only the flags the walks read of ANY box
+            if (bch) {
+                counts[bch] = 0;
+                if (l2cnt) l2cnt[bch] = 0;
+                xflags[bch] = bxf;
+            }
+            continue;
+        }
         const int level = lev;
         const int np = counts[p];
         const int* prow = tmp + (int64_t)p * stride;
@@ -527,17 +535,23 @@ coll_topdown_kernel(TreeView<T, DIM> t, const int* __restrict__ level_start, int
     }
 }
 
-// staged rows -> CSR lists
+// staged rows -> CSR lists: one lane per box (most rows are empty when a row mask is in use),
+// the lanes of a warp copy their rows side by side
 __global__ void __launch_bounds__(256)
 coll_compact_kernel(int nboxes, int stride, const int* __restrict__ tmp, const int* __restrict__ starts,
                     int* __restrict__ lists)
 {
-    const int64_t total = (int64_t)nboxes * stride;
-    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gstride) {
-        const int b = (int)(i / stride), j = (int)(i % stride);
-        const int s = starts[b];
-        if (j < starts[b + 1] - s) lists[s + j] = tmp[i];
+    const int gstride = gridDim.x * blockDim.x;
+    for (int b0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); b0 < nboxes; b0 += gstride) {
+        const int b = b0 + (threadIdx.x & 31);
+        int s = 0, n = 0;
+        if (b < nboxes) { s = starts[b]; n = starts[b + 1] - s; }
+        int nmax = n;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const int y = __shfl_xor_sync(0xffffffffu, nmax, o); nmax = y > nmax ? y : nmax; }
+        const int* row = tmp + (int64_t)b * stride;
+        for (int j = 0; j < nmax; ++j)
+            if (j < n) lists[s + j] = row[j];
     }
 }
 
@@ -597,8 +611,8 @@ static int colleagues_topdown_impl(int phase, const bt_tree_view* tv, const int*
         }
         BT_TRY(counts_to_starts(starts, t.nboxes, totals, s));
     } else {
-        coll_compact_kernel<<<grid_for((int64_t)t.nboxes * stride, 256, 8), 256, 0, s>>>(t.nboxes, stride, tmp,
-                                                                                        starts, lists);
+        coll_compact_kernel<<<grid_for((int64_t)t.nboxes, 256, 8), 256, 0, s>>>(t.nboxes, stride, tmp,
+                                                                               starts, lists);
         BT_LAUNCH_CHECK();
     }
     return BT_OK;

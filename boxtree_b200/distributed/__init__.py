@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from .comm import SingleProcessComm, ThreadComm, ThreadGroup, TorchDistComm
-from .exchange import _local_ranges, exchange_particles, preorder
+from .exchange import _local_ranges, exchange_particle_kinds, exchange_particles, preorder
 from .local_traversal import generate_local_travs
 from .local_tree import LocalTree, assemble_local_tree, box_to_user_rank, generate_local_tree
 from .partition import (BoxMasks, get_box_ids_dfs_order, get_box_masks, get_box_masks_sharded,
@@ -312,9 +312,10 @@ def distributed_tree_setup(actx, dtree, traversal_builder, comm, cost_per_box=No
                 | (masks.multipole_src_boxes << 2))
         allm = comm.allgather_tensor(mine)                                   # [size, nboxes]
         mark("ds:allgather masks")
-        src = exchange_particles(actx, comm, dtree, allm, 1, masks.point_src_boxes, "source", pre)
-        tgt = exchange_particles(actx, comm, dtree, allm, 2, masks.responsible_boxes, "target",
-                                 pre, ranges=tgt_ranges)
+        src, tgt = exchange_particle_kinds(
+            actx, comm, dtree, allm,
+            [(1, masks.point_src_boxes, "source", None),
+             (2, masks.responsible_boxes, "target", tgt_ranges)], pre)
         mark("ds:exchange")
         local_tree = assemble_local_tree(actx, dtree, src, tgt, masks, allm, responsible, bitsel=4)
         local_travs = [dataclasses.replace(t, tree=local_tree) for t in local_travs]

@@ -55,6 +55,93 @@ def _local_ranges(actx, lib, nb, mask, own_counts, pre):
     return lstarts, lnonchild, lcumul
 
 
+class _Exchange:
+    """One particle kind's exchange in three steps -- count, pack + all-to-all, unpack -- so that
+    several kinds can share the one small all-gather + readback of the chunk sizes."""
+
+    def __init__(self, actx, comm, dtree, masks_all_ranks, bitsel, my_mask, kind, pre, ranges):
+        self.actx, self.comm, self.dtree = actx, comm, dtree
+        self.lib = _cabi.load()
+        self.sh = actx.stream_handle
+        self.nb = int(dtree.nboxes)
+        self.dims = int(dtree.dimensions)
+        self.nranks, self.rank = comm.Get_size(), comm.Get_rank()
+        self.dcode = _cabi.dtype_code(dtree.coord_dtype)
+        src = kind == "source"
+        self.parts = list(dtree.sources if src else dtree.targets)
+        self.have_radii = dtree.sources_have_extent if src else dtree.targets_have_extent
+        self.radii = (dtree.source_radii if src else dtree.target_radii) if self.have_radii else None
+        self.lstart = dtree.local_box_source_starts if src else dtree.local_box_target_starts
+        self.lown = dtree.local_box_source_counts_nonchild if src else \
+            dtree.local_box_target_counts_nonchild
+        self.gstart = dtree.box_source_starts if src else dtree.box_target_starts
+        self.gown = dtree.box_source_counts_nonchild if src else dtree.box_target_counts_nonchild
+        self.recbytes = _record_bytes(dtree.coord_dtype, self.dims, self.have_radii)
+        self.my_mask, self.pre, self.ranges = my_mask, pre, ranges
+        self.masks_all_ranks, self.bitsel = masks_all_ranks, bitsel
+
+    def count(self):
+        """Records per destination (device): ``[nranks + 2]`` int64 = chunk offsets, number of
+        boxes of my mask."""
+        actx, lib, sh, nb, nranks = self.actx, self.lib, self.sh, self.nb, self.nranks
+        self.dest_bits = actx.empty(max(nb, 1), np.int32)
+        check(lib.bt_dist_mask_bits(nb, nranks, self.bitsel, dptr(self.masks_all_ranks),
+                                    dptr(self.dest_bits), sh), "bt_dist_mask_bits")
+        n = self.n = int(self.parts[0].shape[0])
+        ntiles = max(int(lib.bt_dist_pack_ntiles(n)), 1)
+        self.pbox = actx.empty(max(n, 1), np.int32)
+        tile_counts = actx.empty(nranks * ntiles, np.int32)
+        self.tile_offs = actx.empty(nranks * ntiles, np.int64)
+        dest_offsets = actx.empty(nranks + 2, np.int64)
+        check(lib.bt_dist_pack_count(nranks, nb, n, dptr(self.dest_bits), dptr(self.lstart),
+                                     dptr(self.lown), dptr(self.pbox), dptr(tile_counts),
+                                     dptr(self.tile_offs), dptr(dest_offsets), sh),
+              "bt_dist_pack_count")
+        self.compact = actx.empty(max(nb, 1), np.int32)
+        nmasked_dev = actx.empty(1, np.int32)
+        check(lib.bt_dist_compact_index(nb, dptr(self.my_mask), dptr(self.compact),
+                                        dptr(nmasked_dev), sh), "bt_dist_compact_index")
+        dest_offsets[nranks + 1:].copy_(nmasked_dev)
+        return dest_offsets
+
+    def send(self, gathered):
+        """*gathered* ``[sender, nranks + 2]`` (host): pack and post the all-to-all."""
+        import ctypes as C
+        actx, lib, sh, nranks, rank = self.actx, self.lib, self.sh, self.nranks, self.rank
+        counts = np.diff(gathered[:, :nranks + 1], axis=1)                  # [sender, dest]
+        self.nmasked = int(gathered[rank, nranks + 1])
+        send_counts, self.recv_counts = counts[rank], counts[:, rank]
+        nsend = int(send_counts.sum())
+        sendbuf = actx.empty(max(nsend, 1) * self.recbytes, np.uint8)
+        check(lib.bt_dist_pack_records(self.dcode, nranks, self.dims, self.n, dptr(self.pbox),
+                                       dptr(self.dest_bits), dptr(self.tile_offs),
+                                       _cabi.ptr_array(self.parts), dptr(self.radii),
+                                       dptr(self.lstart), dptr(sendbuf), sh), "bt_dist_pack_records")
+        self.recvbuf = self.comm.all_to_all_bytes(
+            sendbuf[:nsend * self.recbytes], [int(c) * self.recbytes for c in send_counts],
+            [int(c) * self.recbytes for c in self.recv_counts])
+        self.C = C
+
+    def unpack(self):
+        """The rank's local arrays (global tree order restricted to its boxes)."""
+        actx, lib, sh, nb, nranks, dtree = self.actx, self.lib, self.sh, self.nb, self.nranks, self.dtree
+        lstarts, lnonchild, lcumul = self.ranges if self.ranges is not None else \
+            _local_ranges(actx, lib, nb, self.my_mask, self.gown, self.pre)
+        nrecv = int(self.recv_counts.sum())
+        count_tmp = actx.empty(max(nranks * self.nmasked, 1), np.int32)
+        local = [actx.empty(nrecv, dtree.coord_dtype) for _ in range(self.dims)]
+        local_radii = actx.empty(nrecv, dtree.coord_dtype) if self.have_radii else None
+        idx = actx.empty(nrecv, np.int64)
+        chunk = (self.C.c_int64 * (nranks + 1))(
+            *np.concatenate([[0], np.cumsum(self.recv_counts)]).tolist())
+        check(lib.bt_dist_unpack_records(self.dcode, nranks, self.dims, nrecv, int(self.have_radii),
+                                         dptr(self.recvbuf), chunk, dptr(self.compact), self.nmasked,
+                                         dptr(count_tmp), dptr(lstarts), dptr(self.gstart),
+                                         _cabi.ptr_array(local), dptr(local_radii), dptr(idx), sh),
+              "bt_dist_unpack_records")
+        return make_obj_array(local), local_radii, lstarts, lnonchild, lcumul, idx
+
+
 def exchange_particles(actx, comm, dtree, masks_all_ranks, bitsel, my_mask, kind, pre,
                        ranges=None):
     """Collective.  *masks_all_ranks* ``[nranks, nboxes]`` int8 bit fields: rank *d* needs the
@@ -66,76 +153,17 @@ def exchange_particles(actx, comm, dtree, masks_all_ranks, bitsel, my_mask, kind
     :returns: ``(particles, radii, local_starts, local_counts_nonchild, local_counts_cumul,
         idx)`` like ``construct_local_particles_and_lists`` (``local_tree.py:198-284``); *idx*
         (int64) is every local particle's position in the global tree order."""
-    import ctypes as C
-    lib = _cabi.load()
-    sh = actx.stream_handle
-    nb = int(dtree.nboxes)
-    dims = int(dtree.dimensions)
-    nranks, rank = comm.Get_size(), comm.Get_rank()
-    dcode = _cabi.dtype_code(dtree.coord_dtype)
-    src = kind == "source"
-    parts = list(dtree.sources if src else dtree.targets)
-    have_radii = dtree.sources_have_extent if src else dtree.targets_have_extent
-    radii = (dtree.source_radii if src else dtree.target_radii) if have_radii else None
-    lstart = dtree.local_box_source_starts if src else dtree.local_box_target_starts
-    lown = dtree.local_box_source_counts_nonchild if src else \
-        dtree.local_box_target_counts_nonchild
-    gstart = dtree.box_source_starts if src else dtree.box_target_starts
-    gown = dtree.box_source_counts_nonchild if src else dtree.box_target_counts_nonchild
-    recbytes = _record_bytes(dtree.coord_dtype, dims, have_radii)
+    return exchange_particle_kinds(
+        actx, comm, dtree, masks_all_ranks, [(bitsel, my_mask, kind, ranges)], pre)[0]
 
-    # {{{ count, agree on the chunk sizes (one small all-gather + one readback), pack
 
-    dest_bits = actx.empty(max(nb, 1), np.int32)
-    check(lib.bt_dist_mask_bits(nb, nranks, bitsel, dptr(masks_all_ranks), dptr(dest_bits), sh),
-          "bt_dist_mask_bits")
-    n = int(parts[0].shape[0])
-    ntiles = max(int(lib.bt_dist_pack_ntiles(n)), 1)
-    pbox = actx.empty(max(n, 1), np.int32)
-    tile_counts = actx.empty(nranks * ntiles, np.int32)
-    tile_offs = actx.empty(nranks * ntiles, np.int64)
-    dest_offsets = actx.empty(nranks + 2, np.int64)
-    check(lib.bt_dist_pack_count(nranks, nb, n, dptr(dest_bits), dptr(lstart), dptr(lown),
-                                 dptr(pbox), dptr(tile_counts), dptr(tile_offs),
-                                 dptr(dest_offsets), sh), "bt_dist_pack_count")
-    # number of boxes of my mask rides along with the offsets (one readback for both)
-    compact = actx.empty(max(nb, 1), np.int32)
-    nmasked_dev = actx.empty(1, np.int32)
-    check(lib.bt_dist_compact_index(nb, dptr(my_mask), dptr(compact), dptr(nmasked_dev), sh),
-          "bt_dist_compact_index")
-    dest_offsets[nranks + 1:].copy_(nmasked_dev)
-    gathered = comm.allgather_tensor(dest_offsets).cpu().numpy()         # [sender, dest + 2]
-    counts, nmasked = np.diff(gathered[:, :nranks + 1], axis=1), int(gathered[rank, nranks + 1])
-    send_counts = counts[rank]
-    recv_counts = counts[:, rank]
-    nsend = int(send_counts.sum())
-    sendbuf = actx.empty(max(nsend, 1) * recbytes, np.uint8)
-    check(lib.bt_dist_pack_records(dcode, nranks, dims, n, dptr(pbox), dptr(dest_bits),
-                                   dptr(tile_offs), _cabi.ptr_array(parts), dptr(radii),
-                                   dptr(lstart), dptr(sendbuf), sh), "bt_dist_pack_records")
-
-    # }}}
-
-    nrecv = int(recv_counts.sum())
-    recvbuf = comm.all_to_all_bytes(sendbuf[:nsend * recbytes],
-                                    [int(c) * recbytes for c in send_counts],
-                                    [int(c) * recbytes for c in recv_counts])
-
-    # {{{ unpack into the rank's local arrays (global tree order restricted to its boxes)
-
-    lstarts, lnonchild, lcumul = ranges if ranges is not None else \
-        _local_ranges(actx, lib, nb, my_mask, gown, pre)
-    count_tmp = actx.empty(max(nranks * nmasked, 1), np.int32)
-    coord_dtype = dtree.coord_dtype
-    local = [actx.empty(nrecv, coord_dtype) for _ in range(dims)]
-    local_radii = actx.empty(nrecv, coord_dtype) if have_radii else None
-    idx = actx.empty(nrecv, np.int64)
-    chunk = (C.c_int64 * (nranks + 1))(*np.concatenate([[0], np.cumsum(recv_counts)]).tolist())
-    check(lib.bt_dist_unpack_records(dcode, nranks, dims, nrecv, int(have_radii), dptr(recvbuf),
-                                     chunk, dptr(compact), nmasked, dptr(count_tmp), dptr(lstarts),
-                                     dptr(gstart), _cabi.ptr_array(local), dptr(local_radii),
-                                     dptr(idx), sh), "bt_dist_unpack_records")
-
-    # }}}
-
-    return make_obj_array(local), local_radii, lstarts, lnonchild, lcumul, idx
+def exchange_particle_kinds(actx, comm, dtree, masks_all_ranks, kinds, pre):
+    """Several exchanges (*kinds*: ``(bitsel, my_mask, kind, ranges)``) sharing ONE all-gather +
+    readback of the chunk sizes; the all-to-alls are posted back to back."""
+    xs = [_Exchange(actx, comm, dtree, masks_all_ranks, bitsel, my_mask, kind, pre, ranges)
+          for bitsel, my_mask, kind, ranges in kinds]
+    offs = torch.stack([x.count() for x in xs])                          # [kinds, nranks + 2]
+    gathered = comm.allgather_tensor(offs).cpu().numpy()                 # [sender, kinds, ...]
+    for k, x in enumerate(xs):
+        x.send(gathered[:, k])
+    return [x.unpack() for x in xs]

@@ -78,19 +78,16 @@ def partition_segments_device(actx, cost_per_box, dfs_order, mpi_size):
     c = cost[dfs_order.long()]
     cum = torch.cumsum(c, 0)
     nboxes = int(c.shape[0])
-    thr_host = None
     total = cum[-1]
     ok = ((c == torch.round(c)) & (c >= 0)).all() & (total < 2.0 ** 52)
-    # thresholds with the reference's expression, evaluated in float64 on the host
-    ok_total = torch.stack([ok.double(), total]).cpu().numpy()
-    if not ok_total[0]:
+    # thresholds with the reference's expression ((k + 1) * total / size, IEEE float64 on the
+    # device as on the host) and ONE readback: [qualifies, cut positions...]
+    ks = torch.arange(1, mpi_size, dtype=torch.float64, device=cum.device)
+    hits = torch.searchsorted(cum, ks * total / mpi_size, right=True)
+    packed = torch.cat([ok.to(torch.int64).view(1), hits.to(torch.int64)]).cpu().numpy()
+    if not packed[0]:
         return None
-    total_workload = np.float64(ok_total[1])
-    thr_host = np.array([(k + 1) * total_workload / mpi_size for k in range(mpi_size - 1)], np.float64)
-    if mpi_size > 1:
-        hits = torch.searchsorted(cum, actx.from_numpy(thr_host), right=True).cpu().numpy()
-    else:
-        hits = np.zeros(0, np.int64)
+    hits = packed[1:]
     segments = np.empty((mpi_size, 2), dtype=np.int32)
     start = 0
     for k in range(mpi_size - 1):
