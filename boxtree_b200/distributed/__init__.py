@@ -227,6 +227,15 @@ def distributed_tree_setup(actx, dtree, traversal_builder, comm, cost_per_box=No
 
         # {{{ local traversal, then the masks from its rows + the corner rows
 
+        # a deferred build (``build_distributed_tree(defer_extents=True)``): the all-reduce of the
+        # particle extents has been running beside the partition; it is waited for where the
+        # traversal first reads the extents (after the colleague pass), at the latest below
+        pending = getattr(dtree, "pending", None)
+
+        def finish_pending():
+            if pending is not None:
+                pending.finish()
+
         def local_piece(row_mask):
             # rows of the boxes of row_mask only (None: all rows of the local traversal)
             fl = local_flags
@@ -241,7 +250,8 @@ def distributed_tree_setup(actx, dtree, traversal_builder, comm, cost_per_box=No
                 actx, dataclasses.replace(dtree, box_flags=fl),
                 source_boxes_mask=resp_mask if row_mask is None else (resp_mask & row_mask),
                 source_parent_boxes_mask=anc_mask if row_mask is None else (anc_mask & row_mask),
-                _colleague_row_mask=need, _keep_shared=prev is None, _shared=prev)[0]
+                _colleague_row_mask=need, _keep_shared=prev is None, _shared=prev,
+                _before_extents=finish_pending)[0]
 
         # one piece, or -- when a list of the rank's rows exceeds the int32 CSR range
         # (``traversal_pieces`` > 1, or on OverflowError) -- row pieces as in
@@ -273,6 +283,7 @@ def distributed_tree_setup(actx, dtree, traversal_builder, comm, cost_per_box=No
                 torch.cuda.empty_cache()
         shared = traversal_builder.last_shared
         traversal_builder.last_shared = None
+        finish_pending()
         mark("ds:local traversal")
         # every row of the local traversal is a row the masks read: its target boxes are
         # responsible boxes, its target-or-target-parent boxes responsible boxes or ancestors;

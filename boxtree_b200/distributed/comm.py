@@ -8,6 +8,13 @@ import numpy as np
 import torch
 
 
+class _Done:
+    """Handle of a collective that has already been carried out."""
+
+    def wait(self):
+        pass
+
+
 class SingleProcessComm:
     """One rank; collectives are identities."""
 
@@ -31,6 +38,9 @@ class SingleProcessComm:
 
     def allreduce_(self, t, op="sum"):
         return t
+
+    def allreduce_async_(self, t, op="sum"):
+        return _Done()
 
     def all_to_all_bytes(self, send, send_splits, recv_splits):
         return send
@@ -126,6 +136,19 @@ class TorchDistComm:
             t.copy_(staged)
         return t
 
+    def allreduce_async_(self, t, op="sum"):
+        """In-place all-reduce that is only ENQUEUED: it runs on the backend's own stream after
+        the work already queued on the current stream; kernels launched afterwards on the
+        current stream overlap it.  ``handle.wait()`` makes the current stream wait for the
+        result (no host synchronisation with NCCL)."""
+        ops = {"sum": self.dist.ReduceOp.SUM, "min": self.dist.ReduceOp.MIN,
+               "max": self.dist.ReduceOp.MAX}
+        assert t.is_contiguous()
+        if t.device != self.device:
+            self.allreduce_(t, op)
+            return _Done()
+        return self.dist.all_reduce(t, op=ops[op], group=self.group, async_op=True)
+
     def all_to_all_bytes(self, send, send_splits, recv_splits):
         """Variable all-to-all of a uint8 buffer: ``send_splits[d]`` bytes go to rank *d*,
         ``recv_splits[s]`` bytes arrive from rank *s* (NCCL: grouped send/recv over NVLink)."""
@@ -199,6 +222,10 @@ class ThreadComm:
             torch.cuda.synchronize(t.device)
         self.g.barrier.wait()
         return t
+
+    def allreduce_async_(self, t, op="sum"):
+        self.allreduce_(t, op)
+        return _Done()
 
     def all_to_all_bytes(self, send, send_splits, recv_splits):
         allv = self._exchange((send.clone(), [int(x) for x in send_splits]))

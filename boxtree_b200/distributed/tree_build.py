@@ -49,11 +49,22 @@ class DistributedTree(Tree):
     ntargets_global: int = 0
     rank: int = 0
     nranks: int = 1
+    #: set by ``build_distributed_tree(..., defer_extents=True)``: the all-reduce of the particle
+    #: bounding boxes is still in flight; ``pending.finish()`` (called by
+    #: ``distributed_tree_setup``) completes ``box_{source,target}_bounding_box_{min,max}``
+    pending: Any = None
 
 
-def build_distributed_tree(actx, tree_builder, comm, particles, **kwargs) -> DistributedTree:
+def build_distributed_tree(actx, tree_builder, comm, particles, defer_extents=False,
+                           **kwargs) -> DistributedTree:
     """Collective over *comm*: *particles* (and ``targets``, radii in *kwargs*) are this rank's
     slice of the global particle set; the global set is the concatenation in rank order.
-    Accepts :class:`boxtree_b200.TreeBuilder`'s arguments except refine weights."""
-    tree, _ = tree_builder(actx, particles, comm=comm, **kwargs)
+    Accepts :class:`boxtree_b200.TreeBuilder`'s arguments except refine weights.
+
+    *defer_extents*: return while the all-reduce of the boxes' particle extents is still in
+    flight on the backend's stream (``tree.pending``); every other array is final.
+    :func:`boxtree_b200.distributed.distributed_tree_setup` overlaps the reduction with the work
+    partition and the colleague pass and completes the extents before anything reads them; any
+    other consumer calls ``tree.pending.finish()`` first."""
+    tree, _ = tree_builder(actx, particles, comm=comm, _defer_extents=bool(defer_extents), **kwargs)
     return tree

@@ -370,8 +370,13 @@ class FMMTraversalBuilder:
                  debug: bool = False, _from_sep_smaller_min_nsources_cumul: int | None = None,
                  source_boxes_mask=None, source_parent_boxes_mask=None,
                  _colleague_row_mask=None, _list13_row_mask=None, _keep_shared=False,
-                 _shared=None):
+                 _shared=None, _before_extents=None):
         """See ``boxtree/traversal.py:1969-1990``.
+
+        :arg _before_extents: (internal, deferred distributed build) called once, after the
+            colleagues and the count passes of lists 2 and 4 have been launched and before the
+            first kernel that reads ``box_target_bounding_box_{min,max}`` (trees whose targets
+            have extent; otherwise the traversal never reads them and the hook is not called).
 
         :arg _colleague_row_mask: (internal, used by the sharded distributed setup) int8
             ``[nboxes]``; same-level non-well-separated boxes are only computed for boxes
@@ -663,6 +668,8 @@ class FMMTraversalBuilder:
             a3.sources_have_extent = int(tree.sources_have_extent)
             a3.crit = CRIT_CODE[crit]
             keep_alive = []
+            if _before_extents is not None and tree.targets_have_extent:
+                _before_extents()
             if tree.targets_have_extent:
                 bbmin = dev(dev_tree.box_target_bounding_box_min)
                 bbmax = dev(dev_tree.box_target_bounding_box_max)

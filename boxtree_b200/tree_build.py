@@ -104,6 +104,22 @@ class _Pool:
         return p
 
 
+class _Pending:
+    """Work that a deferred build still owes (``_defer_extents``): ``finish()`` runs it once."""
+
+    def __init__(self, fn):
+        self._fn = fn
+
+    def finish(self):
+        fn, self._fn = self._fn, None
+        if fn is not None:
+            fn()
+
+    @property
+    def done(self):
+        return self._fn is None
+
+
 class TreeBuilder:
     """Builds a :class:`boxtree_b200.Tree`; mirrors ``boxtree.TreeBuilder``."""
 
@@ -499,18 +515,30 @@ class TreeBuilder:
                     # one GPU: decide + children + commit in one go; distributed: the children's
                     # local (lower bound, count, nonchild) are summed over the ranks before the commit
                     first = STEP_DECIDE | STEP_CREATE if dist else STEP_ALL
-                    run_step(first)
-                    h = read_ctl()
-                    while h[CTL_OVERFLOW]:
-                        nreallocs += 1
-                        pool.ensure(nboxes + nb * int(h[CTL_NSPLIT]))
-                        run_step(first & ~STEP_DECIDE)
-                        h = read_ctl()
-                    if dist:
-                        if h[CTL_NSPLIT] and not (skip_if_no_regular and not h[CTL_NSPLIT_REGULAR]):
-                            comm.allreduce_(pool.xch[:2 * nb * int(h[CTL_NSPLIT])], "sum")
+                    if dist and ncand <= 4096:
+                        # few candidates (the top levels): room for all of them to split and the
+                        # counts of all their children summed, so that no readback is needed
+                        # between the children and the commit
+                        pool.ensure(nboxes + nb * ncand)
+                        run_step(first)
+                        comm.allreduce_(pool.xch[:2 * nb * ncand], "sum")
                         run_step(STEP_COMMIT)
                         h = read_ctl()
+                        assert not h[CTL_OVERFLOW]
+                    else:
+                        run_step(first)
+                        h = read_ctl()
+                        while h[CTL_OVERFLOW]:
+                            nreallocs += 1
+                            pool.ensure(nboxes + nb * int(h[CTL_NSPLIT]))
+                            run_step(first & ~STEP_DECIDE)
+                            h = read_ctl()
+                        if dist:
+                            if h[CTL_NSPLIT] and not (skip_if_no_regular
+                                                      and not h[CTL_NSPLIT_REGULAR]):
+                                comm.allreduce_(pool.xch[:2 * nb * int(h[CTL_NSPLIT])], "sum")
+                            run_step(STEP_COMMIT)
+                            h = read_ctl()
 
                     nsplit_regular = int(h[CTL_NSPLIT_REGULAR])
                     have_oversize_split_box = int(h[CTL_OVERSIZE])
@@ -741,16 +769,38 @@ class TreeBuilder:
             # child merge on the global values
             # (a rank's share of a box is a particle or two: one lane per box, flag 4)
             sparse = 0      # (measured slower than 8 lanes per box on 12M boxes at 8 ranks)
-            for phases in ((1 | sparse, 2) if dist else (3,)):
+
+            def extents_phase(phases):
                 for parts, radii, pstarts, pcounts, bmin, bmax in rounds:
                     check(lib.bt_box_extents_phase(
                         dcode, dimensions, nfinal, aligned_nboxes, nlevels, ls_host,
                         dptr(box_child_ids), dptr(box_centers), dptr(pstarts), dptr(pcounts),
                         _cabi.ptr_array(list(parts)), dptr(radii), dptr(bmin), dptr(bmax), phases,
                         sh), "bt_box_extents")
-                if dist and phases & 1:
-                    comm.allreduce_(bb_min_all, "min")
-                    comm.allreduce_(bb_max_all, "max")
+
+            pending_extents = None
+            if not dist:
+                extents_phase(3)
+            elif not kwargs.get("_defer_extents"):
+                extents_phase(1 | sparse)
+                comm.allreduce_(bb_min_all, "min")
+                comm.allreduce_(bb_max_all, "max")
+                extents_phase(2)
+            else:
+                # the two big reductions (2 x nsets x dim x nboxes coordinates) are only enqueued:
+                # they run on the backend's stream while this stream goes on with work that does
+                # not read the extents (work partition, colleagues, lists 2 and 4);
+                # `pending_extents.finish()` waits for them and merges the children's boxes
+                extents_phase(1 | sparse)
+                waits = [comm.allreduce_async_(bb_min_all, "min"),
+                         comm.allreduce_async_(bb_max_all, "max")]
+
+                def finish_extents():
+                    with torch.cuda.stream(stream), torch.cuda.device(actx.device):
+                        for w in waits:
+                            w.wait()
+                        extents_phase(2)
+                pending_extents = _Pending(finish_extents)
 
             # }}}
 
@@ -775,7 +825,7 @@ class TreeBuilder:
                 local_box_target_counts_nonchild=local_ranges[4],
                 local_box_target_counts_cumul=local_ranges[5],
                 nsources_global=nsources_global, ntargets_global=ntargets_global,
-                rank=comm.Get_rank(), nranks=comm.Get_size())
+                rank=comm.Get_rank(), nranks=comm.Get_size(), pending=pending_extents)
         tree = cls(
             **extra,
             sources_are_targets=sources_are_targets,

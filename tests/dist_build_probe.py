@@ -52,7 +52,9 @@ def main():
             lib.bt_prof_reset()
             lib.bt_prof_enable(1)
         t0 = time.perf_counter()
-        dtree = bd.build_distributed_tree(actx, tb, comm, ssrc, **skw)
+        dtree = bd.build_distributed_tree(actx, tb, comm, ssrc,
+                                          defer_extents=os.environ.get("BT_DIST_DEFER", "1") != "0",
+                                          **skw)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         out = bd.distributed_tree_setup(actx, dtree, tg, comm)

@@ -36,8 +36,13 @@ def slice_inputs(src, tkw, rank, size):
     return s, kw
 
 
-def run_rank(actx, comm, src, tkw, vkw):
-    """The distributed build + setup of one rank (collective)."""
+def run_rank(actx, comm, src, tkw, vkw, defer=None):
+    """The distributed build + setup of one rank (collective).  *defer*: the build returns with
+    the all-reduce of the particle extents in flight, as ``bench.py`` runs it (default; set
+    ``BT_DIST_DEFER=0`` or pass False for the build that completes them itself)."""
+    import os
+    if defer is None:
+        defer = os.environ.get("BT_DIST_DEFER", "1") != "0"
     from boxtree_b200 import FMMTraversalBuilder, TreeBuilder
     from boxtree_b200 import distributed as bd
     rank, size = comm.Get_rank(), comm.Get_size()
@@ -45,7 +50,8 @@ def run_rank(actx, comm, src, tkw, vkw):
     dkw = {k: (actx.from_numpy(v) if isinstance(v, np.ndarray) else
                [actx.from_numpy(x) for x in v] if k == "targets" else v) for k, v in kw.items()}
     dtree = bd.build_distributed_tree(actx, TreeBuilder(actx), comm,
-                                      [actx.from_numpy(x) for x in s], **dkw)
+                                      [actx.from_numpy(x) for x in s], defer_extents=defer, **dkw)
+    assert (dtree.pending is not None) == bool(defer)
     tg = FMMTraversalBuilder(actx, **vkw)
     lt, ltrav, sidx, tidx = bd.distributed_tree_setup(actx, dtree, tg, comm)
     return dtree, lt, ltrav, sidx, tidx

@@ -131,8 +131,10 @@ def _collective_worker(rank, world, port, out):
     comm.allreduce_(counts, "sum")
     lo = torch.tensor([1.0 + rank, -3.0 * rank], dtype=torch.float64)
     hi = lo.clone()
-    comm.allreduce_(lo, "min")
-    comm.allreduce_(hi, "max")
+    # enqueued, both in flight, waited for in order: how the deferred build reduces the extents
+    waits = [comm.allreduce_async_(lo, "min"), comm.allreduce_async_(hi, "max")]
+    for w in waits:
+        w.wait()
     # rank r sends (d + 1 + r) bytes of value 10 * r + d to rank d
     send_splits = [d + 1 + rank for d in range(world)]
     send = torch.cat([torch.full((n,), 10 * rank + d, dtype=torch.uint8)
@@ -175,8 +177,8 @@ def test_thread_comm_collectives():
         comm.allreduce_(counts, "sum")
         lo = torch.tensor([1.0 + rank, -3.0 * rank], dtype=torch.float64)
         hi = lo.clone()
-        comm.allreduce_(lo, "min")
-        comm.allreduce_(hi, "max")
+        for w in [comm.allreduce_async_(lo, "min"), comm.allreduce_async_(hi, "max")]:
+            w.wait()
         send_splits = [d + 1 + rank for d in range(world)]
         send = torch.cat([torch.full((n,), 10 * rank + d, dtype=torch.uint8)
                           for d, n in enumerate(send_splits)])

@@ -33,6 +33,18 @@ def test_distributed_build_matches_reference_flow(actx, name, nranks):
     assert sum(int(o[4].shape[0]) for o in outs) == rtree.ntargets
 
 
+@pytest.mark.parametrize("name", sorted(CASES)[:3])
+def test_distributed_build_without_deferred_extents(actx, name):
+    """``run_rank`` defers the extents' all-reduce by default (as the bench does); the build that
+    completes the extents itself must give the same arrays, also before any setup call."""
+    src, tkw, vkw = CASES[name]()
+    rtree, want = oracle_ranks(src, tkw, vkw, 2)
+    outs = run_threads(2, lambda comm: run_rank(actx, comm, src, tkw, vkw, defer=False))
+    for r in range(2):
+        bad = check_rank(actx, r, 2, outs[r], rtree, want[r])
+        assert not bad, (r, bad[:10])
+
+
 @pytest.mark.parametrize("kind", ["adaptive", "non-adaptive", "adaptive-level-restricted"])
 @pytest.mark.parametrize("dims", [1, 2, 3])
 def test_distributed_build_kinds(actx, kind, dims):
