@@ -2366,38 +2366,76 @@ heavy_map_rowscan_kernel(int nslots, int64_t rowlen, int* __restrict__ G, HeavyW
     }
 }
 
-// fill: ordered pass over the map (one warp per chunk)
+// fill: ordered pass over the map (one warp per chunk).  Most positions are empty (the walk only
+// visits the shell around the target box), so the chunk's entries are first compacted, in position
+// order, into shared memory (16 map bytes per lane and load); ranking (match_any), the segment
+// search and the stores then run on full warps.
 __global__ void __launch_bounds__(256)
 heavy_map_extract_kernel(int nslots, int64_t rowlen, const int* __restrict__ G, int* __restrict__ lists,
                          HeavyWs ws)
 {
+    static_assert(kMapChunk == 1024 && kMaxWalkLevels + 2 < 64, "entry = position (10 bits) | code << 10");
     __shared__ int run[8][kMaxWalkLevels + 2];
+    __shared__ unsigned short buf[8][kMapChunk];
     const int nheavy = ws.hctl[kHctlNHeavy];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long nchunks = ws.hplan[0] / kMapChunk;
     const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long c = w; c < nchunks; c += nw) {
+        const long long base = c * kMapChunk;
+        // compaction: lane l of load i holds positions (32 i + l) * 16 .. + 15
+        const uint4* src = reinterpret_cast<const uint4*>(ws.hmap + base);
+        int n = 0;
+#pragma unroll
+        for (int i = 0; i < kMapChunk / 16 / 32; ++i) {
+            const uint4 v = src[i * 32 + lane];
+            const unsigned wd[4] = {v.x, v.y, v.z, v.w};
+            int cnt = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) cnt += ((wd[k] >> (8 * b)) & 0xffu) ? 1 : 0;
+            int inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += y;
+            }
+            int off = n + inc - cnt;
+            if (cnt) {
+                const unsigned p0 = (unsigned)(i * 32 + lane) * 16u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const unsigned code = (wd[k] >> (8 * b)) & 0xffu;
+                        if (code) buf[wib][off++] = (unsigned short)((p0 + 4 * k + b) | (code << 10));
+                    }
+            }
+            n += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (n == 0) continue;                 // (warp-uniform)
         const int h = heavy_row_of_chunk(ws, nheavy, c);
         const int r = ws.heavy_rows[h];
         const int S = ws.seg_stride, ns = ws.hseg_n[h];
         const int* spre = ws.hseg_prefix + (int64_t)h * S;
         const int* srank = ws.hseg_rank + (int64_t)h * S;
-        for (int l = lane; l < nslots; l += 32) run[wib][l] = ws.chunk_cnt[c * nslots + l];
+        const int local0 = (int)(base - ws.hrow_base[h]);
+        // next output position of every slot: the row's start in the slot + the chunk's offset
+        for (int l = lane; l < nslots; l += 32) run[wib][l] = G[l * rowlen + r] + ws.chunk_cnt[c * nslots + l];
         __syncwarp();
-        const long long base = c * kMapChunk;
-        for (int i0 = 0; i0 < kMapChunk; i0 += 32) {
-            const unsigned code = ws.hmap[base + i0 + lane];
-            if (!__any_sync(0xffffffffu, code != 0)) continue;
-            const int sl = code ? (int)code - 1 : 63;
+        for (int j0 = 0; j0 < n; j0 += 32) {
+            const bool valid = j0 + lane < n;
+            const unsigned e = valid ? buf[wib][j0 + lane] : 0u;
+            const int sl = valid ? (int)(e >> 10) - 1 : 63;
             const unsigned peers = __match_any_sync(0xffffffffu, sl);
-            const int prior = code ? run[wib][sl] : 0;
+            const int prior = valid ? run[wib][sl] : 0;
             __syncwarp();
-            if (code) {
-                const int local = (int)(base + i0 + lane - ws.hrow_base[h]);
+            if (valid) {
+                const int local = local0 + (int)(e & 1023u);
                 int lo = 0, hi = ns;                  // last segment with prefix <= local
                 while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (spre[mid] <= local) lo = mid; else hi = mid; }
-                const int box = ws.dfs_order[srank[lo] + (local - spre[lo])];
-                lists[G[sl * rowlen + r] + prior + __popc(peers & ((1u << lane) - 1u))] = box;
+                lists[prior + __popc(peers & ((1u << lane) - 1u))] = ws.dfs_order[srank[lo] + (local - spre[lo])];
                 if (lane == __ffs(peers) - 1) run[wib][sl] = prior + __popc(peers);
             }
             __syncwarp();
@@ -2424,7 +2462,10 @@ static int list13_impl(int phase, const bt_tree_view* tv, const bt_list3_args* a
     const bool use_map = ws.hrow_base != nullptr;   // heavy rows by position map (else: radix sort)
     const int64_t rowlen = (int64_t)ntgt + 1;
     const int64_t total_len = rowlen * nrows;
+    // two waves of resident blocks (measured: 2.9 ms against 3.0 ms with one wave on config 3 --
+    // the rows' walks differ widely in length and the second wave evens the SMs out)
     const int cgrid = grid_for((int64_t)ntgt << DIM, kTravBlock, 16);
+    const int fgrid = cgrid;
     const int nsteps = t.nlevels;
     // counts -> global offsets (one flattened scan), non-empty ranks, summary for the host
     auto finish_counts = [&]() -> int {
@@ -2483,12 +2524,13 @@ static int list13_impl(int phase, const bt_tree_view* tv, const bt_list3_args* a
             BT_LAUNCH_CHECK();
             heavy_map_seed_kernel<T, DIM><<<grid_for((int64_t)nheavy_host * ws.seg_stride, 256, 8), 256, 0, s>>>(t, x, xflags, ws);
             BT_LAUNCH_CHECK();
+            const int step_grid = grid_resident(heavy_map_step_kernel<T, DIM>, (int64_t)1 << 40, 256);
             for (int st = 0; st < nsteps; ++st) {
-                heavy_map_step_kernel<T, DIM><<<kNumSMs * 8, 256, 0, s>>>(t, x, st, ws);
+                heavy_map_step_kernel<T, DIM><<<step_grid, 256, 0, s>>>(t, x, st, ws);
                 BT_LAUNCH_CHECK();
             }
             const long long nchunks = ws.hmap_cap / kMapChunk;
-            heavy_map_hist_kernel<<<grid_for(nchunks * 32, 256, 8), 256, 0, s>>>(nrows, ws);
+            heavy_map_hist_kernel<<<grid_resident(heavy_map_hist_kernel, nchunks * 32, 256), 256, 0, s>>>(nrows, ws);
             BT_LAUNCH_CHECK();
             heavy_map_rowscan_kernel<<<grid_for((int64_t)nheavy_host * 32, 256, 8), 256, 0, s>>>(nrows, rowlen, G, ws);
             BT_LAUNCH_CHECK();
@@ -2505,14 +2547,15 @@ static int list13_impl(int phase, const bt_tree_view* tv, const bt_list3_args* a
         }
         if (nwalk_host > 0) {        // rows the count pass could not stage are walked again
             BT_PROF("l13_walk_fill", s);
-            list13_coop_kernel<T, DIM, true><<<cgrid, kTravBlock, 0, s>>>(t, x, xflags, ntgt, G, lists, ws, near_cap);
+            list13_coop_kernel<T, DIM, true><<<fgrid, kTravBlock, 0, s>>>(t, x, xflags, ntgt, G, lists, ws, near_cap);
             BT_LAUNCH_CHECK();
         }
         if (use_map) {
             if (nheavy_host > 0) {
                 BT_PROF("l13_heavy_extract", s);
                 const long long nchunks = ws.hmap_cap / kMapChunk;
-                heavy_map_extract_kernel<<<grid_for(nchunks * 32, 256, 8), 256, 0, s>>>(nrows, rowlen, G, lists, ws);
+                heavy_map_extract_kernel<<<grid_resident(heavy_map_extract_kernel, nchunks * 32, 256), 256, 0, s>>>(
+                    nrows, rowlen, G, lists, ws);
                 BT_LAUNCH_CHECK();
             }
         } else if (heavy_total_host > 0) {

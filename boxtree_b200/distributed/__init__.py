@@ -251,7 +251,7 @@ def distributed_tree_setup(actx, dtree, traversal_builder, comm, cost_per_box=No
                 source_boxes_mask=resp_mask if row_mask is None else (resp_mask & row_mask),
                 source_parent_boxes_mask=anc_mask if row_mask is None else (anc_mask & row_mask),
                 _colleague_row_mask=need, _keep_shared=prev is None, _shared=prev,
-                _before_extents=finish_pending)[0]
+                _before_extents=finish_pending, _preorder=(pre[2], pre[0]))[0]
 
         # one piece, or -- when a list of the rank's rows exceeds the int32 CSR range
         # (``traversal_pieces`` > 1, or on OverflowError) -- row pieces as in

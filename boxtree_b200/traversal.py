@@ -370,9 +370,11 @@ class FMMTraversalBuilder:
                  debug: bool = False, _from_sep_smaller_min_nsources_cumul: int | None = None,
                  source_boxes_mask=None, source_parent_boxes_mask=None,
                  _colleague_row_mask=None, _list13_row_mask=None, _keep_shared=False,
-                 _shared=None, _before_extents=None):
+                 _shared=None, _before_extents=None, _preorder=None):
         """See ``boxtree/traversal.py:1969-1990``.
 
+        :arg _preorder: (internal) ``(subtree_size, dfs_rank)`` of the tree's boxes when the caller
+            has them already (``bt_trav_dfs_rank``).
         :arg _before_extents: (internal, deferred distributed build) called once, after the
             colleagues and the count passes of lists 2 and 4 have been launched and before the
             first kernel that reads ``box_target_bounding_box_{min,max}`` (trees whose targets
@@ -543,6 +545,8 @@ class FMMTraversalBuilder:
             budget = int(os.environ.get("BT_WALK_BUDGET", DEFAULT_WALK_BUDGET))
             if _shared is not None:
                 subtree_size, dfs_rank = _shared["subtree_size"], _shared["dfs_rank"]
+            elif _preorder is not None:
+                subtree_size, dfs_rank = _preorder
             else:
                 subtree_size = actx.empty(max(nboxes, 1), np.int32)
                 dfs_rank = actx.empty(max(nboxes, 1), np.int32)

@@ -44,11 +44,12 @@ def main():
     skw = {k: (actx.from_numpy(v) if isinstance(v, np.ndarray) else
                [actx.from_numpy(x) for x in v] if k == "targets" else v) for k, v in kw.items()}
     lib = _cabi.load()
-    for rep in range(5):
+    nrep = int(os.environ.get("BT_PROBE_REPS", "5"))
+    for rep in range(nrep):
         dist.barrier()
         torch.cuda.synchronize()
         _timing.report()
-        if rep == 4 and rank == 0:
+        if rep == nrep - 1 and rank == 0:
             lib.bt_prof_reset()
             lib.bt_prof_enable(1)
         t0 = time.perf_counter()
@@ -63,7 +64,7 @@ def main():
         print(f"rank {rank} rep{rep}: tree {1e3 * (t1 - t0):.2f} ms  setup {1e3 * (t2 - t1):.2f} ms  "
               f"total {1e3 * (t2 - t0):.2f} ms  nboxes={dtree.nboxes} "
               f"local src={int(out[2].shape[0])} tgt={int(out[3].shape[0])}", flush=True)
-        if rep == 4:
+        if rep == nrep - 1:
             ph = _timing.report()
             if ph:
                 print(f"rank {rank} phases: " + "  ".join(f"{k}={v:.2f}" for k, v in ph.items()),
