@@ -2519,23 +2519,32 @@ static int list13_impl(int phase, const bt_tree_view* tv, const bt_list3_args* a
         if (!use_map) return BT_ERR_BAD_ARG;
         if (ntgt > 0 && nheavy_host > 0) {
             BT_PROF("l13_heavy_expand", s);
-            BT_CHECK(cudaMemsetAsync(ws.hmap, 0, (size_t)ws.hmap_cap, s));
-            heavy_map_plan_kernel<T, DIM><<<grid_for(nheavy_host, 128, 8), 128, 0, s>>>(t, x, xflags, ws);
-            BT_LAUNCH_CHECK();
-            heavy_map_seed_kernel<T, DIM><<<grid_for((int64_t)nheavy_host * ws.seg_stride, 256, 8), 256, 0, s>>>(t, x, xflags, ws);
-            BT_LAUNCH_CHECK();
-            const int step_grid = grid_resident(heavy_map_step_kernel<T, DIM>, (int64_t)1 << 40, 256);
-            for (int st = 0; st < nsteps; ++st) {
-                heavy_map_step_kernel<T, DIM><<<step_grid, 256, 0, s>>>(t, x, st, ws);
+            {
+                BT_PROF("l13h_plan_seed", s);
+                BT_CHECK(cudaMemsetAsync(ws.hmap, 0, (size_t)ws.hmap_cap, s));
+                heavy_map_plan_kernel<T, DIM><<<grid_for(nheavy_host, 128, 8), 128, 0, s>>>(t, x, xflags, ws);
+                BT_LAUNCH_CHECK();
+                heavy_map_seed_kernel<T, DIM><<<grid_for((int64_t)nheavy_host * ws.seg_stride, 256, 8), 256, 0, s>>>(t, x, xflags, ws);
                 BT_LAUNCH_CHECK();
             }
-            const long long nchunks = ws.hmap_cap / kMapChunk;
-            heavy_map_hist_kernel<<<grid_resident(heavy_map_hist_kernel, nchunks * 32, 256), 256, 0, s>>>(nrows, ws);
-            BT_LAUNCH_CHECK();
-            heavy_map_rowscan_kernel<<<grid_for((int64_t)nheavy_host * 32, 256, 8), 256, 0, s>>>(nrows, rowlen, G, ws);
-            BT_LAUNCH_CHECK();
-            heavy_total_kernel<<<kNumSMs, 256, 0, s>>>(G, rowlen, nrows, ws);
-            BT_LAUNCH_CHECK();
+            {
+                BT_PROF("l13h_steps", s);
+                const int step_grid = grid_resident(heavy_map_step_kernel<T, DIM>, (int64_t)1 << 40, 256);
+                for (int st = 0; st < nsteps; ++st) {
+                    heavy_map_step_kernel<T, DIM><<<step_grid, 256, 0, s>>>(t, x, st, ws);
+                    BT_LAUNCH_CHECK();
+                }
+            }
+            {
+                BT_PROF("l13h_counts", s);
+                const long long nchunks = ws.hmap_cap / kMapChunk;
+                heavy_map_hist_kernel<<<grid_resident(heavy_map_hist_kernel, nchunks * 32, 256), 256, 0, s>>>(nrows, ws);
+                BT_LAUNCH_CHECK();
+                heavy_map_rowscan_kernel<<<grid_for((int64_t)nheavy_host * 32, 256, 8), 256, 0, s>>>(nrows, rowlen, G, ws);
+                BT_LAUNCH_CHECK();
+                heavy_total_kernel<<<kNumSMs, 256, 0, s>>>(G, rowlen, nrows, ws);
+                BT_LAUNCH_CHECK();
+            }
         }
         BT_TRY(finish_counts());
     } else if (ntgt > 0) {

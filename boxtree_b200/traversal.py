@@ -25,12 +25,18 @@ from .tree import Tree, TreeOfBoxes
 CRIT_CODE = {"static_linf": 0, "precise_linf": 1, "static_l2": 2}
 
 #: child visits one thread may spend on one row of list 1 / list 3 before the row is handed
-#: to the grid-wide "heavy row" path (csrc/traversal.cu); BT_WALK_BUDGET overrides (tests)
-DEFAULT_WALK_BUDGET = 1024
+#: to the grid-wide "heavy row" path (csrc/traversal.cu); BT_WALK_BUDGET overrides (tests).
+#: Measured on config 3 (B200, profiles/r02_budget_sweep.txt): the breadth-first expansion of the
+#: heavy path handles mid-size rows (a few hundred entries) faster than the row walk -- budget
+#: 2048 / 1024 / 512 / 256 / 128: 15.5 / 14.3 / 13.2 / 13.1 / 14.1 ms per step (below 256 the
+#: per-row overhead of the maps takes over)
+DEFAULT_WALK_BUDGET = 256
 
 #: entries per row the count pass of the fused list-1+3 walk may stage for the fill pass
-#: (rows with more are walked a second time); BT_STAGE_STRIDE overrides, 0 disables
-DEFAULT_STAGE_STRIDE = 256
+#: (rows with more are walked a second time); BT_STAGE_STRIDE overrides, 0 disables.
+#: A row within the budget makes at most budget / 2^d + 1 expansions of 2^d children, plus its
+#: <= 27 roots and <= 24 near-field boxes from above: 320 holds every such row in 3-D
+DEFAULT_STAGE_STRIDE = 320
 _STAGE_MAX_BYTES = 8 << 30
 
 # bits of bt_set_walk_mode (include/boxtree_b200.h) that select a different host sequence

@@ -72,7 +72,7 @@ def main():
                   f"list2={int(trav.from_sep_siblings_lists.shape[0])}", flush=True)
         rep_ = _cabi.profile_report()
         # entry scopes only: nested ones (radix passes, the parts of the fused walk) are inside them
-        tot = sum(ms for k, (c, ms) in rep_.items() if not k.startswith(("rs_", "l13_")))
+        tot = sum(ms for k, (c, ms) in rep_.items() if not k.startswith(("rs_", "l13_", "l13h_")))
         for k, (c, ms) in sorted(rep_.items(), key=lambda kv: -kv[1][1]):
             print(f"    {k:28s} calls={c:4d}  {ms:9.3f} ms  {100 * ms / max(tot, 1e-9):5.1f}%")
         print(f"    sum of entry scopes {tot:.3f} ms; stats {tb.last_stats}")
