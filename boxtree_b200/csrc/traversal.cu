@@ -2219,13 +2219,14 @@ heavy_map_plan_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, const unsigned ch
     }
 }
 
-// position of the box with depth-first rank rk in the map of heavy row h
-__device__ __forceinline__ long long heavy_map_pos(const HeavyWs& ws, int h, int rk)
+// frontier item of the map expansion: heavy-row index (23 bits) | segment of the row's map the
+// walk parent lies in (9 bits; a root's whole subtree is one segment, so the walk never leaves
+// it and the position of a box needs no search) | near-ok | walk parent (31 bits)
+constexpr int kMapSegBits = 9, kMapRowBits = 23;
+__device__ __forceinline__ unsigned long long heavy_map_item(int h, int seg, bool nearok, int parent)
 {
-    const int* srank = ws.hseg_rank + (int64_t)h * ws.seg_stride;
-    int lo = 0, hi = ws.hseg_n[h];                 // last segment with srank <= rk
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (srank[mid] <= rk) lo = mid; else hi = mid; }
-    return ws.hrow_base[h] + ws.hseg_prefix[(int64_t)h * ws.seg_stride + lo] + (rk - srank[lo]);
+    return ((unsigned long long)h << (32 + kMapSegBits)) | ((unsigned long long)seg << 32) |
+           (nearok ? 0x80000000ull : 0ull) | (unsigned)parent;
 }
 
 template <typename T, int DIM>
@@ -2261,7 +2262,7 @@ heavy_map_seed_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, const unsigned ch
         else { if (!(xflags[cb] & kXfHasChild)) continue; nearok = adj && (fl & BT_BOX_HAS_SOURCE_CHILD_BOXES); }
         const int q = atomicAdd(ws.hctl + kHctlFrontier, 1);
         if (q < ws.frontier_cap)
-            ws.frontier[0][q] = ((unsigned long long)h << 32) | (nearok ? 0x80000000ull : 0ull) | (unsigned)cb;
+            ws.frontier[0][q] = heavy_map_item(h, k, nearok, cb);
         else ws.hctl[kHctlOverflow] = 1;
     }
 }
@@ -2281,11 +2282,12 @@ heavy_map_step_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, int step, HeavyWs
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x; tid < ((total + 31) & ~31ll);
          tid += stride) {
-        int act = 0, wb = 0, h = 0;
+        int act = 0, wb = 0, h = 0, seg = 0;
         unsigned long long nearok = 0;
         if (tid < total) {
             const unsigned long long item = fin[tid / NB];
-            h = (int)(item >> 32);
+            h = (int)(item >> (32 + kMapSegBits));
+            seg = (int)(item >> 32) & ((1 << kMapSegBits) - 1);
             nearok = item & 0x80000000ull;
             const int parent = (int)(item & 0x7fffffffull), m = (int)(tid % NB);
             const L3Ctx<T, DIM> c = reinterpret_cast<const L3Ctx<T, DIM>*>(ws.hctx)[h];
@@ -2295,11 +2297,13 @@ heavy_map_step_kernel(TreeView<T, DIM> t, List3Args<T, DIM> x, int step, HeavyWs
         }
         if (act & (kVisitEmit | kVisitClose | kVisitNear)) {
             const int slot = (act & kVisitNear) ? t.nlevels + 1 : (act & kVisitEmit) ? (int)t.levels[wb] : t.nlevels;
-            ws.hmap[heavy_map_pos(ws, h, ws.dfs_rank[wb])] = (unsigned char)(slot + 1);
+            const int64_t sg = (int64_t)h * ws.seg_stride + seg;
+            ws.hmap[ws.hrow_base[h] + ws.hseg_prefix[sg] + (ws.dfs_rank[wb] - ws.hseg_rank[sg])] =
+                (unsigned char)(slot + 1);
         }
         const long long q = warp_append(act & kVisitPush, ws.hctl + kHctlFrontier + step + 1);
         if (q >= 0) {
-            if (q < ws.frontier_cap) fout[q] = ((unsigned long long)h << 32) | nearok | (unsigned)wb;
+            if (q < ws.frontier_cap) fout[q] = heavy_map_item(h, seg, nearok != 0, wb);
             else ws.hctl[kHctlOverflow] = 1;
         }
     }
@@ -2421,6 +2425,10 @@ heavy_map_extract_kernel(int nslots, int64_t rowlen, const int* __restrict__ G, 
         const int* spre = ws.hseg_prefix + (int64_t)h * S;
         const int* srank = ws.hseg_rank + (int64_t)h * S;
         const int local0 = (int)(base - ws.hrow_base[h]);
+        // segment of the chunk's first position (warp-uniform search); the entries of one chunk
+        // span a segment or two, so each entry only steps forward from there
+        int seg0 = 0;
+        { int hi = ns; while (hi - seg0 > 1) { const int mid = (seg0 + hi) >> 1; if (spre[mid] <= local0) seg0 = mid; else hi = mid; } }
         // next output position of every slot: the row's start in the slot + the chunk's offset
         for (int l = lane; l < nslots; l += 32) run[wib][l] = G[l * rowlen + r] + ws.chunk_cnt[c * nslots + l];
         __syncwarp();
@@ -2433,8 +2441,8 @@ heavy_map_extract_kernel(int nslots, int64_t rowlen, const int* __restrict__ G, 
             __syncwarp();
             if (valid) {
                 const int local = local0 + (int)(e & 1023u);
-                int lo = 0, hi = ns;                  // last segment with prefix <= local
-                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (spre[mid] <= local) lo = mid; else hi = mid; }
+                int lo = seg0;                        // last segment with prefix <= local
+                while (lo + 1 < ns && spre[lo + 1] <= local) ++lo;
                 lists[prior + __popc(peers & ((1u << lane) - 1u))] = ws.dfs_order[srank[lo] + (local - spre[lo])];
                 if (lane == __ffs(peers) - 1) run[wib][sl] = prior + __popc(peers);
             }
@@ -2464,7 +2472,8 @@ static int list13_impl(int phase, const bt_tree_view* tv, const bt_list3_args* a
     const int64_t total_len = rowlen * nrows;
     // two waves of resident blocks (measured: 2.9 ms against 3.0 ms with one wave on config 3 --
     // the rows' walks differ widely in length and the second wave evens the SMs out)
-    const int cgrid = grid_for((int64_t)ntgt << DIM, kTravBlock, 16);
+    static const int walk_bps = [] { const char* e = getenv("BT_L13_BLOCKS_PER_SM"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 16; }();
+    const int cgrid = grid_for((int64_t)ntgt << DIM, kTravBlock, walk_bps);
     const int fgrid = cgrid;
     const int nsteps = t.nlevels;
     // counts -> global offsets (one flattened scan), non-empty ranks, summary for the host
@@ -2517,6 +2526,7 @@ static int list13_impl(int phase, const bt_tree_view* tv, const bt_list3_args* a
     } else if (phase == 2) {
         // map mode: expand the heavy rows ONCE into their position maps, count from the maps
         if (!use_map) return BT_ERR_BAD_ARG;
+        if (nheavy_host >= (1 << kMapRowBits) || ws.seg_stride > (1 << kMapSegBits)) return BT_ERR_UNSUPPORTED;
         if (ntgt > 0 && nheavy_host > 0) {
             BT_PROF("l13_heavy_expand", s);
             {
