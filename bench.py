@@ -11,9 +11,11 @@ configuration the metric is quoted on.
 
 * ``value``: Mpoints/s with the inputs already resident in HBM, CUDA-event timed
   over exactly K steps, max over ranks.
-* ``e2e``: the same through the public API starting from pinned HOST buffers
-  (H2D copies of coordinates/radii and a D2H read of the result summary inside
-  the timed region).
+* ``e2e``: the same through the public API starting from pinned HOST buffers: every step
+  copies its own coordinates/radii host->device and reads its result summary device->host
+  inside the timed region.  ``e2e.value`` is the double-buffered loop (the H2D copy of step
+  k+1 runs on a copy stream into a second, preallocated set of device buffers while step k
+  builds); ``e2e.serial`` is upload, build, read back one after the other.
 * ``roofline``: the dominant kernel scope, timed live with CUDA events on the
   launching stream (library instrumentation ``bt_prof_*``), achieved algorithmic
   GB/s against the measured HBM peak of MEASURED_PEAKS.json.
