@@ -152,6 +152,7 @@ SIGNATURES = {
                                vp],
     "bt_remap_classes": [_i64, vp, vp, vp],
     "bt_dist_dfs_order": [_i, _i, _i, _i, vp, vp, vp, vp, vp, vp],
+    "bt_dist_partition_cuts": [_i, _i, vp, vp, vp, vp, vp],
     "bt_dist_mask_from_list": [_i, vp, vp, vp],
     "bt_dist_ancestor_mask": [_i, vp, vp, vp, vp],
     "bt_dist_add_list_boxes": [_i, vp, vp, vp, vp, vp, vp, vp],

@@ -621,6 +621,59 @@ int bt_dist_dfs_order(int dim, int nboxes, int aligned_nboxes, int nlevels,
     return BT_OK;
 }
 
+// ---- work partition for the default cost 1 + own sources + own targets (partition.py:81-116) --
+// The reference accumulates the costs in depth-first order and cuts where the running sum first
+// exceeds (k + 1) * total / size.  With integer costs the running sums are exact in int64 as in
+// float64 (any summation order), so one look-back scan of the gathered costs + a binary search
+// per cut give the reference's cut positions; thresholds in the reference's float64 expression.
+namespace bt {
+struct PartCostIn {
+    const int* order; const int* nsrc; const int* ntgt;
+    __device__ int operator()(int64_t i) const { const int b = order[i]; return 1 + nsrc[b] + ntgt[b]; }
+};
+struct PartPrefixOut {
+    long long* excl; long long* tot;
+    __device__ void operator()(int64_t i, long long e) const { excl[i] = e; }
+    __device__ void total(long long t) const { *tot = t; }
+};
+__global__ void dist_partition_cuts_kernel(int nboxes, int nranks, const long long* __restrict__ excl,
+                                           const long long* __restrict__ tot, long long* __restrict__ cuts)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x + 1;       // cut between segments k-1 and k
+    if (k >= nranks) return;
+    const double total = (double)*tot;
+    const double thr = (double)k * total / (double)nranks;
+    // first i with (inclusive running sum of i) > thr; inclusive(i) = excl[i + 1], inclusive(n-1) = total
+    int lo = 0, hi = nboxes;                                        // answer in [lo, hi]
+    while (lo < hi) {
+        const int mid = lo + ((hi - lo) >> 1);
+        const double inc = (double)(mid + 1 < nboxes ? excl[mid + 1] : *tot);
+        if (inc > thr) hi = mid; else lo = mid + 1;
+    }
+    cuts[k - 1] = lo;
+    if (k == 1) cuts[nranks - 1] = *tot;
+}
+}  // namespace bt
+
+int bt_dist_partition_cuts(int nboxes, int nranks, const int32_t* dfs_order,
+                           const int32_t* box_source_counts_nonchild,
+                           const int32_t* box_target_counts_nonchild, int64_t* cuts, void* stream)
+{
+    BT_PROF("bt_dist_partition_cuts", (cudaStream_t)stream);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (nboxes <= 0 || nranks < 1) return BT_ERR_BAD_ARG;
+    long long* tmp = nullptr;
+    BT_CHECK(bt::temp_alloc((void**)&tmp, sizeof(long long) * ((size_t)nboxes + 1), s));
+    bt::PartCostIn in{dfs_order, box_source_counts_nonchild, box_target_counts_nonchild};
+    bt::PartPrefixOut out{tmp, tmp + nboxes};
+    BT_TRY(bt::scan_exclusive(nboxes, nullptr, in, out, s));
+    bt::dist_partition_cuts_kernel<<<(nranks + 63) / 64, 64, 0, s>>>(nboxes, nranks, tmp, tmp + nboxes,
+                                                                     (long long*)cuts);
+    BT_LAUNCH_CHECK();
+    BT_CHECK(cudaFreeAsync(tmp, s));
+    return BT_OK;
+}
+
 int bt_dist_mask_from_list(int n, const int32_t* list, int8_t* mask, void* stream)
 {
     BT_PROF("bt_dist_mask_from_list", (cudaStream_t)stream);

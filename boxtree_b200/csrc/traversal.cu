@@ -436,8 +436,6 @@ coll_topdown_kernel(TreeView<T, DIM> t, const int* __restrict__ level_start, int
             for (int m = 0; m < NB; ++m) hc = hc || (t.child(bch, m) != 0);
             bxf = (unsigned char)((hc ? kXfHasChild : 0) | ((t.flags[bch] & BT_BOX_IS_SOURCE_BOX) ? kXfCollSource : 0));
             brow = !(row_mask && !row_mask[bch]);
-#pragma unroll
-            for (int a = 0; a < DIM; ++a) bcen[lane][a] = t.centers[t.aligned * a + bch];
         }
         const unsigned rowm = __ballot_sync(0xffffffffu, brow) & nbmask;
         if (!rowm) {        // no child's row is wanted: only the flags the walks read of ANY box
@@ -447,6 +445,10 @@ coll_topdown_kernel(TreeView<T, DIM> t, const int* __restrict__ level_start, int
                 xflags[bch] = bxf;
             }
             continue;
+        }
+        if (bch) {
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) bcen[lane][a] = t.centers[t.aligned * a + bch];
         }
         const int level = lev;
         const int np = counts[p];
@@ -535,11 +537,27 @@ coll_topdown_kernel(TreeView<T, DIM> t, const int* __restrict__ level_start, int
     }
 }
 
-// staged rows -> CSR lists: one lane per box (most rows are empty when a row mask is in use),
-// the lanes of a warp copy their rows side by side
+// staged rows -> CSR lists: one thread per staged slot (box, j): the reads of the staging area
+// and -- rows being consecutive in the lists -- the writes are contiguous across a warp; a slot
+// beyond its row's length (all of them for a row masked out) costs two cached loads of `starts`
 __global__ void __launch_bounds__(256)
 coll_compact_kernel(int nboxes, int stride, const int* __restrict__ tmp, const int* __restrict__ starts,
                     int* __restrict__ lists)
+{
+    const int64_t total = (int64_t)nboxes * stride;
+    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gstride) {
+        const int b = (int)(i / stride), j = (int)(i - (int64_t)b * stride);
+        const int s = starts[b];
+        if (j < starts[b + 1] - s) lists[s + j] = tmp[i];
+    }
+}
+
+// the same with one lane per box, for a pass with a row mask (distributed setup: most rows are
+// empty, and a thread per staged slot would mostly find nothing to copy)
+__global__ void __launch_bounds__(256)
+coll_compact_rows_kernel(int nboxes, int stride, const int* __restrict__ tmp, const int* __restrict__ starts,
+                         int* __restrict__ lists)
 {
     const int gstride = gridDim.x * blockDim.x;
     for (int b0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); b0 < nboxes; b0 += gstride) {
@@ -611,8 +629,12 @@ static int colleagues_topdown_impl(int phase, const bt_tree_view* tv, const int*
         }
         BT_TRY(counts_to_starts(starts, t.nboxes, totals, s));
     } else {
-        coll_compact_kernel<<<grid_for((int64_t)t.nboxes, 256, 8), 256, 0, s>>>(t.nboxes, stride, tmp,
-                                                                               starts, lists);
+        if (row_mask)
+            coll_compact_rows_kernel<<<grid_for((int64_t)t.nboxes, 256, 8), 256, 0, s>>>(t.nboxes, stride, tmp,
+                                                                                        starts, lists);
+        else
+            coll_compact_kernel<<<grid_for((int64_t)t.nboxes * stride, 256, 8), 256, 0, s>>>(t.nboxes, stride, tmp,
+                                                                                            starts, lists);
         BT_LAUNCH_CHECK();
     }
     return BT_OK;
@@ -2340,33 +2362,33 @@ heavy_map_hist_kernel(int nslots, HeavyWs ws)
     }
 }
 
-// per heavy row: chunk counts -> exclusive offsets inside the row; row totals -> G.  One warp per
-// row, 32 chunks per step (lane = chunk), one warp scan per slot.
+// per heavy row and slot: chunk counts -> exclusive offsets inside the row; row totals -> G.  One
+// warp per (row, slot), 32 chunks per step (lane = chunk).  (A warp per ROW looping over the
+// slots left one SM scanning the few rows with thousands of chunks -- an upper-level box's
+// map covers a large part of the tree -- long after the others were done.)
 __global__ void __launch_bounds__(256)
 heavy_map_rowscan_kernel(int nslots, int64_t rowlen, int* __restrict__ G, HeavyWs ws)
 {
     const int nheavy = ws.hctl[kHctlNHeavy];
     const int lane = threadIdx.x & 31;
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    for (int h = w; h < nheavy; h += nw) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long idx = w; idx < (long long)nheavy * nslots; idx += nw) {
+        const int h = (int)(idx / nslots), sl = (int)(idx % nslots);
         const long long c0 = ws.hrow_base[h] / kMapChunk, c1 = ws.hrow_base[h + 1] / kMapChunk;
-        const int r = ws.heavy_rows[h];
-        for (int sl = 0; sl < nslots; ++sl) {
-            int carry = 0;
-            for (long long cb = c0; cb < c1; cb += 32) {
-                const long long c = cb + lane;
-                const int v = (c < c1) ? ws.chunk_cnt[c * nslots + sl] : 0;
-                int inc = v;
+        int carry = 0;
+        for (long long cb = c0; cb < c1; cb += 32) {
+            const long long c = cb + lane;
+            const int v = (c < c1) ? ws.chunk_cnt[c * nslots + sl] : 0;
+            int inc = v;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int y = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += y;
-                }
-                if (c < c1) ws.chunk_cnt[c * nslots + sl] = carry + inc - v;
-                carry += __shfl_sync(0xffffffffu, inc, 31);
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += y;
             }
-            if (lane == 0) G[sl * rowlen + r] = carry;
+            if (c < c1) ws.chunk_cnt[c * nslots + sl] = carry + inc - v;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
         }
+        if (lane == 0) G[sl * rowlen + ws.heavy_rows[h]] = carry;
     }
 }
 
@@ -2550,7 +2572,7 @@ static int list13_impl(int phase, const bt_tree_view* tv, const bt_list3_args* a
                 const long long nchunks = ws.hmap_cap / kMapChunk;
                 heavy_map_hist_kernel<<<grid_resident(heavy_map_hist_kernel, nchunks * 32, 256), 256, 0, s>>>(nrows, ws);
                 BT_LAUNCH_CHECK();
-                heavy_map_rowscan_kernel<<<grid_for((int64_t)nheavy_host * 32, 256, 8), 256, 0, s>>>(nrows, rowlen, G, ws);
+                heavy_map_rowscan_kernel<<<grid_for((int64_t)nheavy_host * nrows * 32, 256, 8), 256, 0, s>>>(nrows, rowlen, G, ws);
                 BT_LAUNCH_CHECK();
                 heavy_total_kernel<<<kNumSMs, 256, 0, s>>>(G, rowlen, nrows, ws);
                 BT_LAUNCH_CHECK();

@@ -115,17 +115,25 @@ bbox_partial_kernel(Particles<T, DIM> P, int have_radii, T* __restrict__ partial
     }
 }
 
+// one block of 2 * DIM warps: warp k reduces component k of the partial results (its lanes
+// stride over the blocks' rows, so the loads are independent, not a 592-long dependent chain)
 template <typename T, int DIM>
 __global__ void bbox_final_kernel(const T* __restrict__ partial, int nparts, T* __restrict__ out)
 {
-    const int k = threadIdx.x;
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (k >= 2 * DIM) return;
+    const bool is_max = k & 1;
     T v = partial[k];
-    for (int p = 1; p < nparts; ++p) {
+    for (int p = 1 + lane; p < nparts; p += 32) {
         const T o = partial[p * 2 * DIM + k];
-        v = (k & 1) ? ((v < o) ? o : v) : ((o < v) ? o : v);
+        v = is_max ? ((v < o) ? o : v) : ((o < v) ? o : v);
     }
-    out[k] = v;     // layout: min_x, max_x, min_y, max_y, ...
+#pragma unroll
+    for (int o_ = 16; o_ > 0; o_ >>= 1) {
+        const T o = __shfl_xor_sync(0xffffffffu, v, o_);
+        v = is_max ? ((v < o) ? o : v) : ((o < v) ? o : v);
+    }
+    if (lane == 0) out[k] = v;     // layout: min_x, max_x, min_y, max_y, ...
 }
 
 // ---------------------------------------------------------------------------
@@ -888,7 +896,7 @@ box_extents_own_kernel(int nboxes, int aligned, const T* __restrict__ box_center
         const bool huge = (e - s) > kExtHuge;
         if (huge && gl == 0) huge_list[atomicAdd(huge_count, 1)] = ibox;
         const bool big = !huge && (e - s) > (kExtGroup == 1 ? 8 : kExtBig);
-        if (!big) {
+        if (!big && !huge) {        // (a huge box is box_extents_huge_kernel's: do not walk it here)
             for (int ip = s + gl; ip < e; ip += kExtGroup) {
                 const T rad = radii ? radii[ip] : (T)0;
 #pragma unroll
@@ -1093,7 +1101,7 @@ static int bbox_impl(const bt_particles* p, void* out, cudaStream_t s)
     BT_CHECK(bt::temp_alloc((void**)&partial, sizeof(T) * 2 * DIM * grid, s));
     bbox_partial_kernel<T, DIM><<<grid, 256, 0, s>>>(P, have_radii, partial);
     BT_LAUNCH_CHECK();
-    bbox_final_kernel<T, DIM><<<1, 32, 0, s>>>(partial, grid, (T*)out);
+    bbox_final_kernel<T, DIM><<<1, 32 * 2 * DIM, 0, s>>>(partial, grid, (T*)out);
     BT_LAUNCH_CHECK();
     BT_CHECK(cudaFreeAsync(partial, s));
     return BT_OK;

@@ -15,7 +15,8 @@ from .exchange import _local_ranges, exchange_particle_kinds, exchange_particles
 from .local_traversal import generate_local_travs
 from .local_tree import LocalTree, assemble_local_tree, box_to_user_rank, generate_local_tree
 from .partition import (BoxMasks, get_box_ids_dfs_order, get_box_masks, get_box_masks_sharded,
-                        partition_segments, partition_segments_device, partition_work)
+                        partition_segments, partition_segments_default_cost,
+                        partition_segments_device, partition_work)
 from .tree_build import DistributedTree, build_distributed_tree
 
 __all__ = [
@@ -194,11 +195,16 @@ def distributed_tree_setup(actx, dtree, traversal_builder, comm, cost_per_box=No
     sh = actx.stream_handle
     with torch.cuda.stream(actx.stream), torch.cuda.device(actx.device):
         mark("start")
-        if cost_per_box is None:
-            cost_per_box = (1.0 + dtree.box_source_counts_nonchild.double()
-                            + dtree.box_target_counts_nonchild.double())
         dfs_order = get_box_ids_dfs_order(actx, dtree)
-        segs = partition_segments_device(actx, cost_per_box, dfs_order, size)
+        segs = None
+        if cost_per_box is None:
+            # the default cost, 1 + own sources + own targets: cut positions from one scan
+            segs = partition_segments_default_cost(actx, dtree, dfs_order, size)
+        if segs is None:
+            if cost_per_box is None:
+                cost_per_box = (1.0 + dtree.box_source_counts_nonchild.double()
+                                + dtree.box_target_counts_nonchild.double())
+            segs = partition_segments_device(actx, cost_per_box, dfs_order, size)
         if segs is None:
             cost_host = cost_per_box.cpu().numpy() if isinstance(cost_per_box, torch.Tensor) \
                 else np.asarray(cost_per_box)

@@ -98,6 +98,29 @@ def partition_segments_device(actx, cost_per_box, dfs_order, mpi_size):
     return segments
 
 
+def partition_segments_default_cost(actx, tree, dfs_order, mpi_size):
+    """:func:`partition_segments` for the default cost ``1 + own sources + own targets`` of a
+    box, on the device (``bt_dist_partition_cuts``: one scan of the costs gathered in depth-first
+    order, one binary search per cut, ONE readback).  Integer costs: the running sums are exact,
+    so the cuts are the reference's (``partition.py:81-116``) bit for bit."""
+    lib = _cabi.load()
+    nboxes = int(tree.nboxes)
+    cuts = actx.empty(mpi_size, np.int64)
+    check(lib.bt_dist_partition_cuts(nboxes, mpi_size, dptr(dfs_order),
+                                     dptr(tree.box_source_counts_nonchild),
+                                     dptr(tree.box_target_counts_nonchild), dptr(cuts),
+                                     actx.stream_handle), "bt_dist_partition_cuts")
+    hits = cuts.cpu().numpy()[:mpi_size - 1]
+    segments = np.empty((mpi_size, 2), dtype=np.int32)
+    start = 0
+    for k in range(mpi_size - 1):
+        i = min(max(int(hits[k]), start), nboxes - 1)
+        segments[k] = [start, i + 1]
+        start = i + 1
+    segments[mpi_size - 1] = [start, nboxes]
+    return segments
+
+
 def partition_work(actx, cost_per_box, traversal, comm):
     """``partition.py:60-121``.  *cost_per_box* (numpy) is only significant on the root rank.
     Returns the numpy array of boxes the calling rank is responsible for."""

@@ -476,6 +476,15 @@ int bt_dist_dfs_order(int dim, int nboxes, int aligned_nboxes, int nlevels,
                       const int32_t *level_start_box_nrs, const int32_t *box_child_ids,
                       int32_t *subtree_size, int32_t *rank_tmp, int32_t *dfs_order, void *stream);
 
+/* The cut positions of boxtree/distributed/partition.py:81-116 for the default cost
+ * 1 + own sources + own targets of a box: cuts[k-1], k = 1..nranks-1, is the first depth-first
+ * position whose running cost exceeds k * total / nranks (float64 expression of the reference;
+ * the integer running sums are exact); cuts[nranks-1] receives the total cost.
+ * cuts: int64[nranks], device. */
+int bt_dist_partition_cuts(int nboxes, int nranks, const int32_t *dfs_order,
+                           const int32_t *box_source_counts_nonchild,
+                           const int32_t *box_target_counts_nonchild, int64_t *cuts, void *stream);
+
 /* get_box_masks (distributed/partition.py:124-357) building blocks: int8 masks [nboxes] */
 int bt_dist_mask_from_list(int n, const int32_t *list, int8_t *mask, void *stream);
 int bt_dist_ancestor_mask(int nboxes, const int8_t *responsible, const int32_t *box_parent_ids,

@@ -180,3 +180,29 @@ def test_distributed_setup_with_cost_model_weights(actx):
                                                         level_orders=level_orders)
     assert int(lt.sources[0].shape[0]) == 20000 and int(lt.targets[0].shape[0]) == 20000
     assert not trav_mismatches(actx.to_numpy(gtrav), actx.to_numpy(ltrav))
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3, 5, 8, 64])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_default_cost_partition_cuts_on_device(actx, name, nranks):
+    """``bt_dist_partition_cuts`` (one scan + one binary search per cut) against the sequential
+    accumulation of ``partition.py:81-116`` on the default cost, and against the generic device
+    path."""
+    from boxtree_b200 import TreeBuilder
+    from boxtree_b200 import distributed as bd
+    from boxtree_b200.distributed.partition import (partition_segments,
+                                                    partition_segments_default_cost,
+                                                    partition_segments_device)
+    src, tkw, _ = CASES[name]()
+    dkw = {k: (actx.from_numpy(v) if isinstance(v, np.ndarray) else
+               [actx.from_numpy(x) for x in v] if k == "targets" else v) for k, v in tkw.items()}
+    tree, _ = TreeBuilder(actx)(actx, [actx.from_numpy(s) for s in src], **dkw)
+    order = bd.get_box_ids_dfs_order(actx, tree)
+    got = partition_segments_default_cost(actx, tree, order, nranks)
+    cost = (1.0 + tree.box_source_counts_nonchild.double()
+            + tree.box_target_counts_nonchild.double())
+    cost_host = cost.cpu().numpy()
+    want = partition_segments(cost_host[order.cpu().numpy()], nranks,
+                              total_workload=np.sum(cost_host))
+    assert np.array_equal(got, want)
+    assert np.array_equal(got, partition_segments_device(actx, cost, order, nranks))
