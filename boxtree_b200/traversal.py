@@ -511,25 +511,8 @@ class FMMTraversalBuilder:
                 check(lib.bt_trav_box_list(which, nboxes, dptr(box_flags), dptr(masks[which]),
                                            dptr(raw[which]), dptr(counts_dev[which:which + 1]),
                                            sh), "bt_trav_box_list")
-            counts = counts_dev.cpu().numpy()
-            source_parent_boxes = raw[0][:int(counts[0])]
-            source_boxes = raw[1][:int(counts[1])]
-            target_or_target_parent_boxes = raw[2][:int(counts[2])]
-            target_boxes = source_boxes if sources_are_targets else raw[3][:int(counts[3])]
-            ntb = int(target_boxes.shape[0])
-            ntp = int(target_or_target_parent_boxes.shape[0])
-
-            def level_starts(box_list):
-                out = actx.empty(nlevels + 1, np.int32)
-                check(lib.bt_trav_level_starts(nlevels, dptr(level_start_box_nrs),
-                                               dptr(box_list), int(box_list.shape[0]),
-                                               dptr(out), sh), "bt_trav_level_starts")
-                return out
-
-            lss = level_starts(source_boxes)
-            lssp = level_starts(source_parent_boxes)
-            lst = lss if sources_are_targets else level_starts(target_boxes)
-            lstp = level_starts(target_or_target_parent_boxes)
+            # (their sizes are read back together with the colleague total below: one
+            # synchronisation for both)
 
             # }}}
 
@@ -601,13 +584,40 @@ class FMMTraversalBuilder:
                                                  None, dptr(totals), sh), "colleagues")
             if not reuse_coll:
                 colleagues(0, None)
-                total = int(_read_i64(actx, totals)[0])
+                both = _read_i64(actx, torch.cat([totals[:1], counts_dev.to(torch.int64)]))
+                total, counts = int(both[0]), both[1:]
                 _check_int32(total, "same_level_non_well_sep_boxes")
                 coll_lists = actx.empty(total, np.int32)
                 colleagues(1, coll_lists)
                 if topdown:
                     del staging
+            else:
+                counts = counts_dev.cpu().numpy()
             coll = (coll_starts, coll_lists)
+
+            # {{{ b1/b2 continued: the box lists' sizes and level starts
+
+            source_parent_boxes = raw[0][:int(counts[0])]
+            source_boxes = raw[1][:int(counts[1])]
+            target_or_target_parent_boxes = raw[2][:int(counts[2])]
+            target_boxes = source_boxes if sources_are_targets else raw[3][:int(counts[3])]
+            ntb = int(target_boxes.shape[0])
+            ntp = int(target_or_target_parent_boxes.shape[0])
+
+            def level_starts(box_list):
+                out = actx.empty(nlevels + 1, np.int32)
+                check(lib.bt_trav_level_starts(nlevels, dptr(level_start_box_nrs),
+                                               dptr(box_list), int(box_list.shape[0]),
+                                               dptr(out), sh), "bt_trav_level_starts")
+                return out
+
+            lss = level_starts(source_boxes)
+            lssp = level_starts(source_parent_boxes)
+            lst = lss if sources_are_targets else level_starts(target_boxes)
+            lstp = level_starts(target_or_target_parent_boxes)
+
+            # }}}
+
             if _keep_shared:
                 self.last_shared = {
                     "child_t": child_t, "subtree_size": subtree_size, "dfs_rank": dfs_rank,

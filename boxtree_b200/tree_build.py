@@ -104,6 +104,9 @@ class _Pool:
         return p
 
 
+_LEVEL_START_WORDS = 128        # >= nlevels + 2 (trees end at level 31)
+
+
 class _Pending:
     """Work that a deferred build still owes (``_defer_extents``): ``finish()`` runs it once."""
 
@@ -450,8 +453,10 @@ class TreeBuilder:
                                              // max_leaf_refine_weight)) + 1
                 assert nboxes_guess > 0
                 pool = _Pool(actx, dimensions, coord_tdtype, max(int(nboxes_guess), 2), dist)
-                ctl = actx.zeros(CTL_SIZE, np.int32)
-                ctl_host = torch.empty(CTL_SIZE, dtype=torch.int32, pin_memory=True)
+                # control words, then the level starts of the final numbering (read back together)
+                ctl = actx.zeros(CTL_SIZE + _LEVEL_START_WORDS, np.int32)
+                ctl_host = torch.empty(CTL_SIZE + _LEVEL_START_WORDS, dtype=torch.int32,
+                                       pin_memory=True)
                 check(lib.bt_pool_init(dcode, dimensions, C.byref(pool.struct()), nsrcntgts, have_ext,
                                        dptr(keys), _cabi.darray(root_center), dptr(ctl), sh),
                       "bt_pool_init")
@@ -582,14 +587,15 @@ class TreeBuilder:
             prune_empty_leaves = not kwargs.get("skip_prune")
             map_old2new = actx.empty(nboxes, np.int32)
             src_of_new = actx.empty(nboxes, np.int32)
-            level_start_dev = actx.zeros(nlevels + 2, np.int32)
+            assert nlevels + 2 <= _LEVEL_START_WORDS
+            level_start_dev = ctl[CTL_SIZE:CTL_SIZE + nlevels + 2]
             check(lib.bt_finalize_numbering(dcode, dimensions, C.byref(pool.struct()), nboxes,
                                             int(level_restrict), int(not prune_empty_leaves),
                                             dptr(ctl), dptr(map_old2new), dptr(src_of_new),
                                             dptr(level_start_dev), sh), "bt_finalize_numbering")
             h = read_ctl()
             nfinal = int(h[CTL_NBOXES_FINAL])
-            level_start_box_nrs = level_start_dev.cpu().numpy()[:nlevels + 1].copy()
+            level_start_box_nrs = h[CTL_SIZE:CTL_SIZE + nlevels + 1].copy()
             level_start_box_nrs[nlevels] = nfinal
 
             aligned_nboxes = ((nfinal + 31) // 32) * 32
@@ -804,7 +810,9 @@ class TreeBuilder:
 
             # }}}
 
-            level_start_dev_out = actx.from_numpy(level_start_box_nrs.astype(np.int32))
+            # (assembled on the device: a host -> device copy of pageable memory would synchronise)
+            level_start_dev_out = ctl[CTL_SIZE:CTL_SIZE + nlevels + 1].clone()
+            level_start_dev_out[nlevels:] = ctl[CTL_NBOXES_FINAL:CTL_NBOXES_FINAL + 1]
             evt = torch.cuda.Event()
             evt.record(stream)
 
