@@ -234,9 +234,22 @@ class FMMTraversalInfo:
 
 
 def _read_i64(actx, dev: torch.Tensor) -> np.ndarray:
+    return _read_finish(*_read_start(actx, dev))
+
+
+def _read_start(actx, dev: torch.Tensor):
+    """Enqueue the device -> pinned-host copy of *dev* and an event behind it.  Work launched
+    between this and :func:`_read_finish` keeps the GPU busy while the host waits for the
+    numbers, digests them and prepares the launches that depend on them."""
     host = torch.empty(dev.shape, dtype=dev.dtype, pin_memory=True)
     host.copy_(dev, non_blocking=True)
-    actx.stream.synchronize()
+    ev = torch.cuda.Event()
+    ev.record(actx.stream)
+    return host, ev
+
+
+def _read_finish(host, ev) -> np.ndarray:
+    ev.synchronize()
     return host.numpy().copy()
 
 
@@ -675,9 +688,19 @@ class FMMTraversalBuilder:
             l4_starts = actx.empty(ntp + 1, np.int32)
             l4c_starts_raw = actx.empty(ntp + 1, np.int32) if with_extent else None
             a4 = list_args(target_or_target_parent_boxes, coll)
-            check(lib.bt_trav_build_list(dcode, 4, 0, C.byref(tv), C.byref(a4), ntp,
-                                         dptr(l4_starts), None, dptr(l4c_starts_raw), None,
-                                         dptr(totals[2:]), sh), "list 4 count")
+
+            def count_list4():
+                check(lib.bt_trav_build_list(dcode, 4, 0, C.byref(tv), C.byref(a4), ntp,
+                                             dptr(l4_starts), None, dptr(l4c_starts_raw), None,
+                                             dptr(totals[2:]), sh), "list 4 count")
+            # With the heavy-row maps the host reads the map sizes in the middle of the list-1+3
+            # count (count_list3): the list-4 count is launched right behind that copy, so the GPU
+            # works on it while the host allocates the maps.  (Not with deferred extents: there
+            # it belongs to the work that hides the reduction, before the first use of extents.)
+            l4_in_shadow = (fused13 and ws3.hrow_base is not None
+                            and not (_before_extents is not None and tree.targets_have_extent))
+            if not l4_in_shadow:
+                count_list4()
 
             a3 = bt_list3_args()
             a3.target_boxes = dptr(target_boxes)
@@ -705,15 +728,22 @@ class FMMTraversalBuilder:
             Cc = actx.empty(nslots * rowlen + 1, np.int32)
             summary = actx.zeros(2 * (nslots + 1) + 1, np.int64)
 
-            def count_list3():
+            early = {}
+
+            def count_list3(in_shadow=None):
                 if fused13:
                     check(lib.bt_trav_list13(dcode, 0, C.byref(tv), C.byref(a3), dptr(xflags), ntb,
                                              dptr(G), dptr(Cc), None, dptr(summary),
                                              C.byref(ws3.struct()), 0, 0, 0, sh), "list 1+3 count")
                     if ws3.hrow_base is not None:
                         # heavy rows by position map: size the maps, expand the rows once
-                        plan = _read_i64(actx, torch.cat([ws3.hctl[:1].to(torch.int64),
-                                                          ws3.hplan[:1]]))
+                        # (the list-2 total rides along: its fill can then be launched early)
+                        pending = _read_start(actx, torch.cat([
+                            ws3.hctl[:1].to(torch.int64), ws3.hplan[:1], totals[1:2]]))
+                        if in_shadow is not None:
+                            in_shadow()
+                        plan = _read_finish(*pending)
+                        early["l2_total"] = int(plan[2])
                         ws3.alloc_map(int(plan[0]), int(plan[1]), nslots)
                         check(lib.bt_trav_list13(dcode, 2, C.byref(tv), C.byref(a3), dptr(xflags),
                                                  ntb, dptr(G), dptr(Cc), None, dptr(summary),
@@ -723,16 +753,38 @@ class FMMTraversalBuilder:
                     check(lib.bt_trav_list3(dcode, 0, C.byref(tv), C.byref(a3), ntb, dptr(G),
                                             dptr(Cc), None, dptr(summary), C.byref(ws3.struct()),
                                             0, sh), "list 3 count")
-            count_list3()
+            count_list3(count_list4 if l4_in_shadow else None)
 
             zero1 = actx.zeros(1, np.int64)
             zero2 = actx.zeros(2, np.int64)
 
+            def fill_list2(total):
+                lists = actx.empty(total, np.int32)
+                if topdown:
+                    check(lib.bt_trav_list2_fill_masked(
+                        dimensions, ntp, dptr(target_or_target_parent_boxes), dptr(box_parent_ids),
+                        dptr(coll_starts), dptr(coll_lists), dptr(child_t), dptr(l2_masks),
+                        mask_words, dptr(l2_starts), dptr(lists), sh), "list 2 fill")
+                else:
+                    check(lib.bt_trav_build_list(dcode, 2, 1, C.byref(tv), C.byref(a2), ntp,
+                                                 dptr(l2_starts), dptr(lists), None, None, None,
+                                                 sh), "list 2 fill")
+                return lists
+
+            l2_lists = None
+
             def read_counts():
-                both = _read_i64(actx, torch.cat([
+                nonlocal l2_lists
+                pending = _read_start(actx, torch.cat([
                     totals, summary, zero1 if fused13 else ws1.heavy_total, ws3.heavy_total,
                     zero2 if fused13 else ws1.hctl[:2].to(torch.int64),
                     ws3.hctl[:4].to(torch.int64)]))
+                # the list-2 fill needs none of these numbers: launched behind the copy, it keeps
+                # the GPU busy while the host digests the totals and sets up the other fills
+                if l2_lists is None and "l2_total" in early:
+                    _check_int32(early["l2_total"], "from_sep_siblings")
+                    l2_lists = fill_list2(early["l2_total"])
+                both = _read_finish(*pending)
                 ns = summary.shape[0]
                 return both[:8], both[8:8 + ns], both[8 + ns:]
 
@@ -777,18 +829,11 @@ class FMMTraversalBuilder:
                                         dptr(l1_starts), dptr(l1_lists), None,
                                         C.byref(ws1.struct()), heavy1_total, sh), "list 1 fill")
             del ws1
-            l2_lists = actx.empty(int(tot[1]), np.int32)
-            if topdown:
-                check(lib.bt_trav_list2_fill_masked(
-                    dimensions, ntp, dptr(target_or_target_parent_boxes), dptr(box_parent_ids),
-                    dptr(coll_starts), dptr(coll_lists), dptr(child_t), dptr(l2_masks), mask_words,
-                    dptr(l2_starts), dptr(l2_lists), sh), "list 2 fill")
-                if not _keep_shared:
-                    del l2_masks
-            else:
-                check(lib.bt_trav_build_list(dcode, 2, 1, C.byref(tv), C.byref(a2), ntp,
-                                             dptr(l2_starts), dptr(l2_lists), None, None, None, sh),
-                      "list 2 fill")
+            if l2_lists is None:
+                l2_lists = fill_list2(int(tot[1]))
+            assert int(l2_lists.shape[0]) == int(tot[1])
+            if topdown and not _keep_shared:
+                del l2_masks
             l4_lists = actx.empty(int(tot[2]), np.int32)
             l4c_lists_raw = actx.empty(int(tot[3]), np.int32) if with_extent else None
             check(lib.bt_trav_build_list(dcode, 4, 1, C.byref(tv), C.byref(a4), ntp,
