@@ -145,7 +145,8 @@ template <typename T> struct BBox { T mn[3]; T mx[3]; };
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256)
 make_keys_kernel(Particles<T, DIM> P, BBox<T> bb, int extent_norm, T stick_out_factor, int D, int Dh,
-                 int points_never_stop, unsigned long long* __restrict__ keys,
+                 int points_never_stop, double so_minext, double skip_slack,
+                 unsigned long long* __restrict__ keys,
                  unsigned long long* __restrict__ keys_lo, T* __restrict__ records)
 {
     // D levels in total; `keys` resolves the first Dh of them, `keys_lo` (two-word keys, only for
@@ -192,7 +193,17 @@ make_keys_kernel(Particles<T, DIM> P, BBox<T> bb, int extent_norm, T stick_out_f
         // that dwarfs the rounding errors of the tests below (make_keys_impl decides) none of them
         // can fire for it, so the level loop is skipped with the identical result.
         if (extent_norm && !(points_never_stop && radius == (T)0)) {
-            for (int lev = 0; lev < D; ++lev) {    // lev = level of the box the particle sits in
+            // The same argument with the radius in it: at loop level lev the tests compare against
+            // the box inflated by stick_out * min_ext * 2^-(2+lev); while that exceeds
+            // radius + (the rounding bound, skip_slack = 64 eps M) none of them can fire, so the
+            // walk starts at the first level where one could (a target of radius 2^-10 in a
+            // 13-level key is tested on 4 levels instead of 13).  so_minext = 0 switches it off.
+            int lev0 = 0;
+            if (so_minext > 0) {
+                const double R = so_minext / ((double)radius + skip_slack);
+                if (R > 8.0) { const int l = ilogb(R) - 2; lev0 = l < D ? l : D; }
+            }
+            for (int lev = lev0; lev < D; ++lev) {    // lev = level of the box the particle sits in
                 const T size_factor = ((T)1) / ((T)(1u << (1 + lev)));
                 bool st = false;
                 T center[DIM];
@@ -1123,6 +1134,7 @@ static int make_keys_impl(const bt_particles* p, const double* bmin, const doubl
     // a factor (1 + O(eps))).  Skipping is exact while that margin, at the finest level D, exceeds
     // the error bound; the check asks for 64 eps M, 8x the bound.  fp32 builds seldom qualify.
     int points_never_stop = 0;
+    double so_minext = 0, skip_slack = 0;
     if (extent_norm && stick_out > 0 && !(getenv("BT_KEYS_NO_SKIP"))) {
         double min_ext = 1e300, M = 0;
         for (int a = 0; a < DIM; ++a) {
@@ -1133,10 +1145,11 @@ static int make_keys_impl(const bt_particles* p, const double* bmin, const doubl
         const double eps = sizeof(T) == 8 ? 2.220446049250313e-16 : 1.1920928955078125e-07;
         const double margin = (double)(T)stick_out * min_ext / (double)(1ull << (D + 1));
         points_never_stop = (min_ext > 0 && margin > 64.0 * eps * M) ? 1 : 0;
+        if (min_ext > 0) { so_minext = (double)(T)stick_out * min_ext; skip_slack = 64.0 * eps * M; }
     }
     make_keys_kernel<T, DIM><<<grid_for(P.n, 256, 8), 256, 0, s>>>(P, bb, extent_norm, (T)stick_out, D, Dh,
-                                                                  points_never_stop, keys, keys_lo,
-                                                                  (T*)records);
+                                                                  points_never_stop, so_minext, skip_slack,
+                                                                  keys, keys_lo, (T*)records);
     BT_LAUNCH_CHECK();
     return BT_OK;
 }

@@ -163,7 +163,7 @@ def exchange_particle_kinds(actx, comm, dtree, masks_all_ranks, kinds, pre):
     xs = [_Exchange(actx, comm, dtree, masks_all_ranks, bitsel, my_mask, kind, pre, ranges)
           for bitsel, my_mask, kind, ranges in kinds]
     offs = torch.stack([x.count() for x in xs])                          # [kinds, nranks + 2]
-    gathered = comm.allgather_tensor(offs).cpu().numpy()                 # [sender, kinds, ...]
+    gathered = actx.read_back(comm.allgather_tensor(offs))               # [sender, kinds, ...]
     for k, x in enumerate(xs):
         x.send(gathered[:, k])
     return [x.unpack() for x in xs]

@@ -84,7 +84,7 @@ def partition_segments_device(actx, cost_per_box, dfs_order, mpi_size):
     # device as on the host) and ONE readback: [qualifies, cut positions...]
     ks = torch.arange(1, mpi_size, dtype=torch.float64, device=cum.device)
     hits = torch.searchsorted(cum, ks * total / mpi_size, right=True)
-    packed = torch.cat([ok.to(torch.int64).view(1), hits.to(torch.int64)]).cpu().numpy()
+    packed = actx.read_back(torch.cat([ok.to(torch.int64).view(1), hits.to(torch.int64)]))
     if not packed[0]:
         return None
     hits = packed[1:]
@@ -110,7 +110,7 @@ def partition_segments_default_cost(actx, tree, dfs_order, mpi_size):
                                      dptr(tree.box_source_counts_nonchild),
                                      dptr(tree.box_target_counts_nonchild), dptr(cuts),
                                      actx.stream_handle), "bt_dist_partition_cuts")
-    hits = cuts.cpu().numpy()[:mpi_size - 1]
+    hits = actx.read_back(cuts)[:mpi_size - 1]
     segments = np.empty((mpi_size, 2), dtype=np.int32)
     start = 0
     for k in range(mpi_size - 1):

@@ -337,9 +337,12 @@ class TreeBuilder:
             if dist:
                 # ONE small all-gather + readback: every rank's particle counts and bounding box
                 # (as float64, exact for either coordinate type); min / max / sums on the host
-                mine = torch.cat([torch.tensor([nsources, ntargets], dtype=torch.float64,
-                                               device=actx.device), bbox_dev.to(torch.float64)])
-                allv = comm.allgather_tensor(mine).cpu().numpy()            # [size, 2 + 2 dim]
+                # (counts through pinned memory, result back through pinned memory: no staging)
+                cnt_host = torch.tensor([nsources, ntargets], dtype=torch.float64).pin_memory()
+                mine = torch.empty(2 + 2 * dimensions, dtype=torch.float64, device=actx.device)
+                mine[:2].copy_(cnt_host, non_blocking=True)
+                mine[2:] = bbox_dev
+                allv = actx.read_back(comm.allgather_tensor(mine))          # [size, 2 + 2 dim]
                 nsources_global, ntargets_global = (int(x) for x in allv[:, :2].sum(axis=0))
                 nsrcntgts_global = total_refine_weight = nsources_global + ntargets_global
                 if nsrcntgts_global >= 2**31 - 1:

@@ -105,3 +105,53 @@ def test_the_condition_is_not_vacuous():
     stop = stop_levels(pos, np.zeros(len(pos), np.float32), gmin, gext, 0.0, "linf", 19,
                        np.float32)
     assert np.count_nonzero(stop != STOP_NEVER) > 0
+
+
+def first_tested_level(radius, gmin, gext, sof, D, dtype):
+    """Mirror of ``make_keys_kernel``'s ``lev0``: the loop level the walk starts at for a particle
+    of the given radius (``make_keys_impl``: so_minext, skip_slack)."""
+    eps = float(np.finfo(dtype).eps)
+    gmax = gmin + gext
+    M = float(max(np.max(np.abs(gmin)), np.max(np.abs(gmax)), np.max(gext)))
+    min_ext = float(np.min(gext))
+    if not (sof > 0 and min_ext > 0):
+        return np.zeros(len(radius), np.int64)
+    so_minext = float(dtype(sof)) * min_ext
+    slack = 64.0 * eps * M
+    with np.errstate(divide="ignore"):
+        R = so_minext / (radius.astype(np.float64) + slack)
+    lev0 = np.zeros(len(radius), np.int64)
+    big = R > 8.0
+    # ilogb(R) - 2, capped at D (ilogb(inf) is INT_MAX)
+    e = np.where(np.isfinite(R[big]), np.floor(np.log2(np.where(np.isfinite(R[big]), R[big], 1.0))), 1e9)
+    lev0[big] = np.minimum(e - 2, D).astype(np.int64)
+    return lev0
+
+
+@pytest.mark.parametrize("norm", ["linf", "l2"])
+@pytest.mark.parametrize("dtype,d,D", [(np.float64, 3, 19), (np.float64, 2, 28),
+                                       (np.float32, 3, 19), (np.float64, 1, 31)])
+@pytest.mark.parametrize("offset", [0.0, -3.5, 1e3, 1e9])
+@pytest.mark.parametrize("sof", [0.25, 0.01, 1.0])
+def test_no_stop_test_fires_below_the_first_tested_level(norm, dtype, d, D, offset, sof):
+    """The radius-aware skip of ``make_keys_kernel``: the full level loop never stops a particle
+    at a level below ``lev0``, so starting the loop there gives the same stop level.  Radii sit
+    on and around the per-level thresholds ``sof * extent / 2^(2+lev)`` (times 1/8 ... 8) and
+    positions on and around box faces of every level."""
+    rng = np.random.default_rng(hash((norm, d, D, offset, sof, "r")) % 2 ** 32)
+    ext = dtype(1.000100001 * 7.3)
+    gmin = np.full(d, dtype(offset), dtype) + (rng.random(d) * 0.1).astype(dtype)
+    gext = (gmin + ext) - gmin
+    if not np.all(gext > 0):
+        pytest.skip("degenerate box at this offset")
+    pos = adversarial_points(gmin, gext, D, dtype, rng, d)
+    n = len(pos)
+    lev = rng.integers(0, D, n)
+    thr = float(dtype(sof)) * float(np.min(gext)) / np.exp2(2.0 + lev)
+    radius = (thr * np.exp2(rng.integers(-3, 4, n)) * (1 + rng.integers(-2, 3, n) * 1e-15)).astype(dtype)
+    radius[rng.random(n) < 0.05] = 0
+    stop = stop_levels(pos, radius, gmin, gext, sof, norm, D, dtype)
+    lev0 = first_tested_level(radius, gmin, gext, sof, D, dtype)
+    assert np.all(stop >= lev0), int(np.count_nonzero(stop < lev0))
+    # the skip is not vacuous: many particles start beyond level 0, and some stop right at lev0 + k
+    assert np.count_nonzero(lev0 > 0) > n // 4
