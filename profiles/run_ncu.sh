@@ -4,13 +4,14 @@
 #   spec: tests/perf_probe.py workload spec, e.g. config3:10000000 or uniform:10000000:f64
 set -u
 TAG=${1:-r01}; SPEC=${2:-config3:10000000}
-REGEX=${3:-'list13_coop|coll_topdown|list2_warp|rs_onesweep|box_extents|permute_kernel|make_keys'}
-COUNT=${4:-60}
+REGEX=${3:-'list13_coop|coll_topdown|coll_compact|list2_masked|list13_unstage|heavy_map|list_kernel|rs_onesweep|box_extents_own|permute_kernel|make_keys|leaf_fixup_kernel|level_restrict'}
+COUNT=${4:-120}
 NAME=$(echo "$SPEC" | tr ':' '_')
 mkdir -p gpurun_out
 # (1) every launch of ONE warm step (tests/ncu_driver.py brackets it with cudaProfilerStart/Stop)
 #     with its device time; serialised: compare SHARES with the bench's live numbers
-ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+#     (+ sm__cycles_active avg / max: an SM busy far longer than the average is a tail to fix)
+ncu --profile-from-start off --metrics gpu__time_duration.sum,sm__cycles_active.avg,sm__cycles_active.max,sm__cycles_elapsed.max --clock-control none --csv \
     --log-file gpurun_out/launches_${TAG}_${NAME}.csv \
     python tests/ncu_driver.py $SPEC > gpurun_out/ncu_launches_${TAG}.log 2>&1
 # (2) full metric set of the top kernels of the same warm step

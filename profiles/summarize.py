@@ -17,26 +17,35 @@ idx = {h: i for i, h in enumerate(hdr)}
 agg = collections.OrderedDict()
 tot = 0.0
 n = 0
-for row in r:
-    if len(row) < len(hdr):
-        continue
+imb = {}                 # launch id -> {metric: value} for the SM-balance columns
+all_rows = [row for row in r if len(row) >= len(hdr)]
+for row in all_rows:
+    if row[idx["Metric Name"]] != "gpu__time_duration.sum":
+        imb.setdefault(row[idx["ID"]], {})[row[idx["Metric Name"]]] = float(row[idx["Metric Value"]].replace(",", ""))
+for row in all_rows:
     name = row[idx["Kernel Name"]]
+    if row[idx["Metric Name"]] != "gpu__time_duration.sum":
+        continue
     val = float(row[idx["Metric Value"]].replace(",", ""))
     unit = row[idx["Metric Unit"]]
     val *= {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}.get(unit, 1.0)
     short = re.sub(r"\(.*", "", re.sub(r"<.*", "", name)).replace("bt::", "").replace("void ", "")
-    a = agg.setdefault(short, [0, 0.0])
+    a = agg.setdefault(short, [0, 0.0, 0.0])
     a[0] += 1
     a[1] += val
+    m = imb.get(row[idx["ID"]], {})
+    if m.get("sm__cycles_elapsed.max"):
+        # time the average SM was NOT busy while the kernel ran (tail / under-filled grid)
+        a[2] += val * (1.0 - m.get("sm__cycles_active.avg", 0.0) / m["sm__cycles_elapsed.max"])
     tot += val
     n += 1
 with open(f"profiles/{tag}_launches_{wl}.txt", "w") as f:
     f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none (profiles/run_ncu.sh {tag} {wl})\n")
     f.write(f"# {n} launches captured (one warm step), serialised: compare SHARES, not absolutes\n")
     f.write(f"# total {tot / 1e6:.3f} ms\n")
-    f.write(f"{'kernel':42s} {'launches':>8s} {'total ms':>10s} {'share':>7s}\n")
-    for k, (c, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        f.write(f"{k:42s} {c:8d} {v / 1e6:10.3f} {100 * v / tot:6.1f}%\n")
+    f.write(f"{'kernel':42s} {'launches':>8s} {'total ms':>10s} {'share':>7s} {'avg SM idle ms':>15s}\n")
+    for k, (c, v, idle) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        f.write(f"{k:42s} {c:8d} {v / 1e6:10.3f} {100 * v / tot:6.1f}% {idle / 1e6:15.3f}\n")
 
 import os
 raw_csv = f"gpurun_out/prof_{tag}_{wl}_raw.csv"
@@ -68,8 +77,14 @@ SCOPE_OF = [("list13_coop_kernel<double, 3, 0>", "l13_walk_count"), ("list13_coo
             ("coll_topdown_kernel", "trav_colleagues_count"), ("list2_masked_fill_kernel", "trav_list2_fill"),
             ("list13_unstage_kernel", "l13_unstage"), ("rs_onesweep_kernel<0, 1>", "l13_heavy_sort_pass"),
             ("rs_onesweep_kernel", "rs_onesweep_pass"), ("permute_kernel", "bt_permute"),
-            ("make_keys_kernel", "bt_make_keys"), ("box_extents_own_kernel", "bt_box_extents")]
-PER_CALL = {"trav_colleagues_count"}          # scopes whose one call launches the kernel once per level
+            ("make_keys_kernel", "bt_make_keys"), ("box_extents_own_kernel", "bt_box_extents"),
+            ("heavy_map_extract_kernel", "l13_heavy_extract"), ("heavy_map_step_kernel", "l13_heavy_expand"),
+            ("heavy_map_hist_kernel", "l13_heavy_expand"), ("heavy_map_rowscan_kernel", "l13_heavy_expand"),
+            ("heavy_map_plan_kernel", "l13_heavy_expand"), ("heavy_map_seed_kernel", "l13_heavy_expand"),
+            ("coll_compact", "trav_colleagues_fill"), ("list_kernel<double, 3, 4, 0>", "trav_list4_count"),
+            ("list_kernel<double, 3, 4, 1>", "trav_list4_fill")]
+# scopes whose one call launches several kernels (per level / per step): bytes per CALL
+PER_CALL = {"trav_colleagues_count", "l13_heavy_expand"}
 ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
 mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 acc = {}
