@@ -616,8 +616,12 @@ class TreeBuilder:
             box_srcntgt_counts_nonchild = actx.empty(nfinal, np.int32)
             box_levels = actx.empty(nfinal, np.uint8)
             box_parent_ids = actx.empty(nfinal, np.int32)
-            box_child_ids = actx.zeros((nb, aligned_nboxes), np.int32)
-            box_centers = actx.zeros((dimensions, aligned_nboxes), coord_dtype)
+            # (bt_gather_boxes writes every entry of the nfinal boxes: only the padding up to
+            # aligned_nboxes is cleared, not 0.7 GB of box arrays of a 12 M-box global tree)
+            box_child_ids = actx.empty((nb, aligned_nboxes), np.int32)
+            box_centers = actx.empty((dimensions, aligned_nboxes), coord_dtype)
+            box_child_ids[:, nfinal:].zero_()
+            box_centers[:, nfinal:].zero_()
             box_has_children = actx.empty(nfinal, np.uint8)
             box_real_children = actx.empty(nfinal, np.uint8)
             out = bt_box_out()
@@ -766,8 +770,11 @@ class TreeBuilder:
             # source and target boxes side by side: the distributed build all-reduces all minima
             # (and all maxima) in one collective
             nsets = 1 if sources_are_targets else 2
-            bb_min_all = actx.zeros((nsets, dimensions, aligned_nboxes), coord_dtype)
-            bb_max_all = actx.zeros((nsets, dimensions, aligned_nboxes), coord_dtype)
+            # (every box's entry is written by the own-particle pass, seeded with the centre)
+            bb_min_all = actx.empty((nsets, dimensions, aligned_nboxes), coord_dtype)
+            bb_max_all = actx.empty((nsets, dimensions, aligned_nboxes), coord_dtype)
+            bb_min_all[:, :, nfinal:].zero_()
+            bb_max_all[:, :, nfinal:].zero_()
             bb_src_min, bb_src_max = bb_min_all[0], bb_max_all[0]
             bb_tgt_min, bb_tgt_max = (bb_src_min, bb_src_max) if sources_are_targets else \
                 (bb_min_all[1], bb_max_all[1])
