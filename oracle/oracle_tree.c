@@ -158,6 +158,21 @@ static int morton_nr_of_particle(
     return mnr;
 }
 
+/* Test helper: the Morton number (or -1 = "stops here") scan_t_from_particle computes for every
+ * particle sitting in a box of level particle_level -- the per-level digit the reference's
+ * morton_count_scan bins by (tree_build_kernels.py:308-470).  tests/test_gpu_morton_keys.py
+ * holds the digits packed into the CUDA path's sort keys to these. */
+void orc_particle_morton_nrs(int d, int extent_norm, int particle_level, int64_t n,
+                             const coord_t *bbox_min, const coord_t *bbox_max,
+                             const coord_t *const *coords, const coord_t *radii,
+                             coord_t stick_out_factor, morton_nr_t *out)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i)
+        out[i] = (morton_nr_t)morton_nr_of_particle(d, extent_norm, particle_level, bbox_min, bbox_max,
+                                                    (particle_id_t)i, coords, radii, stick_out_factor);
+}
+
 /* morton_count_scan: segmented inclusive scan + output statement
  * tree_build_kernels.py:247-508, 1555-1572; called from tree_build.py:732 */
 void orc_morton_count_scan(
