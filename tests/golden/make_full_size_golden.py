@@ -39,7 +39,13 @@ def full_size_cases():
     def config2():
         return uniform_particles(1_000_000, 3, np.float64), dict(max_particles_in_box=30), {}
 
-    return {"config2_3d_1e6": config2, "config3_3d_1e7": config3, "uniform_3d_1e7_f64": uniform}
+    def plummer():
+        # BASELINE config 4's recipe (bench.py "config4": Plummer sphere, fp32) at 1e7 points
+        from tests.parity_util import plummer_particles
+        return plummer_particles(10_000_000, np.float32, seed=15), dict(max_particles_in_box=30), {}
+
+    return {"config2_3d_1e6": config2, "config3_3d_1e7": config3, "uniform_3d_1e7_f64": uniform,
+            "plummer_3d_1e7_f32": plummer}
 
 
 def main():
