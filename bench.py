@@ -699,12 +699,12 @@ def run_reference(args):
     recipe, n, dtype, desc = WORKLOADS[args.workload]
     if args.n:
         n = args.n
-    # the FULL workload per step when the whole run then stays within ~4 minutes (measured:
+    # the FULL workload per step when the whole run then stays within ~3 minutes (measured:
     # 0.53 s per 1e6 points of config 3 on 16 cores -- 20 steps of 1e7 points: under 2 minutes),
     # otherwise the largest sample of the same recipe that does (at least CPU_SAMPLE_POINTS)
     nsteps = args.steps + min(args.warmup, 1)
     per_mpoint = 0.53 * 16.0 / max(os.cpu_count() or 1, 1)
-    fit = int(240.0 / (max(nsteps, 1) * per_mpoint) * 1e6)
+    fit = int(180.0 / (max(nsteps, 1) * per_mpoint) * 1e6)
     sample_n = n if (n <= CPU_BASELINE_POINTS and n <= fit) else min(n, max(CPU_SAMPLE_POINTS, min(fit, n)))
     v, dt = time_oracle(recipe, sample_n, dtype, steps=args.steps, warmup=min(args.warmup, 1))
     line = {
