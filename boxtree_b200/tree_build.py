@@ -15,6 +15,7 @@ per level.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Any
 
 import numpy as np
@@ -792,22 +793,29 @@ class TreeBuilder:
             ls_host = (C.c_int32 * (nlevels + 1))(*[int(x) for x in level_start_box_nrs])
             # distributed: min/max over the rank's own particles, all-reduced (exact), then the
             # child merge on the global values
-            # (a rank's share of a box is a particle or two: one lane per box, flag 4)
-            sparse = 0      # (measured slower than 8 lanes per box on 12M boxes at 8 ranks)
+            # A rank's share of a box of a big global tree is a particle or two: then ONE lane per
+            # box (flag 4) instead of 8 -- 0.68 -> 0.17 ms for 7.5e6 particles in 8.2e6 boxes, 0.17
+            # -> 0.05 ms in 1.8e6 boxes (tests/extents_sparse_probe.py; same bits).  Decided per
+            # particle kind by the rank's particles per box; BT_EXTENTS_SPARSE_BELOW overrides the
+            # threshold (tests force either variant).
+            sparse_below = float(os.environ.get("BT_EXTENTS_SPARSE_BELOW", 3.0))
 
             def extents_phase(phases):
                 for parts, radii, pstarts, pcounts, bmin, bmax in rounds:
+                    ph = phases
+                    if dist and (phases & 1) and int(parts[0].shape[0]) < sparse_below * nfinal:
+                        ph |= 4
                     check(lib.bt_box_extents_phase(
                         dcode, dimensions, nfinal, aligned_nboxes, nlevels, ls_host,
                         dptr(box_child_ids), dptr(box_centers), dptr(pstarts), dptr(pcounts),
-                        _cabi.ptr_array(list(parts)), dptr(radii), dptr(bmin), dptr(bmax), phases,
+                        _cabi.ptr_array(list(parts)), dptr(radii), dptr(bmin), dptr(bmax), ph,
                         sh), "bt_box_extents")
 
             pending_extents = None
             if not dist:
                 extents_phase(3)
             elif not kwargs.get("_defer_extents"):
-                extents_phase(1 | sparse)
+                extents_phase(1)
                 comm.allreduce_(bb_min_all, "min")
                 comm.allreduce_(bb_max_all, "max")
                 extents_phase(2)
@@ -816,7 +824,7 @@ class TreeBuilder:
                 # they run on the backend's stream while this stream goes on with work that does
                 # not read the extents (work partition, colleagues, lists 2 and 4);
                 # `pending_extents.finish()` waits for them and merges the children's boxes
-                extents_phase(1 | sparse)
+                extents_phase(1)
                 waits = [comm.allreduce_async_(bb_min_all, "min"),
                          comm.allreduce_async_(bb_max_all, "max")]
 

@@ -45,6 +45,21 @@ def test_distributed_build_without_deferred_extents(actx, name):
         assert not bad, (r, bad[:10])
 
 
+@pytest.mark.parametrize("below", ["0", "1e30"])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_distributed_build_extents_variants(actx, monkeypatch, name, below):
+    """The own-particle pass of the box extents has a one-lane-per-box variant for ranks that hold
+    only a particle or two of each box (chosen by density, ``BT_EXTENTS_SPARSE_BELOW``): both
+    variants, forced, give the reference's arrays."""
+    monkeypatch.setenv("BT_EXTENTS_SPARSE_BELOW", below)
+    src, tkw, vkw = CASES[name]()
+    rtree, want = oracle_ranks(src, tkw, vkw, 3)
+    outs = run_threads(3, lambda comm: run_rank(actx, comm, src, tkw, vkw))
+    for r in range(3):
+        bad = check_rank(actx, r, 3, outs[r], rtree, want[r])
+        assert not bad, (r, bad[:10])
+
+
 @pytest.mark.parametrize("kind", ["adaptive", "non-adaptive", "adaptive-level-restricted"])
 @pytest.mark.parametrize("dims", [1, 2, 3])
 def test_distributed_build_kinds(actx, kind, dims):
