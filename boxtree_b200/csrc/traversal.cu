@@ -428,25 +428,18 @@ coll_topdown_kernel(TreeView<T, DIM> t, const int* __restrict__ level_start, int
         const int bch = (lane < NB) ? t.child(p, lane) : 0;
         const unsigned chm = __ballot_sync(0xffffffffu, bch != 0) & nbmask;
         if (!chm) continue;
+        // row wanted (not masked out)?  With a row mask (distributed setup: 7 of 8 parents on 8
+        // ranks) a parent none of whose children's rows are wanted costs two loads: the empty
+        // counts and the flags the walks read of ANY box are coll_init_kernel's
+        const bool brow = bch && !(row_mask && !row_mask[bch]);
+        const unsigned rowm = __ballot_sync(0xffffffffu, brow) & nbmask;
+        if (!rowm) continue;
         unsigned char bxf = 0;
-        bool brow = false;                         // row wanted (not masked out)
         if (bch) {
             bool hc = false;
 #pragma unroll
             for (int m = 0; m < NB; ++m) hc = hc || (t.child(bch, m) != 0);
             bxf = (unsigned char)((hc ? kXfHasChild : 0) | ((t.flags[bch] & BT_BOX_IS_SOURCE_BOX) ? kXfCollSource : 0));
-            brow = !(row_mask && !row_mask[bch]);
-        }
-        const unsigned rowm = __ballot_sync(0xffffffffu, brow) & nbmask;
-        if (!rowm) {        // no child's row is wanted: only the flags the walks read of ANY box
-            if (bch) {
-                counts[bch] = 0;
-                if (l2cnt) l2cnt[bch] = 0;
-                xflags[bch] = bxf;
-            }
-            continue;
-        }
-        if (bch) {
 #pragma unroll
             for (int a = 0; a < DIM; ++a) bcen[lane][a] = t.centers[t.aligned * a + bch];
         }
@@ -537,6 +530,26 @@ coll_topdown_kernel(TreeView<T, DIM> t, const int* __restrict__ level_start, int
     }
 }
 
+// With a row mask: empty rows and the structural flags (has a child; is a source box) of EVERY box
+// in one streaming pass, so that the per-level kernel can leave a parent whose children are all
+// masked out after testing the mask.  Rows that are wanted overwrite their entries.
+template <typename T, int DIM>
+__global__ void __launch_bounds__(256)
+coll_init_kernel(TreeView<T, DIM> t, int* __restrict__ counts, int* __restrict__ l2cnt,
+                 unsigned char* __restrict__ xflags)
+{
+    constexpr int NB = 1 << DIM;
+    const int stride = gridDim.x * blockDim.x;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < t.nboxes; b += stride) {
+        bool hc = false;
+#pragma unroll
+        for (int m = 0; m < NB; ++m) hc = hc || (t.child(b, m) != 0);
+        counts[b] = 0;
+        if (l2cnt) l2cnt[b] = 0;
+        xflags[b] = (unsigned char)((hc ? kXfHasChild : 0) | ((t.flags[b] & BT_BOX_IS_SOURCE_BOX) ? kXfCollSource : 0));
+    }
+}
+
 // staged rows -> CSR lists: one thread per staged slot (box, j): the reads of the staging area
 // and -- rows being consecutive in the lists -- the writes are contiguous across a warp; a slot
 // beyond its row's length (all of them for a row masked out) costs two cached loads of `starts`
@@ -622,6 +635,10 @@ static int colleagues_topdown_impl(int phase, const bt_tree_view* tv, const int*
     if (t.nboxes <= 0) return BT_OK;
     if (phase == 0) {
         const int grid = grid_for((int64_t)t.nboxes * 32, 256, 8);
+        if (row_mask) {
+            coll_init_kernel<T, DIM><<<grid_for(t.nboxes, 256, 8), 256, 0, s>>>(t, starts, l2cnt, xflags);
+            BT_LAUNCH_CHECK();
+        }
         for (int lev = 0; lev < t.nlevels; ++lev) {
             coll_topdown_kernel<T, DIM><<<grid, 256, 0, s>>>(t, level_start, lev, stride, tmp, starts, dfs_rank,
                                                              row_mask, l2cnt, xflags, l2mask, mask_words);
