@@ -227,3 +227,24 @@ def test_box_ranges_are_sums_of_rank_local_ranges(nranks):
             for k in range(int(own_cnt[r, b])):
                 # rank r's k-th own particle of box b really sits at that global position
                 assert local[r][lower[r, b] + k] == starts[b] + excl[r, b] + k
+
+
+def test_pending_work_runs_once():
+    """``build_distributed_tree(defer_extents=True)`` hands its unfinished work over as an object
+    whose ``finish()`` may be called from several places (the traversal's hook, the setup's
+    catch-all): it must run exactly once."""
+    from boxtree_b200.tree_build import _Pending
+    ran = []
+    p = _Pending(lambda: ran.append(1))
+    assert not p.done
+    p.finish()
+    p.finish()
+    assert ran == [1] and p.done
+
+
+def test_single_process_comm_async_handle():
+    from boxtree_b200.distributed.comm import SingleProcessComm
+    t = torch.arange(4, dtype=torch.float64)
+    h = SingleProcessComm().allreduce_async_(t, "max")
+    h.wait()
+    assert t.tolist() == [0.0, 1.0, 2.0, 3.0]
